@@ -1,0 +1,103 @@
+/* mus_oracle.h -- CPU ORACLE for the Musubi per-level LBM time step.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a plain-C restatement of the reference's
+ * CPU algorithm (AOS state, PULL streaming through the `neigh` position list,
+ * separate auxField sweep, per-element omega) used as the checker by tests/,
+ * __graft_entry__.smoke() and the cpu_baseline / --impl reference legs of
+ * bench.py.  Nothing under musubi_b200/ may include, link or call it.
+ *
+ * Parity status: PINNED for fluid/BGK/D3Q19 + IC + unit conversion + periodic
+ * connectivity by the reference's own golden
+ *   mus/examples/fluid/benchmark/gaussianPulse/reference/ (the .res files)
+ * (tests/test_oracle_golden.py) and by restated utest properties
+ * (optimised-vs-NoOpt, rest-state fixed point, M*Minv = I).  TRT D3Q19,
+ * BGK/TRT/MRT D3Q27, the boundary and interpolation routines are
+ * "parity unpinned by reference fixtures" (no reproducible golden exists
+ * without Seeder / a Fortran toolchain); they are pinned by analytic checks.
+ *
+ * Conventions follow the reference's default build (AOS + PULL,
+ * mus/source/header/lbm_macros.inc:70-110), all positions 1-based as in
+ * Fortran:
+ *   state position  IDX(dir,elem)   = (elem-1)*QQ + dir
+ *   neigh position  NGPOS(dir,elem) = (dir-1)*nSize + elem
+ *   aux position    (elem-1)*4 + {1:rho, 2:ux, 3:uy, 4:uz}
+ */
+#ifndef MUS_ORACLE_H
+#define MUS_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { ORA_BGK = 0, ORA_TRT = 1, ORA_MRT = 2 };
+
+/* relaxation parameters the kernels read besides omega(elem) */
+typedef struct {
+  double lambda;     /* TRT magic parameter, fluid%lambda (mus_fluid_module.f90:104) */
+  double omegaBulk;  /* fluid%omegaBulkLvl(level) (mus_fluid_module.f90:482-484)      */
+} ora_relax_t;
+
+/* ---- stencil tables (tem_stencil_module.fpp:91-168) -------------------- */
+const int *ora_cxDir(int QQ);      /* [QQ][3] */
+const int *ora_cxDirInv(int QQ);   /* [QQ], 1-based values */
+const double *ora_weights(int QQ); /* mus_scheme_layout_module.f90:699-705 */
+
+/* ---- equilibrium + moments (mus_scheme_derived_quantities_type_module.f90) */
+void ora_pdfEq(int QQ, double rho, const double vel[3], double *fEq);
+void ora_pdfEq_incomp(int QQ, double rho, const double vel[3], double *fEq);
+
+/* mus_calcAuxField_fluid_d3q19/_d3q27 (mus_auxFieldVar_module.fpp:605-817) */
+void ora_calc_aux(int QQ, double *aux, const double *state, const int32_t *neigh,
+                  int nSize, int nSolve);
+void ora_calc_aux_incomp(int QQ, double *aux, const double *state,
+                         const int32_t *neigh, int nSize, int nSolve);
+
+/* mus_update_relaxParamKine (mus_relaxationParam_module.f90:276-280) */
+void ora_update_omega(double *omega, const double *visc, int nSolve);
+double ora_omega_bulk(double viscBulkLat); /* mus_fluid_module.f90:482-484 */
+
+/* ---- the compute kernels (scheme%compute pointees) ---------------------- */
+/* relax = ORA_BGK/TRT/MRT, QQ = 19/27; returns 0 or -1 for an unknown combo  */
+int ora_compute(int relax, int QQ, int incompressible, const double *in, double *out,
+                const double *aux, const int32_t *neigh, const double *omega,
+                int nSize, int nSolve, const ora_relax_t *rp);
+/* generic unoptimised kernels used by the reference's utests as the
+ * comparison partner (mus_compute_bgk_module.fpp:77-159,
+ * mus_compute_mrt_d3q19_module.fpp:999-1100, mus_compute_mrt_d3q27_module.fpp:88-185) */
+int ora_compute_noopt(int relax, int QQ, const double *in, double *out,
+                      const double *aux, const int32_t *neigh, const double *omega,
+                      int nSize, int nSolve, const ora_relax_t *rp);
+void ora_mrt_diag(int QQ, double omegaKine, double omegaBulk, double *s_mrt);
+
+/* ---- connectivity (mus_connectivity_module.fpp:73-179) ------------------ */
+/* nghElems: [nElems][QQN] (row per element, 1-based neighbour positions, <=0
+ * = missing / BC id); property: prp bits per element; offsets as levelDesc. */
+void ora_construct_connectivity(int32_t *neigh, int nSize, int nElems, int QQ,
+                                const int32_t *nghElems, const int64_t *property,
+                                int nFluid, int haloOffset /* offset(1,eT_halo) */);
+
+/* ---- boundary conditions (bc/mus_bc_fluid_module.fpp) ------------------- */
+void ora_fill_bcBuffer(double *bcBuffer, const double *state, int QQ,
+                       const int32_t *bcElems, int nBcElems);
+void ora_velocity_bounceback(double *state, const double *bcBuffer, int QQ,
+                             int nLinks, const int32_t *links, const int32_t *outPos,
+                             const int32_t *iDirLink, const int32_t *posInBuffer,
+                             const double *velLat /* [nLinks][3] lattice units */,
+                             int incompressible);
+/* mus_init_pdf with zero strain rate: state = fEq(rho, vel) */
+void ora_init_equilibrium(int QQ, int incompressible, int nElems, const double *rho,
+                          const double *vel, double *state);
+
+/* ---- halo exchange (tem_comm_module.fpp:549-646) ------------------------ */
+void ora_comm_gather(double *buf, const double *state, const int32_t *pos, int n);
+void ora_comm_scatter(double *state, const double *buf, const int32_t *pos, int n);
+
+/* ---- diagnostics -------------------------------------------------------- */
+double ora_total_mass(const double *state, int QQ, int nFluid);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

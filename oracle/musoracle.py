@@ -1,0 +1,471 @@
+"""musoracle.py -- CPU ORACLE driver (TEST INFRASTRUCTURE ONLY).
+
+numpy restatement of the host-side pieces of the reference that surround the
+per-level LBM time step, plus ctypes access to the C restatement of the
+kernels (oracle/*.c -> oracle/_build/libmusoracle.so).  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module; the product (musubi_b200/) never does.
+
+What is restated here (reference file:line):
+  * Morton treeIDs, periodic wrap      tem/source/tem_topology_module.f90:88-108, 528-638
+  * predefined cube + SFC partition    tem/source/treelmesh_module.f90:1224-1318 (:1276-1296)
+  * total list [fluid|gFC|gFF|halo]    tem/source/tem_construction_module.f90:2358-2460
+  * state connectivity                 mus/source/mus_connectivity_module.fpp:73-179 (C side)
+  * reduced halo link lists            mus/source/mus_construction_module.fpp:1162-1356
+  * boundary element / link lists      mus/source/mus_construction_module.fpp:2203-2376,
+                                       mus/source/bc/mus_bc_header_module.fpp:1702-1739, 1876-1967
+  * initial condition                  mus/source/mus_flow_module.fpp:484-589
+  * unit conversion                    mus/source/mus_physics_module.f90:511-580
+  * single-level schedule              mus/source/mus_control_module.f90:507-701
+All index lists are kept 1-based exactly as the Fortran arrays hold them.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+BGK, TRT, MRT = 0, 1, 2
+RELAX = {"bgk": BGK, "trt": TRT, "mrt": MRT}
+PRP_FLUID, PRP_SOLID, PRP_HASBND, PRP_SENDHALO = 1, 2, 3, 12
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int32)
+_lp = ctypes.POINTER(ctypes.c_int64)
+
+
+class _Relax(ctypes.Structure):
+    _fields_ = [("lambda_", ctypes.c_double), ("omegaBulk", ctypes.c_double)]
+
+
+def build(force=False):
+    """compile oracle/*.c with the committed Makefile (gcc, -ffp-contract=off)."""
+    so = os.path.join(_HERE, "_build", "libmusoracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(build())
+        _LIB.ora_omega_bulk.restype = ctypes.c_double
+        _LIB.ora_omega_bulk.argtypes = [ctypes.c_double]
+        _LIB.ora_total_mass.restype = ctypes.c_double
+        _LIB.ora_cxDir.restype = ctypes.POINTER(ctypes.c_int)
+        _LIB.ora_cxDirInv.restype = ctypes.POINTER(ctypes.c_int)
+        _LIB.ora_weights.restype = _dp
+    return _LIB
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+def _l(a):
+    return a.ctypes.data_as(_lp)
+
+
+# --------------------------------------------------------------------------
+# stencil tables
+# --------------------------------------------------------------------------
+def cx_dir(QQ):
+    p = lib().ora_cxDir(QQ)
+    return np.array([[p[3 * i + k] for k in range(3)] for i in range(QQ)], dtype=np.int64)
+
+
+def cx_dir_inv(QQ):
+    p = lib().ora_cxDirInv(QQ)
+    return np.array([p[i] for i in range(QQ)], dtype=np.int64)  # 1-based values
+
+
+def weights(QQ):
+    p = lib().ora_weights(QQ)
+    return np.array([p[i] for i in range(QQ)])
+
+
+# --------------------------------------------------------------------------
+# treelm topology
+# --------------------------------------------------------------------------
+def first_id_at_level(level):
+    return (8 ** level - 1) // 7
+
+
+def _spread3(v):
+    """insert two zero bits between the bits of v (21-bit input)."""
+    v = v.astype(np.uint64)
+    v = (v | (v << np.uint64(32))) & np.uint64(0x1F00000000FFFF)
+    v = (v | (v << np.uint64(16))) & np.uint64(0x1F0000FF0000FF)
+    v = (v | (v << np.uint64(8))) & np.uint64(0x100F00F00F00F00F)
+    v = (v | (v << np.uint64(4))) & np.uint64(0x10C30C30C30C30C3)
+    v = (v | (v << np.uint64(2))) & np.uint64(0x1249249249249249)
+    return v
+
+
+def _compact3(v):
+    v = v.astype(np.uint64) & np.uint64(0x1249249249249249)
+    v = (v | (v >> np.uint64(2))) & np.uint64(0x10C30C30C30C30C3)
+    v = (v | (v >> np.uint64(4))) & np.uint64(0x100F00F00F00F00F)
+    v = (v | (v >> np.uint64(8))) & np.uint64(0x1F0000FF0000FF)
+    v = (v | (v >> np.uint64(16))) & np.uint64(0x1F00000000FFFF)
+    v = (v | (v >> np.uint64(32))) & np.uint64(0x1FFFFF)
+    return v
+
+
+def morton_of_coord(x, y, z):
+    """x -> bit 0, y -> bit 1, z -> bit 2 of every octal digit (tem_IdOfCoord)."""
+    return (_spread3(np.asarray(x)) | (_spread3(np.asarray(y)) << np.uint64(1))
+            | (_spread3(np.asarray(z)) << np.uint64(2))).astype(np.int64)
+
+
+def coord_of_morton(m):
+    m = np.asarray(m).astype(np.uint64)
+    return (_compact3(m).astype(np.int64), _compact3(m >> np.uint64(1)).astype(np.int64),
+            _compact3(m >> np.uint64(2)).astype(np.int64))
+
+
+def id_of_coord(x, y, z, level):
+    n = 1 << level
+    return first_id_at_level(level) + morton_of_coord(np.mod(x + n, n), np.mod(y + n, n), np.mod(z + n, n))
+
+
+def coord_of_id(tid, level):
+    return coord_of_morton(np.asarray(tid) - first_id_at_level(level))
+
+
+def partition_ranges(nElems, nParts):
+    """contiguous equal shares; the first `remainder` parts get one more."""
+    share, rem = divmod(nElems, nParts)
+    first, out = 0, []
+    for p in range(nParts):
+        n = share + (1 if p < rem else 0)
+        out.append((first, first + n))
+        first += n
+    return out
+
+
+# --------------------------------------------------------------------------
+# level descriptor of a single-level box (periodic cube or walled cavity)
+# --------------------------------------------------------------------------
+class LevelDesc:
+    pass
+
+
+def box_boundary_id(xn, yn, zn, n, kind):
+    """BC id seen when looking from a fluid cell to position (xn,yn,zn).
+    kind 'periodic': no boundaries (treelm wraps at the universe cube).
+    kind 'cavity'  : id 2 ('lid', velocity_bounceback) where only the top plane
+                     z = n is crossed; id 1 ('wall') for every other exit.
+    The synthetic-mesh convention (Seeder would store these ids in bnd.lsb)."""
+    if kind == "periodic":
+        return np.zeros(xn.shape, dtype=np.int64)
+    out_xy = (xn < 0) | (xn >= n) | (yn < 0) | (yn >= n)
+    bid = np.zeros(xn.shape, dtype=np.int64)
+    bid[out_xy | (zn < 0)] = 1
+    bid[(~out_xy) & (zn >= n)] = 2
+    return bid
+
+
+def build_level_desc(level, QQ, kind="periodic", rank=0, nranks=1, comm_reduced=True,
+                     _with_send=True):
+    """total list, neighbour lists, connectivity, halo and BC lists of one rank."""
+    ld = LevelDesc()
+    n = 1 << level
+    nGlob = n ** 3
+    cx = cx_dir(QQ)
+    inv = cx_dir_inv(QQ)
+    QQN = QQ - 1
+    ranges = partition_ranges(nGlob, nranks)
+    lo, hi = ranges[rank]
+    nFluid = hi - lo
+    first = first_id_at_level(level)
+    mloc = np.arange(lo, hi, dtype=np.int64)
+    x, y, z = coord_of_morton(mloc)
+
+    # neighbour morton index per direction (or -bcid)
+    ngh_m = np.empty((nFluid, QQN), dtype=np.int64)
+    for d in range(QQN):
+        xn, yn, zn = x + cx[d, 0], y + cx[d, 1], z + cx[d, 2]
+        bid = box_boundary_id(xn, yn, zn, n, kind)
+        m = morton_of_coord(np.mod(xn, n), np.mod(yn, n), np.mod(zn, n))
+        ngh_m[:, d] = np.where(bid > 0, -bid, m)
+    remote = (ngh_m >= 0) & ((ngh_m < lo) | (ngh_m >= hi))
+    halo_m = np.unique(ngh_m[remote])
+    nHalo = halo_m.size
+    nElems = nFluid + nHalo
+    ld.level, ld.QQ, ld.kind = level, QQ, kind
+    ld.nFluid, ld.nGhostFromCoarser, ld.nGhostFromFiner, ld.nHalo = nFluid, 0, 0, nHalo
+    ld.nElems = nElems
+    ld.nSize = ((nElems + 3) // 4) * 4          # mus_pdf_module.f90:128-129
+    ld.nSolve = nFluid                          # nElems_fluid + nElems_ghostFromCoarser
+    ld.total = np.concatenate([first + mloc, first + halo_m]).astype(np.int64)
+
+    # nghElems(QQN, nElems): 1-based positions in the total list, <= 0 = none / -bcid
+    ngh = np.zeros((nElems, QQN), dtype=np.int32)
+    loc = (ngh_m >= lo) & (ngh_m < hi)
+    pos = np.where(loc, ngh_m - lo + 1, 0)
+    if nHalo:
+        hp = np.searchsorted(halo_m, np.where(remote, ngh_m, halo_m[0]))
+        pos = np.where(remote, nFluid + hp + 1, pos)
+    pos = np.where(ngh_m < 0, ngh_m, pos)
+    ngh[:nFluid] = pos
+    if nHalo:  # halos: neighbours that exist locally (fluid or halo), else 0
+        hx, hy, hz = coord_of_morton(halo_m)
+        for d in range(QQN):
+            xn, yn, zn = hx + cx[d, 0], hy + cx[d, 1], hz + cx[d, 2]
+            bid = box_boundary_id(xn, yn, zn, n, kind)
+            m = morton_of_coord(np.mod(xn, n), np.mod(yn, n), np.mod(zn, n))
+            isloc = (m >= lo) & (m < hi) & (bid == 0)
+            hp = np.searchsorted(halo_m, m)
+            hp_c = np.minimum(hp, nHalo - 1)
+            ishalo = (~isloc) & (bid == 0) & (halo_m[hp_c] == m)
+            p = np.where(isloc, m - lo + 1, np.where(ishalo, nFluid + hp_c + 1, 0))
+            ngh[nFluid:, d] = np.where(bid > 0, -bid, p)
+    ld.nghElems = ngh
+
+    prop = np.zeros(nElems, dtype=np.int64)
+    prop[:nFluid] |= (1 << PRP_FLUID)
+    hasbnd = (ngh[:nFluid] < 0).any(axis=1)
+    prop[:nFluid][hasbnd] |= (1 << PRP_HASBND)
+    ld.property = prop
+
+    ld.neigh = np.zeros(QQ * ld.nSize, dtype=np.int32)
+    lib().ora_construct_connectivity(_i(ld.neigh), ld.nSize, nElems, QQ, _i(ld.nghElems),
+                                     _l(ld.property), nFluid, nFluid)
+
+    # ---------------- halo exchange lists (reduced link set) ----------------
+    ld.recv, ld.send, ld.recv_masks = [], [], []
+    if nranks > 1:
+        owner = np.searchsorted(np.array([r[1] for r in ranges]), halo_m, side="right")
+        for p in range(nranks):
+            hsel = np.nonzero(owner == p)[0]
+            if hsel.size == 0:
+                continue
+            epos = nFluid + hsel + 1
+            posl, mask = _recv_positions(ld, epos, QQ, inv, nFluid, comm_reduced)
+            ld.recv.append(dict(proc=p, elemPos=epos.astype(np.int32), pos=posl))
+            ld.recv_masks.append(mask)
+        if _with_send:
+            # init_sendBuffers (mus_construction_module.fpp:1297-1356): the peer's halo
+            # list and link bitmask, replayed here instead of being sent over MPI.
+            for p in range(nranks):
+                if p == rank:
+                    continue
+                other = _peer_desc(level, QQ, kind, p, nranks, comm_reduced)
+                for r, m in zip(other.recv, other.recv_masks):
+                    if r["proc"] != rank:
+                        continue
+                    tids = other.total[r["elemPos"] - 1]
+                    epos = (tids - first - lo + 1).astype(np.int32)
+                    ei, di = np.nonzero(m)
+                    posl = ((epos[ei].astype(np.int64) - 1) * QQ + di + 1).astype(np.int32)
+                    ld.send.append(dict(proc=p, elemPos=epos, pos=posl))
+            sendmask = np.zeros(nElems, dtype=bool)
+            for snd in ld.send:
+                sendmask[snd["elemPos"] - 1] = True
+            ld.property[sendmask] |= (1 << PRP_SENDHALO)
+
+    # ---------------- boundary lists ----------------------------------------
+    ld.bc = []
+    if kind == "cavity":
+        ld.bc_elemBuffer = (np.nonzero(hasbnd)[0] + 1).astype(np.int32)   # levelDesc%bc_elemBuffer
+        posInBuf = np.zeros(nElems + 1, dtype=np.int32)
+        posInBuf[ld.bc_elemBuffer] = np.arange(1, ld.bc_elemBuffer.size + 1)
+        for bid, label, bkind in ((1, "wall", "wall"), (2, "lid", "velocity_bounceback")):
+            hit = (ngh[:nFluid] == -bid)                      # [elem][k]: boundary in direction k
+            elems = np.nonzero(hit.any(axis=1))[0] + 1
+            bitmask = np.zeros((elems.size, QQN), dtype=bool)
+            for k in range(QQN):                              # bitmask(cxDirInv(k)) = .true.
+                bitmask[:, inv[k] - 1] |= hit[elems - 1, k]
+            e_idx, d_idx = np.nonzero(bitmask)                # elem-major, dir ascending
+            el = elems[e_idx]
+            dirs = d_idx + 1
+            links = ld.neigh[(dirs - 1) * ld.nSize + el - 1]  # FETCH(iDir, elem)
+            pib = posInBuf[el]
+            outPos = inv[dirs - 1] + (pib.astype(np.int64) - 1) * QQ
+            ld.bc.append(dict(id=bid, label=label, kind=bkind, elems=elems.astype(np.int32),
+                              bitmask=bitmask, links=links.astype(np.int32),
+                              iDir=dirs.astype(np.int32), posInBuffer=pib.astype(np.int32),
+                              outPos=outPos.astype(np.int32), elemOfLink=el.astype(np.int32)))
+    else:
+        ld.bc_elemBuffer = np.zeros(0, dtype=np.int32)
+    return ld
+
+
+def _recv_positions(ld, epos, QQ, inv, halo_offset, comm_reduced):
+    """init_recvBuffers (mus_construction_module.fpp:1203-1261): elem-major, dir ascending;
+    link iDir of halo h is received when the element h pulls inv(iDir) from is local."""
+    e = epos.astype(np.int64)
+    keep = np.zeros((e.size, QQ), dtype=bool)
+    for d in range(1, QQ + 1):
+        neighDir = inv[d - 1]
+        nghElem = (ld.neigh[(neighDir - 1) * ld.nSize + e - 1].astype(np.int64) - 1) // QQ + 1
+        keep[:, d - 1] = (nghElem <= halo_offset) | (not comm_reduced)
+    ei, di = np.nonzero(keep)
+    return ((e[ei] - 1) * QQ + di + 1).astype(np.int32), keep
+
+
+_PEER_CACHE = {}
+
+
+def _peer_desc(level, QQ, kind, p, nranks, comm_reduced):
+    key = (level, QQ, kind, p, nranks, comm_reduced)
+    if key not in _PEER_CACHE:
+        _PEER_CACHE[key] = build_level_desc(level, QQ, kind, p, nranks, comm_reduced,
+                                            _with_send=False)
+    return _PEER_CACHE[key]
+
+
+# --------------------------------------------------------------------------
+# physics / unit conversion (mus_physics_module.f90:511-580)
+# --------------------------------------------------------------------------
+class Physics:
+    def __init__(self, dx, dt, rho0=1.0):
+        self.dx, self.dt, self.rho0 = dx, dt, rho0
+        self.fac_vel = dx / dt
+        self.fac_visc = dx ** 2 / dt
+        self.fac_press = rho0 * dx ** 2 / dt ** 2
+        self.fac_strainRate = 1.0 / dt
+
+
+def barycenters(ld, origin, length):
+    """tem_BaryOfId (tem_geometry_module.f90:419-435)."""
+    dx = length / float(1 << ld.level)
+    x, y, z = coord_of_id(ld.total, ld.level)
+    o = np.asarray(origin, dtype=np.float64)
+    return np.stack([o[0] + (x.astype(np.float64) + 0.5) * dx,
+                     o[1] + (y.astype(np.float64) + 0.5) * dx,
+                     o[2] + (z.astype(np.float64) + 0.5) * dx], axis=1)
+
+
+# --------------------------------------------------------------------------
+# the scheme: state arrays + one level step
+# --------------------------------------------------------------------------
+class Scheme:
+    """mus_scheme_type restricted to what the single-level step touches."""
+
+    def __init__(self, ld, relaxation="bgk", kind="fluid", omega=1.0, lambda_=0.25,
+                 omega_bulk=None):
+        if kind not in ("fluid", "fluid_incompressible"):
+            raise ValueError("scheme kind %r is outside the hot path" % kind)
+        self.ld = ld
+        self.QQ = ld.QQ
+        self.relax = RELAX[relaxation]
+        self.incomp = 1 if kind == "fluid_incompressible" else 0
+        n = ld.nSize * self.QQ
+        self.state = [np.full(n, -1.0e6), np.full(n, -1.0e6)]   # poison as in mus_construct :513
+        self.aux = np.full(ld.nSize * 4, -1.0e6)
+        self.nNow, self.nNext = 0, 1
+        self.visc = np.full(ld.nSize, (1.0 / omega - 0.5) / 3.0)
+        self.omega = np.full(ld.nSize, float(omega))
+        self.omega_uniform = float(omega)
+        self.rp = _Relax(lambda_, omega if omega_bulk is None else omega_bulk)
+        self.bc_vel = {}      # bc id -> [nLinks][3] lattice velocity per link
+        self.bcBuffer = np.zeros(max(1, ld.bc_elemBuffer.size) * self.QQ)
+        self.exchange = None  # callable(state) for multi-rank runs
+
+    # -- initial condition: f = fEq(rho, u) (+ fNeq(S) = 0), mus_init_pdf -----
+    def init_equilibrium(self, rho, vel):
+        ld, QQ = self.ld, self.QQ
+        rho = np.ascontiguousarray(np.broadcast_to(np.asarray(rho, dtype=np.float64), (ld.nElems,)))
+        vel = np.ascontiguousarray(np.broadcast_to(np.asarray(vel, dtype=np.float64), (ld.nElems, 3)))
+        st = self.state[self.nNext]
+        lib().ora_init_equilibrium(QQ, self.incomp, ld.nElems, _d(rho), _d(vel), _d(st))
+        self.state[self.nNow][:] = st            # mus_flow_module.fpp:181-185
+        self.calc_aux(self.state[self.nNext], local_only=True)
+
+    def calc_aux(self, state, local_only=False):
+        L = lib()
+        fn = L.ora_calc_aux_incomp if self.incomp else L.ora_calc_aux
+        if local_only:
+            # initial aux: moments of the element's own PDFs (mus_init_aux ... initAuxField)
+            ident = np.zeros(self.QQ * self.ld.nSize, dtype=np.int32)
+            e = np.arange(self.ld.nSize, dtype=np.int64)
+            for d in range(self.QQ):
+                ident[d * self.ld.nSize:(d + 1) * self.ld.nSize] = e * self.QQ + d + 1
+            fn(self.QQ, _d(self.aux), _d(state), _i(ident), self.ld.nSize, self.ld.nElems)
+        else:
+            fn(self.QQ, _d(self.aux), _d(state), _i(self.ld.neigh), self.ld.nSize, self.ld.nSolve)
+
+    def set_boundary(self):
+        ld, L = self.ld, lib()
+        if not ld.bc:
+            return
+        st = self.state[self.nNext]
+        L.ora_fill_bcBuffer(_d(self.bcBuffer), _d(st), self.QQ, _i(ld.bc_elemBuffer),
+                            int(ld.bc_elemBuffer.size))
+        for bc in ld.bc:
+            if bc["kind"] == "wall":
+                continue                        # do_nothing: bounce-back lives in neigh
+            if bc["kind"] == "velocity_bounceback":
+                v = np.ascontiguousarray(self.bc_vel[bc["id"]], dtype=np.float64)
+                L.ora_velocity_bounceback(_d(st), _d(self.bcBuffer), self.QQ,
+                                          int(bc["links"].size), _i(bc["links"]), _i(bc["outPos"]),
+                                          _i(bc["iDir"]), _i(bc["posInBuffer"]), _d(v),
+                                          self.incomp)
+            else:
+                raise ValueError("boundary kind %r not restated" % bc["kind"])
+
+    def step(self):
+        """do_fast_singleLevel (mus_control_module.f90:507-701), steps 3-9."""
+        L = lib()
+        self.set_boundary()                                     # 3 (on state(:,nNext))
+        self.nNow, self.nNext = self.nNext, self.nNow           # 4 mus_swap_now_next
+        self.calc_aux(self.state[self.nNow])                    # 5
+        L.ora_update_omega(_d(self.omega), _d(self.visc), self.ld.nSolve)   # 6
+        rc = L.ora_compute(self.relax, self.QQ, self.incomp, _d(self.state[self.nNow]),
+                           _d(self.state[self.nNext]), _d(self.aux), _i(self.ld.neigh),
+                           _d(self.omega), self.ld.nSize, self.ld.nSolve,
+                           ctypes.byref(self.rp))               # 7
+        if rc != 0:
+            raise RuntimeError("no oracle kernel for this (relaxation, layout, kind)")
+        if self.exchange is not None:
+            self.exchange(self)                                 # 9 exchange_real(state(:,next))
+
+    def run(self, nsteps):
+        for _ in range(nsteps):
+            self.step()
+
+    def total_mass(self):
+        return lib().ora_total_mass(_d(self.state[self.nNext]), self.QQ, self.ld.nFluid)
+
+    def set_omega(self, omega):
+        self.visc[:] = (1.0 / omega - 0.5) / 3.0
+        self.omega[:] = omega
+        self.omega_uniform = float(omega)
+
+
+def exchange_all(schemes):
+    """comm_isend_irecv_real for all ranks held in one process: gather every send
+    buffer from state(:,next), then scatter into the receivers."""
+    L = lib()
+    mail = {}
+    for r, s in enumerate(schemes):
+        st = s.state[s.nNext]
+        for snd in s.ld.send:
+            buf = np.empty(snd["pos"].size)
+            L.ora_comm_gather(_d(buf), _d(st), _i(snd["pos"]), int(buf.size))
+            mail[(r, snd["proc"])] = buf
+    for r, s in enumerate(schemes):
+        st = s.state[s.nNext]
+        for rcv in s.ld.recv:
+            buf = mail[(rcv["proc"], r)]
+            assert buf.size == rcv["pos"].size
+            L.ora_comm_scatter(_d(st), _d(buf), _i(rcv["pos"]), int(buf.size))
+
+
+def run_multi(schemes, nsteps):
+    for _ in range(nsteps):
+        for s in schemes:
+            s.step()
+        exchange_all(schemes)

@@ -1,0 +1,82 @@
+"""Pins the CPU oracle against the reference's own golden vector for this path:
+mus/examples/fluid/benchmark/gaussianPulse (fluid / BGK / D3Q19, predefined cube
+level 4, periodic, np=2, 9506 steps), compared exactly as the reference's pysys
+test does: numpy.allclose(rtol=1e-10, atol=1e-5)
+(pysys-extensions/apes/apeshelper.py:90-123)."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden",
+                    "gaussianPulse_pressAlongLength_p00000_t10.001E+00.res")
+
+
+def gaussian_pulse_setup(mo, nranks=1, rank=0):
+    """musubi.lua of the example restated (values, not code)."""
+    length, level = 10.0, 4
+    dx = length / 2.0 ** level
+    nu_phy, cs_phy, rho0 = 0.01, 343.0, 1.0
+    cs_lat = 1.0 / math.sqrt(3.0)
+    dt = cs_lat / cs_phy * dx
+    phys = mo.Physics(dx, dt, rho0)
+    nu_lat = nu_phy / phys.fac_visc
+    omega = 1.0 / (3.0 * nu_lat + 0.5)
+    nsteps = int(math.ceil(10.0 / dt))
+    ld = mo.build_level_desc(level, 19, "periodic", rank, nranks)
+    sch = mo.Scheme(ld, "bgk", "fluid", omega=omega)
+    sch.visc[:] = nu_lat
+    bary = mo.barycenters(ld, (0.0, 0.0, 0.0), length)
+    r = (bary[:, 0] - 5.0) ** 2 + (bary[:, 1] - 5.0) ** 2 + (bary[:, 2] - 5.0) ** 2
+    p = rho0 * cs_phy ** 2 + 1.20 * np.exp((-math.log(2.0) / 1.0 ** 2) * r)
+    rho = p * 3.0 * (1.0 / phys.fac_press)        # rho*cs2inv*inv_p, mus_flow_module.fpp:527
+    sch.init_equilibrium(rho, np.zeros(3))
+    return sch, phys, bary, nsteps
+
+
+def track_line(sch, phys, bary):
+    """tracking shape canoND origin (0, 5, 5) vec (10,0,0): the cells cut by the line;
+    the 16 cells with barycentre (x, 5.3125, 5.3125) as in the golden file."""
+    sel = np.nonzero((np.abs(bary[:sch.ld.nFluid, 1] - 5.3125) < 1e-9)
+                     & (np.abs(bary[:sch.ld.nFluid, 2] - 5.3125) < 1e-9))[0]
+    sel = sel[np.argsort(bary[sel, 0])]
+    aux = sch.aux.reshape(-1, 4)[sel]
+    dens = aux[:, 0] * phys.rho0
+    press = aux[:, 0] * (1.0 / 3.0) * phys.fac_press
+    vel = aux[:, 1:4] * phys.fac_vel
+    return np.column_stack([bary[sel], dens, press, vel])
+
+
+def test_gaussian_pulse_matches_reference_golden(oracle):
+    gold = np.loadtxt(GOLD, comments="#")
+    sch, phys, bary, nsteps = gaussian_pulse_setup(oracle)
+    assert nsteps == 9506
+    m0 = sch.total_mass()
+    sch.run(nsteps)
+    got = track_line(sch, phys, bary)
+    assert got.shape == gold.shape
+    assert np.allclose(got, gold, rtol=1e-10, atol=1e-5)
+    # far tighter than the reference's own criterion on the well-conditioned columns
+    assert np.max(np.abs(got[:, 3] / gold[:, 3] - 1.0)) < 1e-13     # density_phy
+    assert np.max(np.abs(got[:, 4] / gold[:, 4] - 1.0)) < 1e-13     # pressure_phy
+    assert np.max(np.abs(got[:, 5:] - gold[:, 5:])) < 2e-11         # velocity_phy (abs; fac_vel=594 => 3e-14 lattice, rounding noise)
+    assert abs(sch.total_mass() / m0 - 1.0) < 1e-13
+
+
+def test_gaussian_pulse_two_ranks_identical(oracle):
+    """the reference ran this case with np=2; the partitioned oracle must give the
+    same line (halo exchange moves bytes only)."""
+    gold = np.loadtxt(GOLD, comments="#")
+    runs = [gaussian_pulse_setup(oracle, nranks=2, rank=r) for r in range(2)]
+    schemes = [r[0] for r in runs]
+    oracle.run_multi(schemes, 400)
+    single, phys, bary, _ = gaussian_pulse_setup(oracle)
+    single.run(400)
+    ref = single.state[single.nNext].reshape(-1, 19)[:single.ld.nFluid]
+    off = 0
+    for s in schemes:
+        got = s.state[s.nNext].reshape(-1, 19)[:s.ld.nFluid]
+        assert np.array_equal(got, ref[off:off + s.ld.nFluid])
+        off += s.ld.nFluid
+    assert gold.shape == (16, 8)
