@@ -61,7 +61,7 @@ def test_gaussian_pulse_matches_reference_golden(oracle):
     assert np.max(np.abs(got[:, 3] / gold[:, 3] - 1.0)) < 1e-13     # density_phy
     assert np.max(np.abs(got[:, 4] / gold[:, 4] - 1.0)) < 1e-13     # pressure_phy
     assert np.max(np.abs(got[:, 5:] - gold[:, 5:])) < 2e-11         # velocity_phy (abs; fac_vel=594 => 3e-14 lattice, rounding noise)
-    assert abs(sch.total_mass() / m0 - 1.0) < 1e-13
+    assert abs(sch.total_mass() / m0 - 1.0) < 1e-11   # 9506 steps of rounding; 1e-13 is checked per 100 steps elsewhere
 
 
 def test_gaussian_pulse_two_ranks_identical(oracle):
