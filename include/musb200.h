@@ -1,0 +1,193 @@
+/* musb200.h -- C ABI of libmusb200.so: the B200-native per-level LBM time step
+ * behind Musubi's plugin surface.
+ *
+ * The reference (apes-suite/musubi, Fortran 2003 + MPI) has NO C ABI on this
+ * path; its plugin points are Fortran procedure pointers with derived-type
+ * arguments.  Every entry point below names the reference interface whose
+ * pointee it replaces; the Fortran shim that unwraps the derived types and
+ * calls these functions through ISO_C_BINDING is
+ * musubi_b200/fortran/mus_b200_module.f90.
+ *
+ * Conventions
+ *  - every function returns 0 on success and a non-zero code on failure; the
+ *    message is available through musb200_last_error().  The shim calls
+ *    tem_abort() on non-zero (tem/source/tem_aux_module.f90:457-478).
+ *  - host arrays are BORROWED for the duration of the call (copied to the
+ *    device); index lists are passed exactly as the Fortran arrays hold them:
+ *    1-based, default-integer (int32), AOS state positions
+ *        IDX(dir,elem)   = (elem-1)*nScalars + dir
+ *        NGPOS(dir,elem) = (dir-1)*nSize + elem        (lbm_macros.inc:82,104)
+ *  - one process = one MPI rank = one GPU; all calls come from the rank's main
+ *    thread.
+ *  - there is no CPU fallback: without a CUDA device every compute entry
+ *    point fails with MUSB200_ERR_CUDA.
+ */
+#ifndef MUSB200_H
+#define MUSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MUSB200_OK            0
+#define MUSB200_ERR_ARG       1   /* bad argument / unknown handle            */
+#define MUSB200_ERR_CUDA      2   /* CUDA runtime error (message has detail)  */
+#define MUSB200_ERR_NCCL      3
+#define MUSB200_ERR_UNSUPPORTED 4 /* valid Musubi configuration outside the hot path */
+#define MUSB200_ERR_CONNECTIVITY 5 /* neigh entry that is neither a plain pull nor a bounce-back */
+#define MUSB200_ERR_STATE     6   /* call order violated (e.g. step before level_create) */
+
+/* relaxation / kind / layout identifiers: mus_scheme_header_type
+ * (mus/source/scheme/mus_scheme_header_module.f90) identify{kind,relaxation,layout} */
+#define MUSB200_RELAX_BGK 0
+#define MUSB200_RELAX_TRT 1
+#define MUSB200_RELAX_MRT 2
+#define MUSB200_KIND_FLUID 0
+#define MUSB200_KIND_FLUID_INCOMPRESSIBLE 1
+
+/* boundary kinds: field%bc(i)%BC_kind (mus/source/bc/mus_bc_header_module.fpp) */
+#define MUSB200_BC_WALL                 0  /* do_nothing, mus_bc_fluid_wall_module.fpp:407-450 */
+#define MUSB200_BC_VELOCITY_BOUNCEBACK  1  /* mus_bc_fluid_module.fpp:1503-1597 */
+#define MUSB200_BC_PRESSURE_ANTIBOUNCEBACK 2 /* mus_bc_fluid_module.fpp:2161-2353 */
+#define MUSB200_BC_PRESSURE_EXPOL       3  /* mus_bc_fluid_module.fpp:1165-1362 */
+
+/* comm buffer kinds: tem_levelDesc_type%{send,recv}buffer[FromCoarser|FromFiner]
+ * (tem/source/tem_construction_module.f90:186-306) */
+#define MUSB200_BUF_HALO        0
+#define MUSB200_BUF_FROMCOARSER 1
+#define MUSB200_BUF_FROMFINER   2
+#define MUSB200_DIR_SEND 0
+#define MUSB200_DIR_RECV 1
+
+/* interpolation direction / order: mus_interpolation_type
+ * (mus/source/intp/mus_interpolate_header_module.f90:103-128) */
+#define MUSB200_INTP_FROMFINER   0  /* fillMineFromFiner   (average)            */
+#define MUSB200_INTP_FROMCOARSER 1  /* fillFinerFromMe(order): 0 weighted avg, 1 linear, 2 quadratic */
+
+/* ---- library life cycle ------------------------------------------------- */
+/* Replaces nothing in the reference (MPI is initialised by tem_start); binds
+ * this rank to `local_device` and, for nranks > 1, joins the NCCL communicator
+ * described by the 128-byte unique id (rank 0 obtains it from
+ * musb200_get_unique_id and broadcasts it with MPI_Bcast).                   */
+int musb200_init(int rank, int nranks, int local_device, const void *nccl_unique_id);
+int musb200_get_unique_id(void *out128);
+int musb200_finalize(void);
+int musb200_last_error(char *buf, int buflen);
+int musb200_device_count(int *n);
+
+/* ---- kernel selection ---------------------------------------------------
+ * Mirrors mus_init_advRel_fluid / _fluid_incompressible
+ * (mus/source/init/mus_initFluid_module.f90:102-232, 288-409): the Lua
+ * `identify` strings select the pointee of scheme%compute.  Unknown or
+ * out-of-scope combinations return MUSB200_ERR_UNSUPPORTED (the reference
+ * calls tem_abort for unknown ones).                                          */
+int musb200_scheme_select(const char *kind, const char *relaxation, const char *variant,
+                          const char *layout, int *relax_id, int *kind_id, int *QQ);
+
+/* ---- per-level data: pdf_data_type + tem_levelDesc_type ------------------
+ * mus/source/mus_pdf_module.f90:55-102, tem_construction_module.f90:186-306.
+ * neigh: pdf(level)%neigh(1:QQ*nSize); property / treeID: levelDesc%property,
+ * levelDesc%total (may be NULL).                                              */
+int musb200_level_create(int level, int QQ, int nScalars, int nAuxScalars, int nSize,
+                         int nFluid, int nGhostFromCoarser, int nGhostFromFiner, int nHalo,
+                         const int32_t *neigh, const int64_t *property, const int64_t *treeID);
+int musb200_level_destroy(int level);
+/* reads back the device neighbour list re-encoded as the Fortran positions
+ * (bit-exact parity check of the index lists) */
+int musb200_neigh_download(int level, int32_t *neigh);
+
+/* state(level)%val(:, which), which = 1|2 (array2D_type, mus_scheme_type_module.f90:75-80) */
+int musb200_state_upload(int level, int which, const double *aos_state);
+int musb200_state_download(int level, int which, double *aos_state);
+/* pdf%nNow / pdf%nNext (mus_pdf_module.f90:167-175) */
+int musb200_set_now_next(int level, int nNow, int nNext);
+int musb200_get_now_next(int level, int *nNow, int *nNext);
+/* auxField(level)%val(1:nSize*nAuxScalars), AOS (elem-1)*nAuxScalars + {rho,ux,uy,uz} */
+int musb200_aux_upload(int level, const double *aos_aux);
+int musb200_aux_download(int level, double *aos_aux);
+/* tracking of one element (tem_tracking with a point shape, interval {iter=1}):
+ * reads auxField((elemPos-1)*4 + 1:4) of one element, 32 bytes device -> host */
+int musb200_aux_probe(int level, int elemPos, double *rho_ux_uy_uz);
+/* state(:, nNow) = state(:, nNext) on the device (mus_flow_module.fpp:181-185) */
+int musb200_state_copy_next_to_now(int level);
+
+/* fluid%viscKine%omLvl(level)%val, fluid%lambda, fluid%omegaBulkLvl(level)
+ * (mus_relaxationParam_module.f90:249-283, mus_fluid_module.f90:104, 468-485).
+ * omega == NULL: every element uses omega_uniform.                            */
+int musb200_set_relaxation(int level, int relax_id, int kind_id, const double *omega,
+                           double omega_uniform, double lambda, double omega_bulk);
+
+/* ---- boundaries: boundary_type + glob_boundary_type per level -------------
+ * links      me%links(level)%val            (mus_bc_header_module.fpp:1702-1739)
+ * outPos, posInBuffer, iDir: me%inletUbbQVal(level)  (:1876-1967)
+ * bc_elemBuffer: levelDesc%bc_elemBuffer%val  (all BC elements of the level)   */
+int musb200_bc_elembuffer(int level, int nBcElems, const int32_t *bc_elemBuffer);
+int musb200_bc_register(int level, int bc_id, int bc_kind, int nLinks, const int32_t *links,
+                        const int32_t *outPos, const int32_t *posInBuffer, const int32_t *iDir);
+/* per-link boundary values in LATTICE units (velocity: 3 per link; pressure:
+ * 1 per link as lattice density), evaluated by the host's spacetime function */
+int musb200_bc_set_values(int level, int bc_id, int nVals, const double *vals);
+
+/* ---- halo exchange: tem_communication_type --------------------------------
+ * tem/source/tem_comm_module.fpp:93-177; pos(iProc) = buf_real(iProc)%pos.
+ * proc: 0-based ranks; nVals[iProc]; pos: concatenated position lists.        */
+int musb200_comm_register(int level, int buf_kind, int dir, int nProcs, const int32_t *proc,
+                          const int32_t *nVals, const int32_t *pos);
+
+/* ---- ghost interpolation: levelDesc%intpFromFiner / intpFromCoarser(order) -
+ * targetList: positions of the target ghosts in the target level's total list;
+ * per target a CSR row of source positions on the source level with weights
+ * (average / weighted average) or an index into the least-square matrices
+ * (mus_interpolate_header_module.f90:103-237, tem_matrix_module.fpp:161-425).  */
+int musb200_intp_register(int tgtLevel, int direction, int order, int nTargets,
+                          const int32_t *targetList, const int32_t *srcOffset /* nTargets+1 */,
+                          const int32_t *srcPos, const double *weights,
+                          const int32_t *posInMat, int nMatrices, const int32_t *matOffset,
+                          const double *matrices, const double *childCoord /* 3 per target */);
+
+/* ---- the time step: control%do_computation(minLevel) ----------------------
+ * Runs nCoarseCycles iterations of do_fast_singleLevel / do_recursive_multiLevel
+ * (mus/source/mus_control_module.f90:242-701) on the device: set_boundary, swap,
+ * fused auxField + stream-collide, halo exchange, ghost interpolation.         */
+int musb200_step(int minLevel, int maxLevel, int nCoarseCycles);
+/* 1: auxField is written by every level step (needed by tracking every step);
+ * 0 (default): only where the schedule reads it and on the last step of a call */
+int musb200_set_aux_every_step(int flag);
+int musb200_synchronize(void);
+
+/* check_density / check_flow_status (mus_tools_module.f90:224-313):
+ * sum of all PDFs of the fluid elements, max |u| and a NaN flag               */
+int musb200_reduce(int level, double *total_mass, double *max_vel, int *any_nan);
+
+/* ---- strict drop-in of the `kernel` interface -----------------------------
+ * scheme%compute (mus_scheme_type_module.f90:204-235) with HOST arrays, one
+ * call = H2D of inState, the fused kernel, D2H of outState and auxField.
+ * Used by the unit-test style parity checks (mus/utests/mus_bgk_d3q19_compare_test.f90). */
+int musb200_compute_host(int relax_id, int kind_id, int QQ, const double *inState,
+                         double *outState, double *auxField, const int32_t *neigh,
+                         int nElems /* = nSize */, int nSolve, const double *omega,
+                         double lambda, double omega_bulk);
+
+/* ---- timers: mus_timerHandles (mus_timer_module.f90) ---------------------- */
+/* device time in ms accumulated since the last reset: compute, bc, comm, intp */
+int musb200_timers(double *compute_ms, double *bc_ms, double *comm_ms, double *intp_ms);
+int musb200_timers_reset(void);
+/* number of kernel launches issued by this library since the last reset */
+int musb200_launch_count(long long *n);
+/* elapsed device time (ms) of the stepping stream between two marks */
+int musb200_event_mark(int which /*0 start, 1 stop*/);
+int musb200_event_elapsed(double *ms);
+/* 1: bracket every stage with CUDA events (the reference's per-stage timers) */
+int musb200_set_profiling(int flag);
+
+/* pinned host memory for the state mirrors (the shim may use it for state/auxField) */
+int musb200_host_alloc(size_t bytes, void **ptr);
+int musb200_host_free(void *ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUSB200_H */

@@ -1,0 +1,794 @@
+// api.cu -- the C ABI of libmusb200.so (include/musb200.h): per-level device
+// data, host <-> device conversion, and the time-step schedule of
+// mus/source/mus_control_module.f90 (do_fast_singleLevel :507-701,
+// do_recursive_multiLevel :242-497, do_intpFinerAndExchange :861-947,
+// do_intpCoarserAndExchange :955-1051) issued on CUDA streams.
+#include "../../include/musb200.h"
+#include "intp.cuh"
+#include "kernels.cuh"
+#include "nccl_dyn.h"
+
+#include <dlfcn.h>
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <vector>
+
+namespace musb200 {
+
+// ---------------------------------------------------------------------------
+std::string &lastError() {
+  static std::string s;
+  return s;
+}
+int setError(int code, const std::string &msg) {
+  lastError() = msg;
+  return code;
+}
+
+NcclApi *ncclApi() {
+  static NcclApi api;
+  static bool tried = false;
+  if (api.handle) return &api;
+  if (tried) return nullptr;
+  tried = true;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *n : names) {
+    api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (api.handle) break;
+  }
+  if (!api.handle) {
+    setError(MUSB200_ERR_NCCL, std::string("cannot load libnccl: ") + dlerror());
+    return nullptr;
+  }
+#define SYM(field, name)                                                        \
+  api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, name));  \
+  if (!api.field) {                                                            \
+    setError(MUSB200_ERR_NCCL, std::string("libnccl lacks ") + name);          \
+    api.handle = nullptr;                                                      \
+    return nullptr;                                                            \
+  }
+  SYM(GetUniqueId, "ncclGetUniqueId")
+  SYM(CommInitRank, "ncclCommInitRank")
+  SYM(CommDestroy, "ncclCommDestroy")
+  SYM(Send, "ncclSend")
+  SYM(Recv, "ncclRecv")
+  SYM(AllReduce, "ncclAllReduce")
+  SYM(GroupStart, "ncclGroupStart")
+  SYM(GroupEnd, "ncclGroupEnd")
+  SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  return &api;
+}
+
+#define MUSB_NCCL(call)                                                                   \
+  do {                                                                                    \
+    ncclResult_t r__ = (call);                                                            \
+    if (r__ != ncclSuccess)                                                               \
+      return setError(MUSB200_ERR_NCCL, std::string(#call) + ": " + g.nccl->GetErrorString(r__)); \
+  } while (0)
+
+#define MUSB_TRY(call)            \
+  do {                            \
+    int rc__ = (call);            \
+    if (rc__ != 0) return rc__;   \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  int alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) return 0;
+    MUSB_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    return 0;
+  }
+  int upload(const T *h, size_t count, cudaStream_t st) {
+    MUSB_TRY(alloc(count));
+    if (count) MUSB_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, st));
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { release(); }
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+};
+
+struct BcData {
+  int id = 0, kind = 0, nLinks = 0;
+  DevBuf<int32_t> links, outPos, posInBuffer, iDir;
+  DevBuf<double> vals;
+};
+
+struct CommBuf {
+  std::vector<int> proc, nVals, offset;
+  int total = 0;
+  DevBuf<int32_t> pos;
+  DevBuf<double> buf;
+};
+
+struct Level {
+  int level = 0, QQ = 0, nSize = 0, nFluid = 0, nGFC = 0, nGFF = 0, nHalo = 0;
+  int nElems = 0, nSolve = 0;
+  long long S = 0;
+  int nNow = 0, nNext = 1;  // 0-based buffer indices
+  DevBuf<double> state[2], aux, omega, bcBuffer;
+  DevBuf<uint32_t> nbr;
+  DevBuf<int32_t> bcElems;
+  int relax = 0, kind = 0;
+  bool relaxSet = false, elemOmega = false;
+  RelaxParams rp{1.0, 0.25, 1.0};
+  std::vector<std::unique_ptr<BcData>> bcs;
+  CommBuf send[3], recv[3];
+  IntpSet fromFiner;                 // fill my ghostFromFiner from level+1
+  std::vector<IntpSet> fromCoarser;  // fill my ghostFromCoarser from level-1, per order
+};
+
+struct Context {
+  bool ready = false;
+  int rank = 0, nranks = 1, device = 0;
+  cudaStream_t stream = nullptr;
+  NcclApi *nccl = nullptr;
+  ncclComm_t comm = nullptr;
+  std::map<int, std::unique_ptr<Level>> levels;
+  DevBuf<double> stage;  // AOS staging for up/download
+  DevBuf<double> red;    // reduction scratch + result
+  DevBuf<int> flag;
+  int auxEveryStep = 0;
+  long long launches = 0;
+  cudaEvent_t mark[2] = {nullptr, nullptr};
+  // section timers (device time, only sampled when profiling is on)
+  struct Span { int cat; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> pool;
+  int profiling = 0;
+  double acc[4] = {0, 0, 0, 0};
+};
+static Context g;
+
+static int needReady() {
+  if (!g.ready) return setError(MUSB200_ERR_STATE, "musb200_init has not been called");
+  return 0;
+}
+static Level *findLevel(int level) {
+  auto it = g.levels.find(level);
+  return it == g.levels.end() ? nullptr : it->second.get();
+}
+#define GET_LEVEL(L, level)                                                          \
+  MUSB_TRY(needReady());                                                             \
+  Level *L = findLevel(level);                                                       \
+  if (!L) return setError(MUSB200_ERR_ARG, "unknown level " + std::to_string(level))
+
+static int stageBuf(size_t n) {
+  if (g.stage.n < n) MUSB_TRY(g.stage.alloc(n));
+  return 0;
+}
+
+struct Timed {
+  int cat;
+  bool on;
+  cudaEvent_t a = nullptr, b = nullptr;
+  explicit Timed(int c) : cat(c), on(g.profiling != 0) {
+    if (!on) return;
+    auto get = [] {
+      cudaEvent_t e;
+      if (!g.pool.empty()) { e = g.pool.back(); g.pool.pop_back(); }
+      else cudaEventCreate(&e);
+      return e;
+    };
+    a = get(); b = get();
+    cudaEventRecord(a, g.stream);
+  }
+  ~Timed() {
+    if (!on) return;
+    cudaEventRecord(b, g.stream);
+    g.spans.push_back({cat, a, b});
+  }
+};
+enum { T_COMPUTE = 0, T_BC = 1, T_COMM = 2, T_INTP = 3 };
+
+// ---------------------------------------------------------------------------
+// the schedule
+static int setBoundary(Level &L) {
+  if (L.bcElems.n == 0) return 0;
+  Timed t(T_BC);
+  double *st = L.state[L.nNext].p;
+  bool any = false;
+  for (auto &b : L.bcs) any = any || (b->kind != MUSB200_BC_WALL && b->nLinks > 0);
+  if (!any) return 0;
+  MUSB_TRY(launchFillBcBuffer(L.QQ, st, L.S, L.bcElems.p, (int)L.bcElems.n, L.bcBuffer.p, g.stream));
+  ++g.launches;
+  for (auto &b : L.bcs) {
+    if (b->kind == MUSB200_BC_WALL || b->nLinks == 0) continue;
+    if (b->kind == MUSB200_BC_VELOCITY_BOUNCEBACK) {
+      if (b->vals.n < (size_t)3 * b->nLinks)
+        return setError(MUSB200_ERR_STATE, "velocity_bounceback: musb200_bc_set_values missing");
+      MUSB_TRY(launchVelocityBounceBack(L.QQ, L.kind == MUSB200_KIND_FLUID_INCOMPRESSIBLE, st, L.S,
+                                        L.bcBuffer.p, b->nLinks, b->links.p, b->outPos.p,
+                                        b->posInBuffer.p, b->iDir.p, b->vals.p, g.stream));
+      ++g.launches;
+    } else {
+      return setError(MUSB200_ERR_UNSUPPORTED, "boundary kind not built yet");
+    }
+  }
+  return 0;
+}
+
+static int exchange(Level &L, int kind, double *state, int nComp) {
+  if (g.nranks == 1) return 0;
+  CommBuf &s = L.send[kind], &r = L.recv[kind];
+  if (s.total == 0 && r.total == 0) return 0;
+  Timed t(T_COMM);
+  if (s.total) {
+    MUSB_TRY(launchPack(nComp, state, L.S, s.pos.p, s.total, s.buf.p, g.stream));
+    ++g.launches;
+  }
+  MUSB_NCCL(g.nccl->GroupStart());
+  for (size_t i = 0; i < s.proc.size(); ++i)
+    MUSB_NCCL(g.nccl->Send(s.buf.p + s.offset[i], (size_t)s.nVals[i], ncclDouble, s.proc[i], g.comm,
+                           g.stream));
+  for (size_t i = 0; i < r.proc.size(); ++i)
+    MUSB_NCCL(g.nccl->Recv(r.buf.p + r.offset[i], (size_t)r.nVals[i], ncclDouble, r.proc[i], g.comm,
+                           g.stream));
+  MUSB_NCCL(g.nccl->GroupEnd());
+  if (r.total) {
+    MUSB_TRY(launchUnpack(nComp, state, L.S, r.pos.p, r.total, r.buf.p, g.stream));
+    ++g.launches;
+  }
+  return 0;
+}
+
+static int sweep(Level &L, bool writeAux) {
+  if (!L.relaxSet) return setError(MUSB200_ERR_STATE, "musb200_set_relaxation missing");
+  Timed t(T_COMPUTE);
+  SweepArgs a{};
+  a.in = L.state[L.nNow].p;
+  a.out = L.state[L.nNext].p;
+  a.nbr = L.nbr.p;
+  a.aux = L.aux.p;
+  a.omega = L.elemOmega ? L.omega.p : nullptr;
+  a.list = nullptr;
+  a.skip = nullptr;
+  a.S = L.S;
+  a.first = 0;
+  a.count = L.nSolve;
+  a.write_aux = writeAux ? 1 : 0;
+  a.rp = L.rp;
+  MUSB_TRY(launchSweep(L.QQ, L.relax, L.kind, a, g.stream));
+  ++g.launches;
+  return 0;
+}
+
+static int applyIntp(Level &src, Level &tgt, IntpSet &set, bool fromFiner) {
+  if (set.nTargets == 0) return 0;
+  Timed t(T_INTP);
+  IntpArgs a{};
+  a.QQ = tgt.QQ;
+  a.incomp = tgt.kind == MUSB200_KIND_FLUID_INCOMPRESSIBLE;
+  a.sState = src.state[src.nNext].p;
+  a.sAux = src.aux.p;
+  a.sS = src.S;
+  a.tState = tgt.state[tgt.nNext].p;
+  a.tS = tgt.S;
+  a.tOmega = tgt.elemOmega ? tgt.omega.p : nullptr;
+  a.tOmegaUniform = tgt.rp.omega_uniform;
+  MUSB_TRY(launchIntp(a, set, fromFiner, g.stream));
+  ++g.launches;
+  return 0;
+}
+
+static int levelStep(int iLevel, int minLevel, int maxLevel, bool lastCycle) {
+  Level *Lp = findLevel(iLevel);
+  if (!Lp) return setError(MUSB200_ERR_ARG, "level " + std::to_string(iLevel) + " was not created");
+  Level &L = *Lp;
+  const bool multi = (maxLevel > minLevel);
+  if (iLevel < maxLevel) {
+    // nNesting = 2 (acoustic scaling, mus_param_module.f90:191-195)
+    for (int n = 0; n < 2; ++n) MUSB_TRY(levelStep(iLevel + 1, minLevel, maxLevel, lastCycle && n == 1));
+  }
+  MUSB_TRY(setBoundary(L));
+  std::swap(L.nNow, L.nNext);
+  // multi-level: the interpolation routines read auxField of their sources every step
+  const bool writeAux = g.auxEveryStep || multi || lastCycle;
+  if (multi && iLevel < maxLevel) {
+    // aux of my ghostFromFiner elements is interpolated from level+1
+    // (mus_intpAuxFieldCoarserAndExchange, mus_auxField_module.f90:404-444): done inside
+    // the fromFiner state interpolation below, which recomputes what it needs.
+  }
+  MUSB_TRY(sweep(L, writeAux));
+  if (multi && writeAux) MUSB_TRY(exchange(L, MUSB200_BUF_HALO, L.aux.p, 4)); // aux halo (tag level+100)
+  MUSB_TRY(exchange(L, MUSB200_BUF_HALO, L.state[L.nNext].p, L.QQ));
+  if (iLevel > minLevel) MUSB_TRY(exchange(L, MUSB200_BUF_FROMCOARSER, L.state[L.nNext].p, L.QQ));
+  if (iLevel < maxLevel) {
+    Level *F = findLevel(iLevel + 1);
+    // do_intpFinerAndExchange: my ghostFromFiner <- average over the children on level+1
+    MUSB_TRY(applyIntp(*F, L, L.fromFiner, true));
+    MUSB_TRY(exchange(L, MUSB200_BUF_FROMFINER, L.state[L.nNext].p, L.QQ));
+    // do_intpCoarserAndExchange: ghostFromCoarser of level+1 <- me, orders 0..order
+    for (auto &set : F->fromCoarser) MUSB_TRY(applyIntp(L, *F, set, false));
+    MUSB_TRY(exchange(*F, MUSB200_BUF_FROMCOARSER, F->state[F->nNext].p, F->QQ));
+  }
+  return 0;
+}
+
+}  // namespace musb200
+
+using namespace musb200;
+
+// ===========================================================================
+extern "C" {
+
+int musb200_last_error(char *buf, int buflen) {
+  if (!buf || buflen <= 0) return MUSB200_ERR_ARG;
+  std::strncpy(buf, lastError().c_str(), (size_t)buflen - 1);
+  buf[buflen - 1] = 0;
+  return 0;
+}
+
+int musb200_device_count(int *n) {
+  if (!n) return setError(MUSB200_ERR_ARG, "null argument");
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) {
+    *n = 0;
+    return setError(MUSB200_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+  }
+  *n = c;
+  return 0;
+}
+
+int musb200_get_unique_id(void *out128) {
+  if (!out128) return setError(MUSB200_ERR_ARG, "null argument");
+  NcclApi *api = ncclApi();
+  if (!api) return MUSB200_ERR_NCCL;
+  ncclUniqueId id;
+  if (api->GetUniqueId(&id) != ncclSuccess) return setError(MUSB200_ERR_NCCL, "ncclGetUniqueId failed");
+  std::memcpy(out128, &id, 128);
+  return 0;
+}
+
+int musb200_init(int rank, int nranks, int local_device, const void *nccl_unique_id) {
+  if (g.ready) return setError(MUSB200_ERR_STATE, "musb200_init called twice");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return setError(MUSB200_ERR_ARG, "bad rank/nranks");
+  int ndev = 0;
+  MUSB_TRY(musb200_device_count(&ndev));
+  if (ndev == 0) return setError(MUSB200_ERR_CUDA, "no CUDA device: libmusb200 has no CPU fallback");
+  if (local_device < 0 || local_device >= ndev) return setError(MUSB200_ERR_ARG, "bad device index");
+  MUSB_CUDA(cudaSetDevice(local_device));
+  cudaDeviceProp prop;
+  MUSB_CUDA(cudaGetDeviceProperties(&prop, local_device));
+  if (prop.major < 10)
+    return setError(MUSB200_ERR_CUDA, std::string("device ") + prop.name + " is not sm_100 class");
+  g.rank = rank; g.nranks = nranks; g.device = local_device;
+  MUSB_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  MUSB_CUDA(cudaEventCreate(&g.mark[0]));
+  MUSB_CUDA(cudaEventCreate(&g.mark[1]));
+  MUSB_TRY(g.red.alloc(3 * 592 + 8));
+  MUSB_TRY(g.flag.alloc(1));
+  if (nranks > 1) {
+    if (!nccl_unique_id) return setError(MUSB200_ERR_ARG, "nranks > 1 needs the NCCL unique id");
+    g.nccl = ncclApi();
+    if (!g.nccl) return MUSB200_ERR_NCCL;
+    ncclUniqueId id;
+    std::memcpy(&id, nccl_unique_id, 128);
+    MUSB_NCCL(g.nccl->CommInitRank(&g.comm, nranks, id, rank));
+  }
+  g.ready = true;
+  return 0;
+}
+
+int musb200_finalize(void) {
+  if (!g.ready) return 0;
+  cudaStreamSynchronize(g.stream);
+  g.levels.clear();
+  g.stage.release(); g.red.release(); g.flag.release();
+  for (auto &s : g.spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+  g.spans.clear();
+  for (auto e : g.pool) cudaEventDestroy(e);
+  g.pool.clear();
+  if (g.comm) { g.nccl->CommDestroy(g.comm); g.comm = nullptr; }
+  cudaEventDestroy(g.mark[0]); cudaEventDestroy(g.mark[1]);
+  cudaStreamDestroy(g.stream);
+  g.stream = nullptr;
+  g.ready = false;
+  g.launches = 0;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+int musb200_scheme_select(const char *kind, const char *relaxation, const char *variant,
+                          const char *layout, int *relax_id, int *kind_id, int *QQ) {
+  if (!kind || !relaxation || !layout || !relax_id || !kind_id || !QQ)
+    return setError(MUSB200_ERR_ARG, "null argument");
+  const std::string k(kind), r(relaxation), l(layout), v(variant ? variant : "standard");
+  int kk, rr, qq;
+  if (k == "fluid") kk = MUSB200_KIND_FLUID;
+  else if (k == "fluid_incompressible") kk = MUSB200_KIND_FLUID_INCOMPRESSIBLE;
+  else return setError(MUSB200_ERR_UNSUPPORTED, "scheme kind '" + k + "' is outside the B200 hot path");
+  if (l == "d3q19") qq = 19;
+  else if (l == "d3q27") qq = 27;
+  else return setError(MUSB200_ERR_UNSUPPORTED, "layout '" + l + "' is outside the B200 hot path");
+  if (r == "bgk") rr = MUSB200_RELAX_BGK;
+  else if (r == "trt") rr = MUSB200_RELAX_TRT;
+  else if (r == "mrt") rr = MUSB200_RELAX_MRT;
+  else return setError(MUSB200_ERR_UNSUPPORTED, "relaxation '" + r + "' is outside the B200 hot path");
+  if (v != "standard" && v != "b200")
+    return setError(MUSB200_ERR_UNSUPPORTED, "relaxation variant '" + v + "' is outside the B200 hot path");
+  if (kk == MUSB200_KIND_FLUID_INCOMPRESSIBLE && !(qq == 19 && rr == MUSB200_RELAX_BGK))
+    return setError(MUSB200_ERR_UNSUPPORTED,
+                    "fluid_incompressible: only bgk/d3q19 is built (the others are a 'next' row)");
+  *relax_id = rr; *kind_id = kk; *QQ = qq;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+int musb200_level_create(int level, int QQ, int nScalars, int nAuxScalars, int nSize, int nFluid,
+                         int nGhostFromCoarser, int nGhostFromFiner, int nHalo,
+                         const int32_t *neigh, const int64_t *property, const int64_t *treeID) {
+  (void)property; (void)treeID;
+  MUSB_TRY(needReady());
+  if (QQ != 19 && QQ != 27) return setError(MUSB200_ERR_UNSUPPORTED, "only d3q19 / d3q27");
+  if (nScalars != QQ) return setError(MUSB200_ERR_UNSUPPORTED, "multi-field schemes (nScalars != QQ)");
+  if (nAuxScalars != 4) return setError(MUSB200_ERR_UNSUPPORTED, "nAuxScalars must be 4 (rho, u)");
+  const long long nElems = (long long)nFluid + nGhostFromCoarser + nGhostFromFiner + nHalo;
+  if (nSize < nElems || nSize <= 0 || !neigh) return setError(MUSB200_ERR_ARG, "bad sizes / null neigh");
+  if ((long long)nSize > (long long)kElemMask) return setError(MUSB200_ERR_ARG, "nSize exceeds 2^31-1");
+  if ((long long)nSize * QQ > 2147483647LL)
+    return setError(MUSB200_ERR_ARG, "nSize*QQ exceeds the 32-bit state positions of the host lists");
+  auto L = std::make_unique<Level>();
+  L->level = level; L->QQ = QQ; L->nSize = nSize; L->nFluid = nFluid;
+  L->nGFC = nGhostFromCoarser; L->nGFF = nGhostFromFiner; L->nHalo = nHalo;
+  L->nElems = (int)nElems;
+  L->nSolve = nFluid + nGhostFromCoarser;  // mus_pdf_module.f90:125
+  L->S = ((long long)nSize + 31) / 32 * 32;
+  for (int b = 0; b < 2; ++b) {
+    MUSB_TRY(L->state[b].alloc((size_t)L->S * QQ));
+    MUSB_CUDA(cudaMemsetAsync(L->state[b].p, 0, (size_t)L->S * QQ * sizeof(double), g.stream));
+  }
+  MUSB_TRY(L->aux.alloc((size_t)L->S * 4));
+  MUSB_CUDA(cudaMemsetAsync(L->aux.p, 0, (size_t)L->S * 4 * sizeof(double), g.stream));
+  MUSB_TRY(L->nbr.alloc((size_t)L->S * (QQ - 1)));
+  MUSB_CUDA(cudaMemsetAsync(L->nbr.p, 0, (size_t)L->S * (QQ - 1) * sizeof(uint32_t), g.stream));
+  // upload the Fortran list and encode it on the device
+  DevBuf<int32_t> tmp;
+  MUSB_TRY(tmp.upload(neigh, (size_t)nSize * QQ, g.stream));
+  MUSB_CUDA(cudaMemsetAsync(g.flag.p, 0, sizeof(int), g.stream));
+  MUSB_TRY(launchEncodeNeigh(QQ, tmp.p, L->nbr.p, nSize, L->nElems, L->S, g.flag.p, g.stream));
+  int bad = 0;
+  MUSB_CUDA(cudaMemcpyAsync(&bad, g.flag.p, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+  MUSB_CUDA(cudaStreamSynchronize(g.stream));
+  if (bad)
+    return setError(MUSB200_ERR_CONNECTIVITY,
+                    std::to_string(bad) + " neigh entries are neither a plain pull nor a bounce-back");
+  g.levels[level] = std::move(L);
+  return 0;
+}
+
+int musb200_level_destroy(int level) {
+  MUSB_TRY(needReady());
+  cudaStreamSynchronize(g.stream);
+  g.levels.erase(level);
+  return 0;
+}
+
+int musb200_neigh_download(int level, int32_t *neigh) {
+  GET_LEVEL(L, level);
+  if (!neigh) return setError(MUSB200_ERR_ARG, "null argument");
+  DevBuf<int32_t> tmp;
+  MUSB_TRY(tmp.alloc((size_t)L->nSize * L->QQ));
+  MUSB_CUDA(cudaMemsetAsync(tmp.p, 0, tmp.n * sizeof(int32_t), g.stream));
+  MUSB_TRY(launchDecodeNeigh(L->QQ, L->nbr.p, tmp.p, L->nSize, L->nElems, L->S, g.stream));
+  MUSB_CUDA(cudaMemcpyAsync(neigh, tmp.p, tmp.n * sizeof(int32_t), cudaMemcpyDeviceToHost, g.stream));
+  MUSB_CUDA(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+static int uploadAos(Level *L, const double *host, double *soa, int nComp) {
+  const size_t n = (size_t)L->nSize * nComp;
+  MUSB_TRY(stageBuf(n));
+  MUSB_CUDA(cudaMemcpyAsync(g.stage.p, host, n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  MUSB_TRY(launchAosToSoa(g.stage.p, soa, nComp, L->nSize, L->S, g.stream));
+  ++g.launches;
+  return 0;
+}
+static int downloadAos(Level *L, const double *soa, double *host, int nComp) {
+  const size_t n = (size_t)L->nSize * nComp;
+  MUSB_TRY(stageBuf(n));
+  MUSB_TRY(launchSoaToAos(soa, g.stage.p, nComp, L->nSize, L->S, g.stream));
+  ++g.launches;
+  MUSB_CUDA(cudaMemcpyAsync(host, g.stage.p, n * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  MUSB_CUDA(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+int musb200_state_upload(int level, int which, const double *aos_state) {
+  GET_LEVEL(L, level);
+  if (which < 1 || which > 2 || !aos_state) return setError(MUSB200_ERR_ARG, "which must be 1|2");
+  return uploadAos(L, aos_state, L->state[which - 1].p, L->QQ);
+}
+int musb200_state_download(int level, int which, double *aos_state) {
+  GET_LEVEL(L, level);
+  if (which < 1 || which > 2 || !aos_state) return setError(MUSB200_ERR_ARG, "which must be 1|2");
+  return downloadAos(L, L->state[which - 1].p, aos_state, L->QQ);
+}
+int musb200_aux_upload(int level, const double *aos_aux) {
+  GET_LEVEL(L, level);
+  if (!aos_aux) return setError(MUSB200_ERR_ARG, "null argument");
+  return uploadAos(L, aos_aux, L->aux.p, 4);
+}
+int musb200_aux_download(int level, double *aos_aux) {
+  GET_LEVEL(L, level);
+  if (!aos_aux) return setError(MUSB200_ERR_ARG, "null argument");
+  return downloadAos(L, L->aux.p, aos_aux, 4);
+}
+int musb200_aux_probe(int level, int elemPos, double *out) {
+  GET_LEVEL(L, level);
+  if (!out || elemPos < 1 || elemPos > L->nElems) return setError(MUSB200_ERR_ARG, "bad probe element");
+  MUSB_CUDA(cudaMemcpy2DAsync(out, sizeof(double), L->aux.p + (elemPos - 1), (size_t)L->S * sizeof(double),
+                              sizeof(double), 4, cudaMemcpyDeviceToHost, g.stream));
+  MUSB_CUDA(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+int musb200_state_copy_next_to_now(int level) {
+  GET_LEVEL(L, level);
+  MUSB_CUDA(cudaMemcpyAsync(L->state[L->nNow].p, L->state[L->nNext].p,
+                            (size_t)L->S * L->QQ * sizeof(double), cudaMemcpyDeviceToDevice, g.stream));
+  return 0;
+}
+int musb200_set_now_next(int level, int nNow, int nNext) {
+  GET_LEVEL(L, level);
+  if (!((nNow == 1 && nNext == 2) || (nNow == 2 && nNext == 1)))
+    return setError(MUSB200_ERR_ARG, "nNow/nNext must be a permutation of 1,2");
+  L->nNow = nNow - 1; L->nNext = nNext - 1;
+  return 0;
+}
+int musb200_get_now_next(int level, int *nNow, int *nNext) {
+  GET_LEVEL(L, level);
+  if (nNow) *nNow = L->nNow + 1;
+  if (nNext) *nNext = L->nNext + 1;
+  return 0;
+}
+
+int musb200_set_relaxation(int level, int relax_id, int kind_id, const double *omega,
+                           double omega_uniform, double lambda, double omega_bulk) {
+  GET_LEVEL(L, level);
+  if (relax_id < 0 || relax_id > 2 || kind_id < 0 || kind_id > 1)
+    return setError(MUSB200_ERR_ARG, "bad relaxation / kind id");
+  if (kind_id == MUSB200_KIND_FLUID_INCOMPRESSIBLE && !(L->QQ == 19 && relax_id == 0))
+    return setError(MUSB200_ERR_UNSUPPORTED, "fluid_incompressible: only bgk/d3q19 is built");
+  L->relax = relax_id; L->kind = kind_id;
+  L->rp.omega_uniform = omega_uniform; L->rp.lambda = lambda; L->rp.omega_bulk = omega_bulk;
+  L->elemOmega = (omega != nullptr);
+  if (omega) {
+    if (L->omega.n < (size_t)L->S) MUSB_TRY(L->omega.alloc((size_t)L->S));
+    MUSB_CUDA(cudaMemcpyAsync(L->omega.p, omega, (size_t)L->nSolve * sizeof(double),
+                              cudaMemcpyHostToDevice, g.stream));
+  }
+  L->relaxSet = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+int musb200_bc_elembuffer(int level, int nBcElems, const int32_t *bc_elemBuffer) {
+  GET_LEVEL(L, level);
+  if (nBcElems < 0 || (nBcElems > 0 && !bc_elemBuffer)) return setError(MUSB200_ERR_ARG, "bad BC element buffer");
+  MUSB_TRY(L->bcElems.upload(bc_elemBuffer, (size_t)nBcElems, g.stream));
+  MUSB_TRY(L->bcBuffer.alloc((size_t)std::max(1, nBcElems) * L->QQ));
+  return 0;
+}
+
+int musb200_bc_register(int level, int bc_id, int bc_kind, int nLinks, const int32_t *links,
+                        const int32_t *outPos, const int32_t *posInBuffer, const int32_t *iDir) {
+  GET_LEVEL(L, level);
+  if (bc_kind != MUSB200_BC_WALL && bc_kind != MUSB200_BC_VELOCITY_BOUNCEBACK)
+    return setError(MUSB200_ERR_UNSUPPORTED, "boundary kind " + std::to_string(bc_kind) + " is not built yet");
+  if (nLinks < 0) return setError(MUSB200_ERR_ARG, "nLinks < 0");
+  auto b = std::make_unique<BcData>();
+  b->id = bc_id; b->kind = bc_kind; b->nLinks = nLinks;
+  if (bc_kind != MUSB200_BC_WALL && nLinks > 0) {
+    if (!links || !outPos || !posInBuffer || !iDir) return setError(MUSB200_ERR_ARG, "null link list");
+    if (L->bcElems.n == 0) return setError(MUSB200_ERR_STATE, "musb200_bc_elembuffer must come first");
+    MUSB_TRY(b->links.upload(links, nLinks, g.stream));
+    MUSB_TRY(b->outPos.upload(outPos, nLinks, g.stream));
+    MUSB_TRY(b->posInBuffer.upload(posInBuffer, nLinks, g.stream));
+    MUSB_TRY(b->iDir.upload(iDir, nLinks, g.stream));
+  }
+  for (auto &o : L->bcs)
+    if (o->id == bc_id) { o = std::move(b); return 0; }
+  L->bcs.push_back(std::move(b));
+  return 0;
+}
+
+int musb200_bc_set_values(int level, int bc_id, int nVals, const double *vals) {
+  GET_LEVEL(L, level);
+  for (auto &b : L->bcs) {
+    if (b->id != bc_id) continue;
+    if (nVals < 0 || (nVals > 0 && !vals)) return setError(MUSB200_ERR_ARG, "bad values");
+    if (b->vals.n != (size_t)nVals) MUSB_TRY(b->vals.alloc((size_t)nVals));
+    if (nVals)
+      MUSB_CUDA(cudaMemcpyAsync(b->vals.p, vals, (size_t)nVals * sizeof(double), cudaMemcpyHostToDevice,
+                                g.stream));
+    return 0;
+  }
+  return setError(MUSB200_ERR_ARG, "unknown boundary id " + std::to_string(bc_id));
+}
+
+// ---------------------------------------------------------------------------
+int musb200_comm_register(int level, int buf_kind, int dir, int nProcs, const int32_t *proc,
+                          const int32_t *nVals, const int32_t *pos) {
+  GET_LEVEL(L, level);
+  if (buf_kind < 0 || buf_kind > 2 || dir < 0 || dir > 1 || nProcs < 0)
+    return setError(MUSB200_ERR_ARG, "bad buffer kind / direction");
+  CommBuf &c = (dir == MUSB200_DIR_SEND) ? L->send[buf_kind] : L->recv[buf_kind];
+  c.proc.clear(); c.nVals.clear(); c.offset.clear(); c.total = 0;
+  for (int i = 0; i < nProcs; ++i) {
+    if (proc[i] < 0 || proc[i] >= g.nranks || proc[i] == g.rank || nVals[i] < 0)
+      return setError(MUSB200_ERR_ARG, "bad peer rank in comm buffer");
+    c.proc.push_back(proc[i]); c.nVals.push_back(nVals[i]); c.offset.push_back(c.total);
+    c.total += nVals[i];
+  }
+  MUSB_TRY(c.pos.upload(pos, (size_t)c.total, g.stream));
+  MUSB_TRY(c.buf.alloc((size_t)std::max(1, c.total)));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+int musb200_intp_register(int tgtLevel, int direction, int order, int nTargets,
+                          const int32_t *targetList, const int32_t *srcOffset, const int32_t *srcPos,
+                          const double *weights, const int32_t *posInMat, int nMatrices,
+                          const int32_t *matOffset, const double *matrices, const double *childCoord) {
+  GET_LEVEL(L, tgtLevel);
+  if (nTargets < 0 || order < 0 || order > 2) return setError(MUSB200_ERR_ARG, "bad interpolation set");
+  IntpSet *set;
+  if (direction == MUSB200_INTP_FROMFINER) {
+    set = &L->fromFiner;
+  } else if (direction == MUSB200_INTP_FROMCOARSER) {
+    if ((int)L->fromCoarser.size() <= order) L->fromCoarser.resize(order + 1);
+    set = &L->fromCoarser[order];
+  } else {
+    return setError(MUSB200_ERR_ARG, "bad interpolation direction");
+  }
+  return registerIntp(*set, order, nTargets, targetList, srcOffset, srcPos, weights, posInMat,
+                      nMatrices, matOffset, matrices, childCoord, g.stream);
+}
+
+// ---------------------------------------------------------------------------
+int musb200_set_aux_every_step(int flag) {
+  g.auxEveryStep = flag ? 1 : 0;
+  return 0;
+}
+
+int musb200_step(int minLevel, int maxLevel, int nCoarseCycles) {
+  MUSB_TRY(needReady());
+  if (maxLevel < minLevel || nCoarseCycles < 0) return setError(MUSB200_ERR_ARG, "bad level range / cycles");
+  for (int it = 0; it < nCoarseCycles; ++it)
+    MUSB_TRY(levelStep(minLevel, minLevel, maxLevel, it == nCoarseCycles - 1));
+  return 0;
+}
+
+int musb200_synchronize(void) {
+  MUSB_TRY(needReady());
+  MUSB_CUDA(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+int musb200_reduce(int level, double *total_mass, double *max_vel, int *any_nan) {
+  GET_LEVEL(L, level);
+  double *out = g.red.p + 3 * 592;
+  MUSB_TRY(launchReduce(L->QQ, L->state[L->nNext].p, L->S, L->nFluid, g.red.p, out, g.stream));
+  g.launches += 2;
+  if (g.nranks > 1) {
+    // check_density: mpi_reduce of the total density (mus_tools_module.f90:298)
+    MUSB_NCCL(g.nccl->AllReduce(out, out + 4, 1, ncclDouble, ncclSum, g.comm, g.stream));
+    MUSB_NCCL(g.nccl->AllReduce(out + 1, out + 5, 1, ncclDouble, ncclMax, g.comm, g.stream));
+    MUSB_NCCL(g.nccl->AllReduce(out + 2, out + 6, 1, ncclDouble, ncclSum, g.comm, g.stream));
+    out += 4;
+  }
+  double h[3];
+  MUSB_CUDA(cudaMemcpyAsync(h, out, 3 * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  MUSB_CUDA(cudaStreamSynchronize(g.stream));
+  if (total_mass) *total_mass = h[0];
+  if (max_vel) *max_vel = sqrt(h[1]);
+  if (any_nan) *any_nan = (h[2] > 0.0 || h[0] != h[0]) ? 1 : 0;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+int musb200_compute_host(int relax_id, int kind_id, int QQ, const double *inState, double *outState,
+                         double *auxField, const int32_t *neigh, int nElems, int nSolve,
+                         const double *omega, double lambda, double omega_bulk) {
+  MUSB_TRY(needReady());
+  if (!inState || !outState || !neigh || !omega || nSolve > nElems)
+    return setError(MUSB200_ERR_ARG, "bad arguments");
+  const int tmpLevel = -4711;
+  MUSB_TRY(musb200_level_create(tmpLevel, QQ, QQ, 4, nElems, nSolve, 0, 0, nElems - nSolve, neigh,
+                                nullptr, nullptr));
+  int rc = 0;
+  do {
+    if ((rc = musb200_state_upload(tmpLevel, 1, inState))) break;
+    if ((rc = musb200_set_now_next(tmpLevel, 1, 2))) break;
+    if ((rc = musb200_set_relaxation(tmpLevel, relax_id, kind_id, omega, 0.0, lambda, omega_bulk))) break;
+    Level *L = findLevel(tmpLevel);
+    if ((rc = sweep(*L, true))) break;
+    if ((rc = musb200_state_download(tmpLevel, 2, outState))) break;
+    if (auxField) rc = musb200_aux_download(tmpLevel, auxField);
+  } while (0);
+  musb200_level_destroy(tmpLevel);
+  return rc;
+}
+
+// ---------------------------------------------------------------------------
+int musb200_set_profiling(int flag) {
+  g.profiling = flag ? 1 : 0;
+  return 0;
+}
+
+int musb200_timers(double *compute_ms, double *bc_ms, double *comm_ms, double *intp_ms) {
+  MUSB_TRY(needReady());
+  MUSB_CUDA(cudaStreamSynchronize(g.stream));
+  for (auto &s : g.spans) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, s.a, s.b);
+    g.acc[s.cat] += ms;
+    g.pool.push_back(s.a);
+    g.pool.push_back(s.b);
+  }
+  g.spans.clear();
+  if (compute_ms) *compute_ms = g.acc[T_COMPUTE];
+  if (bc_ms) *bc_ms = g.acc[T_BC];
+  if (comm_ms) *comm_ms = g.acc[T_COMM];
+  if (intp_ms) *intp_ms = g.acc[T_INTP];
+  return 0;
+}
+
+int musb200_timers_reset(void) {
+  MUSB_TRY(musb200_timers(nullptr, nullptr, nullptr, nullptr));
+  for (double &a : g.acc) a = 0.0;
+  g.launches = 0;
+  return 0;
+}
+
+int musb200_launch_count(long long *n) {
+  if (!n) return setError(MUSB200_ERR_ARG, "null argument");
+  *n = g.launches;
+  return 0;
+}
+
+int musb200_event_mark(int which) {
+  MUSB_TRY(needReady());
+  if (which < 0 || which > 1) return setError(MUSB200_ERR_ARG, "which must be 0|1");
+  MUSB_CUDA(cudaEventRecord(g.mark[which], g.stream));
+  return 0;
+}
+
+int musb200_event_elapsed(double *ms) {
+  MUSB_TRY(needReady());
+  if (!ms) return setError(MUSB200_ERR_ARG, "null argument");
+  MUSB_CUDA(cudaEventSynchronize(g.mark[1]));
+  float f = 0.f;
+  MUSB_CUDA(cudaEventElapsedTime(&f, g.mark[0], g.mark[1]));
+  *ms = f;
+  return 0;
+}
+
+int musb200_host_alloc(size_t bytes, void **ptr) {
+  if (!ptr) return setError(MUSB200_ERR_ARG, "null argument");
+  MUSB_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+  return 0;
+}
+
+int musb200_host_free(void *ptr) {
+  if (ptr) MUSB_CUDA(cudaFreeHost(ptr));
+  return 0;
+}
+
+}  // extern "C"

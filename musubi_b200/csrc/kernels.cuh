@@ -1,0 +1,56 @@
+// kernels.cuh -- launch interface of the device kernels (implemented in *.cu)
+#pragma once
+#include "collide.cuh"
+
+namespace musb200 {
+
+// Arguments of one fused "auxField + stream + collide" sweep over a level.
+// State and aux are SoA with row stride S (elements): f[q][e] = ptr[q*S + e].
+struct SweepArgs {
+  const double *in;        // state(:, now)
+  double *out;             // state(:, next)
+  const uint32_t *nbr;     // [QQ-1][S] encoded pull sources (rest direction is implicit)
+  double *aux;             // [4][S] rho, ux, uy, uz (written when write_aux)
+  const double *omega;     // per-element omega or nullptr (uniform)
+  const int32_t *list;     // optional element list (0-based) or nullptr
+  const uint32_t *skip;    // optional bitmask (1 bit / element): skip when set
+  long long S;
+  int first;               // first element (0-based) of the contiguous range
+  int count;               // number of elements (range) or list entries
+  int write_aux;
+  RelaxParams rp;
+};
+
+int launchSweep(int QQ, int relax, int kind, const SweepArgs &a, cudaStream_t st);
+
+// layout conversion
+int launchAosToSoa(const double *aos, double *soa, int nComp, int nElems, long long S,
+                   cudaStream_t st);
+int launchSoaToAos(const double *soa, double *aos, int nComp, int nElems, long long S,
+                   cudaStream_t st);
+// neigh (Fortran positions, NGPOS layout) -> encoded device list; *bad counts entries
+// that are neither plain pulls nor bounce-backs
+int launchEncodeNeigh(int QQ, const int32_t *neigh, uint32_t *nbr, int nSize, int nElems,
+                      long long S, int *bad, cudaStream_t st);
+int launchDecodeNeigh(int QQ, const uint32_t *nbr, int32_t *neigh, int nSize, int nElems,
+                      long long S, cudaStream_t st);
+
+// boundary kernels
+int launchFillBcBuffer(int QQ, const double *state, long long S, const int32_t *bcElems,
+                       int nBcElems, double *bcBuffer, cudaStream_t st);
+int launchVelocityBounceBack(int QQ, int incomp, double *state, long long S,
+                             const double *bcBuffer, int nLinks, const int32_t *links,
+                             const int32_t *outPos, const int32_t *posInBuffer,
+                             const int32_t *iDir, const double *velLat, cudaStream_t st);
+
+// halo exchange pack / unpack (positions are Fortran AOS state positions)
+int launchPack(int QQ, const double *state, long long S, const int32_t *pos, int n, double *buf,
+               cudaStream_t st);
+int launchUnpack(int QQ, double *state, long long S, const int32_t *pos, int n, const double *buf,
+                 cudaStream_t st);
+
+// reductions: out[0] = total mass, out[1] = max |u|^2, out[2] = nan count
+int launchReduce(int QQ, const double *state, long long S, int nFluid, double *scratch,
+                 double *out, cudaStream_t st);
+
+}  // namespace musb200

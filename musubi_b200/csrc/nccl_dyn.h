@@ -1,0 +1,38 @@
+// nccl_dyn.h -- NCCL entry points resolved with dlopen at musb200_init time, so
+// that libmusb200.so loads on hosts without NCCL (single-GPU runs, CPU-only
+// build checks).  Only the stable subset of the API is used (NCCL >= 2.7).
+// The halo exchange replaces comm_isend_irecv_real
+// (tem/source/tem_comm_module.fpp:549-646): MPI_Isend/Irecv/Waitall become
+// ncclSend/ncclRecv inside one group on a CUDA stream.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+
+namespace musb200 {
+
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef enum { ncclSuccess = 0 } ncclResult_t;
+typedef enum { ncclInt8 = 0, ncclChar = 0, ncclUint8 = 1, ncclInt32 = 2, ncclInt = 2,
+               ncclUint32 = 3, ncclInt64 = 4, ncclUint64 = 5, ncclFloat16 = 6, ncclHalf = 6,
+               ncclFloat32 = 7, ncclFloat = 7, ncclFloat64 = 8, ncclDouble = 8 } ncclDataType_t;
+typedef enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3 } ncclRedOp_t;
+
+struct NcclApi {
+  void *handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+// returns nullptr (and sets lastError) when libnccl cannot be loaded
+NcclApi *ncclApi();
+
+}  // namespace musb200

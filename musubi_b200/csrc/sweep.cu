@@ -1,0 +1,102 @@
+// sweep.cu -- the fused per-level sweep: pull-stream through the encoded
+// neighbour list, pre-collision moments (the reference's separate
+// mus_calcAuxField pass, mus_auxFieldVar_module.fpp:605-817), relaxation
+// parameter (mus_update_relaxParamKine) and collision, one pass over HBM.
+//
+// Replaces the pointee of scheme%compute (kernel interface,
+// mus/source/scheme/mus_scheme_type_module.f90:204-235) plus steps 5-7 of
+// do_fast_singleLevel (mus/source/mus_control_module.f90:564-617).
+//
+// Data layout: SoA, f[q][e] = state[q*S + e]; one thread per element, so every
+// store and the rest-direction load are fully coalesced 8-byte accesses; the
+// QQ-1 pulls go through the 4-byte encoded neighbour list (coalesced) and gather
+// from the source rows (Morton order keeps them within a few sectors per warp).
+// Algorithmic HBM traffic per lattice update: 2*QQ*8 B (PDF read + write) +
+// (QQ-1)*4 B (neighbour list) = 376 B (D3Q19) / 536 B (D3Q27).
+#include "kernels.cuh"
+
+namespace musb200 {
+
+template <int QQ, int RELAX, bool INCOMP>
+__global__ void __launch_bounds__(256) sweepKernel(const SweepArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.count) return;
+  int e;
+  if (a.list != nullptr) {
+    e = a.list[i];
+  } else {
+    e = a.first + i;
+    if (a.skip != nullptr && ((a.skip[e >> 5] >> (e & 31)) & 1u)) return;
+  }
+  const long long S = a.S;
+
+  double f[QQ];
+  {
+    uint32_t n[QQ - 1];
+#pragma unroll
+    for (int q = 0; q < QQ - 1; ++q) n[q] = __ldcs(a.nbr + q * S + e);
+#pragma unroll
+    for (int q = 0; q < QQ - 1; ++q) {
+      const long long row = (n[q] & kBounceBit) ? (long long)invDir<QQ>(q) * S : (long long)q * S;
+      f[q] = __ldg(a.in + row + (n[q] & kElemMask));
+    }
+    f[QQ - 1] = __ldg(a.in + (long long)(QQ - 1) * S + e);
+  }
+
+  double rho, ux, uy, uz;
+  moments<QQ>(f, rho, ux, uy, uz);
+  if (!INCOMP) {
+    ux = ux / rho;
+    uy = uy / rho;
+    uz = uz / rho;
+  }
+  if (a.write_aux) {
+    __stcs(a.aux + e, rho);
+    __stcs(a.aux + S + e, ux);
+    __stcs(a.aux + 2 * S + e, uy);
+    __stcs(a.aux + 3 * S + e, uz);
+  }
+  const double omega = (a.omega != nullptr) ? __ldcs(a.omega + e) : a.rp.omega_uniform;
+
+  double *out = a.out + e;
+  auto st = [&](int q, double v) { __stcs(out + (long long)q * S, v); };
+  if (QQ == 19) {
+    const double(&g)[19] = reinterpret_cast<const double(&)[19]>(f);
+    if (RELAX == 0) collide_bgk_d3q19<INCOMP>(g, rho, ux, uy, uz, omega, st);
+    if (RELAX == 1) collide_trt_d3q19(g, rho, ux, uy, uz, omega, a.rp.lambda, st);
+    if (RELAX == 2) collide_mrt_d3q19(g, rho, ux, uy, uz, omega, a.rp.omega_bulk, st);
+  } else {
+    const double(&g)[27] = reinterpret_cast<const double(&)[27]>(f);
+    if (RELAX == 0) collide_bgk_d3q27(g, rho, ux, uy, uz, omega, st);
+    if (RELAX == 1) collide_trt_d3q27(g, rho, ux, uy, uz, omega, a.rp.lambda, st);
+    if (RELAX == 2) collide_mrt_d3q27(g, rho, ux, uy, uz, omega, a.rp.omega_bulk, st);
+  }
+}
+
+template <int QQ, int RELAX, bool INCOMP>
+static int launchT(const SweepArgs &a, cudaStream_t st) {
+  if (a.count <= 0) return 0;
+  const int block = 256;
+  sweepKernel<QQ, RELAX, INCOMP><<<divUp(a.count, block), block, 0, st>>>(a);
+  MUSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launchSweep(int QQ, int relax, int kind, const SweepArgs &a, cudaStream_t st) {
+  if (kind == 1) {
+    if (QQ == 19 && relax == 0) return launchT<19, 0, true>(a, st);
+    return setError(4, "fluid_incompressible: only bgk/d3q19 is built (others are a 'next' row)");
+  }
+  if (QQ == 19) {
+    if (relax == 0) return launchT<19, 0, false>(a, st);
+    if (relax == 1) return launchT<19, 1, false>(a, st);
+    if (relax == 2) return launchT<19, 2, false>(a, st);
+  } else if (QQ == 27) {
+    if (relax == 0) return launchT<27, 0, false>(a, st);
+    if (relax == 1) return launchT<27, 1, false>(a, st);
+    if (relax == 2) return launchT<27, 2, false>(a, st);
+  }
+  return setError(4, "no kernel for this (layout, relaxation)");
+}
+
+}  // namespace musb200

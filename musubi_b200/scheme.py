@@ -1,0 +1,178 @@
+"""Host-side mirror of the reference's plugin surface for the per-level time
+step, above the C ABI:
+
+  identify{kind, relaxation, layout}  -> scheme%compute pointee
+        (mus_init_advRel_fluid, mus/source/init/mus_initFluid_module.f90:102-409)
+  mus_scheme_type%{state, pdf, auxField, levelDesc}
+        (mus/source/scheme/mus_scheme_type_module.f90:88-180)
+  control%do_computation(minLevel)
+        (mus/source/mus_control_module.f90:149-221)
+
+All arithmetic runs in libmusb200.so on the GPU; this module only moves the
+host arrays through the C ABI, as the Fortran shim does.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import P_DBL, P_I32, P_I64, check, lib, ptr
+
+BC_KIND = {"wall": 0, "velocity_bounceback": 1, "pressure_antibounceback": 2, "pressure_expol": 3}
+_initialized = False
+
+
+def mus_init(rank=0, nranks=1, device=None, unique_id=None):
+    """binds this process to one GPU (tem_start analogue for the device side)."""
+    global _initialized
+    if _initialized:
+        return
+    if device is None:
+        device = rank
+    uid = None
+    if nranks > 1:
+        if unique_id is None:
+            raise ValueError("nranks > 1 needs the NCCL unique id")
+        uid = ctypes.c_char_p(bytes(unique_id))
+    check(lib.musb200_init(rank, nranks, device, uid))
+    _initialized = True
+
+
+def mus_finalize():
+    global _initialized
+    check(lib.musb200_finalize())
+    _initialized = False
+
+
+def get_unique_id():
+    buf = ctypes.create_string_buffer(128)
+    check(lib.musb200_get_unique_id(buf))
+    return buf.raw
+
+
+def select_kernel(identify):
+    """mus_init_advRel_fluid: the (kind, relaxation, variant, layout) dispatch."""
+    rel = identify.get("relaxation", "bgk")
+    variant = "standard"
+    if isinstance(rel, dict):
+        variant = rel.get("variant", "standard")
+        rel = rel.get("name", "bgk")
+    relax, kind, QQ = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    check(lib.musb200_scheme_select(identify.get("kind", "fluid").encode(), rel.encode(),
+                                    variant.encode(), identify.get("layout", "d3q19").encode(),
+                                    ctypes.byref(relax), ctypes.byref(kind), ctypes.byref(QQ)))
+    return relax.value, kind.value, QQ.value
+
+
+class Scheme:
+    """mus_scheme_type for one level range on one rank, device resident."""
+
+    def __init__(self, identify, levelDescs, omega, lambda_=0.25, omega_bulk=None):
+        self.relax, self.kind, self.QQ = select_kernel(identify)
+        if not isinstance(levelDescs, dict):
+            levelDescs = {levelDescs.level: levelDescs}
+        self.levelDesc = levelDescs
+        self.minLevel, self.maxLevel = min(levelDescs), max(levelDescs)
+        self.lambda_ = lambda_
+        for lvl, ld in levelDescs.items():
+            if ld.QQ != self.QQ:
+                raise ValueError("levelDesc built for another stencil")
+            check(lib.musb200_level_create(lvl, self.QQ, self.QQ, 4, ld.nSize, ld.nFluid,
+                                           ld.nGhostFromCoarser, ld.nGhostFromFiner, ld.nHalo,
+                                           ptr(ld.neigh, P_I32), ptr(ld.property, P_I64),
+                                           ptr(ld.total, P_I64)))
+            om = omega[lvl] if isinstance(omega, dict) else omega
+            ob = omega_bulk if omega_bulk is not None else (om if np.isscalar(om) else 1.0)
+            self.set_relaxation(lvl, om, ob)
+            if len(ld.bc_elemBuffer):
+                check(lib.musb200_bc_elembuffer(lvl, len(ld.bc_elemBuffer), ptr(ld.bc_elemBuffer, P_I32)))
+            for bc in ld.bc:
+                check(lib.musb200_bc_register(lvl, bc["id"], BC_KIND[bc["kind"]], len(bc["links"]),
+                                              ptr(bc["links"], P_I32), ptr(bc["outPos"], P_I32),
+                                              ptr(bc["posInBuffer"], P_I32), ptr(bc["iDir"], P_I32)))
+            for d, lists in ((0, ld.send), (1, ld.recv)):
+                if not lists:
+                    continue
+                proc = np.array([c["proc"] for c in lists], dtype=np.int32)
+                nVals = np.array([len(c["pos"]) for c in lists], dtype=np.int32)
+                pos = np.concatenate([c["pos"] for c in lists]).astype(np.int32)
+                check(lib.musb200_comm_register(lvl, 0, d, len(lists), ptr(proc, P_I32),
+                                                ptr(nVals, P_I32), ptr(pos, P_I32)))
+
+    # -- fluid%viscKine%omLvl / lambda / omegaBulkLvl ------------------------
+    def set_relaxation(self, level, omega, omega_bulk):
+        if np.isscalar(omega):
+            check(lib.musb200_set_relaxation(level, self.relax, self.kind, None, float(omega),
+                                             float(self.lambda_), float(omega_bulk)))
+        else:
+            om = np.ascontiguousarray(omega, dtype=np.float64)
+            check(lib.musb200_set_relaxation(level, self.relax, self.kind, ptr(om, P_DBL), 0.0,
+                                             float(self.lambda_), float(omega_bulk)))
+
+    # -- state(level)%val(:, 1:2), AOS, host layout ---------------------------
+    def upload_state(self, level, aos_now, aos_next=None, nNow=1, nNext=2):
+        a = np.ascontiguousarray(aos_now, dtype=np.float64)
+        check(lib.musb200_state_upload(level, nNow, a.ctypes.data))
+        b = a if aos_next is None else np.ascontiguousarray(aos_next, dtype=np.float64)
+        check(lib.musb200_state_upload(level, nNext, b.ctypes.data))
+        check(lib.musb200_set_now_next(level, nNow, nNext))
+
+    def now_next(self, level):
+        a, b = ctypes.c_int(), ctypes.c_int()
+        check(lib.musb200_get_now_next(level, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def download_state(self, level, which=None):
+        ld = self.levelDesc[level]
+        out = np.empty(ld.nSize * self.QQ)
+        if which is None:
+            which = self.now_next(level)[1]
+        check(lib.musb200_state_download(level, which, out.ctypes.data))
+        return out
+
+    def download_aux(self, level):
+        out = np.empty(self.levelDesc[level].nSize * 4)
+        check(lib.musb200_aux_download(level, out.ctypes.data))
+        return out
+
+    def download_neigh(self, level):
+        ld = self.levelDesc[level]
+        out = np.zeros(ld.nSize * self.QQ, dtype=np.int32)
+        check(lib.musb200_neigh_download(level, ptr(out, P_I32)))
+        return out
+
+    def set_bc_values(self, level, bc_id, vals):
+        v = np.ascontiguousarray(vals, dtype=np.float64)
+        check(lib.musb200_bc_set_values(level, bc_id, v.size, v.ctypes.data))
+
+    # -- control%do_computation ----------------------------------------------
+    def do_computation(self, nCycles=1):
+        check(lib.musb200_step(self.minLevel, self.maxLevel, int(nCycles)))
+
+    def synchronize(self):
+        check(lib.musb200_synchronize())
+
+    def reduce(self, level=None):
+        level = self.minLevel if level is None else level
+        m, v, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
+        check(lib.musb200_reduce(level, ctypes.byref(m), ctypes.byref(v), ctypes.byref(n)))
+        return m.value, v.value, n.value
+
+    def destroy(self):
+        for lvl in list(self.levelDesc):
+            lib.musb200_level_destroy(lvl)
+
+
+def compute_host(identify, inState, neigh, nElems, nSolve, omega, lambda_=0.25, omega_bulk=1.0):
+    """strict drop-in of the `kernel` interface with host arrays
+    (mus_scheme_type_module.f90:204-235); returns (outState, auxField)."""
+    relax, kind, QQ = select_kernel(identify)
+    a = np.ascontiguousarray(inState, dtype=np.float64)
+    out = np.zeros_like(a)
+    aux = np.zeros(nElems * 4)
+    om = np.ascontiguousarray(omega, dtype=np.float64)
+    ng = np.ascontiguousarray(neigh, dtype=np.int32)
+    check(lib.musb200_compute_host(relax, kind, QQ, ptr(a, P_DBL), ptr(out, P_DBL), ptr(aux, P_DBL),
+                                   ptr(ng, P_I32), int(nElems), int(nSolve), ptr(om, P_DBL),
+                                   float(lambda_), float(omega_bulk)))
+    return out, aux

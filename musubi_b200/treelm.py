@@ -1,0 +1,82 @@
+"""Host-side level descriptor of a single-level box mesh, produced by the C++
+generator (csrc/host/treelm_box.cpp).  The attribute names follow the
+reference's tem_levelDesc_type / pdf_data_type / boundary_type members so that
+what is handed to libmusb200 reads like what the Fortran shim hands over."""
+import numpy as np
+
+from . import _lib
+from ._lib import P_I32, P_I64, P_DBL, mesh, ptr
+
+KIND = {"periodic": 0, "cavity": 1}
+
+
+class LevelDesc:
+    """tem_levelDesc_type + pdf_data_type of one level on one rank."""
+
+    def __init__(self, level, QQ, kind="periodic", rank=0, nranks=1, comm_reduced=True):
+        h = mesh.musb200_mesh_box_create(level, QQ, KIND[kind], rank, nranks, 1 if comm_reduced else 0)
+        if not h:
+            raise ValueError("bad box-mesh parameters")
+        try:
+            info = np.zeros(16, dtype=np.int64)
+            mesh.musb200_mesh_info(h, ptr(info, P_I64))
+            (self.nFluid, self.nHalo, self.nElems, self.nSize, nBcE, nBc, nRp, nSp, nRv, nSv, nRe,
+             nSe) = [int(v) for v in info[:12]]
+            self.level, self.QQ, self.kind, self.rank, self.nranks = level, QQ, kind, rank, nranks
+            self.nGhostFromCoarser = self.nGhostFromFiner = 0
+            self.nSolve = self.nFluid
+            self.total = np.zeros(self.nElems, dtype=np.int64)
+            self.property = np.zeros(self.nElems, dtype=np.int64)
+            self.nghElems = np.zeros((self.nElems, QQ - 1), dtype=np.int32)
+            self.neigh = np.zeros(QQ * self.nSize, dtype=np.int32)
+            mesh.musb200_mesh_total(h, ptr(self.total, P_I64))
+            mesh.musb200_mesh_property(h, ptr(self.property, P_I64))
+            mesh.musb200_mesh_nghelems(h, ptr(self.nghElems, P_I32))
+            mesh.musb200_mesh_neigh(h, ptr(self.neigh, P_I32))
+            self.bc_elemBuffer = np.zeros(nBcE, dtype=np.int32)
+            mesh.musb200_mesh_bc_elembuffer(h, ptr(self.bc_elemBuffer, P_I32))
+            self.recv, self.send = [], []
+            for d, (np_, nv, ne, out) in enumerate(((nSp, nSv, nSe, self.send), (nRp, nRv, nRe, self.recv))):
+                proc = np.zeros(np_, dtype=np.int32)
+                nVals = np.zeros(np_, dtype=np.int32)
+                pos = np.zeros(nv, dtype=np.int32)
+                ecnt = np.zeros(np_, dtype=np.int32)
+                epos = np.zeros(ne, dtype=np.int32)
+                mesh.musb200_mesh_comm(h, d, ptr(proc, P_I32), ptr(nVals, P_I32), ptr(pos, P_I32),
+                                       ptr(ecnt, P_I32), ptr(epos, P_I32))
+                o = oe = 0
+                for i in range(np_):
+                    out.append(dict(proc=int(proc[i]), pos=pos[o:o + nVals[i]].copy(),
+                                    elemPos=epos[oe:oe + ecnt[i]].copy()))
+                    o += int(nVals[i])
+                    oe += int(ecnt[i])
+            self.bc = []
+            for i in range(nBc):
+                sz = np.zeros(4, dtype=np.int32)
+                mesh.musb200_mesh_bc_info(h, i, ptr(sz, P_I32))
+                bc = dict(id=int(sz[0]), kind=("wall", "velocity_bounceback")[int(sz[1])],
+                          label=("wall", "lid")[int(sz[1])],
+                          elems=np.zeros(sz[2], dtype=np.int32), links=np.zeros(sz[3], dtype=np.int32),
+                          outPos=np.zeros(sz[3], dtype=np.int32),
+                          posInBuffer=np.zeros(sz[3], dtype=np.int32),
+                          iDir=np.zeros(sz[3], dtype=np.int32))
+                mesh.musb200_mesh_bc_lists(h, i, ptr(bc["elems"], P_I32), ptr(bc["links"], P_I32),
+                                           ptr(bc["outPos"], P_I32), ptr(bc["posInBuffer"], P_I32),
+                                           ptr(bc["iDir"], P_I32))
+                self.bc.append(bc)
+            self._bary_args = None
+            self._h_for_bary = None
+        finally:
+            self._handle = h
+
+    def barycenters(self, origin=(0.0, 0.0, 0.0), length=1.0):
+        out = np.zeros((self.nElems, 3))
+        mesh.musb200_mesh_bary(self._handle, float(origin[0]), float(origin[1]), float(origin[2]),
+                               float(length), ptr(out, P_DBL))
+        return out
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h:
+            mesh.musb200_mesh_destroy(h)
+            self._handle = None

@@ -1,0 +1,30 @@
+"""shared set-up of parity cases: the oracle scheme and the device scheme fed
+with identical inputs."""
+import numpy as np
+
+
+def make_pair(mb, mo, level, ident, omega, kind="periodic", rank=0, nranks=1, lambda_=0.25,
+              omega_bulk=None, ic="tgv", u_lid=(0.05, 0.02, 0.0)):
+    from musubi_b200 import cases
+    QQ = 19 if ident["layout"] == "d3q19" else 27
+    ld = mb.LevelDesc(level, QQ, kind, rank, nranks)
+    old = mo.build_level_desc(level, QQ, kind, rank, nranks)
+    ob = omega if omega_bulk is None else omega_bulk
+    ref = mo.Scheme(old, ident["relaxation"], ident["kind"], omega=omega, lambda_=lambda_, omega_bulk=ob)
+    if ic == "tgv":
+        rho, vel = cases.taylor_green(ld, mean=(0.01, -0.02, 0.015))
+    else:
+        rho, vel = cases.cavity_rest(ld)
+    ref.init_equilibrium(rho, vel)
+    sch = mb.Scheme(ident, ld, omega, lambda_=lambda_, omega_bulk=ob)
+    sch.upload_state(level, ref.state[ref.nNow], ref.state[ref.nNext])
+    if kind == "cavity":
+        v = cases.lid_values(ld, u_lid)
+        ref.bc_vel[2] = v
+        sch.set_bc_values(level, 2, v)
+    return ld, old, ref, sch
+
+
+def rel_diff(got, exp):
+    den = np.maximum(np.abs(exp), 1e-300)
+    return float(np.max(np.abs(got - exp) / den))
