@@ -164,7 +164,7 @@ def run_reference(args, wl_name, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="musb200", choices=["musb200", "reference"])
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS))

@@ -16,7 +16,10 @@ def make_pair(mb, mo, level, ident, omega, kind="periodic", rank=0, nranks=1, la
     else:
         rho, vel = cases.cavity_rest(ld)
     ref.init_equilibrium(rho, vel)
-    sch = mb.Scheme(ident, ld, omega, lambda_=lambda_, omega_bulk=ob)
+    # the reference derives omega from the lattice viscosity every step
+    # (mus_update_relaxParamKine): hand the device exactly that value
+    omega_eff = float(1.0 / (3.0 * ref.visc[0] + 0.5))
+    sch = mb.Scheme(ident, ld, omega_eff, lambda_=lambda_, omega_bulk=ob)
     sch.upload_state(level, ref.state[ref.nNow], ref.state[ref.nNext])
     if kind == "cavity":
         v = cases.lid_values(ld, u_lid)

@@ -36,7 +36,7 @@ def test_periodic_tgv_matches_oracle(mb, oracle, ident, omega):
     QQ = ld.QQ
     m0, _, nan0 = sch.reduce()
     assert nan0 == 0
-    assert abs(m0 / ref.total_mass() - 1.0) < 1e-14
+    assert abs(m0 / ref.total_mass() - 1.0) < 1e-12   # different (tree) summation order
     sch.do_computation(nsteps)
     ref.run(nsteps)
     got = sch.download_state(level)
