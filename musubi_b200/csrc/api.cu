@@ -124,6 +124,9 @@ struct Level {
   DevBuf<double> state[2], aux, omega, bcBuffer;
   DevBuf<uint32_t> nbr;
   DevBuf<int32_t> bcElems;
+  std::vector<int32_t> bcElemsHost;
+  std::vector<char> bcSlotNeeded;   // bcBuffer slots read by a non-wall boundary
+  DevBuf<int32_t> bcNeeded;         // those slots (1-based), compact
   int relax = 0, kind = 0;
   bool relaxSet = false, elemOmega = false;
   RelaxParams rp{1.0, 0.25, 1.0};
@@ -205,7 +208,9 @@ static int setBoundary(Level &L) {
   bool any = false;
   for (auto &b : L.bcs) any = any || (b->kind != MUSB200_BC_WALL && b->nLinks > 0);
   if (!any) return 0;
-  MUSB_TRY(launchFillBcBuffer(L.QQ, st, L.S, L.bcElems.p, (int)L.bcElems.n, L.bcBuffer.p, g.stream));
+  // fill_bcBuffer restricted to the slots a non-wall boundary reads (walls are do_nothing)
+  MUSB_TRY(launchFillBcBuffer(L.QQ, st, L.S, L.bcElems.p, L.bcNeeded.p, (int)L.bcNeeded.n, L.bcBuffer.p,
+                              g.stream));
   ++g.launches;
   for (auto &b : L.bcs) {
     if (b->kind == MUSB200_BC_WALL || b->nLinks == 0) continue;
@@ -582,7 +587,10 @@ int musb200_bc_elembuffer(int level, int nBcElems, const int32_t *bc_elemBuffer)
   GET_LEVEL(L, level);
   if (nBcElems < 0 || (nBcElems > 0 && !bc_elemBuffer)) return setError(MUSB200_ERR_ARG, "bad BC element buffer");
   MUSB_TRY(L->bcElems.upload(bc_elemBuffer, (size_t)nBcElems, g.stream));
+  L->bcElemsHost.assign(bc_elemBuffer, bc_elemBuffer + nBcElems);
+  L->bcSlotNeeded.assign((size_t)nBcElems, 0);
   MUSB_TRY(L->bcBuffer.alloc((size_t)std::max(1, nBcElems) * L->QQ));
+  MUSB_CUDA(cudaMemsetAsync(L->bcBuffer.p, 0, L->bcBuffer.n * sizeof(double), g.stream));
   return 0;
 }
 
@@ -601,6 +609,18 @@ int musb200_bc_register(int level, int bc_id, int bc_kind, int nLinks, const int
     MUSB_TRY(b->outPos.upload(outPos, nLinks, g.stream));
     MUSB_TRY(b->posInBuffer.upload(posInBuffer, nLinks, g.stream));
     MUSB_TRY(b->iDir.upload(iDir, nLinks, g.stream));
+    for (int l = 0; l < nLinks; ++l) {
+      const int pib = posInBuffer[l], op = (outPos[l] - 1) / L->QQ + 1;
+      if (pib < 1 || pib > (int)L->bcSlotNeeded.size() || op < 1 || op > (int)L->bcSlotNeeded.size())
+        return setError(MUSB200_ERR_ARG, "boundary link refers to a slot outside bc_elemBuffer");
+      L->bcSlotNeeded[pib - 1] = 1;
+      L->bcSlotNeeded[op - 1] = 1;
+    }
+    std::vector<int32_t> needed;
+    for (size_t i = 0; i < L->bcSlotNeeded.size(); ++i)
+      if (L->bcSlotNeeded[i]) needed.push_back((int32_t)i + 1);
+    MUSB_TRY(L->bcNeeded.upload(needed.data(), needed.size(), g.stream));
+    MUSB_CUDA(cudaStreamSynchronize(g.stream));
   }
   for (auto &o : L->bcs)
     if (o->id == bc_id) { o = std::move(b); return 0; }

@@ -15,13 +15,17 @@
 namespace musb200 {
 
 __global__ void fillBcBufferKernel(const double *__restrict__ state, long long S, int QQ,
-                                   const int32_t *__restrict__ bcElems, int nBcElems,
+                                   const int32_t *__restrict__ bcElems,
+                                   const int32_t *__restrict__ needed, int nNeeded,
                                    double *__restrict__ bcBuffer) {
+  // thread -> (slot, direction) with the slot index fastest: reads of one direction row
+  // are as contiguous as the boundary surface allows
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nBcElems * QQ) return;
-  const int b = i / QQ, q = i % QQ;
-  const int e = bcElems[b] - 1;
-  bcBuffer[i] = state[(long long)q * S + e];
+  if (i >= nNeeded * QQ) return;
+  const int q = i / nNeeded, k = i % nNeeded;
+  const int slot = needed[k] - 1;
+  const int e = bcElems[slot] - 1;
+  bcBuffer[(long long)slot * QQ + q] = state[(long long)q * S + e];
 }
 
 template <int QQ>
@@ -56,10 +60,10 @@ __global__ void velocityBounceBackKernel(int incomp, double *__restrict__ state,
 }
 
 int launchFillBcBuffer(int QQ, const double *state, long long S, const int32_t *bcElems,
-                       int nBcElems, double *bcBuffer, cudaStream_t st) {
-  if (nBcElems <= 0) return 0;
-  fillBcBufferKernel<<<divUp((long long)nBcElems * QQ, 256), 256, 0, st>>>(state, S, QQ, bcElems,
-                                                                           nBcElems, bcBuffer);
+                       const int32_t *needed, int nNeeded, double *bcBuffer, cudaStream_t st) {
+  if (nNeeded <= 0) return 0;
+  fillBcBufferKernel<<<divUp((long long)nNeeded * QQ, 256), 256, 0, st>>>(state, S, QQ, bcElems, needed,
+                                                                          nNeeded, bcBuffer);
   MUSB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -37,7 +37,7 @@ int launchDecodeNeigh(int QQ, const uint32_t *nbr, int32_t *neigh, int nSize, in
 
 // boundary kernels
 int launchFillBcBuffer(int QQ, const double *state, long long S, const int32_t *bcElems,
-                       int nBcElems, double *bcBuffer, cudaStream_t st);
+                       const int32_t *needed, int nNeeded, double *bcBuffer, cudaStream_t st);
 int launchVelocityBounceBack(int QQ, int incomp, double *state, long long S,
                              const double *bcBuffer, int nLinks, const int32_t *links,
                              const int32_t *outPos, const int32_t *posInBuffer,
