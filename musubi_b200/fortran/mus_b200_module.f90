@@ -1,0 +1,372 @@
+!> mus_b200_module -- ISO_C_BINDING shim between Musubi's plugin surface and
+!! libmusb200.so (include/musb200.h).
+!!
+!! NOT compiled in this repository's image (no Fortran compiler / MPI / CoCo);
+!! delivered as the source a maintainer adds to mus/source/ (see INTEGRATION.md
+!! for the three registration hunks).  Every routine conforms to one of the
+!! reference's abstract interfaces and only unwraps derived types into the raw
+!! arrays the C ABI takes:
+!!
+!!   mus_b200_compute      kernel interface      mus_scheme_type_module.f90:204-235
+!!   do_b200               control routine       mus_control_module.f90:149-221
+!!   mus_b200_upload/...   hand-over of state    mus_construction_module.fpp:500-660
+!!
+!! State ownership: after mus_b200_upload the device copy is authoritative;
+!! state/auxField on the host are stale mirrors refreshed by mus_b200_download
+!! at tracking / restart / check intervals.
+module mus_b200_module
+  use, intrinsic :: iso_c_binding
+
+  use env_module,               only: rk, long_k
+  use tem_aux_module,           only: tem_abort
+  use tem_logging_module,       only: logUnit
+  use tem_construction_module,  only: tem_levelDesc_type
+  use tem_comm_module,          only: tem_communication_type
+  use mus_scheme_type_module,   only: mus_scheme_type
+  use mus_param_module,         only: mus_param_type
+  use mus_pdf_module,           only: pdf_data_type
+
+  implicit none
+  private
+
+  public :: mus_b200_init, mus_b200_finalize
+  public :: mus_b200_upload, mus_b200_download
+  public :: mus_b200_step, mus_b200_compute
+  public :: mus_b200_check
+
+  integer(c_int), parameter :: buf_halo = 0, buf_fromCoarser = 1, buf_fromFiner = 2
+  integer(c_int), parameter :: dir_send = 0, dir_recv = 1
+
+  interface
+    function musb200_init(rank, nranks, device, id) bind(C, name='musb200_init') result(rc)
+      import :: c_int, c_ptr
+      integer(c_int), value :: rank, nranks, device
+      type(c_ptr), value :: id
+      integer(c_int) :: rc
+    end function
+    function musb200_get_unique_id(id) bind(C, name='musb200_get_unique_id') result(rc)
+      import :: c_int, c_char
+      character(kind=c_char) :: id(128)
+      integer(c_int) :: rc
+    end function
+    function musb200_finalize() bind(C, name='musb200_finalize') result(rc)
+      import :: c_int
+      integer(c_int) :: rc
+    end function
+    function musb200_last_error(buf, n) bind(C, name='musb200_last_error') result(rc)
+      import :: c_int, c_char
+      character(kind=c_char) :: buf(*)
+      integer(c_int), value :: n
+      integer(c_int) :: rc
+    end function
+    function musb200_scheme_select(kind, relaxation, variant, layout, relax_id, kind_id, QQ) &
+      & bind(C, name='musb200_scheme_select') result(rc)
+      import :: c_int, c_char
+      character(kind=c_char) :: kind(*), relaxation(*), variant(*), layout(*)
+      integer(c_int) :: relax_id, kind_id, QQ
+      integer(c_int) :: rc
+    end function
+    function musb200_level_create(level, QQ, nScalars, nAuxScalars, nSize, nFluid, nGFC, nGFF, &
+      & nHalo, neigh, property, treeID) bind(C, name='musb200_level_create') result(rc)
+      import :: c_int, c_int32_t, c_int64_t
+      integer(c_int), value :: level, QQ, nScalars, nAuxScalars, nSize, nFluid, nGFC, nGFF, nHalo
+      integer(c_int32_t) :: neigh(*)
+      integer(c_int64_t) :: property(*), treeID(*)
+      integer(c_int) :: rc
+    end function
+    function musb200_state_upload(level, which, state) bind(C, name='musb200_state_upload') result(rc)
+      import :: c_int, c_double
+      integer(c_int), value :: level, which
+      real(c_double) :: state(*)
+      integer(c_int) :: rc
+    end function
+    function musb200_state_download(level, which, state) bind(C, name='musb200_state_download') result(rc)
+      import :: c_int, c_double
+      integer(c_int), value :: level, which
+      real(c_double) :: state(*)
+      integer(c_int) :: rc
+    end function
+    function musb200_aux_upload(level, aux) bind(C, name='musb200_aux_upload') result(rc)
+      import :: c_int, c_double
+      integer(c_int), value :: level
+      real(c_double) :: aux(*)
+      integer(c_int) :: rc
+    end function
+    function musb200_aux_download(level, aux) bind(C, name='musb200_aux_download') result(rc)
+      import :: c_int, c_double
+      integer(c_int), value :: level
+      real(c_double) :: aux(*)
+      integer(c_int) :: rc
+    end function
+    function musb200_set_now_next(level, nNow, nNext) bind(C, name='musb200_set_now_next') result(rc)
+      import :: c_int
+      integer(c_int), value :: level, nNow, nNext
+      integer(c_int) :: rc
+    end function
+    function musb200_get_now_next(level, nNow, nNext) bind(C, name='musb200_get_now_next') result(rc)
+      import :: c_int
+      integer(c_int), value :: level
+      integer(c_int) :: nNow, nNext
+      integer(c_int) :: rc
+    end function
+    function musb200_set_relaxation(level, relax_id, kind_id, omega, omega_uniform, lambda, &
+      & omega_bulk) bind(C, name='musb200_set_relaxation') result(rc)
+      import :: c_int, c_double
+      integer(c_int), value :: level, relax_id, kind_id
+      real(c_double) :: omega(*)
+      real(c_double), value :: omega_uniform, lambda, omega_bulk
+      integer(c_int) :: rc
+    end function
+    function musb200_bc_elembuffer(level, n, elems) bind(C, name='musb200_bc_elembuffer') result(rc)
+      import :: c_int, c_int32_t
+      integer(c_int), value :: level, n
+      integer(c_int32_t) :: elems(*)
+      integer(c_int) :: rc
+    end function
+    function musb200_bc_register(level, bc_id, bc_kind, nLinks, links, outPos, posInBuffer, iDir) &
+      & bind(C, name='musb200_bc_register') result(rc)
+      import :: c_int, c_int32_t
+      integer(c_int), value :: level, bc_id, bc_kind, nLinks
+      integer(c_int32_t) :: links(*), outPos(*), posInBuffer(*), iDir(*)
+      integer(c_int) :: rc
+    end function
+    function musb200_bc_set_values(level, bc_id, nVals, vals) bind(C, name='musb200_bc_set_values') result(rc)
+      import :: c_int, c_double
+      integer(c_int), value :: level, bc_id, nVals
+      real(c_double) :: vals(*)
+      integer(c_int) :: rc
+    end function
+    function musb200_comm_register(level, buf_kind, dir, nProcs, proc, nVals, pos) &
+      & bind(C, name='musb200_comm_register') result(rc)
+      import :: c_int, c_int32_t
+      integer(c_int), value :: level, buf_kind, dir, nProcs
+      integer(c_int32_t) :: proc(*), nVals(*), pos(*)
+      integer(c_int) :: rc
+    end function
+    function musb200_step(minLevel, maxLevel, nCycles) bind(C, name='musb200_step') result(rc)
+      import :: c_int
+      integer(c_int), value :: minLevel, maxLevel, nCycles
+      integer(c_int) :: rc
+    end function
+    function musb200_reduce(level, mass, maxvel, anynan) bind(C, name='musb200_reduce') result(rc)
+      import :: c_int, c_double
+      integer(c_int), value :: level
+      real(c_double) :: mass, maxvel
+      integer(c_int) :: anynan
+      integer(c_int) :: rc
+    end function
+    function musb200_compute_host(relax_id, kind_id, QQ, inState, outState, auxField, neigh, &
+      & nElems, nSolve, omega, lambda, omega_bulk) bind(C, name='musb200_compute_host') result(rc)
+      import :: c_int, c_int32_t, c_double
+      integer(c_int), value :: relax_id, kind_id, QQ, nElems, nSolve
+      real(c_double) :: inState(*), outState(*), auxField(*), omega(*)
+      integer(c_int32_t) :: neigh(*)
+      real(c_double), value :: lambda, omega_bulk
+      integer(c_int) :: rc
+    end function
+  end interface
+
+  integer(c_int), save :: relax_id = 0, kind_id = 0, QQ_id = 19
+
+contains
+
+  !> tem_abort with the library's message on a non-zero return code
+  subroutine chk(rc, where)
+    integer(c_int), intent(in) :: rc
+    character(len=*), intent(in) :: where
+    character(kind=c_char) :: buf(512)
+    character(len=512) :: msg
+    integer :: i
+    if (rc == 0) return
+    i = musb200_last_error(buf, 512_c_int)
+    msg = ''
+    do i = 1, 512
+      if (buf(i) == c_null_char) exit
+      msg(i:i) = buf(i)
+    end do
+    call tem_abort('libmusb200 ('//trim(where)//'): '//trim(msg))
+  end subroutine chk
+
+  !> one rank = one GPU; rank 0 creates the NCCL id and broadcasts it with MPI
+  subroutine mus_b200_init(params)
+    use mpi
+    type(mus_param_type), intent(in) :: params
+    character(kind=c_char), target :: id(128)
+    integer :: iError, localComm, localRank
+    if (params%general%proc%rank == 0) call chk(musb200_get_unique_id(id), 'get_unique_id')
+    call mpi_bcast(id, 128, mpi_character, 0, params%general%proc%comm, iError)
+    call mpi_comm_split_type(params%general%proc%comm, mpi_comm_type_shared, 0, mpi_info_null, &
+      &                      localComm, iError)
+    call mpi_comm_rank(localComm, localRank, iError)
+    call chk(musb200_init(int(params%general%proc%rank, c_int),      &
+      &                   int(params%general%proc%comm_size, c_int), &
+      &                   int(localRank, c_int), c_loc(id)), 'init')
+  end subroutine mus_b200_init
+
+  subroutine mus_b200_finalize()
+    call chk(musb200_finalize(), 'finalize')
+  end subroutine mus_b200_finalize
+
+  !> hand pdf(level), levelDesc(level), state, auxField, omega, BC and comm lists over
+  !! (called once after mus_init_flow / mus_init_boundary, mus_program_module.fpp:118-238)
+  subroutine mus_b200_upload(scheme, params, minLevel, maxLevel)
+    type(mus_scheme_type), intent(inout) :: scheme
+    type(mus_param_type), intent(in) :: params
+    integer, intent(in) :: minLevel, maxLevel
+    integer :: iLevel, iBnd, nBCs
+    character(len=64) :: variant
+    variant = trim(scheme%header%relaxHeader%variant)
+    if (variant == 'b200') variant = 'standard'
+    call chk(musb200_scheme_select(trim(scheme%header%kind)//c_null_char,       &
+      &        trim(scheme%header%relaxation)//c_null_char,                      &
+      &        trim(variant)//c_null_char, trim(scheme%header%layout)//c_null_char, &
+      &        relax_id, kind_id, QQ_id), 'scheme_select')
+    do iLevel = minLevel, maxLevel
+      associate(pdf => scheme%pdf(iLevel), ld => scheme%levelDesc(iLevel), &
+        &       fluid => scheme%field(1)%fieldProp%fluid)
+        call chk(musb200_level_create(int(iLevel, c_int), int(QQ_id, c_int),                 &
+          &   int(scheme%varSys%nScalars, c_int), int(scheme%varSys%nAuxScalars, c_int),      &
+          &   int(pdf%nSize, c_int), int(pdf%nElems_fluid, c_int),                            &
+          &   int(pdf%nElems_ghostFromCoarser, c_int), int(pdf%nElems_ghostFromFiner, c_int), &
+          &   int(pdf%nElems_halo, c_int), pdf%neigh, ld%property, ld%total), 'level_create')
+        call chk(musb200_state_upload(int(iLevel, c_int), 1_c_int, scheme%state(iLevel)%val(:,1)), 'state')
+        call chk(musb200_state_upload(int(iLevel, c_int), 2_c_int, scheme%state(iLevel)%val(:,2)), 'state')
+        call chk(musb200_set_now_next(int(iLevel, c_int), int(pdf%nNow, c_int), int(pdf%nNext, c_int)), 'now')
+        call chk(musb200_aux_upload(int(iLevel, c_int), scheme%auxField(iLevel)%val), 'aux')
+        call chk(musb200_set_relaxation(int(iLevel, c_int), relax_id, kind_id,            &
+          &   fluid%viscKine%omLvl(iLevel)%val, 0.0_c_double, real(fluid%lambda, c_double), &
+          &   real(fluid%omegaBulkLvl(iLevel), c_double)), 'relaxation')
+        call upload_comm(iLevel, buf_halo, ld%sendBuffer, ld%recvBuffer)
+        call upload_comm(iLevel, buf_fromCoarser, ld%sendBufferFromCoarser, ld%recvBufferFromCoarser)
+        call upload_comm(iLevel, buf_fromFiner, ld%sendBufferFromFiner, ld%recvBufferFromFiner)
+        if (ld%bc_elemBuffer%nVals > 0) then
+          call chk(musb200_bc_elembuffer(int(iLevel, c_int), int(ld%bc_elemBuffer%nVals, c_int), &
+            &      ld%bc_elemBuffer%val), 'bc_elembuffer')
+        end if
+      end associate
+      nBCs = size(scheme%field(1)%bc)
+      do iBnd = 1, nBCs
+        call upload_bc(scheme, iLevel, iBnd)
+      end do
+    end do
+  end subroutine mus_b200_upload
+
+  subroutine upload_comm(iLevel, bufKind, send, recv)
+    integer, intent(in) :: iLevel
+    integer(c_int), intent(in) :: bufKind
+    type(tem_communication_type), intent(in) :: send, recv
+    call one(send, dir_send)
+    call one(recv, dir_recv)
+  contains
+    subroutine one(c, dir)
+      type(tem_communication_type), intent(in) :: c
+      integer(c_int), intent(in) :: dir
+      integer(c_int32_t), allocatable :: proc(:), nVals(:), pos(:)
+      integer :: iProc, n
+      if (c%nProcs == 0) return
+      allocate(proc(c%nProcs), nVals(c%nProcs))
+      n = 0
+      do iProc = 1, c%nProcs
+        proc(iProc) = c%proc(iProc)
+        nVals(iProc) = c%buf_real(iProc)%nVals
+        n = n + nVals(iProc)
+      end do
+      allocate(pos(n))
+      n = 0
+      do iProc = 1, c%nProcs
+        pos(n+1:n+nVals(iProc)) = c%buf_real(iProc)%pos(1:nVals(iProc))
+        n = n + nVals(iProc)
+      end do
+      call chk(musb200_comm_register(int(iLevel, c_int), bufKind, dir, int(c%nProcs, c_int), &
+        &                            proc, nVals, pos), 'comm_register')
+    end subroutine one
+  end subroutine upload_comm
+
+  subroutine upload_bc(scheme, iLevel, iBnd)
+    type(mus_scheme_type), intent(inout) :: scheme
+    integer, intent(in) :: iLevel, iBnd
+    integer(c_int) :: kind
+    associate(bc => scheme%field(1)%bc(iBnd))
+      select case (trim(bc%BC_kind))
+      case ('wall');                kind = 0
+      case ('velocity_bounceback'); kind = 1
+      case default
+        call tem_abort('boundary kind "'//trim(bc%BC_kind)//'" is outside the B200 hot path')
+      end select
+      if (kind == 0) then
+        call chk(musb200_bc_register(int(iLevel, c_int), int(iBnd, c_int), kind, 0_c_int, &
+          &      bc%links(iLevel)%val, bc%links(iLevel)%val, bc%links(iLevel)%val,        &
+          &      bc%links(iLevel)%val), 'bc_register')
+      else
+        call chk(musb200_bc_register(int(iLevel, c_int), int(iBnd, c_int), kind,            &
+          &      int(bc%links(iLevel)%nVals, c_int), bc%links(iLevel)%val,                   &
+          &      bc%inletUbbQVal(iLevel)%outPos, bc%inletUbbQVal(iLevel)%posInBuffer,        &
+          &      bc%inletUbbQVal(iLevel)%iDir), 'bc_register')
+      end if
+    end associate
+  end subroutine upload_bc
+
+  !> control routine: one C call per coarse cycle instead of steps 1-9 of do_fast_singleLevel
+  !! (registered in mus_init_control for control_routine = 'b200')
+  subroutine mus_b200_step(minLevel, maxLevel, nCycles)
+    integer, intent(in) :: minLevel, maxLevel, nCycles
+    call chk(musb200_step(int(minLevel, c_int), int(maxLevel, c_int), int(nCycles, c_int)), 'step')
+  end subroutine mus_b200_step
+
+  !> refresh the host mirrors (tracking, restart, check_flow_status)
+  subroutine mus_b200_download(scheme, minLevel, maxLevel)
+    type(mus_scheme_type), intent(inout) :: scheme
+    integer, intent(in) :: minLevel, maxLevel
+    integer :: iLevel
+    integer(c_int) :: nNow, nNext
+    do iLevel = minLevel, maxLevel
+      call chk(musb200_get_now_next(int(iLevel, c_int), nNow, nNext), 'now_next')
+      scheme%pdf(iLevel)%nNow = nNow
+      scheme%pdf(iLevel)%nNext = nNext
+      call chk(musb200_state_download(int(iLevel, c_int), nNext, scheme%state(iLevel)%val(:,nNext)), 'state')
+      call chk(musb200_aux_download(int(iLevel, c_int), scheme%auxField(iLevel)%val), 'aux')
+    end do
+  end subroutine mus_b200_download
+
+  !> check_density replacement (mus_tools_module.f90:224-313)
+  subroutine mus_b200_check(iLevel, totalDens, maxVel, hasNaN)
+    integer, intent(in) :: iLevel
+    real(kind=rk), intent(out) :: totalDens, maxVel
+    logical, intent(out) :: hasNaN
+    integer(c_int) :: flag
+    real(c_double) :: m, v
+    call chk(musb200_reduce(int(iLevel, c_int), m, v, flag), 'reduce')
+    totalDens = m; maxVel = v; hasNaN = (flag /= 0)
+  end subroutine mus_b200_check
+
+  !> strict drop-in of the `kernel` interface (host arrays in, host arrays out); registered by
+  !! mus_init_advRel_fluid for relaxation variant 'b200'.  One H2D + kernel + D2H per call:
+  !! meant for verification runs, the production path is control_routine = 'b200'.
+  subroutine mus_b200_compute(fieldProp, inState, outState, auxField, neigh, nElems, &
+    &                         nSolve, level, layout, params, varSys, derVarPos)
+    use mus_field_prop_module,        only: mus_field_prop_type
+    use mus_scheme_layout_module,     only: mus_scheme_layout_type
+    use mus_derVarPos_module,         only: mus_derVarPos_type
+    use tem_varSys_module,            only: tem_varSys_type
+    type(mus_field_prop_type), intent(in) :: fieldProp(:)
+    type(tem_varSys_type), intent(in) :: varSys
+    type(mus_scheme_layout_type), intent(in) :: layout
+    integer, intent(in) :: nElems
+    real(kind=rk), intent(in)  ::  inState(nElems * varSys%nScalars)
+    real(kind=rk), intent(out) :: outState(nElems * varSys%nScalars)
+    real(kind=rk), intent(inout) :: auxField(nElems * varSys%nAuxScalars)
+    integer, intent(in) :: neigh(nElems * layout%fStencil%QQ)
+    integer, intent(in) :: nSolve
+    integer, intent(in) :: level
+    type(mus_param_type), intent(in) :: params
+    type(mus_derVarPos_type), intent(in) :: derVarPos(:)
+    !$omp master
+    call chk(musb200_compute_host(relax_id, kind_id, int(layout%fStencil%QQ, c_int), inState,      &
+      &   outState, auxField, neigh, int(nElems, c_int), int(nSolve, c_int),                        &
+      &   fieldProp(1)%fluid%viscKine%omLvl(level)%val, real(fieldProp(1)%fluid%lambda, c_double), &
+      &   real(fieldProp(1)%fluid%omegaBulkLvl(level), c_double)), 'compute_host')
+    !$omp end master
+    !$omp barrier
+  end subroutine mus_b200_compute
+
+end module mus_b200_module
