@@ -120,6 +120,11 @@ int musb200_state_copy_next_to_now(int level);
 int musb200_set_relaxation(int level, int relax_id, int kind_id, const double *omega,
                            double omega_uniform, double lambda, double omega_bulk);
 
+/* fluid%viscKine%dataOnLvl(level)%val: lattice kinematic viscosity per element (or one
+ * value); read by the ghost interpolation for the non-equilibrium rescaling
+ * (mus_interpolate_average_module.fpp:328-337, mus_interpolate_linear_module.fpp:471-480) */
+int musb200_set_viscosity(int level, const double *visc, double visc_uniform);
+
 /* ---- boundaries: boundary_type + glob_boundary_type per level -------------
  * links      me%links(level)%val            (mus_bc_header_module.fpp:1702-1739)
  * outPos, posInBuffer, iDir: me%inletUbbQVal(level)  (:1876-1967)

@@ -2,7 +2,7 @@
 surface (libmusb200.so, sm_100a).  Host-side mirror of the reference interface
 for this path; see DESIGN.md and INTEGRATION.md."""
 from . import _lib  # noqa: F401  (fails loudly when the CUDA library is missing)
-from .scheme import (Scheme, compute_host, get_unique_id, mus_finalize, mus_init,  # noqa: F401
-                     select_kernel)
+from .scheme import (Scheme, compute_host, get_unique_id, multilevel_tables, mus_finalize,  # noqa: F401
+                     mus_init, select_kernel)
 from .treelm import LevelDesc  # noqa: F401
 from ._lib import Musb200Error  # noqa: F401

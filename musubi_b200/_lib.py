@@ -41,6 +41,7 @@ SIGNATURES = {
     "musb200_aux_probe": [c_int, c_int, P_DBL],
     "musb200_state_copy_next_to_now": [c_int],
     "musb200_set_relaxation": [c_int, c_int, c_int, P_DBL, c_double, c_double, c_double],
+    "musb200_set_viscosity": [c_int, P_DBL, c_double],
     "musb200_bc_elembuffer": [c_int, c_int, P_I32],
     "musb200_bc_register": [c_int, c_int, c_int, c_int, P_I32, P_I32, P_I32, P_I32],
     "musb200_bc_set_values": [c_int, c_int, c_int, c_void_p],

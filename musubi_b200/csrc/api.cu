@@ -121,7 +121,9 @@ struct Level {
   int nElems = 0, nSolve = 0;
   long long S = 0;
   int nNow = 0, nNext = 1;  // 0-based buffer indices
-  DevBuf<double> state[2], aux, omega, bcBuffer;
+  DevBuf<double> state[2], aux, omega, visc, bcBuffer;
+  bool elemVisc = false, viscSet = false;
+  double viscUniform = 0.0;
   DevBuf<uint32_t> nbr;
   DevBuf<int32_t> bcElems;
   std::vector<int32_t> bcElemsHost;
@@ -273,9 +275,7 @@ static int sweep(Level &L, bool writeAux) {
   return 0;
 }
 
-static int applyIntp(Level &src, Level &tgt, IntpSet &set, bool fromFiner) {
-  if (set.nTargets == 0) return 0;
-  Timed t(T_INTP);
+static IntpArgs intpArgs(Level &src, Level &tgt) {
   IntpArgs a{};
   a.QQ = tgt.QQ;
   a.incomp = tgt.kind == MUSB200_KIND_FLUID_INCOMPRESSIBLE;
@@ -283,10 +283,29 @@ static int applyIntp(Level &src, Level &tgt, IntpSet &set, bool fromFiner) {
   a.sAux = src.aux.p;
   a.sS = src.S;
   a.tState = tgt.state[tgt.nNext].p;
+  a.tAux = tgt.aux.p;
   a.tS = tgt.S;
-  a.tOmega = tgt.elemOmega ? tgt.omega.p : nullptr;
-  a.tOmegaUniform = tgt.rp.omega_uniform;
-  MUSB_TRY(launchIntp(a, set, fromFiner, g.stream));
+  a.tVisc = tgt.elemVisc ? tgt.visc.p : nullptr;
+  // fluid%viscKine%dataOnLvl(level): from musb200_set_viscosity, else derived from omega
+  a.tViscUniform = tgt.viscSet ? tgt.viscUniform : (1.0 / tgt.rp.omega_uniform - 0.5) / 3.0;
+  return a;
+}
+
+static int applyIntp(Level &src, Level &tgt, IntpSet &set, bool fromFiner) {
+  if (set.nTargets == 0) return 0;
+  if (!tgt.viscSet && tgt.elemOmega)
+    return setError(MUSB200_ERR_STATE, "per-element omega needs musb200_set_viscosity for interpolation");
+  Timed t(T_INTP);
+  int n = 0;
+  MUSB_TRY(launchIntp(intpArgs(src, tgt), set, fromFiner, g.stream, &n));
+  g.launches += n;
+  return 0;
+}
+
+static int auxFromFiner(Level &fine, Level &coarse) {
+  if (coarse.fromFiner.nTargets == 0) return 0;
+  Timed t(T_INTP);
+  MUSB_TRY(launchAuxFromFiner(intpArgs(fine, coarse), coarse.fromFiner, g.stream));
   ++g.launches;
   return 0;
 }
@@ -304,12 +323,15 @@ static int levelStep(int iLevel, int minLevel, int maxLevel, bool lastCycle) {
   std::swap(L.nNow, L.nNext);
   // multi-level: the interpolation routines read auxField of their sources every step
   const bool writeAux = g.auxEveryStep || multi || lastCycle;
-  if (multi && iLevel < maxLevel) {
-    // aux of my ghostFromFiner elements is interpolated from level+1
-    // (mus_intpAuxFieldCoarserAndExchange, mus_auxField_module.f90:404-444): done inside
-    // the fromFiner state interpolation below, which recomputes what it needs.
-  }
   MUSB_TRY(sweep(L, writeAux));
+  if (iLevel < maxLevel) {
+    // auxField of my ghostFromFiner elements <- average of level+1
+    // (mus_intpAuxFieldCoarserAndExchange, mus_auxField_module.f90:404-444); the sweep does not
+    // touch those entries, so running it after the fused sweep equals the reference's order
+    Level *F = findLevel(iLevel + 1);
+    if (!F) return setError(MUSB200_ERR_ARG, "level " + std::to_string(iLevel + 1) + " was not created");
+    MUSB_TRY(auxFromFiner(*F, L));
+  }
   if (multi && writeAux) MUSB_TRY(exchange(L, MUSB200_BUF_HALO, L.aux.p, 4)); // aux halo (tag level+100)
   MUSB_TRY(exchange(L, MUSB200_BUF_HALO, L.state[L.nNext].p, L.QQ));
   if (iLevel > minLevel) MUSB_TRY(exchange(L, MUSB200_BUF_FROMCOARSER, L.state[L.nNext].p, L.QQ));
@@ -583,6 +605,19 @@ int musb200_set_relaxation(int level, int relax_id, int kind_id, const double *o
 }
 
 // ---------------------------------------------------------------------------
+int musb200_set_viscosity(int level, const double *visc, double visc_uniform) {
+  GET_LEVEL(L, level);
+  L->elemVisc = (visc != nullptr);
+  L->viscUniform = visc_uniform;
+  if (visc) {
+    if (L->visc.n < (size_t)L->S) MUSB_TRY(L->visc.alloc((size_t)L->S));
+    MUSB_CUDA(cudaMemcpyAsync(L->visc.p, visc, (size_t)L->nElems * sizeof(double), cudaMemcpyHostToDevice,
+                              g.stream));
+  }
+  L->viscSet = true;
+  return 0;
+}
+
 int musb200_bc_elembuffer(int level, int nBcElems, const int32_t *bc_elemBuffer) {
   GET_LEVEL(L, level);
   if (nBcElems < 0 || (nBcElems > 0 && !bc_elemBuffer)) return setError(MUSB200_ERR_ARG, "bad BC element buffer");

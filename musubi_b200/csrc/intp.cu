@@ -1,37 +1,240 @@
-// intp.cu -- ghost interpolation kernels (see intp.cuh). Filled in below.
+// intp.cu -- ghost interpolation kernels (see intp.cuh for the reference routines).
 #include "intp.cuh"
+#include "equilibrium.cuh"
+#include <algorithm>
 #include <utility>
 
 namespace musb200 {
 
 void IntpSet::release() {
   auto fr = [](auto *&p) { if (p) cudaFree(p); p = nullptr; };
-  fr(targets); fr(srcOffset); fr(srcPos); fr(weights); fr(posInMat); fr(matOffset);
-  fr(matrices); fr(childCoord);
-  nTargets = 0; nMatrices = 0;
+  fr(targets); fr(srcOffset); fr(srcSlot); fr(uniqueSrc); fr(weights); fr(posInMat); fr(matOffset);
+  fr(matrices); fr(coord); fr(scratch);
+  nTargets = 0; nMatrices = 0; nUnique = 0;
 }
 
 IntpSet &IntpSet::operator=(IntpSet &&o) noexcept {
   if (this != &o) {
     release();
-    order = o.order; nTargets = o.nTargets; nMatrices = o.nMatrices;
-    targets = o.targets; srcOffset = o.srcOffset; srcPos = o.srcPos; weights = o.weights;
-    posInMat = o.posInMat; matOffset = o.matOffset; matrices = o.matrices; childCoord = o.childCoord;
-    o.targets = nullptr; o.srcOffset = nullptr; o.srcPos = nullptr; o.weights = nullptr;
-    o.posInMat = nullptr; o.matOffset = nullptr; o.matrices = nullptr; o.childCoord = nullptr;
-    o.nTargets = 0; o.nMatrices = 0;
+    order = o.order; nTargets = o.nTargets; nMatrices = o.nMatrices; nUnique = o.nUnique;
+    targets = o.targets; srcOffset = o.srcOffset; srcSlot = o.srcSlot; uniqueSrc = o.uniqueSrc;
+    weights = o.weights; posInMat = o.posInMat; matOffset = o.matOffset; matrices = o.matrices;
+    coord = o.coord; scratch = o.scratch;
+    o.targets = nullptr; o.srcOffset = nullptr; o.srcSlot = nullptr; o.uniqueSrc = nullptr;
+    o.weights = nullptr; o.posInMat = nullptr; o.matOffset = nullptr; o.matrices = nullptr;
+    o.coord = nullptr; o.scratch = nullptr;
+    o.nTargets = 0; o.nMatrices = 0; o.nUnique = 0;
   }
   return *this;
 }
 
-int registerIntp(IntpSet &, int, int, const int32_t *, const int32_t *, const int32_t *,
-                 const double *, const int32_t *, int, const int32_t *, const double *,
-                 const double *, cudaStream_t) {
-  return setError(4, "ghost interpolation is not built yet");
+template <class T>
+static int up(T *&dst, const T *src, size_t n, cudaStream_t st) {
+  dst = nullptr;
+  if (n == 0) return 0;
+  MUSB_CUDA(cudaMalloc(&dst, n * sizeof(T)));
+  MUSB_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, st));
+  return 0;
 }
 
-int launchIntp(const IntpArgs &, const IntpSet &, bool, cudaStream_t) {
-  return setError(4, "ghost interpolation is not built yet");
+int registerIntp(IntpSet &set, int order, int nTargets, const int32_t *targetList,
+                 const int32_t *srcOffset, const int32_t *srcPos, const double *weights,
+                 const int32_t *posInMat, int nMatrices, const int32_t *matOffset,
+                 const double *matrices, const double *childCoord, cudaStream_t st) {
+  set.release();
+  set.order = order;
+  if (nTargets == 0) return 0;
+  if (!targetList || !srcOffset || !srcPos) return setError(1, "interpolation lists missing");
+  const int nSrc = srcOffset[nTargets];
+  // distinct sources (sourceFromCoarser of the reference) and the CSR re-expressed in slots
+  std::vector<int32_t> uniq(srcPos, srcPos + nSrc);
+  std::sort(uniq.begin(), uniq.end());
+  uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+  std::vector<int32_t> slot(nSrc);
+  for (int i = 0; i < nSrc; ++i)
+    slot[i] = (int32_t)(std::lower_bound(uniq.begin(), uniq.end(), srcPos[i]) - uniq.begin());
+  for (int i = 0; i < nTargets; ++i)
+    if (srcOffset[i + 1] - srcOffset[i] < 1 || srcOffset[i + 1] - srcOffset[i] > 27)
+      return setError(1, "an interpolation target needs between 1 and 27 sources");
+  int rc = 0;
+  rc |= up(set.targets, targetList, nTargets, st);
+  rc |= up(set.srcOffset, srcOffset, (size_t)nTargets + 1, st);
+  rc |= up(set.srcSlot, slot.data(), (size_t)nSrc, st);
+  rc |= up(set.uniqueSrc, uniq.data(), uniq.size(), st);
+  if (order == 0 && weights) rc |= up(set.weights, weights, (size_t)nSrc, st);
+  if (order > 0) {
+    if (!posInMat || !matOffset || !matrices || !childCoord || nMatrices < 1)
+      return setError(1, "least-square interpolation needs matrices, posInMat and coordinates");
+    rc |= up(set.posInMat, posInMat, nTargets, st);
+    rc |= up(set.matOffset, matOffset, (size_t)nMatrices + 1, st);
+    rc |= up(set.matrices, matrices, (size_t)matOffset[nMatrices], st);
+    rc |= up(set.coord, childCoord, (size_t)3 * nTargets, st);
+  }
+  if (rc) return rc;
+  set.nTargets = nTargets;
+  set.nMatrices = nMatrices;
+  set.nUnique = (int)uniq.size();
+  MUSB_CUDA(cudaMalloc(&set.scratch, (size_t)2 * 27 * set.nUnique * sizeof(double)));
+  MUSB_CUDA(cudaStreamSynchronize(st));  // host vectors go out of scope
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+template <int QQ>
+__global__ void eqNeqKernel(int incomp, const double *__restrict__ sState,
+                            const double *__restrict__ sAux, long long sS,
+                            const int32_t *__restrict__ uniqueSrc, int nUnique,
+                            double *__restrict__ scratch) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= nUnique) return;
+  const int e = uniqueSrc[u] - 1;
+  const double rho = sAux[e], vx = sAux[sS + e], vy = sAux[2 * sS + e], vz = sAux[3 * sS + e];
+  double feq[QQ];
+  if (QQ == 19) {
+    double(&g)[19] = reinterpret_cast<double(&)[19]>(feq);
+    if (incomp) pdfEqIncompD3Q19(rho, vx, vy, vz, g);
+    else pdfEqD3Q19(rho, vx, vy, vz, g);
+  } else {
+    double(&g)[27] = reinterpret_cast<double(&)[27]>(feq);
+    pdfEqD3Q27(rho, vx, vy, vz, g);
+  }
+#pragma unroll
+  for (int q = 0; q < QQ; ++q) {
+    const double f = sState[(long long)q * sS + e];
+    scratch[(long long)q * nUnique + u] = feq[q];
+    scratch[(long long)(27 + q) * nUnique + u] = f - feq[q];
+  }
+}
+
+__device__ __forceinline__ double omegaFromVisc(double v) { return 1.0 / (3.0 * v + 0.5); }
+// getNonEqFac_intp, PULL build (post-collision PDFs), mus_derivedQuantities_module.fpp:601-614
+__device__ __forceinline__ double neqFac(double omegaS, double omegaT) {
+  return omegaS * (1.0 - omegaT) / ((1.0 - omegaS) * omegaT);
+}
+
+// mode 0: average from finer; 1: weighted average; 2: linear; 3: quadratic
+__global__ void intpKernel(int mode, int QQ, const double *__restrict__ scratch, int nUnique,
+                           int nTargets, const int32_t *__restrict__ targets,
+                           const int32_t *__restrict__ srcOffset,
+                           const int32_t *__restrict__ srcSlot, const double *__restrict__ weights,
+                           const int32_t *__restrict__ posInMat,
+                           const int32_t *__restrict__ matOffset,
+                           const double *__restrict__ matrices, const double *__restrict__ coord,
+                           double *__restrict__ tState, long long tS,
+                           const double *__restrict__ tVisc, double tViscUniform) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nTargets * QQ) return;
+  const int i = idx % nTargets, d = idx / nTargets;
+  const int tgt = targets[i] - 1;
+  const int s0 = srcOffset[i], n = srcOffset[i + 1] - s0;
+  const double *eq = scratch + (long long)d * nUnique;
+  const double *neq = scratch + (long long)(27 + d) * nUnique;
+  const double visc = tVisc ? tVisc[tgt] : tViscUniform;
+  double t_eq, t_neq;
+  if (mode == 0) {
+    const double inv_n = 1.0 / (double)n;
+    double a = 0.0, b = 0.0;
+    for (int s = 0; s < n; ++s) {
+      const int u = srcSlot[s0 + s];
+      a = a + eq[u];
+      b = b + neq[u];
+    }
+    const double fOmega = omegaFromVisc(2.0 * visc), cOmega = omegaFromVisc(visc);
+    const double fac = 2.0 * neqFac(fOmega, cOmega);  // getNonEqFac_intp_fine_to_coarse
+    t_eq = a * inv_n;
+    t_neq = b * inv_n * fac;
+    tState[(long long)d * tS + tgt] = t_eq + t_neq;
+    return;
+  }
+  if (mode == 1) {
+    double a = 0.0, b = 0.0;
+    for (int s = 0; s < n; ++s) {
+      const int u = srcSlot[s0 + s];
+      const double w = weights[s0 + s];
+      a = a + w * eq[u];
+      b = b + w * neq[u];
+    }
+    t_eq = a;
+    t_neq = b;
+  } else {
+    const int nCoeff = mode == 2 ? 4 : 10;
+    const double *A = matrices + matOffset[posInMat[i]];
+    const double x = coord[3 * i + 0], y = coord[3 * i + 1], z = coord[3 * i + 2];
+    double ce[10], cn[10];
+    for (int k = 0; k < nCoeff; ++k) {
+      double a = 0.0, b = 0.0;
+      for (int s = 0; s < n; ++s) {
+        const int u = srcSlot[s0 + s];
+        const double m = A[(long long)k * n + s];
+        a = a + m * eq[u];
+        b = b + m * neq[u];
+      }
+      ce[k] = a;
+      cn[k] = b;
+    }
+    t_eq = ce[0] + ce[1] * x + ce[2] * y + ce[3] * z;
+    t_neq = cn[0] + cn[1] * x + cn[2] * y + cn[3] * z;
+    if (mode == 3) {
+      t_eq = t_eq + ce[4] * x * x + ce[5] * y * y + ce[6] * z * z + ce[7] * x * y + ce[8] * y * z +
+             ce[9] * z * x;
+      t_neq = t_neq + cn[4] * x * x + cn[5] * y * y + cn[6] * z * z + cn[7] * x * y + cn[8] * y * z +
+              cn[9] * z * x;
+    }
+  }
+  const double fOmega = omegaFromVisc(visc), cOmega = omegaFromVisc(0.5 * visc);
+  const double fac = 0.5 * neqFac(cOmega, fOmega);  // getNonEqFac_intp_coarse_to_fine
+  t_neq = t_neq * fac;
+  tState[(long long)d * tS + tgt] = t_neq + t_eq;
+}
+
+// fillArbiMyGhostsFromFiner_avg for the 4 auxField scalars
+__global__ void auxFromFinerKernel(const double *__restrict__ sAux, long long sS,
+                                   const int32_t *__restrict__ uniqueSrc, int nTargets,
+                                   const int32_t *__restrict__ targets,
+                                   const int32_t *__restrict__ srcOffset,
+                                   const int32_t *__restrict__ srcSlot, double *__restrict__ tAux,
+                                   long long tS) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nTargets * 4) return;
+  const int i = idx % nTargets, k = idx / nTargets;
+  const int s0 = srcOffset[i], n = srcOffset[i + 1] - s0;
+  const double inv_n = 1.0 / (double)n;
+  double t = 0.0;
+  for (int s = 0; s < n; ++s) {
+    const int e = uniqueSrc[srcSlot[s0 + s]] - 1;
+    t = sAux[(long long)k * sS + e] + t;
+  }
+  tAux[(long long)k * tS + targets[i] - 1] = t * inv_n;
+}
+
+int launchIntp(const IntpArgs &a, const IntpSet &set, bool fromFiner, cudaStream_t st, int *nLaunch) {
+  if (nLaunch) *nLaunch = 0;
+  if (set.nTargets == 0) return 0;
+  const int B = 128;
+  if (a.QQ == 19)
+    eqNeqKernel<19><<<divUp(set.nUnique, B), B, 0, st>>>(a.incomp, a.sState, a.sAux, a.sS,
+                                                         set.uniqueSrc, set.nUnique, set.scratch);
+  else
+    eqNeqKernel<27><<<divUp(set.nUnique, B), B, 0, st>>>(a.incomp, a.sState, a.sAux, a.sS,
+                                                         set.uniqueSrc, set.nUnique, set.scratch);
+  MUSB_CUDA(cudaGetLastError());
+  const int mode = fromFiner ? 0 : 1 + set.order;
+  if (mode == 1 && !set.weights) return setError(1, "weighted-average set without weights");
+  intpKernel<<<divUp((long long)set.nTargets * a.QQ, B), B, 0, st>>>(
+      mode, a.QQ, set.scratch, set.nUnique, set.nTargets, set.targets, set.srcOffset, set.srcSlot,
+      set.weights, set.posInMat, set.matOffset, set.matrices, set.coord, a.tState, a.tS, a.tVisc,
+      a.tViscUniform);
+  MUSB_CUDA(cudaGetLastError());
+  if (nLaunch) *nLaunch = 2;
+  return 0;
+}
+
+int launchAuxFromFiner(const IntpArgs &a, const IntpSet &set, cudaStream_t st) {
+  if (set.nTargets == 0) return 0;
+  auxFromFinerKernel<<<divUp((long long)set.nTargets * 4, 128), 128, 0, st>>>(
+      a.sAux, a.sS, set.uniqueSrc, set.nTargets, set.targets, set.srcOffset, set.srcSlot, a.tAux, a.tS);
+  MUSB_CUDA(cudaGetLastError());
+  return 0;
 }
 
 }  // namespace musb200

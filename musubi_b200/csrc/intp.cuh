@@ -1,9 +1,22 @@
-// intp.cuh -- coarse <-> fine ghost interpolation sets (device side).
-// fillMyGhostsFromFiner_avg_feq_fneq   mus/source/intp/mus_interpolate_average_module.fpp:186-347
-// fillFinerGhostsFromMe_{weighAvg,linear,quad}_feq_fneq
-//     average:854-1038, linear:315-505, quadratic:292-...
+// intp.cuh -- coarse <-> fine ghost interpolation on the device.
+//
+// Replaces the pointees of intp%fillMineFromFiner%do_intp / do_intpArbiVal and
+// intp%fillFinerFromMe(order)%do_intp (mus_interpolate_header_module.f90:103-237):
+//   fillMyGhostsFromFiner_avg_feq_fneq       mus_interpolate_average_module.fpp:186-347
+//   fillArbiMyGhostsFromFiner_avg            mus_interpolate_average_module.fpp:95-185
+//   fillFinerGhostsFromMe_weighAvg_feq_fneq  mus_interpolate_average_module.fpp:854-1038
+//   fillFinerGhostsFromMe_linear_feq_fneq    mus_interpolate_linear_module.fpp:315-505
+//   fillFinerGhostsFromMe_quad_feq_fneq      mus_interpolate_quadratic_module.fpp:292-...
+// The dependency lists, weights and least-square matrices come from the host
+// (levelDesc%depFromFiner / depFromCoarser, intpMat_forLSF) unchanged.
+//
+// Two phases per set, both on the refinement surface only:
+//   A  one thread per distinct source element: f_eq(rho,u from auxField), f_neq = f - f_eq
+//   B  one thread per (target, direction): average / weighted sum / least-square polynomial
+//      over the sources in the host's order, non-equilibrium rescaling, store.
 #pragma once
 #include "common.cuh"
+#include <vector>
 
 namespace musb200 {
 
@@ -11,14 +24,17 @@ struct IntpSet {
   int order = 0;
   int nTargets = 0;
   int nMatrices = 0;
-  int32_t *targets = nullptr;    // [nTargets] 0-based target element
-  int32_t *srcOffset = nullptr;  // [nTargets+1]
-  int32_t *srcPos = nullptr;     // CSR, 0-based source element
-  double *weights = nullptr;     // CSR (average / weighted average)
-  int32_t *posInMat = nullptr;   // [nTargets] matrix index (linear / quadratic)
-  int32_t *matOffset = nullptr;  // [nMatrices+1] offsets into matrices
-  double *matrices = nullptr;    // concatenated (nCoeff x nSrc) row-major LSQ matrices
-  double *childCoord = nullptr;  // [nTargets][3] child offset in coarse units (+-0.25)
+  int nUnique = 0;
+  int32_t *targets = nullptr;    // [nTargets] 1-based position of the target in its total list
+  int32_t *srcOffset = nullptr;  // [nTargets+1] CSR
+  int32_t *srcSlot = nullptr;    // CSR: index into the unique-source scratch
+  int32_t *uniqueSrc = nullptr;  // [nUnique] 1-based source positions
+  double *weights = nullptr;     // CSR (weighted average)
+  int32_t *posInMat = nullptr;   // [nTargets]
+  int32_t *matOffset = nullptr;  // [nMatrices+1]
+  double *matrices = nullptr;    // concatenated row-major (nCoeff x nSrc)
+  double *coord = nullptr;       // [nTargets][3]
+  double *scratch = nullptr;     // [2][QQmax=27][nUnique]  f_eq | f_neq
   void release();
   ~IntpSet() { release(); }
   IntpSet() = default;
@@ -35,15 +51,18 @@ struct IntpArgs {
   const double *sAux;    // source level auxField, SoA [4][sS]
   long long sS;
   double *tState;        // target level state(:, next)
+  double *tAux;          // target level auxField (aux averaging only)
   long long tS;
-  const double *tOmega;  // per-element omega of the target level or nullptr
-  double tOmegaUniform;
+  const double *tVisc;   // per-element lattice viscosity of the target level or nullptr
+  double tViscUniform;
 };
 
 int registerIntp(IntpSet &set, int order, int nTargets, const int32_t *targetList,
                  const int32_t *srcOffset, const int32_t *srcPos, const double *weights,
                  const int32_t *posInMat, int nMatrices, const int32_t *matOffset,
                  const double *matrices, const double *childCoord, cudaStream_t st);
-int launchIntp(const IntpArgs &a, const IntpSet &set, bool fromFiner, cudaStream_t st);
+// returns the number of kernels launched through *nLaunch
+int launchIntp(const IntpArgs &a, const IntpSet &set, bool fromFiner, cudaStream_t st, int *nLaunch);
+int launchAuxFromFiner(const IntpArgs &a, const IntpSet &set, cudaStream_t st);
 
 }  // namespace musb200

@@ -67,7 +67,10 @@ def select_kernel(identify):
 class Scheme:
     """mus_scheme_type for one level range on one rank, device resident."""
 
-    def __init__(self, identify, levelDescs, omega, lambda_=0.25, omega_bulk=None):
+    def __init__(self, identify, levelDescs, omega, lambda_=0.25, omega_bulk=None, intp=None,
+                 viscosity=None):
+        """intp: None or (tables, order) with tables as built by multilevel_tables();
+        viscosity: {level: lattice viscosity} (fluid%viscKine%dataOnLvl) for the interpolation."""
         self.relax, self.kind, self.QQ = select_kernel(identify)
         if not isinstance(levelDescs, dict):
             levelDescs = {levelDescs.level: levelDescs}
@@ -90,6 +93,13 @@ class Scheme:
                 check(lib.musb200_bc_register(lvl, bc["id"], BC_KIND[bc["kind"]], len(bc["links"]),
                                               ptr(bc["links"], P_I32), ptr(bc["outPos"], P_I32),
                                               ptr(bc["posInBuffer"], P_I32), ptr(bc["iDir"], P_I32)))
+            if viscosity is not None:
+                v = viscosity[lvl]
+                if np.isscalar(v):
+                    check(lib.musb200_set_viscosity(lvl, None, float(v)))
+                else:
+                    v = np.ascontiguousarray(v, dtype=np.float64)
+                    check(lib.musb200_set_viscosity(lvl, ptr(v, P_DBL), 0.0))
             for d, lists in ((0, ld.send), (1, ld.recv)):
                 if not lists:
                     continue
@@ -98,6 +108,23 @@ class Scheme:
                 pos = np.concatenate([c["pos"] for c in lists]).astype(np.int32)
                 check(lib.musb200_comm_register(lvl, 0, d, len(lists), ptr(proc, P_I32),
                                                 ptr(nVals, P_I32), ptr(pos, P_I32)))
+
+        if intp is not None:
+            tables, order = intp
+            for (lvl, what), t in tables.items():
+                direction, o = (0, 0) if what == "fromFiner" else (1, what[1])
+                if len(t["targets"]) == 0:
+                    continue
+                coord = np.ascontiguousarray(t["coord"], dtype=np.float64)
+                wts = np.ascontiguousarray(t["weights"], dtype=np.float64)
+                mats = np.ascontiguousarray(t["matrices"], dtype=np.float64)
+                check(lib.musb200_intp_register(
+                    lvl, direction, o, len(t["targets"]), ptr(t["targets"], P_I32),
+                    ptr(t["srcOffset"], P_I32), ptr(t["srcPos"], P_I32),
+                    ptr(wts, P_DBL) if wts.size else None,
+                    ptr(t["posInMat"], P_I32) if len(t["posInMat"]) else None, int(t["nMat"]),
+                    ptr(t["matOffset"], P_I32), ptr(mats, P_DBL) if mats.size else None,
+                    ptr(coord, P_DBL) if coord.size else None))
 
     # -- fluid%viscKine%omLvl / lambda / omegaBulkLvl ------------------------
     def set_relaxation(self, level, omega, omega_bulk):
@@ -176,3 +203,17 @@ def compute_host(identify, inState, neigh, nElems, nSolve, omega, lambda_=0.25, 
                                    ptr(ng, P_I32), int(nElems), int(nSolve), ptr(om, P_DBL),
                                    float(lambda_), float(omega_bulk)))
     return out, aux
+
+
+def multilevel_tables(levels, intp):
+    """flat dependency tables {(level, 'fromFiner' | ('fromCoarser', order)): arrays} of a
+    multi-level mesh (levelDesc%depFromFiner / depFromCoarser / intpFromCoarser(order))."""
+    from . import treelm_multilevel as tm
+    t = {}
+    for lvl, L in levels.items():
+        if L.nGhostFromFiner:
+            t[(lvl, "fromFiner")] = tm.intp_tables(L, intp, "fromFiner")
+        if L.nGhostFromCoarser:
+            for o in range(intp["order"] + 1):
+                t[(lvl, ("fromCoarser", o))] = tm.intp_tables(L, intp, "fromCoarser", o)
+    return t

@@ -1,0 +1,372 @@
+"""Synthetic multi-level treelm meshes (nested refined boxes in a periodic cube,
+optionally with a solid cylinder inside the finest box) and their level
+descriptors, on one rank.
+
+This plays the role Seeder + treelm's tem_find_allElements + mus_construct play
+for the Fortran host: it produces the per-level arrays BOTH the CPU oracle and
+libmusb200 consume (total list, property, nghElems, neigh, ghost dependencies,
+interpolation source lists / weights / least-square matrices).  Rules followed
+(reference file:line):
+
+  * total list per level [fluid | ghostFromCoarser | ghostFromFiner | halo], each
+    block ascending treeID           tem_construction_module.f90:2358-2460
+  * ghosts are created for the stencil neighbours of fluid elements that live on
+    another level, in reqNesting = nNesting + 1 = 3 layers
+                                     mus_construction_module.fpp:310-318
+  * vertical dependencies: parent of a ghostFromCoarser (childNum, coord =
+    0.25*childPosition), the locally present children of a ghostFromFiner
+                                     tem_construction_module.f90:2894-2985
+  * coarse->fine source selection, order fallback, weights, least-square matrices
+                                     mus_interpolate_module.fpp:544-1011,
+                                     mus_interpolate_header_module.f90:405-607,
+                                     tem_matrix_module.fpp:161-425
+  * state connectivity               mus_connectivity_module.fpp:73-179
+All lists are 1-based as in Fortran.
+"""
+import numpy as np
+
+from .cases import _CX27
+
+PRP_FLUID, PRP_SOLID, PRP_HASBND = 1, 2, 3
+NO_INTP, WEIGHTED_AVERAGE, LINEAR, QUADRATIC = -1, 0, 1, 2
+ORDER_OF = {"average": 0, "weighted_average": 0, "linear": 1, "quadratic": 2}
+
+# childPosition(childNum, xyz), tem_param_module.f90:170-173 (Z-curve order)
+CHILD_POSITION = np.array([[-1, -1, -1], [1, -1, -1], [-1, 1, -1], [1, 1, -1],
+                           [-1, -1, 1], [1, -1, 1], [-1, 1, 1], [1, 1, 1]], dtype=np.float64)
+
+
+def _spread3(v):
+    v = v.astype(np.uint64)
+    v = (v | (v << np.uint64(32))) & np.uint64(0x1F00000000FFFF)
+    v = (v | (v << np.uint64(16))) & np.uint64(0x1F0000FF0000FF)
+    v = (v | (v << np.uint64(8))) & np.uint64(0x100F00F00F00F00F)
+    v = (v | (v << np.uint64(4))) & np.uint64(0x10C30C30C30C30C3)
+    v = (v | (v << np.uint64(2))) & np.uint64(0x1249249249249249)
+    return v
+
+
+def _compact3(v):
+    v = v.astype(np.uint64) & np.uint64(0x1249249249249249)
+    v = (v | (v >> np.uint64(2))) & np.uint64(0x10C30C30C30C30C3)
+    v = (v | (v >> np.uint64(4))) & np.uint64(0x100F00F00F00F00F)
+    v = (v | (v >> np.uint64(8))) & np.uint64(0x1F0000FF0000FF)
+    v = (v | (v >> np.uint64(16))) & np.uint64(0x1F00000000FFFF)
+    v = (v | (v >> np.uint64(32))) & np.uint64(0x1FFFFF)
+    return v
+
+
+def morton(x, y, z):
+    return (_spread3(x) | (_spread3(y) << np.uint64(1)) | (_spread3(z) << np.uint64(2))).astype(np.int64)
+
+
+def coords(m):
+    m = np.asarray(m).astype(np.uint64)
+    return (_compact3(m).astype(np.int64), _compact3(m >> np.uint64(1)).astype(np.int64),
+            _compact3(m >> np.uint64(2)).astype(np.int64))
+
+
+def first_id(level):
+    return (8 ** level - 1) // 7
+
+
+def stencil_tables(QQ):
+    cx = np.vstack([_CX27[:QQ - 1], np.zeros((1, 3))]).astype(np.int64)
+    inv = np.zeros(QQ, dtype=np.int64)
+    for i in range(QQ):
+        for j in range(QQ):
+            if np.array_equal(cx[i], -cx[j]):
+                inv[i] = j + 1
+    return cx, inv
+
+
+def weighted_avg_dirs(QQ):
+    """init_cxDirWeightedAvg (mus_interpolate_header_module.f90:568-607): per child the
+    parent + the face/edge(/corner) neighbours on the child's side, as 1-based directions."""
+    cx, _ = stencil_tables(QQ)
+    out = []
+    for c in range(8):
+        side = CHILD_POSITION[c]
+        dirs = []
+        for q in range(QQ):
+            v = cx[q]
+            if all(v[k] == 0 or v[k] == side[k] for k in range(3)):
+                dirs.append(q + 1)
+        out.append(set(dirs))
+    return out
+
+
+class MLLevel:
+    """tem_levelDesc_type + pdf_data_type of one level (one rank)."""
+    pass
+
+
+def construct_connectivity(QQ, nghElems, property_, nFluid, haloOffset, nSize):
+    """mus_construct_connectivity for AOS + PULL, vectorised (host-side product code;
+    the oracle has its own C restatement and the tests compare the two)."""
+    _, inv = stencil_tables(QQ)
+    nElems = nghElems.shape[0]
+    neigh = np.zeros(QQ * nSize, dtype=np.int32)
+    e = np.arange(1, nElems + 1, dtype=np.int64)
+    neigh[(QQ - 1) * nSize:(QQ - 1) * nSize + nElems] = (e - 1) * QQ + QQ
+    solid_e = ((property_ >> PRP_SOLID) & 1).astype(bool)
+    for d in range(1, QQ):
+        nghDir = inv[d - 1]
+        npos = nghElems[:, nghDir - 1].astype(np.int64)
+        nprop = np.where(npos > 0, property_[np.maximum(npos, 1) - 1], 0)
+        solid = solid_e | (((nprop >> PRP_SOLID) & 1).astype(bool))
+        missing_nonghost = (npos <= 0) & ((e <= nFluid) | (e > haloOffset))
+        sdir = np.where(missing_nonghost | solid, inv[d - 1], d)
+        src = np.where((npos <= 0) | solid, e, npos)
+        neigh[(d - 1) * nSize:(d - 1) * nSize + nElems] = (src - 1) * QQ + sdir
+    return neigh
+
+
+def build_multilevel(min_level, boxes, QQ=19, cylinder=None, intp_method="linear"):
+    """nested refined boxes in a periodic cube.
+
+    boxes: list, one entry per level above min_level: (lo, hi) in cells of THAT level's
+           parent level (the box [lo,hi)^3 of parent cells is replaced by its children).
+    cylinder: None or (cx, cy, r, zlo, zhi) in cells of the finest level: solid cylinder
+              along z between zlo and zhi (its cells are absent from the mesh; neighbours
+              see a wall, boundary id 1).  Keep it >= 8 finest cells away from the box faces.
+    returns {level: MLLevel}, intp dict (matrices per order).
+    """
+    cx, inv = stencil_tables(QQ)
+    QQN = QQ - 1
+    levels = list(range(min_level, min_level + len(boxes) + 1))
+    max_level = levels[-1]
+    # kind per cell: 0 none, 1 fluid, 2 ghostFromCoarser, 3 ghostFromFiner, 9 solid
+    kind, pos = {}, {}
+    region = {}  # region[l] = (lo, hi) box of level-l cells that belong to level >= l
+    region[min_level] = (0, 1 << min_level)
+    for i, (lo, hi) in enumerate(boxes):
+        region[min_level + i + 1] = (2 * lo, 2 * hi)
+        plo, phi = region[min_level + i]
+        assert plo + 4 <= lo and hi + 4 <= phi, "refined box needs a margin of >= 4 parent cells"
+    for l in levels:
+        n = 1 << l
+        k = np.zeros(n ** 3, dtype=np.int8)
+        lo, hi = region[l]
+        ax = np.arange(lo, hi, dtype=np.int64)
+        X, Y, Z = np.meshgrid(ax, ax, ax, indexing="ij")
+        inside = np.ones(X.shape, dtype=bool)
+        if l < max_level:
+            clo, chi = region[l + 1]
+            clo, chi = clo // 2, chi // 2
+            inside &= ~((X >= clo) & (X < chi) & (Y >= clo) & (Y < chi) & (Z >= clo) & (Z < chi))
+        m = morton(X[inside].ravel(), Y[inside].ravel(), Z[inside].ravel())
+        k[m] = 1
+        if l == max_level and cylinder is not None:
+            ccx, ccy, r, zlo, zhi = cylinder
+            xs, ys, zs = coords(m)
+            sol = (((xs + 0.5 - ccx) ** 2 + (ys + 0.5 - ccy) ** 2) < r * r) & (zs >= zlo) & (zs < zhi)
+            k[m[sol]] = 9
+        kind[l] = k
+
+    # ---- ghost layers: reqNesting = 3 rounds of stencil neighbours -----------------
+    for l in levels:
+        n = 1 << l
+        k = kind[l]
+        frontier = np.nonzero(k == 1)[0]
+        for _ in range(3):
+            if frontier.size == 0:
+                break
+            fx, fy, fz = coords(frontier)
+            new = []
+            for q in range(QQN):
+                xn, yn, zn = (fx + cx[q, 0]) % n, (fy + cx[q, 1]) % n, (fz + cx[q, 2]) % n
+                mn = morton(xn, yn, zn)
+                empty = k[mn] == 0
+                if not empty.any():
+                    continue
+                mn, xn, yn, zn = mn[empty], xn[empty], yn[empty], zn[empty]
+                is_gfc = np.zeros(mn.size, dtype=bool)
+                is_gff = np.zeros(mn.size, dtype=bool)
+                if l > min_level:
+                    is_gfc = kind[l - 1][morton(xn >> 1, yn >> 1, zn >> 1)] == 1
+                if l < max_level:
+                    base = morton(xn << 1, yn << 1, zn << 1)
+                    for c in range(8):   # a ghostFromFiner needs at least one fluid child
+                        is_gff |= kind[l + 1][base + c] == 1
+                k[mn[is_gfc]] = 2
+                k[mn[is_gff & ~is_gfc]] = 3
+                new.append(mn[is_gfc | is_gff])
+            frontier = np.unique(np.concatenate(new)) if new else np.zeros(0, dtype=np.int64)
+
+    # ---- total lists + positions ----------------------------------------------------
+    out = {}
+    for l in levels:
+        L = MLLevel()
+        k = kind[l]
+        fl, gc, gf = np.nonzero(k == 1)[0], np.nonzero(k == 2)[0], np.nonzero(k == 3)[0]
+        codes = np.concatenate([fl, gc, gf])
+        L.level, L.QQ = l, QQ
+        L.nFluid, L.nGhostFromCoarser, L.nGhostFromFiner, L.nHalo = fl.size, gc.size, gf.size, 0
+        L.nElems = codes.size
+        L.nSize = (L.nElems + 3) // 4 * 4
+        L.nSolve = L.nFluid + L.nGhostFromCoarser
+        L.total = (first_id(l) + codes).astype(np.int64)
+        L.codes = codes
+        p = np.zeros(k.size, dtype=np.int32)
+        p[codes] = np.arange(1, codes.size + 1, dtype=np.int32)
+        pos[l] = p
+        out[l] = L
+    for l in levels:
+        L = out[l]
+        n = 1 << l
+        x, y, z = coords(L.codes)
+        ngh = np.zeros((L.nElems, QQN), dtype=np.int32)
+        for q in range(QQN):
+            mn = morton((x + cx[q, 0]) % n, (y + cx[q, 1]) % n, (z + cx[q, 2]) % n)
+            pq = pos[l][mn]
+            wall = (kind[l][mn] == 9)
+            ngh[:, q] = np.where(wall, -1, pq)
+        L.nghElems = ngh
+        prop = np.zeros(L.nElems, dtype=np.int64)
+        prop[:L.nFluid] = 1 << PRP_FLUID
+        hasbnd = (ngh[:L.nFluid] < 0).any(axis=1)
+        prop[:L.nFluid][hasbnd] |= 1 << PRP_HASBND
+        L.property = prop
+        L.neigh = construct_connectivity(QQ, ngh, prop, L.nFluid, L.nElems, L.nSize)
+        L.bc_elemBuffer = np.zeros(0, dtype=np.int32)   # only 'wall' (do_nothing) boundaries
+        L.bc, L.recv, L.send = [], [], []
+        L.bary_unit = np.stack([(x + 0.5) / n, (y + 0.5) / n, (z + 0.5) / n], axis=1)
+
+    # ---- vertical dependencies --------------------------------------------------------
+    order_max = ORDER_OF[intp_method]
+    wavg = weighted_avg_dirs(QQ)
+    nmax_wavg = 7 if QQ == 19 else 8
+    nmin = {LINEAR: 4, QUADRATIC: 10}
+    intp = {"order": order_max, "matrices": {LINEAR: [], QUADRATIC: []},
+            "mat_ids": {LINEAR: {}, QUADRATIC: {}}, "mat_ok": {LINEAR: [], QUADRATIC: []}}
+    cxr = cx.astype(np.float64)
+
+    def poly(order, c):
+        if order == LINEAR:
+            return np.array([1.0, c[0], c[1], c[2]])
+        return np.array([1.0, c[0], c[1], c[2], c[0] ** 2, c[1] ** 2, c[2] ** 2,
+                         c[0] * c[1], c[1] * c[2], c[2] * c[0]])
+
+    def lsf_matrix(order, dirs):
+        """append_intpMatrixLSF: one matrix per distinct source-direction set."""
+        key = 0
+        for d in dirs:
+            key |= 1 << int(d)
+        ids = intp["mat_ids"][order]
+        if key in ids:
+            i = ids[key]
+            return (i if intp["mat_ok"][order][i] else -1)
+        A = np.array([poly(order, cxr[d - 1]) for d in dirs])
+        AtA = A.T @ A
+        ok = np.linalg.matrix_rank(AtA) == AtA.shape[0] and np.linalg.cond(AtA) < 1e12
+        M = np.linalg.inv(AtA) @ A.T if ok else np.zeros((1, 1))
+        ids[key] = len(intp["matrices"][order])
+        intp["matrices"][order].append(M)
+        intp["mat_ok"][order].append(bool(ok))
+        return ids[key] if ok else -1
+
+    for l in levels:
+        L = out[l]
+        # ghostFromFiner <- children (tem_build_verticalDependencies second loop)
+        L.depFromFiner = []
+        if L.nGhostFromFiner:
+            gcodes = L.codes[L.nFluid + L.nGhostFromCoarser:]
+            for g in gcodes:
+                ch = pos[l + 1][8 * g + np.arange(8)]
+                ch = ch[ch > 0]
+                assert ch.size > 0, "ghostFromFiner without any child present"
+                L.depFromFiner.append(ch.astype(np.int32))
+        L.intpFromFiner = np.arange(1, L.nGhostFromFiner + 1, dtype=np.int32)
+        # ghostFromCoarser <- parent + its stencil neighbours
+        L.depFromCoarser = []
+        L.intpFromCoarser = {o: [] for o in range(0, order_max + 1)}
+        if L.nGhostFromCoarser:
+            C = out[l - 1]
+            gcodes = L.codes[L.nFluid:L.nFluid + L.nGhostFromCoarser]
+            for i, g in enumerate(gcodes):
+                parentPos = int(pos[l - 1][g >> 3])
+                assert parentPos > 0, "ghostFromCoarser without parent"
+                childNum = int(g & 7) + 1
+                coord = 0.25 * CHILD_POSITION[childNum - 1]
+                srcs, dirs = [], []
+                for iNeigh in range(1, QQ + 1):
+                    p = parentPos if iNeigh == QQ else int(C.nghElems[parentPos - 1, iNeigh - 1])
+                    if p > 0:
+                        srcs.append(p)
+                        dirs.append(iNeigh)
+                # find_possIntpOrderAndUpdateMySources
+                order = WEIGHTED_AVERAGE
+                for o in range(order_max, LINEAR - 1, -1):
+                    if len(srcs) >= nmin[o]:
+                        order = o
+                        break
+                if order in (WEIGHTED_AVERAGE, LINEAR):
+                    keep = [j for j, d in enumerate(dirs) if d in wavg[childNum - 1]]
+                    if len(keep) == nmax_wavg:
+                        srcs, dirs = [srcs[j] for j in keep], [dirs[j] for j in keep]
+                dep = dict(childNum=childNum, coord=coord, posInMat=-1, weights=None)
+                if order == QUADRATIC:
+                    mi = lsf_matrix(QUADRATIC, dirs)
+                    if mi >= 0:
+                        dep["posInMat"] = mi
+                    else:
+                        order = LINEAR
+                if order == LINEAR:
+                    mi = lsf_matrix(LINEAR, dirs)
+                    if mi >= 0:
+                        dep["posInMat"] = mi
+                    else:
+                        order = WEIGHTED_AVERAGE
+                if order == WEIGHTED_AVERAGE:
+                    # compute_weight, 'linear_distance'
+                    dist = np.abs(cxr[np.array(dirs) - 1] - coord[None, :])
+                    w = (1.0 - dist[:, 0]) * (1.0 - dist[:, 1]) * (1.0 - dist[:, 2])
+                    dep["weights"] = w / w.sum()
+                dep["order"] = order
+                dep["sources"] = np.array(srcs, dtype=np.int32)
+                dep["dirs"] = np.array(dirs, dtype=np.int32)
+                L.depFromCoarser.append(dep)
+                L.intpFromCoarser[order].append(i + 1)
+        for o in L.intpFromCoarser:
+            L.intpFromCoarser[o] = np.array(L.intpFromCoarser[o], dtype=np.int32)
+    return out, intp
+
+
+def intp_tables(L, intp, direction, order=None):
+    """flattens the dependency lists of one level into the arrays musb200_intp_register
+    (and the oracle) take: targets (positions in the total list), CSR sources, weights,
+    posInMat, concatenated row-major matrices, child coordinates."""
+    if direction == "fromFiner":
+        off0 = L.nFluid + L.nGhostFromCoarser
+        tg = (L.intpFromFiner + off0).astype(np.int32)
+        srcOff = np.zeros(len(tg) + 1, dtype=np.int32)
+        src = []
+        for i, t in enumerate(L.intpFromFiner):
+            s = L.depFromFiner[t - 1]
+            src.append(s)
+            srcOff[i + 1] = srcOff[i] + len(s)
+        src = np.concatenate(src).astype(np.int32) if src else np.zeros(0, dtype=np.int32)
+        return dict(targets=tg, srcOffset=srcOff, srcPos=src, weights=np.zeros(0), posInMat=np.zeros(0, np.int32),
+                    matOffset=np.zeros(1, np.int32), matrices=np.zeros(0), coord=np.zeros((0, 3)), nMat=0)
+    lst = L.intpFromCoarser[order]
+    tg = (lst + L.nFluid).astype(np.int32)
+    srcOff = np.zeros(len(tg) + 1, dtype=np.int32)
+    src, wts, pim, crd = [], [], [], []
+    for i, t in enumerate(lst):
+        dep = L.depFromCoarser[t - 1]
+        src.append(dep["sources"])
+        srcOff[i + 1] = srcOff[i] + len(dep["sources"])
+        wts.append(dep["weights"] if dep["weights"] is not None else np.zeros(len(dep["sources"])))
+        pim.append(dep["posInMat"])
+        crd.append(dep["coord"])
+    mats = intp["matrices"].get(order, []) if order > 0 else []
+    matOff = np.zeros(len(mats) + 1, dtype=np.int32)
+    for i, M in enumerate(mats):
+        matOff[i + 1] = matOff[i] + M.size
+    return dict(targets=tg, srcOffset=srcOff,
+                srcPos=np.concatenate(src).astype(np.int32) if src else np.zeros(0, np.int32),
+                weights=np.concatenate(wts) if wts else np.zeros(0),
+                posInMat=np.array(pim, dtype=np.int32), matOffset=matOff,
+                matrices=np.concatenate([M.ravel() for M in mats]) if mats else np.zeros(0),
+                coord=np.array(crd).reshape(-1, 3) if crd else np.zeros((0, 3)), nMat=len(mats))

@@ -90,6 +90,22 @@ void ora_velocity_bounceback(double *state, const double *bcBuffer, int QQ,
 void ora_init_equilibrium(int QQ, int incompressible, int nElems, const double *rho,
                           const double *vel, double *state);
 
+/* ---- ghost interpolation (mus/source/intp) ----------------------------- */
+void ora_fill_my_ghosts_from_finer_avg(int QQ, int incomp, const double *sState,
+                                       const double *sAux, double *tState, int nTargets,
+                                       const int32_t *targetPos, const int32_t *srcOffset,
+                                       const int32_t *srcPos, const double *tVisc);
+void ora_fill_arbi_from_finer_avg(int nScalars, const double *sVal, double *tVal, int nTargets,
+                                  const int32_t *targetPos, const int32_t *srcOffset,
+                                  const int32_t *srcPos);
+void ora_fill_finer_ghosts_from_me(int order, int QQ, int incomp, const double *sState,
+                                   const double *sAux, double *tState, int nTargets,
+                                   const int32_t *targetPos, const int32_t *srcOffset,
+                                   const int32_t *srcPos, const double *weights,
+                                   const int32_t *posInMat, const int32_t *matOffset,
+                                   const double *matrices, const double *coord,
+                                   const double *tVisc);
+
 /* ---- halo exchange (tem_comm_module.fpp:549-646) ------------------------ */
 void ora_comm_gather(double *buf, const double *state, const int32_t *pos, int n);
 void ora_comm_scatter(double *state, const double *buf, const int32_t *pos, int n);

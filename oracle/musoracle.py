@@ -469,3 +469,94 @@ def run_multi(schemes, nsteps):
         for s in schemes:
             s.step()
         exchange_all(schemes)
+
+
+# --------------------------------------------------------------------------
+# multi-level: do_recursive_multiLevel (mus_control_module.f90:242-497)
+# --------------------------------------------------------------------------
+class MultiLevelScheme:
+    """one Scheme per level + the recursive level-sync schedule with ghost interpolation.
+    `levels`: {level: descriptor} with the tem_levelDesc_type members (any generator);
+    `tables`: {(level, 'fromFiner'| ('fromCoarser', order)): dict of flat dependency arrays}
+    acoustic scaling: nu_lat doubles per finer level (mus_physics_module.f90:528)."""
+
+    def __init__(self, levels, tables, relaxation="bgk", kind="fluid", omega_min=1.7, lambda_=0.25,
+                 omega_bulk=None, order=1):
+        self.levels = dict(levels)
+        self.minLevel, self.maxLevel = min(levels), max(levels)
+        self.tables = tables
+        self.order = order
+        self.s = {}
+        nu0 = (1.0 / omega_min - 0.5) / 3.0
+        for l, ld in self.levels.items():
+            nu = nu0 * 2.0 ** (l - self.minLevel)
+            om = 1.0 / (3.0 * nu + 0.5)
+            self.s[l] = Scheme(ld, relaxation, kind, omega=om, lambda_=lambda_,
+                               omega_bulk=om if omega_bulk is None else omega_bulk)
+            self.s[l].visc[:] = nu
+            self.s[l].omega[:] = om
+
+    def _from_finer(self, l):
+        """do_intpFinerAndExchange: my ghostFromFiner <- level l+1"""
+        t = self.tables.get((l, "fromFiner"))
+        if t is None or len(t["targets"]) == 0:
+            return
+        c, f = self.s[l], self.s[l + 1]
+        lib().ora_fill_my_ghosts_from_finer_avg(
+            c.QQ, c.incomp, _d(f.state[f.nNext]), _d(f.aux), _d(c.state[c.nNext]), len(t["targets"]),
+            _i(t["targets"]), _i(t["srcOffset"]), _i(t["srcPos"]), _d(c.visc))
+
+    def _aux_from_finer(self, l):
+        """mus_intpAuxFieldCoarserAndExchange: auxField of my ghostFromFiner <- level l+1"""
+        t = self.tables.get((l, "fromFiner"))
+        if t is None or len(t["targets"]) == 0:
+            return
+        c, f = self.s[l], self.s[l + 1]
+        lib().ora_fill_arbi_from_finer_avg(4, _d(f.aux), _d(c.aux), len(t["targets"]), _i(t["targets"]),
+                                           _i(t["srcOffset"]), _i(t["srcPos"]))
+
+    def _from_coarser(self, l):
+        """do_intpCoarserAndExchange: ghostFromCoarser of level l+1 <- me, orders 0..order"""
+        c, f = self.s[l], self.s[l + 1]
+        for o in range(0, self.order + 1):
+            t = self.tables.get((l + 1, ("fromCoarser", o)))
+            if t is None or len(t["targets"]) == 0:
+                continue
+            coord = np.ascontiguousarray(t["coord"], dtype=np.float64)
+            lib().ora_fill_finer_ghosts_from_me(
+                o, c.QQ, c.incomp, _d(c.state[c.nNext]), _d(c.aux), _d(f.state[f.nNext]),
+                len(t["targets"]), _i(t["targets"]), _i(t["srcOffset"]), _i(t["srcPos"]),
+                _d(np.ascontiguousarray(t["weights"])), _i(t["posInMat"]), _i(t["matOffset"]),
+                _d(np.ascontiguousarray(t["matrices"])), _d(coord), _d(f.visc))
+
+    def do_computation(self, l=None):
+        l = self.minLevel if l is None else l
+        L = lib()
+        if l < self.maxLevel:
+            for _ in range(2):                                   # nNesting = 2 (acoustic)
+                self.do_computation(l + 1)
+        s = self.s[l]
+        s.set_boundary()
+        s.nNow, s.nNext = s.nNext, s.nNow
+        s.calc_aux(s.state[s.nNow])
+        if l < self.maxLevel:
+            self._aux_from_finer(l)
+        L.ora_update_omega(_d(s.omega), _d(s.visc), s.ld.nSolve)
+        rc = L.ora_compute(s.relax, s.QQ, s.incomp, _d(s.state[s.nNow]), _d(s.state[s.nNext]), _d(s.aux),
+                           _i(s.ld.neigh), _d(s.omega), s.ld.nSize, s.ld.nSolve, ctypes.byref(s.rp))
+        if rc != 0:
+            raise RuntimeError("no oracle kernel for this (relaxation, layout, kind)")
+        if l < self.maxLevel:
+            self._from_finer(l)
+            self._from_coarser(l)
+
+    def run(self, ncycles):
+        for _ in range(ncycles):
+            self.do_computation()
+
+    def total_mass(self):
+        """sum over levels of fluid PDFs weighted by the cell volume relative to minLevel"""
+        tot = 0.0
+        for l, s in self.s.items():
+            tot += s.total_mass() / 8.0 ** (l - self.minLevel)
+        return tot

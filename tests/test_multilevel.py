@@ -1,0 +1,145 @@
+"""Multi-level (config 4): ghost interpolation + the level-sync schedule.
+
+CPU: the synthetic multi-level generator against the oracle's restatement of
+mus_construct_connectivity, and analytic properties of the oracle's interpolation
+(the reference's own interpolation utests are deactivated -> "parity unpinned"):
+uniform flow is a fixed point, linear/quadratic interpolation reproduce linear fields.
+GPU: libmusb200 against the oracle on the same two- and three-level meshes, bit-exact."""
+import numpy as np
+import pytest
+
+
+def tgv_like(bary_unit, u0=0.03):
+    x = 2.0 * np.pi * bary_unit
+    vel = np.stack([u0 * np.sin(x[:, 0]) * np.cos(x[:, 1]) * np.cos(x[:, 2]) + 0.02,
+                    -u0 * np.cos(x[:, 0]) * np.sin(x[:, 1]) * np.cos(x[:, 2]) - 0.01,
+                    0.015 + 0.0 * x[:, 0]], axis=1)
+    rho = 1.0 + 3.0 * (u0 * u0 / 16.0) * (np.cos(2 * x[:, 0]) + np.cos(2 * x[:, 1])) * (np.cos(2 * x[:, 2]) + 2.0)
+    return rho, vel
+
+
+def build(mo, min_level, boxes, QQ, method, relaxation="bgk", cylinder=None, omega_min=1.6):
+    import musubi_b200 as mb
+    from musubi_b200 import treelm_multilevel as tm
+    lv, intp = tm.build_multilevel(min_level, boxes, QQ=QQ, cylinder=cylinder, intp_method=method)
+    tables = mb.multilevel_tables(lv, intp)
+    ms = mo.MultiLevelScheme(lv, tables, relaxation, "fluid", omega_min=omega_min, omega_bulk=1.2,
+                             order=intp["order"])
+    for l, s in ms.s.items():
+        rho, vel = tgv_like(lv[l].bary_unit)
+        s.init_equilibrium(rho, vel)
+    return lv, intp, tables, ms
+
+
+@pytest.mark.parametrize("QQ", [19, 27])
+def test_generator_connectivity_matches_oracle(oracle, QQ):
+    from musubi_b200 import treelm_multilevel as tm
+    lv, _ = tm.build_multilevel(5, [(10, 22)], QQ=QQ, cylinder=(32.0, 32.0, 3.0, 29, 35))
+    for l, L in lv.items():
+        ng = np.zeros(QQ * L.nSize, dtype=np.int32)
+        oracle.lib().ora_construct_connectivity(oracle._i(ng), L.nSize, L.nElems, QQ,
+                                                oracle._i(np.ascontiguousarray(L.nghElems)),
+                                                oracle._l(L.property), L.nFluid, L.nElems)
+        assert np.array_equal(ng, L.neigh)
+        assert np.all(np.diff(L.total[:L.nFluid]) > 0)
+        a, b = L.nFluid, L.nFluid + L.nGhostFromCoarser
+        assert np.all(np.diff(L.total[a:b]) > 0) and np.all(np.diff(L.total[b:]) > 0)
+    assert lv[5].nGhostFromFiner > 0 and lv[6].nGhostFromCoarser > 0
+    assert (lv[6].nghElems[:lv[6].nFluid] == -1).any()      # the cylinder is seen as a wall
+
+
+@pytest.mark.parametrize("method", ["weighted_average", "linear", "quadratic"])
+@pytest.mark.parametrize("QQ", [19, 27])
+def test_uniform_flow_is_a_fixed_point(oracle, method, QQ):
+    import musubi_b200 as mb
+    from musubi_b200 import treelm_multilevel as tm
+    lv, intp = tm.build_multilevel(4, [(5, 11)], QQ=QQ, intp_method=method)
+    ms = oracle.MultiLevelScheme(lv, mb.multilevel_tables(lv, intp), "bgk", "fluid", omega_min=1.6,
+                                 order=intp["order"])
+    u = np.array([0.02, 0.01, -0.015])
+    for l, s in ms.s.items():
+        s.init_equilibrium(np.ones(lv[l].nElems), np.tile(u, (lv[l].nElems, 1)))
+    ref = ms.s[4].state[ms.s[4].nNext][:QQ].copy()
+    m0 = ms.total_mass()
+    ms.run(6)
+    for l, s in ms.s.items():
+        got = s.state[s.nNext][:lv[l].nFluid * QQ].reshape(-1, QQ)
+        assert np.abs(got - ref).max() < 5e-15
+    assert abs(ms.total_mass() / m0 - 1.0) < 1e-14
+
+
+@pytest.mark.parametrize("method,order", [("linear", 1), ("quadratic", 2)])
+def test_interpolation_reproduces_linear_fields(oracle, method, order):
+    """a density field linear in x,y,z at rest (f = f_eq) must be interpolated exactly to the
+    fine ghosts by the least-square linear and quadratic interpolation."""
+    import musubi_b200 as mb
+    from musubi_b200 import treelm_multilevel as tm
+    QQ = 19
+    lv, intp = tm.build_multilevel(4, [(5, 11)], QQ=QQ, intp_method=method)
+    tables = mb.multilevel_tables(lv, intp)
+    ms = oracle.MultiLevelScheme(lv, tables, "bgk", "fluid", omega_min=1.6, order=order)
+    g = np.array([0.3, -0.2, 0.1])
+    for l, s in ms.s.items():
+        b = lv[l].bary_unit
+        # wrap-free coordinate: the refined box is in the interior of the cube
+        rho = 1.0 + (b - 0.5) @ g
+        s.init_equilibrium(rho, np.zeros((lv[l].nElems, 3)))
+    ms._from_coarser(4)
+    f = ms.s[5]
+    L5 = lv[5]
+    gh = slice(L5.nFluid, L5.nFluid + L5.nGhostFromCoarser)
+    got_rho = f.state[f.nNext].reshape(-1, QQ)[gh].sum(axis=1)
+    exp_rho = 1.0 + (L5.bary_unit[gh] - 0.5) @ g
+    assert np.abs(got_rho - exp_rho).max() < 1e-13
+
+
+# ---------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def mbgpu():
+    import musubi_b200
+    musubi_b200.mus_init(0, 1, 0)
+    yield musubi_b200
+    musubi_b200.mus_finalize()
+
+
+CASES = [
+    (4, [(5, 11)], 19, "linear", "bgk", None),
+    (5, [(10, 22)], 19, "linear", "bgk", (32.0, 32.0, 3.0, 29, 35)),
+    (4, [(5, 11)], 27, "quadratic", "mrt", None),
+    (4, [(5, 11)], 19, "weighted_average", "trt", None),
+    (4, [(4, 12), (12, 20)], 19, "linear", "bgk", None),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("min_level,boxes,QQ,method,relax,cyl", CASES,
+                         ids=["2lvl-linear-bgk19", "2lvl-cylinder", "2lvl-quad-mrt27", "2lvl-wavg-trt19",
+                              "3lvl-linear-bgk19"])
+def test_multilevel_gpu_matches_oracle(mbgpu, oracle, min_level, boxes, QQ, method, relax, cyl):
+    mb = mbgpu
+    lv, intp, tables, ms = build(oracle, min_level, boxes, QQ, method, relax, cyl)
+    ident = {"kind": "fluid", "relaxation": relax, "layout": "d3q%d" % QQ}
+    omega = {l: float(1.0 / (3.0 * s.visc[0] + 0.5)) for l, s in ms.s.items()}
+    visc = {l: float(s.visc[0]) for l, s in ms.s.items()}
+    sch = mb.Scheme(ident, lv, omega, lambda_=0.25, omega_bulk=1.2, intp=(tables, intp["order"]),
+                    viscosity=visc)
+    from musubi_b200._lib import check, lib
+    for l, s in ms.s.items():
+        sch.upload_state(l, s.state[s.nNow], s.state[s.nNext])
+        check(lib.musb200_aux_upload(l, s.aux.ctypes.data))
+    ncyc = 12
+    sch.do_computation(ncyc)
+    ms.run(ncyc)
+    for l, s in ms.s.items():
+        L = lv[l]
+        got = sch.download_state(l)[:L.nElems * QQ].reshape(-1, QQ)
+        exp = s.state[s.nNext][:L.nElems * QQ].reshape(-1, QQ)
+        nf = L.nFluid
+        rel = np.max(np.abs(got[:nf] - exp[:nf]) / np.abs(exp[:nf]))
+        assert rel < 1e-10, (l, rel)
+        assert np.array_equal(got[:nf], exp[:nf]), "fluid PDFs of level %d not bit-identical" % l
+        # ghosts filled by interpolation
+        assert np.array_equal(got[nf:], exp[nf:]), "ghost PDFs of level %d differ" % l
+        aux = sch.download_aux(l)[:L.nElems * 4]
+        assert np.array_equal(aux[:nf * 4], s.aux[:nf * 4])
+    sch.destroy()
