@@ -450,9 +450,11 @@ int musb200_scheme_select(const char *kind, const char *relaxation, const char *
   else return setError(MUSB200_ERR_UNSUPPORTED, "relaxation '" + r + "' is outside the B200 hot path");
   if (v != "standard" && v != "b200")
     return setError(MUSB200_ERR_UNSUPPORTED, "relaxation variant '" + v + "' is outside the B200 hot path");
-  if (kk == MUSB200_KIND_FLUID_INCOMPRESSIBLE && !(qq == 19 && rr == MUSB200_RELAX_BGK))
+  // mus_init_advRel_fluid_incompressible aborts for trt with a layout other than d3q19
+  // (init/mus_initFluidIncomp_module.f90:80-93)
+  if (kk == MUSB200_KIND_FLUID_INCOMPRESSIBLE && rr == MUSB200_RELAX_TRT && qq != 19)
     return setError(MUSB200_ERR_UNSUPPORTED,
-                    "fluid_incompressible: only bgk/d3q19 is built (the others are a 'next' row)");
+                    "fluid_incompressible: the reference has no trt kernel for layout '" + l + "'");
   *relax_id = rr; *kind_id = kk; *QQ = qq;
   return 0;
 }
@@ -590,8 +592,8 @@ int musb200_set_relaxation(int level, int relax_id, int kind_id, const double *o
   GET_LEVEL(L, level);
   if (relax_id < 0 || relax_id > 2 || kind_id < 0 || kind_id > 1)
     return setError(MUSB200_ERR_ARG, "bad relaxation / kind id");
-  if (kind_id == MUSB200_KIND_FLUID_INCOMPRESSIBLE && !(L->QQ == 19 && relax_id == 0))
-    return setError(MUSB200_ERR_UNSUPPORTED, "fluid_incompressible: only bgk/d3q19 is built");
+  if (kind_id == MUSB200_KIND_FLUID_INCOMPRESSIBLE && relax_id == MUSB200_RELAX_TRT && L->QQ != 19)
+    return setError(MUSB200_ERR_UNSUPPORTED, "fluid_incompressible: the reference has no trt kernel for d3q27");
   L->relax = relax_id; L->kind = kind_id;
   L->rp.omega_uniform = omega_uniform; L->rp.lambda = lambda; L->rp.omega_bulk = omega_bulk;
   L->elemOmega = (omega != nullptr);

@@ -4,7 +4,10 @@
 // Arithmetic (operation order kept so that, compiled with -fmad=false, results
 // are bit-identical to the reference algorithm evaluated in IEEE double):
 //   BGK D3Q19   mus/source/compute/mus_compute_d3q19_module.fpp:483-640
-//   BGK D3Q19 incompressible                            ...:1596-1700
+//   fluid_incompressible: BGK D3Q19 ...:1596-1700, TRT D3Q19 ...:2782-2959,
+//               MRT D3Q19 mus_compute_mrt_d3q19_module.fpp:466-739,
+//               MRT D3Q27 mus_compute_mrt_d3q27_module.fpp:374-546,
+//               BGK D3Q27 = the kCFD kernel with get_pdfEq_incomp_d3q27
 //   TRT D3Q19   mus/source/compute/mus_compute_d3q19_module.fpp:2644-2763
 //   MRT D3Q19   mus/source/compute/mus_compute_mrt_d3q19_module.fpp:238-450
 //   BGK D3Q27   mus/source/compute/mus_compute_d3q27_module.fpp:398-517
@@ -19,6 +22,7 @@
 // post-collision PDF of 0-based direction q (a coalesced SoA store).
 #pragma once
 #include "common.cuh"
+#include "equilibrium.cuh"
 #include "mrt_tables.cuh"
 #include <utility>
 
@@ -134,7 +138,41 @@ __device__ __forceinline__ void collide_trt_d3q19(const double (&f)[19], double 
 }
 
 // ---------------------------------------------------------------------------
+// mus_advRel_kFluidIncomp_rTRT_vStd_lD3Q19 (mus_compute_d3q19_module.fpp:2782-2959)
 template <class St>
+__device__ __forceinline__ void collide_trt_d3q19_incomp(const double (&f)[19], double rho,
+                                                         double u_x, double u_y, double u_z,
+                                                         double omega, double lambda, St st) {
+  constexpr double div1_3 = 1.0 / 3.0, div1_6 = 1.0 / 6.0, t2cs4inv = 4.5;
+  constexpr double t1x2 = 1.0 / 9.0, t2x2 = 1.0 / 18.0;
+  constexpr double fac1 = t1x2 * t2cs4inv, fac2 = t2x2 * t2cs4inv;
+  const double usq = (u_x * u_x) + (u_y * u_y) + (u_z * u_z);
+  const double feq_common = rho - 1.5 * usq;
+  const double omega_h = 0.5 * omega;
+  const double asym_omega = 1.0 / (0.5 + lambda / (1.0 / omega - 0.5));
+  const double asym_omega_h = 0.5 * asym_omega;
+  st(18, f[18] * (1.0 - omega) + omega * div1_3 * feq_common);
+  auto link = [&](double fc, double tfeq, double dv, int qp, int qm, double ui) {
+    const double sym = omega_h * (f[qp] + f[qm] - fc * ui * ui - tfeq);
+    const double asym = asym_omega_h * (f[qp] - f[qm] - dv * ui);
+    st(qp, f[qp] - sym - asym);
+    st(qm, f[qm] - sym + asym);
+  };
+  const double t2_feq = t2x2 * feq_common;
+  link(fac2, t2_feq, div1_6, PP0, NN0, u_x + u_y);
+  link(fac2, t2_feq, div1_6, PN0, NP0, u_x - u_y);
+  link(fac2, t2_feq, div1_6, PZP, NZN, u_x + u_z);
+  link(fac2, t2_feq, div1_6, PZN, NZP, u_x - u_z);
+  link(fac2, t2_feq, div1_6, ZPP, ZNN, u_y + u_z);
+  link(fac2, t2_feq, div1_6, ZPN, ZNP, u_y - u_z);
+  const double t1_feq = t1x2 * feq_common;
+  link(fac1, t1_feq, div1_3, ZP0, ZN0, u_y);
+  link(fac1, t1_feq, div1_3, P00, N00, u_x);
+  link(fac1, t1_feq, div1_3, ZZP, ZZN, u_z);
+}
+
+// ---------------------------------------------------------------------------
+template <bool INCOMP, class St>
 __device__ __forceinline__ void collide_mrt_d3q19(const double (&f)[19], double rho, double u_x,
                                                   double u_y, double u_z, double omegaKine,
                                                   double omegaBulk, St st) {
@@ -165,16 +203,18 @@ __device__ __forceinline__ void collide_mrt_d3q19(const double (&f)[19], double 
   const double sum5 = sum2 + sum3;
   const double mout3 = (2.0 * (f000 - sum5) - sum4 + m2) * s3;
 
-  const double meq2 = rho * (u_x * u_x + u_y * u_y + u_z * u_z);
-  const double meq10 = rho * 3.0 * u_x * u_x - meq2;
-  const double meq12 = rho * (u_y * u_y - u_z * u_z);
+  // incompressible (mus_compute_mrt_d3q19_module.fpp:578-603): rho0 = 1 replaces rho
+  const double meq2 = INCOMP ? u_x * u_x + u_y * u_y + u_z * u_z
+                             : rho * (u_x * u_x + u_y * u_y + u_z * u_z);
+  const double meq10 = INCOMP ? 3.0 * u_x * u_x - meq2 : rho * 3.0 * u_x * u_x - meq2;
+  const double meq12 = INCOMP ? u_y * u_y - u_z * u_z : rho * (u_y * u_y - u_z * u_z);
   const double mout2 = s2 * (m2 - meq2);
   const double m14 = f110 + fNN0 - f1N0 - fN10;
-  const double mout14 = s14 * (m14 - rho * u_x * u_y);
+  const double mout14 = s14 * (m14 - (INCOMP ? u_x * u_y : rho * u_x * u_y));
   const double m15 = f011 + f0NN - f01N - f0N1;
-  const double mout15 = s15 * (m15 - rho * u_y * u_z);
+  const double mout15 = s15 * (m15 - (INCOMP ? u_y * u_z : rho * u_y * u_z));
   const double m16 = f101 + fN0N - f10N - fN01;
-  const double mout16 = s16 * (m16 - rho * u_x * u_z);
+  const double mout16 = s16 * (m16 - (INCOMP ? u_x * u_z : rho * u_x * u_z));
 
   const double sum6 = sum1 + m6 - m8 * 2.0;
   const double sum7 = sum4 - sum5;
@@ -247,52 +287,16 @@ __device__ __forceinline__ void collide_mrt_d3q19(const double (&f)[19], double 
 }
 
 // ---------------------------------------------------------------------------
-// second-order equilibrium of D3Q27 in the reference's sigma form
-template <class St>
+// mus_advRel_kCFD_rBGK_vStd_lD3Q27: out = f - omega*(f - fEq), fEq = pdfEq_ptr(rho, vel):
+// get_pdfEq_d3q27 (fluid) or get_pdfEq_incomp_d3q27 (fluid_incompressible)
+template <bool INCOMP, class St>
 __device__ __forceinline__ void collide_bgk_d3q27(const double (&f)[27], double rho, double vx,
                                                   double vy, double vz, double omega, St st) {
-  // sigma(k), k = 1..34 (get_sigma_d3q27 :640-682)
-  const double s34 = vx + vy, s33 = vx - vy, s32 = vx + vz, s31 = vx - vz;
-  const double s30 = vy + vz, s29 = vy - vz;
-  const double s28 = vx + vy + vz, s27 = vx + vy - vz, s26 = vx - vy + vz, s25 = vy - vx + vz;
-  const double s24 = 3.0 * s34, s23 = 3.0 * s33, s22 = 3.0 * s32, s21 = 3.0 * s31;
-  const double s20 = 3.0 * s30, s19 = 3.0 * s29, s18 = 3.0 * s28, s17 = 3.0 * s27;
-  const double s16 = 3.0 * s26, s15 = 3.0 * s25;
-  const double s14 = 4.5 * (s34 * s34), s13 = 4.5 * (s33 * s33), s12 = 4.5 * (s32 * s32);
-  const double s11 = 4.5 * (s31 * s31), s10 = 4.5 * (s30 * s30), s9 = 4.5 * (s29 * s29);
-  const double s8 = 4.5 * (s28 * s28), s7 = 4.5 * (s27 * s27), s6 = 4.5 * (s26 * s26);
-  const double s5 = 4.5 * (s25 * s25);
-  const double s4 = 4.5 * (vx * vx), s3 = 4.5 * (vy * vy), s2 = 4.5 * (vz * vz);
-  const double s1 = (1.0 / 3.0) * (s2 + s3 + s4);
-  const double r27 = (2.0 / 27.0) * rho, r54 = (1.0 / 54.0) * rho, r216 = (1.0 / 216.0) * rho;
-  auto relax = [&](int q, double feq) { st(q, f[q] - omega * (f[q] - feq)); };
-  relax(0, -r27 * (3.0 * vx - s4 + s1 - 1.0));
-  relax(1, -r27 * (3.0 * vy - s3 + s1 - 1.0));
-  relax(2, -r27 * (3.0 * vz - s2 + s1 - 1.0));
-  relax(3, r27 * (3.0 * vx + s4 - s1 + 1.0));
-  relax(4, r27 * (3.0 * vy + s3 - s1 + 1.0));
-  relax(5, r27 * (3.0 * vz + s2 - s1 + 1.0));
-  relax(6, r54 * (s10 - s20 - s1 + 1.0));
-  relax(7, r54 * (s9 - s19 - s1 + 1.0));
-  relax(8, r54 * (s9 + s19 - s1 + 1.0));
-  relax(9, r54 * (s10 + s20 - s1 + 1.0));
-  relax(10, r54 * (s12 - s22 - s1 + 1.0));
-  relax(11, r54 * (s11 + s21 - s1 + 1.0));
-  relax(12, r54 * (s11 - s21 - s1 + 1.0));
-  relax(13, r54 * (s12 + s22 - s1 + 1.0));
-  relax(14, r54 * (s14 - s24 - s1 + 1.0));
-  relax(15, r54 * (s13 - s23 - s1 + 1.0));
-  relax(16, r54 * (s13 + s23 - s1 + 1.0));
-  relax(17, r54 * (s14 + s24 - s1 + 1.0));
-  relax(18, -r216 * (s18 - s8 + s1 - 1.0));
-  relax(19, -r216 * (s17 - s7 + s1 - 1.0));
-  relax(20, -r216 * (s16 - s6 + s1 - 1.0));
-  relax(21, r216 * (s15 + s5 - s1 + 1.0));
-  relax(22, -r216 * (s15 - s5 + s1 - 1.0));
-  relax(23, r216 * (s16 + s6 - s1 + 1.0));
-  relax(24, r216 * (s17 + s7 - s1 + 1.0));
-  relax(25, r216 * (s18 + s8 - s1 + 1.0));
-  relax(26, -(8.0 / 27.0) * rho * (s1 - 1.0));
+  double feq[27];
+  if (INCOMP) pdfEqIncompD3Q27(rho, vx, vy, vz, feq);
+  else pdfEqD3Q27(rho, vx, vy, vz, feq);
+#pragma unroll
+  for (int q = 0; q < 27; ++q) st(q, f[q] - omega * (f[q] - feq[q]));
 }
 
 // ---------------------------------------------------------------------------
@@ -349,7 +353,7 @@ __device__ __forceinline__ void mrt27BackTransform(const double (&g)[27], const 
 }
 
 // ---------------------------------------------------------------------------
-template <class St>
+template <bool INCOMP, class St>
 __device__ __forceinline__ void collide_mrt_d3q27(const double (&g)[27], double rho, double u_x,
                                                   double u_y, double u_z, double omegaKine,
                                                   double omegaBulk, St st) {
@@ -404,11 +408,13 @@ __device__ __forceinline__ void collide_mrt_d3q27(const double (&g)[27], double 
   const double mom27 = 2.0 * (f(1) + f(2) + f(3) + f(4) + f(5) + f(6)) +
                        4.0 * (-sum_7_10 - sum_11_18) + 8.0 * (sum_19_26) - f(27);
 
-  const double meq2 = rho * u_x, meq3 = rho * u_y, meq4 = rho * u_z;
+  // incompressible (mus_compute_mrt_d3q27_module.fpp:516-526): rho0 = 1 in meq(2:10)
+  const double rq = INCOMP ? 1.0 : rho;
+  const double meq2 = rq * u_x, meq3 = rq * u_y, meq4 = rq * u_z;
   const double meq5 = meq2 * u_y, meq6 = meq3 * u_z, meq7 = meq4 * u_x;
-  const double meq8 = rho * (2.0 * u_x * u_x - u_y * u_y - u_z * u_z);
-  const double meq9 = rho * (u_y * u_y - u_z * u_z);
-  const double meq10 = rho * (u_x * u_x + u_y * u_y + u_z * u_z);
+  const double meq8 = rq * (2.0 * u_x * u_x - u_y * u_y - u_z * u_z);
+  const double meq9 = rq * (u_y * u_y - u_z * u_z);
+  const double meq10 = rq * (u_x * u_x + u_y * u_y + u_z * u_z);
 
   // s_mrt of mrt_d3q27 (mus_mrtRelaxation_module.fpp:267-288), s(5:9) = omegaKine
   mneq[0] = 0.0; mneq[1] = 0.0; mneq[2] = 0.0; mneq[3] = 0.0;

@@ -96,7 +96,8 @@ __global__ void eqNeqKernel(int incomp, const double *__restrict__ sState,
     else pdfEqD3Q19(rho, vx, vy, vz, g);
   } else {
     double(&g)[27] = reinterpret_cast<double(&)[27]>(feq);
-    pdfEqD3Q27(rho, vx, vy, vz, g);
+    if (incomp) pdfEqIncompD3Q27(rho, vx, vy, vz, g);
+    else pdfEqD3Q27(rho, vx, vy, vz, g);
   }
 #pragma unroll
   for (int q = 0; q < QQ; ++q) {

@@ -63,13 +63,14 @@ __global__ void __launch_bounds__(256) sweepKernel(const SweepArgs a) {
   if (QQ == 19) {
     const double(&g)[19] = reinterpret_cast<const double(&)[19]>(f);
     if (RELAX == 0) collide_bgk_d3q19<INCOMP>(g, rho, ux, uy, uz, omega, st);
-    if (RELAX == 1) collide_trt_d3q19(g, rho, ux, uy, uz, omega, a.rp.lambda, st);
-    if (RELAX == 2) collide_mrt_d3q19(g, rho, ux, uy, uz, omega, a.rp.omega_bulk, st);
+    if (RELAX == 1 && !INCOMP) collide_trt_d3q19(g, rho, ux, uy, uz, omega, a.rp.lambda, st);
+    if (RELAX == 1 && INCOMP) collide_trt_d3q19_incomp(g, rho, ux, uy, uz, omega, a.rp.lambda, st);
+    if (RELAX == 2) collide_mrt_d3q19<INCOMP>(g, rho, ux, uy, uz, omega, a.rp.omega_bulk, st);
   } else {
     const double(&g)[27] = reinterpret_cast<const double(&)[27]>(f);
-    if (RELAX == 0) collide_bgk_d3q27(g, rho, ux, uy, uz, omega, st);
+    if (RELAX == 0) collide_bgk_d3q27<INCOMP>(g, rho, ux, uy, uz, omega, st);
     if (RELAX == 1) collide_trt_d3q27(g, rho, ux, uy, uz, omega, a.rp.lambda, st);
-    if (RELAX == 2) collide_mrt_d3q27(g, rho, ux, uy, uz, omega, a.rp.omega_bulk, st);
+    if (RELAX == 2) collide_mrt_d3q27<INCOMP>(g, rho, ux, uy, uz, omega, a.rp.omega_bulk, st);
   }
 }
 
@@ -84,8 +85,14 @@ static int launchT(const SweepArgs &a, cudaStream_t st) {
 
 int launchSweep(int QQ, int relax, int kind, const SweepArgs &a, cudaStream_t st) {
   if (kind == 1) {
+    // mus_init_advRel_fluid_incompressible (init/mus_initFluidIncomp_module.f90:73-218):
+    // trt exists for d3q19 only
     if (QQ == 19 && relax == 0) return launchT<19, 0, true>(a, st);
-    return setError(4, "fluid_incompressible: only bgk/d3q19 is built (others are a 'next' row)");
+    if (QQ == 19 && relax == 1) return launchT<19, 1, true>(a, st);
+    if (QQ == 19 && relax == 2) return launchT<19, 2, true>(a, st);
+    if (QQ == 27 && relax == 0) return launchT<27, 0, true>(a, st);
+    if (QQ == 27 && relax == 2) return launchT<27, 2, true>(a, st);
+    return setError(4, "fluid_incompressible: the reference has no trt kernel for this layout");
   }
   if (QQ == 19) {
     if (relax == 0) return launchT<19, 0, false>(a, st);

@@ -162,6 +162,12 @@ class Scheme:
         check(lib.musb200_aux_download(level, out.ctypes.data))
         return out
 
+    def aux_probe(self, level, elemPos):
+        """tracking of one element (1-based position in the level's total list): rho, ux, uy, uz"""
+        out = np.empty(4)
+        check(lib.musb200_aux_probe(level, int(elemPos), ptr(out, P_DBL)))
+        return out
+
     def download_neigh(self, level):
         ld = self.levelDesc[level]
         out = np.zeros(ld.nSize * self.QQ, dtype=np.int32)

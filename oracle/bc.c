@@ -42,6 +42,22 @@ void ora_velocity_bounceback(double *state, const double *bcBuffer, int QQ,
   }
 }
 
+/* mus_init_pdf (mus_flow_module.fpp:422-601), acoustic scaling: state = fEq(rho, vel) +
+ * fNeq(omega, S); S6 = (Sxx, Syy, Szz, Sxy, Syz, Sxz) per element in LATTICE units, omega per
+ * element.  The 3x3 tensor is assembled as at :548-552.                       */
+void ora_init_pdf(int QQ, int incompressible, int nElems, const double *rho, const double *vel,
+                  const double *S6, const double *omega, double *state) {
+  for (int e = 0; e < nElems; ++e) {
+    double fEq[27], fNeq[27];
+    if (incompressible) ora_pdfEq_incomp(QQ, rho[e], vel + 3 * (size_t)e, fEq);
+    else ora_pdfEq(QQ, rho[e], vel + 3 * (size_t)e, fEq);
+    const double *s = S6 + 6 * (size_t)e;
+    const double S[9] = {s[0], s[3], s[5], s[3], s[1], s[4], s[5], s[4], s[2]};
+    ora_nEq_acoustic(QQ, omega[e], S, fNeq);
+    for (int d = 0; d < QQ; ++d) state[(size_t)e * QQ + d] = fEq[d] + fNeq[d];
+  }
+}
+
 void ora_init_equilibrium(int QQ, int incompressible, int nElems, const double *rho,
                           const double *vel /* [nElems][3] */, double *state) {
   for (int e = 0; e < nElems; ++e) {

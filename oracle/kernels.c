@@ -3,6 +3,10 @@
  *
  *   BGK D3Q19  mus/source/compute/mus_compute_d3q19_module.fpp:483-640
  *   TRT D3Q19  mus/source/compute/mus_compute_d3q19_module.fpp:2644-2763
+ *   fluid_incompressible: BGK D3Q19 :1215-1705, TRT D3Q19 :2782-2959,
+ *              MRT D3Q19 mus_compute_mrt_d3q19_module.fpp:466-739,
+ *              MRT D3Q27 mus_compute_mrt_d3q27_module.fpp:374-546,
+ *              BGK D3Q27 = the kCFD kernel with get_pdfEq_incomp_d3q27
  *   MRT D3Q19  mus/source/compute/mus_compute_mrt_d3q19_module.fpp:238-450
  *   BGK D3Q27  mus/source/compute/mus_compute_d3q27_module.fpp:398-517
  *   TRT D3Q27  mus/source/compute/mus_compute_d3q27_module.fpp:601-740
@@ -48,6 +52,13 @@ void ora_mrt_diag(int QQ, double omegaKine, double omegaBulk, double *s /*0-base
     for (int i = 24; i <= 26; ++i) m[i] = 1.83;
     m[27] = 1.61;
   }
+}
+
+/* MMtrD3Q19 / MMivD3Q19 / WMMtrD3Q27 / WMMIvD3Q27 (mus_mrtInit_module.f90:66-301), row-major */
+const double *ora_mrt_matrix(int QQ, int inverse) {
+  if (QQ == 19) return inverse ? &ORA_MMivD3Q19[0][0] : &ORA_MMtrD3Q19[0][0];
+  if (QQ == 27) return inverse ? &ORA_WMMIvD3Q27[0][0] : &ORA_WMMtrD3Q27[0][0];
+  return 0;
 }
 
 /* ======================================================================== */
@@ -161,7 +172,56 @@ static void trt_d3q19(const double *in, double *out, const double *aux,
 }
 
 /* ======================================================================== */
-static void mrt_d3q19(const double *in, double *out, const double *aux,
+/* mus_advRel_kFluidIncomp_rTRT_vStd_lD3Q19, mus_compute_d3q19_module.fpp:2782-2959 */
+static void trt_d3q19_incomp(const double *in, double *out, const double *aux,
+                             const int32_t *neigh, const double *omg, int nSize, int nSolve,
+                             double lambda) {
+  const int QQ = 19;
+  const double div1_3 = 1.0 / 3.0, div1_6 = 1.0 / 6.0, t2cs4inv = 4.5;
+  const double t1x2 = 1.0 / 9.0, t2x2 = 1.0 / 18.0;
+  const double fac1 = t1x2 * t2cs4inv, fac2 = t2x2 * t2cs4inv;
+#pragma omp parallel for schedule(static)
+  for (int e = 1; e <= nSolve; ++e) {
+    const double fN00 = PULL(qN00), f0N0 = PULL(q0N0), f00N = PULL(q00N);
+    const double f100 = PULL(q100), f010 = PULL(q010), f001 = PULL(q001);
+    const double f0NN = PULL(q0NN), f0N1 = PULL(q0N1), f01N = PULL(q01N), f011 = PULL(q011);
+    const double fN0N = PULL(qN0N), f10N = PULL(q10N), fN01 = PULL(qN01), f101 = PULL(q101);
+    const double fNN0 = PULL(qNN0), fN10 = PULL(qN10), f1N0 = PULL(q1N0), f110 = PULL(q110);
+    const double f000 = PULL(19);
+
+    const double rho = AUX(0), u_x = AUX(1), u_y = AUX(2), u_z = AUX(3);
+    const double usq = (u_x * u_x) + (u_y * u_y) + (u_z * u_z);
+    const double feq_common = rho - 1.5 * usq;
+    const double omega = omg[e - 1];
+    const double omega_h = 0.5 * omega;
+    const double asym_omega = 1.0 / (0.5 + lambda / (1.0 / omega - 0.5));
+    const double asym_omega_h = 0.5 * asym_omega;
+
+    SAVE(19) = f000 * (1.0 - omega) + omega * div1_3 * feq_common;
+
+    double ui, sym, asym;
+    const double t2_feq = t2x2 * feq_common;
+#define LINK(fc, tfeq, dv, plus, minus, fp, fm)                 \
+    sym = omega_h * (fp + fm - fc * ui * ui - tfeq);            \
+    asym = asym_omega_h * (fp - fm - dv * ui);                  \
+    SAVE(plus) = fp - sym - asym;                               \
+    SAVE(minus) = fm - sym + asym;
+    ui = u_x + u_y; LINK(fac2, t2_feq, div1_6, q110, qNN0, f110, fNN0)
+    ui = u_x - u_y; LINK(fac2, t2_feq, div1_6, q1N0, qN10, f1N0, fN10)
+    ui = u_x + u_z; LINK(fac2, t2_feq, div1_6, q101, qN0N, f101, fN0N)
+    ui = u_x - u_z; LINK(fac2, t2_feq, div1_6, q10N, qN01, f10N, fN01)
+    ui = u_y + u_z; LINK(fac2, t2_feq, div1_6, q011, q0NN, f011, f0NN)
+    ui = u_y - u_z; LINK(fac2, t2_feq, div1_6, q01N, q0N1, f01N, f0N1)
+    const double t1_feq = t1x2 * feq_common;
+    ui = u_y; LINK(fac1, t1_feq, div1_3, q010, q0N0, f010, f0N0)
+    ui = u_x; LINK(fac1, t1_feq, div1_3, q100, qN00, f100, fN00)
+    ui = u_z; LINK(fac1, t1_feq, div1_3, q001, q00N, f001, f00N)
+#undef LINK
+  }
+}
+
+/* ======================================================================== */
+static void mrt_d3q19(int incomp, const double *in, double *out, const double *aux,
                       const int32_t *neigh, const double *omg, int nSize, int nSolve,
                       double omegaBulk) {
   const int QQ = 19;
@@ -200,16 +260,18 @@ static void mrt_d3q19(const double *in, double *out, const double *aux,
     s[10] = omegaKine; s[12] = omegaKine;
     s[14] = div1_4 * omegaKine; s[15] = div1_4 * omegaKine; s[16] = div1_4 * omegaKine;
 
-    const double meq2 = rho * (u_x * u_x + u_y * u_y + u_z * u_z);
-    const double meq10 = rho * 3.0 * u_x * u_x - meq2;
-    const double meq12 = rho * (u_y * u_y - u_z * u_z);
+    /* incompressible (mus_compute_mrt_d3q19_module.fpp:578-603): rho0 = 1 replaces rho */
+    const double meq2 = incomp ? u_x * u_x + u_y * u_y + u_z * u_z
+                               : rho * (u_x * u_x + u_y * u_y + u_z * u_z);
+    const double meq10 = incomp ? 3.0 * u_x * u_x - meq2 : rho * 3.0 * u_x * u_x - meq2;
+    const double meq12 = incomp ? u_y * u_y - u_z * u_z : rho * (u_y * u_y - u_z * u_z);
     const double mout2 = s[2] * (m2 - meq2);
     const double m14 = f110 + fNN0 - f1N0 - fN10;
-    const double mout14 = s[14] * (m14 - rho * u_x * u_y);
+    const double mout14 = s[14] * (m14 - (incomp ? u_x * u_y : rho * u_x * u_y));
     const double m15 = f011 + f0NN - f01N - f0N1;
-    const double mout15 = s[15] * (m15 - rho * u_y * u_z);
+    const double mout15 = s[15] * (m15 - (incomp ? u_y * u_z : rho * u_y * u_z));
     const double m16 = f101 + fN0N - f10N - fN01;
-    const double mout16 = s[16] * (m16 - rho * u_x * u_z);
+    const double mout16 = s[16] * (m16 - (incomp ? u_x * u_z : rho * u_x * u_z));
 
     const double sum6 = sum1 + m6 - m8 * 2.0;
     const double sum7 = sum4 - sum5;
@@ -283,18 +345,20 @@ static void mrt_d3q19(const double *in, double *out, const double *aux,
 }
 
 /* ======================================================================== */
-static void bgk_generic(int QQ, const double *in, double *out, const double *aux,
+static void bgk_generic(int QQ, int incomp, const double *in, double *out, const double *aux,
                         const int32_t *neigh, const double *omg, int nSize, int nSolve) {
   /* D3Q27 BGK (mus_compute_d3q27_module.fpp:398-517) and the NoOpt BGK
    * (mus_compute_bgk_module.fpp:126-157) are the same arithmetic:
-   * out = f - omega*(f - fEq) with fEq = pdfEq_ptr(rho, vel).                 */
+   * out = f - omega*(f - fEq) with fEq = pdfEq_ptr(rho, vel); for
+   * fluid_incompressible the pointer is get_pdfEq_incomp_d3q27
+   * (mus_scheme_derived_quantities_type_module.f90:751-811).                  */
 #pragma omp parallel for schedule(static)
   for (int e = 1; e <= nSolve; ++e) {
     double f[27], fEq[27];
     for (int d = 1; d <= QQ; ++d) f[d - 1] = PULL(d);
     const double rho = AUX(0);
     const double vel[3] = {AUX(1), AUX(2), AUX(3)};
-    ora_pdfEq(QQ, rho, vel, fEq);
+    if (incomp) ora_pdfEq_incomp(QQ, rho, vel, fEq); else ora_pdfEq(QQ, rho, vel, fEq);
     const double omega = omg[e - 1];
     for (int d = 1; d <= QQ; ++d) SAVE(d) = f[d - 1] - omega * (f[d - 1] - fEq[d - 1]);
   }
@@ -341,7 +405,7 @@ static void trt_d3q27(const double *in, double *out, const double *aux,
 }
 
 /* ======================================================================== */
-static void mrt_d3q27(const double *in, double *out, const double *aux,
+static void mrt_d3q27(int incomp, const double *in, double *out, const double *aux,
                       const int32_t *neigh, const double *omg, int nSize, int nSolve,
                       double omegaBulk) {
   const int QQ = 27;
@@ -398,14 +462,16 @@ static void mrt_d3q27(const double *in, double *out, const double *aux,
     mom[27] = 2.0 * (f[1] + f[2] + f[3] + f[4] + f[5] + f[6]) + 4.0 * (-sum_7_10 - sum_11_18)
             + 8.0 * (sum_19_26) - f[27];
 
+    /* incompressible (mus_compute_mrt_d3q27_module.fpp:516-526): rho0 = 1 in meq(2:10) */
+    const double rq = incomp ? 1.0 : rho;
     meq[1] = rho;
-    meq[2] = rho * u_x; meq[3] = rho * u_y; meq[4] = rho * u_z;
+    meq[2] = rq * u_x; meq[3] = rq * u_y; meq[4] = rq * u_z;
     meq[5] = meq[2] * u_y;
     meq[6] = meq[3] * u_z;
     meq[7] = meq[4] * u_x;
-    meq[8] = rho * (2.0 * u_x * u_x - u_y * u_y - u_z * u_z);
-    meq[9] = rho * (u_y * u_y - u_z * u_z);
-    meq[10] = rho * (u_x * u_x + u_y * u_y + u_z * u_z);
+    meq[8] = rq * (2.0 * u_x * u_x - u_y * u_y - u_z * u_z);
+    meq[9] = rq * (u_y * u_y - u_z * u_z);
+    meq[10] = rq * (u_x * u_x + u_y * u_y + u_z * u_z);
 
     for (int i = 5; i <= 9; ++i) s[i] = omg[e - 1];
     for (int i = 1; i <= QQ; ++i) mneq[i] = s[i] * (mom[i] - meq[i]);
@@ -419,7 +485,7 @@ static void mrt_d3q27(const double *in, double *out, const double *aux,
 }
 
 /* ======================================================================== */
-static void mrt_noopt(int QQ, const double *in, double *out, const double *aux,
+static void mrt_noopt(int QQ, int incomp, const double *in, double *out, const double *aux,
                       const int32_t *neigh, const double *omg, int nSize, int nSolve,
                       double omegaBulk) {
   /* M^-1 S M (f - fEq); the D3Q27 NoOpt variant (mrt_d3q27:88-185) has the
@@ -430,7 +496,7 @@ static void mrt_noopt(int QQ, const double *in, double *out, const double *aux,
     for (int d = 1; d <= QQ; ++d) f[d - 1] = PULL(d);
     const double rho = AUX(0);
     const double vel[3] = {AUX(1), AUX(2), AUX(3)};
-    ora_pdfEq(QQ, rho, vel, fEq);
+    if (incomp) ora_pdfEq_incomp(QQ, rho, vel, fEq); else ora_pdfEq(QQ, rho, vel, fEq);
     for (int d = 0; d < QQ; ++d) fneq[d] = f[d] - fEq[d];
     for (int i = 0; i < QQ; ++i) {
       double acc = 0.0;
@@ -452,21 +518,33 @@ static void mrt_noopt(int QQ, const double *in, double *out, const double *aux,
 int ora_compute(int relax, int QQ, int incomp, const double *in, double *out,
                 const double *aux, const int32_t *neigh, const double *omega,
                 int nSize, int nSolve, const ora_relax_t *rp) {
+  /* dispatch of mus_init_advRel_fluid / _fluid_incompressible
+   * (mus/source/init/mus_initFluid_module.f90, mus_initFluidIncomp_module.f90:73-218);
+   * fluid_incompressible + trt exists for d3q19 only (the reference aborts otherwise) */
   if (QQ == 19 && relax == ORA_BGK) { bgk_d3q19(incomp, in, out, aux, neigh, omega, nSize, nSolve); return 0; }
-  if (incomp) return -1; /* other incompressible variants: "next" row n1 */
-  if (QQ == 19 && relax == ORA_TRT) { trt_d3q19(in, out, aux, neigh, omega, nSize, nSolve, rp->lambda); return 0; }
-  if (QQ == 19 && relax == ORA_MRT) { mrt_d3q19(in, out, aux, neigh, omega, nSize, nSolve, rp->omegaBulk); return 0; }
-  if (QQ == 27 && relax == ORA_BGK) { bgk_generic(27, in, out, aux, neigh, omega, nSize, nSolve); return 0; }
-  if (QQ == 27 && relax == ORA_TRT) { trt_d3q27(in, out, aux, neigh, omega, nSize, nSolve, rp->lambda); return 0; }
-  if (QQ == 27 && relax == ORA_MRT) { mrt_d3q27(in, out, aux, neigh, omega, nSize, nSolve, rp->omegaBulk); return 0; }
+  if (QQ == 19 && relax == ORA_TRT) {
+    if (incomp) trt_d3q19_incomp(in, out, aux, neigh, omega, nSize, nSolve, rp->lambda);
+    else trt_d3q19(in, out, aux, neigh, omega, nSize, nSolve, rp->lambda);
+    return 0;
+  }
+  if (QQ == 19 && relax == ORA_MRT) { mrt_d3q19(incomp, in, out, aux, neigh, omega, nSize, nSolve, rp->omegaBulk); return 0; }
+  if (QQ == 27 && relax == ORA_BGK) { bgk_generic(27, incomp, in, out, aux, neigh, omega, nSize, nSolve); return 0; }
+  if (QQ == 27 && relax == ORA_TRT && !incomp) { trt_d3q27(in, out, aux, neigh, omega, nSize, nSolve, rp->lambda); return 0; }
+  if (QQ == 27 && relax == ORA_MRT) { mrt_d3q27(incomp, in, out, aux, neigh, omega, nSize, nSolve, rp->omegaBulk); return 0; }
+  return -1;
+}
+
+int ora_compute_noopt_kind(int relax, int QQ, int incomp, const double *in, double *out,
+                           const double *aux, const int32_t *neigh, const double *omega,
+                           int nSize, int nSolve, const ora_relax_t *rp) {
+  if (QQ != 19 && QQ != 27) return -1;
+  if (relax == ORA_BGK) { bgk_generic(QQ, incomp, in, out, aux, neigh, omega, nSize, nSolve); return 0; }
+  if (relax == ORA_MRT) { mrt_noopt(QQ, incomp, in, out, aux, neigh, omega, nSize, nSolve, rp->omegaBulk); return 0; }
   return -1;
 }
 
 int ora_compute_noopt(int relax, int QQ, const double *in, double *out,
                       const double *aux, const int32_t *neigh, const double *omega,
                       int nSize, int nSolve, const ora_relax_t *rp) {
-  if (QQ != 19 && QQ != 27) return -1;
-  if (relax == ORA_BGK) { bgk_generic(QQ, in, out, aux, neigh, omega, nSize, nSolve); return 0; }
-  if (relax == ORA_MRT) { mrt_noopt(QQ, in, out, aux, neigh, omega, nSize, nSolve, rp->omegaBulk); return 0; }
-  return -1;
+  return ora_compute_noopt_kind(relax, QQ, 0, in, out, aux, neigh, omega, nSize, nSolve, rp);
 }

@@ -69,6 +69,12 @@ int ora_compute(int relax, int QQ, int incompressible, const double *in, double 
 int ora_compute_noopt(int relax, int QQ, const double *in, double *out,
                       const double *aux, const int32_t *neigh, const double *omega,
                       int nSize, int nSolve, const ora_relax_t *rp);
+/* the same with the incompressible equilibrium (mus_advRel_kFluidIncomp_rMRT_vStdNoOpt_lD3Q19,
+ * mus_compute_mrt_d3q19_module.fpp:751-866, written there with explicit m_eq) */
+int ora_compute_noopt_kind(int relax, int QQ, int incompressible, const double *in, double *out,
+                           const double *aux, const int32_t *neigh, const double *omega,
+                           int nSize, int nSolve, const ora_relax_t *rp);
+const double *ora_mrt_matrix(int QQ, int inverse); /* [QQ][QQ] row-major */
 void ora_mrt_diag(int QQ, double omegaKine, double omegaBulk, double *s_mrt);
 
 /* ---- connectivity (mus_connectivity_module.fpp:73-179) ------------------ */
@@ -89,6 +95,13 @@ void ora_velocity_bounceback(double *state, const double *bcBuffer, int QQ,
 /* mus_init_pdf with zero strain rate: state = fEq(rho, vel) */
 void ora_init_equilibrium(int QQ, int incompressible, int nElems, const double *rho,
                           const double *vel, double *state);
+
+/* mus_init_pdf with the acoustic non-equilibrium part getNEq_acoustic
+ * (mus_flow_module.fpp:422-601, mus_derivedQuantities_module.fpp:441-478) */
+void ora_nEq_acoustic(int QQ, double omega, const double *S /* 3x3 column-major */, double *nEq);
+void ora_init_pdf(int QQ, int incompressible, int nElems, const double *rho, const double *vel,
+                  const double *S6 /* [nElems][6] Sxx,Syy,Szz,Sxy,Syz,Sxz */,
+                  const double *omega /* [nElems] */, double *state);
 
 /* ---- ghost interpolation (mus/source/intp) ----------------------------- */
 void ora_fill_my_ghosts_from_finer_avg(int QQ, int incomp, const double *sState,

@@ -61,6 +61,8 @@ def lib():
         _LIB.ora_cxDir.restype = ctypes.POINTER(ctypes.c_int)
         _LIB.ora_cxDirInv.restype = ctypes.POINTER(ctypes.c_int)
         _LIB.ora_weights.restype = _dp
+        _LIB.ora_mrt_matrix.restype = _dp
+        _LIB.ora_nEq_acoustic.argtypes = [ctypes.c_int, ctypes.c_double, _dp, _dp]
     return _LIB
 
 
@@ -382,6 +384,20 @@ class Scheme:
         st = self.state[self.nNext]
         lib().ora_init_equilibrium(QQ, self.incomp, ld.nElems, _d(rho), _d(vel), _d(st))
         self.state[self.nNow][:] = st            # mus_flow_module.fpp:181-185
+        self.calc_aux(self.state[self.nNext], local_only=True)
+
+    # -- mus_init_pdf with the strain-rate part: f = fEq(rho, u) + fNeq(omega, S) ----------
+    def init_pdf(self, rho, vel, S6):
+        """S6[nElems][6] = (Sxx, Syy, Szz, Sxy, Syz, Sxz) in lattice units (mus_flow_module.fpp:484-589)"""
+        ld, QQ = self.ld, self.QQ
+        rho = np.ascontiguousarray(rho, dtype=np.float64)
+        vel = np.ascontiguousarray(vel, dtype=np.float64)
+        S6 = np.ascontiguousarray(S6, dtype=np.float64)
+        assert rho.shape == (ld.nElems,) and vel.shape == (ld.nElems, 3) and S6.shape == (ld.nElems, 6)
+        omega = np.ascontiguousarray(1.0 / (3.0 * self.visc[:ld.nElems] + 0.5))
+        st = self.state[self.nNext]
+        lib().ora_init_pdf(QQ, self.incomp, ld.nElems, _d(rho), _d(vel), _d(S6), _d(omega), _d(st))
+        self.state[self.nNow][:] = st
         self.calc_aux(self.state[self.nNext], local_only=True)
 
     def calc_aux(self, state, local_only=False):

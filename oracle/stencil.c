@@ -203,9 +203,71 @@ static void pdfEq_incomp_d3q19(double rho, const double v[3], double *fEq) {
   f[19] = (1.0 / 3.0) * rho - (1.0 / 3.0) * rho0 * s[1];
 }
 
+static void pdfEq_incomp_d3q27(double rho, const double v[3], double *fEq) {
+  double s[35];
+  sigma_d3q27(v, s);
+  const double rho0 = 1.0;
+  const double r27 = (2.0 / 27.0) * rho, r54 = (1.0 / 54.0) * rho, r216 = (1.0 / 216.0) * rho;
+  const double z27 = (2.0 / 27.0) * rho0, z54 = (1.0 / 54.0) * rho0, z216 = (1.0 / 216.0) * rho0;
+  double *f = fEq - 1;
+  f[1] = r27 - z27 * (3.0 * v[0] - s[4] + s[1]);
+  f[2] = r27 - z27 * (3.0 * v[1] - s[3] + s[1]);
+  f[3] = r27 - z27 * (3.0 * v[2] - s[2] + s[1]);
+  f[4] = r27 + z27 * (3.0 * v[0] + s[4] - s[1]);
+  f[5] = r27 + z27 * (3.0 * v[1] + s[3] - s[1]);
+  f[6] = r27 + z27 * (3.0 * v[2] + s[2] - s[1]);
+  f[7] = r54 + z54 * (s[10] - s[20] - s[1]);
+  f[8] = r54 + z54 * (s[9] - s[19] - s[1]);
+  f[9] = r54 + z54 * (s[9] + s[19] - s[1]);
+  f[10] = r54 + z54 * (s[10] + s[20] - s[1]);
+  f[11] = r54 + z54 * (s[12] - s[22] - s[1]);
+  f[12] = r54 + z54 * (s[11] + s[21] - s[1]);
+  f[13] = r54 + z54 * (s[11] - s[21] - s[1]);
+  f[14] = r54 + z54 * (s[12] + s[22] - s[1]);
+  f[15] = r54 + z54 * (s[14] - s[24] - s[1]);
+  f[16] = r54 + z54 * (s[13] - s[23] - s[1]);
+  f[17] = r54 + z54 * (s[13] + s[23] - s[1]);
+  f[18] = r54 + z54 * (s[14] + s[24] - s[1]);
+  f[19] = r216 - z216 * (s[18] - s[8] + s[1]);
+  f[20] = r216 - z216 * (s[17] - s[7] + s[1]);
+  f[21] = r216 - z216 * (s[16] - s[6] + s[1]);
+  f[22] = r216 + z216 * (s[15] + s[5] - s[1]);
+  f[23] = r216 - z216 * (s[15] - s[5] + s[1]);
+  f[24] = r216 + z216 * (s[16] + s[6] - s[1]);
+  f[25] = r216 + z216 * (s[17] + s[7] - s[1]);
+  f[26] = r216 + z216 * (s[18] + s[8] - s[1]);
+  f[27] = (8.0 / 27.0) * rho - (8.0 / 27.0) * rho0 * s[1];
+}
+
 void ora_pdfEq_incomp(int QQ, double rho, const double vel[3], double *fEq) {
   if (QQ == 19) pdfEq_incomp_d3q19(rho, vel, fEq);
-  /* D3Q27 incompressible: not restated yet ("next" row n1) */
+  else pdfEq_incomp_d3q27(rho, vel, fEq);
+}
+
+/* getNEq_acoustic (mus_derivedQuantities_module.fpp:441-478): non-equilibrium part from the
+ * strain rate S(3,3) (Fortran column-major: S[j*3+i] = Sxx(i,j)), converted to the
+ * post-collision form of the PULL build (convPrePost :584-595).                */
+void ora_nEq_acoustic(int QQ, double omega, const double *S, double *nEq) {
+  const double cs2 = 1.0 / 3.0, cs4inv = 9.0;
+  const int *cx = ora_cxDir(QQ);
+  const double *w = ora_weights(QQ);
+  const double nu = cs2 * (1.0 / omega - 0.5);
+  double tau[9];
+  for (int k = 0; k < 9; ++k) tau[k] = 2.0 * nu * S[k];
+  const double coeff = cs4inv / (2.0 - omega);
+  for (int d = 0; d < QQ; ++d) {
+    double acc = 0.0;
+    for (int j = 0; j < 3; ++j) {
+      for (int i = 0; i < 3; ++i)
+        acc = acc + tau[j * 3 + i] * (double)cx[3 * d + i] * (double)cx[3 * d + j];
+      acc = acc - cs2 * tau[j * 3 + j];
+    }
+    nEq[d] = -w[d] * acc * coeff;
+  }
+  if (omega != 1.0) {
+    const double conv = 1.0 / (1.0 - omega);
+    for (int d = 0; d < QQ; ++d) nEq[d] = nEq[d] / conv;
+  }
 }
 
 /* ------------------------------------------------------------------------ */

@@ -1,18 +1,30 @@
 #!/usr/bin/env python3
 """Copies the reference's own golden result files that pin the hot path into
-tests/golden/ (they are DATA of the reference's test-suite, 16 lines each) so
-that the oracle can be checked on machines without /root/reference.
+tests/golden/ (they are DATA of the reference's test-suite) so that the oracle and
+the device path can be checked on machines without /root/reference.
 
   mus/examples/fluid/benchmark/gaussianPulse/reference/
-     gaussianPulse_pressAlongLength_p00000_t10.001E+00.res   (level 4, np=2, t=10.001)
+     gaussianPulse_pressAlongLength_p00000_t10.001E+00.res
+        fluid / bgk / d3q19, level 4, np=2, line sample at t=10.001 (9506 steps)
+  mus/examples/fluid_incompressible/benchmark/TaylorGreenVortex/TGV_Simple/
+     TGV_Simple_Re800/reference/TGV_Simple_Re800_probeAtCenter_p00000.res
+        fluid_incompressible / mrt / d3q19, level 6 (64^3), np=12, centre probe every step
+        (1962 samples of velocity_phy, pressure_phy)
+     TGV_Simple_Re1600/reference/TGV_Simple_Re1600_kE_all_p00000.res
+        fluid_incompressible / bgk / d3q19, level 7 (128^3), np=8, sum of kinetic_energy_phy
+        over all elements every step (237 samples)
 
 Run in the build container only:  python tests/golden/make_golden.py
 """
 import os
 import shutil
 
-REF = "/root/reference/mus/examples/fluid/benchmark/gaussianPulse/reference"
+EX = "/root/reference/mus/examples"
+TGV = EX + "/fluid_incompressible/benchmark/TaylorGreenVortex/TGV_Simple"
 HERE = os.path.dirname(os.path.abspath(__file__))
-for f in ("gaussianPulse_pressAlongLength_p00000_t10.001E+00.res",):
-    shutil.copy(os.path.join(REF, f), os.path.join(HERE, f))
+for d, f in ((EX + "/fluid/benchmark/gaussianPulse/reference",
+              "gaussianPulse_pressAlongLength_p00000_t10.001E+00.res"),
+             (TGV + "/TGV_Simple_Re800/reference", "TGV_Simple_Re800_probeAtCenter_p00000.res"),
+             (TGV + "/TGV_Simple_Re1600/reference", "TGV_Simple_Re1600_kE_all_p00000.res")):
+    shutil.copy(os.path.join(d, f), os.path.join(HERE, f))
     print("copied", f)

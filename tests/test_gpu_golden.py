@@ -1,0 +1,86 @@
+"""GPU vs the REFERENCE'S OWN golden vectors, through the C ABI: the device path is run on the
+golden cases (initial state built by the host as mus_init_pdf does) and compared with the
+committed .res files by the reference's criterion numpy.allclose(rtol=1e-10, atol=1e-5)
+(pysys-extensions/apes/apeshelper.py:90-123), plus tighter bounds that hold for this build."""
+import numpy as np
+import pytest
+
+from golden_cases import (GOLD_PULSE, GOLD_TGV800, GOLD_TGV1600, gaussian_pulse_setup,
+                          kinetic_energy_phy, pulse_line_elements, pulse_track, tgv800_row,
+                          tgv800_setup, tgv1600_sample_steps, tgv1600_setup)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mb():
+    import musubi_b200
+    musubi_b200.mus_init(0, 1, 0)
+    yield musubi_b200
+    musubi_b200.mus_finalize()
+
+
+def device_scheme(mb, ref, ident, level, omega_bulk=None):
+    ld = mb.LevelDesc(level, 19, "periodic")
+    assert np.array_equal(ld.neigh, ref.ld.neigh)
+    omega = float(1.0 / (3.0 * ref.visc[0] + 0.5))
+    sch = mb.Scheme(ident, ld, omega, omega_bulk=omega if omega_bulk is None else omega_bulk)
+    sch.upload_state(level, ref.state[ref.nNow], ref.state[ref.nNext])
+    return ld, sch
+
+
+def test_gaussian_pulse_device_matches_reference_golden(mb, oracle):
+    gold = np.loadtxt(GOLD_PULSE, comments="#")
+    ref, phys, bary, nsteps = gaussian_pulse_setup(oracle)
+    ld, sch = device_scheme(mb, ref, {"kind": "fluid", "relaxation": "bgk", "layout": "d3q19"}, 4)
+    sch.do_computation(nsteps)                       # 9506 steps in one call
+    aux = sch.download_aux(4).reshape(-1, 4)
+    got = pulse_track(aux, pulse_line_elements(ref, bary), phys, bary)
+    assert np.allclose(got, gold, rtol=1e-10, atol=1e-5)
+    assert np.max(np.abs(got[:, 3] / gold[:, 3] - 1.0)) < 1e-13     # density_phy
+    assert np.max(np.abs(got[:, 4] / gold[:, 4] - 1.0)) < 1e-13     # pressure_phy
+    assert np.max(np.abs(got[:, 5:] - gold[:, 5:])) < 2e-11         # velocity_phy
+    sch.destroy()
+
+
+def test_tgv_re800_device_probe_series_matches_reference_golden(mb, oracle):
+    """fluid_incompressible / mrt / d3q19 at 64^3: all 1962 samples of the centre probe."""
+    gold = np.loadtxt(GOLD_TGV800, comments="#")
+    ref, phys, probe, nsteps, omega_bulk = tgv800_setup(oracle)
+    ident = {"kind": "fluid_incompressible", "relaxation": "mrt", "layout": "d3q19"}
+    ld, sch = device_scheme(mb, ref, ident, 6, omega_bulk)
+    rows = [tgv800_row(0, ref.aux.reshape(-1, 4)[probe], phys)]     # initAuxField of the host
+    for k in range(1, nsteps + 1):
+        sch.do_computation(1)
+        rows.append(tgv800_row(k, sch.aux_probe(6, probe + 1), phys))
+    got = np.array(rows)
+    assert got.shape == gold.shape
+    assert np.allclose(got, gold, rtol=1e-10, atol=1e-5)
+    assert np.max(np.abs(got[:, 1:4] - gold[:, 1:4])) < 5e-11
+    assert np.max(np.abs(got[:, 4] / gold[:, 4] - 1.0)) < 1e-14
+    # and the device equals the oracle bit for bit on the first 60 steps
+    ref.run(60)
+    ld2, sch2 = device_scheme(mb, tgv800_setup(oracle)[0], ident, 6, omega_bulk)
+    sch2.do_computation(60)
+    n = ld2.nFluid * 19
+    assert np.array_equal(sch2.download_state(6)[:n], ref.state[ref.nNext][:n])
+    sch.destroy()
+
+
+def test_tgv_re1600_device_kinetic_energy_matches_reference_golden(mb, oracle):
+    """fluid_incompressible / bgk / d3q19 at 128^3: all 237 samples of the summed kinetic energy."""
+    gold = np.loadtxt(GOLD_TGV1600, comments="#")
+    ref, phys, nsteps = tgv1600_setup(oracle)
+    steps = set(tgv1600_sample_steps(gold, phys).tolist())
+    ident = {"kind": "fluid_incompressible", "relaxation": "bgk", "layout": "d3q19"}
+    ld, sch = device_scheme(mb, ref, ident, 7)
+    got = [kinetic_energy_phy(ref.aux.reshape(-1, 4), ld.nFluid, phys)]
+    for k in range(1, nsteps + 1):
+        sch.do_computation(1)
+        if k in steps:
+            got.append(kinetic_energy_phy(sch.download_aux(7).reshape(-1, 4), ld.nFluid, phys))
+    got = np.array(got)
+    assert got.shape == (gold.shape[0],)
+    assert np.allclose(got, gold[:, 1], rtol=1e-10, atol=1e-5)
+    assert np.max(np.abs(got / gold[:, 1] - 1.0)) < 1e-11
+    sch.destroy()

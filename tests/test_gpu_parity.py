@@ -18,6 +18,10 @@ KERNELS = [
     ({"kind": "fluid", "relaxation": "trt", "layout": "d3q27"}, 1.7),
     ({"kind": "fluid", "relaxation": "mrt", "layout": "d3q27"}, 1.9),
     ({"kind": "fluid_incompressible", "relaxation": "bgk", "layout": "d3q19"}, 1.7),
+    ({"kind": "fluid_incompressible", "relaxation": "trt", "layout": "d3q19"}, 1.7),
+    ({"kind": "fluid_incompressible", "relaxation": "mrt", "layout": "d3q19"}, 1.8),
+    ({"kind": "fluid_incompressible", "relaxation": "bgk", "layout": "d3q27"}, 1.6),
+    ({"kind": "fluid_incompressible", "relaxation": "mrt", "layout": "d3q27"}, 1.9),
 ]
 
 
@@ -62,8 +66,9 @@ def test_neighbour_list_bit_exact(mb, oracle):
         sch.destroy()
 
 
-@pytest.mark.parametrize("ident,omega", [KERNELS[1], KERNELS[5], KERNELS[6]],
-                         ids=["trt-d3q19", "mrt-d3q27", "bgk-d3q19-incomp"])
+@pytest.mark.parametrize("ident,omega", [KERNELS[1], KERNELS[5], KERNELS[6], KERNELS[8], KERNELS[10]],
+                         ids=["trt-d3q19", "mrt-d3q27", "bgk-d3q19-incomp", "mrt-d3q19-incomp",
+                              "mrt-d3q27-incomp"])
 def test_lid_driven_cavity_matches_oracle(mb, oracle, ident, omega):
     level, nsteps = 4, 150
     ld, old, ref, sch = make_pair(mb, oracle, level, ident, omega, kind="cavity", ic="rest",

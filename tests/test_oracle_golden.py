@@ -1,51 +1,20 @@
-"""Pins the CPU oracle against the reference's own golden vector for this path:
-mus/examples/fluid/benchmark/gaussianPulse (fluid / BGK / D3Q19, predefined cube
-level 4, periodic, np=2, 9506 steps), compared exactly as the reference's pysys
-test does: numpy.allclose(rtol=1e-10, atol=1e-5)
-(pysys-extensions/apes/apeshelper.py:90-123)."""
-import math
-import os
-
+"""Pins the CPU oracle against the reference's own golden vectors for this path, compared
+exactly as the reference's pysys tests do: numpy.allclose(rtol=1e-10, atol=1e-5)
+(pysys-extensions/apes/apeshelper.py:90-123):
+  gaussianPulse      fluid / bgk / d3q19, level 4, periodic, np=2, 9506 steps, line sample
+  TGV_Simple_Re800   fluid_incompressible / mrt / d3q19, 64^3, np=12, centre probe EVERY step
+                     (1962 samples) -- also pins mus_init_pdf with the acoustic f_neq
+  TGV_Simple_Re1600  fluid_incompressible / bgk / d3q19, 128^3, np=8, sum of kinetic energy"""
 import numpy as np
 import pytest
 
-GOLD = os.path.join(os.path.dirname(__file__), "golden",
-                    "gaussianPulse_pressAlongLength_p00000_t10.001E+00.res")
-
-
-def gaussian_pulse_setup(mo, nranks=1, rank=0):
-    """musubi.lua of the example restated (values, not code)."""
-    length, level = 10.0, 4
-    dx = length / 2.0 ** level
-    nu_phy, cs_phy, rho0 = 0.01, 343.0, 1.0
-    cs_lat = 1.0 / math.sqrt(3.0)
-    dt = cs_lat / cs_phy * dx
-    phys = mo.Physics(dx, dt, rho0)
-    nu_lat = nu_phy / phys.fac_visc
-    omega = 1.0 / (3.0 * nu_lat + 0.5)
-    nsteps = int(math.ceil(10.0 / dt))
-    ld = mo.build_level_desc(level, 19, "periodic", rank, nranks)
-    sch = mo.Scheme(ld, "bgk", "fluid", omega=omega)
-    sch.visc[:] = nu_lat
-    bary = mo.barycenters(ld, (0.0, 0.0, 0.0), length)
-    r = (bary[:, 0] - 5.0) ** 2 + (bary[:, 1] - 5.0) ** 2 + (bary[:, 2] - 5.0) ** 2
-    p = rho0 * cs_phy ** 2 + 1.20 * np.exp((-math.log(2.0) / 1.0 ** 2) * r)
-    rho = p * 3.0 * (1.0 / phys.fac_press)        # rho*cs2inv*inv_p, mus_flow_module.fpp:527
-    sch.init_equilibrium(rho, np.zeros(3))
-    return sch, phys, bary, nsteps
+from golden_cases import (GOLD_PULSE as GOLD, GOLD_TGV800, GOLD_TGV1600, gaussian_pulse_setup,
+                          kinetic_energy_phy, pulse_line_elements, pulse_track, tgv800_row,
+                          tgv800_setup, tgv1600_sample_steps, tgv1600_setup)
 
 
 def track_line(sch, phys, bary):
-    """tracking shape canoND origin (0, 5, 5) vec (10,0,0): the cells cut by the line;
-    the 16 cells with barycentre (x, 5.3125, 5.3125) as in the golden file."""
-    sel = np.nonzero((np.abs(bary[:sch.ld.nFluid, 1] - 5.3125) < 1e-9)
-                     & (np.abs(bary[:sch.ld.nFluid, 2] - 5.3125) < 1e-9))[0]
-    sel = sel[np.argsort(bary[sel, 0])]
-    aux = sch.aux.reshape(-1, 4)[sel]
-    dens = aux[:, 0] * phys.rho0
-    press = aux[:, 0] * (1.0 / 3.0) * phys.fac_press
-    vel = aux[:, 1:4] * phys.fac_vel
-    return np.column_stack([bary[sel], dens, press, vel])
+    return pulse_track(sch.aux.reshape(-1, 4), pulse_line_elements(sch, bary), phys, bary)
 
 
 def test_gaussian_pulse_matches_reference_golden(oracle):
@@ -80,3 +49,39 @@ def test_gaussian_pulse_two_ranks_identical(oracle):
         assert np.array_equal(got, ref[off:off + s.ld.nFluid])
         off += s.ld.nFluid
     assert gold.shape == (16, 8)
+
+
+def test_tgv_re800_probe_series_matches_reference_golden(oracle):
+    """every one of the 1962 samples of the reference's centre probe (u, v, w, p)"""
+    gold = np.loadtxt(GOLD_TGV800, comments="#")
+    sch, phys, probe, nsteps, _ = tgv800_setup(oracle)
+    assert nsteps == 1961 and gold.shape == (nsteps + 1, 5)
+    rows = []
+    for k in range(nsteps + 1):
+        rows.append(tgv800_row(k, sch.aux.reshape(-1, 4)[probe], phys))
+        if k < nsteps:
+            sch.step()
+    got = np.array(rows)
+    assert np.allclose(got, gold, rtol=1e-10, atol=1e-5)            # the reference's criterion
+    assert np.max(np.abs(got[:, 1:4] - gold[:, 1:4])) < 5e-11       # velocity_phy, absolute
+    assert np.max(np.abs(got[:, 4] / gold[:, 4] - 1.0)) < 1e-14     # pressure_phy
+    assert np.max(np.abs(got[:, 0] - gold[:, 0])) < 1e-12           # time axis = k*dt
+
+
+def test_tgv_re1600_kinetic_energy_matches_reference_golden(oracle):
+    """the first 13 of the 237 samples (the GPU test covers all of them)"""
+    gold = np.loadtxt(GOLD_TGV1600, comments="#")
+    sch, phys, nsteps = tgv1600_setup(oracle)
+    steps = tgv1600_sample_steps(gold, phys)
+    assert nsteps == 471 and steps[-1] == nsteps and gold.shape == (237, 2)
+    n = 24
+    got = []
+    for k in range(n + 1):
+        if k in steps:
+            got.append(kinetic_energy_phy(sch.aux.reshape(-1, 4), sch.ld.nFluid, phys))
+        if k < n:
+            sch.step()
+    got = np.array(got)
+    assert len(got) == 13
+    assert np.allclose(got, gold[:len(got), 1], rtol=1e-10, atol=1e-5)
+    assert np.max(np.abs(got / gold[:len(got), 1] - 1.0)) < 1e-12
