@@ -132,8 +132,22 @@ int musb200_set_viscosity(int level, const double *visc, double visc_uniform);
 int musb200_bc_elembuffer(int level, int nBcElems, const int32_t *bc_elemBuffer);
 int musb200_bc_register(int level, int bc_id, int bc_kind, int nLinks, const int32_t *links,
                         const int32_t *outPos, const int32_t *posInBuffer, const int32_t *iDir);
-/* per-link boundary values in LATTICE units (velocity: 3 per link; pressure:
- * 1 per link as lattice density), evaluated by the host's spacetime function */
+/* boundaries that read neighbours along the inward normal (pressure_expol: nNeighs = 2,
+ * neighBufferPre_nNext; pressure_antibounceback: nNeighs = 1, neighBufferPost;
+ * mus_bc_header_module.fpp:1036-1060), to be called after musb200_bc_register:
+ * elemPos        globBC%elemLvl(level)%elem%val            (position in the total list)
+ * posInBcElemBuf globBC%elemLvl(level)%posInBcElemBuf%val
+ * normalInd      globBC%elemLvl(level)%normalInd%val       (mus_construction_module.fpp:2393-2440)
+ * neighPos       fieldBC%neigh(level)%posInState(nNeighs, nElems), Fortran column-major
+ *                (setFieldBCNeigh, mus_construction_module.fpp:1733-1900)
+ * iElemOfLink    me%outletExpol(level)%iElem(nLinks)       (mus_bc_header_module.fpp:2256-2319);
+ *                statePos(l) = iDir(l) + (iElem(l)-1)*QQ is implied                         */
+int musb200_bc_register_elems(int level, int bc_id, int nElems, const int32_t *elemPos,
+                              const int32_t *posInBcElemBuf, const int32_t *normalInd, int nNeighs,
+                              const int32_t *neighPos, const int32_t *iElemOfLink);
+/* boundary values in LATTICE units, evaluated by the host's spacetime function:
+ * velocity boundaries 3 per link; pressure boundaries 1 per boundary element as lattice
+ * density (pressure * cs2inv / fac%press, mus_bc_fluid_module.fpp:1270) */
 int musb200_bc_set_values(int level, int bc_id, int nVals, const double *vals);
 
 /* ---- halo exchange: tem_communication_type --------------------------------

@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_PKG, "libmusb200.so")
+# MUSB200_LIB: path of an alternative build of the same library (kernel experiments only)
+_SO = os.environ.get("MUSB200_LIB") or os.path.join(_PKG, "libmusb200.so")
 _MESH_SO = os.path.join(_PKG, "libmusb200_mesh.so")
 
 c_int = ctypes.c_int
@@ -45,6 +46,7 @@ SIGNATURES = {
     "musb200_bc_elembuffer": [c_int, c_int, P_I32],
     "musb200_bc_register": [c_int, c_int, c_int, c_int, P_I32, P_I32, P_I32, P_I32],
     "musb200_bc_set_values": [c_int, c_int, c_int, c_void_p],
+    "musb200_bc_register_elems": [c_int, c_int, c_int, P_I32, P_I32, P_I32, c_int, P_I32, P_I32],
     "musb200_comm_register": [c_int, c_int, c_int, c_int, P_I32, P_I32, P_I32],
     "musb200_intp_register": [c_int, c_int, c_int, c_int, P_I32, P_I32, P_I32, P_DBL, P_I32, c_int,
                               P_I32, P_DBL, P_DBL],
@@ -100,6 +102,7 @@ for _n in ("nghelems", "neigh", "bc_elembuffer"):
 mesh.musb200_mesh_comm.argtypes = [c_void_p, c_int, P_I32, P_I32, P_I32, P_I32, P_I32]
 mesh.musb200_mesh_bc_info.argtypes = [c_void_p, c_int, P_I32]
 mesh.musb200_mesh_bc_lists.argtypes = [c_void_p, c_int, P_I32, P_I32, P_I32, P_I32, P_I32]
+mesh.musb200_mesh_bc_elem_lists.argtypes = [c_void_p, c_int, P_I32, P_I32, P_I32, P_I32, P_I32]
 mesh.musb200_mesh_bary.argtypes = [c_void_p, c_double, c_double, c_double, c_double, P_DBL]
 
 

@@ -107,7 +107,14 @@ struct BcData {
   int id = 0, kind = 0, nLinks = 0;
   DevBuf<int32_t> links, outPos, posInBuffer, iDir;
   DevBuf<double> vals;
+  // boundaries that read neighbours along the inward normal (musb200_bc_register_elems)
+  int nElems = 0, nNeighs = 0;
+  DevBuf<int32_t> elemPos, posInBcElemBuf, normalInd, neighPos, iElemOfLink;
+  DevBuf<double> neighBuf;  // neighBufferPre_nNext (expol) / neighBufferPost (anti-bounce-back)
 };
+static bool isPressureBc(int kind) {
+  return kind == MUSB200_BC_PRESSURE_EXPOL || kind == MUSB200_BC_PRESSURE_ANTIBOUNCEBACK;
+}
 
 struct CommBuf {
   std::vector<int> proc, nVals, offset;
@@ -131,6 +138,7 @@ struct Level {
   DevBuf<int32_t> bcNeeded;         // those slots (1-based), compact
   int relax = 0, kind = 0;
   bool relaxSet = false, elemOmega = false;
+  bool auxForBc = false;            // a boundary reads auxField: materialise it every step
   RelaxParams rp{1.0, 0.25, 1.0};
   std::vector<std::unique_ptr<BcData>> bcs;
   CommBuf send[3], recv[3];
@@ -214,8 +222,37 @@ static int setBoundary(Level &L) {
   MUSB_TRY(launchFillBcBuffer(L.QQ, st, L.S, L.bcElems.p, L.bcNeeded.p, (int)L.bcNeeded.n, L.bcBuffer.p,
                               g.stream));
   ++g.launches;
+  // fill_neighBuffer for every boundary that needs it, before any boundary writes its links
+  for (auto &b : L.bcs) {
+    if (!isPressureBc(b->kind) || b->nLinks == 0) continue;
+    if (b->nElems == 0) return setError(MUSB200_ERR_STATE, "pressure boundary: musb200_bc_register_elems missing");
+    const int post = b->kind == MUSB200_BC_PRESSURE_ANTIBOUNCEBACK ? 1 : 0;
+    MUSB_TRY(launchFillNeighBuffer(L.QQ, st, L.S, L.nbr.p, b->nNeighs, b->nElems, b->neighPos.p, post,
+                                   b->neighBuf.p, g.stream));
+    ++g.launches;
+  }
+  const int incomp = L.kind == MUSB200_KIND_FLUID_INCOMPRESSIBLE;
   for (auto &b : L.bcs) {
     if (b->kind == MUSB200_BC_WALL || b->nLinks == 0) continue;
+    if (isPressureBc(b->kind)) {
+      if (b->vals.n < (size_t)b->nElems)
+        return setError(MUSB200_ERR_STATE, "pressure boundary: musb200_bc_set_values missing (one density per element)");
+      if (b->kind == MUSB200_BC_PRESSURE_EXPOL) {
+        MUSB_TRY(launchPressureExpol(L.QQ, incomp, st, L.S, L.nbr.p, L.bcBuffer.p, L.aux.p, b->nElems,
+                                     b->elemPos.p, b->posInBcElemBuf.p, b->normalInd.p, b->vals.p,
+                                     b->nLinks, b->links.p, b->iElemOfLink.p, b->iDir.p, b->neighBuf.p,
+                                     g.stream));
+        g.launches += 2;
+      } else {
+        MUSB_TRY(launchPressureAntiBounceBack(L.QQ, incomp, st, L.S, L.bcBuffer.p, b->nLinks, b->links.p,
+                                              b->iElemOfLink.p, b->iDir.p, b->elemPos.p,
+                                              b->posInBcElemBuf.p, b->vals.p,
+                                              L.elemOmega ? L.omega.p : nullptr, L.rp.omega_uniform,
+                                              b->neighBuf.p, g.stream));
+        ++g.launches;
+      }
+      continue;
+    }
     if (b->kind == MUSB200_BC_VELOCITY_BOUNCEBACK) {
       if (b->vals.n < (size_t)3 * b->nLinks)
         return setError(MUSB200_ERR_STATE, "velocity_bounceback: musb200_bc_set_values missing");
@@ -322,7 +359,7 @@ static int levelStep(int iLevel, int minLevel, int maxLevel, bool lastCycle) {
   MUSB_TRY(setBoundary(L));
   std::swap(L.nNow, L.nNext);
   // multi-level: the interpolation routines read auxField of their sources every step
-  const bool writeAux = g.auxEveryStep || multi || lastCycle;
+  const bool writeAux = g.auxEveryStep || multi || lastCycle || L.auxForBc;
   MUSB_TRY(sweep(L, writeAux));
   if (iLevel < maxLevel) {
     // auxField of my ghostFromFiner elements <- average of level+1
@@ -634,8 +671,9 @@ int musb200_bc_elembuffer(int level, int nBcElems, const int32_t *bc_elemBuffer)
 int musb200_bc_register(int level, int bc_id, int bc_kind, int nLinks, const int32_t *links,
                         const int32_t *outPos, const int32_t *posInBuffer, const int32_t *iDir) {
   GET_LEVEL(L, level);
-  if (bc_kind != MUSB200_BC_WALL && bc_kind != MUSB200_BC_VELOCITY_BOUNCEBACK)
-    return setError(MUSB200_ERR_UNSUPPORTED, "boundary kind " + std::to_string(bc_kind) + " is not built yet");
+  if (bc_kind < MUSB200_BC_WALL || bc_kind > MUSB200_BC_PRESSURE_EXPOL)
+    return setError(MUSB200_ERR_UNSUPPORTED,
+                    "boundary kind " + std::to_string(bc_kind) + " is outside the B200 hot path");
   if (nLinks < 0) return setError(MUSB200_ERR_ARG, "nLinks < 0");
   auto b = std::make_unique<BcData>();
   b->id = bc_id; b->kind = bc_kind; b->nLinks = nLinks;
@@ -663,6 +701,42 @@ int musb200_bc_register(int level, int bc_id, int bc_kind, int nLinks, const int
     if (o->id == bc_id) { o = std::move(b); return 0; }
   L->bcs.push_back(std::move(b));
   return 0;
+}
+
+int musb200_bc_register_elems(int level, int bc_id, int nElems, const int32_t *elemPos,
+                              const int32_t *posInBcElemBuf, const int32_t *normalInd, int nNeighs,
+                              const int32_t *neighPos, const int32_t *iElemOfLink) {
+  GET_LEVEL(L, level);
+  for (auto &b : L->bcs) {
+    if (b->id != bc_id) continue;
+    if (!isPressureBc(b->kind)) return setError(MUSB200_ERR_ARG, "boundary kind reads no neighbours");
+    const int need = b->kind == MUSB200_BC_PRESSURE_EXPOL ? 2 : 1;   // me%nNeighs, mus_bc_header_module.fpp
+    if (nElems <= 0 || nNeighs < need || !elemPos || !posInBcElemBuf || !normalInd || !neighPos || !iElemOfLink)
+      return setError(MUSB200_ERR_ARG, "bad boundary element lists");
+    for (int i = 0; i < nElems; ++i) {
+      if (elemPos[i] < 1 || elemPos[i] > L->nElems || posInBcElemBuf[i] < 1 ||
+          posInBcElemBuf[i] > (int)L->bcSlotNeeded.size() || normalInd[i] < 1 || normalInd[i] > L->QQ)
+        return setError(MUSB200_ERR_ARG, "boundary element list entry out of range");
+      for (int k = 0; k < nNeighs; ++k)
+        if (neighPos[(size_t)i * nNeighs + k] < 1 || neighPos[(size_t)i * nNeighs + k] > L->nElems)
+          return setError(MUSB200_ERR_ARG, "boundary neighbour position out of range");
+    }
+    // keep the first `need` neighbours of every element (posInState(1:need, iElem))
+    std::vector<int32_t> np((size_t)nElems * need);
+    for (int i = 0; i < nElems; ++i)
+      for (int k = 0; k < need; ++k) np[(size_t)i * need + k] = neighPos[(size_t)i * nNeighs + k];
+    b->nElems = nElems; b->nNeighs = need;
+    MUSB_TRY(b->elemPos.upload(elemPos, nElems, g.stream));
+    MUSB_TRY(b->posInBcElemBuf.upload(posInBcElemBuf, nElems, g.stream));
+    MUSB_TRY(b->normalInd.upload(normalInd, nElems, g.stream));
+    MUSB_TRY(b->neighPos.upload(np.data(), np.size(), g.stream));
+    MUSB_TRY(b->iElemOfLink.upload(iElemOfLink, b->nLinks, g.stream));
+    MUSB_TRY(b->neighBuf.alloc((size_t)need * nElems * L->QQ));
+    MUSB_CUDA(cudaStreamSynchronize(g.stream));
+    if (b->kind == MUSB200_BC_PRESSURE_EXPOL) L->auxForBc = true;   // reads auxField of the previous step
+    return 0;
+  }
+  return setError(MUSB200_ERR_ARG, "unknown boundary id " + std::to_string(bc_id));
 }
 
 int musb200_bc_set_values(int level, int bc_id, int nVals, const double *vals) {

@@ -14,6 +14,7 @@
 //                                     mus/source/bc/mus_bc_header_module.fpp:1702-1739, 1876-1967
 // All lists are produced 1-based, exactly as the Fortran arrays hold them.
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -51,8 +52,11 @@ const int kCx[26][3] = {
     {1, -1, -1}, {1, -1, 1}, {1, 1, -1}, {1, 1, 1}};
 
 struct Bc {
-  int id, kind;  // kind: 0 wall, 1 velocity_bounceback
+  int id, kind;  // kind: 0 wall, 1 velocity_bounceback, 2 pressure (expol / anti-bounce-back)
   std::vector<int32_t> elems, links, outPos, posInBuffer, iDir;
+  // per element: discretised inward normal index, slot in bc_elemBuffer, the two neighbours
+  // along the normal; per link: element counter and outletExpol%statePos
+  std::vector<int32_t> normalInd, posInBcElemBuf, neighPos, iElemOfLink, statePos;
 };
 
 struct Comm {
@@ -78,6 +82,12 @@ struct Box {
   // boundary id met when stepping from inside to (x,y,z); 0 = none
   int bid(int x, int y, int z, int n) const {
     if (kind == 0) return 0;
+    if (kind == 2) {  // channel: walls on the y/z faces, inlet at x < 0, outlet at x >= n
+      if (y < 0 || y >= n || z < 0 || z >= n) return 1;
+      if (x < 0) return 2;
+      if (x >= n) return 3;
+      return 0;
+    }
     const bool outxy = x < 0 || x >= n || y < 0 || y >= n;
     if (outxy || z < 0) return 1;  // 'wall'
     if (z >= n) return 2;          // 'lid'
@@ -237,33 +247,86 @@ void build(Box &b, int commReduced) {
     }
   }
 
-  // boundary lists (cavity): id 1 'wall' (do_nothing), id 2 'lid' (velocity_bounceback)
-  if (b.kind == 1) {
+  // boundary lists.  cavity: id 1 'wall' (do_nothing), id 2 'lid' (velocity_bounceback);
+  // channel: id 1 'wall', id 2 'inlet' (velocity_bounceback), id 3 'outlet' (pressure)
+  if (b.kind >= 1) {
     std::vector<int32_t> posInBuf(b.nElems + 1, 0);
     for (int e = 0; e < nF; ++e)
       if (b.property[e] & (1ll << 3)) {
         b.bcElemBuffer.push_back(e + 1);
         posInBuf[e + 1] = (int32_t)b.bcElemBuffer.size();
       }
-    for (int id = 1; id <= 2; ++id) {
+    // prevailing directions = normalised stencil directions; weights 4/2/1 (assignBCList)
+    double prevail[26][3];
+    int wgt[26];
+    for (int k = 0; k < QQN; ++k) {
+      const int len = kCx[k][0] * kCx[k][0] + kCx[k][1] * kCx[k][1] + kCx[k][2] * kCx[k][2];
+      wgt[k] = len == 1 ? 4 : (len == 2 ? 2 : 1);
+      const double r = std::sqrt((double)len);
+      for (int c = 0; c < 3; ++c) prevail[k][c] = (double)kCx[k][c] / r;
+    }
+    const int nIds = b.kind == 1 ? 2 : 3;
+    for (int id = 1; id <= nIds; ++id) {
       Bc bc;
       bc.id = id;
-      bc.kind = id == 1 ? 0 : 1;
+      bc.kind = id - 1;
       for (int e = 0; e < nF; ++e) {
         if (!(b.property[e] & (1ll << 3))) continue;
         bool mask[26] = {false};
         bool any = false;
+        long long nrm[3] = {0, 0, 0};
         for (int k = 0; k < QQN; ++k)
-          if (b.ngh[(size_t)e * QQN + k] == -id) { mask[b.inv[k]] = true; any = true; }
+          if (b.ngh[(size_t)e * QQN + k] == -id) {
+            mask[b.inv[k]] = true;
+            any = true;
+            for (int c = 0; c < 3; ++c) nrm[c] -= (long long)wgt[k] * kCx[k][c];
+          }
         if (!any) continue;
         bc.elems.push_back(e + 1);
+        const int iElem = (int)bc.elems.size();
         for (int d = 1; d <= QQN; ++d) {
           if (!mask[d - 1]) continue;
           bc.links.push_back(b.neigh[(size_t)(d - 1) * b.nSize + e]);  // FETCH(iDir, elem)
           bc.iDir.push_back(d);
           bc.posInBuffer.push_back(posInBuf[e + 1]);
           bc.outPos.push_back((b.inv[d - 1] + 1) + (posInBuf[e + 1] - 1) * QQ);
+          bc.iElemOfLink.push_back(iElem);
+          bc.statePos.push_back(d + (iElem - 1) * QQ);
         }
+        // tem_determine_discreteVector: first strict maximum of the projection, exit at 1
+        const double len = std::sqrt((double)(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]));
+        int best = 0;
+        double mx = -2.0;
+        for (int k = 0; k < QQN; ++k) {
+          double dp = (nrm[0] / len) * prevail[k][0] + (nrm[1] / len) * prevail[k][1] +
+                      (nrm[2] / len) * prevail[k][2];
+          dp = std::min(std::max(dp, -1.0), 1.0);
+          if (dp > mx) {
+            mx = dp;
+            best = k;
+            if (std::fabs(mx - 1.0) <= 2.220446049250313e-16) break;
+          }
+        }
+        bc.normalInd.push_back(best + 1);
+        bc.posInBcElemBuf.push_back(posInBuf[e + 1]);
+        // setFieldBCNeigh: the elements at x + k*normal, k = 1, 2
+        const uint64_t m = (uint64_t)(b.lo + e);
+        const int x = (int)compact3(m), y = (int)compact3(m >> 1), z = (int)compact3(m >> 2);
+        int32_t np[2] = {e + 1, e + 1};
+        for (int k = 1; k <= 2; ++k) {
+          const int xn = x + k * kCx[best][0], yn = y + k * kCx[best][1], zn = z + k * kCx[best][2];
+          int32_t p = 0;
+          if (xn >= 0 && xn < n && yn >= 0 && yn < n && zn >= 0 && zn < n) p = posOf(mortonOf(xn, yn, zn));
+          if (p <= 0) {                       // no valid neighbour: keep the last valid one
+            if (k == 1) { np[0] = np[1] = e + 1; }
+            else np[1] = np[0];
+            break;
+          }
+          np[k - 1] = p;
+          if (k == 1) np[1] = p;
+        }
+        bc.neighPos.push_back(np[0]);
+        bc.neighPos.push_back(np[1]);
       }
       b.bcs.push_back(std::move(bc));
     }
@@ -280,9 +343,10 @@ int copyOut(const std::vector<T> &v, T *out) {
 
 extern "C" {
 
-// kind: 0 = fully periodic cube, 1 = cavity (5 walls + moving lid at z = top)
+// kind: 0 = fully periodic cube, 1 = cavity (5 walls + moving lid at z = top),
+//       2 = channel (4 walls, velocity inlet at x = 0, pressure outlet at x = top)
 void *musb200_mesh_box_create(int level, int QQ, int kind, int rank, int nranks, int comm_reduced) {
-  if (level < 1 || level > 10 || (QQ != 19 && QQ != 27) || kind < 0 || kind > 1 || nranks < 1 ||
+  if (level < 1 || level > 10 || (QQ != 19 && QQ != 27) || kind < 0 || kind > 2 || nranks < 1 ||
       rank < 0 || rank >= nranks)
     return nullptr;
   Box *b = new Box();
@@ -332,6 +396,17 @@ int musb200_mesh_bc_lists(void *h, int i, int32_t *elems, int32_t *links, int32_
   const Bc &bc = b->bcs[i];
   copyOut(bc.elems, elems); copyOut(bc.links, links); copyOut(bc.outPos, outPos);
   copyOut(bc.posInBuffer, posInBuffer); copyOut(bc.iDir, iDir);
+  return 0;
+}
+// per element: normalInd, posInBcElemBuf [nElems], neighPos [nElems][2]; per link: iElem, statePos
+int musb200_mesh_bc_elem_lists(void *h, int i, int32_t *normalInd, int32_t *posInBcElemBuf,
+                               int32_t *neighPos, int32_t *iElemOfLink, int32_t *statePos) {
+  Box *b = static_cast<Box *>(h);
+  if (i < 0 || i >= (int)b->bcs.size()) return 1;
+  const Bc &bc = b->bcs[i];
+  copyOut(bc.normalInd, normalInd); copyOut(bc.posInBcElemBuf, posInBcElemBuf);
+  copyOut(bc.neighPos, neighPos); copyOut(bc.iElemOfLink, iElemOfLink);
+  copyOut(bc.statePos, statePos);
   return 0;
 }
 // barycentres (tem_BaryOfId, tem_geometry_module.f90:419-435): out[nElems][3]

@@ -43,6 +43,21 @@ int launchVelocityBounceBack(int QQ, int incomp, double *state, long long S,
                              const int32_t *outPos, const int32_t *posInBuffer,
                              const int32_t *iDir, const double *velLat, cudaStream_t st);
 
+// boundaries that read neighbours along the inward normal
+int launchFillNeighBuffer(int QQ, const double *state, long long S, const uint32_t *nbr, int nNeighs,
+                          int nElems, const int32_t *neighPos, int post, double *nb, cudaStream_t st);
+int launchPressureExpol(int QQ, int incomp, double *state, long long S, const uint32_t *nbr,
+                        const double *bcBuffer, const double *aux, int nElems, const int32_t *elemPos,
+                        const int32_t *posInBcElemBuf, const int32_t *normalInd, const double *rhoDef,
+                        int nLinks, const int32_t *links, const int32_t *iElemOfLink,
+                        const int32_t *iDir, const double *nbPre, cudaStream_t st);
+int launchPressureAntiBounceBack(int QQ, int incomp, double *state, long long S,
+                                 const double *bcBuffer, int nLinks, const int32_t *links,
+                                 const int32_t *iElemOfLink, const int32_t *iDir,
+                                 const int32_t *elemPos, const int32_t *posInBcElemBuf,
+                                 const double *rhoDef, const double *omegaElem, double omegaUniform,
+                                 const double *nbPost, cudaStream_t st);
+
 // halo exchange pack / unpack (positions are Fortran AOS state positions)
 int launchPack(int QQ, const double *state, long long S, const int32_t *pos, int n, double *buf,
                cudaStream_t st);

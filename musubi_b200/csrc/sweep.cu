@@ -17,8 +17,29 @@
 
 namespace musb200 {
 
+// Launch shape: 128 threads per CTA.  D3Q19 needs 72-80 registers (6 CTAs/SM), D3Q27 up to 128
+// (4 CTAs/SM, no spills).  A warp lives long here (26 index loads -> 27 gathers -> 800-1300 FP64
+// instructions -> 27 stores) and a CTA's registers are only released when its last warp retires,
+// so small CTAs keep more loads in flight: measured on B200 (profiles/r01_launch_shape.md)
+// D3Q27 MRT 256^3: 256 threads 2.30 ms, 128 threads 1.55 ms, 64 threads 1.57 ms, 512 threads
+// 1.81 ms; D3Q19 TRT 256^3: 1.132 / 1.079 / 1.074 / 1.198 ms.  Capping D3Q27 at 96 or 80
+// registers (5-6 CTAs/SM) spills 270-570 B per thread and is slower (1.98 / 2.64 ms).
+#ifndef SWEEP27_THREADS
+#define SWEEP27_THREADS 128
+#endif
+#ifndef SWEEP27_MINBLOCKS
+#define SWEEP27_MINBLOCKS 4
+#endif
+#ifndef SWEEP19_THREADS
+#define SWEEP19_THREADS 128
+#endif
+template <int QQ>
+constexpr int sweepThreads() { return QQ == 27 ? SWEEP27_THREADS : SWEEP19_THREADS; }
+template <int QQ>
+constexpr int sweepMinBlocks() { return QQ == 27 ? SWEEP27_MINBLOCKS : 1; }
+
 template <int QQ, int RELAX, bool INCOMP>
-__global__ void __launch_bounds__(256) sweepKernel(const SweepArgs a) {
+__global__ void __launch_bounds__(sweepThreads<QQ>(), sweepMinBlocks<QQ>()) sweepKernel(const SweepArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.count) return;
   int e;
@@ -77,7 +98,7 @@ __global__ void __launch_bounds__(256) sweepKernel(const SweepArgs a) {
 template <int QQ, int RELAX, bool INCOMP>
 static int launchT(const SweepArgs &a, cudaStream_t st) {
   if (a.count <= 0) return 0;
-  const int block = 256;
+  const int block = sweepThreads<QQ>();
   sweepKernel<QQ, RELAX, INCOMP><<<divUp(a.count, block), block, 0, st>>>(a);
   MUSB_CUDA(cudaGetLastError());
   return 0;

@@ -68,9 +68,11 @@ class Scheme:
     """mus_scheme_type for one level range on one rank, device resident."""
 
     def __init__(self, identify, levelDescs, omega, lambda_=0.25, omega_bulk=None, intp=None,
-                 viscosity=None):
+                 viscosity=None, bc_kind=None):
         """intp: None or (tables, order) with tables as built by multilevel_tables();
-        viscosity: {level: lattice viscosity} (fluid%viscKine%dataOnLvl) for the interpolation."""
+        viscosity: {level: lattice viscosity} (fluid%viscKine%dataOnLvl) for the interpolation;
+        bc_kind: {boundary id: kind} binds the mesh's 'pressure' boundaries to pressure_expol or
+        pressure_antibounceback (the boundary_condition table of the Lua configuration)."""
         self.relax, self.kind, self.QQ = select_kernel(identify)
         if not isinstance(levelDescs, dict):
             levelDescs = {levelDescs.level: levelDescs}
@@ -90,9 +92,18 @@ class Scheme:
             if len(ld.bc_elemBuffer):
                 check(lib.musb200_bc_elembuffer(lvl, len(ld.bc_elemBuffer), ptr(ld.bc_elemBuffer, P_I32)))
             for bc in ld.bc:
-                check(lib.musb200_bc_register(lvl, bc["id"], BC_KIND[bc["kind"]], len(bc["links"]),
+                kind = (bc_kind or {}).get(bc["id"], bc["kind"])
+                if kind not in BC_KIND:
+                    raise ValueError("boundary %d: kind %r needs a bc_kind binding" % (bc["id"], kind))
+                check(lib.musb200_bc_register(lvl, bc["id"], BC_KIND[kind], len(bc["links"]),
                                               ptr(bc["links"], P_I32), ptr(bc["outPos"], P_I32),
                                               ptr(bc["posInBuffer"], P_I32), ptr(bc["iDir"], P_I32)))
+                if kind.startswith("pressure") and len(bc["elems"]):
+                    npos = np.ascontiguousarray(bc["neighPos"], dtype=np.int32)
+                    check(lib.musb200_bc_register_elems(
+                        lvl, bc["id"], len(bc["elems"]), ptr(bc["elems"], P_I32),
+                        ptr(bc["posInBcElemBuf"], P_I32), ptr(bc["normalInd"], P_I32),
+                        npos.shape[1], ptr(npos, P_I32), ptr(bc["iElemOfLink"], P_I32)))
             if viscosity is not None:
                 v = viscosity[lvl]
                 if np.isscalar(v):

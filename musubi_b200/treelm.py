@@ -7,7 +7,8 @@ import numpy as np
 from . import _lib
 from ._lib import P_I32, P_I64, P_DBL, mesh, ptr
 
-KIND = {"periodic": 0, "cavity": 1}
+KIND = {"periodic": 0, "cavity": 1, "channel": 2}
+_BC_LABEL = {"cavity": ("wall", "lid"), "channel": ("wall", "inlet", "outlet")}
 
 
 class LevelDesc:
@@ -54,8 +55,8 @@ class LevelDesc:
             for i in range(nBc):
                 sz = np.zeros(4, dtype=np.int32)
                 mesh.musb200_mesh_bc_info(h, i, ptr(sz, P_I32))
-                bc = dict(id=int(sz[0]), kind=("wall", "velocity_bounceback")[int(sz[1])],
-                          label=("wall", "lid")[int(sz[1])],
+                bc = dict(id=int(sz[0]), kind=("wall", "velocity_bounceback", "pressure")[int(sz[1])],
+                          label=_BC_LABEL[kind][int(sz[0]) - 1],
                           elems=np.zeros(sz[2], dtype=np.int32), links=np.zeros(sz[3], dtype=np.int32),
                           outPos=np.zeros(sz[3], dtype=np.int32),
                           posInBuffer=np.zeros(sz[3], dtype=np.int32),
@@ -63,6 +64,15 @@ class LevelDesc:
                 mesh.musb200_mesh_bc_lists(h, i, ptr(bc["elems"], P_I32), ptr(bc["links"], P_I32),
                                            ptr(bc["outPos"], P_I32), ptr(bc["posInBuffer"], P_I32),
                                            ptr(bc["iDir"], P_I32))
+                # boundary_type%elemLvl / %neigh(level)%posInState / outletExpol (pressure boundaries)
+                bc.update(normalInd=np.zeros(sz[2], dtype=np.int32),
+                          posInBcElemBuf=np.zeros(sz[2], dtype=np.int32),
+                          neighPos=np.zeros((int(sz[2]), 2), dtype=np.int32),
+                          iElemOfLink=np.zeros(sz[3], dtype=np.int32),
+                          statePos=np.zeros(sz[3], dtype=np.int32))
+                mesh.musb200_mesh_bc_elem_lists(h, i, ptr(bc["normalInd"], P_I32),
+                                                ptr(bc["posInBcElemBuf"], P_I32), ptr(bc["neighPos"], P_I32),
+                                                ptr(bc["iElemOfLink"], P_I32), ptr(bc["statePos"], P_I32))
                 self.bc.append(bc)
             self._bary_args = None
             self._h_for_bary = None

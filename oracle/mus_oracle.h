@@ -92,6 +92,21 @@ void ora_velocity_bounceback(double *state, const double *bcBuffer, int QQ,
                              const int32_t *iDirLink, const int32_t *posInBuffer,
                              const double *velLat /* [nLinks][3] lattice units */,
                              int incompressible);
+void ora_first_moment(int QQ, const double *pdf_1based, double m[3]);
+/* fill_neighBuffer (mus_bc_general_module.fpp:1589-1717), pressure_expol
+ * (mus_bc_fluid_module.fpp:1165-1362), pressure_antiBounceBack (:2161-2353) */
+void ora_fill_neighBuffer(double *nb, const double *state, const int32_t *neigh, int nSize,
+                          int QQ, int nNeighs, int nElems, const int32_t *neighPos, int post);
+void ora_pressure_expol(double *state, const double *bcBuffer, const double *aux,
+                        const int32_t *neigh, int nSize, int QQ, int incompressible, int nElems,
+                        const int32_t *elemPos, const int32_t *posInBcElemBuf,
+                        const int32_t *normalInd, const double *rhoDef, int nLinks,
+                        const int32_t *links, const int32_t *statePos, const double *nbPre);
+void ora_pressure_antibounceback(double *state, const double *bcBuffer, int QQ, int incompressible,
+                                 int nElems, const int32_t *elemPos, const int32_t *posInBcElemBuf,
+                                 const double *rhoDef, const double *omega, int nLinks,
+                                 const int32_t *links, const int32_t *iElemOfLink,
+                                 const int32_t *iDirOfLink, const double *nbPost);
 /* mus_init_pdf with zero strain rate: state = fEq(rho, vel) */
 void ora_init_equilibrium(int QQ, int incompressible, int nElems, const double *rho,
                           const double *vel, double *state);

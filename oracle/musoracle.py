@@ -168,9 +168,18 @@ def box_boundary_id(xn, yn, zn, n, kind):
     kind 'periodic': no boundaries (treelm wraps at the universe cube).
     kind 'cavity'  : id 2 ('lid', velocity_bounceback) where only the top plane
                      z = n is crossed; id 1 ('wall') for every other exit.
+    kind 'channel' : id 1 ('wall') where a y or z plane is crossed; else id 2 ('inlet',
+                     velocity_bounceback) at x < 0 and id 3 ('outlet', a pressure boundary) at x >= n.
     The synthetic-mesh convention (Seeder would store these ids in bnd.lsb)."""
     if kind == "periodic":
         return np.zeros(xn.shape, dtype=np.int64)
+    if kind == "channel":
+        out_yz = (yn < 0) | (yn >= n) | (zn < 0) | (zn >= n)
+        bid = np.zeros(xn.shape, dtype=np.int64)
+        bid[out_yz] = 1
+        bid[(~out_yz) & (xn < 0)] = 2
+        bid[(~out_yz) & (xn >= n)] = 3
+        return bid
     out_xy = (xn < 0) | (xn >= n) | (yn < 0) | (yn >= n)
     bid = np.zeros(xn.shape, dtype=np.int64)
     bid[out_xy | (zn < 0)] = 1
@@ -279,11 +288,19 @@ def build_level_desc(level, QQ, kind="periodic", rank=0, nranks=1, comm_reduced=
 
     # ---------------- boundary lists ----------------------------------------
     ld.bc = []
-    if kind == "cavity":
+    bcs = {"cavity": ((1, "wall", "wall"), (2, "lid", "velocity_bounceback")),
+           "channel": ((1, "wall", "wall"), (2, "inlet", "velocity_bounceback"),
+                       (3, "outlet", "pressure"))}.get(kind, ())
+    if bcs:
         ld.bc_elemBuffer = (np.nonzero(hasbnd)[0] + 1).astype(np.int32)   # levelDesc%bc_elemBuffer
         posInBuf = np.zeros(nElems + 1, dtype=np.int32)
         posInBuf[ld.bc_elemBuffer] = np.arange(1, ld.bc_elemBuffer.size + 1)
-        for bid, label, bkind in ((1, "wall", "wall"), (2, "lid", "velocity_bounceback")):
+        # weights of the normal: 4 / 2 / 1 for axis / edge / corner directions (assignBCList,
+        # mus_construction_module.fpp:2237-2252); prevailing directions = normalised stencil
+        clen = (cx[:QQN] ** 2).sum(axis=1)
+        wgt = np.where(clen == 1, 4, np.where(clen == 2, 2, 1)).astype(np.int64)
+        prevail = cx[:QQN].astype(np.float64) / np.sqrt(clen.astype(np.float64))[:, None]
+        for bid, label, bkind in bcs:
             hit = (ngh[:nFluid] == -bid)                      # [elem][k]: boundary in direction k
             elems = np.nonzero(hit.any(axis=1))[0] + 1
             bitmask = np.zeros((elems.size, QQN), dtype=bool)
@@ -295,10 +312,48 @@ def build_level_desc(level, QQ, kind="periodic", rank=0, nranks=1, comm_reduced=
             links = ld.neigh[(dirs - 1) * ld.nSize + el - 1]  # FETCH(iDir, elem)
             pib = posInBuf[el]
             outPos = inv[dirs - 1] + (pib.astype(np.int64) - 1) * QQ
-            ld.bc.append(dict(id=bid, label=label, kind=bkind, elems=elems.astype(np.int32),
-                              bitmask=bitmask, links=links.astype(np.int32),
-                              iDir=dirs.astype(np.int32), posInBuffer=pib.astype(np.int32),
-                              outPos=outPos.astype(np.int32), elemOfLink=el.astype(np.int32)))
+            bc = dict(id=bid, label=label, kind=bkind, elems=elems.astype(np.int32),
+                      bitmask=bitmask, links=links.astype(np.int32),
+                      iDir=dirs.astype(np.int32), posInBuffer=pib.astype(np.int32),
+                      outPos=outPos.astype(np.int32), elemOfLink=el.astype(np.int32))
+            # element normals: -sum_k weight_k c_k over the boundary directions, aligned to the
+            # best prevailing direction (normalizeBC :2393-2440, tem_determine_discreteVector)
+            nrm = -(hit[elems - 1].astype(np.int64) * wgt[None, :]) @ cx[:QQN]
+            nlen = np.sqrt((nrm.astype(np.float64) ** 2).sum(axis=1))
+            dots = np.clip((nrm / nlen[:, None]) @ prevail.T, -1.0, 1.0)
+            best = np.zeros(elems.size, dtype=np.int64)
+            for i in range(elems.size):                       # first strict maximum, exit at 1
+                mx = -2.0
+                for k in range(QQN):
+                    if dots[i, k] > mx:
+                        mx, best[i] = dots[i, k], k
+                        if abs(mx - 1.0) <= np.finfo(float).eps:
+                            break
+            bc["normal"] = cx[best].astype(np.int32)
+            bc["normalInd"] = (best + 1).astype(np.int32)
+            bc["posInBcElemBuf"] = posInBuf[elems].astype(np.int32)
+            # iElem / statePos per link (mus_set_outletExpol, mus_bc_header_module.fpp:2256-2319)
+            bc["iElemOfLink"] = (e_idx + 1).astype(np.int32)
+            bc["statePos"] = (dirs + e_idx * QQ).astype(np.int32)
+            # neighbours along the inward normal (setFieldBCNeigh, mus_construction_module.fpp:
+            # 1733-1840): position of the element at x + k*normal, k = 1..2; a missing first
+            # neighbour -> the element itself, a missing second -> the first
+            ex, ey, ez = x[elems - 1], y[elems - 1], z[elems - 1]
+            npos = np.zeros((elems.size, 2), dtype=np.int32)
+            for k in (1, 2):
+                xn, yn, zn = ex + k * bc["normal"][:, 0], ey + k * bc["normal"][:, 1], ez + k * bc["normal"][:, 2]
+                inside = (xn >= 0) & (xn < n) & (yn >= 0) & (yn < n) & (zn >= 0) & (zn < n)
+                m = morton_of_coord(np.mod(xn, n), np.mod(yn, n), np.mod(zn, n))
+                p = np.where((m >= lo) & (m < hi), m - lo + 1, 0)
+                if nHalo:
+                    hp = np.minimum(np.searchsorted(halo_m, m), nHalo - 1)
+                    p = np.where((p == 0) & (halo_m[hp] == m), nFluid + hp + 1, p)
+                p = np.where(inside, p, 0)
+                prev = elems if k == 1 else npos[:, 0]
+                npos[:, k - 1] = np.where(p > 0, p, prev)
+            npos[:, 1] = np.where(npos[:, 0] == elems, elems, npos[:, 1])
+            bc["neighPos"] = npos
+            ld.bc.append(bc)
     else:
         ld.bc_elemBuffer = np.zeros(0, dtype=np.int32)
     return ld
@@ -373,6 +428,10 @@ class Scheme:
         self.omega_uniform = float(omega)
         self.rp = _Relax(lambda_, omega if omega_bulk is None else omega_bulk)
         self.bc_vel = {}      # bc id -> [nLinks][3] lattice velocity per link
+        self.bc_rho = {}      # bc id -> [nElems] lattice density of a pressure boundary
+        # the mesh only knows the boundary id; 'pressure' ids are bound to a kind here
+        # (boundary_condition table of the Lua config): pressure_expol | pressure_antibounceback
+        self.bc_kind = {bc["id"]: bc["kind"] for bc in ld.bc}
         self.bcBuffer = np.zeros(max(1, ld.bc_elemBuffer.size) * self.QQ)
         self.exchange = None  # callable(state) for multi-rank runs
 
@@ -421,16 +480,41 @@ class Scheme:
         L.ora_fill_bcBuffer(_d(self.bcBuffer), _d(st), self.QQ, _i(ld.bc_elemBuffer),
                             int(ld.bc_elemBuffer.size))
         for bc in ld.bc:
-            if bc["kind"] == "wall":
+            kind = self.bc_kind[bc["id"]]
+            if kind == "wall":
                 continue                        # do_nothing: bounce-back lives in neigh
-            if bc["kind"] == "velocity_bounceback":
+            if kind in ("pressure_expol", "pressure_antibounceback"):
+                nE = int(bc["elems"].size)
+                rho = np.ascontiguousarray(np.broadcast_to(self.bc_rho[bc["id"]], (nE,)), dtype=np.float64)
+                npos = np.ascontiguousarray(bc["neighPos"], dtype=np.int32)
+                if kind == "pressure_expol":
+                    nb = np.zeros(2 * nE * self.QQ)      # requireNeighBufPre_nNext, nNeighs = 2
+                    L.ora_fill_neighBuffer(_d(nb), _d(st), _i(ld.neigh), ld.nSize, self.QQ, 2, nE,
+                                           _i(npos), 0)
+                    L.ora_pressure_expol(_d(st), _d(self.bcBuffer), _d(self.aux), _i(ld.neigh), ld.nSize,
+                                         self.QQ, self.incomp, nE, _i(bc["elems"]),
+                                         _i(bc["posInBcElemBuf"]), _i(bc["normalInd"]), _d(rho),
+                                         int(bc["links"].size), _i(bc["links"]), _i(bc["statePos"]),
+                                         _d(nb))
+                else:
+                    n1 = np.ascontiguousarray(npos[:, :1])  # requireNeighBufPost, nNeighs = 1
+                    nb = np.zeros(nE * self.QQ)
+                    L.ora_fill_neighBuffer(_d(nb), _d(st), _i(ld.neigh), ld.nSize, self.QQ, 1, nE,
+                                           _i(n1), 1)
+                    L.ora_pressure_antibounceback(_d(st), _d(self.bcBuffer), self.QQ, self.incomp, nE,
+                                                  _i(bc["elems"]), _i(bc["posInBcElemBuf"]), _d(rho),
+                                                  _d(self.omega), int(bc["links"].size),
+                                                  _i(bc["links"]), _i(bc["iElemOfLink"]),
+                                                  _i(bc["iDir"]), _d(nb))
+                continue
+            if kind == "velocity_bounceback":
                 v = np.ascontiguousarray(self.bc_vel[bc["id"]], dtype=np.float64)
                 L.ora_velocity_bounceback(_d(st), _d(self.bcBuffer), self.QQ,
                                           int(bc["links"].size), _i(bc["links"]), _i(bc["outPos"]),
                                           _i(bc["iDir"]), _i(bc["posInBuffer"]), _d(v),
                                           self.incomp)
             else:
-                raise ValueError("boundary kind %r not restated" % bc["kind"])
+                raise ValueError("boundary kind %r not restated" % kind)
 
     def step(self):
         """do_fast_singleLevel (mus_control_module.f90:507-701), steps 3-9."""

@@ -286,6 +286,11 @@ static void mom1_d3q27(const double *p, double m[3]) {
        - p[19] + p[20] - p[21] + p[22] - p[23] + p[24] - p[25] + p[26];
 }
 
+/* sum_i c_i f_i in the literal order of get_vel_from_pdf_d3q19/_d3q27; p is 1-based */
+void ora_first_moment(int QQ, const double *p, double m[3]) {
+  if (QQ == 19) mom1_d3q19(p, m); else mom1_d3q27(p, m);
+}
+
 static void calc_aux(int QQ, int incomp, double *aux, const double *state,
                      const int32_t *neigh, int nSize, int nSolve) {
 #pragma omp parallel for schedule(static)

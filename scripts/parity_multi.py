@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--relaxation", default="mrt")
     ap.add_argument("--kind", default="periodic")
     ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--outlet", default="pressure_expol")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -77,6 +78,11 @@ def main():
         if a.kind == "cavity":
             rho, vel = cases.cavity_rest(gld)
             ref.bc_vel[2] = cases.lid_values(gld, (0.05, 0.02, 0.0))
+        elif a.kind == "channel":
+            rho, vel = cases.cavity_rest(gld)
+            ref.bc_vel[2] = cases.lid_values(gld, (0.03, 0.0, 0.0))
+            ref.bc_kind[3] = a.outlet
+            ref.bc_rho[3] = 1.0
         else:
             rho, vel = cases.taylor_green(gld, mean=(0.01, -0.02, 0.015))
         ref.init_equilibrium(rho, vel)
@@ -85,10 +91,20 @@ def main():
         gpos = (ld.total - gld.total[0]).astype(np.int64)
         init = np.zeros(ld.nSize * QQ)
         init[:ld.nElems * QQ] = ref.state[ref.nNext].reshape(-1, QQ)[gpos].ravel()
-        sch = mb.Scheme(ident, ld, float(1.0 / (3.0 * ref.visc[0] + 0.5)), lambda_=0.25, omega_bulk=1.3)
+        sch = mb.Scheme(ident, ld, float(1.0 / (3.0 * ref.visc[0] + 0.5)), lambda_=0.25, omega_bulk=1.3,
+                        bc_kind={3: a.outlet} if a.kind == "channel" else None)
         sch.upload_state(a.level, init, init)
         if a.kind == "cavity":
             sch.set_bc_values(a.level, 2, cases.lid_values(ld, (0.05, 0.02, 0.0)))
+        if a.kind == "channel":
+            sch.set_bc_values(a.level, 2, cases.lid_values(ld, (0.03, 0.0, 0.0)))
+            nOut = len([b for b in ld.bc if b["id"] == 3][0]["elems"])
+            if nOut:
+                sch.set_bc_values(a.level, 3, np.full(nOut, 1.0))
+            aux0 = np.zeros(ld.nSize * 4)
+            aux0[:ld.nElems * 4] = ref.aux.reshape(-1, 4)[gpos].ravel()
+            from musubi_b200._lib import check, lib
+            check(lib.musb200_aux_upload(a.level, aux0.ctypes.data))
         m0 = sch.reduce()[0]
         sch.do_computation(a.steps)
         ref.run(a.steps)

@@ -86,6 +86,37 @@ def test_lid_driven_cavity_matches_oracle(mb, oracle, ident, omega):
     sch.destroy()
 
 
+CHANNEL = [
+    ({"kind": "fluid", "relaxation": "bgk", "layout": "d3q19"}, "pressure_expol"),
+    ({"kind": "fluid", "relaxation": "mrt", "layout": "d3q27"}, "pressure_antibounceback"),
+    ({"kind": "fluid_incompressible", "relaxation": "trt", "layout": "d3q19"}, "pressure_antibounceback"),
+    ({"kind": "fluid", "relaxation": "bgk", "layout": "d3q27"}, "pressure_expol"),
+    ({"kind": "fluid_incompressible", "relaxation": "mrt", "layout": "d3q19"}, "pressure_expol"),
+]
+
+
+@pytest.mark.parametrize("ident,outlet", CHANNEL,
+                         ids=["bgk19-expol", "mrt27-antibb", "trt19incomp-antibb", "bgk27-expol",
+                              "mrt19incomp-expol"])
+def test_channel_with_pressure_outlet_matches_oracle(mb, oracle, ident, outlet):
+    """walls + velocity_bounceback inlet + pressure outlet (a12): 200 steps, bit-exact"""
+    level, nsteps = 4, 200
+    ld, old, ref, sch = make_pair(mb, oracle, level, ident, 1.6, kind="channel", ic="rest",
+                                  omega_bulk=1.2, u_lid=(0.03, 0.0, 0.0), outlet=outlet, rho_out=1.0)
+    sch.do_computation(nsteps)
+    ref.run(nsteps)
+    got = sch.download_state(level)
+    exp = ref.state[ref.nNext]
+    n = ld.nFluid * ld.QQ
+    assert np.isfinite(exp[:n]).all()
+    assert rel_diff(got[:n], exp[:n]) < 1e-10
+    assert np.array_equal(got[:n], exp[:n])
+    aux = sch.download_aux(level)[:ld.nFluid * 4].reshape(-1, 4)
+    assert np.array_equal(aux, ref.aux[:ld.nFluid * 4].reshape(-1, 4))
+    assert aux[:, 1].mean() > 0.02          # the inlet drives a through-flow
+    sch.destroy()
+
+
 def test_random_omega_per_element(mb, oracle):
     """per-element omega (viscosity spacetime function), fixed seed 12345, omega in [0.5, 1.95]."""
     ident = {"kind": "fluid", "relaxation": "trt", "layout": "d3q19"}

@@ -53,7 +53,8 @@ def test_no_cpu_fallback_without_gpu():
 
 @pytest.mark.parametrize("level,QQ,kind,nranks", [
     (3, 19, "periodic", 1), (4, 27, "periodic", 1), (4, 19, "cavity", 1), (4, 27, "cavity", 1),
-    (4, 19, "periodic", 2), (4, 27, "periodic", 4), (4, 19, "cavity", 3), (5, 27, "periodic", 8)])
+    (4, 19, "periodic", 2), (4, 27, "periodic", 4), (4, 19, "cavity", 3), (5, 27, "periodic", 8),
+    (4, 19, "channel", 1), (4, 27, "channel", 1), (4, 19, "channel", 2), (4, 27, "channel", 8)])
 def test_index_lists_bit_exact_vs_oracle(oracle, level, QQ, kind, nranks):
     import musubi_b200 as mb
     for r in range(nranks):
@@ -67,7 +68,9 @@ def test_index_lists_bit_exact_vs_oracle(oracle, level, QQ, kind, nranks):
         for x, y in zip(a.recv + a.send, b.recv + b.send):
             assert np.array_equal(x["pos"], y["pos"]) and np.array_equal(x["elemPos"], y["elemPos"])
         for x, y in zip(a.bc, b.bc):
-            for k in ("elems", "links", "outPos", "posInBuffer", "iDir"):
+            assert x["id"] == y["id"] and x["kind"] == y["kind"]
+            for k in ("elems", "links", "outPos", "posInBuffer", "iDir", "normalInd", "posInBcElemBuf",
+                      "neighPos", "iElemOfLink", "statePos"):
                 assert np.array_equal(x[k], y[k]), k
 
 

@@ -19,7 +19,7 @@ def _launch(nproc, extra, port):
 
 
 @pytest.mark.parametrize("nproc,layout,kind", [(2, "d3q19", "periodic"), (4, "d3q27", "periodic"),
-                                               (3, "d3q19", "cavity")])
+                                               (3, "d3q19", "cavity"), (4, "d3q19", "channel")])
 def test_halo_lists_over_gloo(nproc, layout, kind):
     r = _launch(nproc, ["--mode", "lists", "--layout", layout, "--kind", kind, "--level", "4"], 29611 + nproc)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
@@ -37,7 +37,8 @@ def _ngpu():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("layout,relax,kind", [("d3q27", "mrt", "periodic"), ("d3q19", "trt", "cavity")])
+@pytest.mark.parametrize("layout,relax,kind", [("d3q27", "mrt", "periodic"), ("d3q19", "trt", "cavity"),
+                                               ("d3q19", "bgk", "channel")])
 def test_multi_gpu_matches_single_domain_oracle(layout, relax, kind):
     n = _ngpu()
     if n < 2:
