@@ -8,8 +8,12 @@ GPU) with the HBM roofline and the reference's CPU algorithm timed beside it.
 Workloads (BASELINE.json configs):
   N = 1 : cfg2  D3Q19 TRT lid-driven cavity 256^3 (level 8), bounce-back walls +
                 velocity_bounceback lid  -- the configuration the metric is quoted on
-  N > 1 : cfg3  D3Q27 MRT periodic 512^3 (level 9), SFC-partitioned into N equal
-                Morton ranges, halo exchange over NCCL (strong scaling: total work fixed)
+  N = 2, 4, 8 : the same cavity WEAK-scaled, 256^3 cells per GPU: the first N octants of the
+                level-9 cube (512x256x256, 512x512x256, 512^3 -- the "512^3-equivalent mesh" of
+                north_star at 8 GPUs), SFC-partitioned into N equal Morton ranges, halo exchange
+                through peer memory over NVLink (NCCL send/recv with --no-p2p)
+  --workload cfg3 : D3Q27 MRT periodic 512^3 (level 9) strong-scaled over N ranks (BASELINE
+                config 3; also cfg3-256 on one GPU)
 A "step" is one level time step (set_boundary, swap, fused aux+stream+collide,
 halo exchange) over the whole mesh.  `value` is device-timed with inputs resident
 in HBM; `e2e` goes through the public C ABI with HOST buffers: state upload from
@@ -171,15 +175,26 @@ def main():
     ap.add_argument("--level", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--overlap", action="store_true",
+                    help="sweep the send-halo elements first and overlap their exchange with the rest")
+    ap.add_argument("--no-p2p", action="store_true",
+                    help="halo exchange through pack/ncclSend/ncclRecv/unpack instead of peer memory")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    wl_name = args.workload or ("cfg2" if world == 1 else "cfg3")
+    wl_name = args.workload or "cfg2"
     wl = dict(WORKLOADS[wl_name])
+    octants = 8
+    if wl_name == "cfg2" and world > 1:
+        if world not in (2, 4, 8):
+            raise SystemExit("the weak-scaled cavity needs 1, 2, 4 or 8 ranks (whole octants per rank)")
+        wl["level"], octants = wl["level"] + 1, world       # 256^3 cells per GPU
+        wl["name"] = "D3Q19 TRT lid-driven cavity, 256^3 cells per GPU (first %d octants of 512^3)" % world
     if args.level:
         wl["level"] = args.level
+    weak = (wl_name == "cfg2")
     if args.impl == "reference":
         run_reference(args, wl_name, wl)
         return
@@ -228,7 +243,8 @@ def main():
 
     ident, level, QQ = wl["ident"], wl["level"], (19 if wl["ident"]["layout"] == "d3q19" else 27)
     t_setup = time.perf_counter()
-    ld = mb.LevelDesc(level, QQ, wl["kind"], rank, world)
+    ld = mb.LevelDesc(level, QQ, wl["kind"], rank, world, octants=octants)
+    check(lib.musb200_set_overlap(1 if args.overlap else 0))
     if wl["kind"] == "cavity":
         rho, vel = cases.cavity_rest(ld)
     else:
@@ -240,6 +256,14 @@ def main():
     host_state[:] = cases.equilibrium_state(QQ, rho, vel, ld.nSize)
     del rho, vel
     sch = mb.Scheme(ident, ld, wl["omega"], lambda_=3.0 / 16.0, omega_bulk=wl["omega"])
+    halo_path = "NCCL send/recv"
+    if world > 1 and not args.no_p2p:
+        try:
+            sch.p2p_connect(dist, level)
+            halo_path = "peer-memory stores over NVLink (one kernel)"
+        except Exception as ex:       # no peer access on this box: stay on the NCCL path
+            sys.stderr.write("rank %d: peer-memory halo exchange unavailable (%s), using NCCL\n" % (rank, ex))
+            check(lib.musb200_p2p_enable(level, 0))
     lid = cases.lid_values(ld) if wl["kind"] == "cavity" else None
     lid_pinned = None
     if lid is not None and lid.size:
@@ -324,10 +348,14 @@ def main():
         line = {
             "metric": "MLUPS", "value": value, "unit": "MLUPS", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": t_ms / K, "higher_is_better": True,
-            "scaling": "weak" if world == 1 else "strong",
+            "scaling": "weak" if weak else "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl_name + ": " + wl["name"], "level": level, "cells": int(nFluid_total),
                        "partition": "treelm SFC, %d equal Morton ranges" % world,
+                       "cells_per_gpu": int(nFluid_total / world),
+                       "halo_exchange": ("none (1 rank)" if world == 1 else
+                                         "%s, %s" % (halo_path, "overlapped with the interior sweep"
+                                                     if args.overlap else "after compute")),
                        "relaxation": ident["relaxation"], "layout": ident["layout"], "omega": wl["omega"],
                        "l2": "state of %.2f GB per buffer per GPU >> 126 MB L2, no flush needed" % (nbytes / 1e9),
                        "aux_every_step": False, "setup_s": round(setup_s, 2)},
@@ -342,6 +370,8 @@ def main():
             "check": {"total_mass": mass, "max_vel": vmax, "nan": nan},
         }
         print(json.dumps(line), flush=True)
+    sch.synchronize()
+    barrier()                    # peers may still store into this rank's halo rows
     sch.destroy()
     mb.mus_finalize()
     if dist is not None:

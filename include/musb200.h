@@ -156,6 +156,28 @@ int musb200_bc_set_values(int level, int bc_id, int nVals, const double *vals);
 int musb200_comm_register(int level, int buf_kind, int dir, int nProcs, const int32_t *proc,
                           const int32_t *nVals, const int32_t *pos);
 
+/* ---- halo exchange through peer memory (ranks of one node, NVLink / NVSwitch) ----------
+ * Optional replacement of pack -> ncclSend/ncclRecv -> unpack for the state halo buffer
+ * (buf_kind HALO): ONE kernel per level step stores every communicated link directly into
+ * the halo rows of the receiver's state array (CUDA IPC peer mapping) and completes the
+ * exchange with arrival counters -- the MPI_Isend/Irecv/Waitall of comm_isend_irecv_real
+ * (tem_comm_module.fpp:549-646) in one launch.  Set-up, once per level after
+ * musb200_comm_register:
+ *   1. every rank: musb200_p2p_export(level, blob)        -> MUSB200_P2P_BLOB bytes
+ *   2. host: all-gather the blobs (MPI_Allgather); every receiver sends its recv-buffer
+ *      position list buf_real(iProc)%pos to the rank it receives from (MPI_Sendrecv)
+ *   3. every rank: musb200_p2p_connect(level, nProcs, proc, blobs of those procs in the
+ *      order of the SEND buffer, nVals, remotePos = the receivers' position lists,
+ *      concatenated in the same order)
+ * Ranks must keep pdf%nNow/nNext in lockstep (they do: one swap per level step) and must
+ * synchronise + barrier before musb200_level_destroy.  The NCCL path stays available
+ * (musb200_p2p_enable(level, 0)) and is the one used across nodes.                       */
+#define MUSB200_P2P_BLOB 256
+int musb200_p2p_export(int level, void *blob);
+int musb200_p2p_connect(int level, int nProcs, const int32_t *proc, const void *blobs,
+                        const int32_t *nVals, const int32_t *remotePos);
+int musb200_p2p_enable(int level, int flag);
+
 /* ---- ghost interpolation: levelDesc%intpFromFiner / intpFromCoarser(order) -
  * targetList: positions of the target ghosts in the target level's total list;
  * per target a CSR row of source positions on the source level with weights
@@ -175,6 +197,13 @@ int musb200_step(int minLevel, int maxLevel, int nCoarseCycles);
 /* 1: auxField is written by every level step (needed by tracking every step);
  * 0 (default): only where the schedule reads it and on the last step of a call */
 int musb200_set_aux_every_step(int flag);
+/* 1: on several ranks the elements that own a send-buffer link (prp_sendHalo) are swept first
+ * and their halo exchange (on a second, high-priority stream) overlaps the sweep of the
+ * remaining elements; 0 (default): exchange strictly after compute as comm_isend_irecv_real is
+ * called in do_fast_singleLevel (mus_control_module.f90:644-649).  Both orders give identical
+ * results; the split sweep costs more than the exchange it hides at 256^3 elements per GPU
+ * (profiles/r01_multi_gpu.md), so it is opt-in. */
+int musb200_set_overlap(int flag);
 int musb200_synchronize(void);
 
 /* check_density / check_flow_status (mus_tools_module.f90:224-313):

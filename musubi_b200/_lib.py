@@ -59,6 +59,10 @@ SIGNATURES = {
     "musb200_timers": [P_DBL, P_DBL, P_DBL, P_DBL],
     "musb200_timers_reset": [],
     "musb200_launch_count": [P_LL],
+    "musb200_set_overlap": [c_int],
+    "musb200_p2p_export": [c_int, c_void_p],
+    "musb200_p2p_connect": [c_int, c_int, P_I32, c_void_p, P_I32, P_I32],
+    "musb200_p2p_enable": [c_int, c_int],
     "musb200_event_mark": [c_int],
     "musb200_event_elapsed": [P_DBL],
     "musb200_set_profiling": [c_int],
@@ -91,7 +95,7 @@ for _name, _args in SIGNATURES.items():
 
 mesh = _load(_MESH_SO)
 mesh.musb200_mesh_box_create.restype = c_void_p
-mesh.musb200_mesh_box_create.argtypes = [c_int] * 6
+mesh.musb200_mesh_box_create.argtypes = [c_int] * 7
 mesh.musb200_mesh_destroy.argtypes = [c_void_p]
 mesh.musb200_mesh_destroy.restype = None
 mesh.musb200_mesh_info.argtypes = [c_void_p, P_I64]

@@ -123,6 +123,24 @@ struct CommBuf {
   DevBuf<double> buf;
 };
 
+// peer-memory halo exchange of one level (p2p.cu)
+struct PeerLink {
+  bool on = false;
+  unsigned long long count = 0;          // exchanges done so far (same on every rank)
+  std::vector<int> sendRank, recvRank;
+  std::vector<void *> opened;            // IPC-opened pointers, closed at destroy
+  double *remoteState[kMaxPeers][2] = {};
+  long long remoteS[kMaxPeers] = {};
+  unsigned long long *remoteArrived[kMaxPeers] = {};
+  DevBuf<int32_t> srcPos, dstPos;        // send entries re-ordered for coalesced remote stores
+  DevBuf<uint8_t> peerOf;
+  DevBuf<unsigned long long> arrived;    // [nranks], written by the senders
+  DevBuf<unsigned int> ticket;
+  ~PeerLink() {
+    for (void *p : opened) cudaIpcCloseMemHandle(p);
+  }
+};
+
 struct Level {
   int level = 0, QQ = 0, nSize = 0, nFluid = 0, nGFC = 0, nGFF = 0, nHalo = 0;
   int nElems = 0, nSolve = 0;
@@ -142,6 +160,12 @@ struct Level {
   RelaxParams rp{1.0, 0.25, 1.0};
   std::vector<std::unique_ptr<BcData>> bcs;
   CommBuf send[3], recv[3];
+  // elements that own a link of the halo send buffer (prp_sendHalo, set_sendHaloBits
+  // mus_construction_module.fpp:2765): swept first so that their exchange overlaps the rest
+  PeerLink p2p;
+  DevBuf<int32_t> sendElems;   // 0-based, ascending
+  DevBuf<uint32_t> sendMask;   // 1 bit per element
+  int nSendElems = 0;
   IntpSet fromFiner;                 // fill my ghostFromFiner from level+1
   std::vector<IntpSet> fromCoarser;  // fill my ghostFromCoarser from level-1, per order
 };
@@ -150,6 +174,9 @@ struct Context {
   bool ready = false;
   int rank = 0, nranks = 1, device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t commStream = nullptr;   // halo exchange, high priority, overlaps the interior sweep
+  cudaEvent_t evBoundary = nullptr, evComm = nullptr;
+  int overlap = 0;   // measured slower than exchange-after-compute at 256^3 per GPU (profiles/)
   NcclApi *nccl = nullptr;
   ncclComm_t comm = nullptr;
   std::map<int, std::unique_ptr<Level>> levels;
@@ -189,8 +216,10 @@ static int stageBuf(size_t n) {
 struct Timed {
   int cat;
   bool on;
+  cudaStream_t st;
   cudaEvent_t a = nullptr, b = nullptr;
-  explicit Timed(int c) : cat(c), on(g.profiling != 0) {
+  explicit Timed(int c, cudaStream_t stream = nullptr)
+      : cat(c), on(g.profiling != 0), st(stream ? stream : g.stream) {
     if (!on) return;
     auto get = [] {
       cudaEvent_t e;
@@ -199,11 +228,11 @@ struct Timed {
       return e;
     };
     a = get(); b = get();
-    cudaEventRecord(a, g.stream);
+    cudaEventRecord(a, st);
   }
   ~Timed() {
     if (!on) return;
-    cudaEventRecord(b, g.stream);
+    cudaEventRecord(b, st);
     g.spans.push_back({cat, a, b});
   }
 };
@@ -267,31 +296,49 @@ static int setBoundary(Level &L) {
   return 0;
 }
 
-static int exchange(Level &L, int kind, double *state, int nComp) {
+static int exchange(Level &L, int kind, double *state, int nComp, cudaStream_t st = nullptr) {
   if (g.nranks == 1) return 0;
+  if (!st) st = g.stream;
   CommBuf &s = L.send[kind], &r = L.recv[kind];
   if (s.total == 0 && r.total == 0) return 0;
-  Timed t(T_COMM);
+  Timed t(T_COMM, st);
+  if (kind == MUSB200_BUF_HALO && L.p2p.on && state == L.state[L.nNext].p) {
+    // peer-memory path: one kernel stores every link into the receivers' halo rows
+    PeerLink &P = L.p2p;
+    P2PArgs a{};
+    a.state = state; a.S = L.S; a.QQ = L.QQ; a.n = s.total;
+    a.srcPos = P.srcPos.p; a.dstPos = P.dstPos.p; a.peerOf = P.peerOf.p;
+    a.nSendPeers = (int)P.sendRank.size(); a.nRecvPeers = (int)P.recvRank.size(); a.myRank = g.rank;
+    for (int k = 0; k < a.nSendPeers; ++k) {
+      a.remoteState[k] = P.remoteState[k][L.nNext];   // ranks swap now/next in lockstep
+      a.remoteS[k] = P.remoteS[k];
+      a.remoteArrived[k] = P.remoteArrived[k];
+    }
+    for (int k = 0; k < a.nRecvPeers; ++k) a.recvRank[k] = P.recvRank[k];
+    a.arrived = P.arrived.p; a.count = ++P.count; a.ticket = P.ticket.p;
+    MUSB_TRY(launchPushHalo(a, st));
+    ++g.launches;
+    return 0;
+  }
   if (s.total) {
-    MUSB_TRY(launchPack(nComp, state, L.S, s.pos.p, s.total, s.buf.p, g.stream));
+    MUSB_TRY(launchPack(nComp, state, L.S, s.pos.p, s.total, s.buf.p, st));
     ++g.launches;
   }
   MUSB_NCCL(g.nccl->GroupStart());
   for (size_t i = 0; i < s.proc.size(); ++i)
-    MUSB_NCCL(g.nccl->Send(s.buf.p + s.offset[i], (size_t)s.nVals[i], ncclDouble, s.proc[i], g.comm,
-                           g.stream));
+    MUSB_NCCL(g.nccl->Send(s.buf.p + s.offset[i], (size_t)s.nVals[i], ncclDouble, s.proc[i], g.comm, st));
   for (size_t i = 0; i < r.proc.size(); ++i)
-    MUSB_NCCL(g.nccl->Recv(r.buf.p + r.offset[i], (size_t)r.nVals[i], ncclDouble, r.proc[i], g.comm,
-                           g.stream));
+    MUSB_NCCL(g.nccl->Recv(r.buf.p + r.offset[i], (size_t)r.nVals[i], ncclDouble, r.proc[i], g.comm, st));
   MUSB_NCCL(g.nccl->GroupEnd());
   if (r.total) {
-    MUSB_TRY(launchUnpack(nComp, state, L.S, r.pos.p, r.total, r.buf.p, g.stream));
+    MUSB_TRY(launchUnpack(nComp, state, L.S, r.pos.p, r.total, r.buf.p, st));
     ++g.launches;
   }
   return 0;
 }
 
-static int sweep(Level &L, bool writeAux) {
+enum { SWEEP_ALL = 0, SWEEP_SENDHALO = 1, SWEEP_INTERIOR = 2 };
+static int sweep(Level &L, bool writeAux, int part = SWEEP_ALL) {
   if (!L.relaxSet) return setError(MUSB200_ERR_STATE, "musb200_set_relaxation missing");
   Timed t(T_COMPUTE);
   SweepArgs a{};
@@ -307,6 +354,8 @@ static int sweep(Level &L, bool writeAux) {
   a.count = L.nSolve;
   a.write_aux = writeAux ? 1 : 0;
   a.rp = L.rp;
+  if (part == SWEEP_SENDHALO) { a.list = L.sendElems.p; a.count = L.nSendElems; }
+  if (part == SWEEP_INTERIOR) a.skip = L.sendMask.p;
   MUSB_TRY(launchSweep(L.QQ, L.relax, L.kind, a, g.stream));
   ++g.launches;
   return 0;
@@ -360,6 +409,20 @@ static int levelStep(int iLevel, int minLevel, int maxLevel, bool lastCycle) {
   std::swap(L.nNow, L.nNext);
   // multi-level: the interpolation routines read auxField of their sources every step
   const bool writeAux = g.auxEveryStep || multi || lastCycle || L.auxForBc;
+  if (!multi && g.nranks > 1 && g.overlap && L.nSendElems > 0) {
+    // single level, several ranks: sweep the send-halo elements first, then exchange them on the
+    // communication stream while the remaining elements are swept (the reference exchanges
+    // strictly after compute, mus_control_module.f90:605-649; results are identical because the
+    // packed links are final once their elements are collided and the unpack touches halo rows only)
+    MUSB_TRY(sweep(L, writeAux, SWEEP_SENDHALO));
+    MUSB_CUDA(cudaEventRecord(g.evBoundary, g.stream));
+    MUSB_CUDA(cudaStreamWaitEvent(g.commStream, g.evBoundary, 0));
+    MUSB_TRY(exchange(L, MUSB200_BUF_HALO, L.state[L.nNext].p, L.QQ, g.commStream));
+    MUSB_CUDA(cudaEventRecord(g.evComm, g.commStream));
+    MUSB_TRY(sweep(L, writeAux, SWEEP_INTERIOR));
+    MUSB_CUDA(cudaStreamWaitEvent(g.stream, g.evComm, 0));
+    return 0;
+  }
   MUSB_TRY(sweep(L, writeAux));
   if (iLevel < maxLevel) {
     // auxField of my ghostFromFiner elements <- average of level+1
@@ -434,6 +497,13 @@ int musb200_init(int rank, int nranks, int local_device, const void *nccl_unique
     return setError(MUSB200_ERR_CUDA, std::string("device ") + prop.name + " is not sm_100 class");
   g.rank = rank; g.nranks = nranks; g.device = local_device;
   MUSB_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;
+    MUSB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    MUSB_CUDA(cudaStreamCreateWithPriority(&g.commStream, cudaStreamNonBlocking, hi));
+    MUSB_CUDA(cudaEventCreateWithFlags(&g.evBoundary, cudaEventDisableTiming));
+    MUSB_CUDA(cudaEventCreateWithFlags(&g.evComm, cudaEventDisableTiming));
+  }
   MUSB_CUDA(cudaEventCreate(&g.mark[0]));
   MUSB_CUDA(cudaEventCreate(&g.mark[1]));
   MUSB_TRY(g.red.alloc(3 * 592 + 8));
@@ -461,8 +531,11 @@ int musb200_finalize(void) {
   g.pool.clear();
   if (g.comm) { g.nccl->CommDestroy(g.comm); g.comm = nullptr; }
   cudaEventDestroy(g.mark[0]); cudaEventDestroy(g.mark[1]);
+  cudaEventDestroy(g.evBoundary); cudaEventDestroy(g.evComm);
+  cudaStreamSynchronize(g.commStream);
+  cudaStreamDestroy(g.commStream);
   cudaStreamDestroy(g.stream);
-  g.stream = nullptr;
+  g.stream = nullptr; g.commStream = nullptr;
   g.ready = false;
   g.launches = 0;
   return 0;
@@ -769,6 +842,133 @@ int musb200_comm_register(int level, int buf_kind, int dir, int nProcs, const in
   }
   MUSB_TRY(c.pos.upload(pos, (size_t)c.total, g.stream));
   MUSB_TRY(c.buf.alloc((size_t)std::max(1, c.total)));
+  if (buf_kind == MUSB200_BUF_HALO && dir == MUSB200_DIR_SEND) {
+    std::vector<uint32_t> mask(((size_t)L->S + 31) / 32, 0u);
+    std::vector<int32_t> elems;
+    for (int i = 0; i < c.total; ++i) {
+      const int e = (pos[i] - 1) / L->QQ;
+      if (e < 0 || e >= L->nSolve) return setError(MUSB200_ERR_ARG, "send position outside the solved elements");
+      if (!((mask[e >> 5] >> (e & 31)) & 1u)) { mask[e >> 5] |= 1u << (e & 31); elems.push_back(e); }
+    }
+    std::sort(elems.begin(), elems.end());
+    L->nSendElems = (int)elems.size();
+    MUSB_TRY(L->sendElems.upload(elems.data(), elems.size(), g.stream));
+    MUSB_TRY(L->sendMask.upload(mask.data(), mask.size(), g.stream));
+    MUSB_CUDA(cudaStreamSynchronize(g.stream));
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// peer-memory halo exchange: export / connect
+namespace {
+struct P2PBlob {                 // MUSB200_P2P_BLOB bytes, plain data
+  cudaIpcMemHandle_t state[2];
+  cudaIpcMemHandle_t arrived;
+  long long S;
+  int rank, QQ, nSize, device;
+  char pad[MUSB200_P2P_BLOB - 3 * (int)sizeof(cudaIpcMemHandle_t) - (int)sizeof(long long) - 4 * (int)sizeof(int)];
+};
+static_assert(sizeof(P2PBlob) == MUSB200_P2P_BLOB, "blob layout");
+}  // namespace
+
+int musb200_p2p_export(int level, void *blob) {
+  GET_LEVEL(L, level);
+  if (!blob) return setError(MUSB200_ERR_ARG, "null argument");
+  PeerLink &P = L->p2p;
+  if (P.arrived.n == 0) {
+    MUSB_TRY(P.arrived.alloc((size_t)std::max(g.nranks, 1)));
+    MUSB_TRY(P.ticket.alloc(1));
+    MUSB_CUDA(cudaMemsetAsync(P.arrived.p, 0, P.arrived.n * sizeof(unsigned long long), g.stream));
+    MUSB_CUDA(cudaMemsetAsync(P.ticket.p, 0, sizeof(unsigned int), g.stream));
+    MUSB_CUDA(cudaStreamSynchronize(g.stream));
+  }
+  P2PBlob b;
+  std::memset(&b, 0, sizeof(b));
+  MUSB_CUDA(cudaIpcGetMemHandle(&b.state[0], L->state[0].p));
+  MUSB_CUDA(cudaIpcGetMemHandle(&b.state[1], L->state[1].p));
+  MUSB_CUDA(cudaIpcGetMemHandle(&b.arrived, P.arrived.p));
+  b.S = L->S; b.rank = g.rank; b.QQ = L->QQ; b.nSize = L->nSize; b.device = g.device;
+  std::memcpy(blob, &b, sizeof(b));
+  return 0;
+}
+
+int musb200_p2p_connect(int level, int nProcs, const int32_t *proc, const void *blobs,
+                        const int32_t *nVals, const int32_t *remotePos) {
+  GET_LEVEL(L, level);
+  PeerLink &P = L->p2p;
+  CommBuf &s = L->send[MUSB200_BUF_HALO], &r = L->recv[MUSB200_BUF_HALO];
+  if (P.arrived.n == 0) return setError(MUSB200_ERR_STATE, "musb200_p2p_export must come first");
+  if (nProcs != (int)s.proc.size() || nProcs > kMaxPeers || (int)r.proc.size() > kMaxPeers)
+    return setError(MUSB200_ERR_ARG, "peer list does not match the halo send buffer");
+  if (nProcs > 0 && (!proc || !blobs || !nVals || !remotePos)) return setError(MUSB200_ERR_ARG, "null argument");
+  std::vector<uint8_t> peerOf((size_t)s.total);
+  for (int k = 0; k < nProcs; ++k) {
+    if (proc[k] != s.proc[k] || nVals[k] != s.nVals[k])
+      return setError(MUSB200_ERR_ARG, "peer order / message length differs from musb200_comm_register");
+    P2PBlob b;
+    std::memcpy(&b, static_cast<const char *>(blobs) + (size_t)k * MUSB200_P2P_BLOB, sizeof(b));
+    if (b.rank != proc[k] || b.QQ != L->QQ) return setError(MUSB200_ERR_ARG, "blob belongs to another rank / stencil");
+    int can = 0;
+    MUSB_CUDA(cudaDeviceCanAccessPeer(&can, g.device, b.device));
+    if (!can) return setError(MUSB200_ERR_CUDA, "no peer access between devices " + std::to_string(g.device) +
+                                                    " and " + std::to_string(b.device));
+    void *p0 = nullptr, *p1 = nullptr, *pf = nullptr;
+    MUSB_CUDA(cudaIpcOpenMemHandle(&p0, b.state[0], cudaIpcMemLazyEnablePeerAccess));
+    P.opened.push_back(p0);
+    MUSB_CUDA(cudaIpcOpenMemHandle(&p1, b.state[1], cudaIpcMemLazyEnablePeerAccess));
+    P.opened.push_back(p1);
+    MUSB_CUDA(cudaIpcOpenMemHandle(&pf, b.arrived, cudaIpcMemLazyEnablePeerAccess));
+    P.opened.push_back(pf);
+    P.remoteState[k][0] = static_cast<double *>(p0);
+    P.remoteState[k][1] = static_cast<double *>(p1);
+    P.remoteArrived[k] = static_cast<unsigned long long *>(pf);
+    P.remoteS[k] = b.S;
+    for (int i = 0; i < nVals[k]; ++i) {
+      const int rp = remotePos[s.offset[k] + i];
+      if (rp < 1 || rp > b.nSize * b.QQ) return setError(MUSB200_ERR_ARG, "remote position out of range");
+      peerOf[(size_t)s.offset[k] + i] = (uint8_t)k;
+    }
+  }
+  P.sendRank.assign(s.proc.begin(), s.proc.end());
+  P.recvRank.assign(r.proc.begin(), r.proc.end());
+  // The lists come elem-major / direction-minor (the reference's AOS order).  The receiver's
+  // rows are SoA and its halo block is sorted by treeID, so ordering the entries by (peer,
+  // remote direction, remote element) makes consecutive threads store consecutive addresses:
+  // full 128-byte NVLink writes instead of scattered 8-byte ones.
+  std::vector<int32_t> srcHost((size_t)s.total);
+  MUSB_CUDA(cudaMemcpyAsync(srcHost.data(), s.pos.p, (size_t)s.total * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                            g.stream));
+  MUSB_CUDA(cudaStreamSynchronize(g.stream));
+  std::vector<int32_t> order((size_t)s.total);
+  for (int i = 0; i < s.total; ++i) order[i] = i;
+  const int QQ = L->QQ;
+  std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
+    if (peerOf[x] != peerOf[y]) return peerOf[x] < peerOf[y];
+    const int dx = (remotePos[x] - 1) % QQ, dy = (remotePos[y] - 1) % QQ;
+    if (dx != dy) return dx < dy;
+    return remotePos[x] < remotePos[y];
+  });
+  std::vector<int32_t> srcSorted((size_t)s.total), dstSorted((size_t)s.total);
+  std::vector<uint8_t> peerSorted((size_t)s.total);
+  for (int i = 0; i < s.total; ++i) {
+    srcSorted[i] = srcHost[order[i]];
+    dstSorted[i] = remotePos[order[i]];
+    peerSorted[i] = peerOf[order[i]];
+  }
+  MUSB_TRY(P.srcPos.upload(srcSorted.data(), srcSorted.size(), g.stream));
+  MUSB_TRY(P.dstPos.upload(dstSorted.data(), dstSorted.size(), g.stream));
+  MUSB_TRY(P.peerOf.upload(peerSorted.data(), peerSorted.size(), g.stream));
+  MUSB_CUDA(cudaStreamSynchronize(g.stream));
+  P.on = true;
+  return 0;
+}
+
+int musb200_p2p_enable(int level, int flag) {
+  GET_LEVEL(L, level);
+  if (flag && L->p2p.dstPos.n == 0 && L->send[MUSB200_BUF_HALO].total > 0)
+    return setError(MUSB200_ERR_STATE, "musb200_p2p_connect must come first");
+  L->p2p.on = flag != 0;
   return 0;
 }
 
@@ -806,9 +1006,15 @@ int musb200_step(int minLevel, int maxLevel, int nCoarseCycles) {
   return 0;
 }
 
+int musb200_set_overlap(int flag) {
+  g.overlap = flag ? 1 : 0;
+  return 0;
+}
+
 int musb200_synchronize(void) {
   MUSB_TRY(needReady());
   MUSB_CUDA(cudaStreamSynchronize(g.stream));
+  MUSB_CUDA(cudaStreamSynchronize(g.commStream));
   return 0;
 }
 

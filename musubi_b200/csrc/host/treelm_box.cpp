@@ -65,6 +65,8 @@ struct Comm {
 
 struct Box {
   int level, QQ, kind, rank, nranks;
+  int octants = 8;       // the domain = the first 1, 2, 4 or 8 octants of the universe cube
+  int ext[3] = {0, 0, 0};  // its extent in cells: x doubles first, then y, then z (Morton order)
   int64_t lo, hi, firstId;
   int nFluid, nHalo, nElems, nSize;
   std::vector<int64_t> total, property;
@@ -80,24 +82,28 @@ struct Box {
     return (int)(std::upper_bound(partEnd.begin(), partEnd.end(), m) - partEnd.begin());
   }
   // boundary id met when stepping from inside to (x,y,z); 0 = none
-  int bid(int x, int y, int z, int n) const {
+  int bid(int x, int y, int z, int) const {
     if (kind == 0) return 0;
-    if (kind == 2) {  // channel: walls on the y/z faces, inlet at x < 0, outlet at x >= n
-      if (y < 0 || y >= n || z < 0 || z >= n) return 1;
+    if (kind == 2) {  // channel: walls on the y/z faces, inlet at x < 0, outlet at x >= extent
+      if (y < 0 || y >= ext[1] || z < 0 || z >= ext[2]) return 1;
       if (x < 0) return 2;
-      if (x >= n) return 3;
+      if (x >= ext[0]) return 3;
       return 0;
     }
-    const bool outxy = x < 0 || x >= n || y < 0 || y >= n;
+    const bool outxy = x < 0 || x >= ext[0] || y < 0 || y >= ext[1];
     if (outxy || z < 0) return 1;  // 'wall'
-    if (z >= n) return 2;          // 'lid'
+    if (z >= ext[2]) return 2;     // 'lid'
     return 0;
   }
 };
 
 void build(Box &b, int commReduced) {
   const int QQ = b.QQ, QQN = QQ - 1, n = 1 << b.level;
-  const int64_t nGlob = (int64_t)n * n * n;
+  b.ext[0] = b.octants >= 2 ? n : n / 2;
+  b.ext[1] = b.octants >= 4 ? n : n / 2;
+  b.ext[2] = b.octants >= 8 ? n : n / 2;
+  // whole octants in Morton order: the element list is the contiguous Morton range [0, nGlob)
+  const int64_t nGlob = (int64_t)b.octants * (n / 2) * (n / 2) * (n / 2);
   b.firstId = 0;
   for (int l = 0; l < b.level; ++l) b.firstId = b.firstId * 8 + 1;  // (8^L - 1)/7
   for (int q = 0; q < QQN; ++q)
@@ -316,7 +322,8 @@ void build(Box &b, int commReduced) {
         for (int k = 1; k <= 2; ++k) {
           const int xn = x + k * kCx[best][0], yn = y + k * kCx[best][1], zn = z + k * kCx[best][2];
           int32_t p = 0;
-          if (xn >= 0 && xn < n && yn >= 0 && yn < n && zn >= 0 && zn < n) p = posOf(mortonOf(xn, yn, zn));
+          if (xn >= 0 && xn < b.ext[0] && yn >= 0 && yn < b.ext[1] && zn >= 0 && zn < b.ext[2])
+            p = posOf(mortonOf(xn, yn, zn));
           if (p <= 0) {                       // no valid neighbour: keep the last valid one
             if (k == 1) { np[0] = np[1] = e + 1; }
             else np[1] = np[0];
@@ -345,12 +352,18 @@ extern "C" {
 
 // kind: 0 = fully periodic cube, 1 = cavity (5 walls + moving lid at z = top),
 //       2 = channel (4 walls, velocity inlet at x = 0, pressure outlet at x = top)
-void *musb200_mesh_box_create(int level, int QQ, int kind, int rank, int nranks, int comm_reduced) {
+// octants: the domain is the first 1, 2, 4 or 8 octants of the level-L cube (a periodic mesh
+//          must fill the cube: treelm wraps at the universe)
+void *musb200_mesh_box_create(int level, int QQ, int kind, int rank, int nranks, int comm_reduced,
+                              int octants) {
   if (level < 1 || level > 10 || (QQ != 19 && QQ != 27) || kind < 0 || kind > 2 || nranks < 1 ||
       rank < 0 || rank >= nranks)
     return nullptr;
+  if ((octants != 1 && octants != 2 && octants != 4 && octants != 8) || (kind == 0 && octants != 8))
+    return nullptr;
   Box *b = new Box();
   b->level = level; b->QQ = QQ; b->kind = kind; b->rank = rank; b->nranks = nranks;
+  b->octants = octants;
   build(*b, comm_reduced);
   return b;
 }

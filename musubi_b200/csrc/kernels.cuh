@@ -64,6 +64,26 @@ int launchPack(int QQ, const double *state, long long S, const int32_t *pos, int
 int launchUnpack(int QQ, double *state, long long S, const int32_t *pos, int n, const double *buf,
                  cudaStream_t st);
 
+// peer-memory halo exchange (p2p.cu)
+constexpr int kMaxPeers = 16;
+struct P2PArgs {
+  const double *state;        // my state(:, next)
+  long long S;
+  int QQ, n;                  // n = all send entries, peers concatenated
+  const int32_t *srcPos;      // my state positions (the send buffer's pos list)
+  const int32_t *dstPos;      // the receiver's state positions (its recv buffer's pos list)
+  const uint8_t *peerOf;      // entry -> index into the peer tables below
+  int nSendPeers, nRecvPeers, myRank;
+  double *remoteState[kMaxPeers];              // receiver's state(:, next), peer-mapped
+  long long remoteS[kMaxPeers];
+  unsigned long long *remoteArrived[kMaxPeers];  // receiver's arrived[nranks], peer-mapped
+  int recvRank[kMaxPeers];
+  unsigned long long *arrived;  // my arrived[nranks]
+  unsigned long long count;     // number of this exchange
+  unsigned int *ticket;
+};
+int launchPushHalo(const P2PArgs &a, cudaStream_t st);
+
 // reductions: out[0] = total mass, out[1] = max |u|^2, out[2] = nan count
 int launchReduce(int QQ, const double *state, long long S, int nFluid, double *scratch,
                  double *out, cudaStream_t st);

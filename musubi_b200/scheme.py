@@ -189,6 +189,36 @@ class Scheme:
         v = np.ascontiguousarray(vals, dtype=np.float64)
         check(lib.musb200_bc_set_values(level, bc_id, v.size, v.ctypes.data))
 
+    # -- peer-memory halo exchange ------------------------------------------------
+    def p2p_connect(self, dist, level=None):
+        """set-up of the peer-memory halo exchange over a torch.distributed (gloo) group: the
+        blobs are all-gathered and every receiver ships its recv position list to its sender
+        -- what the Fortran shim does with MPI_Allgather / MPI_Sendrecv."""
+        import torch
+        level = self.minLevel if level is None else level
+        ld = self.levelDesc[level]
+        blob = ctypes.create_string_buffer(256)
+        check(lib.musb200_p2p_export(level, blob))
+        mine = torch.frombuffer(bytearray(blob.raw), dtype=torch.uint8).clone()
+        allb = [torch.zeros(256, dtype=torch.uint8) for _ in range(dist.get_world_size())]
+        dist.all_gather(allb, mine)
+        reqs, got = [], {}
+        for r in ld.recv:                                   # my recv list goes to its sender
+            reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(r["pos"], dtype=np.int32)), r["proc"]))
+        for s_ in ld.send:                                  # the receiver's list for my message
+            got[s_["proc"]] = torch.zeros(len(s_["pos"]), dtype=torch.int32)
+            reqs.append(dist.irecv(got[s_["proc"]], s_["proc"]))
+        for q in reqs:
+            q.wait()
+        proc = np.array([s_["proc"] for s_ in ld.send], dtype=np.int32)
+        nVals = np.array([len(s_["pos"]) for s_ in ld.send], dtype=np.int32)
+        rpos = (np.concatenate([got[int(p)].numpy() for p in proc]).astype(np.int32)
+                if len(proc) else np.zeros(0, dtype=np.int32))
+        blobs = b"".join(bytes(allb[int(p)].numpy().tobytes()) for p in proc)
+        check(lib.musb200_p2p_connect(level, len(proc), ptr(proc, P_I32), ctypes.c_char_p(blobs),
+                                      ptr(nVals, P_I32), ptr(rpos, P_I32)))
+        dist.barrier()
+
     # -- control%do_computation ----------------------------------------------
     def do_computation(self, nCycles=1):
         check(lib.musb200_step(self.minLevel, self.maxLevel, int(nCycles)))

@@ -14,8 +14,12 @@ _BC_LABEL = {"cavity": ("wall", "lid"), "channel": ("wall", "inlet", "outlet")}
 class LevelDesc:
     """tem_levelDesc_type + pdf_data_type of one level on one rank."""
 
-    def __init__(self, level, QQ, kind="periodic", rank=0, nranks=1, comm_reduced=True):
-        h = mesh.musb200_mesh_box_create(level, QQ, KIND[kind], rank, nranks, 1 if comm_reduced else 0)
+    def __init__(self, level, QQ, kind="periodic", rank=0, nranks=1, comm_reduced=True, octants=8):
+        """octants: the domain is the first 1, 2, 4 or 8 octants of the level-`level` universe cube
+        in Morton order (extent doubles in x, then y, then z); walled kinds only when < 8."""
+        h = mesh.musb200_mesh_box_create(level, QQ, KIND[kind], rank, nranks, 1 if comm_reduced else 0,
+                                         octants)
+        self.octants = octants
         if not h:
             raise ValueError("bad box-mesh parameters")
         try:

@@ -163,6 +163,16 @@ class LevelDesc:
     pass
 
 
+def box_extents(level, octants):
+    """the domain is the first `octants` (1, 2, 4, 8) octants of the level-L universe cube in
+    Morton order: x doubles first, then y, then z (treelm meshes are sparse octrees; absent
+    octants are simply not in the element list)."""
+    assert octants in (1, 2, 4, 8)
+    n = 1 << level
+    h = n // 2
+    return (n if octants >= 2 else h, n if octants >= 4 else h, n if octants >= 8 else h)
+
+
 def box_boundary_id(xn, yn, zn, n, kind):
     """BC id seen when looking from a fluid cell to position (xn,yn,zn).
     kind 'periodic': no boundaries (treelm wraps at the universe cube).
@@ -173,26 +183,30 @@ def box_boundary_id(xn, yn, zn, n, kind):
     The synthetic-mesh convention (Seeder would store these ids in bnd.lsb)."""
     if kind == "periodic":
         return np.zeros(xn.shape, dtype=np.int64)
+    nx, ny, nz = n if isinstance(n, tuple) else (n, n, n)
     if kind == "channel":
-        out_yz = (yn < 0) | (yn >= n) | (zn < 0) | (zn >= n)
+        out_yz = (yn < 0) | (yn >= ny) | (zn < 0) | (zn >= nz)
         bid = np.zeros(xn.shape, dtype=np.int64)
         bid[out_yz] = 1
         bid[(~out_yz) & (xn < 0)] = 2
-        bid[(~out_yz) & (xn >= n)] = 3
+        bid[(~out_yz) & (xn >= nx)] = 3
         return bid
-    out_xy = (xn < 0) | (xn >= n) | (yn < 0) | (yn >= n)
+    out_xy = (xn < 0) | (xn >= nx) | (yn < 0) | (yn >= ny)
     bid = np.zeros(xn.shape, dtype=np.int64)
     bid[out_xy | (zn < 0)] = 1
-    bid[(~out_xy) & (zn >= n)] = 2
+    bid[(~out_xy) & (zn >= nz)] = 2
     return bid
 
 
 def build_level_desc(level, QQ, kind="periodic", rank=0, nranks=1, comm_reduced=True,
-                     _with_send=True):
+                     _with_send=True, octants=8):
     """total list, neighbour lists, connectivity, halo and BC lists of one rank."""
     ld = LevelDesc()
     n = 1 << level
-    nGlob = n ** 3
+    dims = box_extents(level, octants)
+    if octants != 8 and kind == "periodic":
+        raise ValueError("treelm wraps at the universe cube: a periodic mesh must fill it")
+    nGlob = octants * (n // 2) ** 3
     cx = cx_dir(QQ)
     inv = cx_dir_inv(QQ)
     QQN = QQ - 1
@@ -207,14 +221,14 @@ def build_level_desc(level, QQ, kind="periodic", rank=0, nranks=1, comm_reduced=
     ngh_m = np.empty((nFluid, QQN), dtype=np.int64)
     for d in range(QQN):
         xn, yn, zn = x + cx[d, 0], y + cx[d, 1], z + cx[d, 2]
-        bid = box_boundary_id(xn, yn, zn, n, kind)
+        bid = box_boundary_id(xn, yn, zn, dims, kind)
         m = morton_of_coord(np.mod(xn, n), np.mod(yn, n), np.mod(zn, n))
         ngh_m[:, d] = np.where(bid > 0, -bid, m)
     remote = (ngh_m >= 0) & ((ngh_m < lo) | (ngh_m >= hi))
     halo_m = np.unique(ngh_m[remote])
     nHalo = halo_m.size
     nElems = nFluid + nHalo
-    ld.level, ld.QQ, ld.kind = level, QQ, kind
+    ld.level, ld.QQ, ld.kind, ld.octants = level, QQ, kind, octants
     ld.nFluid, ld.nGhostFromCoarser, ld.nGhostFromFiner, ld.nHalo = nFluid, 0, 0, nHalo
     ld.nElems = nElems
     ld.nSize = ((nElems + 3) // 4) * 4          # mus_pdf_module.f90:128-129
@@ -234,7 +248,7 @@ def build_level_desc(level, QQ, kind="periodic", rank=0, nranks=1, comm_reduced=
         hx, hy, hz = coord_of_morton(halo_m)
         for d in range(QQN):
             xn, yn, zn = hx + cx[d, 0], hy + cx[d, 1], hz + cx[d, 2]
-            bid = box_boundary_id(xn, yn, zn, n, kind)
+            bid = box_boundary_id(xn, yn, zn, dims, kind)
             m = morton_of_coord(np.mod(xn, n), np.mod(yn, n), np.mod(zn, n))
             isloc = (m >= lo) & (m < hi) & (bid == 0)
             hp = np.searchsorted(halo_m, m)
@@ -272,7 +286,7 @@ def build_level_desc(level, QQ, kind="periodic", rank=0, nranks=1, comm_reduced=
             for p in range(nranks):
                 if p == rank:
                     continue
-                other = _peer_desc(level, QQ, kind, p, nranks, comm_reduced)
+                other = _peer_desc(level, QQ, kind, p, nranks, comm_reduced, octants)
                 for r, m in zip(other.recv, other.recv_masks):
                     if r["proc"] != rank:
                         continue
@@ -342,7 +356,8 @@ def build_level_desc(level, QQ, kind="periodic", rank=0, nranks=1, comm_reduced=
             npos = np.zeros((elems.size, 2), dtype=np.int32)
             for k in (1, 2):
                 xn, yn, zn = ex + k * bc["normal"][:, 0], ey + k * bc["normal"][:, 1], ez + k * bc["normal"][:, 2]
-                inside = (xn >= 0) & (xn < n) & (yn >= 0) & (yn < n) & (zn >= 0) & (zn < n)
+                inside = ((xn >= 0) & (xn < dims[0]) & (yn >= 0) & (yn < dims[1]) & (zn >= 0)
+                          & (zn < dims[2]))
                 m = morton_of_coord(np.mod(xn, n), np.mod(yn, n), np.mod(zn, n))
                 p = np.where((m >= lo) & (m < hi), m - lo + 1, 0)
                 if nHalo:
@@ -375,11 +390,11 @@ def _recv_positions(ld, epos, QQ, inv, halo_offset, comm_reduced):
 _PEER_CACHE = {}
 
 
-def _peer_desc(level, QQ, kind, p, nranks, comm_reduced):
-    key = (level, QQ, kind, p, nranks, comm_reduced)
+def _peer_desc(level, QQ, kind, p, nranks, comm_reduced, octants=8):
+    key = (level, QQ, kind, p, nranks, comm_reduced, octants)
     if key not in _PEER_CACHE:
         _PEER_CACHE[key] = build_level_desc(level, QQ, kind, p, nranks, comm_reduced,
-                                            _with_send=False)
+                                            _with_send=False, octants=octants)
     return _PEER_CACHE[key]
 
 

@@ -27,6 +27,9 @@ def main():
     ap.add_argument("--kind", default="periodic")
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--outlet", default="pressure_expol")
+    ap.add_argument("--octants", type=int, default=8)
+    ap.add_argument("--overlap", action="store_true")
+    ap.add_argument("--p2p", action="store_true")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -34,7 +37,7 @@ def main():
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import musubi_b200 as mb
     QQ = 19 if a.layout == "d3q19" else 27
-    ld = mb.LevelDesc(a.level, QQ, a.kind, rank, world)
+    ld = mb.LevelDesc(a.level, QQ, a.kind, rank, world, octants=a.octants)
 
     if a.mode == "lists":
         code = lambda tid, d: tid.astype(np.float64) * 100.0 + d  # noqa: E731
@@ -72,9 +75,10 @@ def main():
         dist.broadcast(t, 0)
         mb.mus_init(rank, world, int(os.environ.get("LOCAL_RANK", rank)), bytes(t.numpy().tobytes()))
         # single-domain oracle = the truth for every rank
-        gl = mo.build_level_desc(a.level, QQ, a.kind)
+        mb._lib.check(mb._lib.lib.musb200_set_overlap(1 if a.overlap else 0))
+        gl = mo.build_level_desc(a.level, QQ, a.kind, octants=a.octants)
         ref = mo.Scheme(gl, a.relaxation, "fluid", omega=1.7, lambda_=0.25, omega_bulk=1.3)
-        gld = mb.LevelDesc(a.level, QQ, a.kind, 0, 1)
+        gld = mb.LevelDesc(a.level, QQ, a.kind, 0, 1, octants=a.octants)
         if a.kind == "cavity":
             rho, vel = cases.cavity_rest(gld)
             ref.bc_vel[2] = cases.lid_values(gld, (0.05, 0.02, 0.0))
@@ -94,6 +98,8 @@ def main():
         sch = mb.Scheme(ident, ld, float(1.0 / (3.0 * ref.visc[0] + 0.5)), lambda_=0.25, omega_bulk=1.3,
                         bc_kind={3: a.outlet} if a.kind == "channel" else None)
         sch.upload_state(a.level, init, init)
+        if a.p2p:
+            sch.p2p_connect(dist, a.level)
         if a.kind == "cavity":
             sch.set_bc_values(a.level, 2, cases.lid_values(ld, (0.05, 0.02, 0.0)))
         if a.kind == "channel":
@@ -119,6 +125,8 @@ def main():
         assert abs(m1 / ref.total_mass() - 1.0) < 1e-12
         if a.kind == "periodic":
             assert abs(m1 / m0 - 1.0) < 1e-13
+        sch.synchronize()
+        dist.barrier()           # peers may still store into this rank's halo rows
         sch.destroy()
         mb.mus_finalize()
     dist.barrier()

@@ -74,6 +74,26 @@ def test_index_lists_bit_exact_vs_oracle(oracle, level, QQ, kind, nranks):
                 assert np.array_equal(x[k], y[k]), k
 
 
+@pytest.mark.parametrize("QQ,kind,octants,nranks", [(19, "cavity", 1, 1), (19, "cavity", 2, 2),
+                                                      (27, "cavity", 4, 4), (19, "channel", 2, 2),
+                                                      (27, "channel", 4, 3)])
+def test_partial_cube_lists_bit_exact_vs_oracle(oracle, QQ, kind, octants, nranks):
+    """weak-scaling meshes: the first 1/2/4 octants of the cube (what bench.py --gpus N uses)"""
+    import musubi_b200 as mb
+    for r in range(nranks):
+        a = mb.LevelDesc(4, QQ, kind, r, nranks, octants=octants)
+        b = oracle.build_level_desc(4, QQ, kind, r, nranks, octants=octants)
+        assert a.nFluid + sum(mb.LevelDesc(4, QQ, kind, q, nranks, octants=octants).nFluid
+                              for q in range(nranks) if q != r) == octants * 8 ** 3
+        for k in ("total", "property", "nghElems", "neigh", "bc_elemBuffer"):
+            assert np.array_equal(getattr(a, k), getattr(b, k)), k
+        for x, y in zip(a.recv + a.send, b.recv + b.send):
+            assert x["proc"] == y["proc"] and np.array_equal(x["pos"], y["pos"])
+        for x, y in zip(a.bc, b.bc):
+            for k in ("elems", "links", "outPos", "posInBuffer", "iDir", "normalInd", "neighPos"):
+                assert np.array_equal(x[k], y[k]), k
+
+
 def test_send_and_recv_lists_pair_up(oracle):
     """what rank p receives from q is exactly what q sends to p (same length, same links)."""
     import musubi_b200 as mb

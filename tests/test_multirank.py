@@ -37,14 +37,23 @@ def _ngpu():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("layout,relax,kind", [("d3q27", "mrt", "periodic"), ("d3q19", "trt", "cavity"),
-                                               ("d3q19", "bgk", "channel")])
-def test_multi_gpu_matches_single_domain_oracle(layout, relax, kind):
+@pytest.mark.parametrize("layout,relax,kind,extra", [
+    ("d3q27", "mrt", "periodic", []), ("d3q19", "trt", "cavity", []), ("d3q19", "bgk", "channel", []),
+    ("d3q27", "mrt", "periodic", ["--overlap"]),             # send-halo elements first, 2 streams
+    ("d3q19", "trt", "cavity", ["--octants", "2"]),          # the weak-scaling mesh of bench.py
+    ("d3q27", "mrt", "periodic", ["--p2p"]),                 # peer-memory halo exchange
+    ("d3q19", "trt", "cavity", ["--octants", "2", "--p2p"]),
+    ("d3q19", "bgk", "channel", ["--p2p", "--overlap"])],
+    ids=["mrt27-periodic", "trt19-cavity", "bgk19-channel", "mrt27-periodic-overlap", "trt19-cavity-2oct",
+         "mrt27-periodic-p2p", "trt19-cavity-2oct-p2p", "bgk19-channel-p2p-overlap"])
+def test_multi_gpu_matches_single_domain_oracle(layout, relax, kind, extra):
     n = _ngpu()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     nproc = 2 if n < 4 else 4
+    if "--octants" in extra:
+        nproc = 2
     r = _launch(nproc, ["--mode", "gpu", "--layout", layout, "--relaxation", relax, "--kind", kind,
-                        "--level", "5", "--steps", "40"], 29651)
+                        "--level", "5", "--steps", "40"] + extra, 29651)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert r.stdout.count("ndiff=0") == nproc
