@@ -60,6 +60,19 @@ def measured_peak():
     return 6650.0, "fallback"
 
 
+def measured_traffic(kernel, cells):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/r01_traffic.json); None when no capture matches this kernel and cell count."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(kernel)
+        if t and int(t["cells"]) == int(cells):
+            return {"value": float(t["traffic_gb"]), "unit": "GB per launch (ncu dram read+write)",
+                    "algorithmic_gb": None, "source": t["source"]}
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
 
@@ -309,6 +322,10 @@ def main():
     value = nFluid_total * K / (t_ms * 1e-3) / 1e6
     peak, peak_src = measured_peak()
     achieved = BYTES_PER_LUP[QQ] * float(ld.nFluid) / (sweep_ms * 1e-3) / 1e9   # per GPU, dominant kernel
+    kernel_name = "sweepKernel<%d,%s>" % (QQ, ident["relaxation"])
+    traffic = measured_traffic(kernel_name, ld.nFluid)
+    if traffic is not None:
+        traffic["algorithmic_gb"] = BYTES_PER_LUP[QQ] * float(ld.nFluid) / 1e9
 
     # ---------------- end to end through the C ABI with host buffers --------
     e2e = None
@@ -360,8 +377,8 @@ def main():
                        "l2": "state of %.2f GB per buffer per GPU >> 126 MB L2, no flush needed" % (nbytes / 1e9),
                        "aux_every_step": False, "setup_s": round(setup_s, 2)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "sweepKernel<%d,%s>" % (QQ, ident["relaxation"]),
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": kernel_name,
                          "bytes_per_lup": BYTES_PER_LUP[QQ], "kernel_ms": sweep_ms,
                          "share_of_step": sweep_ms / (t_ms / K)},
             "timers_ms_per_step": {"compute": cm.value / K, "bc": bm.value / K, "comm": com.value / K,

@@ -17,13 +17,18 @@
 
 namespace musb200 {
 
-// Launch shape: 128 threads per CTA.  D3Q19 needs 72-80 registers (6 CTAs/SM), D3Q27 up to 128
+// Launch shape: 128 threads per CTA.  D3Q19 is capped at 80 registers (__launch_bounds__(128, 6):
+// 6 CTAs = 24 warps per SM, at most 24 B of spills in the MRT variants); uncapped the compiler
+// takes 94-110 registers, only 16 warps fit and the TRT sweep of 256^3 drops from 0.961 ms
+// (1.01 of the measured HBM peak) to 1.079 ms (0.90).  D3Q27 needs up to 128 registers
 // (4 CTAs/SM, no spills).  A warp lives long here (26 index loads -> 27 gathers -> 800-1300 FP64
 // instructions -> 27 stores) and a CTA's registers are only released when its last warp retires,
-// so small CTAs keep more loads in flight: measured on B200 (profiles/r01_launch_shape.md)
+// so small CTAs keep more loads in flight.  Measured on B200 (profiles/r01_launch_shape.md):
+// D3Q19 TRT 256^3, 80 registers: 64 / 128 / 192 / 256 threads = 0.966 / 0.961 / 0.966 / 0.964 ms,
+// 94 registers (5 CTAs) 0.984 ms, 72 registers (7 CTAs, 52 B spills) 0.987 ms;
 // D3Q27 MRT 256^3: 256 threads 2.30 ms, 128 threads 1.55 ms, 64 threads 1.57 ms, 512 threads
-// 1.81 ms; D3Q19 TRT 256^3: 1.132 / 1.079 / 1.074 / 1.198 ms.  Capping D3Q27 at 96 or 80
-// registers (5-6 CTAs/SM) spills 270-570 B per thread and is slower (1.98 / 2.64 ms).
+// 1.81 ms.  Capping D3Q27 at 96 or 80 registers (5-6 CTAs/SM) spills 270-570 B per thread and
+// is slower (1.98 / 2.64 ms).
 #ifndef SWEEP27_THREADS
 #define SWEEP27_THREADS 128
 #endif
@@ -33,10 +38,13 @@ namespace musb200 {
 #ifndef SWEEP19_THREADS
 #define SWEEP19_THREADS 128
 #endif
+#ifndef SWEEP19_MINBLOCKS
+#define SWEEP19_MINBLOCKS 6
+#endif
 template <int QQ>
 constexpr int sweepThreads() { return QQ == 27 ? SWEEP27_THREADS : SWEEP19_THREADS; }
 template <int QQ>
-constexpr int sweepMinBlocks() { return QQ == 27 ? SWEEP27_MINBLOCKS : 1; }
+constexpr int sweepMinBlocks() { return QQ == 27 ? SWEEP27_MINBLOCKS : SWEEP19_MINBLOCKS; }
 
 template <int QQ, int RELAX, bool INCOMP>
 __global__ void __launch_bounds__(sweepThreads<QQ>(), sweepMinBlocks<QQ>()) sweepKernel(const SweepArgs a) {

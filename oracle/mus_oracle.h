@@ -134,6 +134,23 @@ void ora_fill_finer_ghosts_from_me(int order, int QQ, int incomp, const double *
                                    const double *matrices, const double *coord,
                                    const double *tVisc);
 
+/* ---- source terms and passive scalar (source.c) ------------------------ */
+/* force in lattice units, [nElems][3]; posInTotal = fun%elemLvl(iLevel)%posInTotal (1-based) */
+void ora_add_force_to_aux(double *aux, int incompressible, int nElems, const int32_t *posInTotal,
+                          const double *force);
+/* order 2: applySrc_force (bgk, trt) / applySrc_force_MRT_d3q19 / _d3q27; order 1:
+ * applySrc_force1stOrd.  omega = omLvl(iLevel)%val, indexed by posInTotal */
+int ora_apply_src_force(int relax, int QQ, int order, double *out, const double *aux,
+                        const double *omega, double omegaBulk, int nElems,
+                        const int32_t *posInTotal, const double *force);
+/* mus_calcAuxField_zerothMoment: aux(iElem) = sum of the pulled PDFs (nAuxScalars = 1) */
+void ora_calc_aux_zeroth(int QQ, double *aux, const double *state, const int32_t *neigh,
+                         int nSize, int nSolve);
+/* variant 1 bgk/first, 2 bgk/second, 3 trt (vStdNoOpt) */
+int ora_compute_passive_scalar(int variant, int QQ, const double *in, double *out,
+                               const int32_t *neigh, int nSize, int nSolve,
+                               const double *transVel, double diff_coeff, double lambda);
+
 /* ---- halo exchange (tem_comm_module.fpp:549-646) ------------------------ */
 void ora_comm_gather(double *buf, const double *state, const int32_t *pos, int n);
 void ora_comm_scatter(double *state, const double *buf, const int32_t *pos, int n);

@@ -63,6 +63,11 @@ def lib():
         _LIB.ora_weights.restype = _dp
         _LIB.ora_mrt_matrix.restype = _dp
         _LIB.ora_nEq_acoustic.argtypes = [ctypes.c_int, ctypes.c_double, _dp, _dp]
+        _LIB.ora_apply_src_force.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, _dp, _dp, _dp,
+                                             ctypes.c_double, ctypes.c_int, _ip, _dp]
+        _LIB.ora_compute_passive_scalar.argtypes = [ctypes.c_int, ctypes.c_int, _dp, _dp, _ip,
+                                                    ctypes.c_int, ctypes.c_int, _dp, ctypes.c_double,
+                                                    ctypes.c_double]
     return _LIB
 
 
@@ -449,6 +454,34 @@ class Scheme:
         self.bc_kind = {bc["id"]: bc["kind"] for bc in ld.bc}
         self.bcBuffer = np.zeros(max(1, ld.bc_elemBuffer.size) * self.QQ)
         self.exchange = None  # callable(state) for multi-rank runs
+        self.force = None     # (order, posInTotal int32 1-based, force [n][3] lattice units)
+
+    # -- source = { force = ... } (mus_source_module.f90:83-310: all nSolve elements whose
+    #    barycentre lies in the variable's shape; here: a list of positions or all of them)
+    def set_force(self, force, order=2, posInTotal=None):
+        ld = self.ld
+        pos = (np.arange(1, ld.nSolve + 1, dtype=np.int32) if posInTotal is None
+               else np.ascontiguousarray(posInTotal, dtype=np.int32))
+        F = np.ascontiguousarray(np.broadcast_to(np.asarray(force, dtype=np.float64), (pos.size, 3)))
+        if order not in (1, 2):
+            raise ValueError("force source: order must be 1 or 2")
+        self.force = (int(order), pos, F)
+
+    def add_src_to_aux(self):
+        """field%source%method%addSrcToAuxField (mus_auxField_module.f90:341-375)"""
+        if self.force is not None and self.force[0] == 2:
+            _, pos, F = self.force
+            lib().ora_add_force_to_aux(_d(self.aux), self.incomp, int(pos.size), _i(pos), _d(F))
+
+    def apply_source_terms(self):
+        """mus_apply_sourceTerms (mus_source_module.f90:430-512) on state(:, nNext)"""
+        if self.force is not None:
+            order, pos, F = self.force
+            rc = lib().ora_apply_src_force(self.relax, self.QQ, order, _d(self.state[self.nNext]),
+                                           _d(self.aux), _d(self.omega), self.rp.omegaBulk,
+                                           int(pos.size), _i(pos), _d(F))
+            if rc != 0:
+                raise RuntimeError("no oracle force source for this configuration")
 
     # -- initial condition: f = fEq(rho, u) (+ fNeq(S) = 0), mus_init_pdf -----
     def init_equilibrium(self, rho, vel):
@@ -537,6 +570,7 @@ class Scheme:
         self.set_boundary()                                     # 3 (on state(:,nNext))
         self.nNow, self.nNext = self.nNext, self.nNow           # 4 mus_swap_now_next
         self.calc_aux(self.state[self.nNow])                    # 5
+        self.add_src_to_aux()                                   # 5 (source -> auxField)
         L.ora_update_omega(_d(self.omega), _d(self.visc), self.ld.nSolve)   # 6
         rc = L.ora_compute(self.relax, self.QQ, self.incomp, _d(self.state[self.nNow]),
                            _d(self.state[self.nNext]), _d(self.aux), _i(self.ld.neigh),
@@ -544,6 +578,7 @@ class Scheme:
                            ctypes.byref(self.rp))               # 7
         if rc != 0:
             raise RuntimeError("no oracle kernel for this (relaxation, layout, kind)")
+        self.apply_source_terms()                               # 8
         if self.exchange is not None:
             self.exchange(self)                                 # 9 exchange_real(state(:,next))
 
@@ -654,6 +689,7 @@ class MultiLevelScheme:
         s.set_boundary()
         s.nNow, s.nNext = s.nNext, s.nNow
         s.calc_aux(s.state[s.nNow])
+        s.add_src_to_aux()
         if l < self.maxLevel:
             self._aux_from_finer(l)
         L.ora_update_omega(_d(s.omega), _d(s.visc), s.ld.nSolve)
@@ -661,6 +697,7 @@ class MultiLevelScheme:
                            _i(s.ld.neigh), _d(s.omega), s.ld.nSize, s.ld.nSolve, ctypes.byref(s.rp))
         if rc != 0:
             raise RuntimeError("no oracle kernel for this (relaxation, layout, kind)")
+        s.apply_source_terms()
         if l < self.maxLevel:
             self._from_finer(l)
             self._from_coarser(l)

@@ -1,0 +1,15 @@
+#!/bin/bash
+# one-GPU verification pass: GPU parity suite, smoke, default bench, D3Q27 bench, ncu launch list + full capture
+mkdir -p gpurun_out
+( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
+( time timeout 600 python bench.py ) > gpurun_out/bench_n1.log 2>&1
+( time timeout 300 python bench.py --impl reference --steps 10 --warmup 3 ) > gpurun_out/bench_ref.log 2>&1
+timeout 300 python bench.py --workload cfg3-256 --steps 200 --no-cpu-baseline --no-e2e > gpurun_out/bench_cfg3_256.log 2>&1
+timeout 300 python bench.py --workload cfg1 --steps 2000 --no-cpu-baseline --no-e2e > gpurun_out/bench_cfg1.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_cfg2.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_list.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:sweepKernel -s 4 -c 2 -f -o gpurun_out/prof_sweep_mrt27 python bench.py --workload cfg3-256 --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_mrt27.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:sweepKernel -s 4 -c 2 -f -o gpurun_out/prof_sweep_trt19 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_trt19.log 2>&1
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/smi.log
+tail -3 gpurun_out/pytest_gpu.log; tail -1 gpurun_out/bench_n1.log | cut -c1-600
