@@ -3,7 +3,7 @@
 GPU) with the HBM roofline and the reference's CPU algorithm timed beside it.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl musb200|reference]
-                  [--workload cfg1|cfg2|cfg3|cfg3-256] [--level L]
+                  [--workload cfg1|cfg2|cfg3|cfg3-256|cfg4] [--level L]
 
 Workloads (BASELINE.json configs):
   N = 1 : cfg2  D3Q19 TRT lid-driven cavity 256^3 (level 8), bounce-back walls +
@@ -12,6 +12,8 @@ Workloads (BASELINE.json configs):
                 level-9 cube (512x256x256, 512x512x256, 512^3 -- the "512^3-equivalent mesh" of
                 north_star at 8 GPUs), SFC-partitioned into N equal Morton ranges, halo exchange
                 through peer memory over NVLink (NCCL send/recv with --no-p2p)
+  --workload cfg4 : BASELINE config 4, two-level octree with linear ghost interpolation on one
+                GPU; a step is one coarse cycle (1 coarse + 2 fine level steps)
   --workload cfg3 : D3Q27 MRT periodic 512^3 (level 9) strong-scaled over N ranks (BASELINE
                 config 3; also cfg3-256 on one GPU)
 A "step" is one level time step (set_boundary, swap, fused aux+stream+collide,
@@ -45,6 +47,10 @@ WORKLOADS = {
                  kind="cavity", omega=1.7, name="D3Q19 TRT lid-driven cavity 256^3, bounce-back walls"),
     "cfg3": dict(ident={"kind": "fluid", "relaxation": "mrt", "layout": "d3q27"}, level=9,
                  kind="periodic", omega=1.9, name="D3Q27 MRT periodic channel 512^3"),
+    "cfg4": dict(ident={"kind": "fluid", "relaxation": "bgk", "layout": "d3q19"}, level=7,
+                 kind="multilevel", omega=1.7, boxes=[(32, 96)], cylinder=(128.0, 128.0, 16.0, 72, 184),
+                 name="two-level octree: level-7 periodic cube, 64^3 coarse cells refined to level 8 "
+                      "around a solid cylinder, D3Q19 BGK, linear ghost interpolation"),
     "cfg3-256": dict(ident={"kind": "fluid", "relaxation": "mrt", "layout": "d3q27"}, level=8,
                      kind="periodic", omega=1.9, name="D3Q27 MRT periodic channel 256^3"),
 }
@@ -178,6 +184,109 @@ def run_reference(args, wl_name, wl):
 
 
 # ---------------------------------------------------------------------------
+def run_multilevel(args, wl_name, wl):
+    """cfg4 on one GPU: K coarse cycles of do_recursive_multiLevel, device timed."""
+    import musubi_b200 as mb
+    from musubi_b200 import treelm_multilevel as tm
+    from musubi_b200._lib import check, lib
+    W, K = max(3, args.warmup), max(1, args.steps)
+    mb.mus_init(0, 1, int(os.environ.get("LOCAL_RANK", "0")))
+    t_setup = time.perf_counter()
+    minL = args.level or wl["level"]
+    scale = 2 ** (minL - wl["level"])
+    boxes = [(int(lo * scale), int(hi * scale)) for lo, hi in wl["boxes"]]
+    cyl = tuple(c * scale for c in wl["cylinder"][:3]) + tuple(int(c * scale) for c in wl["cylinder"][3:])
+    lv, intp = tm.build_multilevel(minL, boxes, QQ=19, cylinder=cyl, intp_method="linear")
+    tables = mb.multilevel_tables(lv, intp)
+    levels = sorted(lv)
+    nu0 = (1.0 / wl["omega"] - 0.5) / 3.0
+    visc = {l: nu0 * 2.0 ** (l - levels[0]) for l in levels}       # acoustic scaling
+    omega = {l: 1.0 / (3.0 * visc[l] + 0.5) for l in levels}
+    sch = mb.Scheme(wl["ident"], lv, omega, intp=(tables, intp["order"]), viscosity=visc)
+    host, nbytes = {}, 0
+    for l in levels:
+        L = lv[l]
+        x = 2.0 * math.pi * L.bary_unit
+        u0 = 0.03
+        vel = np.stack([u0 * np.sin(x[:, 0]) * np.cos(x[:, 1]) * np.cos(x[:, 2]) + 0.02,
+                        -u0 * np.cos(x[:, 0]) * np.sin(x[:, 1]) * np.cos(x[:, 2]),
+                        np.zeros(L.nElems)], axis=1)
+        from musubi_b200 import cases
+        host[l] = cases.equilibrium_state(19, np.ones(L.nElems), vel, L.nSize)
+        nbytes += host[l].nbytes
+        sch.upload_state(l, host[l])
+        aux = np.zeros(L.nSize * 4)
+        aux[:L.nElems * 4] = np.concatenate([np.ones((L.nElems, 1)), vel], axis=1).ravel()
+        check(lib.musb200_aux_upload(l, aux.ctypes.data))
+    sch.synchronize()
+    setup_s = time.perf_counter() - t_setup
+    upd = {l: 2 ** (l - levels[0]) for l in levels}                # level steps per coarse cycle
+    lups_cycle = sum(lv[l].nFluid * upd[l] for l in levels)
+    solve_cycle = sum((lv[l].nFluid + lv[l].nGhostFromCoarser) * upd[l] for l in levels)
+
+    sch.do_computation(W)
+    sch.synchronize()
+    check(lib.musb200_set_profiling(1))
+    check(lib.musb200_timers_reset())
+    sampler = ClockSampler(0)
+    sampler.start()
+    check(lib.musb200_event_mark(0))
+    sch.do_computation(K)
+    check(lib.musb200_event_mark(1))
+    sch.synchronize()
+    ms = ctypes.c_double()
+    check(lib.musb200_event_elapsed(ctypes.byref(ms)))
+    clocks = sampler.finish()
+    cm, bm, com, im = (ctypes.c_double() for _ in range(4))
+    check(lib.musb200_timers(ctypes.byref(cm), ctypes.byref(bm), ctypes.byref(com), ctypes.byref(im)))
+    nl = ctypes.c_longlong()
+    check(lib.musb200_launch_count(ctypes.byref(nl)))
+    check(lib.musb200_set_profiling(0))
+    value = lups_cycle * K / (ms.value * 1e-3) / 1e6
+    sweep_ms = cm.value / K
+    peak, peak_src = measured_peak()
+    achieved = BYTES_PER_LUP[19] * float(solve_cycle) / (sweep_ms * 1e-3) / 1e9
+    mass = sum(sch.reduce(l)[0] / 8.0 ** (l - levels[0]) for l in levels)
+
+    e2e = None
+    if not args.no_e2e:
+        t0 = time.perf_counter()
+        for l in levels:
+            sch.upload_state(l, host[l])
+        sch.do_computation(K)
+        for l in levels:
+            host[l] = sch.download_state(l)
+        sch.synchronize()
+        dt = time.perf_counter() - t0
+        e2e = {"value": lups_cycle * K / dt / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": int(2 * nbytes / K),
+               "d2h_bytes_per_step": int(nbytes / K), "steps": K, "wall_s": dt,
+               "protocol": "state upload of every level (pageable host arrays) + K coarse cycles + state download"}
+    line = {
+        "metric": "MLUPS", "value": value, "unit": "MLUPS", "n_gpus": 1, "steps": K, "warmup": W,
+        "ms_per_step": ms.value / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl_name + ": " + wl["name"], "levels": levels,
+                   "cells": {str(l): int(lv[l].nFluid) for l in levels},
+                   "ghostFromCoarser": {str(l): int(lv[l].nGhostFromCoarser) for l in levels},
+                   "ghostFromFiner": {str(l): int(lv[l].nGhostFromFiner) for l in levels},
+                   "step": "one coarse cycle = %s level steps" % "+".join(str(upd[l]) for l in levels),
+                   "mlups_definition": "sum_l nFluid(l) * 2^(l-minLevel) per coarse cycle / time (SURVEY 8d)",
+                   "interpolation": "linear", "omega": {str(l): omega[l] for l in levels},
+                   "l2": "state %.2f GB > 126 MB L2" % (2 * nbytes / 1e9), "setup_s": round(setup_s, 2)},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "sweepKernel<19,bgk> (all level steps of a cycle)",
+                     "bytes_per_lup": BYTES_PER_LUP[19], "kernel_ms": sweep_ms,
+                     "share_of_step": sweep_ms / (ms.value / K)},
+        "timers_ms_per_step": {"compute": cm.value / K, "bc": bm.value / K, "comm": com.value / K,
+                               "intp": im.value / K},
+        "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(nl.value), "clocks": clocks,
+        "check": {"total_mass": mass},
+    }
+    print(json.dumps(line), flush=True)
+    sch.destroy()
+    mb.mus_finalize()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -209,7 +318,14 @@ def main():
         wl["level"] = args.level
     weak = (wl_name == "cfg2")
     if args.impl == "reference":
+        if wl["kind"] == "multilevel":
+            raise SystemExit("--impl reference times the single-level workloads")
         run_reference(args, wl_name, wl)
+        return
+    if wl["kind"] == "multilevel":
+        if world > 1:
+            raise SystemExit("cfg4 runs on one GPU (the multi-level mesh generator is single-rank)")
+        run_multilevel(args, wl_name, wl)
         return
     W = max(3, args.warmup)
     K = max(1, args.steps)

@@ -47,6 +47,7 @@ extern "C" {
 #define MUSB200_RELAX_MRT 2
 #define MUSB200_KIND_FLUID 0
 #define MUSB200_KIND_FLUID_INCOMPRESSIBLE 1
+#define MUSB200_KIND_PASSIVE_SCALAR 2
 
 /* boundary kinds: field%bc(i)%BC_kind (mus/source/bc/mus_bc_header_module.fpp) */
 #define MUSB200_BC_WALL                 0  /* do_nothing, mus_bc_fluid_wall_module.fpp:407-450 */
@@ -124,6 +125,35 @@ int musb200_set_relaxation(int level, int relax_id, int kind_id, const double *o
  * value); read by the ghost interpolation for the non-equilibrium rescaling
  * (mus_interpolate_average_module.fpp:328-337, mus_interpolate_linear_module.fpp:471-480) */
 int musb200_set_viscosity(int level, const double *visc, double visc_uniform);
+
+/* ---- source terms: field%source / globSrc with varname 'force' ------------
+ * mus_source_module.f90:83-310 (element lists), :430-512 (mus_apply_sourceTerms);
+ * order 2 (default): mus_addForceToAuxField_fluid / _fluidIncomp
+ * (mus_auxFieldVar_module.fpp:1032-1214) + applySrc_force | applySrc_force_MRT_d3q19 |
+ * applySrc_force_MRT_d3q27 (mus_derQuan_module.fpp:3129-3862, chosen by relaxation and layout
+ * as mus_variable_module.f90:1043-1081 does); order 1: applySrc_force1stOrd (:4043-4143).
+ * posInTotal  fun%elemLvl(level)%posInTotal(1:nElems)  (NULL: elements 1..nElems_solve)
+ * force       forceField / fac%body_force: LATTICE units, 3 per element as the Fortran array
+ *             holds them, or 3 values when uniform != 0
+ * Both halves are fused into the sweep; a time-dependent force is handed over again before
+ * the step it applies to.  order = 0 or nElems = 0 removes the source.                        */
+int musb200_source_force(int level, int order, int nElems, const int32_t *posInTotal,
+                         const double *force, int uniform);
+
+/* ---- passive scalar (scheme kind 'passive_scalar', nAuxScalars = 1) --------
+ * mus_init_advRel_lbm_ps (init/mus_initLBMPS_module.f90:59-160): relaxation bgk with variant
+ * 1 = 'first' | 2 = 'second' (mus_compute_passiveScalar_module.fpp:77-279), trt = vStdNoOpt
+ * (:293-398); diff_coeff = species%diff_coeff(1), lambda = species%lambda.                   */
+int musb200_set_species(int level, int relax_id, int variant, double diff_coeff, double lambda);
+/* scheme%transVar%method(1): transport velocity in LATTICE units (transVel * 1/fac%vel), one
+ * triple per element 1..nElems_solve as get_valOfIndex returns them, or 3 values (uniform)   */
+int musb200_set_transport_velocity(int level, int nElems, const double *vel, int uniform);
+/* Several schemes on one mesh: every call addresses the levels of the bound slot (default 0).
+ * musb200_couple_transport_velocity lets the passive scalar of the bound slot read its
+ * transport velocity from the auxField of the flow scheme in `flow_slot` on the device
+ * (the flow must have been stepped with auxField materialised: musb200_set_aux_every_step). */
+int musb200_scheme_bind(int slot);
+int musb200_couple_transport_velocity(int level, int flow_slot, int flow_level);
 
 /* ---- boundaries: boundary_type + glob_boundary_type per level -------------
  * links      me%links(level)%val            (mus_bc_header_module.fpp:1702-1739)

@@ -43,6 +43,11 @@ SIGNATURES = {
     "musb200_state_copy_next_to_now": [c_int],
     "musb200_set_relaxation": [c_int, c_int, c_int, P_DBL, c_double, c_double, c_double],
     "musb200_set_viscosity": [c_int, P_DBL, c_double],
+    "musb200_source_force": [c_int, c_int, c_int, P_I32, P_DBL, c_int],
+    "musb200_set_species": [c_int, c_int, c_int, c_double, c_double],
+    "musb200_set_transport_velocity": [c_int, c_int, P_DBL, c_int],
+    "musb200_scheme_bind": [c_int],
+    "musb200_couple_transport_velocity": [c_int, c_int, c_int],
     "musb200_bc_elembuffer": [c_int, c_int, P_I32],
     "musb200_bc_register": [c_int, c_int, c_int, c_int, P_I32, P_I32, P_I32, P_I32],
     "musb200_bc_set_values": [c_int, c_int, c_int, c_void_p],

@@ -166,6 +166,20 @@ struct Level {
   DevBuf<int32_t> sendElems;   // 0-based, ascending
   DevBuf<uint32_t> sendMask;   // 1 bit per element
   int nSendElems = 0;
+  // source = { force }: order 0 (none) / 1 / 2, uniform or per-element SoA [3][S]
+  int forceOrder = 0;
+  bool forceElem = false;
+  double forceUniform[3] = {0, 0, 0};
+  DevBuf<double> force;
+  // passive scalar: kernel variant (1 bgk/first, 2 bgk/second, 3 trt), species parameters,
+  // transport velocity (uniform / own array / auxField rows of a flow scheme)
+  int nAux = 4;
+  int psVariant = 0;
+  double psDOmega = 0.0, psAuxOmega = 0.0;
+  int velMode = 0;             // 0 uniform, 1 own array, 2 coupled to (slot, level)
+  double velUniform[3] = {0, 0, 0};
+  DevBuf<double> vel;
+  int velSlot = 0, velLevel = 0;
   IntpSet fromFiner;                 // fill my ghostFromFiner from level+1
   std::vector<IntpSet> fromCoarser;  // fill my ghostFromCoarser from level-1, per order
 };
@@ -179,7 +193,12 @@ struct Context {
   int overlap = 0;   // measured slower than exchange-after-compute at 256^3 per GPU (profiles/)
   NcclApi *nccl = nullptr;
   ncclComm_t comm = nullptr;
-  std::map<int, std::unique_ptr<Level>> levels;
+  // one element list per (scheme slot, level); slot 0 is the default scheme, further slots hold
+  // schemes living on the same mesh (a passive scalar transported by the flow of slot 0)
+  static constexpr int kSlots = 4;
+  int slot = 0;
+  std::map<int, std::unique_ptr<Level>> levelsOf[kSlots];
+  std::map<int, std::unique_ptr<Level>> &levels() { return levelsOf[slot]; }
   DevBuf<double> stage;  // AOS staging for up/download
   DevBuf<double> red;    // reduction scratch + result
   DevBuf<int> flag;
@@ -200,8 +219,8 @@ static int needReady() {
   return 0;
 }
 static Level *findLevel(int level) {
-  auto it = g.levels.find(level);
-  return it == g.levels.end() ? nullptr : it->second.get();
+  auto it = g.levels().find(level);
+  return it == g.levels().end() ? nullptr : it->second.get();
 }
 #define GET_LEVEL(L, level)                                                          \
   MUSB_TRY(needReady());                                                             \
@@ -341,6 +360,25 @@ enum { SWEEP_ALL = 0, SWEEP_SENDHALO = 1, SWEEP_INTERIOR = 2 };
 static int sweep(Level &L, bool writeAux, int part = SWEEP_ALL) {
   if (!L.relaxSet) return setError(MUSB200_ERR_STATE, "musb200_set_relaxation missing");
   Timed t(T_COMPUTE);
+  if (L.kind == MUSB200_KIND_PASSIVE_SCALAR) {
+    if (part != SWEEP_ALL) return setError(MUSB200_ERR_UNSUPPORTED, "passive scalar: no split sweep");
+    PsArgs p{};
+    p.in = L.state[L.nNow].p; p.out = L.state[L.nNext].p; p.nbr = L.nbr.p; p.aux = L.aux.p;
+    p.S = L.S; p.count = L.nSolve; p.write_aux = writeAux ? 1 : 0;
+    p.d_omega = L.psDOmega; p.aux_omega = L.psAuxOmega;
+    for (int k = 0; k < 3; ++k) p.vel_uniform[k] = L.velUniform[k];
+    if (L.velMode == 1) { p.vel = L.vel.p; p.velS = L.S; }
+    if (L.velMode == 2) {
+      auto it = g.levelsOf[L.velSlot].find(L.velLevel);
+      if (it == g.levelsOf[L.velSlot].end())
+        return setError(MUSB200_ERR_STATE, "passive scalar: the coupled flow level no longer exists");
+      p.vel = it->second->aux.p + it->second->S;   // rows ux, uy, uz of the flow's auxField
+      p.velS = it->second->S;
+    }
+    MUSB_TRY(launchPassiveScalar(L.QQ, L.psVariant, p, g.stream));
+    ++g.launches;
+    return 0;
+  }
   SweepArgs a{};
   a.in = L.state[L.nNow].p;
   a.out = L.state[L.nNext].p;
@@ -354,6 +392,9 @@ static int sweep(Level &L, bool writeAux, int part = SWEEP_ALL) {
   a.count = L.nSolve;
   a.write_aux = writeAux ? 1 : 0;
   a.rp = L.rp;
+  a.force_order = L.forceOrder;
+  a.force = L.forceElem ? L.force.p : nullptr;
+  for (int k = 0; k < 3; ++k) a.force_uniform[k] = L.forceUniform[k];
   if (part == SWEEP_SENDHALO) { a.list = L.sendElems.p; a.count = L.nSendElems; }
   if (part == SWEEP_INTERIOR) a.skip = L.sendMask.p;
   MUSB_TRY(launchSweep(L.QQ, L.relax, L.kind, a, g.stream));
@@ -523,7 +564,8 @@ int musb200_init(int rank, int nranks, int local_device, const void *nccl_unique
 int musb200_finalize(void) {
   if (!g.ready) return 0;
   cudaStreamSynchronize(g.stream);
-  g.levels.clear();
+  for (auto &m : g.levelsOf) m.clear();
+  g.slot = 0;
   g.stage.release(); g.red.release(); g.flag.release();
   for (auto &s : g.spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
   g.spans.clear();
@@ -550,6 +592,7 @@ int musb200_scheme_select(const char *kind, const char *relaxation, const char *
   int kk, rr, qq;
   if (k == "fluid") kk = MUSB200_KIND_FLUID;
   else if (k == "fluid_incompressible") kk = MUSB200_KIND_FLUID_INCOMPRESSIBLE;
+  else if (k == "passive_scalar") kk = MUSB200_KIND_PASSIVE_SCALAR;
   else return setError(MUSB200_ERR_UNSUPPORTED, "scheme kind '" + k + "' is outside the B200 hot path");
   if (l == "d3q19") qq = 19;
   else if (l == "d3q27") qq = 27;
@@ -558,6 +601,18 @@ int musb200_scheme_select(const char *kind, const char *relaxation, const char *
   else if (r == "trt") rr = MUSB200_RELAX_TRT;
   else if (r == "mrt") rr = MUSB200_RELAX_MRT;
   else return setError(MUSB200_ERR_UNSUPPORTED, "relaxation '" + r + "' is outside the B200 hot path");
+  if (kk == MUSB200_KIND_PASSIVE_SCALAR) {
+    // mus_init_advRel_lbm_ps (init/mus_initLBMPS_module.f90:59-160): bgk first|second for any
+    // layout, trt without a named variant = vStdNoOpt; the E/L-model variants and mrt are d3q19
+    // special kernels outside the hot path
+    const bool ok = (rr == MUSB200_RELAX_BGK && (v == "first" || v == "second")) ||
+                    (rr == MUSB200_RELAX_TRT && v != "Emodel" && v != "EmodelCorr" && v != "Lmodel");
+    if (!ok)
+      return setError(MUSB200_ERR_UNSUPPORTED, "passive_scalar: relaxation '" + r + "' variant '" + v +
+                                                   "' is outside the B200 hot path");
+    *relax_id = rr; *kind_id = kk; *QQ = qq;
+    return 0;
+  }
   if (v != "standard" && v != "b200")
     return setError(MUSB200_ERR_UNSUPPORTED, "relaxation variant '" + v + "' is outside the B200 hot path");
   // mus_init_advRel_fluid_incompressible aborts for trt with a layout other than d3q19
@@ -577,7 +632,8 @@ int musb200_level_create(int level, int QQ, int nScalars, int nAuxScalars, int n
   MUSB_TRY(needReady());
   if (QQ != 19 && QQ != 27) return setError(MUSB200_ERR_UNSUPPORTED, "only d3q19 / d3q27");
   if (nScalars != QQ) return setError(MUSB200_ERR_UNSUPPORTED, "multi-field schemes (nScalars != QQ)");
-  if (nAuxScalars != 4) return setError(MUSB200_ERR_UNSUPPORTED, "nAuxScalars must be 4 (rho, u)");
+  if (nAuxScalars != 4 && nAuxScalars != 1)
+    return setError(MUSB200_ERR_UNSUPPORTED, "nAuxScalars must be 4 (rho, u) or 1 (passive scalar)");
   const long long nElems = (long long)nFluid + nGhostFromCoarser + nGhostFromFiner + nHalo;
   if (nSize < nElems || nSize <= 0 || !neigh) return setError(MUSB200_ERR_ARG, "bad sizes / null neigh");
   if ((long long)nSize > (long long)kElemMask) return setError(MUSB200_ERR_ARG, "nSize exceeds 2^31-1");
@@ -587,6 +643,7 @@ int musb200_level_create(int level, int QQ, int nScalars, int nAuxScalars, int n
   L->level = level; L->QQ = QQ; L->nSize = nSize; L->nFluid = nFluid;
   L->nGFC = nGhostFromCoarser; L->nGFF = nGhostFromFiner; L->nHalo = nHalo;
   L->nElems = (int)nElems;
+  L->nAux = nAuxScalars;
   L->nSolve = nFluid + nGhostFromCoarser;  // mus_pdf_module.f90:125
   L->S = ((long long)nSize + 31) / 32 * 32;
   for (int b = 0; b < 2; ++b) {
@@ -608,14 +665,14 @@ int musb200_level_create(int level, int QQ, int nScalars, int nAuxScalars, int n
   if (bad)
     return setError(MUSB200_ERR_CONNECTIVITY,
                     std::to_string(bad) + " neigh entries are neither a plain pull nor a bounce-back");
-  g.levels[level] = std::move(L);
+  g.levels()[level] = std::move(L);
   return 0;
 }
 
 int musb200_level_destroy(int level) {
   MUSB_TRY(needReady());
   cudaStreamSynchronize(g.stream);
-  g.levels.erase(level);
+  g.levels().erase(level);
   return 0;
 }
 
@@ -662,18 +719,18 @@ int musb200_state_download(int level, int which, double *aos_state) {
 int musb200_aux_upload(int level, const double *aos_aux) {
   GET_LEVEL(L, level);
   if (!aos_aux) return setError(MUSB200_ERR_ARG, "null argument");
-  return uploadAos(L, aos_aux, L->aux.p, 4);
+  return uploadAos(L, aos_aux, L->aux.p, L->nAux);
 }
 int musb200_aux_download(int level, double *aos_aux) {
   GET_LEVEL(L, level);
   if (!aos_aux) return setError(MUSB200_ERR_ARG, "null argument");
-  return downloadAos(L, L->aux.p, aos_aux, 4);
+  return downloadAos(L, L->aux.p, aos_aux, L->nAux);
 }
 int musb200_aux_probe(int level, int elemPos, double *out) {
   GET_LEVEL(L, level);
   if (!out || elemPos < 1 || elemPos > L->nElems) return setError(MUSB200_ERR_ARG, "bad probe element");
   MUSB_CUDA(cudaMemcpy2DAsync(out, sizeof(double), L->aux.p + (elemPos - 1), (size_t)L->S * sizeof(double),
-                              sizeof(double), 4, cudaMemcpyDeviceToHost, g.stream));
+                              sizeof(double), (size_t)L->nAux, cudaMemcpyDeviceToHost, g.stream));
   MUSB_CUDA(cudaStreamSynchronize(g.stream));
   return 0;
 }
@@ -701,7 +758,8 @@ int musb200_set_relaxation(int level, int relax_id, int kind_id, const double *o
                            double omega_uniform, double lambda, double omega_bulk) {
   GET_LEVEL(L, level);
   if (relax_id < 0 || relax_id > 2 || kind_id < 0 || kind_id > 1)
-    return setError(MUSB200_ERR_ARG, "bad relaxation / kind id");
+    return setError(MUSB200_ERR_ARG, "bad relaxation / kind id (passive scalar: musb200_set_species)");
+  if (L->nAux != 4) return setError(MUSB200_ERR_ARG, "a fluid scheme needs nAuxScalars = 4");
   if (kind_id == MUSB200_KIND_FLUID_INCOMPRESSIBLE && relax_id == MUSB200_RELAX_TRT && L->QQ != 19)
     return setError(MUSB200_ERR_UNSUPPORTED, "fluid_incompressible: the reference has no trt kernel for d3q27");
   L->relax = relax_id; L->kind = kind_id;
@@ -713,6 +771,109 @@ int musb200_set_relaxation(int level, int relax_id, int kind_id, const double *o
                               cudaMemcpyHostToDevice, g.stream));
   }
   L->relaxSet = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+int musb200_scheme_bind(int slot) {
+  MUSB_TRY(needReady());
+  if (slot < 0 || slot >= Context::kSlots) return setError(MUSB200_ERR_ARG, "scheme slot out of range");
+  g.slot = slot;
+  return 0;
+}
+
+int musb200_source_force(int level, int order, int nElems, const int32_t *posInTotal,
+                         const double *force, int uniform) {
+  GET_LEVEL(L, level);
+  if (order == 0 || nElems == 0) { L->forceOrder = 0; return 0; }
+  if ((order != 1 && order != 2) || nElems < 0 || !force) return setError(MUSB200_ERR_ARG, "bad force source");
+  if (L->kind == MUSB200_KIND_PASSIVE_SCALAR)
+    return setError(MUSB200_ERR_UNSUPPORTED, "force source on a passive-scalar scheme");
+  if (nElems > L->nSolve) return setError(MUSB200_ERR_ARG, "force source: more elements than nElems_solve");
+  if (uniform && !posInTotal && nElems == L->nSolve) {
+    // the common case (global shape, constant force): no array, no extra traffic
+    for (int k = 0; k < 3; ++k) L->forceUniform[k] = force[k];
+    L->forceElem = false;
+    L->forceOrder = order;
+    return 0;
+  }
+  if (!posInTotal && nElems != L->nSolve)
+    return setError(MUSB200_ERR_ARG, "force source: posInTotal missing for a partial element list");
+  // dense SoA field, zero outside the source's elements (adding a zero force changes nothing)
+  if (L->force.n < (size_t)L->S * 3) MUSB_TRY(L->force.alloc((size_t)L->S * 3));
+  MUSB_CUDA(cudaMemsetAsync(L->force.p, 0, (size_t)L->S * 3 * sizeof(double), g.stream));
+  std::vector<double> rep;
+  const double *src = force;
+  if (uniform) {
+    rep.resize((size_t)nElems * 3);
+    for (int i = 0; i < nElems; ++i)
+      for (int k = 0; k < 3; ++k) rep[(size_t)i * 3 + k] = force[k];
+    src = rep.data();
+  }
+  MUSB_TRY(stageBuf((size_t)nElems * 3));
+  MUSB_CUDA(cudaMemcpyAsync(g.stage.p, src, (size_t)nElems * 3 * sizeof(double), cudaMemcpyHostToDevice,
+                            g.stream));
+  DevBuf<int32_t> pos;
+  if (posInTotal) {
+    for (int i = 0; i < nElems; ++i)
+      if (posInTotal[i] < 1 || posInTotal[i] > L->nSolve)
+        return setError(MUSB200_ERR_ARG, "force source: posInTotal outside 1..nElems_solve");
+    MUSB_TRY(pos.upload(posInTotal, (size_t)nElems, g.stream));
+  }
+  MUSB_TRY(launchScatterRows(g.stage.p, posInTotal ? pos.p : nullptr, nElems, 3, L->force.p, L->S, g.stream));
+  MUSB_CUDA(cudaStreamSynchronize(g.stream));   // rep / pos are released on return
+  L->forceElem = true;
+  L->forceOrder = order;
+  return 0;
+}
+
+int musb200_set_species(int level, int relax_id, int variant, double diff_coeff, double lambda) {
+  GET_LEVEL(L, level);
+  if (L->nAux != 1) return setError(MUSB200_ERR_ARG, "passive scalar needs nAuxScalars = 1");
+  int v;
+  if (relax_id == MUSB200_RELAX_BGK && (variant == 1 || variant == 2)) v = variant;
+  else if (relax_id == MUSB200_RELAX_TRT) v = 3;
+  else return setError(MUSB200_ERR_UNSUPPORTED, "passive_scalar: bgk first|second or trt");
+  L->kind = MUSB200_KIND_PASSIVE_SCALAR;
+  L->relax = relax_id;
+  L->psVariant = v;
+  L->psDOmega = 2.0 / (1.0 + 6.0 * diff_coeff);
+  L->psAuxOmega = 1.0 / (lambda / (1.0 / L->psDOmega - 0.5) + 0.5);
+  L->relaxSet = true;
+  return 0;
+}
+
+int musb200_set_transport_velocity(int level, int nElems, const double *vel, int uniform) {
+  GET_LEVEL(L, level);
+  if (!vel) return setError(MUSB200_ERR_ARG, "null argument");
+  if (uniform) {
+    for (int k = 0; k < 3; ++k) L->velUniform[k] = vel[k];
+    L->velMode = 0;
+    return 0;
+  }
+  if (nElems != L->nSolve) return setError(MUSB200_ERR_ARG, "transport velocity: one triple per solved element");
+  if (L->vel.n < (size_t)L->S * 3) {
+    MUSB_TRY(L->vel.alloc((size_t)L->S * 3));
+    MUSB_CUDA(cudaMemsetAsync(L->vel.p, 0, (size_t)L->S * 3 * sizeof(double), g.stream));
+  }
+  MUSB_TRY(stageBuf((size_t)nElems * 3));
+  MUSB_CUDA(cudaMemcpyAsync(g.stage.p, vel, (size_t)nElems * 3 * sizeof(double), cudaMemcpyHostToDevice,
+                            g.stream));
+  MUSB_TRY(launchAosToSoa(g.stage.p, L->vel.p, 3, nElems, L->S, g.stream));
+  MUSB_CUDA(cudaStreamSynchronize(g.stream));   // vel is borrowed for the call only
+  L->velMode = 1;
+  return 0;
+}
+
+int musb200_couple_transport_velocity(int level, int flow_slot, int flow_level) {
+  GET_LEVEL(L, level);
+  if (flow_slot < 0 || flow_slot >= Context::kSlots || flow_slot == g.slot)
+    return setError(MUSB200_ERR_ARG, "coupling: flow scheme slot out of range / same as the scalar's");
+  auto it = g.levelsOf[flow_slot].find(flow_level);
+  if (it == g.levelsOf[flow_slot].end()) return setError(MUSB200_ERR_ARG, "coupling: unknown flow level");
+  if (it->second->nAux != 4 || it->second->nSolve < L->nSolve)
+    return setError(MUSB200_ERR_ARG, "coupling: the flow level must hold rho,u for the same element list");
+  L->velMode = 2; L->velSlot = flow_slot; L->velLevel = flow_level;
   return 0;
 }
 

@@ -1,6 +1,7 @@
 // kernels.cuh -- launch interface of the device kernels (implemented in *.cu)
 #pragma once
 #include "collide.cuh"
+#include "mrt_tables.cuh"
 
 namespace musb200 {
 
@@ -19,9 +20,34 @@ struct SweepArgs {
   int count;               // number of elements (range) or list entries
   int write_aux;
   RelaxParams rp;
+  // body-force source (0 = none): per-element SoA [3][S] in lattice units, or uniform
+  int force_order;
+  const double *force;
+  double force_uniform[3];
 };
 
 int launchSweep(int QQ, int relax, int kind, const SweepArgs &a, cudaStream_t st);
+
+// passive scalar (passive_scalar.cu)
+struct PsArgs {
+  const double *in;
+  double *out;
+  const uint32_t *nbr;
+  double *aux;             // [1][S] zeroth moment (written when write_aux)
+  long long S;
+  int count;               // nElems_solve
+  int write_aux;
+  const double *vel;       // transport velocity rows [3][velS] or nullptr (uniform)
+  long long velS;
+  double vel_uniform[3];
+  double d_omega;          // 2 / (1 + 6 diff_coeff)
+  double aux_omega;        // trt: 1 / (lambda / (1/d_omega - 1/2) + 1/2)
+};
+// variant: 1 bgk/first, 2 bgk/second, 3 trt (vStdNoOpt)
+int launchPassiveScalar(int QQ, int variant, const PsArgs &a, cudaStream_t st);
+// SoA rows [nComp][S] <- AOS list entries: dst[k*S + pos[i]-1] = src[i*nComp + k] (pos == nullptr: i)
+int launchScatterRows(const double *aos, const int32_t *pos, int n, int nComp, double *soa, long long S,
+                      cudaStream_t st);
 
 // layout conversion
 int launchAosToSoa(const double *aos, double *soa, int nComp, int nElems, long long S,

@@ -66,6 +66,24 @@ int launchSoaToAos(const double *soa, double *aos, int nComp, int nElems, long l
   return 0;
 }
 
+// per-element source data handed over as a list (force field, transport velocity):
+// soa[k][pos[i]-1] = aos[i*nComp + k]
+__global__ void scatterRowsKernel(const double *__restrict__ aos, const int32_t *__restrict__ pos, int n,
+                                  int nComp, double *__restrict__ soa, long long S) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * nComp) return;
+  const int i = t / nComp, k = t % nComp;
+  const int e = pos ? pos[i] - 1 : i;
+  soa[(long long)k * S + e] = aos[t];
+}
+int launchScatterRows(const double *aos, const int32_t *pos, int n, int nComp, double *soa, long long S,
+                      cudaStream_t st) {
+  if (n <= 0) return 0;
+  scatterRowsKernel<<<divUp((long long)n * nComp, 256), 256, 0, st>>>(aos, pos, n, nComp, soa, S);
+  MUSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ---------------------------------------------------------------------------
 template <int QQ>
 __global__ void encodeNeighKernel(const int32_t *__restrict__ neigh, uint32_t *__restrict__ nbr,

@@ -1,0 +1,223 @@
+// sweep_kernel.cuh -- the fused sweep kernel template, instantiated without the force source in
+// sweep.cu and with it in sweep_force.cu (two translation units so they compile in parallel).
+#pragma once
+#include "kernels.cuh"
+
+namespace musb200 {
+
+// Launch shape: 128 threads per CTA.  D3Q19 is capped at 80 registers (__launch_bounds__(128, 6):
+// 6 CTAs = 24 warps per SM, at most 24 B of spills in the MRT variants); uncapped the compiler
+// takes 94-110 registers, only 16 warps fit and the TRT sweep of 256^3 drops from 0.961 ms
+// (1.01 of the measured HBM peak) to 1.079 ms (0.90).  D3Q27 needs up to 128 registers
+// (4 CTAs/SM, no spills).  A warp lives long here (26 index loads -> 27 gathers -> 800-1300 FP64
+// instructions -> 27 stores) and a CTA's registers are only released when its last warp retires,
+// so small CTAs keep more loads in flight.  Measured on B200 (profiles/r01_launch_shape.md):
+// D3Q19 TRT 256^3, 80 registers: 64 / 128 / 192 / 256 threads = 0.966 / 0.961 / 0.966 / 0.964 ms,
+// 94 registers (5 CTAs) 0.984 ms, 72 registers (7 CTAs, 52 B spills) 0.987 ms;
+// D3Q27 MRT 256^3: 256 threads 2.30 ms, 128 threads 1.55 ms, 64 threads 1.57 ms, 512 threads
+// 1.81 ms.  Capping D3Q27 at 96 or 80 registers (5-6 CTAs/SM) spills 270-570 B per thread and
+// is slower (1.98 / 2.64 ms).
+#ifndef SWEEP27_THREADS
+#define SWEEP27_THREADS 128
+#endif
+#ifndef SWEEP27_MINBLOCKS
+#define SWEEP27_MINBLOCKS 4
+#endif
+#ifndef SWEEP19_THREADS
+#define SWEEP19_THREADS 128
+#endif
+#ifndef SWEEP19_MINBLOCKS
+#define SWEEP19_MINBLOCKS 6
+#endif
+template <int QQ>
+constexpr int sweepThreads() { return QQ == 27 ? SWEEP27_THREADS : SWEEP19_THREADS; }
+template <int QQ>
+constexpr int sweepMinBlocks() { return QQ == 27 ? SWEEP27_MINBLOCKS : SWEEP19_MINBLOCKS; }
+
+// exact product with a lattice component c in {-1, 0, 1}
+__device__ __forceinline__ double mulc(int c, double x) { return c == 0 ? 0.0 : (c > 0 ? x : -x); }
+
+// Body-force source term fused into the sweep (source = { force = ... }):
+//   order 2: velocity shift F/(2 rho) of mus_addForceToAuxField_fluid / _fluidIncomp
+//            (mus_auxFieldVar_module.fpp:1032-1214) before the collision, then per direction
+//            applySrc_force (bgk, trt; mus_derQuan_module.fpp:3129-3243),
+//            applySrc_force_MRT_d3q19 (:3716-3862) or applySrc_force_MRT_d3q27 (:3555-3693)
+//   order 1: applySrc_force1stOrd (:4043-4143), no velocity shift
+// added to the post-collision value in the same operation order as the reference; matrix
+// entries and lattice components that are zero are skipped (x + 0*y = x).
+template <int QQ, int RELAX>
+struct ForceSrc {
+  double Fx, Fy, Fz, ux, uy, uz;
+  double ofac;   // bgk / trt: 1 - omega/2
+  double sK, sB; // mrt: 1 - omegaKine/2, 1 - omegaBulk/2
+  double m[9];   // mrt: the nine non-zero force moments, ascending moment index
+  int order;
+
+  __device__ __forceinline__ void prepare(double omega, double omegaBulk) {
+    if (order != 2) return;
+    if (RELAX != 2) { ofac = 1.0 - omega * 0.5; return; }
+    sK = 1.0 - 0.5 * omega;
+    sB = 1.0 - 0.5 * omegaBulk;
+    const double fu2 = 2.0 * (Fx * ux + Fy * uy + Fz * uz);
+    const double m10 = -2.0 * (Fy * uy - 2.0 * Fx * ux + Fz * uz);
+    const double m12 = 2.0 * (Fy * uy - Fz * uz);
+    const double mxy = Fx * uy + Fy * ux, myz = Fy * uz + Fz * uy, mxz = Fx * uz + Fz * ux;
+    if (QQ == 19) {  // momForce(2,4,6,8,10,12,14,15,16)
+      m[0] = fu2; m[1] = Fx; m[2] = Fy; m[3] = Fz; m[4] = m10; m[5] = m12; m[6] = mxy; m[7] = myz; m[8] = mxz;
+    } else {         // momForce(2..10)
+      m[0] = Fx; m[1] = Fy; m[2] = Fz; m[3] = mxy; m[4] = myz; m[5] = mxz; m[6] = m10; m[7] = m12; m[8] = fu2;
+    }
+  }
+  // 0-based moment index and relaxation factor of the j-th non-zero force moment
+  static __device__ __forceinline__ constexpr int momIdx(int j) {
+    if (QQ == 19) { constexpr int t[9] = {1, 3, 5, 7, 9, 11, 13, 14, 15}; return t[j]; }
+    return j + 1;
+  }
+  __device__ __forceinline__ double sOf(int j) const {
+    if (QQ == 19) return j == 0 ? sB : (j < 4 ? 1.0 : sK);
+    return j < 3 ? 1.0 : (j < 8 ? sK : sB);
+  }
+  static __device__ __forceinline__ constexpr double toPdf(int q, int k) {
+    return QQ == 19 ? mmIvD3Q19(q, k) : wmmIvD3Q27(q, k);
+  }
+
+  __device__ __forceinline__ double term(int q) const {
+    const int c0 = cx<QQ>(q, 0), c1 = cx<QQ>(q, 1), c2 = cx<QQ>(q, 2);
+    const double w = weight<QQ>(q);
+    if (order == 1) {
+      const double ft = mulc(c0, Fx) + mulc(c1, Fy) + mulc(c2, Fz);
+      return w * 3.0 * ft;
+    }
+    if (RELAX != 2) {
+      const double ucx = mulc(c0, ux) + mulc(c1, uy) + mulc(c2, uz);
+      const double t0 = ((double)c0 - ux) * 3.0 + mulc(c0, ucx) * 9.0;
+      const double t1 = ((double)c1 - uy) * 3.0 + mulc(c1, ucx) * 9.0;
+      const double t2 = ((double)c2 - uz) * 3.0 + mulc(c2, ucx) * 9.0;
+      const double ft = t0 * Fx + t1 * Fy + t2 * Fz;
+      return ofac * w * ft;
+    }
+    double disc = 0.0;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const double A = toPdf(q, momIdx(j));
+      if (A != 0.0) disc = disc + (A * sOf(j)) * m[j];
+    }
+    return disc;
+  }
+};
+
+template <int QQ, int RELAX, bool INCOMP, bool FORCE>
+__global__ void __launch_bounds__(sweepThreads<QQ>(), sweepMinBlocks<QQ>()) sweepKernel(const SweepArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.count) return;
+  int e;
+  if (a.list != nullptr) {
+    e = a.list[i];
+  } else {
+    e = a.first + i;
+    if (a.skip != nullptr && ((a.skip[e >> 5] >> (e & 31)) & 1u)) return;
+  }
+  const long long S = a.S;
+
+  double f[QQ];
+  {
+    uint32_t n[QQ - 1];
+#pragma unroll
+    for (int q = 0; q < QQ - 1; ++q) n[q] = __ldcs(a.nbr + q * S + e);
+#pragma unroll
+    for (int q = 0; q < QQ - 1; ++q) {
+      const long long row = (n[q] & kBounceBit) ? (long long)invDir<QQ>(q) * S : (long long)q * S;
+      f[q] = __ldg(a.in + row + (n[q] & kElemMask));
+    }
+    f[QQ - 1] = __ldg(a.in + (long long)(QQ - 1) * S + e);
+  }
+
+  double rho, ux, uy, uz;
+  moments<QQ>(f, rho, ux, uy, uz);
+  if (!INCOMP) {
+    ux = ux / rho;
+    uy = uy / rho;
+    uz = uz / rho;
+  }
+  ForceSrc<QQ, RELAX> fs;
+  if (FORCE) {
+    if (a.force != nullptr) {
+      fs.Fx = __ldcs(a.force + e);
+      fs.Fy = __ldcs(a.force + S + e);
+      fs.Fz = __ldcs(a.force + 2 * S + e);
+    } else {
+      fs.Fx = a.force_uniform[0]; fs.Fy = a.force_uniform[1]; fs.Fz = a.force_uniform[2];
+    }
+    fs.order = a.force_order;
+    if (fs.order == 2) {
+      const double inv_rho = INCOMP ? 1.0 : 1.0 / rho;
+      ux = ux + fs.Fx * 0.5 * inv_rho;
+      uy = uy + fs.Fy * 0.5 * inv_rho;
+      uz = uz + fs.Fz * 0.5 * inv_rho;
+    }
+    fs.ux = ux; fs.uy = uy; fs.uz = uz;
+  }
+  if (a.write_aux) {
+    __stcs(a.aux + e, rho);
+    __stcs(a.aux + S + e, ux);
+    __stcs(a.aux + 2 * S + e, uy);
+    __stcs(a.aux + 3 * S + e, uz);
+  }
+  const double omega = (a.omega != nullptr) ? __ldcs(a.omega + e) : a.rp.omega_uniform;
+
+  double *out = a.out + e;
+  if (FORCE) fs.prepare(omega, a.rp.omega_bulk);
+  auto st = [&](int q, double v) {
+    if (FORCE) v = v + fs.term(q);
+    __stcs(out + (long long)q * S, v);
+  };
+  if (QQ == 19) {
+    const double(&g)[19] = reinterpret_cast<const double(&)[19]>(f);
+    if (RELAX == 0) collide_bgk_d3q19<INCOMP>(g, rho, ux, uy, uz, omega, st);
+    if (RELAX == 1 && !INCOMP) collide_trt_d3q19(g, rho, ux, uy, uz, omega, a.rp.lambda, st);
+    if (RELAX == 1 && INCOMP) collide_trt_d3q19_incomp(g, rho, ux, uy, uz, omega, a.rp.lambda, st);
+    if (RELAX == 2) collide_mrt_d3q19<INCOMP>(g, rho, ux, uy, uz, omega, a.rp.omega_bulk, st);
+  } else {
+    const double(&g)[27] = reinterpret_cast<const double(&)[27]>(f);
+    if (RELAX == 0) collide_bgk_d3q27<INCOMP>(g, rho, ux, uy, uz, omega, st);
+    if (RELAX == 1) collide_trt_d3q27(g, rho, ux, uy, uz, omega, a.rp.lambda, st);
+    if (RELAX == 2) collide_mrt_d3q27<INCOMP>(g, rho, ux, uy, uz, omega, a.rp.omega_bulk, st);
+  }
+}
+
+template <int QQ, int RELAX, bool INCOMP, bool FORCE>
+static int launchT(const SweepArgs &a, cudaStream_t st) {
+  if (a.count <= 0) return 0;
+  const int block = sweepThreads<QQ>();
+  sweepKernel<QQ, RELAX, INCOMP, FORCE><<<divUp(a.count, block), block, 0, st>>>(a);
+  MUSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+
+// (layout, relaxation, kind) -> instantiation; FORCE selects the translation unit
+template <bool FORCE>
+static int dispatchSweep(int QQ, int relax, int kind, const SweepArgs &a, cudaStream_t st) {
+  if (kind == 1) {
+    // mus_init_advRel_fluid_incompressible (init/mus_initFluidIncomp_module.f90:73-218):
+    // trt exists for d3q19 only
+    if (QQ == 19 && relax == 0) return launchT<19, 0, true, FORCE>(a, st);
+    if (QQ == 19 && relax == 1) return launchT<19, 1, true, FORCE>(a, st);
+    if (QQ == 19 && relax == 2) return launchT<19, 2, true, FORCE>(a, st);
+    if (QQ == 27 && relax == 0) return launchT<27, 0, true, FORCE>(a, st);
+    if (QQ == 27 && relax == 2) return launchT<27, 2, true, FORCE>(a, st);
+    return setError(4, "fluid_incompressible: the reference has no trt kernel for this layout");
+  }
+  if (QQ == 19) {
+    if (relax == 0) return launchT<19, 0, false, FORCE>(a, st);
+    if (relax == 1) return launchT<19, 1, false, FORCE>(a, st);
+    if (relax == 2) return launchT<19, 2, false, FORCE>(a, st);
+  } else if (QQ == 27) {
+    if (relax == 0) return launchT<27, 0, false, FORCE>(a, st);
+    if (relax == 1) return launchT<27, 1, false, FORCE>(a, st);
+    if (relax == 2) return launchT<27, 2, false, FORCE>(a, st);
+  }
+  return setError(4, "no kernel for this (layout, relaxation)");
+}
+
+}  // namespace musb200

@@ -50,8 +50,21 @@ def get_unique_id():
     return buf.raw
 
 
+PS_VARIANT = {"first": 1, "second": 2}
+
+
+def _relaxation_of(identify):
+    rel = identify.get("relaxation", "bgk")
+    variant = "standard"
+    if isinstance(rel, dict):
+        variant = rel.get("variant", "standard")
+        rel = rel.get("name", "bgk")
+    return rel, variant
+
+
 def select_kernel(identify):
-    """mus_init_advRel_fluid: the (kind, relaxation, variant, layout) dispatch."""
+    """mus_init_advRel_fluid / _fluid_incompressible / _lbm_ps: the (kind, relaxation, variant,
+    layout) dispatch."""
     rel = identify.get("relaxation", "bgk")
     variant = "standard"
     if isinstance(rel, dict):
@@ -67,13 +80,25 @@ def select_kernel(identify):
 class Scheme:
     """mus_scheme_type for one level range on one rank, device resident."""
 
-    def __init__(self, identify, levelDescs, omega, lambda_=0.25, omega_bulk=None, intp=None,
-                 viscosity=None, bc_kind=None):
+    def __init__(self, identify, levelDescs, omega=None, lambda_=0.25, omega_bulk=None, intp=None,
+                 viscosity=None, bc_kind=None, slot=0, species=None):
         """intp: None or (tables, order) with tables as built by multilevel_tables();
         viscosity: {level: lattice viscosity} (fluid%viscKine%dataOnLvl) for the interpolation;
         bc_kind: {boundary id: kind} binds the mesh's 'pressure' boundaries to pressure_expol or
-        pressure_antibounceback (the boundary_condition table of the Lua configuration)."""
+        pressure_antibounceback (the boundary_condition table of the Lua configuration);
+        slot: scheme slot of the library (several schemes on one mesh);
+        species: {"diff_coeff": D, "lambda": 0.25} of a passive_scalar scheme."""
+        self.slot = int(slot)
+        self._bind()
         self.relax, self.kind, self.QQ = select_kernel(identify)
+        self.passive_scalar = identify.get("kind", "fluid") == "passive_scalar"
+        self.nAux = 1 if self.passive_scalar else 4
+        if self.passive_scalar:
+            if species is None:
+                raise ValueError("passive_scalar needs species = {diff_coeff, lambda}")
+            self.ps_variant = PS_VARIANT.get(_relaxation_of(identify)[1], 0)
+        elif omega is None:
+            raise ValueError("a fluid scheme needs omega")
         if not isinstance(levelDescs, dict):
             levelDescs = {levelDescs.level: levelDescs}
         self.levelDesc = levelDescs
@@ -82,13 +107,18 @@ class Scheme:
         for lvl, ld in levelDescs.items():
             if ld.QQ != self.QQ:
                 raise ValueError("levelDesc built for another stencil")
-            check(lib.musb200_level_create(lvl, self.QQ, self.QQ, 4, ld.nSize, ld.nFluid,
+            check(lib.musb200_level_create(lvl, self.QQ, self.QQ, self.nAux, ld.nSize, ld.nFluid,
                                            ld.nGhostFromCoarser, ld.nGhostFromFiner, ld.nHalo,
                                            ptr(ld.neigh, P_I32), ptr(ld.property, P_I64),
                                            ptr(ld.total, P_I64)))
-            om = omega[lvl] if isinstance(omega, dict) else omega
-            ob = omega_bulk if omega_bulk is not None else (om if np.isscalar(om) else 1.0)
-            self.set_relaxation(lvl, om, ob)
+            if self.passive_scalar:
+                check(lib.musb200_set_species(lvl, self.relax, self.ps_variant,
+                                              float(species["diff_coeff"]),
+                                              float(species.get("lambda", 0.25))))
+            else:
+                om = omega[lvl] if isinstance(omega, dict) else omega
+                ob = omega_bulk if omega_bulk is not None else (om if np.isscalar(om) else 1.0)
+                self.set_relaxation(lvl, om, ob)
             if len(ld.bc_elemBuffer):
                 check(lib.musb200_bc_elembuffer(lvl, len(ld.bc_elemBuffer), ptr(ld.bc_elemBuffer, P_I32)))
             for bc in ld.bc:
@@ -137,8 +167,34 @@ class Scheme:
                     ptr(t["matOffset"], P_I32), ptr(mats, P_DBL) if mats.size else None,
                     ptr(coord, P_DBL) if coord.size else None))
 
+    def _bind(self):
+        check(lib.musb200_scheme_bind(self.slot))
+
+    # -- source = { force = ... } (lattice units) -------------------------------
+    def set_force(self, level, force, order=2, posInTotal=None):
+        """force: 3 values (uniform) or [n][3] for the elements posInTotal (default 1..nSolve)"""
+        self._bind()
+        F = np.ascontiguousarray(force, dtype=np.float64)
+        pos = None if posInTotal is None else np.ascontiguousarray(posInTotal, dtype=np.int32)
+        ld = self.levelDesc[level]
+        n = (ld.nFluid + ld.nGhostFromCoarser) if pos is None else pos.size
+        uniform = 1 if (F.ndim == 1 and F.size == 3) else 0
+        check(lib.musb200_source_force(level, int(order), int(n), ptr(pos, P_I32), ptr(F, P_DBL), uniform))
+
+    # -- scheme%transVar (passive scalar) ----------------------------------------
+    def set_transport_velocity(self, level, vel):
+        self._bind()
+        v = np.ascontiguousarray(vel, dtype=np.float64)
+        check(lib.musb200_set_transport_velocity(level, v.size // 3, ptr(v, P_DBL), 1 if v.size == 3 else 0))
+
+    def couple_transport_velocity(self, level, flow):
+        """device-side coupling: read the velocity from the auxField of the Scheme `flow`"""
+        self._bind()
+        check(lib.musb200_couple_transport_velocity(level, flow.slot, level))
+
     # -- fluid%viscKine%omLvl / lambda / omegaBulkLvl ------------------------
     def set_relaxation(self, level, omega, omega_bulk):
+        self._bind()
         if np.isscalar(omega):
             check(lib.musb200_set_relaxation(level, self.relax, self.kind, None, float(omega),
                                              float(self.lambda_), float(omega_bulk)))
@@ -149,6 +205,7 @@ class Scheme:
 
     # -- state(level)%val(:, 1:2), AOS, host layout ---------------------------
     def upload_state(self, level, aos_now, aos_next=None, nNow=1, nNext=2):
+        self._bind()
         a = np.ascontiguousarray(aos_now, dtype=np.float64)
         check(lib.musb200_state_upload(level, nNow, a.ctypes.data))
         b = a if aos_next is None else np.ascontiguousarray(aos_next, dtype=np.float64)
@@ -156,11 +213,13 @@ class Scheme:
         check(lib.musb200_set_now_next(level, nNow, nNext))
 
     def now_next(self, level):
+        self._bind()
         a, b = ctypes.c_int(), ctypes.c_int()
         check(lib.musb200_get_now_next(level, ctypes.byref(a), ctypes.byref(b)))
         return a.value, b.value
 
     def download_state(self, level, which=None):
+        self._bind()
         ld = self.levelDesc[level]
         out = np.empty(ld.nSize * self.QQ)
         if which is None:
@@ -169,23 +228,27 @@ class Scheme:
         return out
 
     def download_aux(self, level):
-        out = np.empty(self.levelDesc[level].nSize * 4)
+        self._bind()
+        out = np.empty(self.levelDesc[level].nSize * self.nAux)
         check(lib.musb200_aux_download(level, out.ctypes.data))
         return out
 
     def aux_probe(self, level, elemPos):
+        self._bind()
         """tracking of one element (1-based position in the level's total list): rho, ux, uy, uz"""
-        out = np.empty(4)
+        out = np.empty(self.nAux)
         check(lib.musb200_aux_probe(level, int(elemPos), ptr(out, P_DBL)))
         return out
 
     def download_neigh(self, level):
+        self._bind()
         ld = self.levelDesc[level]
         out = np.zeros(ld.nSize * self.QQ, dtype=np.int32)
         check(lib.musb200_neigh_download(level, ptr(out, P_I32)))
         return out
 
     def set_bc_values(self, level, bc_id, vals):
+        self._bind()
         v = np.ascontiguousarray(vals, dtype=np.float64)
         check(lib.musb200_bc_set_values(level, bc_id, v.size, v.ctypes.data))
 
@@ -221,18 +284,21 @@ class Scheme:
 
     # -- control%do_computation ----------------------------------------------
     def do_computation(self, nCycles=1):
+        self._bind()
         check(lib.musb200_step(self.minLevel, self.maxLevel, int(nCycles)))
 
     def synchronize(self):
         check(lib.musb200_synchronize())
 
     def reduce(self, level=None):
+        self._bind()
         level = self.minLevel if level is None else level
         m, v, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
         check(lib.musb200_reduce(level, ctypes.byref(m), ctypes.byref(v), ctypes.byref(n)))
         return m.value, v.value, n.value
 
     def destroy(self):
+        self._bind()
         for lvl in list(self.levelDesc):
             lib.musb200_level_destroy(lvl)
 

@@ -595,6 +595,56 @@ class Scheme:
         self.omega_uniform = float(omega)
 
 
+class PassiveScalarScheme:
+    """scheme kind 'passive_scalar' on one level: mus_calcAuxField_zerothMoment +
+    mus_advRel_kPS_* (mus_compute_passiveScalar_module.fpp), transport velocity in lattice units."""
+    VARIANT = {("bgk", "first"): 1, ("bgk", "second"): 2, ("trt", "standard"): 3}
+
+    def __init__(self, ld, relaxation="bgk", variant="first", diff_coeff=0.01, lambda_=0.25):
+        self.ld, self.QQ = ld, ld.QQ
+        self.variant = self.VARIANT[(relaxation, variant)]
+        self.diff_coeff, self.lambda_ = float(diff_coeff), float(lambda_)
+        n = ld.nSize * self.QQ
+        self.state = [np.full(n, -1.0e6), np.full(n, -1.0e6)]
+        self.aux = np.full(ld.nSize, -1.0e6)
+        self.nNow, self.nNext = 0, 1
+        self.transVel = np.zeros((ld.nSolve, 3))
+
+    def init_equilibrium(self, rho, vel=None):
+        """f = w * rho * (1 + 3 c.u) (first-order equilibrium) for every element of the level"""
+        ld, QQ = self.ld, self.QQ
+        rho = np.broadcast_to(np.asarray(rho, dtype=np.float64), (ld.nElems,))
+        vel = np.zeros((ld.nElems, 3)) if vel is None else np.broadcast_to(np.asarray(vel, float), (ld.nElems, 3))
+        c, w = cx_dir(QQ).astype(np.float64), weights(QQ)
+        st = self.state[self.nNext]
+        st[:] = 0.0
+        f = w[None, :] * rho[:, None] * (1.0 + 3.0 * (vel @ c.T))
+        st[:ld.nElems * QQ] = f.reshape(-1)
+        self.state[self.nNow][:] = st
+
+    def set_transport_velocity(self, vel):
+        self.transVel = np.ascontiguousarray(np.broadcast_to(np.asarray(vel, dtype=np.float64),
+                                                             (self.ld.nSolve, 3)))
+
+    def step(self):
+        L, ld = lib(), self.ld
+        self.nNow, self.nNext = self.nNext, self.nNow
+        L.ora_calc_aux_zeroth(self.QQ, _d(self.aux), _d(self.state[self.nNow]), _i(ld.neigh), ld.nSize,
+                              ld.nSolve)
+        rc = L.ora_compute_passive_scalar(self.variant, self.QQ, _d(self.state[self.nNow]),
+                                          _d(self.state[self.nNext]), _i(ld.neigh), ld.nSize, ld.nSolve,
+                                          _d(self.transVel), self.diff_coeff, self.lambda_)
+        if rc != 0:
+            raise RuntimeError("no oracle passive-scalar kernel for this configuration")
+
+    def run(self, nsteps):
+        for _ in range(nsteps):
+            self.step()
+
+    def total_mass(self):
+        return lib().ora_total_mass(_d(self.state[self.nNext]), self.QQ, self.ld.nFluid)
+
+
 def exchange_all(schemes):
     """comm_isend_irecv_real for all ranks held in one process: gather every send
     buffer from state(:,next), then scatter into the receivers."""

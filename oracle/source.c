@@ -89,18 +89,17 @@ static void apply_force_mrt_d3q19(double *out, const double *aux, const double *
     const double *F = force + 3 * (size_t)i;
     double sl[QQ], mom[QQ];
     for (int k = 0; k < QQ; ++k) { sl[k] = s0[k]; mom[k] = 0.0; }
-    double *s = sl - 1, *m = mom - 1; /* 1-based */
-    s[10] = 1.0 - 0.5 * omega[e - 1];
-    s[12] = s[10]; s[14] = s[10]; s[15] = s[10]; s[16] = s[10];
-    m[2] = 2.0 * (F[0] * v[0] + F[1] * v[1] + F[2] * v[2]);
-    m[4] = F[0];
-    m[6] = F[1];
-    m[8] = F[2];
-    m[10] = -2.0 * (F[1] * v[1] - 2.0 * F[0] * v[0] + F[2] * v[2]);
-    m[12] = 2.0 * (F[1] * v[1] - F[2] * v[2]);
-    m[14] = F[0] * v[1] + F[1] * v[0];
-    m[15] = F[1] * v[2] + F[2] * v[1];
-    m[16] = F[0] * v[2] + F[2] * v[0];
+    sl[10 - 1] = 1.0 - 0.5 * omega[e - 1];
+    sl[12 - 1] = sl[10 - 1]; sl[14 - 1] = sl[10 - 1]; sl[15 - 1] = sl[10 - 1]; sl[16 - 1] = sl[10 - 1];
+    mom[2 - 1] = 2.0 * (F[0] * v[0] + F[1] * v[1] + F[2] * v[2]);
+    mom[4 - 1] = F[0];
+    mom[6 - 1] = F[1];
+    mom[8 - 1] = F[2];
+    mom[10 - 1] = -2.0 * (F[1] * v[1] - 2.0 * F[0] * v[0] + F[2] * v[2]);
+    mom[12 - 1] = 2.0 * (F[1] * v[1] - F[2] * v[2]);
+    mom[14 - 1] = F[0] * v[1] + F[1] * v[0];
+    mom[15 - 1] = F[1] * v[2] + F[2] * v[1];
+    mom[16 - 1] = F[0] * v[2] + F[2] * v[0];
     for (int d = 0; d < QQ; ++d) {
       double disc = 0.0; /* sum(mInvXOmega(iDir,1:QQ) * momForce(1:QQ)) */
       for (int k = 0; k < QQ; ++k) disc = disc + (A[d * QQ + k] * sl[k]) * mom[k];
@@ -125,15 +124,14 @@ static void apply_force_mrt_d3q27(double *out, const double *aux, const double *
     const double *F = force + 3 * (size_t)i;
     double sl[QQ], mom[QQ];
     for (int k = 0; k < QQ; ++k) { sl[k] = s0[k]; mom[k] = 0.0; }
-    double *s = sl - 1, *m = mom - 1;
-    for (int k = 5; k <= 9; ++k) s[k] = 1.0 - 0.5 * omega[e - 1];
-    m[2] = F[0]; m[3] = F[1]; m[4] = F[2];
-    m[5] = F[0] * v[1] + F[1] * v[0];
-    m[6] = F[1] * v[2] + F[2] * v[1];
-    m[7] = F[0] * v[2] + F[2] * v[0];
-    m[8] = -2.0 * (F[1] * v[1] - 2.0 * F[0] * v[0] + F[2] * v[2]);
-    m[9] = 2.0 * (F[1] * v[1] - F[2] * v[2]);
-    m[10] = 2.0 * (F[0] * v[0] + F[1] * v[1] + F[2] * v[2]);
+    for (int k = 5; k <= 9; ++k) sl[k - 1] = 1.0 - 0.5 * omega[e - 1];
+    mom[2 - 1] = F[0]; mom[3 - 1] = F[1]; mom[4 - 1] = F[2];
+    mom[5 - 1] = F[0] * v[1] + F[1] * v[0];
+    mom[6 - 1] = F[1] * v[2] + F[2] * v[1];
+    mom[7 - 1] = F[0] * v[2] + F[2] * v[0];
+    mom[8 - 1] = -2.0 * (F[1] * v[1] - 2.0 * F[0] * v[0] + F[2] * v[2]);
+    mom[9 - 1] = 2.0 * (F[1] * v[1] - F[2] * v[2]);
+    mom[10 - 1] = 2.0 * (F[0] * v[0] + F[1] * v[1] + F[2] * v[2]);
     for (int d = 0; d < QQ; ++d) {
       double disc = 0.0; /* dot_product(mInvXOmega(iDir,2:10), momForce(2:10)) */
       for (int k = 1; k <= 9; ++k) disc = disc + (A[d * QQ + k] * sl[k]) * mom[k];
