@@ -126,6 +126,16 @@ int musb200_set_relaxation(int level, int relax_id, int kind_id, const double *o
  * (mus_interpolate_average_module.fpp:328-337, mus_interpolate_linear_module.fpp:471-480) */
 int musb200_set_viscosity(int level, const double *visc, double visc_uniform);
 
+/* ---- restart bridge: mus_pdf_serialize / mus_pdf_unserialize ---------------
+ * mus/source/mus_buffer_module.fpp:80-190, called chunk-wise by tem_restart_writeData /
+ * tem_restart_readData (mus_restart_module.f90:89-260).  treeID / levelPointer: the chunk of
+ * tree%treeID and tree%levelPointer (position of each element in its level's total list);
+ * buffer(nElems*QQ): QQ PDFs of state(:, nNext) per element in treeID (space-filling-curve)
+ * order -- byte for byte the payload of the reference's restart *.lsb file.                    */
+int musb200_pdf_serialize(int nElems, const int64_t *treeID, const int32_t *levelPointer, double *buffer);
+int musb200_pdf_unserialize(int nElems, const int64_t *treeID, const int32_t *levelPointer,
+                            const double *buffer);
+
 /* ---- source terms: field%source / globSrc with varname 'force' ------------
  * mus_source_module.f90:83-310 (element lists), :430-512 (mus_apply_sourceTerms);
  * order 2 (default): mus_addForceToAuxField_fluid / _fluidIncomp
@@ -234,6 +244,12 @@ int musb200_set_aux_every_step(int flag);
  * results; the split sweep costs more than the exchange it hides at 256^3 elements per GPU
  * (profiles/r01_multi_gpu.md), so it is opt-in. */
 int musb200_set_overlap(int flag);
+/* 1 (default): when the only non-wall boundaries of a level are velocity_bounceback ones whose
+ * links stay inside their own elements (the lists mus_set_inletUbb builds), fill_bcBuffer and the
+ * link loop run as ONE kernel per boundary, one thread per boundary element, without the
+ * bcBuffer snapshot; 0: always the reference's two phases (fill_bcBuffer, then the link loops).
+ * Identical results; the fused form saves two launches and the snapshot traffic per step. */
+int musb200_set_fused_bc(int flag);
 int musb200_synchronize(void);
 
 /* check_density / check_flow_status (mus_tools_module.f90:224-313):

@@ -43,6 +43,8 @@ SIGNATURES = {
     "musb200_state_copy_next_to_now": [c_int],
     "musb200_set_relaxation": [c_int, c_int, c_int, P_DBL, c_double, c_double, c_double],
     "musb200_set_viscosity": [c_int, P_DBL, c_double],
+    "musb200_pdf_serialize": [c_int, P_I64, P_I32, P_DBL],
+    "musb200_pdf_unserialize": [c_int, P_I64, P_I32, P_DBL],
     "musb200_source_force": [c_int, c_int, c_int, P_I32, P_DBL, c_int],
     "musb200_set_species": [c_int, c_int, c_int, c_double, c_double],
     "musb200_set_transport_velocity": [c_int, c_int, P_DBL, c_int],
@@ -65,6 +67,7 @@ SIGNATURES = {
     "musb200_timers_reset": [],
     "musb200_launch_count": [P_LL],
     "musb200_set_overlap": [c_int],
+    "musb200_set_fused_bc": [c_int],
     "musb200_p2p_export": [c_int, c_void_p],
     "musb200_p2p_connect": [c_int, c_int, P_I32, c_void_p, P_I32, P_I32],
     "musb200_p2p_enable": [c_int, c_int],

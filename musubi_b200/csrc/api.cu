@@ -107,6 +107,11 @@ struct BcData {
   int id = 0, kind = 0, nLinks = 0;
   DevBuf<int32_t> links, outPos, posInBuffer, iDir;
   DevBuf<double> vals;
+  // velocity_bounceback: links grouped per boundary element (fused kernel, bc.cu)
+  bool fusable = false;
+  int nGroups = 0;
+  DevBuf<int32_t> groupStart, groupElem;
+  std::vector<int32_t> slots;   // bc_elemBuffer slots this boundary touches
   // boundaries that read neighbours along the inward normal (musb200_bc_register_elems)
   int nElems = 0, nNeighs = 0;
   DevBuf<int32_t> elemPos, posInBcElemBuf, normalInd, neighPos, iElemOfLink;
@@ -152,6 +157,7 @@ struct Level {
   DevBuf<uint32_t> nbr;
   DevBuf<int32_t> bcElems;
   std::vector<int32_t> bcElemsHost;
+  int bcFused = -1;                 // -1 unknown, 0 two-phase (bcBuffer), 1 fused kernels
   std::vector<char> bcSlotNeeded;   // bcBuffer slots read by a non-wall boundary
   DevBuf<int32_t> bcNeeded;         // those slots (1-based), compact
   int relax = 0, kind = 0;
@@ -190,6 +196,7 @@ struct Context {
   cudaStream_t stream = nullptr;
   cudaStream_t commStream = nullptr;   // halo exchange, high priority, overlaps the interior sweep
   cudaEvent_t evBoundary = nullptr, evComm = nullptr;
+  int noFusedBc = 0; // musb200_set_fused_bc(0): always take the two-phase bcBuffer path
   int overlap = 0;   // measured slower than exchange-after-compute at 256^3 per GPU (profiles/)
   NcclApi *nccl = nullptr;
   ncclComm_t comm = nullptr;
@@ -266,6 +273,32 @@ static int setBoundary(Level &L) {
   bool any = false;
   for (auto &b : L.bcs) any = any || (b->kind != MUSB200_BC_WALL && b->nLinks > 0);
   if (!any) return 0;
+  if (L.bcFused < 0) {
+    // fused path: only velocity_bounceback boundaries, each fusable, on disjoint elements
+    bool ok = true;
+    std::vector<char> used(L.bcSlotNeeded.size(), 0);
+    for (auto &b : L.bcs) {
+      if (b->kind == MUSB200_BC_WALL || b->nLinks == 0) continue;
+      if (b->kind != MUSB200_BC_VELOCITY_BOUNCEBACK || !b->fusable) { ok = false; break; }
+      for (int32_t sl : b->slots) {
+        if (used[sl - 1]) ok = false;
+        used[sl - 1] = 1;
+      }
+    }
+    L.bcFused = ok ? 1 : 0;
+  }
+  if (L.bcFused == 1 && !g.noFusedBc) {
+    for (auto &b : L.bcs) {
+      if (b->kind == MUSB200_BC_WALL || b->nLinks == 0) continue;
+      if (b->vals.n < (size_t)3 * b->nLinks)
+        return setError(MUSB200_ERR_STATE, "velocity_bounceback: musb200_bc_set_values missing");
+      MUSB_TRY(launchVelocityBounceBackFused(L.QQ, L.kind == MUSB200_KIND_FLUID_INCOMPRESSIBLE, st, L.S,
+                                             b->nGroups, b->groupStart.p, b->groupElem.p, b->links.p,
+                                             b->outPos.p, b->iDir.p, b->vals.p, g.stream));
+      ++g.launches;
+    }
+    return 0;
+  }
   // fill_bcBuffer restricted to the slots a non-wall boundary reads (walls are do_nothing)
   MUSB_TRY(launchFillBcBuffer(L.QQ, st, L.S, L.bcElems.p, L.bcNeeded.p, (int)L.bcNeeded.n, L.bcBuffer.p,
                               g.stream));
@@ -775,6 +808,65 @@ int musb200_set_relaxation(int level, int relax_id, int kind_id, const double *o
 }
 
 // ---------------------------------------------------------------------------
+// restart: the chunk of the global treeID list goes through the device level by level
+static int levelOfTreeID(long long id) {   // tem_LevelOf (tem_topology_module.f90): first id of
+  int level = 0;                            // level L is (8^L - 1) / 7
+  long long first = 0, count = 1;
+  while (id >= first + count) { first += count; count *= 8; ++level; }
+  return level;
+}
+static int serializeChunk(int nElems, const int64_t *treeID, const int32_t *levelPointer, double *out,
+                          const double *in) {
+  MUSB_TRY(needReady());
+  if (nElems < 0 || (nElems > 0 && (!treeID || !levelPointer || (!out && !in))))
+    return setError(MUSB200_ERR_ARG, "bad restart chunk");
+  if (nElems == 0) return 0;
+  std::map<int, std::pair<std::vector<int32_t>, std::vector<int32_t>>> byLevel;  // slot, elemPos
+  for (int i = 0; i < nElems; ++i) {
+    auto &b = byLevel[levelOfTreeID((long long)treeID[i])];
+    b.first.push_back(i + 1);
+    b.second.push_back(levelPointer[i]);
+  }
+  int QQ = 0;
+  for (auto &kv : byLevel) {
+    Level *L = findLevel(kv.first);
+    if (!L) return setError(MUSB200_ERR_ARG, "restart chunk holds a treeID of level " +
+                                                 std::to_string(kv.first) + ", which was not created");
+    if (QQ && QQ != L->QQ) return setError(MUSB200_ERR_ARG, "levels with different stencils");
+    QQ = L->QQ;
+    for (int32_t p : kv.second.second)
+      if (p < 1 || p > L->nElems) return setError(MUSB200_ERR_ARG, "levelPointer outside the level");
+  }
+  const size_t nVals = (size_t)nElems * QQ;
+  MUSB_TRY(stageBuf(nVals));
+  if (in) MUSB_CUDA(cudaMemcpyAsync(g.stage.p, in, nVals * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  for (auto &kv : byLevel) {
+    Level *L = findLevel(kv.first);
+    const int n = (int)kv.second.first.size();
+    DevBuf<int32_t> slot, pos;
+    MUSB_TRY(slot.upload(kv.second.first.data(), (size_t)n, g.stream));
+    MUSB_TRY(pos.upload(kv.second.second.data(), (size_t)n, g.stream));
+    double *st = L->state[L->nNext].p;          // restart reads and writes state(:, nNext)
+    if (out) MUSB_TRY(launchSerialize(QQ, st, L->S, slot.p, pos.p, n, g.stage.p, g.stream));
+    else MUSB_TRY(launchUnserialize(QQ, st, L->S, slot.p, pos.p, n, g.stage.p, g.stream));
+    ++g.launches;
+    MUSB_CUDA(cudaStreamSynchronize(g.stream));  // the index buffers are released here
+  }
+  if (out) {
+    MUSB_CUDA(cudaMemcpyAsync(out, g.stage.p, nVals * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    MUSB_CUDA(cudaStreamSynchronize(g.stream));
+  }
+  return 0;
+}
+int musb200_pdf_serialize(int nElems, const int64_t *treeID, const int32_t *levelPointer, double *buffer) {
+  return serializeChunk(nElems, treeID, levelPointer, buffer, nullptr);
+}
+int musb200_pdf_unserialize(int nElems, const int64_t *treeID, const int32_t *levelPointer,
+                            const double *buffer) {
+  return serializeChunk(nElems, treeID, levelPointer, nullptr, buffer);
+}
+
+// ---------------------------------------------------------------------------
 int musb200_scheme_bind(int slot) {
   MUSB_TRY(needReady());
   if (slot < 0 || slot >= Context::kSlots) return setError(MUSB200_ERR_ARG, "scheme slot out of range");
@@ -925,6 +1017,33 @@ int musb200_bc_register(int level, int bc_id, int bc_kind, int nLinks, const int
       L->bcSlotNeeded[pib - 1] = 1;
       L->bcSlotNeeded[op - 1] = 1;
     }
+    if (bc_kind == MUSB200_BC_VELOCITY_BOUNCEBACK) {
+      // group the links by boundary element; the fused kernel needs every link to read and
+      // write slots of its own element and every element to form one contiguous group
+      std::vector<int32_t> gs, ge;
+      std::vector<char> seen(L->bcSlotNeeded.size(), 0);
+      bool ok = true;
+      for (int l = 0; l < nLinks && ok; ++l) {
+        const int pib = posInBuffer[l];
+        const int e = L->bcElemsHost[pib - 1] - 1;
+        if ((outPos[l] - 1) / L->QQ + 1 != pib || (links[l] - 1) / L->QQ != e) ok = false;
+        if (l == 0 || posInBuffer[l - 1] != pib) {
+          if (seen[pib - 1]) ok = false;
+          seen[pib - 1] = 1;
+          gs.push_back(l);
+          ge.push_back(e);
+          b->slots.push_back(pib);
+        }
+      }
+      gs.push_back(nLinks);
+      b->fusable = ok;
+      if (ok) {
+        b->nGroups = (int)ge.size();
+        MUSB_TRY(b->groupStart.upload(gs.data(), gs.size(), g.stream));
+        MUSB_TRY(b->groupElem.upload(ge.data(), ge.size(), g.stream));
+      }
+    }
+    L->bcFused = -1;
     std::vector<int32_t> needed;
     for (size_t i = 0; i < L->bcSlotNeeded.size(); ++i)
       if (L->bcSlotNeeded[i]) needed.push_back((int32_t)i + 1);
@@ -1164,6 +1283,11 @@ int musb200_step(int minLevel, int maxLevel, int nCoarseCycles) {
   if (maxLevel < minLevel || nCoarseCycles < 0) return setError(MUSB200_ERR_ARG, "bad level range / cycles");
   for (int it = 0; it < nCoarseCycles; ++it)
     MUSB_TRY(levelStep(minLevel, minLevel, maxLevel, it == nCoarseCycles - 1));
+  return 0;
+}
+
+int musb200_set_fused_bc(int flag) {
+  g.noFusedBc = flag ? 0 : 1;
   return 0;
 }
 

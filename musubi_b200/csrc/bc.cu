@@ -62,6 +62,47 @@ __global__ void velocityBounceBackKernel(int incomp, double *__restrict__ state,
   state[(long long)(p % QQ) * S + p / QQ] = fOut + eqPlus;
 }
 
+// velocity_bounceback without the bcBuffer snapshot: one thread per boundary ELEMENT reads the
+// element's QQ post-collision PDFs (rho = their sequential sum, exactly what the link loop of
+// the reference sums out of bcBuffer), then writes each of its links from the element's own
+// outgoing slot.  Valid when every link of the level's non-wall boundaries writes a slot of its
+// own element and no element belongs to two such boundaries (checked at registration, api.cu):
+// then no thread reads a value another thread -- or an earlier link of the same thread --
+// has written, and the result equals the two-phase fill_bcBuffer + link loop bit for bit.
+template <int QQ>
+__global__ void velocityBounceBackFusedKernel(int incomp, double *__restrict__ state, long long S,
+                                              int nGroups, const int32_t *__restrict__ groupStart,
+                                              const int32_t *__restrict__ groupElem,
+                                              const int32_t *__restrict__ links,
+                                              const int32_t *__restrict__ outPos,
+                                              const int32_t *__restrict__ iDir,
+                                              const double *__restrict__ velLat) {
+  const int gidx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gidx >= nGroups) return;
+  const int e = groupElem[gidx];
+  double rho = 0.0;
+#pragma unroll
+  for (int q = 0; q < QQ; ++q) rho = rho + state[(long long)q * S + e];
+  if (incomp) rho = 1.0;  // rho0
+  const int l1 = groupStart[gidx + 1];
+  for (int l = groupStart[gidx]; l < l1; ++l) {
+    const int qo = (outPos[l] - 1) % QQ;
+    const double fOut = state[(long long)qo * S + e];
+    const int d = iDir[l] - 1;
+    int c0 = 0, c1 = 0, c2 = 0;
+    double w = 0.0;
+#pragma unroll
+    for (int q = 0; q < QQ - 1; ++q)
+      if (q == d) { c0 = cx<QQ>(q, 0); c1 = cx<QQ>(q, 1); c2 = cx<QQ>(q, 2); w = weight<QQ>(q); }
+    const double eqPlus = w * 6.0 * rho *
+                          ((double)c0 * velLat[3 * (long long)l + 0] +
+                           (double)c1 * velLat[3 * (long long)l + 1] +
+                           (double)c2 * velLat[3 * (long long)l + 2]);
+    const int p = links[l] - 1;
+    state[(long long)(p % QQ) * S + p / QQ] = fOut + eqPlus;
+  }
+}
+
 // run-time inverse direction / lattice vector / weight through a fully unrolled compile-time table
 template <int QQ>
 __device__ __forceinline__ int invDirRt(int d) {
@@ -293,6 +334,21 @@ int launchVelocityBounceBack(int QQ, int incomp, double *state, long long S,
   else
     velocityBounceBackKernel<27><<<divUp(nLinks, 256), 256, 0, st>>>(
         incomp, state, S, bcBuffer, nLinks, links, outPos, posInBuffer, iDir, velLat);
+  MUSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launchVelocityBounceBackFused(int QQ, int incomp, double *state, long long S, int nGroups,
+                                  const int32_t *groupStart, const int32_t *groupElem,
+                                  const int32_t *links, const int32_t *outPos, const int32_t *iDir,
+                                  const double *velLat, cudaStream_t st) {
+  if (nGroups <= 0) return 0;
+  if (QQ == 19)
+    velocityBounceBackFusedKernel<19><<<divUp(nGroups, 128), 128, 0, st>>>(
+        incomp, state, S, nGroups, groupStart, groupElem, links, outPos, iDir, velLat);
+  else
+    velocityBounceBackFusedKernel<27><<<divUp(nGroups, 128), 128, 0, st>>>(
+        incomp, state, S, nGroups, groupStart, groupElem, links, outPos, iDir, velLat);
   MUSB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -338,7 +338,11 @@ __device__ __forceinline__ void collide_trt_d3q27(const double (&f)[27], double 
 template <int D, int J>
 __device__ __forceinline__ void mrt27Acc(double &acc, const double (&m)[27]) {
   constexpr double w = wmmIvD3Q27(D, J);
+#ifdef MRT27_FMA   // experiment only: fused multiply-add changes the rounding sequence
+  if constexpr (w != 0.0) acc = __fma_rn(w, m[J], acc);
+#else
   if constexpr (w != 0.0) acc = acc + w * m[J];
+#endif
 }
 template <int D, int... J>
 __device__ __forceinline__ double mrt27Row(const double (&m)[27], std::integer_sequence<int, J...>) {

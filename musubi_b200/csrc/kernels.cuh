@@ -69,6 +69,11 @@ int launchVelocityBounceBack(int QQ, int incomp, double *state, long long S,
                              const int32_t *outPos, const int32_t *posInBuffer,
                              const int32_t *iDir, const double *velLat, cudaStream_t st);
 
+int launchVelocityBounceBackFused(int QQ, int incomp, double *state, long long S, int nGroups,
+                                  const int32_t *groupStart, const int32_t *groupElem,
+                                  const int32_t *links, const int32_t *outPos, const int32_t *iDir,
+                                  const double *velLat, cudaStream_t st);
+
 // boundaries that read neighbours along the inward normal
 int launchFillNeighBuffer(int QQ, const double *state, long long S, const uint32_t *nbr, int nNeighs,
                           int nElems, const int32_t *neighPos, int post, double *nb, cudaStream_t st);
@@ -89,6 +94,12 @@ int launchPack(int QQ, const double *state, long long S, const int32_t *pos, int
                cudaStream_t st);
 int launchUnpack(int QQ, double *state, long long S, const int32_t *pos, int n, const double *buf,
                  cudaStream_t st);
+
+// restart bridge (mus_pdf_serialize order): chunk buffer <-> state of one level
+int launchSerialize(int QQ, const double *state, long long S, const int32_t *slot, const int32_t *elemPos,
+                    int n, double *buffer, cudaStream_t st);
+int launchUnserialize(int QQ, double *state, long long S, const int32_t *slot, const int32_t *elemPos,
+                      int n, const double *buffer, cudaStream_t st);
 
 // peer-memory halo exchange (p2p.cu)
 constexpr int kMaxPeers = 16;

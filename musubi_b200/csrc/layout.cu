@@ -184,6 +184,42 @@ int launchUnpack(int QQ, double *state, long long S, const int32_t *pos, int n, 
 }
 
 // ---------------------------------------------------------------------------
+// restart bridge: mus_pdf_serialize / mus_pdf_unserialize (mus_buffer_module.fpp:80-190) for the
+// elements of one level inside a chunk of the global treeID list:
+//   buffer((slot(i)-1)*QQ + c) = state(level)%val(IDX(c, levelPointer(i)), nNext)
+// slot = position of the element in the chunk (1-based), elemPos = levelPointer
+__global__ void serializeKernel(const double *__restrict__ state, long long S, int QQ,
+                                const int32_t *__restrict__ slot, const int32_t *__restrict__ elemPos,
+                                int n, double *__restrict__ buffer) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * QQ) return;
+  const int c = (int)(t / n), i = (int)(t % n);   // element index fastest: coalesced row reads
+  buffer[(long long)(slot[i] - 1) * QQ + c] = state[(long long)c * S + (elemPos[i] - 1)];
+}
+__global__ void unserializeKernel(double *__restrict__ state, long long S, int QQ,
+                                  const int32_t *__restrict__ slot, const int32_t *__restrict__ elemPos,
+                                  int n, const double *__restrict__ buffer) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * QQ) return;
+  const int c = (int)(t / n), i = (int)(t % n);
+  state[(long long)c * S + (elemPos[i] - 1)] = buffer[(long long)(slot[i] - 1) * QQ + c];
+}
+int launchSerialize(int QQ, const double *state, long long S, const int32_t *slot, const int32_t *elemPos,
+                    int n, double *buffer, cudaStream_t st) {
+  if (n <= 0) return 0;
+  serializeKernel<<<divUp((long long)n * QQ, 256), 256, 0, st>>>(state, S, QQ, slot, elemPos, n, buffer);
+  MUSB_CUDA(cudaGetLastError());
+  return 0;
+}
+int launchUnserialize(int QQ, double *state, long long S, const int32_t *slot, const int32_t *elemPos,
+                      int n, const double *buffer, cudaStream_t st) {
+  if (n <= 0) return 0;
+  unserializeKernel<<<divUp((long long)n * QQ, 256), 256, 0, st>>>(state, S, QQ, slot, elemPos, n, buffer);
+  MUSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
 // total mass / max |u|^2 / NaN count over the fluid elements; two-stage and
 // deterministic (fixed grid, fixed summation tree).
 constexpr int kRedBlocks = 592;  // 4 x 148 SMs

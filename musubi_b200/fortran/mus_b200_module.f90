@@ -33,6 +33,8 @@ module mus_b200_module
   public :: mus_b200_upload, mus_b200_download
   public :: mus_b200_step, mus_b200_compute
   public :: mus_b200_check
+  public :: mus_b200_upload_intp, mus_b200_set_force, mus_b200_p2p_connect
+  public :: mus_b200_pdf_serialize, mus_b200_pdf_unserialize
 
   integer(c_int), parameter :: buf_halo = 0, buf_fromCoarser = 1, buf_fromFiner = 2
   integer(c_int), parameter :: dir_send = 0, dir_recv = 1
@@ -153,6 +155,83 @@ module mus_b200_module
       integer(c_int), value :: level
       real(c_double) :: mass, maxvel
       integer(c_int) :: anynan
+      integer(c_int) :: rc
+    end function
+    function musb200_set_viscosity(level, visc, visc_uniform) bind(C, name='musb200_set_viscosity') result(rc)
+      import :: c_int, c_double
+      integer(c_int), value :: level
+      real(c_double) :: visc(*)
+      real(c_double), value :: visc_uniform
+      integer(c_int) :: rc
+    end function
+    function musb200_bc_register_elems(level, bc_id, nElems, elemPos, posInBcElemBuf, normalInd, nNeighs, &
+      & neighPos, iElemOfLink) bind(C, name='musb200_bc_register_elems') result(rc)
+      import :: c_int, c_int32_t
+      integer(c_int), value :: level, bc_id, nElems, nNeighs
+      integer(c_int32_t) :: elemPos(*), posInBcElemBuf(*), normalInd(*), neighPos(*), iElemOfLink(*)
+      integer(c_int) :: rc
+    end function
+    function musb200_intp_register(tgtLevel, direction, order, nTargets, targetList, srcOffset, srcPos, &
+      & weights, posInMat, nMatrices, matOffset, matrices, childCoord) &
+      & bind(C, name='musb200_intp_register') result(rc)
+      import :: c_int, c_int32_t, c_double
+      integer(c_int), value :: tgtLevel, direction, order, nTargets, nMatrices
+      integer(c_int32_t) :: targetList(*), srcOffset(*), srcPos(*), posInMat(*), matOffset(*)
+      real(c_double) :: weights(*), matrices(*), childCoord(*)
+      integer(c_int) :: rc
+    end function
+    function musb200_source_force(level, order, nElems, posInTotal, force, uniform) &
+      & bind(C, name='musb200_source_force') result(rc)
+      import :: c_int, c_int32_t, c_double
+      integer(c_int), value :: level, order, nElems, uniform
+      integer(c_int32_t) :: posInTotal(*)
+      real(c_double) :: force(*)
+      integer(c_int) :: rc
+    end function
+    function musb200_set_species(level, relax_id, variant, diff_coeff, lambda) &
+      & bind(C, name='musb200_set_species') result(rc)
+      import :: c_int, c_double
+      integer(c_int), value :: level, relax_id, variant
+      real(c_double), value :: diff_coeff, lambda
+      integer(c_int) :: rc
+    end function
+    function musb200_set_transport_velocity(level, nElems, vel, uniform) &
+      & bind(C, name='musb200_set_transport_velocity') result(rc)
+      import :: c_int, c_double
+      integer(c_int), value :: level, nElems, uniform
+      real(c_double) :: vel(*)
+      integer(c_int) :: rc
+    end function
+    function musb200_pdf_serialize(nElems, treeID, levelPointer, buffer) &
+      & bind(C, name='musb200_pdf_serialize') result(rc)
+      import :: c_int, c_int32_t, c_int64_t, c_double
+      integer(c_int), value :: nElems
+      integer(c_int64_t) :: treeID(*)
+      integer(c_int32_t) :: levelPointer(*)
+      real(c_double) :: buffer(*)
+      integer(c_int) :: rc
+    end function
+    function musb200_pdf_unserialize(nElems, treeID, levelPointer, buffer) &
+      & bind(C, name='musb200_pdf_unserialize') result(rc)
+      import :: c_int, c_int32_t, c_int64_t, c_double
+      integer(c_int), value :: nElems
+      integer(c_int64_t) :: treeID(*)
+      integer(c_int32_t) :: levelPointer(*)
+      real(c_double) :: buffer(*)
+      integer(c_int) :: rc
+    end function
+    function musb200_p2p_export(level, blob) bind(C, name='musb200_p2p_export') result(rc)
+      import :: c_int, c_char
+      integer(c_int), value :: level
+      character(kind=c_char) :: blob(*)
+      integer(c_int) :: rc
+    end function
+    function musb200_p2p_connect(level, nProcs, proc, blobs, nVals, remotePos) &
+      & bind(C, name='musb200_p2p_connect') result(rc)
+      import :: c_int, c_int32_t, c_char
+      integer(c_int), value :: level, nProcs
+      integer(c_int32_t) :: proc(*), nVals(*), remotePos(*)
+      character(kind=c_char) :: blobs(*)
       integer(c_int) :: rc
     end function
     function musb200_compute_host(relax_id, kind_id, QQ, inState, outState, auxField, neigh, &
@@ -290,6 +369,8 @@ contains
       select case (trim(bc%BC_kind))
       case ('wall');                kind = 0
       case ('velocity_bounceback'); kind = 1
+      case ('pressure_antibounceback'); kind = 2
+      case ('pressure_expol');      kind = 3
       case default
         call tem_abort('boundary kind "'//trim(bc%BC_kind)//'" is outside the B200 hot path')
       end select
@@ -303,8 +384,169 @@ contains
           &      bc%inletUbbQVal(iLevel)%outPos, bc%inletUbbQVal(iLevel)%posInBuffer,        &
           &      bc%inletUbbQVal(iLevel)%iDir), 'bc_register')
       end if
+      if (kind >= 2) then
+        ! boundaries reading neighbours along the inward normal (mus_bc_header_module.fpp:1036-1060)
+        associate(gbc => scheme%globBC(iBnd)%elemLvl(iLevel))
+          call chk(musb200_bc_register_elems(int(iLevel, c_int), int(iBnd, c_int),           &
+            &      int(gbc%nElems, c_int), gbc%elem%val, gbc%posInBcElemBuf%val,             &
+            &      gbc%normalInd, int(bc%nNeighs, c_int), bc%neigh(iLevel)%posInState,       &
+            &      bc%outletExpol(iLevel)%iElem), 'bc_register_elems')
+        end associate
+      end if
     end associate
   end subroutine upload_bc
+
+  !> ghost interpolation: flatten depFromFiner / depFromCoarser of the target level into the CSR
+  !! lists the library takes (tem_construction_module.f90:160-276; least-square matrices
+  !! tem_matrix_module.fpp:75-96).  direction 0: fillMineFromFiner, 1: fillFinerFromMe(order)
+  subroutine mus_b200_upload_intp(scheme, iLevel)
+    type(mus_scheme_type), intent(in) :: scheme
+    integer, intent(in) :: iLevel    !< TARGET level
+    integer :: iOrder
+    associate(ld => scheme%levelDesc(iLevel), intp => scheme%intp)
+      if (ld%intpFromFiner%nVals > 0) call one(ld%intpFromFiner%val, ld%intpFromFiner%nVals, &
+        &                                     0_c_int, 0_c_int, .true.)
+      if (allocated(ld%intpFromCoarser)) then
+        do iOrder = 0, intp%config%order
+          if (ld%intpFromCoarser(iOrder)%nVals > 0) &
+            & call one(ld%intpFromCoarser(iOrder)%val, ld%intpFromCoarser(iOrder)%nVals, &
+            &          1_c_int, int(iOrder, c_int), .false.)
+        end do
+      end if
+      ! fluid%viscKine%dataOnLvl(iLevel)%val: target viscosity for the f_neq rescaling
+      call chk(musb200_set_viscosity(int(iLevel, c_int),                                  &
+        &      scheme%field(1)%fieldProp%fluid%viscKine%dataOnLvl(iLevel)%val, 0.0_c_double), 'viscosity')
+    end associate
+  contains
+    subroutine one(list, nTargets, direction, order, fromFiner)
+      integer, intent(in) :: list(:), nTargets
+      integer(c_int), intent(in) :: direction, order
+      logical, intent(in) :: fromFiner
+      integer(c_int32_t), allocatable :: tgt(:), off(:), src(:), pim(:), moff(:)
+      real(c_double), allocatable :: wgt(:), mats(:), coord(:)
+      integer :: i, k, n, nMat, nTot, offs
+      associate(ld => scheme%levelDesc(iLevel))
+        allocate(tgt(nTargets), off(nTargets+1), pim(nTargets), coord(3*nTargets))
+        n = 0
+        do i = 1, nTargets
+          if (fromFiner) then
+            n = n + ld%depFromFiner(list(i))%elem%nVals
+          else
+            n = n + ld%depFromCoarser(list(i))%elem%nVals
+          end if
+        end do
+        allocate(src(n), wgt(n))
+        n = 0; off(1) = 0
+        do i = 1, nTargets
+          if (fromFiner) then
+            associate(dep => ld%depFromFiner(list(i)))
+              tgt(i) = ld%offset(1, 3) + list(i)      ! eT_ghostFromFiner
+              do k = 1, dep%elem%nVals
+                src(n+k) = dep%elem%val(k); wgt(n+k) = 1.0_c_double / dep%elem%nVals
+              end do
+              n = n + dep%elem%nVals; pim(i) = 0; coord(3*i-2:3*i) = 0.0_c_double
+            end associate
+          else
+            associate(dep => ld%depFromCoarser(list(i)))
+              tgt(i) = ld%offset(1, 2) + list(i)      ! eT_ghostFromCoarser
+              do k = 1, dep%elem%nVals
+                src(n+k) = dep%elem%val(k)
+                if (allocated(dep%weight)) wgt(n+k) = dep%weight(k)
+              end do
+              n = n + dep%elem%nVals; pim(i) = dep%posInIntpMatLSF; coord(3*i-2:3*i) = dep%coord
+            end associate
+          end if
+          off(i+1) = n
+        end do
+        nMat = 0; nTot = 0
+        if (.not. fromFiner .and. order > 0) then
+          associate(lsf => scheme%intp%fillFinerFromME(order)%intpMat_forLSF)
+            nMat = lsf%matArray%nVals
+            allocate(moff(nMat+1)); moff(1) = 0
+            do i = 1, nMat
+              moff(i+1) = moff(i) + size(lsf%matArray%val(i)%A)
+            end do
+            allocate(mats(moff(nMat+1)))
+            do i = 1, nMat      ! row-major (nCoeffs, nSources) as the kernels read it
+              offs = moff(i)
+              mats(offs+1:moff(i+1)) = reshape(transpose(lsf%matArray%val(i)%A), [size(lsf%matArray%val(i)%A)])
+            end do
+          end associate
+        else
+          allocate(moff(1), mats(1)); moff(1) = 0
+        end if
+        call chk(musb200_intp_register(int(iLevel, c_int), direction, order, int(nTargets, c_int), &
+          &      tgt, off, src, wgt, pim, int(nMat, c_int), moff, mats, coord), 'intp_register')
+      end associate
+    end subroutine one
+  end subroutine mus_b200_upload_intp
+
+  !> source = { force = ... }: evaluated by the host exactly as applySrc_force does
+  !! (get_valOfIndex + division by fac%body_force), handed over in lattice units; call again
+  !! before a step whose force differs (mus_update_sourceVars position of do_fast_singleLevel)
+  subroutine mus_b200_set_force(iLevel, order, nElems, posInTotal, forceLattice)
+    integer, intent(in) :: iLevel, order, nElems
+    integer, intent(in) :: posInTotal(:)
+    real(kind=rk), intent(in) :: forceLattice(:)     !< (iElem-1)*3 + 1:3
+    call chk(musb200_source_force(int(iLevel, c_int), int(order, c_int), int(nElems, c_int), &
+      &      posInTotal, forceLattice, 0_c_int), 'source_force')
+  end subroutine mus_b200_set_force
+
+  !> peer-memory halo exchange among the ranks of one node: all-gather the export blobs and ship
+  !! every recv position list to the rank that sends into it (include/musb200.h, p2p section)
+  subroutine mus_b200_p2p_connect(iLevel, send, recv, comm)
+    use mpi
+    integer, intent(in) :: iLevel, comm
+    type(tem_communication_type), intent(in) :: send, recv
+    character(kind=c_char), allocatable :: blob(:), allBlobs(:), peerBlobs(:)
+    integer(c_int32_t), allocatable :: proc(:), nVals(:), remotePos(:)
+    integer, allocatable :: req(:)
+    integer :: iProc, nRanks, iError, n, off
+    call mpi_comm_size(comm, nRanks, iError)
+    allocate(blob(256), allBlobs(256*nRanks), peerBlobs(256*max(1, send%nProcs)))
+    call chk(musb200_p2p_export(int(iLevel, c_int), blob), 'p2p_export')
+    call mpi_allgather(blob, 256, mpi_character, allBlobs, 256, mpi_character, comm, iError)
+    allocate(proc(send%nProcs), nVals(send%nProcs), req(send%nProcs + recv%nProcs))
+    n = 0
+    do iProc = 1, send%nProcs
+      proc(iProc) = send%proc(iProc); nVals(iProc) = send%buf_real(iProc)%nVals
+      n = n + nVals(iProc)
+      peerBlobs(256*(iProc-1)+1:256*iProc) = allBlobs(256*send%proc(iProc)+1:256*(send%proc(iProc)+1))
+    end do
+    allocate(remotePos(max(1, n)))
+    off = 0
+    do iProc = 1, send%nProcs       ! the receiver's list for my message
+      call mpi_irecv(remotePos(off+1), nVals(iProc), mpi_integer, send%proc(iProc), 4200 + iLevel, &
+        &            comm, req(iProc), iError)
+      off = off + nVals(iProc)
+    end do
+    do iProc = 1, recv%nProcs       ! my recv list goes to its sender
+      call mpi_isend(recv%buf_real(iProc)%pos, recv%buf_real(iProc)%nVals, mpi_integer, &
+        &            recv%proc(iProc), 4200 + iLevel, comm, req(send%nProcs + iProc), iError)
+    end do
+    call mpi_waitall(size(req), req, mpi_statuses_ignore, iError)
+    call chk(musb200_p2p_connect(int(iLevel, c_int), int(send%nProcs, c_int), proc, peerBlobs, &
+      &      nVals, remotePos), 'p2p_connect')
+    call mpi_barrier(comm, iError)
+  end subroutine mus_b200_p2p_connect
+
+  !> drop-ins of mus_pdf_serialize / mus_pdf_unserialize (mus_buffer_module.fpp:80-190): the
+  !! restart chunk is gathered from / scattered to the device state in treeID order
+  subroutine mus_b200_pdf_serialize(treeID, levelPointer, nElems, buffer)
+    integer, intent(in) :: nElems
+    integer(kind=long_k), intent(in) :: treeID(nElems)
+    integer, intent(in) :: levelPointer(nElems)
+    real(kind=rk), intent(inout) :: buffer(:)
+    call chk(musb200_pdf_serialize(int(nElems, c_int), treeID, levelPointer, buffer), 'pdf_serialize')
+  end subroutine mus_b200_pdf_serialize
+
+  subroutine mus_b200_pdf_unserialize(treeID, levelPointer, nElems, buffer)
+    integer, intent(in) :: nElems
+    integer(kind=long_k), intent(in) :: treeID(nElems)
+    integer, intent(in) :: levelPointer(nElems)
+    real(kind=rk), intent(in) :: buffer(:)
+    call chk(musb200_pdf_unserialize(int(nElems, c_int), treeID, levelPointer, buffer), 'pdf_unserialize')
+  end subroutine mus_b200_pdf_unserialize
 
   !> control routine: one C call per coarse cycle instead of steps 1-9 of do_fast_singleLevel
   !! (registered in mus_init_control for control_routine = 'b200')

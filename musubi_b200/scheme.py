@@ -252,6 +252,25 @@ class Scheme:
         v = np.ascontiguousarray(vals, dtype=np.float64)
         check(lib.musb200_bc_set_values(level, bc_id, v.size, v.ctypes.data))
 
+    # -- restart: mus_pdf_serialize / mus_pdf_unserialize ---------------------------
+    def pdf_serialize(self, treeID, levelPointer):
+        """state(:, nNext) of the chunk's elements in treeID order, QQ values per element"""
+        self._bind()
+        t = np.ascontiguousarray(treeID, dtype=np.int64)
+        lp = np.ascontiguousarray(levelPointer, dtype=np.int32)
+        buf = np.empty(t.size * self.QQ)
+        check(lib.musb200_pdf_serialize(t.size, ptr(t, P_I64), ptr(lp, P_I32), ptr(buf, P_DBL)))
+        return buf
+
+    def pdf_unserialize(self, treeID, levelPointer, buffer):
+        self._bind()
+        t = np.ascontiguousarray(treeID, dtype=np.int64)
+        lp = np.ascontiguousarray(levelPointer, dtype=np.int32)
+        b = np.ascontiguousarray(buffer, dtype=np.float64)
+        if b.size != t.size * self.QQ:
+            raise ValueError("restart buffer: QQ values per element expected")
+        check(lib.musb200_pdf_unserialize(t.size, ptr(t, P_I64), ptr(lp, P_I32), ptr(b, P_DBL)))
+
     # -- peer-memory halo exchange ------------------------------------------------
     def p2p_connect(self, dist, level=None):
         """set-up of the peer-memory halo exchange over a torch.distributed (gloo) group: the

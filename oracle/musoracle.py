@@ -595,6 +595,49 @@ class Scheme:
         self.omega_uniform = float(omega)
 
 
+def level_of(treeID):
+    """tem_LevelOf: the first treeID of level L is (8^L - 1) / 7"""
+    level, first, count = 0, 0, 1
+    while treeID >= first + count:
+        first, count, level = first + count, count * 8, level + 1
+    return level
+
+
+def pdf_serialize(schemes, treeID, levelPointer):
+    """mus_pdf_serialize (mus_buffer_module.fpp:80-137): buffer of a chunk of the global treeID
+    list, QQ values of state(:, nNext) per element; schemes = {level: Scheme}"""
+    QQ = next(iter(schemes.values())).QQ
+    buf = np.empty(len(treeID) * QQ)
+    for i, (t, p) in enumerate(zip(treeID, levelPointer)):
+        s = schemes[level_of(int(t))]
+        buf[i * QQ:(i + 1) * QQ] = s.state[s.nNext][(p - 1) * QQ:p * QQ]
+    return buf
+
+
+def pdf_unserialize(schemes, treeID, levelPointer, buf):
+    """mus_pdf_unserialize (mus_buffer_module.fpp:147-190): only state(:, nNext) is set"""
+    QQ = next(iter(schemes.values())).QQ
+    for i, (t, p) in enumerate(zip(treeID, levelPointer)):
+        s = schemes[level_of(int(t))]
+        s.state[s.nNext][(p - 1) * QQ:p * QQ] = buf[i * QQ:(i + 1) * QQ]
+
+
+def global_tree(levels):
+    """the mesh's global treeID list (all fluid elements, space-filling-curve order) and the
+    levelPointer into each level's total list, from per-level descriptors with `total`"""
+    maxL = max(levels)
+    keys, ids, ptrs = [], [], []
+    for l, ld in levels.items():
+        tid = np.asarray(ld.total[:ld.nFluid], dtype=np.int64)
+        m = tid - first_id_at_level(l)
+        keys.append(m << (3 * (maxL - l)))
+        ids.append(tid)
+        ptrs.append(np.arange(1, ld.nFluid + 1, dtype=np.int32))
+    keys, ids, ptrs = np.concatenate(keys), np.concatenate(ids), np.concatenate(ptrs)
+    o = np.argsort(keys, kind="stable")
+    return ids[o], ptrs[o]
+
+
 class PassiveScalarScheme:
     """scheme kind 'passive_scalar' on one level: mus_calcAuxField_zerothMoment +
     mus_advRel_kPS_* (mus_compute_passiveScalar_module.fpp), transport velocity in lattice units."""

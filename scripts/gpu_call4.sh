@@ -1,0 +1,14 @@
+#!/bin/bash
+# 2-GPU pass: multi-rank parity tests, weak-scaled cavity (p2p / NCCL / overlap), cfg3 strong-scaled
+mkdir -p gpurun_out
+( time timeout 600 python -m pytest tests/test_multirank.py -m gpu -x -q ) > gpurun_out/pytest_multi.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/pytest_multi.log
+run() { label=$1; shift; timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29700 bench.py --gpus 2 --steps 300 --warmup 5 --no-cpu-baseline "$@" > gpurun_out/bench_2gpu_$label.log 2>&1; }
+run p2p
+run nccl --no-p2p --no-e2e
+run p2p_overlap --overlap --no-e2e
+run nccl_overlap --no-p2p --overlap --no-e2e
+run cfg3_p2p --workload cfg3 --no-e2e --steps 100
+nvidia-smi topo -m > gpurun_out/topo.log 2>&1
+tail -3 gpurun_out/pytest_multi.log
+for f in gpurun_out/bench_2gpu_*.log; do echo $f; tail -1 $f | cut -c1-200; done

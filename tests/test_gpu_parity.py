@@ -3,6 +3,8 @@ same seeded inputs.  Tolerances: north_star asks 1e-10 relative on PDFs, density
 and velocity after N steps and 1e-13 on total mass; libmusb200 is built with
 -fmad=false, so on periodic/cavity single-level cases the PDFs are expected to be
 BIT-IDENTICAL to the oracle (asserted where it holds)."""
+import ctypes
+
 import numpy as np
 import pytest
 
@@ -84,6 +86,30 @@ def test_lid_driven_cavity_matches_oracle(mb, oracle, ident, omega):
     # the lid drives a flow: momentum entered the box
     assert np.abs(aux[:, 1]).max() > 1e-3
     sch.destroy()
+
+
+@pytest.mark.parametrize("fused", [0, 1], ids=["two-phase-bcBuffer", "fused-per-element"])
+def test_velocity_bounceback_paths_agree(mb, oracle, fused):
+    """fill_bcBuffer + link loop (the reference's two phases) and the one-kernel-per-boundary form
+    of velocity_bounceback both reproduce the oracle bit for bit"""
+    from musubi_b200._lib import check, lib
+    check(lib.musb200_set_fused_bc(fused))
+    try:
+        ident = {"kind": "fluid", "relaxation": "trt", "layout": "d3q19"}
+        level, nsteps = 4, 60
+        ld, old, ref, sch = make_pair(mb, oracle, level, ident, 1.7, kind="cavity", ic="rest",
+                                      lambda_=3.0 / 16.0)
+        nl = ctypes.c_longlong()
+        check(lib.musb200_timers_reset())
+        sch.do_computation(nsteps)
+        check(lib.musb200_launch_count(ctypes.byref(nl)))
+        assert nl.value == nsteps * (2 if fused else 3)     # BC kernels + sweep per step
+        ref.run(nsteps)
+        n = ld.nFluid * ld.QQ
+        assert np.array_equal(sch.download_state(level)[:n], ref.state[ref.nNext][:n])
+        sch.destroy()
+    finally:
+        check(lib.musb200_set_fused_bc(1))
 
 
 CHANNEL = [
