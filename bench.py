@@ -192,8 +192,8 @@ def run_multilevel(args, wl_name, wl):
     W, K = max(3, args.warmup), max(1, args.steps)
     mb.mus_init(0, 1, int(os.environ.get("LOCAL_RANK", "0")))
     t_setup = time.perf_counter()
-    minL = args.level or wl["level"]
-    scale = 2 ** (minL - wl["level"])
+    minL = args.level or WORKLOADS[wl_name]["level"]
+    scale = 2.0 ** (minL - WORKLOADS[wl_name]["level"])      # boxes / cylinder are given at the base level
     boxes = [(int(lo * scale), int(hi * scale)) for lo, hi in wl["boxes"]]
     cyl = tuple(c * scale for c in wl["cylinder"][:3]) + tuple(int(c * scale) for c in wl["cylinder"][3:])
     lv, intp = tm.build_multilevel(minL, boxes, QQ=19, cylinder=cyl, intp_method="linear")

@@ -113,8 +113,15 @@ __device__ __forceinline__ double neqFac(double omegaS, double omegaT) {
   return omegaS * (1.0 - omegaT) / ((1.0 - omegaS) * omegaT);
 }
 
-// mode 0: average from finer; 1: weighted average; 2: linear; 3: quadratic
-__global__ void intpKernel(int mode, int QQ, const double *__restrict__ scratch, int nUnique,
+// MODE 0: average from finer; 1: weighted average; 2: linear; 3: quadratic.
+// One thread per (target, direction), target index fastest (coalesced stores into the ghost
+// block).  The sources are visited ONCE, in the host's order, and all polynomial coefficients
+// are accumulated side by side in registers: per coefficient the sum runs over the sources in
+// ascending order exactly as in the reference's matrix-vector product, so the bits are the same
+// as evaluating coefficient after coefficient, with a quarter (linear) or a tenth (quadratic) of
+// the gathers.
+template <int MODE>
+__global__ void __launch_bounds__(128) intpKernel(int QQ, const double *__restrict__ scratch, int nUnique,
                            int nTargets, const int32_t *__restrict__ targets,
                            const int32_t *__restrict__ srcOffset,
                            const int32_t *__restrict__ srcSlot, const double *__restrict__ weights,
@@ -132,7 +139,7 @@ __global__ void intpKernel(int mode, int QQ, const double *__restrict__ scratch,
   const double *neq = scratch + (long long)(27 + d) * nUnique;
   const double visc = tVisc ? tVisc[tgt] : tViscUniform;
   double t_eq, t_neq;
-  if (mode == 0) {
+  if (MODE == 0) {
     const double inv_n = 1.0 / (double)n;
     double a = 0.0, b = 0.0;
     for (int s = 0; s < n; ++s) {
@@ -147,7 +154,7 @@ __global__ void intpKernel(int mode, int QQ, const double *__restrict__ scratch,
     tState[(long long)d * tS + tgt] = t_eq + t_neq;
     return;
   }
-  if (mode == 1) {
+  if (MODE == 1) {
     double a = 0.0, b = 0.0;
     for (int s = 0; s < n; ++s) {
       const int u = srcSlot[s0 + s];
@@ -158,24 +165,25 @@ __global__ void intpKernel(int mode, int QQ, const double *__restrict__ scratch,
     t_eq = a;
     t_neq = b;
   } else {
-    const int nCoeff = mode == 2 ? 4 : 10;
+    constexpr int nCoeff = MODE == 2 ? 4 : 10;
     const double *A = matrices + matOffset[posInMat[i]];
     const double x = coord[3 * i + 0], y = coord[3 * i + 1], z = coord[3 * i + 2];
-    double ce[10], cn[10];
-    for (int k = 0; k < nCoeff; ++k) {
-      double a = 0.0, b = 0.0;
-      for (int s = 0; s < n; ++s) {
-        const int u = srcSlot[s0 + s];
+    double ce[nCoeff], cn[nCoeff];
+#pragma unroll
+    for (int k = 0; k < nCoeff; ++k) { ce[k] = 0.0; cn[k] = 0.0; }
+    for (int s = 0; s < n; ++s) {
+      const int u = srcSlot[s0 + s];
+      const double e = eq[u], ne = neq[u];
+#pragma unroll
+      for (int k = 0; k < nCoeff; ++k) {
         const double m = A[(long long)k * n + s];
-        a = a + m * eq[u];
-        b = b + m * neq[u];
+        ce[k] = ce[k] + m * e;
+        cn[k] = cn[k] + m * ne;
       }
-      ce[k] = a;
-      cn[k] = b;
     }
     t_eq = ce[0] + ce[1] * x + ce[2] * y + ce[3] * z;
     t_neq = cn[0] + cn[1] * x + cn[2] * y + cn[3] * z;
-    if (mode == 3) {
+    if (MODE == 3) {
       t_eq = t_eq + ce[4] * x * x + ce[5] * y * y + ce[6] * z * z + ce[7] * x * y + ce[8] * y * z +
              ce[9] * z * x;
       t_neq = t_neq + cn[4] * x * x + cn[5] * y * y + cn[6] * z * z + cn[7] * x * y + cn[8] * y * z +
@@ -186,6 +194,57 @@ __global__ void intpKernel(int mode, int QQ, const double *__restrict__ scratch,
   const double fac = 0.5 * neqFac(cOmega, fOmega);  // getNonEqFac_intp_coarse_to_fine
   t_neq = t_neq * fac;
   tState[(long long)d * tS + tgt] = t_neq + t_eq;
+}
+
+// fillMyGhostsFromFiner_avg_feq_fneq without the scratch pass: one thread per coarse ghost walks
+// its (at most 8, Morton-contiguous) children, forms f_eq(rho, u from auxField) and f - f_eq of
+// each and accumulates both per direction in the children's order -- the sums of intpKernel<0>.
+template <int QQ>
+__global__ void __launch_bounds__(64) fromFinerFusedKernel(int incomp, const double *__restrict__ sState,
+                                     const double *__restrict__ sAux, long long sS,
+                                     const int32_t *__restrict__ uniqueSrc, int nTargets,
+                                     const int32_t *__restrict__ targets,
+                                     const int32_t *__restrict__ srcOffset,
+                                     const int32_t *__restrict__ srcSlot,
+                                     double *__restrict__ tState, long long tS,
+                                     const double *__restrict__ tVisc, double tViscUniform) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nTargets) return;
+  const int tgt = targets[i] - 1;
+  const int s0 = srcOffset[i], n = srcOffset[i + 1] - s0;
+  double a[QQ], b[QQ];
+#pragma unroll
+  for (int q = 0; q < QQ; ++q) { a[q] = 0.0; b[q] = 0.0; }
+  for (int s = 0; s < n; ++s) {
+    const int e = uniqueSrc[srcSlot[s0 + s]] - 1;
+    const double rho = sAux[e], vx = sAux[sS + e], vy = sAux[2 * sS + e], vz = sAux[3 * sS + e];
+    double feq[QQ];
+    if (QQ == 19) {
+      double(&g)[19] = reinterpret_cast<double(&)[19]>(feq);
+      if (incomp) pdfEqIncompD3Q19(rho, vx, vy, vz, g);
+      else pdfEqD3Q19(rho, vx, vy, vz, g);
+    } else {
+      double(&g)[27] = reinterpret_cast<double(&)[27]>(feq);
+      if (incomp) pdfEqIncompD3Q27(rho, vx, vy, vz, g);
+      else pdfEqD3Q27(rho, vx, vy, vz, g);
+    }
+#pragma unroll
+    for (int q = 0; q < QQ; ++q) {
+      const double f = sState[(long long)q * sS + e];
+      a[q] = a[q] + feq[q];
+      b[q] = b[q] + (f - feq[q]);
+    }
+  }
+  const double visc = tVisc ? tVisc[tgt] : tViscUniform;
+  const double inv_n = 1.0 / (double)n;
+  const double fOmega = omegaFromVisc(2.0 * visc), cOmega = omegaFromVisc(visc);
+  const double fac = 2.0 * neqFac(fOmega, cOmega);  // getNonEqFac_intp_fine_to_coarse
+#pragma unroll
+  for (int q = 0; q < QQ; ++q) {
+    const double t_eq = a[q] * inv_n;
+    const double t_neq = b[q] * inv_n * fac;
+    tState[(long long)q * tS + tgt] = t_eq + t_neq;
+  }
 }
 
 // fillArbiMyGhostsFromFiner_avg for the 4 auxField scalars
@@ -212,6 +271,19 @@ int launchIntp(const IntpArgs &a, const IntpSet &set, bool fromFiner, cudaStream
   if (nLaunch) *nLaunch = 0;
   if (set.nTargets == 0) return 0;
   const int B = 128;
+  if (fromFiner) {
+    if (a.QQ == 19)
+      fromFinerFusedKernel<19><<<divUp(set.nTargets, 64), 64, 0, st>>>(
+          a.incomp, a.sState, a.sAux, a.sS, set.uniqueSrc, set.nTargets, set.targets, set.srcOffset,
+          set.srcSlot, a.tState, a.tS, a.tVisc, a.tViscUniform);
+    else
+      fromFinerFusedKernel<27><<<divUp(set.nTargets, 64), 64, 0, st>>>(
+          a.incomp, a.sState, a.sAux, a.sS, set.uniqueSrc, set.nTargets, set.targets, set.srcOffset,
+          set.srcSlot, a.tState, a.tS, a.tVisc, a.tViscUniform);
+    MUSB_CUDA(cudaGetLastError());
+    if (nLaunch) *nLaunch = 1;
+    return 0;
+  }
   if (a.QQ == 19)
     eqNeqKernel<19><<<divUp(set.nUnique, B), B, 0, st>>>(a.incomp, a.sState, a.sAux, a.sS,
                                                          set.uniqueSrc, set.nUnique, set.scratch);
@@ -219,12 +291,19 @@ int launchIntp(const IntpArgs &a, const IntpSet &set, bool fromFiner, cudaStream
     eqNeqKernel<27><<<divUp(set.nUnique, B), B, 0, st>>>(a.incomp, a.sState, a.sAux, a.sS,
                                                          set.uniqueSrc, set.nUnique, set.scratch);
   MUSB_CUDA(cudaGetLastError());
-  const int mode = fromFiner ? 0 : 1 + set.order;
+  const int mode = 1 + set.order;
   if (mode == 1 && !set.weights) return setError(1, "weighted-average set without weights");
-  intpKernel<<<divUp((long long)set.nTargets * a.QQ, B), B, 0, st>>>(
-      mode, a.QQ, set.scratch, set.nUnique, set.nTargets, set.targets, set.srcOffset, set.srcSlot,
-      set.weights, set.posInMat, set.matOffset, set.matrices, set.coord, a.tState, a.tS, a.tVisc,
-      a.tViscUniform);
+  const int grid = divUp((long long)set.nTargets * a.QQ, B);
+#define MUSB_INTP(M)                                                                              \
+  intpKernel<M><<<grid, B, 0, st>>>(a.QQ, set.scratch, set.nUnique, set.nTargets, set.targets,    \
+                                    set.srcOffset, set.srcSlot, set.weights, set.posInMat,        \
+                                    set.matOffset, set.matrices, set.coord, a.tState, a.tS,       \
+                                    a.tVisc, a.tViscUniform)
+  if (mode == 1) MUSB_INTP(1);
+  else if (mode == 2) MUSB_INTP(2);
+  else if (mode == 3) MUSB_INTP(3);
+  else return setError(1, "interpolation order must be 0, 1 or 2");
+#undef MUSB_INTP
   MUSB_CUDA(cudaGetLastError());
   if (nLaunch) *nLaunch = 2;
   return 0;

@@ -48,7 +48,7 @@ def mbgpu():
 def test_device_restart_dump_equals_reference_order_multilevel(mbgpu, oracle):
     """two-level mesh, a few cycles, dump in two chunks: bytes equal the oracle's serialisation;
     then restore into a fresh scheme and continue: identical to the uninterrupted run."""
-    from tests.test_multilevel import build
+    from test_multilevel import build
     mb, mo, QQ = mbgpu, oracle, 19
     lv, intp, tables, ms = build(mo, 4, [(5, 11)], QQ, "linear")
     ident = {"kind": "fluid", "relaxation": "bgk", "layout": "d3q19"}
