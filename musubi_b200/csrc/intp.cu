@@ -9,8 +9,8 @@ namespace musb200 {
 void IntpSet::release() {
   auto fr = [](auto *&p) { if (p) cudaFree(p); p = nullptr; };
   fr(targets); fr(srcOffset); fr(srcSlot); fr(uniqueSrc); fr(weights); fr(posInMat); fr(matOffset);
-  fr(matrices); fr(coord); fr(scratch);
-  nTargets = 0; nMatrices = 0; nUnique = 0;
+  fr(matrices); fr(coord); fr(scratch); fr(sel7); fr(sel8); fr(selRest);
+  nTargets = 0; nMatrices = 0; nUnique = 0; n7 = 0; n8 = 0; nRest = 0;
 }
 
 IntpSet &IntpSet::operator=(IntpSet &&o) noexcept {
@@ -20,6 +20,8 @@ IntpSet &IntpSet::operator=(IntpSet &&o) noexcept {
     targets = o.targets; srcOffset = o.srcOffset; srcSlot = o.srcSlot; uniqueSrc = o.uniqueSrc;
     weights = o.weights; posInMat = o.posInMat; matOffset = o.matOffset; matrices = o.matrices;
     coord = o.coord; scratch = o.scratch;
+    sel7 = o.sel7; sel8 = o.sel8; selRest = o.selRest; n7 = o.n7; n8 = o.n8; nRest = o.nRest;
+    o.sel7 = nullptr; o.sel8 = nullptr; o.selRest = nullptr; o.n7 = 0; o.n8 = 0; o.nRest = 0;
     o.targets = nullptr; o.srcOffset = nullptr; o.srcSlot = nullptr; o.uniqueSrc = nullptr;
     o.weights = nullptr; o.posInMat = nullptr; o.matOffset = nullptr; o.matrices = nullptr;
     o.coord = nullptr; o.scratch = nullptr;
@@ -69,6 +71,17 @@ int registerIntp(IntpSet &set, int order, int nTargets, const int32_t *targetLis
     rc |= up(set.matOffset, matOffset, (size_t)nMatrices + 1, st);
     rc |= up(set.matrices, matrices, (size_t)matOffset[nMatrices], st);
     rc |= up(set.coord, childCoord, (size_t)3 * nTargets, st);
+  }
+  if (order == 1) {
+    std::vector<int32_t> s7, s8, sr;
+    for (int i = 0; i < nTargets; ++i) {
+      const int n = srcOffset[i + 1] - srcOffset[i];
+      (n == 7 ? s7 : (n == 8 ? s8 : sr)).push_back(i);
+    }
+    rc |= up(set.sel7, s7.data(), s7.size(), st);
+    rc |= up(set.sel8, s8.data(), s8.size(), st);
+    rc |= up(set.selRest, sr.data(), sr.size(), st);
+    set.n7 = (int)s7.size(); set.n8 = (int)s8.size(); set.nRest = (int)sr.size();
   }
   if (rc) return rc;
   set.nTargets = nTargets;
@@ -122,7 +135,8 @@ __device__ __forceinline__ double neqFac(double omegaS, double omegaT) {
 // the gathers.
 template <int MODE>
 __global__ void __launch_bounds__(128) intpKernel(int QQ, const double *__restrict__ scratch, int nUnique,
-                           int nTargets, const int32_t *__restrict__ targets,
+                           int nTargets, const int32_t *__restrict__ sel,
+                           const int32_t *__restrict__ targets,
                            const int32_t *__restrict__ srcOffset,
                            const int32_t *__restrict__ srcSlot, const double *__restrict__ weights,
                            const int32_t *__restrict__ posInMat,
@@ -132,7 +146,8 @@ __global__ void __launch_bounds__(128) intpKernel(int QQ, const double *__restri
                            const double *__restrict__ tVisc, double tViscUniform) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nTargets * QQ) return;
-  const int i = idx % nTargets, d = idx / nTargets;
+  const int d = idx / nTargets;
+  const int i = sel ? sel[idx % nTargets] : idx % nTargets;   // nTargets = list length when sel
   const int tgt = targets[i] - 1;
   const int s0 = srcOffset[i], n = srcOffset[i + 1] - s0;
   const double *eq = scratch + (long long)d * nUnique;
@@ -194,6 +209,56 @@ __global__ void __launch_bounds__(128) intpKernel(int QQ, const double *__restri
   const double fac = 0.5 * neqFac(cOmega, fOmega);  // getNonEqFac_intp_coarse_to_fine
   t_neq = t_neq * fac;
   tState[(long long)d * tS + tgt] = t_neq + t_eq;
+}
+
+// Linear interpolation for targets with exactly NS sources: one thread per target keeps the
+// source slots and the 4 x NS least-square matrix in registers and walks the directions, so the
+// list and matrix loads are paid once per target instead of once per (target, direction).  Per
+// (target, direction) the arithmetic is the sequence of intpKernel<2>.
+template <int NS>
+__global__ void __launch_bounds__(128) intpLinearPerTargetKernel(
+    int QQ, const double *__restrict__ scratch, int nUnique, int nSel, const int32_t *__restrict__ sel,
+    const int32_t *__restrict__ targets, const int32_t *__restrict__ srcOffset,
+    const int32_t *__restrict__ srcSlot, const int32_t *__restrict__ posInMat,
+    const int32_t *__restrict__ matOffset, const double *__restrict__ matrices,
+    const double *__restrict__ coord, double *__restrict__ tState, long long tS,
+    const double *__restrict__ tVisc, double tViscUniform) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nSel) return;
+  const int i = sel[t];
+  const int tgt = targets[i] - 1;
+  const int s0 = srcOffset[i];
+  int u[NS];
+  double A[4][NS];
+  const double *Am = matrices + matOffset[posInMat[i]];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) u[s] = srcSlot[s0 + s];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int s = 0; s < NS; ++s) A[k][s] = Am[k * NS + s];
+  const double x = coord[3 * i + 0], y = coord[3 * i + 1], z = coord[3 * i + 2];
+  const double visc = tVisc ? tVisc[tgt] : tViscUniform;
+  const double fOmega = omegaFromVisc(visc), cOmega = omegaFromVisc(0.5 * visc);
+  const double fac = 0.5 * neqFac(cOmega, fOmega);  // getNonEqFac_intp_coarse_to_fine
+  for (int d = 0; d < QQ; ++d) {
+    const double *eq = scratch + (long long)d * nUnique;
+    const double *neq = scratch + (long long)(27 + d) * nUnique;
+    double ce[4] = {0.0, 0.0, 0.0, 0.0}, cn[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const double e = eq[u[s]], ne = neq[u[s]];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        ce[k] = ce[k] + A[k][s] * e;
+        cn[k] = cn[k] + A[k][s] * ne;
+      }
+    }
+    const double t_eq = ce[0] + ce[1] * x + ce[2] * y + ce[3] * z;
+    double t_neq = cn[0] + cn[1] * x + cn[2] * y + cn[3] * z;
+    t_neq = t_neq * fac;
+    tState[(long long)d * tS + tgt] = t_neq + t_eq;
+  }
 }
 
 // fillMyGhostsFromFiner_avg_feq_fneq without the scratch pass: one thread per coarse ghost walks
@@ -293,19 +358,28 @@ int launchIntp(const IntpArgs &a, const IntpSet &set, bool fromFiner, cudaStream
   MUSB_CUDA(cudaGetLastError());
   const int mode = 1 + set.order;
   if (mode == 1 && !set.weights) return setError(1, "weighted-average set without weights");
-  const int grid = divUp((long long)set.nTargets * a.QQ, B);
-#define MUSB_INTP(M)                                                                              \
-  intpKernel<M><<<grid, B, 0, st>>>(a.QQ, set.scratch, set.nUnique, set.nTargets, set.targets,    \
-                                    set.srcOffset, set.srcSlot, set.weights, set.posInMat,        \
-                                    set.matOffset, set.matrices, set.coord, a.tState, a.tS,       \
-                                    a.tVisc, a.tViscUniform)
-  if (mode == 1) MUSB_INTP(1);
-  else if (mode == 2) MUSB_INTP(2);
-  else if (mode == 3) MUSB_INTP(3);
+  int launches = 1;
+#define MUSB_INTP(M, N, SEL)                                                                      \
+  intpKernel<M><<<divUp((long long)(N) * a.QQ, B), B, 0, st>>>(                                   \
+      a.QQ, set.scratch, set.nUnique, (N), (SEL), set.targets, set.srcOffset, set.srcSlot,        \
+      set.weights, set.posInMat, set.matOffset, set.matrices, set.coord, a.tState, a.tS, a.tVisc, \
+      a.tViscUniform)
+#define MUSB_INTP_PT(NS, N, SEL)                                                                  \
+  intpLinearPerTargetKernel<NS><<<divUp((N), B), B, 0, st>>>(                                     \
+      a.QQ, set.scratch, set.nUnique, (N), (SEL), set.targets, set.srcOffset, set.srcSlot,        \
+      set.posInMat, set.matOffset, set.matrices, set.coord, a.tState, a.tS, a.tVisc,              \
+      a.tViscUniform)
+  if (mode == 1) { MUSB_INTP(1, set.nTargets, nullptr); ++launches; }
+  else if (mode == 2) {
+    if (set.n7) { MUSB_INTP_PT(7, set.n7, set.sel7); ++launches; }
+    if (set.n8) { MUSB_INTP_PT(8, set.n8, set.sel8); ++launches; }
+    if (set.nRest) { MUSB_INTP(2, set.nRest, set.selRest); ++launches; }
+  } else if (mode == 3) { MUSB_INTP(3, set.nTargets, nullptr); ++launches; }
   else return setError(1, "interpolation order must be 0, 1 or 2");
 #undef MUSB_INTP
+#undef MUSB_INTP_PT
   MUSB_CUDA(cudaGetLastError());
-  if (nLaunch) *nLaunch = 2;
+  if (nLaunch) *nLaunch = launches;
   return 0;
 }
 

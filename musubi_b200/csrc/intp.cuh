@@ -35,6 +35,11 @@ struct IntpSet {
   double *matrices = nullptr;    // concatenated row-major (nCoeff x nSrc)
   double *coord = nullptr;       // [nTargets][3]
   double *scratch = nullptr;     // [2][QQmax=27][nUnique]  f_eq | f_neq
+  // linear sets: targets with exactly 7 / 8 sources (the weighted-average stencil of D3Q19 /
+  // D3Q27) go through a kernel that keeps the least-square matrix in registers; the rest
+  // through the generic one
+  int32_t *sel7 = nullptr, *sel8 = nullptr, *selRest = nullptr;
+  int n7 = 0, n8 = 0, nRest = 0;
   void release();
   ~IntpSet() { release(); }
   IntpSet() = default;
