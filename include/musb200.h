@@ -244,6 +244,11 @@ int musb200_set_aux_every_step(int flag);
  * results; the split sweep costs more than the exchange it hides at 256^3 elements per GPU
  * (profiles/r01_multi_gpu.md), so it is opt-in. */
 int musb200_set_overlap(int flag);
+/* 1 (default): a single-rank musb200_step call of 8 or more coarse cycles without per-stage
+ * timers replays a CUDA graph of two coarse cycles (captured on first use, re-captured after
+ * any call that changes a level); 0: every kernel is launched directly.  Same kernels, same
+ * order, same results. */
+int musb200_set_graphs(int flag);
 /* 1 (default): when the only non-wall boundaries of a level are velocity_bounceback ones whose
  * links stay inside their own elements (the lists mus_set_inletUbb builds), fill_bcBuffer and the
  * link loop run as ONE kernel per boundary, one thread per boundary element, without the

@@ -67,6 +67,7 @@ SIGNATURES = {
     "musb200_timers_reset": [],
     "musb200_launch_count": [P_LL],
     "musb200_set_overlap": [c_int],
+    "musb200_set_graphs": [c_int],
     "musb200_set_fused_bc": [c_int],
     "musb200_p2p_export": [c_int, c_void_p],
     "musb200_p2p_connect": [c_int, c_int, P_I32, c_void_p, P_I32, P_I32],

@@ -196,6 +196,13 @@ struct Context {
   cudaStream_t stream = nullptr;
   cudaStream_t commStream = nullptr;   // halo exchange, high priority, overlaps the interior sweep
   cudaEvent_t evBoundary = nullptr, evComm = nullptr;
+  // CUDA graph of two coarse cycles (after two cycles every level's now/next parity is back where
+  // it started, so the captured kernel arguments are valid for every replay)
+  int useGraphs = 1;
+  unsigned long long epoch = 0, graphEpoch = 0;
+  int graphMin = -1, graphMax = -1, graphSlot = -1;
+  cudaGraphExec_t graphExec = nullptr;
+  long long graphLaunches = 0;
   int noFusedBc = 0; // musb200_set_fused_bc(0): always take the two-phase bcBuffer path
   int overlap = 0;   // measured slower than exchange-after-compute at 256^3 per GPU (profiles/)
   NcclApi *nccl = nullptr;
@@ -221,6 +228,11 @@ struct Context {
 };
 static Context g;
 
+static void dropGraph() {
+  if (g.graphExec) cudaGraphExecDestroy(g.graphExec);
+  g.graphExec = nullptr;
+}
+
 static int needReady() {
   if (!g.ready) return setError(MUSB200_ERR_STATE, "musb200_init has not been called");
   return 0;
@@ -231,6 +243,7 @@ static Level *findLevel(int level) {
 }
 #define GET_LEVEL(L, level)                                                          \
   MUSB_TRY(needReady());                                                             \
+  ++g.epoch; /* any per-level call may change what a captured step graph would replay */ \
   Level *L = findLevel(level);                                                       \
   if (!L) return setError(MUSB200_ERR_ARG, "unknown level " + std::to_string(level))
 
@@ -597,6 +610,7 @@ int musb200_init(int rank, int nranks, int local_device, const void *nccl_unique
 int musb200_finalize(void) {
   if (!g.ready) return 0;
   cudaStreamSynchronize(g.stream);
+  dropGraph();
   for (auto &m : g.levelsOf) m.clear();
   g.slot = 0;
   g.stage.release(); g.red.release(); g.flag.release();
@@ -699,11 +713,13 @@ int musb200_level_create(int level, int QQ, int nScalars, int nAuxScalars, int n
     return setError(MUSB200_ERR_CONNECTIVITY,
                     std::to_string(bad) + " neigh entries are neither a plain pull nor a bounce-back");
   g.levels()[level] = std::move(L);
+  ++g.epoch;
   return 0;
 }
 
 int musb200_level_destroy(int level) {
   MUSB_TRY(needReady());
+  ++g.epoch;
   cudaStreamSynchronize(g.stream);
   g.levels().erase(level);
   return 0;
@@ -1274,19 +1290,70 @@ int musb200_intp_register(int tgtLevel, int direction, int order, int nTargets,
 
 // ---------------------------------------------------------------------------
 int musb200_set_aux_every_step(int flag) {
+  ++g.epoch;
   g.auxEveryStep = flag ? 1 : 0;
   return 0;
+}
+
+// Long single-rank runs without per-stage timing replay a CUDA graph of two coarse cycles: the
+// stepping loop of a small or multi-level mesh is launch-bound (64^3: 19 us of kernel per 22 us
+// step; a two-level cycle is 7 launches).  Several ranks stay on direct launches: the peer-memory
+// exchange carries a running exchange number as a kernel argument.
+static int stepGraphed(int minLevel, int maxLevel, int nPairs) {
+  if (!g.graphExec || g.graphEpoch != g.epoch || g.graphMin != minLevel || g.graphMax != maxLevel ||
+      g.graphSlot != g.slot) {
+    dropGraph();
+    const long long before = g.launches;
+    const int auxSave = g.auxEveryStep;
+    cudaGraph_t graph = nullptr;
+    MUSB_CUDA(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
+    int rc = 0;
+    for (int it = 0; it < 2 && rc == 0; ++it) rc = levelStep(minLevel, minLevel, maxLevel, false);
+    cudaError_t ce = cudaStreamEndCapture(g.stream, &graph);
+    g.auxEveryStep = auxSave;
+    g.graphLaunches = g.launches - before;
+    g.launches = before;
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    MUSB_CUDA(ce);
+    ce = cudaGraphInstantiate(&g.graphExec, graph, 0);
+    cudaGraphDestroy(graph);
+    MUSB_CUDA(ce);
+    // capturing ran the host side of two cycles: every level toggled now/next an even number of
+    // times, so the indices are where they were and nothing was executed yet
+    g.graphEpoch = g.epoch; g.graphMin = minLevel; g.graphMax = maxLevel; g.graphSlot = g.slot;
+  }
+  for (int p = 0; p < nPairs; ++p) {
+    MUSB_CUDA(cudaGraphLaunch(g.graphExec, g.stream));
+    g.launches += g.graphLaunches;
+  }
+  return 0;   // two cycles leave every level's now/next parity unchanged
 }
 
 int musb200_step(int minLevel, int maxLevel, int nCoarseCycles) {
   MUSB_TRY(needReady());
   if (maxLevel < minLevel || nCoarseCycles < 0) return setError(MUSB200_ERR_ARG, "bad level range / cycles");
-  for (int it = 0; it < nCoarseCycles; ++it)
+  int it = 0;
+  if (g.useGraphs && g.nranks == 1 && !g.profiling && nCoarseCycles >= 8) {
+    // all but the last cycles (the last one materialises auxField) in pairs through the graph
+    const int nPairs = (nCoarseCycles - 1) / 2;
+    for (int l = minLevel; l <= maxLevel; ++l)
+      if (!findLevel(l)) return setError(MUSB200_ERR_ARG, "level " + std::to_string(l) + " was not created");
+    MUSB_TRY(stepGraphed(minLevel, maxLevel, nPairs));
+    it = 2 * nPairs;
+  }
+  for (; it < nCoarseCycles; ++it)
     MUSB_TRY(levelStep(minLevel, minLevel, maxLevel, it == nCoarseCycles - 1));
   return 0;
 }
 
+int musb200_set_graphs(int flag) {
+  g.useGraphs = flag ? 1 : 0;
+  if (!flag) dropGraph();
+  return 0;
+}
+
 int musb200_set_fused_bc(int flag) {
+  ++g.epoch;
   g.noFusedBc = flag ? 0 : 1;
   return 0;
 }

@@ -9,8 +9,8 @@ namespace musb200 {
 void IntpSet::release() {
   auto fr = [](auto *&p) { if (p) cudaFree(p); p = nullptr; };
   fr(targets); fr(srcOffset); fr(srcSlot); fr(uniqueSrc); fr(weights); fr(posInMat); fr(matOffset);
-  fr(matrices); fr(coord); fr(scratch); fr(sel7); fr(sel8); fr(selRest);
-  nTargets = 0; nMatrices = 0; nUnique = 0; n7 = 0; n8 = 0; nRest = 0;
+  fr(matrices); fr(coord); fr(scratch);
+  nTargets = 0; nMatrices = 0; nUnique = 0; maxSrc = 0;
 }
 
 IntpSet &IntpSet::operator=(IntpSet &&o) noexcept {
@@ -20,8 +20,7 @@ IntpSet &IntpSet::operator=(IntpSet &&o) noexcept {
     targets = o.targets; srcOffset = o.srcOffset; srcSlot = o.srcSlot; uniqueSrc = o.uniqueSrc;
     weights = o.weights; posInMat = o.posInMat; matOffset = o.matOffset; matrices = o.matrices;
     coord = o.coord; scratch = o.scratch;
-    sel7 = o.sel7; sel8 = o.sel8; selRest = o.selRest; n7 = o.n7; n8 = o.n8; nRest = o.nRest;
-    o.sel7 = nullptr; o.sel8 = nullptr; o.selRest = nullptr; o.n7 = 0; o.n8 = 0; o.nRest = 0;
+    maxSrc = o.maxSrc; o.maxSrc = 0;
     o.targets = nullptr; o.srcOffset = nullptr; o.srcSlot = nullptr; o.uniqueSrc = nullptr;
     o.weights = nullptr; o.posInMat = nullptr; o.matOffset = nullptr; o.matrices = nullptr;
     o.coord = nullptr; o.scratch = nullptr;
@@ -72,19 +71,10 @@ int registerIntp(IntpSet &set, int order, int nTargets, const int32_t *targetLis
     rc |= up(set.matrices, matrices, (size_t)matOffset[nMatrices], st);
     rc |= up(set.coord, childCoord, (size_t)3 * nTargets, st);
   }
-  if (order == 1) {
-    std::vector<int32_t> s7, s8, sr;
-    for (int i = 0; i < nTargets; ++i) {
-      const int n = srcOffset[i + 1] - srcOffset[i];
-      (n == 7 ? s7 : (n == 8 ? s8 : sr)).push_back(i);
-    }
-    rc |= up(set.sel7, s7.data(), s7.size(), st);
-    rc |= up(set.sel8, s8.data(), s8.size(), st);
-    rc |= up(set.selRest, sr.data(), sr.size(), st);
-    set.n7 = (int)s7.size(); set.n8 = (int)s8.size(); set.nRest = (int)sr.size();
-  }
   if (rc) return rc;
   set.nTargets = nTargets;
+  set.maxSrc = 0;
+  for (int i = 0; i < nTargets; ++i) set.maxSrc = std::max(set.maxSrc, srcOffset[i + 1] - srcOffset[i]);
   set.nMatrices = nMatrices;
   set.nUnique = (int)uniq.size();
   MUSB_CUDA(cudaMalloc(&set.scratch, (size_t)2 * 27 * set.nUnique * sizeof(double)));
@@ -93,31 +83,41 @@ int registerIntp(IntpSet &set, int order, int nTargets, const int32_t *targetLis
 }
 
 // ---------------------------------------------------------------------------
-template <int QQ>
-__global__ void eqNeqKernel(int incomp, const double *__restrict__ sState,
+// phase A: f_eq / f_neq of every distinct source, written source-major
+// ([u][0..QQ) = f_eq, [u][QQ..2QQ) = f_neq) through a shared-memory tile so that the global
+// stores of a CTA are one contiguous, fully coalesced run
+template <int QQ, int THREADS>
+__global__ void __launch_bounds__(THREADS) eqNeqKernel(int incomp, const double *__restrict__ sState,
                             const double *__restrict__ sAux, long long sS,
                             const int32_t *__restrict__ uniqueSrc, int nUnique,
                             double *__restrict__ scratch) {
-  const int u = blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= nUnique) return;
-  const int e = uniqueSrc[u] - 1;
-  const double rho = sAux[e], vx = sAux[sS + e], vy = sAux[2 * sS + e], vz = sAux[3 * sS + e];
-  double feq[QQ];
-  if (QQ == 19) {
-    double(&g)[19] = reinterpret_cast<double(&)[19]>(feq);
-    if (incomp) pdfEqIncompD3Q19(rho, vx, vy, vz, g);
-    else pdfEqD3Q19(rho, vx, vy, vz, g);
-  } else {
-    double(&g)[27] = reinterpret_cast<double(&)[27]>(feq);
-    if (incomp) pdfEqIncompD3Q27(rho, vx, vy, vz, g);
-    else pdfEqD3Q27(rho, vx, vy, vz, g);
-  }
+  constexpr int W = 2 * QQ, P = W + 1;       // odd pitch: conflict-free column access
+  __shared__ double tile[THREADS * P];
+  const int u = blockIdx.x * THREADS + threadIdx.x;
+  if (u < nUnique) {
+    const int e = uniqueSrc[u] - 1;
+    const double rho = sAux[e], vx = sAux[sS + e], vy = sAux[2 * sS + e], vz = sAux[3 * sS + e];
+    double feq[QQ];
+    if (QQ == 19) {
+      double(&g)[19] = reinterpret_cast<double(&)[19]>(feq);
+      if (incomp) pdfEqIncompD3Q19(rho, vx, vy, vz, g);
+      else pdfEqD3Q19(rho, vx, vy, vz, g);
+    } else {
+      double(&g)[27] = reinterpret_cast<double(&)[27]>(feq);
+      if (incomp) pdfEqIncompD3Q27(rho, vx, vy, vz, g);
+      else pdfEqD3Q27(rho, vx, vy, vz, g);
+    }
 #pragma unroll
-  for (int q = 0; q < QQ; ++q) {
-    const double f = sState[(long long)q * sS + e];
-    scratch[(long long)q * nUnique + u] = feq[q];
-    scratch[(long long)(27 + q) * nUnique + u] = f - feq[q];
+    for (int q = 0; q < QQ; ++q) {
+      const double f = sState[(long long)q * sS + e];
+      tile[threadIdx.x * P + q] = feq[q];
+      tile[threadIdx.x * P + QQ + q] = f - feq[q];
+    }
   }
+  __syncthreads();
+  const int rows = min(THREADS, nUnique - (int)blockIdx.x * THREADS);
+  double *out = scratch + (long long)blockIdx.x * THREADS * W;
+  for (int t = threadIdx.x; t < rows * W; t += THREADS) out[t] = tile[(t / W) * P + (t % W)];
 }
 
 __device__ __forceinline__ double omegaFromVisc(double v) { return 1.0 / (3.0 * v + 0.5); }
@@ -126,17 +126,19 @@ __device__ __forceinline__ double neqFac(double omegaS, double omegaT) {
   return omegaS * (1.0 - omegaT) / ((1.0 - omegaS) * omegaT);
 }
 
-// MODE 0: average from finer; 1: weighted average; 2: linear; 3: quadratic.
-// One thread per (target, direction), target index fastest (coalesced stores into the ghost
-// block).  The sources are visited ONCE, in the host's order, and all polynomial coefficients
-// are accumulated side by side in registers: per coefficient the sum runs over the sources in
-// ascending order exactly as in the reference's matrix-vector product, so the bits are the same
-// as evaluating coefficient after coefficient, with a quarter (linear) or a tenth (quadratic) of
-// the gathers.
+// MODE 1: weighted average; 2: linear; 3: quadratic (MODE 0, the average from finer, has its own
+// kernel below).  One thread per (target, direction) with the DIRECTION fastest: the lanes of a
+// warp belong to one or two targets, so the source slots and the least-square matrix are
+// warp-uniform loads (one line each, broadcast) and the f_eq / f_neq values of a source are one
+// contiguous run of the source-major scratch.  A gather touches 2-3 cache lines instead of the
+// 20-30 of a target-fastest mapping -- measured on cfg4: L1 tag throughput, not DRAM, bounds
+// these kernels (profiles/r01_intp_cfg4.md).  The sources are visited ONCE, in the host's order,
+// and all polynomial coefficients are accumulated side by side in registers: per coefficient
+// the sum runs over the sources in ascending order exactly as in the reference's matrix-vector
+// product, so the bits are the same as evaluating coefficient after coefficient.
 template <int MODE>
 __global__ void __launch_bounds__(128) intpKernel(int QQ, const double *__restrict__ scratch, int nUnique,
-                           int nTargets, const int32_t *__restrict__ sel,
-                           const int32_t *__restrict__ targets,
+                           int nTargets, const int32_t *__restrict__ targets,
                            const int32_t *__restrict__ srcOffset,
                            const int32_t *__restrict__ srcSlot, const double *__restrict__ weights,
                            const int32_t *__restrict__ posInMat,
@@ -146,36 +148,35 @@ __global__ void __launch_bounds__(128) intpKernel(int QQ, const double *__restri
                            const double *__restrict__ tVisc, double tViscUniform) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nTargets * QQ) return;
-  const int d = idx / nTargets;
-  const int i = sel ? sel[idx % nTargets] : idx % nTargets;   // nTargets = list length when sel
+  const int i = idx / QQ, d = idx % QQ;
   const int tgt = targets[i] - 1;
   const int s0 = srcOffset[i], n = srcOffset[i + 1] - s0;
-  const double *eq = scratch + (long long)d * nUnique;
-  const double *neq = scratch + (long long)(27 + d) * nUnique;
+  const double *eq = scratch + d;          // + u * 2QQ
+  const double *neq = scratch + QQ + d;
+  const long long pitch = 2 * QQ;
   const double visc = tVisc ? tVisc[tgt] : tViscUniform;
   double t_eq, t_neq;
-  if (MODE == 0) {
-    const double inv_n = 1.0 / (double)n;
-    double a = 0.0, b = 0.0;
-    for (int s = 0; s < n; ++s) {
-      const int u = srcSlot[s0 + s];
-      a = a + eq[u];
-      b = b + neq[u];
-    }
-    const double fOmega = omegaFromVisc(2.0 * visc), cOmega = omegaFromVisc(visc);
-    const double fac = 2.0 * neqFac(fOmega, cOmega);  // getNonEqFac_intp_fine_to_coarse
-    t_eq = a * inv_n;
-    t_neq = b * inv_n * fac;
-    tState[(long long)d * tS + tgt] = t_eq + t_neq;
-    return;
-  }
+  // The sources are fetched in chunks of 8 -- all slot loads of a chunk, then all value loads,
+  // issued back to back -- because a one-source-at-a-time loop is a chain of 2 n dependent
+  // memory latencies (measured: 149 us for the 309 k linear targets of cfg4).  The sums still
+  // take the sources in ascending order.
+  constexpr int CH = 8;
   if (MODE == 1) {
     double a = 0.0, b = 0.0;
-    for (int s = 0; s < n; ++s) {
-      const int u = srcSlot[s0 + s];
-      const double w = weights[s0 + s];
-      a = a + w * eq[u];
-      b = b + w * neq[u];
+    for (int c0 = 0; c0 < n; c0 += CH) {
+      long long u[CH];
+      double w[CH], e[CH], ne[CH];
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        const int sj = min(c0 + j, n - 1);
+        u[j] = srcSlot[s0 + sj] * pitch;
+        w[j] = weights[s0 + sj];
+      }
+#pragma unroll
+      for (int j = 0; j < CH; ++j) { e[j] = eq[u[j]]; ne[j] = neq[u[j]]; }
+#pragma unroll
+      for (int j = 0; j < CH; ++j)
+        if (c0 + j < n) { a = a + w[j] * e[j]; b = b + w[j] * ne[j]; }
     }
     t_eq = a;
     t_neq = b;
@@ -186,14 +187,24 @@ __global__ void __launch_bounds__(128) intpKernel(int QQ, const double *__restri
     double ce[nCoeff], cn[nCoeff];
 #pragma unroll
     for (int k = 0; k < nCoeff; ++k) { ce[k] = 0.0; cn[k] = 0.0; }
-    for (int s = 0; s < n; ++s) {
-      const int u = srcSlot[s0 + s];
-      const double e = eq[u], ne = neq[u];
+    for (int c0 = 0; c0 < n; c0 += CH) {
+      long long u[CH];
+      double e[CH], ne[CH];
 #pragma unroll
-      for (int k = 0; k < nCoeff; ++k) {
-        const double m = A[(long long)k * n + s];
-        ce[k] = ce[k] + m * e;
-        cn[k] = cn[k] + m * ne;
+      for (int j = 0; j < CH; ++j) u[j] = srcSlot[s0 + min(c0 + j, n - 1)] * pitch;
+#pragma unroll
+      for (int j = 0; j < CH; ++j) { e[j] = eq[u[j]]; ne[j] = neq[u[j]]; }
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        if (c0 + j < n) {
+          const int sj = c0 + j;
+#pragma unroll
+          for (int k = 0; k < nCoeff; ++k) {
+            const double m = A[(long long)k * n + sj];
+            ce[k] = ce[k] + m * e[j];
+            cn[k] = cn[k] + m * ne[j];
+          }
+        }
       }
     }
     t_eq = ce[0] + ce[1] * x + ce[2] * y + ce[3] * z;
@@ -211,61 +222,13 @@ __global__ void __launch_bounds__(128) intpKernel(int QQ, const double *__restri
   tState[(long long)d * tS + tgt] = t_neq + t_eq;
 }
 
-// Linear interpolation for targets with exactly NS sources: one thread per target keeps the
-// source slots and the 4 x NS least-square matrix in registers and walks the directions, so the
-// list and matrix loads are paid once per target instead of once per (target, direction).  Per
-// (target, direction) the arithmetic is the sequence of intpKernel<2>.
-template <int NS>
-__global__ void __launch_bounds__(128) intpLinearPerTargetKernel(
-    int QQ, const double *__restrict__ scratch, int nUnique, int nSel, const int32_t *__restrict__ sel,
-    const int32_t *__restrict__ targets, const int32_t *__restrict__ srcOffset,
-    const int32_t *__restrict__ srcSlot, const int32_t *__restrict__ posInMat,
-    const int32_t *__restrict__ matOffset, const double *__restrict__ matrices,
-    const double *__restrict__ coord, double *__restrict__ tState, long long tS,
-    const double *__restrict__ tVisc, double tViscUniform) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nSel) return;
-  const int i = sel[t];
-  const int tgt = targets[i] - 1;
-  const int s0 = srcOffset[i];
-  int u[NS];
-  double A[4][NS];
-  const double *Am = matrices + matOffset[posInMat[i]];
-#pragma unroll
-  for (int s = 0; s < NS; ++s) u[s] = srcSlot[s0 + s];
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-#pragma unroll
-    for (int s = 0; s < NS; ++s) A[k][s] = Am[k * NS + s];
-  const double x = coord[3 * i + 0], y = coord[3 * i + 1], z = coord[3 * i + 2];
-  const double visc = tVisc ? tVisc[tgt] : tViscUniform;
-  const double fOmega = omegaFromVisc(visc), cOmega = omegaFromVisc(0.5 * visc);
-  const double fac = 0.5 * neqFac(cOmega, fOmega);  // getNonEqFac_intp_coarse_to_fine
-  for (int d = 0; d < QQ; ++d) {
-    const double *eq = scratch + (long long)d * nUnique;
-    const double *neq = scratch + (long long)(27 + d) * nUnique;
-    double ce[4] = {0.0, 0.0, 0.0, 0.0}, cn[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      const double e = eq[u[s]], ne = neq[u[s]];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        ce[k] = ce[k] + A[k][s] * e;
-        cn[k] = cn[k] + A[k][s] * ne;
-      }
-    }
-    const double t_eq = ce[0] + ce[1] * x + ce[2] * y + ce[3] * z;
-    double t_neq = cn[0] + cn[1] * x + cn[2] * y + cn[3] * z;
-    t_neq = t_neq * fac;
-    tState[(long long)d * tS + tgt] = t_neq + t_eq;
-  }
-}
-
-// fillMyGhostsFromFiner_avg_feq_fneq without the scratch pass: one thread per coarse ghost walks
-// its (at most 8, Morton-contiguous) children, forms f_eq(rho, u from auxField) and f - f_eq of
-// each and accumulates both per direction in the children's order -- the sums of intpKernel<0>.
-template <int QQ>
-__global__ void __launch_bounds__(64) fromFinerFusedKernel(int incomp, const double *__restrict__ sState,
+// fillMyGhostsFromFiner_avg_feq_fneq without a scratch pass: 8 lanes per coarse ghost, one lane per
+// child (the children are Morton-contiguous fine elements: coalesced loads).  Each lane forms
+// f_eq(rho, u from auxField) and f - f_eq of its child and parks them in shared memory; the lanes
+// of the group then share the QQ directions, each summing its directions over the children in
+// the children's order, a = (..((c1 + c2) + c3)..), as the reference's loop does.
+template <int QQ, int THREADS>
+__global__ void __launch_bounds__(THREADS) fromFinerFusedKernel(int incomp, const double *__restrict__ sState,
                                      const double *__restrict__ sAux, long long sS,
                                      const int32_t *__restrict__ uniqueSrc, int nTargets,
                                      const int32_t *__restrict__ targets,
@@ -273,41 +236,49 @@ __global__ void __launch_bounds__(64) fromFinerFusedKernel(int incomp, const dou
                                      const int32_t *__restrict__ srcSlot,
                                      double *__restrict__ tState, long long tS,
                                      const double *__restrict__ tVisc, double tViscUniform) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nTargets) return;
-  const int tgt = targets[i] - 1;
-  const int s0 = srcOffset[i], n = srcOffset[i + 1] - s0;
-  double a[QQ], b[QQ];
-#pragma unroll
-  for (int q = 0; q < QQ; ++q) { a[q] = 0.0; b[q] = 0.0; }
-  for (int s = 0; s < n; ++s) {
-    const int e = uniqueSrc[srcSlot[s0 + s]] - 1;
+  constexpr int W = 2 * QQ, P = W + 1;
+  __shared__ double tile[THREADS * P];
+  const int idx = blockIdx.x * THREADS + threadIdx.x;
+  const int i = idx >> 3, c = idx & 7;
+  const bool valid = i < nTargets;
+  int n = 0, s0 = 0, tgt = 0;
+  if (valid) { s0 = srcOffset[i]; n = srcOffset[i + 1] - s0; tgt = targets[i] - 1; }
+  if (c < n) {
+    const int e = uniqueSrc[srcSlot[s0 + c]] - 1;
     const double rho = sAux[e], vx = sAux[sS + e], vy = sAux[2 * sS + e], vz = sAux[3 * sS + e];
-    double feq[QQ];
+    double f[QQ], eq[QQ];
+#pragma unroll
+    for (int q = 0; q < QQ; ++q) f[q] = sState[(long long)q * sS + e];
     if (QQ == 19) {
-      double(&g)[19] = reinterpret_cast<double(&)[19]>(feq);
+      double(&g)[19] = reinterpret_cast<double(&)[19]>(eq);
       if (incomp) pdfEqIncompD3Q19(rho, vx, vy, vz, g);
       else pdfEqD3Q19(rho, vx, vy, vz, g);
     } else {
-      double(&g)[27] = reinterpret_cast<double(&)[27]>(feq);
+      double(&g)[27] = reinterpret_cast<double(&)[27]>(eq);
       if (incomp) pdfEqIncompD3Q27(rho, vx, vy, vz, g);
       else pdfEqD3Q27(rho, vx, vy, vz, g);
     }
 #pragma unroll
     for (int q = 0; q < QQ; ++q) {
-      const double f = sState[(long long)q * sS + e];
-      a[q] = a[q] + feq[q];
-      b[q] = b[q] + (f - feq[q]);
+      tile[threadIdx.x * P + q] = eq[q];
+      tile[threadIdx.x * P + QQ + q] = f[q] - eq[q];
     }
   }
+  __syncthreads();
+  if (!valid) return;
   const double visc = tVisc ? tVisc[tgt] : tViscUniform;
   const double inv_n = 1.0 / (double)n;
   const double fOmega = omegaFromVisc(2.0 * visc), cOmega = omegaFromVisc(visc);
   const double fac = 2.0 * neqFac(fOmega, cOmega);  // getNonEqFac_intp_fine_to_coarse
-#pragma unroll
-  for (int q = 0; q < QQ; ++q) {
-    const double t_eq = a[q] * inv_n;
-    const double t_neq = b[q] * inv_n * fac;
+  const double *grp = tile + (threadIdx.x & ~7) * P;   // rows of my group's children
+  for (int q = c; q < QQ; q += 8) {
+    double a = 0.0, b = 0.0;
+    for (int s = 0; s < n; ++s) {
+      a = a + grp[s * P + q];
+      b = b + grp[s * P + QQ + q];
+    }
+    const double t_eq = a * inv_n;
+    const double t_neq = b * inv_n * fac;
     tState[(long long)q * tS + tgt] = t_eq + t_neq;
   }
 }
@@ -337,12 +308,13 @@ int launchIntp(const IntpArgs &a, const IntpSet &set, bool fromFiner, cudaStream
   if (set.nTargets == 0) return 0;
   const int B = 128;
   if (fromFiner) {
-    if (a.QQ == 19)
-      fromFinerFusedKernel<19><<<divUp(set.nTargets, 64), 64, 0, st>>>(
+    if (set.maxSrc > 8) return setError(1, "a ghostFromFiner element has more than 8 children");
+    if (a.QQ == 19)   // 128 threads x 39 doubles = 39 KB of shared memory
+      fromFinerFusedKernel<19, 128><<<divUp((long long)set.nTargets * 8, 128), 128, 0, st>>>(
           a.incomp, a.sState, a.sAux, a.sS, set.uniqueSrc, set.nTargets, set.targets, set.srcOffset,
           set.srcSlot, a.tState, a.tS, a.tVisc, a.tViscUniform);
-    else
-      fromFinerFusedKernel<27><<<divUp(set.nTargets, 64), 64, 0, st>>>(
+    else              // 64 threads x 55 doubles = 27.5 KB
+      fromFinerFusedKernel<27, 64><<<divUp((long long)set.nTargets * 8, 64), 64, 0, st>>>(
           a.incomp, a.sState, a.sAux, a.sS, set.uniqueSrc, set.nTargets, set.targets, set.srcOffset,
           set.srcSlot, a.tState, a.tS, a.tVisc, a.tViscUniform);
     MUSB_CUDA(cudaGetLastError());
@@ -350,36 +322,27 @@ int launchIntp(const IntpArgs &a, const IntpSet &set, bool fromFiner, cudaStream
     return 0;
   }
   if (a.QQ == 19)
-    eqNeqKernel<19><<<divUp(set.nUnique, B), B, 0, st>>>(a.incomp, a.sState, a.sAux, a.sS,
-                                                         set.uniqueSrc, set.nUnique, set.scratch);
+    eqNeqKernel<19, 128><<<divUp(set.nUnique, 128), 128, 0, st>>>(a.incomp, a.sState, a.sAux, a.sS,
+                                                                  set.uniqueSrc, set.nUnique, set.scratch);
   else
-    eqNeqKernel<27><<<divUp(set.nUnique, B), B, 0, st>>>(a.incomp, a.sState, a.sAux, a.sS,
-                                                         set.uniqueSrc, set.nUnique, set.scratch);
+    eqNeqKernel<27, 64><<<divUp(set.nUnique, 64), 64, 0, st>>>(a.incomp, a.sState, a.sAux, a.sS,
+                                                                set.uniqueSrc, set.nUnique, set.scratch);
   MUSB_CUDA(cudaGetLastError());
   const int mode = 1 + set.order;
   if (mode == 1 && !set.weights) return setError(1, "weighted-average set without weights");
-  int launches = 1;
-#define MUSB_INTP(M, N, SEL)                                                                      \
-  intpKernel<M><<<divUp((long long)(N) * a.QQ, B), B, 0, st>>>(                                   \
-      a.QQ, set.scratch, set.nUnique, (N), (SEL), set.targets, set.srcOffset, set.srcSlot,        \
-      set.weights, set.posInMat, set.matOffset, set.matrices, set.coord, a.tState, a.tS, a.tVisc, \
-      a.tViscUniform)
-#define MUSB_INTP_PT(NS, N, SEL)                                                                  \
-  intpLinearPerTargetKernel<NS><<<divUp((N), B), B, 0, st>>>(                                     \
-      a.QQ, set.scratch, set.nUnique, (N), (SEL), set.targets, set.srcOffset, set.srcSlot,        \
-      set.posInMat, set.matOffset, set.matrices, set.coord, a.tState, a.tS, a.tVisc,              \
-      a.tViscUniform)
-  if (mode == 1) { MUSB_INTP(1, set.nTargets, nullptr); ++launches; }
-  else if (mode == 2) {
-    if (set.n7) { MUSB_INTP_PT(7, set.n7, set.sel7); ++launches; }
-    if (set.n8) { MUSB_INTP_PT(8, set.n8, set.sel8); ++launches; }
-    if (set.nRest) { MUSB_INTP(2, set.nRest, set.selRest); ++launches; }
-  } else if (mode == 3) { MUSB_INTP(3, set.nTargets, nullptr); ++launches; }
+  const int grid = divUp((long long)set.nTargets * a.QQ, B);
+#define MUSB_INTP(M)                                                                              \
+  intpKernel<M><<<grid, B, 0, st>>>(a.QQ, set.scratch, set.nUnique, set.nTargets, set.targets,    \
+                                    set.srcOffset, set.srcSlot, set.weights, set.posInMat,        \
+                                    set.matOffset, set.matrices, set.coord, a.tState, a.tS,       \
+                                    a.tVisc, a.tViscUniform)
+  if (mode == 1) MUSB_INTP(1);
+  else if (mode == 2) MUSB_INTP(2);
+  else if (mode == 3) MUSB_INTP(3);
   else return setError(1, "interpolation order must be 0, 1 or 2");
 #undef MUSB_INTP
-#undef MUSB_INTP_PT
   MUSB_CUDA(cudaGetLastError());
-  if (nLaunch) *nLaunch = launches;
+  if (nLaunch) *nLaunch = 2;
   return 0;
 }
 

@@ -10,10 +10,11 @@
 // The dependency lists, weights and least-square matrices come from the host
 // (levelDesc%depFromFiner / depFromCoarser, intpMat_forLSF) unchanged.
 //
-// Two phases per set, both on the refinement surface only:
+// Coarse -> fine, two phases per set, both on the refinement surface only:
 //   A  one thread per distinct source element: f_eq(rho,u from auxField), f_neq = f - f_eq
-//   B  one thread per (target, direction): average / weighted sum / least-square polynomial
-//      over the sources in the host's order, non-equilibrium rescaling, store.
+//   B  one thread per (target, direction), direction fastest: weighted sum / least-square
+//      polynomial over the sources in the host's order, non-equilibrium rescaling, store.
+// Fine -> coarse: one fused kernel, 8 lanes per coarse ghost (one per child).
 #pragma once
 #include "common.cuh"
 #include <vector>
@@ -34,12 +35,8 @@ struct IntpSet {
   int32_t *matOffset = nullptr;  // [nMatrices+1]
   double *matrices = nullptr;    // concatenated row-major (nCoeff x nSrc)
   double *coord = nullptr;       // [nTargets][3]
-  double *scratch = nullptr;     // [2][QQmax=27][nUnique]  f_eq | f_neq
-  // linear sets: targets with exactly 7 / 8 sources (the weighted-average stencil of D3Q19 /
-  // D3Q27) go through a kernel that keeps the least-square matrix in registers; the rest
-  // through the generic one
-  int32_t *sel7 = nullptr, *sel8 = nullptr, *selRest = nullptr;
-  int n7 = 0, n8 = 0, nRest = 0;
+  double *scratch = nullptr;     // [nUnique][2*QQ]  f_eq | f_neq per distinct source
+  int maxSrc = 0;                // largest number of sources of a target
   void release();
   ~IntpSet() { release(); }
   IntpSet() = default;

@@ -14,6 +14,10 @@ the device path can be checked on machines without /root/reference.
         fluid_incompressible / bgk / d3q19, level 7 (128^3), np=8, sum of kinetic_energy_phy
         over all elements every step (237 samples)
 
+     gaussianPulse-L5_... / -L6_..._p0000{0,1,2}_t0.000E+00.res
+        the same case at refinement levels 5 and 6, np=3, line sample of the INITIAL state (the
+        three files are the three ranks' shares of the line)
+
 Run in the build container only:  python tests/golden/make_golden.py
 """
 import os
@@ -24,6 +28,9 @@ TGV = EX + "/fluid_incompressible/benchmark/TaylorGreenVortex/TGV_Simple"
 HERE = os.path.dirname(os.path.abspath(__file__))
 for d, f in ((EX + "/fluid/benchmark/gaussianPulse/reference",
               "gaussianPulse_pressAlongLength_p00000_t10.001E+00.res"),
+             *[(EX + "/fluid/benchmark/gaussianPulse/reference",
+                "gaussianPulse-L%d_pressAlongLength_p0000%d_t0.000E+00.res" % (lv, r))
+               for lv in (5, 6) for r in range(3)],
              (TGV + "/TGV_Simple_Re800/reference", "TGV_Simple_Re800_probeAtCenter_p00000.res"),
              (TGV + "/TGV_Simple_Re1600/reference", "TGV_Simple_Re1600_kE_all_p00000.res")):
     shutil.copy(os.path.join(d, f), os.path.join(HERE, f))

@@ -14,13 +14,15 @@ import os
 import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLD_PULSE_IC = {lv: [os.path.join(GOLDEN_DIR, "gaussianPulse-L%d_pressAlongLength_p0000%d_t0.000E+00.res" % (lv, r))
+                      for r in range(3)] for lv in (5, 6)}
 GOLD_PULSE = os.path.join(GOLDEN_DIR, "gaussianPulse_pressAlongLength_p00000_t10.001E+00.res")
 GOLD_TGV800 = os.path.join(GOLDEN_DIR, "TGV_Simple_Re800_probeAtCenter_p00000.res")
 GOLD_TGV1600 = os.path.join(GOLDEN_DIR, "TGV_Simple_Re1600_kE_all_p00000.res")
 
 
-def gaussian_pulse_setup(mo, nranks=1, rank=0):
-    length, level = 10.0, 4
+def gaussian_pulse_setup(mo, nranks=1, rank=0, level=4):
+    length = 10.0
     dx = length / 2.0 ** level
     nu_phy, cs_phy, rho0 = 0.01, 343.0, 1.0
     cs_lat = 1.0 / math.sqrt(3.0)
@@ -40,11 +42,13 @@ def gaussian_pulse_setup(mo, nranks=1, rank=0):
     return sch, phys, bary, nsteps
 
 
-def pulse_line_elements(sch, bary):
-    """tracking shape canoND origin (0, 5, 5) vec (10,0,0): the 16 cells with barycentre
-    (x, 5.3125, 5.3125) as in the golden file, ascending x; 0-based element indices."""
-    sel = np.nonzero((np.abs(bary[:sch.ld.nFluid, 1] - 5.3125) < 1e-9)
-                     & (np.abs(bary[:sch.ld.nFluid, 2] - 5.3125) < 1e-9))[0]
+def pulse_line_elements(sch, bary, level=4):
+    """tracking shape canoND origin (0, 5, 5) vec (10,0,0): the 2^level cells whose lower face
+    lies at y = z = 5 (barycentre 5 + dx/2: 5.3125 at level 4 as in the golden file), ascending x;
+    0-based element indices."""
+    c = 5.0 + 0.5 * 10.0 / 2.0 ** level
+    sel = np.nonzero((np.abs(bary[:sch.ld.nFluid, 1] - c) < 1e-9)
+                     & (np.abs(bary[:sch.ld.nFluid, 2] - c) < 1e-9))[0]
     return sel[np.argsort(bary[sel, 0])]
 
 

@@ -112,6 +112,37 @@ def test_velocity_bounceback_paths_agree(mb, oracle, fused):
         check(lib.musb200_set_fused_bc(1))
 
 
+@pytest.mark.parametrize("graphs", [0, 1], ids=["direct-launches", "cuda-graph"])
+def test_step_graph_replay_equals_direct_launches(mb, oracle, graphs):
+    """a long musb200_step call replays a CUDA graph of two cycles; odd and even cycle counts,
+    a changed boundary value in between (re-capture), all against the oracle"""
+    from musubi_b200._lib import check, lib
+    check(lib.musb200_set_graphs(graphs))
+    try:
+        ident = {"kind": "fluid", "relaxation": "trt", "layout": "d3q19"}
+        level = 4
+        ld, old, ref, sch = make_pair(mb, oracle, level, ident, 1.7, kind="cavity", ic="rest",
+                                      lambda_=3.0 / 16.0)
+        nl = ctypes.c_longlong()
+        check(lib.musb200_timers_reset())
+        sch.do_computation(31)
+        sch.do_computation(20)
+        check(lib.musb200_launch_count(ctypes.byref(nl)))
+        assert nl.value == 51 * 2
+        ref.run(51)
+        v = 2.0 * ref.bc_vel[2]
+        ref.bc_vel[2] = v
+        sch.set_bc_values(level, 2, v)
+        sch.do_computation(9)
+        ref.run(9)
+        n = ld.nFluid * ld.QQ
+        assert np.array_equal(sch.download_state(level)[:n], ref.state[ref.nNext][:n])
+        assert np.array_equal(sch.download_aux(level)[:ld.nFluid * 4], ref.aux[:ld.nFluid * 4])
+        sch.destroy()
+    finally:
+        check(lib.musb200_set_graphs(1))
+
+
 CHANNEL = [
     ({"kind": "fluid", "relaxation": "bgk", "layout": "d3q19"}, "pressure_expol"),
     ({"kind": "fluid", "relaxation": "mrt", "layout": "d3q27"}, "pressure_antibounceback"),

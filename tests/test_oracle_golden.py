@@ -85,3 +85,20 @@ def test_tgv_re1600_kinetic_energy_matches_reference_golden(oracle):
     assert len(got) == 13
     assert np.allclose(got, gold[:len(got), 1], rtol=1e-10, atol=1e-5)
     assert np.max(np.abs(got / gold[:len(got), 1] - 1.0)) < 1e-12
+
+
+@pytest.mark.parametrize("level", [5, 6])
+def test_gaussian_pulse_initial_state_matches_reference_goldens_at_levels_5_and_6(oracle, level):
+    """gaussianPulse-L5 / -L6 ..._t0.000E+00.res (three ranks' shares of the line): the initial
+    condition (mus_init_pdf + initial auxField) and the unit conversion at two more levels"""
+    from golden_cases import GOLD_PULSE_IC
+    gold = np.vstack([np.loadtxt(f, comments="#", ndmin=2) for f in GOLD_PULSE_IC[level]])
+    gold = gold[np.argsort(gold[:, 0])]
+    sch, phys, bary, _ = gaussian_pulse_setup(oracle, level=level)
+    got = pulse_track(sch.aux.reshape(-1, 4), pulse_line_elements(sch, bary, level), phys, bary)
+    assert got.shape == gold.shape == (1 << level, 8)
+    assert np.allclose(got, gold, rtol=1e-10, atol=1e-5)
+    assert np.max(np.abs(got[:, :3] - gold[:, :3])) < 1e-14       # barycentres
+    assert np.max(np.abs(got[:, 3] / gold[:, 3] - 1.0)) < 1e-15    # density_phy
+    assert np.max(np.abs(got[:, 4] / gold[:, 4] - 1.0)) < 1e-15    # pressure_phy
+    assert np.all(got[:, 5:] == 0.0) and np.all(gold[:, 5:] == 0.0)
