@@ -217,6 +217,11 @@ int musb200_p2p_export(int level, void *blob);
 int musb200_p2p_connect(int level, int nProcs, const int32_t *proc, const void *blobs,
                         const int32_t *nVals, const int32_t *remotePos);
 int musb200_p2p_enable(int level, int flag);
+/* 1 (default): with the peer-memory exchange on, the sweep kernel itself stores the halo links
+ * of the elements it has just collided into the receivers' state arrays (compute and transfer in
+ * one kernel), and the exchange shrinks to the arrival handshake; 0: a separate push kernel
+ * after the sweep.  Identical results. */
+int musb200_set_fused_push(int flag);
 
 /* ---- ghost interpolation: levelDesc%intpFromFiner / intpFromCoarser(order) -
  * targetList: positions of the target ghosts in the target level's total list;

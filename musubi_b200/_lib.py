@@ -72,6 +72,7 @@ SIGNATURES = {
     "musb200_p2p_export": [c_int, c_void_p],
     "musb200_p2p_connect": [c_int, c_int, P_I32, c_void_p, P_I32, P_I32],
     "musb200_p2p_enable": [c_int, c_int],
+    "musb200_set_fused_push": [c_int],
     "musb200_event_mark": [c_int],
     "musb200_event_elapsed": [P_DBL],
     "musb200_set_profiling": [c_int],

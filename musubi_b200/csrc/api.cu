@@ -141,6 +141,10 @@ struct PeerLink {
   DevBuf<uint8_t> peerOf;
   DevBuf<unsigned long long> arrived;    // [nranks], written by the senders
   DevBuf<unsigned int> ticket;
+  // fused push (sweep_push.cu): the send entries grouped by the element that owns them
+  DevBuf<uint32_t> pushMask, pushPrefix;
+  DevBuf<int32_t> pushStart, pushDst;
+  DevBuf<uint8_t> pushQ, pushPeer;
   ~PeerLink() {
     for (void *p : opened) cudaIpcCloseMemHandle(p);
   }
@@ -200,9 +204,10 @@ struct Context {
   // it started, so the captured kernel arguments are valid for every replay)
   int useGraphs = 1;
   unsigned long long epoch = 0, graphEpoch = 0;
-  int graphMin = -1, graphMax = -1, graphSlot = -1;
+  int graphMin = -1, graphMax = -1, graphSlot = -1, graphParity = -1;
   cudaGraphExec_t graphExec = nullptr;
   long long graphLaunches = 0;
+  int fusedPush = 1; // peer-memory exchange: links stored by the sweep itself (musb200_set_fused_push)
   int noFusedBc = 0; // musb200_set_fused_bc(0): always take the two-phase bcBuffer path
   int overlap = 0;   // measured slower than exchange-after-compute at 256^3 per GPU (profiles/)
   NcclApi *nccl = nullptr;
@@ -361,7 +366,8 @@ static int setBoundary(Level &L) {
   return 0;
 }
 
-static int exchange(Level &L, int kind, double *state, int nComp, cudaStream_t st = nullptr) {
+static int exchange(Level &L, int kind, double *state, int nComp, cudaStream_t st = nullptr,
+                    bool pushed = false) {
   if (g.nranks == 1) return 0;
   if (!st) st = g.stream;
   CommBuf &s = L.send[kind], &r = L.recv[kind];
@@ -381,7 +387,9 @@ static int exchange(Level &L, int kind, double *state, int nComp, cudaStream_t s
     }
     for (int k = 0; k < a.nRecvPeers; ++k) a.recvRank[k] = P.recvRank[k];
     a.arrived = P.arrived.p; a.count = ++P.count; a.ticket = P.ticket.p;
-    MUSB_TRY(launchPushHalo(a, st));
+    // pushed: the sweep stored the links itself (sweep_push.cu), only the handshake is left
+    if (pushed) MUSB_TRY(launchSignalHalo(a, st));
+    else MUSB_TRY(launchPushHalo(a, st));
     ++g.launches;
     return 0;
   }
@@ -403,7 +411,7 @@ static int exchange(Level &L, int kind, double *state, int nComp, cudaStream_t s
 }
 
 enum { SWEEP_ALL = 0, SWEEP_SENDHALO = 1, SWEEP_INTERIOR = 2 };
-static int sweep(Level &L, bool writeAux, int part = SWEEP_ALL) {
+static int sweep(Level &L, bool writeAux, int part = SWEEP_ALL, bool push = false) {
   if (!L.relaxSet) return setError(MUSB200_ERR_STATE, "musb200_set_relaxation missing");
   Timed t(T_COMPUTE);
   if (L.kind == MUSB200_KIND_PASSIVE_SCALAR) {
@@ -441,6 +449,15 @@ static int sweep(Level &L, bool writeAux, int part = SWEEP_ALL) {
   a.force_order = L.forceOrder;
   a.force = L.forceElem ? L.force.p : nullptr;
   for (int k = 0; k < 3; ++k) a.force_uniform[k] = L.forceUniform[k];
+  if (push) {
+    PeerLink &P = L.p2p;
+    a.push.mask = P.pushMask.p; a.push.prefix = P.pushPrefix.p; a.push.start = P.pushStart.p;
+    a.push.entQ = P.pushQ.p; a.push.entPeer = P.pushPeer.p; a.push.entDst = P.pushDst.p;
+    for (size_t k = 0; k < P.sendRank.size(); ++k) {
+      a.push.remoteState[k] = P.remoteState[k][L.nNext];   // ranks swap now/next in lockstep
+      a.push.remoteS[k] = P.remoteS[k];
+    }
+  }
   if (part == SWEEP_SENDHALO) { a.list = L.sendElems.p; a.count = L.nSendElems; }
   if (part == SWEEP_INTERIOR) a.skip = L.sendMask.p;
   MUSB_TRY(launchSweep(L.QQ, L.relax, L.kind, a, g.stream));
@@ -470,16 +487,10 @@ static int applyIntp(Level &src, Level &tgt, IntpSet &set, bool fromFiner) {
     return setError(MUSB200_ERR_STATE, "per-element omega needs musb200_set_viscosity for interpolation");
   Timed t(T_INTP);
   int n = 0;
-  MUSB_TRY(launchIntp(intpArgs(src, tgt), set, fromFiner, g.stream, &n));
+  IntpArgs ia = intpArgs(src, tgt);
+  ia.withAux = fromFiner;
+  MUSB_TRY(launchIntp(ia, set, fromFiner, g.stream, &n));
   g.launches += n;
-  return 0;
-}
-
-static int auxFromFiner(Level &fine, Level &coarse) {
-  if (coarse.fromFiner.nTargets == 0) return 0;
-  Timed t(T_INTP);
-  MUSB_TRY(launchAuxFromFiner(intpArgs(fine, coarse), coarse.fromFiner, g.stream));
-  ++g.launches;
   return 0;
 }
 
@@ -510,17 +521,17 @@ static int levelStep(int iLevel, int minLevel, int maxLevel, bool lastCycle) {
     MUSB_CUDA(cudaStreamWaitEvent(g.stream, g.evComm, 0));
     return 0;
   }
-  MUSB_TRY(sweep(L, writeAux));
-  if (iLevel < maxLevel) {
-    // auxField of my ghostFromFiner elements <- average of level+1
-    // (mus_intpAuxFieldCoarserAndExchange, mus_auxField_module.f90:404-444); the sweep does not
-    // touch those entries, so running it after the fused sweep equals the reference's order
-    Level *F = findLevel(iLevel + 1);
-    if (!F) return setError(MUSB200_ERR_ARG, "level " + std::to_string(iLevel + 1) + " was not created");
-    MUSB_TRY(auxFromFiner(*F, L));
-  }
+  // single level on several ranks with the peer-memory exchange: the sweep pushes the halo links
+  // itself (the force-source variant of the sweep keeps the separate push kernel)
+  const bool pushed = !multi && g.nranks > 1 && g.fusedPush && L.p2p.on && L.forceOrder == 0 &&
+                      L.kind != MUSB200_KIND_PASSIVE_SCALAR && L.p2p.pushMask.n > 0;
+  MUSB_TRY(sweep(L, writeAux, SWEEP_ALL, pushed));
+  // auxField of my ghostFromFiner elements <- average of level+1
+  // (mus_intpAuxFieldCoarserAndExchange, mus_auxField_module.f90:404-444) is taken inside the
+  // from-finer interpolation kernel below: same sources, and on one rank nothing reads those
+  // entries before the from-coarser interpolation, which runs after it
   if (multi && writeAux) MUSB_TRY(exchange(L, MUSB200_BUF_HALO, L.aux.p, 4)); // aux halo (tag level+100)
-  MUSB_TRY(exchange(L, MUSB200_BUF_HALO, L.state[L.nNext].p, L.QQ));
+  MUSB_TRY(exchange(L, MUSB200_BUF_HALO, L.state[L.nNext].p, L.QQ, nullptr, pushed));
   if (iLevel > minLevel) MUSB_TRY(exchange(L, MUSB200_BUF_FROMCOARSER, L.state[L.nNext].p, L.QQ));
   if (iLevel < maxLevel) {
     Level *F = findLevel(iLevel + 1);
@@ -1255,6 +1266,37 @@ int musb200_p2p_connect(int level, int nProcs, const int32_t *proc, const void *
   MUSB_TRY(P.srcPos.upload(srcSorted.data(), srcSorted.size(), g.stream));
   MUSB_TRY(P.dstPos.upload(dstSorted.data(), dstSorted.size(), g.stream));
   MUSB_TRY(P.peerOf.upload(peerSorted.data(), peerSorted.size(), g.stream));
+  {
+    // the same entries grouped by owning element, for the push fused into the sweep
+    std::vector<int32_t> byElem((size_t)s.total);
+    for (int i = 0; i < s.total; ++i) byElem[i] = i;
+    std::stable_sort(byElem.begin(), byElem.end(), [&](int32_t x, int32_t y) {
+      return (srcHost[x] - 1) / QQ < (srcHost[y] - 1) / QQ;
+    });
+    const size_t nWords = ((size_t)L->S + 31) / 32;
+    std::vector<uint32_t> mask(nWords, 0u), prefix(nWords, 0u);
+    std::vector<int32_t> start, dst((size_t)s.total);
+    std::vector<uint8_t> eq((size_t)s.total), ep((size_t)s.total);
+    int last = -1;
+    for (int j = 0; j < s.total; ++j) {
+      const int i = byElem[j];
+      const int e = (srcHost[i] - 1) / QQ;
+      if (e >= L->nSolve) return setError(MUSB200_ERR_ARG, "halo send buffer refers to an element that is not solved here");
+      if (e != last) { start.push_back(j); mask[e >> 5] |= 1u << (e & 31); last = e; }
+      eq[j] = (uint8_t)((srcHost[i] - 1) % QQ);
+      ep[j] = peerOf[i];
+      dst[j] = remotePos[i];
+    }
+    start.push_back(s.total);
+    uint32_t run = 0;
+    for (size_t w = 0; w < nWords; ++w) { prefix[w] = run; run += (uint32_t)__builtin_popcount(mask[w]); }
+    MUSB_TRY(P.pushMask.upload(mask.data(), mask.size(), g.stream));
+    MUSB_TRY(P.pushPrefix.upload(prefix.data(), prefix.size(), g.stream));
+    MUSB_TRY(P.pushStart.upload(start.data(), start.size(), g.stream));
+    MUSB_TRY(P.pushDst.upload(dst.data(), dst.size(), g.stream));
+    MUSB_TRY(P.pushQ.upload(eq.data(), eq.size(), g.stream));
+    MUSB_TRY(P.pushPeer.upload(ep.data(), ep.size(), g.stream));
+  }
   MUSB_CUDA(cudaStreamSynchronize(g.stream));
   P.on = true;
   return 0;
@@ -1300,8 +1342,12 @@ int musb200_set_aux_every_step(int flag) {
 // step; a two-level cycle is 7 launches).  Several ranks stay on direct launches: the peer-memory
 // exchange carries a running exchange number as a kernel argument.
 static int stepGraphed(int minLevel, int maxLevel, int nPairs) {
+  // the captured kernel arguments hold the now/next buffers of the capture: a replay must start
+  // from the same parity of the coarsest level (finer levels toggle twice per cycle; an explicit
+  // musb200_set_now_next bumps the epoch)
+  const int parity = findLevel(minLevel)->nNow;
   if (!g.graphExec || g.graphEpoch != g.epoch || g.graphMin != minLevel || g.graphMax != maxLevel ||
-      g.graphSlot != g.slot) {
+      g.graphSlot != g.slot || g.graphParity != parity) {
     dropGraph();
     const long long before = g.launches;
     const int auxSave = g.auxEveryStep;
@@ -1321,6 +1367,7 @@ static int stepGraphed(int minLevel, int maxLevel, int nPairs) {
     // capturing ran the host side of two cycles: every level toggled now/next an even number of
     // times, so the indices are where they were and nothing was executed yet
     g.graphEpoch = g.epoch; g.graphMin = minLevel; g.graphMax = maxLevel; g.graphSlot = g.slot;
+    g.graphParity = parity;
   }
   for (int p = 0; p < nPairs; ++p) {
     MUSB_CUDA(cudaGraphLaunch(g.graphExec, g.stream));
@@ -1349,6 +1396,11 @@ int musb200_step(int minLevel, int maxLevel, int nCoarseCycles) {
 int musb200_set_graphs(int flag) {
   g.useGraphs = flag ? 1 : 0;
   if (!flag) dropGraph();
+  return 0;
+}
+
+int musb200_set_fused_push(int flag) {
+  g.fusedPush = flag ? 1 : 0;
   return 0;
 }
 

@@ -83,8 +83,9 @@ int registerIntp(IntpSet &set, int order, int nTargets, const int32_t *targetLis
 }
 
 // ---------------------------------------------------------------------------
-// phase A: f_eq / f_neq of every distinct source, written source-major
-// ([u][0..QQ) = f_eq, [u][QQ..2QQ) = f_neq) through a shared-memory tile so that the global
+// phase A: f_eq / f_neq of every distinct source, written source-major with the pair of a
+// direction side by side ([u][d] = {f_eq, f_neq}: one 16-byte load in phase B) through a
+// shared-memory tile so that the global
 // stores of a CTA are one contiguous, fully coalesced run
 template <int QQ, int THREADS>
 __global__ void __launch_bounds__(THREADS) eqNeqKernel(int incomp, const double *__restrict__ sState,
@@ -110,8 +111,8 @@ __global__ void __launch_bounds__(THREADS) eqNeqKernel(int incomp, const double 
 #pragma unroll
     for (int q = 0; q < QQ; ++q) {
       const double f = sState[(long long)q * sS + e];
-      tile[threadIdx.x * P + q] = feq[q];
-      tile[threadIdx.x * P + QQ + q] = f - feq[q];
+      tile[threadIdx.x * P + 2 * q] = feq[q];
+      tile[threadIdx.x * P + 2 * q + 1] = f - feq[q];
     }
   }
   __syncthreads();
@@ -126,16 +127,16 @@ __device__ __forceinline__ double neqFac(double omegaS, double omegaT) {
   return omegaS * (1.0 - omegaT) / ((1.0 - omegaS) * omegaT);
 }
 
-// MODE 1: weighted average; 2: linear; 3: quadratic (MODE 0, the average from finer, has its own
-// kernel below).  One thread per (target, direction) with the DIRECTION fastest: the lanes of a
-// warp belong to one or two targets, so the source slots and the least-square matrix are
-// warp-uniform loads (one line each, broadcast) and the f_eq / f_neq values of a source are one
-// contiguous run of the source-major scratch.  A gather touches 2-3 cache lines instead of the
-// 20-30 of a target-fastest mapping -- measured on cfg4: L1 tag throughput, not DRAM, bounds
-// these kernels (profiles/r01_intp_cfg4.md).  The sources are visited ONCE, in the host's order,
-// and all polynomial coefficients are accumulated side by side in registers: per coefficient
-// the sum runs over the sources in ascending order exactly as in the reference's matrix-vector
-// product, so the bits are the same as evaluating coefficient after coefficient.
+// MODE 1: weighted average; 2: linear; 3: quadratic (the average from finer has its own kernel
+// below).  One thread per (target, direction) with the DIRECTION fastest, so the lanes of a warp
+// belong to one or two targets: source slots and least-square matrix are warp-uniform loads, and
+// the {f_eq, f_neq} pairs of a source are one contiguous run of the source-major scratch, fetched
+// as double2.  Per (target, direction) the sources are accumulated in the host's order with all
+// polynomial coefficients side by side in registers -- per coefficient the sum over the sources
+// of the reference's matrix-vector product, so the bits are the same.  The kernel is bound by
+// FP64 issue (every multiply-add is two instructions without contraction), which is why the
+// non-equilibrium factor -- three divisions -- is computed once on the host when the level's
+// viscosity is uniform (profiles/r01_intp_cfg4.md lists the variants that were measured).
 template <int MODE>
 __global__ void __launch_bounds__(128) intpKernel(int QQ, const double *__restrict__ scratch, int nUnique,
                            int nTargets, const int32_t *__restrict__ targets,
@@ -146,67 +147,32 @@ __global__ void __launch_bounds__(128) intpKernel(int QQ, const double *__restri
                            const double *__restrict__ matrices, const double *__restrict__ coord,
                            double *__restrict__ tState, long long tS,
                            const double *__restrict__ tVisc, double tViscUniform) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= nTargets * QQ) return;
-  const int i = idx / QQ, d = idx % QQ;
+  constexpr int nCoeff = MODE == 1 ? 1 : (MODE == 2 ? 4 : 10);
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)nTargets * QQ) return;
+  const int i = (int)(idx / QQ), d = (int)(idx % QQ);
   const int tgt = targets[i] - 1;
   const int s0 = srcOffset[i], n = srcOffset[i + 1] - s0;
-  const double *eq = scratch + d;          // + u * 2QQ
-  const double *neq = scratch + QQ + d;
-  const long long pitch = 2 * QQ;
-  const double visc = tVisc ? tVisc[tgt] : tViscUniform;
+  const double2 *pair = reinterpret_cast<const double2 *>(scratch) + d;   // + u * QQ
+  const double *A = MODE == 1 ? weights + s0 : matrices + matOffset[posInMat[i]];
+  double ce[nCoeff], cn[nCoeff];
+#pragma unroll
+  for (int k = 0; k < nCoeff; ++k) { ce[k] = 0.0; cn[k] = 0.0; }
+  for (int s = 0; s < n; ++s) {
+    const double2 v = pair[(long long)srcSlot[s0 + s] * QQ];
+#pragma unroll
+    for (int k = 0; k < nCoeff; ++k) {
+      const double m = A[k * n + s];   // A(k, s), row-major (nCoeff x n); MODE 1: w(s)
+      ce[k] = ce[k] + m * v.x;
+      cn[k] = cn[k] + m * v.y;
+    }
+  }
   double t_eq, t_neq;
-  // The sources are fetched in chunks of 8 -- all slot loads of a chunk, then all value loads,
-  // issued back to back -- because a one-source-at-a-time loop is a chain of 2 n dependent
-  // memory latencies (measured: 149 us for the 309 k linear targets of cfg4).  The sums still
-  // take the sources in ascending order.
-  constexpr int CH = 8;
   if (MODE == 1) {
-    double a = 0.0, b = 0.0;
-    for (int c0 = 0; c0 < n; c0 += CH) {
-      long long u[CH];
-      double w[CH], e[CH], ne[CH];
-#pragma unroll
-      for (int j = 0; j < CH; ++j) {
-        const int sj = min(c0 + j, n - 1);
-        u[j] = srcSlot[s0 + sj] * pitch;
-        w[j] = weights[s0 + sj];
-      }
-#pragma unroll
-      for (int j = 0; j < CH; ++j) { e[j] = eq[u[j]]; ne[j] = neq[u[j]]; }
-#pragma unroll
-      for (int j = 0; j < CH; ++j)
-        if (c0 + j < n) { a = a + w[j] * e[j]; b = b + w[j] * ne[j]; }
-    }
-    t_eq = a;
-    t_neq = b;
+    t_eq = ce[0];
+    t_neq = cn[0];
   } else {
-    constexpr int nCoeff = MODE == 2 ? 4 : 10;
-    const double *A = matrices + matOffset[posInMat[i]];
     const double x = coord[3 * i + 0], y = coord[3 * i + 1], z = coord[3 * i + 2];
-    double ce[nCoeff], cn[nCoeff];
-#pragma unroll
-    for (int k = 0; k < nCoeff; ++k) { ce[k] = 0.0; cn[k] = 0.0; }
-    for (int c0 = 0; c0 < n; c0 += CH) {
-      long long u[CH];
-      double e[CH], ne[CH];
-#pragma unroll
-      for (int j = 0; j < CH; ++j) u[j] = srcSlot[s0 + min(c0 + j, n - 1)] * pitch;
-#pragma unroll
-      for (int j = 0; j < CH; ++j) { e[j] = eq[u[j]]; ne[j] = neq[u[j]]; }
-#pragma unroll
-      for (int j = 0; j < CH; ++j) {
-        if (c0 + j < n) {
-          const int sj = c0 + j;
-#pragma unroll
-          for (int k = 0; k < nCoeff; ++k) {
-            const double m = A[(long long)k * n + sj];
-            ce[k] = ce[k] + m * e[j];
-            cn[k] = cn[k] + m * ne[j];
-          }
-        }
-      }
-    }
     t_eq = ce[0] + ce[1] * x + ce[2] * y + ce[3] * z;
     t_neq = cn[0] + cn[1] * x + cn[2] * y + cn[3] * z;
     if (MODE == 3) {
@@ -216,8 +182,13 @@ __global__ void __launch_bounds__(128) intpKernel(int QQ, const double *__restri
               cn[9] * z * x;
     }
   }
-  const double fOmega = omegaFromVisc(visc), cOmega = omegaFromVisc(0.5 * visc);
-  const double fac = 0.5 * neqFac(cOmega, fOmega);  // getNonEqFac_intp_coarse_to_fine
+  double fac;   // 0.5 * getNonEqFac_intp_coarse_to_fine
+  if (tVisc) {
+    const double visc = tVisc[tgt];
+    fac = 0.5 * neqFac(omegaFromVisc(0.5 * visc), omegaFromVisc(visc));
+  } else {
+    fac = tViscUniform;   // the factor itself, evaluated by the launcher with the same expression
+  }
   t_neq = t_neq * fac;
   tState[(long long)d * tS + tgt] = t_neq + t_eq;
 }
@@ -234,9 +205,12 @@ __global__ void __launch_bounds__(THREADS) fromFinerFusedKernel(int incomp, cons
                                      const int32_t *__restrict__ targets,
                                      const int32_t *__restrict__ srcOffset,
                                      const int32_t *__restrict__ srcSlot,
-                                     double *__restrict__ tState, long long tS,
+                                     double *__restrict__ tState, double *__restrict__ tAux, long long tS,
                                      const double *__restrict__ tVisc, double tViscUniform) {
-  constexpr int W = 2 * QQ, P = W + 1;
+  // tAux != nullptr: the auxField average of mus_intpAuxFieldCoarserAndExchange
+  // (fillArbiMyGhostsFromFiner_avg) is taken in the same pass -- same sources, and nothing
+  // between the two calls of the reference's schedule writes them
+  constexpr int W = 2 * QQ, P = W + 5;       // + rho, ux, uy, uz; odd pitch
   __shared__ double tile[THREADS * P];
   const int idx = blockIdx.x * THREADS + threadIdx.x;
   const int i = idx >> 3, c = idx & 7;
@@ -258,11 +232,13 @@ __global__ void __launch_bounds__(THREADS) fromFinerFusedKernel(int incomp, cons
       if (incomp) pdfEqIncompD3Q27(rho, vx, vy, vz, g);
       else pdfEqD3Q27(rho, vx, vy, vz, g);
     }
+    double *row = tile + threadIdx.x * P;
 #pragma unroll
     for (int q = 0; q < QQ; ++q) {
-      tile[threadIdx.x * P + q] = eq[q];
-      tile[threadIdx.x * P + QQ + q] = f[q] - eq[q];
+      row[q] = eq[q];
+      row[QQ + q] = f[q] - eq[q];
     }
+    row[W] = rho; row[W + 1] = vx; row[W + 2] = vy; row[W + 3] = vz;
   }
   __syncthreads();
   if (!valid) return;
@@ -280,6 +256,11 @@ __global__ void __launch_bounds__(THREADS) fromFinerFusedKernel(int incomp, cons
     const double t_eq = a * inv_n;
     const double t_neq = b * inv_n * fac;
     tState[(long long)q * tS + tgt] = t_eq + t_neq;
+  }
+  if (tAux != nullptr && c < 4) {
+    double t = 0.0;
+    for (int s = 0; s < n; ++s) t = grp[s * P + W + c] + t;
+    tAux[(long long)c * tS + tgt] = t * inv_n;
   }
 }
 
@@ -303,20 +284,24 @@ __global__ void auxFromFinerKernel(const double *__restrict__ sAux, long long sS
   tAux[(long long)k * tS + targets[i] - 1] = t * inv_n;
 }
 
+// host copies of omegaFromVisc / neqFac: IEEE double on both sides, identical bits
+static double hostOmega(double v) { return 1.0 / (3.0 * v + 0.5); }
+static double hostNeqFac(double omegaS, double omegaT) { return omegaS * (1.0 - omegaT) / ((1.0 - omegaS) * omegaT); }
+
 int launchIntp(const IntpArgs &a, const IntpSet &set, bool fromFiner, cudaStream_t st, int *nLaunch) {
   if (nLaunch) *nLaunch = 0;
   if (set.nTargets == 0) return 0;
   const int B = 128;
   if (fromFiner) {
     if (set.maxSrc > 8) return setError(1, "a ghostFromFiner element has more than 8 children");
-    if (a.QQ == 19)   // 128 threads x 39 doubles = 39 KB of shared memory
+    if (a.QQ == 19)   // 128 threads x 43 doubles = 44 KB of shared memory
       fromFinerFusedKernel<19, 128><<<divUp((long long)set.nTargets * 8, 128), 128, 0, st>>>(
           a.incomp, a.sState, a.sAux, a.sS, set.uniqueSrc, set.nTargets, set.targets, set.srcOffset,
-          set.srcSlot, a.tState, a.tS, a.tVisc, a.tViscUniform);
-    else              // 64 threads x 55 doubles = 27.5 KB
+          set.srcSlot, a.tState, a.withAux ? a.tAux : nullptr, a.tS, a.tVisc, a.tViscUniform);
+    else              // 64 threads x 59 doubles = 30 KB
       fromFinerFusedKernel<27, 64><<<divUp((long long)set.nTargets * 8, 64), 64, 0, st>>>(
           a.incomp, a.sState, a.sAux, a.sS, set.uniqueSrc, set.nTargets, set.targets, set.srcOffset,
-          set.srcSlot, a.tState, a.tS, a.tVisc, a.tViscUniform);
+          set.srcSlot, a.tState, a.withAux ? a.tAux : nullptr, a.tS, a.tVisc, a.tViscUniform);
     MUSB_CUDA(cudaGetLastError());
     if (nLaunch) *nLaunch = 1;
     return 0;
@@ -331,11 +316,14 @@ int launchIntp(const IntpArgs &a, const IntpSet &set, bool fromFiner, cudaStream
   const int mode = 1 + set.order;
   if (mode == 1 && !set.weights) return setError(1, "weighted-average set without weights");
   const int grid = divUp((long long)set.nTargets * a.QQ, B);
+  // uniform viscosity: hand over 0.5 * getNonEqFac_intp_coarse_to_fine instead of the viscosity
+  const double facOrVisc =
+      a.tVisc ? 0.0 : 0.5 * hostNeqFac(hostOmega(0.5 * a.tViscUniform), hostOmega(a.tViscUniform));
 #define MUSB_INTP(M)                                                                              \
   intpKernel<M><<<grid, B, 0, st>>>(a.QQ, set.scratch, set.nUnique, set.nTargets, set.targets,    \
                                     set.srcOffset, set.srcSlot, set.weights, set.posInMat,        \
                                     set.matOffset, set.matrices, set.coord, a.tState, a.tS,       \
-                                    a.tVisc, a.tViscUniform)
+                                    a.tVisc, facOrVisc)
   if (mode == 1) MUSB_INTP(1);
   else if (mode == 2) MUSB_INTP(2);
   else if (mode == 3) MUSB_INTP(3);

@@ -57,6 +57,7 @@ struct IntpArgs {
   long long tS;
   const double *tVisc;   // per-element lattice viscosity of the target level or nullptr
   double tViscUniform;
+  bool withAux;          // from-finer: average the auxField in the same kernel
 };
 
 int registerIntp(IntpSet &set, int order, int nTargets, const int32_t *targetList,

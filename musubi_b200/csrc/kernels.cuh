@@ -5,6 +5,21 @@
 
 namespace musb200 {
 
+constexpr int kMaxPeers = 16;
+
+// halo push fused into the sweep (sweep_push.cu): per send element (bit set in `mask`; its rank
+// among the send elements = prefix[word] + popc of the lower bits) a CSR row of links
+struct PushArgs {
+  const uint32_t *mask;      // 1 bit per element, nullptr = no fused push
+  const uint32_t *prefix;    // send elements before each 32-element word
+  const int32_t *start;      // [nSendElems + 1]
+  const uint8_t *entQ;       // local direction (0-based) of the link
+  const uint8_t *entPeer;    // index into the peer tables
+  const int32_t *entDst;     // receiver's state position (1-based, its recv buffer's pos list)
+  double *remoteState[kMaxPeers];
+  long long remoteS[kMaxPeers];
+};
+
 // Arguments of one fused "auxField + stream + collide" sweep over a level.
 // State and aux are SoA with row stride S (elements): f[q][e] = ptr[q*S + e].
 struct SweepArgs {
@@ -24,6 +39,7 @@ struct SweepArgs {
   int force_order;
   const double *force;
   double force_uniform[3];
+  PushArgs push;
 };
 
 int launchSweep(int QQ, int relax, int kind, const SweepArgs &a, cudaStream_t st);
@@ -102,7 +118,6 @@ int launchUnserialize(int QQ, double *state, long long S, const int32_t *slot, c
                       int n, const double *buffer, cudaStream_t st);
 
 // peer-memory halo exchange (p2p.cu)
-constexpr int kMaxPeers = 16;
 struct P2PArgs {
   const double *state;        // my state(:, next)
   long long S;
@@ -120,6 +135,8 @@ struct P2PArgs {
   unsigned int *ticket;
 };
 int launchPushHalo(const P2PArgs &a, cudaStream_t st);
+// arrival handshake only (the links were stored by the sweep with the fused push)
+int launchSignalHalo(const P2PArgs &a, cudaStream_t st);
 
 // reductions: out[0] = total mass, out[1] = max |u|^2, out[2] = nan count
 int launchReduce(int QQ, const double *state, long long S, int nFluid, double *scratch,

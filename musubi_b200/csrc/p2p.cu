@@ -48,6 +48,30 @@ __global__ void pushHaloKernel(P2PArgs a) {
   __threadfence_system();
 }
 
+// The handshake alone, for steps whose links were stored by the sweep itself (sweep_push.cu):
+// the sweep kernel has completed before this one starts (stream order), its peer stores are
+// performed; the system fence orders them before the arrival flags for every observer.
+__global__ void signalHaloKernel(P2PArgs a) {
+  const int t = threadIdx.x;
+  __threadfence_system();
+  if (t < a.nSendPeers) {
+    volatile unsigned long long *flag = a.remoteArrived[t] + a.myRank;
+    *flag = a.count;
+  }
+  __threadfence_system();
+  if (t < a.nRecvPeers) {
+    volatile unsigned long long *flag = a.arrived + a.recvRank[t];
+    while (*flag < a.count) { __nanosleep(100); }
+  }
+  __threadfence_system();
+}
+
+int launchSignalHalo(const P2PArgs &a, cudaStream_t st) {
+  signalHaloKernel<<<1, 32, 0, st>>>(a);
+  MUSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int launchPushHalo(const P2PArgs &a, cudaStream_t st) {
   // enough CTAs to saturate NVLink stores, few enough to keep the ticket cheap
   int blocks = divUp(a.n > 0 ? a.n : 1, 256);

@@ -18,10 +18,12 @@
 namespace musb200 {
 
 int launchSweepForce(int QQ, int relax, int kind, const SweepArgs &a, cudaStream_t st);  // sweep_force.cu
+int launchSweepPush(int QQ, int relax, int kind, const SweepArgs &a, cudaStream_t st);   // sweep_push.cu
 
 int launchSweep(int QQ, int relax, int kind, const SweepArgs &a, cudaStream_t st) {
   if (a.force_order != 0) return launchSweepForce(QQ, relax, kind, a, st);
-  return dispatchSweep<false>(QQ, relax, kind, a, st);
+  if (a.push.mask != nullptr) return launchSweepPush(QQ, relax, kind, a, st);
+  return dispatchSweep<0>(QQ, relax, kind, a, st);
 }
 
 }  // namespace musb200

@@ -8,7 +8,7 @@
 namespace musb200 {
 
 int launchSweepForce(int QQ, int relax, int kind, const SweepArgs &a, cudaStream_t st) {
-  return dispatchSweep<true>(QQ, relax, kind, a, st);
+  return dispatchSweep<1>(QQ, relax, kind, a, st);
 }
 
 }  // namespace musb200

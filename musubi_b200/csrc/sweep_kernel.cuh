@@ -106,8 +106,14 @@ struct ForceSrc {
   }
 };
 
-template <int QQ, int RELAX, bool INCOMP, bool FORCE>
+// VAR: 0 = plain sweep, 1 = with the body-force source (sweep_force.cu), 2 = with the halo push
+// fused in (sweep_push.cu): an element that owns links of the halo send buffer stores them
+// straight into the halo rows of the receiving ranks' state arrays (peer-mapped) right after
+// its collision, so the transfer rides on the sweep and only the arrival handshake is left
+// for after it (signalHaloKernel, p2p.cu).
+template <int QQ, int RELAX, bool INCOMP, int VAR>
 __global__ void __launch_bounds__(sweepThreads<QQ>(), sweepMinBlocks<QQ>()) sweepKernel(const SweepArgs a) {
+  constexpr bool FORCE = VAR == 1, PUSH = VAR == 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.count) return;
   int e;
@@ -183,39 +189,52 @@ __global__ void __launch_bounds__(sweepThreads<QQ>(), sweepMinBlocks<QQ>()) swee
     if (RELAX == 1) collide_trt_d3q27(g, rho, ux, uy, uz, omega, a.rp.lambda, st);
     if (RELAX == 2) collide_mrt_d3q27<INCOMP>(g, rho, ux, uy, uz, omega, a.rp.omega_bulk, st);
   }
+  if (PUSH) {
+    const uint32_t w = a.push.mask[e >> 5];
+    if ((w >> (e & 31)) & 1u) {
+      const int k = (int)a.push.prefix[e >> 5] + __popc(w & ((1u << (e & 31)) - 1u));
+      const int j1 = a.push.start[k + 1];
+      for (int j = a.push.start[k]; j < j1; ++j) {
+        const double v = out[(long long)a.push.entQ[j] * S];   // stored above by this thread
+        const int pk = a.push.entPeer[j];
+        const int r = a.push.entDst[j] - 1;
+        a.push.remoteState[pk][(long long)(r % QQ) * a.push.remoteS[pk] + r / QQ] = v;
+      }
+    }
+  }
 }
 
-template <int QQ, int RELAX, bool INCOMP, bool FORCE>
+template <int QQ, int RELAX, bool INCOMP, int VAR>
 static int launchT(const SweepArgs &a, cudaStream_t st) {
   if (a.count <= 0) return 0;
   const int block = sweepThreads<QQ>();
-  sweepKernel<QQ, RELAX, INCOMP, FORCE><<<divUp(a.count, block), block, 0, st>>>(a);
+  sweepKernel<QQ, RELAX, INCOMP, VAR><<<divUp(a.count, block), block, 0, st>>>(a);
   MUSB_CUDA(cudaGetLastError());
   return 0;
 }
 
 
-// (layout, relaxation, kind) -> instantiation; FORCE selects the translation unit
-template <bool FORCE>
+// (layout, relaxation, kind) -> instantiation; VAR selects the translation unit
+template <int VAR>
 static int dispatchSweep(int QQ, int relax, int kind, const SweepArgs &a, cudaStream_t st) {
   if (kind == 1) {
     // mus_init_advRel_fluid_incompressible (init/mus_initFluidIncomp_module.f90:73-218):
     // trt exists for d3q19 only
-    if (QQ == 19 && relax == 0) return launchT<19, 0, true, FORCE>(a, st);
-    if (QQ == 19 && relax == 1) return launchT<19, 1, true, FORCE>(a, st);
-    if (QQ == 19 && relax == 2) return launchT<19, 2, true, FORCE>(a, st);
-    if (QQ == 27 && relax == 0) return launchT<27, 0, true, FORCE>(a, st);
-    if (QQ == 27 && relax == 2) return launchT<27, 2, true, FORCE>(a, st);
+    if (QQ == 19 && relax == 0) return launchT<19, 0, true, VAR>(a, st);
+    if (QQ == 19 && relax == 1) return launchT<19, 1, true, VAR>(a, st);
+    if (QQ == 19 && relax == 2) return launchT<19, 2, true, VAR>(a, st);
+    if (QQ == 27 && relax == 0) return launchT<27, 0, true, VAR>(a, st);
+    if (QQ == 27 && relax == 2) return launchT<27, 2, true, VAR>(a, st);
     return setError(4, "fluid_incompressible: the reference has no trt kernel for this layout");
   }
   if (QQ == 19) {
-    if (relax == 0) return launchT<19, 0, false, FORCE>(a, st);
-    if (relax == 1) return launchT<19, 1, false, FORCE>(a, st);
-    if (relax == 2) return launchT<19, 2, false, FORCE>(a, st);
+    if (relax == 0) return launchT<19, 0, false, VAR>(a, st);
+    if (relax == 1) return launchT<19, 1, false, VAR>(a, st);
+    if (relax == 2) return launchT<19, 2, false, VAR>(a, st);
   } else if (QQ == 27) {
-    if (relax == 0) return launchT<27, 0, false, FORCE>(a, st);
-    if (relax == 1) return launchT<27, 1, false, FORCE>(a, st);
-    if (relax == 2) return launchT<27, 2, false, FORCE>(a, st);
+    if (relax == 0) return launchT<27, 0, false, VAR>(a, st);
+    if (relax == 1) return launchT<27, 1, false, VAR>(a, st);
+    if (relax == 2) return launchT<27, 2, false, VAR>(a, st);
   }
   return setError(4, "no kernel for this (layout, relaxation)");
 }
