@@ -133,10 +133,10 @@ __device__ __forceinline__ double neqFac(double omegaS, double omegaT) {
 // the {f_eq, f_neq} pairs of a source are one contiguous run of the source-major scratch, fetched
 // as double2.  Per (target, direction) the sources are accumulated in the host's order with all
 // polynomial coefficients side by side in registers -- per coefficient the sum over the sources
-// of the reference's matrix-vector product, so the bits are the same.  The kernel is bound by
-// FP64 issue (every multiply-add is two instructions without contraction), which is why the
-// non-equilibrium factor -- three divisions -- is computed once on the host when the level's
-// viscosity is uniform (profiles/r01_intp_cfg4.md lists the variants that were measured).
+// of the reference's matrix-vector product, so the bits are the same.  The non-equilibrium factor
+// -- three divisions -- is computed once on the host when the level's viscosity is uniform.
+// ncu: L1 wavefronts 62 % of peak, FP64 26 %, L2 14 %, DRAM 3 %: a latency / L1 mix; six other
+// mappings were measured and none beat this one (profiles/r01_intp_cfg4.md).
 template <int MODE>
 __global__ void __launch_bounds__(128) intpKernel(int QQ, const double *__restrict__ scratch, int nUnique,
                            int nTargets, const int32_t *__restrict__ targets,
