@@ -299,8 +299,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--overlap", action="store_true",
                     help="sweep the send-halo elements first and overlap their exchange with the rest")
-    ap.add_argument("--no-fused-push", action="store_true",
-                    help="peer-memory halo exchange with a separate push kernel after the sweep")
+    ap.add_argument("--fused-push", action="store_true",
+                    help="peer-memory halo exchange with the link stores fused into the sweep kernel")
     ap.add_argument("--no-p2p", action="store_true",
                     help="halo exchange through pack/ncclSend/ncclRecv/unpack instead of peer memory")
     args = ap.parse_args()
@@ -376,7 +376,7 @@ def main():
     t_setup = time.perf_counter()
     ld = mb.LevelDesc(level, QQ, wl["kind"], rank, world, octants=octants)
     check(lib.musb200_set_overlap(1 if args.overlap else 0))
-    check(lib.musb200_set_fused_push(0 if args.no_fused_push else 1))
+    check(lib.musb200_set_fused_push(1 if args.fused_push else 0))
     if wl["kind"] == "cavity":
         rho, vel = cases.cavity_rest(ld)
     else:
@@ -401,8 +401,8 @@ def main():
         t = torch.tensor([ok], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         if float(t[0]) > 0.5:
-            halo_path = ("peer-memory stores over NVLink (separate push kernel)" if args.no_fused_push else
-                         "peer-memory stores over NVLink fused into the sweep kernel + arrival handshake")
+            halo_path = ("peer-memory stores over NVLink fused into the sweep kernel + arrival handshake"
+                         if args.fused_push else "peer-memory stores over NVLink (one kernel)")
         else:
             check(lib.musb200_p2p_enable(level, 0))
     lid = cases.lid_values(ld) if wl["kind"] == "cavity" else None

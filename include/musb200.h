@@ -217,10 +217,12 @@ int musb200_p2p_export(int level, void *blob);
 int musb200_p2p_connect(int level, int nProcs, const int32_t *proc, const void *blobs,
                         const int32_t *nVals, const int32_t *remotePos);
 int musb200_p2p_enable(int level, int flag);
-/* 1 (default): with the peer-memory exchange on, the sweep kernel itself stores the halo links
- * of the elements it has just collided into the receivers' state arrays (compute and transfer in
- * one kernel), and the exchange shrinks to the arrival handshake; 0: a separate push kernel
- * after the sweep.  Identical results. */
+/* 1: with the peer-memory exchange on, the sweep kernel itself stores the halo links of the
+ * elements it has just collided into the receivers' state arrays (compute and transfer in one
+ * kernel) and the exchange shrinks to the arrival handshake; 0 (default): a separate push kernel
+ * after the sweep, whose entries are ordered for full 128-byte NVLink writes.  Identical results;
+ * on 2 x B200 the fused form hides 16 us of exchange but its scattered 8-byte peer stores cost
+ * the sweep 25 us (profiles/r01_multi_gpu.md), so it is opt-in. */
 int musb200_set_fused_push(int flag);
 
 /* ---- ghost interpolation: levelDesc%intpFromFiner / intpFromCoarser(order) -

@@ -207,7 +207,9 @@ struct Context {
   int graphMin = -1, graphMax = -1, graphSlot = -1, graphParity = -1;
   cudaGraphExec_t graphExec = nullptr;
   long long graphLaunches = 0;
-  int fusedPush = 1; // peer-memory exchange: links stored by the sweep itself (musb200_set_fused_push)
+  // peer-memory exchange with the links stored by the sweep itself (musb200_set_fused_push):
+  // measured 1.1 % slower than the separate, coalescing push kernel (profiles/r01_multi_gpu.md)
+  int fusedPush = 0;
   int noFusedBc = 0; // musb200_set_fused_bc(0): always take the two-phase bcBuffer path
   int overlap = 0;   // measured slower than exchange-after-compute at 256^3 per GPU (profiles/)
   NcclApi *nccl = nullptr;

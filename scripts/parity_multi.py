@@ -30,8 +30,8 @@ def main():
     ap.add_argument("--octants", type=int, default=8)
     ap.add_argument("--overlap", action="store_true")
     ap.add_argument("--p2p", action="store_true")
-    ap.add_argument("--no-fused-push", action="store_true",
-                    help="peer-memory exchange with the separate push kernel instead of the push fused into the sweep")
+    ap.add_argument("--fused-push", action="store_true",
+                    help="peer-memory exchange with the push fused into the sweep kernel")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -78,7 +78,7 @@ def main():
         mb.mus_init(rank, world, int(os.environ.get("LOCAL_RANK", rank)), bytes(t.numpy().tobytes()))
         # single-domain oracle = the truth for every rank
         mb._lib.check(mb._lib.lib.musb200_set_overlap(1 if a.overlap else 0))
-        mb._lib.check(mb._lib.lib.musb200_set_fused_push(0 if a.no_fused_push else 1))
+        mb._lib.check(mb._lib.lib.musb200_set_fused_push(1 if a.fused_push else 0))
         gl = mo.build_level_desc(a.level, QQ, a.kind, octants=a.octants)
         ref = mo.Scheme(gl, a.relaxation, "fluid", omega=1.7, lambda_=0.25, omega_bulk=1.3)
         gld = mb.LevelDesc(a.level, QQ, a.kind, 0, 1, octants=a.octants)

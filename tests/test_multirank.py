@@ -44,11 +44,11 @@ def _ngpu():
     ("d3q27", "mrt", "periodic", ["--p2p"]),                 # peer-memory halo exchange
     ("d3q19", "trt", "cavity", ["--octants", "2", "--p2p"]),
     ("d3q19", "bgk", "channel", ["--p2p", "--overlap"]),
-    ("d3q27", "mrt", "periodic", ["--p2p", "--no-fused-push"]),   # separate push kernel
-    ("d3q19", "trt", "cavity", ["--octants", "2", "--p2p", "--no-fused-push"])],
+    ("d3q27", "mrt", "periodic", ["--p2p", "--fused-push"]),      # links stored by the sweep itself
+    ("d3q19", "trt", "cavity", ["--octants", "2", "--p2p", "--fused-push"])],
     ids=["mrt27-periodic", "trt19-cavity", "bgk19-channel", "mrt27-periodic-overlap", "trt19-cavity-2oct",
          "mrt27-periodic-p2p", "trt19-cavity-2oct-p2p", "bgk19-channel-p2p-overlap",
-         "mrt27-periodic-p2p-unfused", "trt19-cavity-2oct-p2p-unfused"])
+         "mrt27-periodic-p2p-fusedpush", "trt19-cavity-2oct-p2p-fusedpush"])
 def test_multi_gpu_matches_single_domain_oracle(layout, relax, kind, extra):
     n = _ngpu()
     if n < 2:
