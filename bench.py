@@ -473,7 +473,9 @@ def main():
     # ---------------- end to end through the C ABI with host buffers --------
     e2e = None
     if not args.no_e2e:
-        check(lib.musb200_set_aux_every_step(1))     # the probe is tracked every iteration
+        # the probe is tracked every iteration: lazy auxField, the tracked element's moments are
+        # computed on demand (musb200_aux_probe) instead of materialising auxField every step
+        check(lib.musb200_set_aux_every_step(2))
         probe = np.zeros(4)
         Ke = K
         barrier()
@@ -482,10 +484,13 @@ def main():
         check(lib.musb200_state_upload(level, 2, host_state.ctypes.data))
         check(lib.musb200_set_now_next(level, 1, 2))
         check(lib.musb200_state_copy_next_to_now(level))
-        for _ in range(Ke):
-            if lid_pinned is not None:
-                check(lib.musb200_bc_set_values(level, 2, lid_pinned.size, lid_pinned.ctypes.data))
+        if lid_pinned is not None:
+            check(lib.musb200_bc_set_values(level, 2, lid_pinned.size, lid_pinned.ctypes.data))
+        for it in range(Ke):
             check(lib.musb200_step(level, level, 1))
+            if lid_pinned is not None and it + 1 < Ke:
+                # the next step's boundary values go up while this step runs (copy stream)
+                check(lib.musb200_bc_set_values(level, 2, lid_pinned.size, lid_pinned.ctypes.data))
             check(lib.musb200_aux_probe(level, 1, probe.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
         check(lib.musb200_state_download(level, sch.now_next(level)[1], host_state.ctypes.data))
         sch.synchronize()
@@ -495,7 +500,8 @@ def main():
         e2e = {"value": nFluid_total * Ke / dt / 1e6, "unit": "MLUPS",
                "h2d_bytes_per_step": int(nbytes / Ke + bc_bytes), "d2h_bytes_per_step": int(nbytes / Ke + 32),
                "steps": Ke, "wall_s": dt,
-               "protocol": "pinned-host state upload + K x (BC values H2D, level step, probe D2H) + state download"}
+               "protocol": "pinned-host state upload + K x (BC values H2D on the copy stream, level step, "
+                           "probe element computed on demand + D2H) + state download"}
         check(lib.musb200_set_aux_every_step(0))
 
     cb = None

@@ -189,6 +189,10 @@ int musb200_bc_register_elems(int level, int bc_id, int nElems, const int32_t *e
  * velocity boundaries 3 per link; pressure boundaries 1 per boundary element as lattice
  * density (pressure * cs2inv / fac%press, mus_bc_fluid_module.fpp:1270) */
 int musb200_bc_set_values(int level, int bc_id, int nVals, const double *vals);
+/* The copy runs on a dedicated stream and overlaps the level step in flight; the values become
+ * current at the next musb200_step.  Pageable host memory is staged before the call returns;
+ * pinned memory (musb200_host_alloc) must stay unchanged until that step has been issued and
+ * the copy has completed (musb200_synchronize, or any call that reads back). */
 
 /* ---- halo exchange: tem_communication_type --------------------------------
  * tem/source/tem_comm_module.fpp:93-177; pos(iProc) = buf_real(iProc)%pos.
@@ -241,8 +245,12 @@ int musb200_intp_register(int tgtLevel, int direction, int order, int nTargets,
  * (mus/source/mus_control_module.f90:242-701) on the device: set_boundary, swap,
  * fused auxField + stream-collide, halo exchange, ghost interpolation.         */
 int musb200_step(int minLevel, int maxLevel, int nCoarseCycles);
-/* 1: auxField is written by every level step (needed by tracking every step);
- * 0 (default): only where the schedule reads it and on the last step of a call */
+/* 1: auxField is written by every level step;
+ * 0 (default): only where the schedule reads it and on the last step of a call;
+ * 2 (lazy): only where the schedule reads it -- musb200_aux_probe and musb200_aux_download
+ *    compute the requested entries on demand from state(:, nNow), which still holds what the
+ *    last step pulled from (tracking of a few elements every step then costs a one-thread
+ *    kernel instead of 32 B of HBM writes per element and step) */
 int musb200_set_aux_every_step(int flag);
 /* 1: on several ranks the elements that own a send-buffer link (prp_sendHalo) are swept first
  * and their halo exchange (on a second, high-priority stream) overlaps the sweep of the

@@ -107,6 +107,12 @@ struct BcData {
   int id = 0, kind = 0, nLinks = 0;
   DevBuf<int32_t> links, outPos, posInBuffer, iDir;
   DevBuf<double> vals;
+  // musb200_bc_set_values copies into valsNext on the copy stream (overlapping the running step);
+  // the next set_boundary waits for the copy and swaps the buffers in
+  DevBuf<double> valsNext;
+  bool pending = false;
+  cudaEvent_t copied = nullptr;
+  ~BcData() { if (copied) cudaEventDestroy(copied); }
   // velocity_bounceback: links grouped per boundary element (fused kernel, bc.cu)
   bool fusable = false;
   int nGroups = 0;
@@ -161,6 +167,7 @@ struct Level {
   DevBuf<uint32_t> nbr;
   DevBuf<int32_t> bcElems;
   std::vector<int32_t> bcElemsHost;
+  bool auxValid = false;            // auxField holds the moments of the last level step
   int bcFused = -1;                 // -1 unknown, 0 two-phase (bcBuffer), 1 fused kernels
   std::vector<char> bcSlotNeeded;   // bcBuffer slots read by a non-wall boundary
   DevBuf<int32_t> bcNeeded;         // those slots (1-based), compact
@@ -199,9 +206,12 @@ struct Context {
   int rank = 0, nranks = 1, device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t commStream = nullptr;   // halo exchange, high priority, overlaps the interior sweep
+  cudaStream_t copyStream = nullptr;   // boundary values host -> device, overlaps the running step
+  cudaEvent_t evBcDone = nullptr;      // the boundary kernels of the last step have read their values
   cudaEvent_t evBoundary = nullptr, evComm = nullptr;
   // CUDA graph of two coarse cycles (after two cycles every level's now/next parity is back where
   // it started, so the captured kernel arguments are valid for every replay)
+  bool capturing = false;
   int useGraphs = 1;
   unsigned long long epoch = 0, graphEpoch = 0;
   int graphMin = -1, graphMax = -1, graphSlot = -1, graphParity = -1;
@@ -286,8 +296,21 @@ enum { T_COMPUTE = 0, T_BC = 1, T_COMM = 2, T_INTP = 3 };
 
 // ---------------------------------------------------------------------------
 // the schedule
+// boundary values handed over since the last step: wait for their copies, make them current
+static int applyPendingBc(Level &L) {
+  for (auto &b : L.bcs) {
+    if (!b->pending) continue;
+    MUSB_CUDA(cudaStreamWaitEvent(g.stream, b->copied, 0));
+    std::swap(b->vals.p, b->valsNext.p);
+    std::swap(b->vals.n, b->valsNext.n);
+    b->pending = false;
+  }
+  return 0;
+}
+
 static int setBoundary(Level &L) {
   if (L.bcElems.n == 0) return 0;
+  MUSB_TRY(applyPendingBc(L));
   Timed t(T_BC);
   double *st = L.state[L.nNext].p;
   bool any = false;
@@ -506,9 +529,13 @@ static int levelStep(int iLevel, int minLevel, int maxLevel, bool lastCycle) {
     for (int n = 0; n < 2; ++n) MUSB_TRY(levelStep(iLevel + 1, minLevel, maxLevel, lastCycle && n == 1));
   }
   MUSB_TRY(setBoundary(L));
+  if (!g.capturing && L.bcElems.n) MUSB_CUDA(cudaEventRecord(g.evBcDone, g.stream));
   std::swap(L.nNow, L.nNext);
   // multi-level: the interpolation routines read auxField of their sources every step
-  const bool writeAux = g.auxEveryStep || multi || lastCycle || L.auxForBc;
+  // auxEveryStep: 0 = on the last step of a call, 1 = every step, 2 = lazy (only where the
+  // schedule reads it; musb200_aux_probe / _download compute it on demand)
+  const bool writeAux = g.auxEveryStep == 1 || multi || (lastCycle && g.auxEveryStep != 2) || L.auxForBc;
+  L.auxValid = writeAux;
   if (!multi && g.nranks > 1 && g.overlap && L.nSendElems > 0) {
     // single level, several ranks: sweep the send-halo elements first, then exchange them on the
     // communication stream while the remaining elements are swept (the reference exchanges
@@ -603,6 +630,9 @@ int musb200_init(int rank, int nranks, int local_device, const void *nccl_unique
     MUSB_CUDA(cudaStreamCreateWithPriority(&g.commStream, cudaStreamNonBlocking, hi));
     MUSB_CUDA(cudaEventCreateWithFlags(&g.evBoundary, cudaEventDisableTiming));
     MUSB_CUDA(cudaEventCreateWithFlags(&g.evComm, cudaEventDisableTiming));
+    MUSB_CUDA(cudaStreamCreateWithFlags(&g.copyStream, cudaStreamNonBlocking));
+    MUSB_CUDA(cudaEventCreateWithFlags(&g.evBcDone, cudaEventDisableTiming));
+    MUSB_CUDA(cudaEventRecord(g.evBcDone, g.stream));
   }
   MUSB_CUDA(cudaEventCreate(&g.mark[0]));
   MUSB_CUDA(cudaEventCreate(&g.mark[1]));
@@ -636,8 +666,11 @@ int musb200_finalize(void) {
   cudaEventDestroy(g.evBoundary); cudaEventDestroy(g.evComm);
   cudaStreamSynchronize(g.commStream);
   cudaStreamDestroy(g.commStream);
+  cudaStreamSynchronize(g.copyStream);
+  cudaStreamDestroy(g.copyStream);
+  cudaEventDestroy(g.evBcDone);
   cudaStreamDestroy(g.stream);
-  g.stream = nullptr; g.commStream = nullptr;
+  g.stream = nullptr; g.commStream = nullptr; g.copyStream = nullptr;
   g.ready = false;
   g.launches = 0;
   return 0;
@@ -783,14 +816,31 @@ int musb200_aux_upload(int level, const double *aos_aux) {
   if (!aos_aux) return setError(MUSB200_ERR_ARG, "null argument");
   return uploadAos(L, aos_aux, L->aux.p, L->nAux);
 }
+// auxField of the elements [first, first + count) of the last level step, from state(:, now)
+static int auxOnDemand(Level *L, int first, int count) {
+  if (L->auxValid || !L->relaxSet || L->kind == MUSB200_KIND_PASSIVE_SCALAR) return 0;
+  SweepArgs a{};
+  a.in = L->state[L->nNow].p; a.nbr = L->nbr.p; a.aux = L->aux.p; a.S = L->S;
+  a.first = first; a.count = count;
+  a.force_order = L->forceOrder;
+  a.force = L->forceElem ? L->force.p : nullptr;
+  for (int k = 0; k < 3; ++k) a.force_uniform[k] = L->forceUniform[k];
+  MUSB_TRY(launchAuxOnly(L->QQ, L->kind, a, g.stream));
+  ++g.launches;
+  return 0;
+}
+
 int musb200_aux_download(int level, double *aos_aux) {
   GET_LEVEL(L, level);
   if (!aos_aux) return setError(MUSB200_ERR_ARG, "null argument");
+  MUSB_TRY(auxOnDemand(L, 0, L->nSolve));
+  if (L->relaxSet && L->kind != MUSB200_KIND_PASSIVE_SCALAR) L->auxValid = true;
   return downloadAos(L, L->aux.p, aos_aux, L->nAux);
 }
 int musb200_aux_probe(int level, int elemPos, double *out) {
   GET_LEVEL(L, level);
   if (!out || elemPos < 1 || elemPos > L->nElems) return setError(MUSB200_ERR_ARG, "bad probe element");
+  if (elemPos <= L->nSolve) MUSB_TRY(auxOnDemand(L, elemPos - 1, 1));
   MUSB_CUDA(cudaMemcpy2DAsync(out, sizeof(double), L->aux.p + (elemPos - 1), (size_t)L->S * sizeof(double),
                               sizeof(double), (size_t)L->nAux, cudaMemcpyDeviceToHost, g.stream));
   MUSB_CUDA(cudaStreamSynchronize(g.stream));
@@ -1126,10 +1176,19 @@ int musb200_bc_set_values(int level, int bc_id, int nVals, const double *vals) {
   for (auto &b : L->bcs) {
     if (b->id != bc_id) continue;
     if (nVals < 0 || (nVals > 0 && !vals)) return setError(MUSB200_ERR_ARG, "bad values");
-    if (b->vals.n != (size_t)nVals) MUSB_TRY(b->vals.alloc((size_t)nVals));
+    if (!b->copied) MUSB_CUDA(cudaEventCreateWithFlags(&b->copied, cudaEventDisableTiming));
+    // valsNext was the active buffer until the last swap: its last readers are the boundary
+    // kernels of an earlier step
+    MUSB_CUDA(cudaStreamWaitEvent(g.copyStream, g.evBcDone, 0));
+    if (b->valsNext.n != (size_t)nVals) {
+      MUSB_CUDA(cudaStreamSynchronize(g.copyStream));   // a pending copy into the old allocation
+      MUSB_TRY(b->valsNext.alloc((size_t)nVals));
+    }
     if (nVals)
-      MUSB_CUDA(cudaMemcpyAsync(b->vals.p, vals, (size_t)nVals * sizeof(double), cudaMemcpyHostToDevice,
-                                g.stream));
+      MUSB_CUDA(cudaMemcpyAsync(b->valsNext.p, vals, (size_t)nVals * sizeof(double), cudaMemcpyHostToDevice,
+                                g.copyStream));
+    MUSB_CUDA(cudaEventRecord(b->copied, g.copyStream));
+    b->pending = true;
     return 0;
   }
   return setError(MUSB200_ERR_ARG, "unknown boundary id " + std::to_string(bc_id));
@@ -1335,7 +1394,7 @@ int musb200_intp_register(int tgtLevel, int direction, int order, int nTargets,
 // ---------------------------------------------------------------------------
 int musb200_set_aux_every_step(int flag) {
   ++g.epoch;
-  g.auxEveryStep = flag ? 1 : 0;
+  g.auxEveryStep = (flag == 2) ? 2 : (flag ? 1 : 0);
   return 0;
 }
 
@@ -1356,7 +1415,9 @@ static int stepGraphed(int minLevel, int maxLevel, int nPairs) {
     cudaGraph_t graph = nullptr;
     MUSB_CUDA(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
     int rc = 0;
+    g.capturing = true;
     for (int it = 0; it < 2 && rc == 0; ++it) rc = levelStep(minLevel, minLevel, maxLevel, false);
+    g.capturing = false;
     cudaError_t ce = cudaStreamEndCapture(g.stream, &graph);
     g.auxEveryStep = auxSave;
     g.graphLaunches = g.launches - before;
@@ -1385,9 +1446,17 @@ int musb200_step(int minLevel, int maxLevel, int nCoarseCycles) {
   if (g.useGraphs && g.nranks == 1 && !g.profiling && nCoarseCycles >= 8) {
     // all but the last cycles (the last one materialises auxField) in pairs through the graph
     const int nPairs = (nCoarseCycles - 1) / 2;
-    for (int l = minLevel; l <= maxLevel; ++l)
-      if (!findLevel(l)) return setError(MUSB200_ERR_ARG, "level " + std::to_string(l) + " was not created");
+    for (int l = minLevel; l <= maxLevel; ++l) {
+      Level *Lg = findLevel(l);
+      if (!Lg) return setError(MUSB200_ERR_ARG, "level " + std::to_string(l) + " was not created");
+      MUSB_TRY(applyPendingBc(*Lg));   // cross-stream waits stay outside the capture
+    }
     MUSB_TRY(stepGraphed(minLevel, maxLevel, nPairs));
+    for (int l = minLevel; l <= maxLevel; ++l) {
+      Level *Lg = findLevel(l);
+      if (Lg->bcElems.n) MUSB_CUDA(cudaEventRecord(g.evBcDone, g.stream));
+      Lg->auxValid = (maxLevel > minLevel) || g.auxEveryStep == 1 || Lg->auxForBc;
+    }
     it = 2 * nPairs;
   }
   for (; it < nCoarseCycles; ++it)

@@ -43,6 +43,8 @@ struct SweepArgs {
 };
 
 int launchSweep(int QQ, int relax, int kind, const SweepArgs &a, cudaStream_t st);
+// auxField of the elements [first, first + count) from state(:, now) (fluid kinds only)
+int launchAuxOnly(int QQ, int kind, const SweepArgs &a, cudaStream_t st);
 
 // passive scalar (passive_scalar.cu)
 struct PsArgs {

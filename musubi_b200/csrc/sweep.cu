@@ -26,4 +26,15 @@ int launchSweep(int QQ, int relax, int kind, const SweepArgs &a, cudaStream_t st
   return dispatchSweep<0>(QQ, relax, kind, a, st);
 }
 
+int launchAuxOnly(int QQ, int kind, const SweepArgs &a, cudaStream_t st) {
+  if (a.count <= 0) return 0;
+  const int grid = divUp(a.count, 128);
+  if (QQ == 19 && kind == 0) auxOnlyKernel<19, false><<<grid, 128, 0, st>>>(a);
+  else if (QQ == 19) auxOnlyKernel<19, true><<<grid, 128, 0, st>>>(a);
+  else if (kind == 0) auxOnlyKernel<27, false><<<grid, 128, 0, st>>>(a);
+  else auxOnlyKernel<27, true><<<grid, 128, 0, st>>>(a);
+  MUSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace musb200

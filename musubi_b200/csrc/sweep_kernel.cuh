@@ -204,6 +204,45 @@ __global__ void __launch_bounds__(sweepThreads<QQ>(), sweepMinBlocks<QQ>()) swee
   }
 }
 
+// auxField on demand (lazy auxField, tracking of single elements): the moments of the PDFs an
+// element pulls from state(:, now) -- exactly what the sweep of the same step computed, because
+// state(:, now) is not touched until the next step -- including the half-force velocity shift.
+template <int QQ, bool INCOMP>
+__global__ void __launch_bounds__(128) auxOnlyKernel(const SweepArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.count) return;
+  const int e = a.first + i;
+  const long long S = a.S;
+  double f[QQ];
+#pragma unroll
+  for (int q = 0; q < QQ - 1; ++q) {
+    const uint32_t n = a.nbr[q * S + e];
+    const long long row = (n & kBounceBit) ? (long long)invDir<QQ>(q) * S : (long long)q * S;
+    f[q] = a.in[row + (n & kElemMask)];
+  }
+  f[QQ - 1] = a.in[(long long)(QQ - 1) * S + e];
+  double rho, ux, uy, uz;
+  moments<QQ>(f, rho, ux, uy, uz);
+  if (!INCOMP) {
+    ux = ux / rho;
+    uy = uy / rho;
+    uz = uz / rho;
+  }
+  if (a.force_order == 2) {
+    double Fx, Fy, Fz;
+    if (a.force != nullptr) { Fx = a.force[e]; Fy = a.force[S + e]; Fz = a.force[2 * S + e]; }
+    else { Fx = a.force_uniform[0]; Fy = a.force_uniform[1]; Fz = a.force_uniform[2]; }
+    const double inv_rho = INCOMP ? 1.0 : 1.0 / rho;
+    ux = ux + Fx * 0.5 * inv_rho;
+    uy = uy + Fy * 0.5 * inv_rho;
+    uz = uz + Fz * 0.5 * inv_rho;
+  }
+  a.aux[e] = rho;
+  a.aux[S + e] = ux;
+  a.aux[2 * S + e] = uy;
+  a.aux[3 * S + e] = uz;
+}
+
 template <int QQ, int RELAX, bool INCOMP, int VAR>
 static int launchT(const SweepArgs &a, cudaStream_t st) {
   if (a.count <= 0) return 0;

@@ -83,28 +83,34 @@ def test_abi_error_behaviour(mb):
 
 
 def test_full_size_cavity_properties(mb):
-    """BASELINE config 2 at its full size (256^3, D3Q19 TRT, lid): index lists and state survive
-    the device round trip bit for bit, mass is conserved to 1e-13, nothing turns NaN"""
+    """BASELINE config 2 at its full size (256^3, D3Q19 TRT): index lists and state survive the
+    device round trip bit for bit; with the lid at rest (pure bounce-back box, swirling initial
+    flow) mass is conserved to 1e-13; with the lid moving nothing turns NaN and the only mass
+    source is the well-known one of velocity bounce-back at the lid's edges (< 1e-6 relative)"""
     from musubi_b200 import cases
     level, QQ = 8, 19
     ld = mb.LevelDesc(level, QQ, "cavity")
     assert ld.nFluid == 256 ** 3
     sch = mb.Scheme({"kind": "fluid", "relaxation": "trt", "layout": "d3q19"}, ld, 1.7, lambda_=3.0 / 16.0)
     assert np.array_equal(sch.download_neigh(level), ld.neigh)            # bit-exact index lists
-    rho, vel = cases.cavity_rest(ld)
+    rho, vel = cases.taylor_green(ld)
     st = cases.equilibrium_state(QQ, rho, vel, ld.nSize)
+    del rho, vel
     sch.upload_state(level, st)
     back = sch.download_state(level)
     assert np.array_equal(back, st)                                       # AOS -> SoA -> AOS identity
-    del back
-    sch.set_bc_values(level, 2, cases.lid_values(ld))
+    del back, st
+    sch.set_bc_values(level, 2, cases.lid_values(ld, (0.0, 0.0, 0.0)))    # closed box
     m0 = sch.reduce(level)[0]
-    assert abs(m0 / ld.nFluid - 1.0) < 1e-14
-    sch.do_computation(60)
+    sch.do_computation(40)
     mass, vmax, nan = sch.reduce(level)
-    assert nan == 0
+    assert nan == 0 and vmax > 0.0
     assert abs(mass / m0 - 1.0) < 1e-13
-    assert 0.0 < vmax < 0.06                                              # the lid (0.05) drives the flow
+    sch.set_bc_values(level, 2, cases.lid_values(ld))                     # lid at (0.05, 0, 0)
+    sch.do_computation(40)
+    mass2, vmax2, nan = sch.reduce(level)
+    assert nan == 0 and 0.0 < vmax2 < 0.2
+    assert abs(mass2 / mass - 1.0) < 1e-6
     # restart round trip at full size: dump in treeID order, perturb, restore, dump again
     tid = np.asarray(ld.total[:ld.nFluid], dtype=np.int64)
     lp = np.arange(1, ld.nFluid + 1, dtype=np.int32)

@@ -143,6 +143,34 @@ def test_step_graph_replay_equals_direct_launches(mb, oracle, graphs):
         check(lib.musb200_set_graphs(1))
 
 
+@pytest.mark.parametrize("force", [False, True], ids=["plain", "with-force"])
+def test_lazy_auxfield_on_demand_equals_the_sweeps(mb, oracle, force):
+    """musb200_set_aux_every_step(2): nothing is materialised by the sweep; the probe of one
+    element and the full download are computed on demand from state(:, now) and equal the
+    oracle's auxField of the last step bit for bit"""
+    from musubi_b200._lib import check, lib
+    ident = {"kind": "fluid", "relaxation": "trt", "layout": "d3q19"}
+    level = 4
+    ld, old, ref, sch = make_pair(mb, oracle, level, ident, 1.7, kind="cavity", ic="rest", lambda_=3.0 / 16.0)
+    if force:
+        ref.set_force([1e-5, -2e-5, 3e-6])
+        sch.set_force(level, [1e-5, -2e-5, 3e-6])
+    check(lib.musb200_set_aux_every_step(2))
+    try:
+        for k in (3, 1, 12):                      # 12 >= 8: the graph path
+            sch.do_computation(k)
+            ref.run(k)
+            exp = ref.aux[:ld.nFluid * 4].reshape(-1, 4)
+            for e in (1, 77, ld.nFluid):
+                assert np.array_equal(sch.aux_probe(level, e), exp[e - 1])
+        assert np.array_equal(sch.download_aux(level)[:ld.nFluid * 4], ref.aux[:ld.nFluid * 4])
+        n = ld.nFluid * ld.QQ
+        assert np.array_equal(sch.download_state(level)[:n], ref.state[ref.nNext][:n])
+    finally:
+        check(lib.musb200_set_aux_every_step(0))
+        sch.destroy()
+
+
 CHANNEL = [
     ({"kind": "fluid", "relaxation": "bgk", "layout": "d3q19"}, "pressure_expol"),
     ({"kind": "fluid", "relaxation": "mrt", "layout": "d3q27"}, "pressure_antibounceback"),
