@@ -239,3 +239,56 @@ def test_passive_scalar_coupled_to_flow_on_device(mbgpu, oracle):
     check(lib.musb200_set_aux_every_step(0))
     ps.destroy()
     flow.destroy()
+
+
+@pytest.mark.gpu
+def test_force_source_on_a_two_level_mesh_matches_oracle(mbgpu, oracle):
+    """the body force acts on every level (fluid + ghostFromCoarser elements, in lattice units of
+    that level: half the coarse value per finer level for a physically uniform force with acoustic
+    scaling); device and oracle stay bit-identical through the interpolation schedule"""
+    from test_multilevel import build
+    from musubi_b200._lib import check, lib
+    mb, QQ = mbgpu, 19
+    lv, intp, tables, ms = build(oracle, 4, [(5, 11)], QQ, "linear")
+    ident = {"kind": "fluid", "relaxation": "bgk", "layout": "d3q19"}
+    omega = {l: float(1.0 / (3.0 * s.visc[0] + 0.5)) for l, s in ms.s.items()}
+    visc = {l: float(s.visc[0]) for l, s in ms.s.items()}
+    sch = mb.Scheme(ident, lv, omega, omega_bulk=1.2, intp=(tables, intp["order"]), viscosity=visc)
+    for l, s in ms.s.items():
+        sch.upload_state(l, s.state[s.nNow], s.state[s.nNext])
+        check(lib.musb200_aux_upload(l, s.aux.ctypes.data))
+        Fl = F * 0.5 ** (l - min(lv))            # body_force factor rho0 dx / dt^2 doubles per level
+        s.set_force(Fl)
+        sch.set_force(l, Fl)
+    sch.do_computation(10)
+    ms.run(10)
+    for l, s in ms.s.items():
+        n = lv[l].nElems * QQ
+        assert np.array_equal(sch.download_state(l)[:n], s.state[s.nNext][:n])
+    sch.destroy()
+
+
+@pytest.mark.gpu
+def test_passive_scalar_around_a_sphere_from_mesh_file(mbgpu, oracle, tmp_path):
+    """passive scalar on a mesh that only exists as treelm files, bounce-back at the obstacle:
+    device = oracle bit for bit and the scalar's mass is conserved"""
+    from musubi_b200 import treelm_io as tio
+    from test_treelm_io import _sphere_mesh
+    mb, QQ = mbgpu, 19
+    fd = tio.FileLevelDesc(_sphere_mesh(tmp_path), QQ)
+    ref = oracle.PassiveScalarScheme(fd, "bgk", "second", diff_coeff=0.02)
+    rng = np.random.default_rng(8)
+    ref.init_equilibrium(1.0 + 0.3 * rng.random(fd.nElems))
+    ref.set_transport_velocity([0.04, 0.01, -0.02])
+    sch = mb.Scheme({"kind": "passive_scalar", "relaxation": {"name": "bgk", "variant": "second"},
+                     "layout": "d3q19"}, fd, species={"diff_coeff": 0.02})
+    sch.set_transport_velocity(fd.level, [0.04, 0.01, -0.02])
+    sch.upload_state(fd.level, ref.state[ref.nNow], ref.state[ref.nNext])
+    m0 = ref.total_mass()
+    ref.run(30)
+    sch.do_computation(30)
+    k = fd.nFluid * QQ
+    got = sch.download_state(fd.level)[:k]
+    assert np.array_equal(got, ref.state[ref.nNext][:k])
+    assert abs(math.fsum(got) / m0 - 1.0) < 1e-13
+    sch.destroy()
