@@ -12,8 +12,9 @@ Workloads (BASELINE.json configs):
                 level-9 cube (512x256x256, 512x512x256, 512^3 -- the "512^3-equivalent mesh" of
                 north_star at 8 GPUs), SFC-partitioned into N equal Morton ranges, halo exchange
                 through peer memory over NVLink (NCCL send/recv with --no-p2p)
-  --workload cfg4 : BASELINE config 4, two-level octree with linear ghost interpolation on one
-                GPU; a step is one coarse cycle (1 coarse + 2 fine level steps)
+  --workload cfg4 : BASELINE config 4, two-level octree with linear ghost interpolation; a step is
+                one coarse cycle (1 coarse + 2 fine level steps); with --gpus N the mesh is cut along
+                the global space-filling curve (strong scaling)
   --workload cfg3 : D3Q27 MRT periodic 512^3 (level 9) strong-scaled over N ranks (BASELINE
                 config 3; also cfg3-256 on one GPU)
 A "step" is one level time step (set_boundary, swap, fused aux+stream+collide,
@@ -185,18 +186,47 @@ def run_reference(args, wl_name, wl):
 
 # ---------------------------------------------------------------------------
 def run_multilevel(args, wl_name, wl):
-    """cfg4 on one GPU: K coarse cycles of do_recursive_multiLevel, device timed."""
+    """cfg4: K coarse cycles of do_recursive_multiLevel, device timed; on N > 1 ranks the mesh is
+    cut along the global space-filling curve (strong scaling), halo exchange per level over NCCL."""
     import musubi_b200 as mb
+    from musubi_b200 import cases
     from musubi_b200 import treelm_multilevel as tm
     from musubi_b200._lib import check, lib
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     W, K = max(3, args.warmup), max(1, args.steps)
-    mb.mus_init(0, 1, int(os.environ.get("LOCAL_RANK", "0")))
+    dist, uid = None, None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        t = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            t = torch.frombuffer(bytearray(mb.get_unique_id()), dtype=torch.uint8).clone()
+        dist.broadcast(t, 0)
+        uid = bytes(t.numpy().tobytes())
+    mb.mus_init(rank, world, local_rank, uid)
+
+    def allred(x, op):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
+        return float(t[0])
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
     t_setup = time.perf_counter()
     minL = args.level or WORKLOADS[wl_name]["level"]
     scale = 2.0 ** (minL - WORKLOADS[wl_name]["level"])      # boxes / cylinder are given at the base level
     boxes = [(int(lo * scale), int(hi * scale)) for lo, hi in wl["boxes"]]
     cyl = tuple(c * scale for c in wl["cylinder"][:3]) + tuple(int(c * scale) for c in wl["cylinder"][3:])
-    lv, intp = tm.build_multilevel(minL, boxes, QQ=19, cylinder=cyl, intp_method="linear")
+    glob, intp = tm.build_multilevel(minL, boxes, QQ=19, cylinder=cyl, intp_method="linear")
+    lv = glob if world == 1 else tm.partition_multilevel(glob, world)[rank]
     tables = mb.multilevel_tables(lv, intp)
     levels = sorted(lv)
     nu0 = (1.0 / wl["omega"] - 0.5) / 3.0
@@ -211,7 +241,6 @@ def run_multilevel(args, wl_name, wl):
         vel = np.stack([u0 * np.sin(x[:, 0]) * np.cos(x[:, 1]) * np.cos(x[:, 2]) + 0.02,
                         -u0 * np.cos(x[:, 0]) * np.sin(x[:, 1]) * np.cos(x[:, 2]),
                         np.zeros(L.nElems)], axis=1)
-        from musubi_b200 import cases
         host[l] = cases.equilibrium_state(19, np.ones(L.nElems), vel, L.nSize)
         nbytes += host[l].nbytes
         sch.upload_state(l, host[l])
@@ -221,35 +250,46 @@ def run_multilevel(args, wl_name, wl):
     sch.synchronize()
     setup_s = time.perf_counter() - t_setup
     upd = {l: 2 ** (l - levels[0]) for l in levels}                # level steps per coarse cycle
-    lups_cycle = sum(lv[l].nFluid * upd[l] for l in levels)
-    solve_cycle = sum((lv[l].nFluid + lv[l].nGhostFromCoarser) * upd[l] for l in levels)
+    lups_cycle = allred(float(sum(lv[l].nFluid * upd[l] for l in levels)), "SUM")
+    solve_cycle = sum((lv[l].nFluid + lv[l].nGhostFromCoarser) * upd[l] for l in levels)   # this rank
+
+    def timed_region():
+        barrier()
+        sch.synchronize()
+        check(lib.musb200_event_mark(0))
+        sch.do_computation(K)
+        check(lib.musb200_event_mark(1))
+        sch.synchronize()
+        barrier()
+        ms = ctypes.c_double()
+        check(lib.musb200_event_elapsed(ctypes.byref(ms)))
+        return allred(ms.value, "MAX")
 
     sch.do_computation(W)
     sch.synchronize()
-    check(lib.musb200_set_profiling(1))
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     check(lib.musb200_timers_reset())
-    sampler = ClockSampler(0)
-    sampler.start()
-    check(lib.musb200_event_mark(0))
-    sch.do_computation(K)
-    check(lib.musb200_event_mark(1))
-    sch.synchronize()
-    ms = ctypes.c_double()
-    check(lib.musb200_event_elapsed(ctypes.byref(ms)))
-    clocks = sampler.finish()
-    cm, bm, com, im = (ctypes.c_double() for _ in range(4))
-    check(lib.musb200_timers(ctypes.byref(cm), ctypes.byref(bm), ctypes.byref(com), ctypes.byref(im)))
+    t_ms = timed_region()                       # region 1: nothing but the cycle's own launches
     nl = ctypes.c_longlong()
     check(lib.musb200_launch_count(ctypes.byref(nl)))
+    check(lib.musb200_set_profiling(1))         # region 2: CUDA events around every stage
+    check(lib.musb200_timers_reset())
+    t2_ms = timed_region()
+    clocks = sampler.finish() if rank == 0 else None
+    cm, bm, com, im = (ctypes.c_double() for _ in range(4))
+    check(lib.musb200_timers(ctypes.byref(cm), ctypes.byref(bm), ctypes.byref(com), ctypes.byref(im)))
     check(lib.musb200_set_profiling(0))
-    value = lups_cycle * K / (ms.value * 1e-3) / 1e6
+    value = lups_cycle * K / (t_ms * 1e-3) / 1e6
     sweep_ms = cm.value / K
     peak, peak_src = measured_peak()
     achieved = BYTES_PER_LUP[19] * float(solve_cycle) / (sweep_ms * 1e-3) / 1e9
-    mass = sum(sch.reduce(l)[0] / 8.0 ** (l - levels[0]) for l in levels)
+    mass = allred(sum(sch.reduce(l)[0] / 8.0 ** (l - levels[0]) for l in levels), "SUM") if world == 1 else None
 
     e2e = None
     if not args.no_e2e:
+        barrier()
         t0 = time.perf_counter()
         for l in levels:
             sch.upload_state(l, host[l])
@@ -257,34 +297,44 @@ def run_multilevel(args, wl_name, wl):
         for l in levels:
             host[l] = sch.download_state(l)
         sch.synchronize()
-        dt = time.perf_counter() - t0
+        barrier()
+        dt = allred(time.perf_counter() - t0, "MAX")
         e2e = {"value": lups_cycle * K / dt / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": int(2 * nbytes / K),
                "d2h_bytes_per_step": int(nbytes / K), "steps": K, "wall_s": dt,
                "protocol": "state upload of every level (pageable host arrays) + K coarse cycles + state download"}
-    line = {
-        "metric": "MLUPS", "value": value, "unit": "MLUPS", "n_gpus": 1, "steps": K, "warmup": W,
-        "ms_per_step": ms.value / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl_name + ": " + wl["name"], "levels": levels,
-                   "cells": {str(l): int(lv[l].nFluid) for l in levels},
-                   "ghostFromCoarser": {str(l): int(lv[l].nGhostFromCoarser) for l in levels},
-                   "ghostFromFiner": {str(l): int(lv[l].nGhostFromFiner) for l in levels},
-                   "step": "one coarse cycle = %s level steps" % "+".join(str(upd[l]) for l in levels),
-                   "mlups_definition": "sum_l nFluid(l) * 2^(l-minLevel) per coarse cycle / time (SURVEY 8d)",
-                   "interpolation": "linear", "omega": {str(l): omega[l] for l in levels},
-                   "l2": "state %.2f GB > 126 MB L2" % (2 * nbytes / 1e9), "setup_s": round(setup_s, 2)},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "sweepKernel<19,bgk> (all level steps of a cycle)",
-                     "bytes_per_lup": BYTES_PER_LUP[19], "kernel_ms": sweep_ms,
-                     "share_of_step": sweep_ms / (ms.value / K)},
-        "timers_ms_per_step": {"compute": cm.value / K, "bc": bm.value / K, "comm": com.value / K,
-                               "intp": im.value / K},
-        "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(nl.value), "clocks": clocks,
-        "check": {"total_mass": mass},
-    }
-    print(json.dumps(line), flush=True)
+    if rank == 0:
+        line = {
+            "metric": "MLUPS", "value": value, "unit": "MLUPS", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": t_ms / K, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl_name + ": " + wl["name"], "levels": levels,
+                       "cells": {str(l): int(glob[l].nFluid) for l in levels},
+                       "rank0": {str(l): {"fluid": int(lv[l].nFluid), "ghostFromCoarser": int(lv[l].nGhostFromCoarser),
+                                          "ghostFromFiner": int(lv[l].nGhostFromFiner), "halo": int(lv[l].nHalo)}
+                                 for l in levels},
+                       "partition": "global space-filling curve over all levels, %d equal ranges; ghosts "
+                                    "interpolated locally, fluid-only halos over NCCL" % world,
+                       "step": "one coarse cycle = %s level steps" % "+".join(str(upd[l]) for l in levels),
+                       "mlups_definition": "sum_l nFluid(l) * 2^(l-minLevel) per coarse cycle / time (SURVEY 8d)",
+                       "interpolation": "linear", "omega": {str(l): omega[l] for l in levels},
+                       "l2": "state %.2f GB per rank > 126 MB L2" % (2 * nbytes / 1e9), "setup_s": round(setup_s, 2)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "kernel": "sweepKernel<19,bgk> (all level steps of a cycle, rank 0)",
+                         "bytes_per_lup": BYTES_PER_LUP[19], "kernel_ms": sweep_ms,
+                         "share_of_step": sweep_ms / (t2_ms / K)},
+            "timers_ms_per_step": {"compute": cm.value / K, "bc": bm.value / K, "comm": com.value / K,
+                                   "intp": im.value / K},
+            "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(nl.value), "clocks": clocks,
+            "check": {"total_mass": mass},
+        }
+        print(json.dumps(line), flush=True)
+    sch.synchronize()
+    barrier()
     sch.destroy()
     mb.mus_finalize()
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 def main():
@@ -325,8 +375,6 @@ def main():
         run_reference(args, wl_name, wl)
         return
     if wl["kind"] == "multilevel":
-        if world > 1:
-            raise SystemExit("cfg4 runs on one GPU (the multi-level mesh generator is single-rank)")
         run_multilevel(args, wl_name, wl)
         return
     W = max(3, args.warmup)

@@ -132,6 +132,11 @@ struct CommBuf {
   int total = 0;
   DevBuf<int32_t> pos;
   DevBuf<double> buf;
+  // auxField%sendBuffer / recvBuffer (mus_auxField_module.f90:377-396) of the same elements: the
+  // four auxField entries of every element that appears in `pos`, in order of first appearance
+  std::vector<int> auxNVals, auxOffset;
+  int auxTotal = 0;
+  DevBuf<int32_t> auxPos;
 };
 
 // peer-memory halo exchange of one level (p2p.cu)
@@ -418,18 +423,24 @@ static int exchange(Level &L, int kind, double *state, int nComp, cudaStream_t s
     ++g.launches;
     return 0;
   }
-  if (s.total) {
-    MUSB_TRY(launchPack(nComp, state, L.S, s.pos.p, s.total, s.buf.p, st));
+  // the auxField travels through its own position lists (four entries per element)
+  const bool isAux = (state == L.aux.p);
+  const int32_t *sPos = isAux ? s.auxPos.p : s.pos.p, *rPos = isAux ? r.auxPos.p : r.pos.p;
+  const int sTotal = isAux ? s.auxTotal : s.total, rTotal = isAux ? r.auxTotal : r.total;
+  const std::vector<int> &sN = isAux ? s.auxNVals : s.nVals, &sO = isAux ? s.auxOffset : s.offset;
+  const std::vector<int> &rN = isAux ? r.auxNVals : r.nVals, &rO = isAux ? r.auxOffset : r.offset;
+  if (sTotal) {
+    MUSB_TRY(launchPack(nComp, state, L.S, sPos, sTotal, s.buf.p, st));
     ++g.launches;
   }
   MUSB_NCCL(g.nccl->GroupStart());
   for (size_t i = 0; i < s.proc.size(); ++i)
-    MUSB_NCCL(g.nccl->Send(s.buf.p + s.offset[i], (size_t)s.nVals[i], ncclDouble, s.proc[i], g.comm, st));
+    MUSB_NCCL(g.nccl->Send(s.buf.p + sO[i], (size_t)sN[i], ncclDouble, s.proc[i], g.comm, st));
   for (size_t i = 0; i < r.proc.size(); ++i)
-    MUSB_NCCL(g.nccl->Recv(r.buf.p + r.offset[i], (size_t)r.nVals[i], ncclDouble, r.proc[i], g.comm, st));
+    MUSB_NCCL(g.nccl->Recv(r.buf.p + rO[i], (size_t)rN[i], ncclDouble, r.proc[i], g.comm, st));
   MUSB_NCCL(g.nccl->GroupEnd());
-  if (r.total) {
-    MUSB_TRY(launchUnpack(nComp, state, L.S, r.pos.p, r.total, r.buf.p, st));
+  if (rTotal) {
+    MUSB_TRY(launchUnpack(nComp, state, L.S, rPos, rTotal, r.buf.p, st));
     ++g.launches;
   }
   return 0;
@@ -1210,6 +1221,28 @@ int musb200_comm_register(int level, int buf_kind, int dir, int nProcs, const in
   }
   MUSB_TRY(c.pos.upload(pos, (size_t)c.total, g.stream));
   MUSB_TRY(c.buf.alloc((size_t)std::max(1, c.total)));
+  c.auxNVals.clear(); c.auxOffset.clear(); c.auxTotal = 0;
+  if (buf_kind == MUSB200_BUF_HALO) {
+    std::vector<int32_t> apos;
+    std::vector<char> seen;
+    for (int i = 0; i < nProcs; ++i) {
+      seen.assign((size_t)L->nSize, 0);
+      const int before = (int)apos.size();
+      for (int j = c.offset[i]; j < c.offset[i] + c.nVals[i]; ++j) {
+        const int e = (pos[j] - 1) / L->QQ;
+        if (e < 0 || e >= L->nSize) return setError(MUSB200_ERR_ARG, "comm position outside the level");
+        if (seen[e]) continue;
+        seen[e] = 1;
+        for (int k = 0; k < 4; ++k) apos.push_back(e * 4 + k + 1);
+      }
+      c.auxOffset.push_back(before);
+      c.auxNVals.push_back((int)apos.size() - before);
+    }
+    c.auxTotal = (int)apos.size();
+    MUSB_TRY(c.auxPos.upload(apos.data(), apos.size(), g.stream));
+    if (c.auxTotal > c.total) MUSB_TRY(c.buf.alloc((size_t)c.auxTotal));
+    MUSB_CUDA(cudaStreamSynchronize(g.stream));
+  }
   if (buf_kind == MUSB200_BUF_HALO && dir == MUSB200_DIR_SEND) {
     std::vector<uint32_t> mask(((size_t)L->S + 31) / 32, 0u);
     std::vector<int32_t> elems;

@@ -370,3 +370,200 @@ def intp_tables(L, intp, direction, order=None):
                 posInMat=np.array(pim, dtype=np.int32), matOffset=matOff,
                 matrices=np.concatenate([M.ravel() for M in mats]) if mats else np.zeros(0),
                 coord=np.array(crd).reshape(-1, 3) if crd else np.zeros((0, 3)), nMat=len(mats))
+
+
+# ------------------------------------------------------------------------------------------------
+# several ranks: the global multi-level mesh cut along the space-filling curve
+# ------------------------------------------------------------------------------------------------
+def _sfc_keys(lv):
+    """position of every fluid element on the global space-filling curve: (level, index, key)"""
+    maxL = max(lv)
+    lvl, idx, key = [], [], []
+    for l, L in lv.items():
+        c = L.codes[:L.nFluid].astype(np.int64)
+        lvl.append(np.full(c.size, l, dtype=np.int64))
+        idx.append(np.arange(c.size, dtype=np.int64))
+        key.append(c << (3 * (maxL - l)))
+    lvl, idx, key = np.concatenate(lvl), np.concatenate(idx), np.concatenate(key)
+    o = np.argsort(key, kind="stable")
+    return lvl[o], idx[o]
+
+
+def _grow(mask, ngh, hops):
+    """elements within `hops` stencil neighbours of the masked ones (global positions)"""
+    out = mask.copy()
+    front = mask
+    for _ in range(hops):
+        rows = ngh[front]
+        nxt = np.zeros_like(out)
+        p = rows[rows > 0] - 1
+        nxt[p] = True
+        nxt &= ~out
+        out |= nxt
+        front = nxt
+    return out
+
+
+def partition_multilevel(lv, nranks):
+    """cut a single-rank multi-level mesh (build_multilevel) into `nranks` parts the way treelm
+    does -- equal contiguous ranges of the global space-filling curve over ALL levels
+    (treelmesh_module.f90:1276-1296) -- and build every rank's level descriptors.
+
+    Per rank and level the total list is [own fluid | ghostFromCoarser | ghostFromFiner | halo]:
+      * ghosts are LOCAL and recomputed by interpolation on every rank that needs them: the
+        ghostFromCoarser elements within two stencil hops of an own fluid element (nNesting = 2
+        sub-steps between interpolations), the ghostFromFiner ones within one hop, plus the ghosts
+        that serve as interpolation sources of those;
+      * halos are the remote FLUID elements that an own or ghost element pulls from or
+        interpolates from; they arrive through the level's halo buffer with all QQ links (and
+        their auxField entries), element-major, after every level step.
+    Only fluid elements travel; interpolation results never do.  The fluid elements of every
+    rank evolve bit-identically to the single-rank run.
+    returns [ {level: MLLevel} for each rank ]"""
+    levels = sorted(lv)
+    QQ = lv[levels[0]].QQ
+    glvl, gidx = _sfc_keys(lv)
+    N = glvl.size
+    base, rem = divmod(N, nranks)
+    cnt = np.array([base + (1 if r < rem else 0) for r in range(nranks)], dtype=np.int64)
+    off = np.concatenate([[0], np.cumsum(cnt)])
+    owner = {l: np.full(lv[l].nFluid, -1, dtype=np.int64) for l in levels}
+    for r in range(nranks):
+        sl = slice(int(off[r]), int(off[r + 1]))
+        for l in levels:
+            sel = glvl[sl] == l
+            owner[l][gidx[sl][sel]] = r
+
+    # global source tables as arrays of global positions (1-based) per ghost
+    def gfc_sources(l):
+        L = lv[l]
+        return [d["sources"] for d in L.depFromCoarser]
+
+    ranks = []
+    keep_all = []
+    for r in range(nranks):
+        need = {}
+        for l in levels:
+            L = lv[l]
+            own = np.zeros(L.nElems, dtype=bool)
+            own[:L.nFluid] = owner[l] == r
+            kindv = np.zeros(L.nElems, dtype=np.int8)
+            kindv[:L.nFluid] = 1
+            kindv[L.nFluid:L.nFluid + L.nGhostFromCoarser] = 2
+            kindv[L.nFluid + L.nGhostFromCoarser:] = 3
+            near2 = _grow(own, L.nghElems, 2)
+            near1 = _grow(own, L.nghElems, 1)
+            keep = own | (near2 & (kindv == 2)) | (near1 & (kindv == 3))
+            need[l] = dict(own=own, kind=kindv, keep=keep)
+        # interpolation sources, two passes (a ghost source pulls in its own sources)
+        for _ in range(2):
+            for l in reversed(levels):
+                L, nd = lv[l], need[l]
+                if L.nGhostFromCoarser:
+                    g0 = L.nFluid
+                    for i in np.nonzero(nd["keep"][g0:g0 + L.nGhostFromCoarser])[0]:
+                        need[l - 1]["keep"][L.depFromCoarser[i]["sources"] - 1] = True
+            for l in levels:
+                L, nd = lv[l], need[l]
+                if L.nGhostFromFiner:
+                    g0 = L.nFluid + L.nGhostFromCoarser
+                    for i in np.nonzero(nd["keep"][g0:])[0]:
+                        need[l + 1]["keep"][L.depFromFiner[i] - 1] = True
+        # everything a solved element (own fluid, kept ghostFromCoarser) pulls from must be present
+        for l in levels:
+            L, nd = lv[l], need[l]
+            solved = nd["keep"] & ((nd["own"]) | (nd["kind"] == 2))
+            rows = L.nghElems[solved]
+            p = rows[rows > 0] - 1
+            fluid_nb = p[nd["kind"][p] == 1]
+            nd["keep"][fluid_nb] = True          # remote fluid -> halo; ghosts beyond two hops are
+            # not needed (their values never reach an own fluid element before re-interpolation)
+        keep_all.append(need)
+
+    for r in range(nranks):
+        need = keep_all[r]
+        out = {}
+        maps = {}
+        for l in levels:
+            L, nd = lv[l], need[l]
+            keep, kindv, own = nd["keep"], nd["kind"], nd["own"]
+            fl = np.nonzero(own)[0]
+            gc = np.nonzero(keep & (kindv == 2))[0]
+            gf = np.nonzero(keep & (kindv == 3))[0]
+            ha = np.nonzero(keep & (kindv == 1) & ~own)[0]
+            sel = np.concatenate([fl, gc, gf, ha])          # each block ascending treeID already
+            g2l = np.zeros(L.nElems + 1, dtype=np.int32)    # global position -> local position
+            g2l[sel + 1] = np.arange(1, sel.size + 1, dtype=np.int32)
+            maps[l] = (sel, g2l, fl, gc, gf, ha)
+            M = MLLevel()
+            M.level, M.QQ = l, QQ
+            M.nFluid, M.nGhostFromCoarser, M.nGhostFromFiner, M.nHalo = fl.size, gc.size, gf.size, ha.size
+            M.nElems = sel.size
+            M.nSize = (M.nElems + 3) // 4 * 4
+            M.nSolve = M.nFluid + M.nGhostFromCoarser
+            M.total = L.total[sel]
+            M.codes = L.codes[sel]
+            M.globalPos = (sel + 1).astype(np.int64)
+            ng = L.nghElems[sel]
+            M.nghElems = np.where(ng > 0, g2l[np.maximum(ng, 0)], ng).astype(np.int32)
+            M.property = L.property[sel].copy()
+            haloOffset = M.nFluid + M.nGhostFromCoarser + M.nGhostFromFiner
+            M.neigh = construct_connectivity(QQ, M.nghElems, M.property, M.nFluid, haloOffset, M.nSize)
+            M.bc_elemBuffer = np.zeros(0, dtype=np.int32)
+            M.bc = []
+            M.bary_unit = L.bary_unit[sel]
+            M.haloOwner = owner[l][ha]
+            out[l] = M
+        # dependencies re-expressed in local positions
+        for l in levels:
+            L, M = lv[l], out[l]
+            sel, g2l, fl, gc, gf, ha = maps[l]
+            M.depFromFiner, M.depFromCoarser = [], []
+            M.intpFromFiner = np.arange(1, M.nGhostFromFiner + 1, dtype=np.int32)
+            M.intpFromCoarser = {o: [] for o in L.intpFromCoarser}
+            g0 = L.nFluid + L.nGhostFromCoarser
+            for g in gf:
+                src = maps[l + 1][1][L.depFromFiner[g - g0]]
+                assert np.all(src > 0), "a child of a kept ghostFromFiner is missing on this rank"
+                M.depFromFiner.append(src.astype(np.int32))
+            for i, g in enumerate(gc):
+                d = dict(L.depFromCoarser[g - L.nFluid])
+                src = maps[l - 1][1][d["sources"]]
+                assert np.all(src > 0), "a source of a kept ghostFromCoarser is missing on this rank"
+                d["sources"] = src.astype(np.int32)
+                M.depFromCoarser.append(d)
+                M.intpFromCoarser[d["order"]].append(i + 1)
+            for o in M.intpFromCoarser:
+                M.intpFromCoarser[o] = np.array(M.intpFromCoarser[o], dtype=np.int32)
+        ranks.append(out)
+
+    # halo exchange lists: all QQ links of every halo element, element-major (the order of the
+    # receiver's halo block = ascending treeID); the sender's list mirrors it
+    for r in range(nranks):
+        for l in levels:
+            M = ranks[r][l]
+            M.recv, M.send = [], []
+            h0 = M.nFluid + M.nGhostFromCoarser + M.nGhostFromFiner
+            for p in np.unique(M.haloOwner):
+                hs = np.nonzero(M.haloOwner == p)[0]
+                epos = (h0 + hs + 1).astype(np.int64)
+                pos = ((epos[:, None] - 1) * QQ + np.arange(1, QQ + 1)[None, :]).ravel().astype(np.int32)
+                M.recv.append(dict(proc=int(p), pos=pos, elemPos=epos.astype(np.int32),
+                                   globalPos=M.globalPos[h0 + hs]))
+    for r in range(nranks):
+        for l in levels:
+            M = ranks[r][l]
+            g2l = np.zeros(lv[l].nElems + 1, dtype=np.int64)
+            g2l[M.globalPos] = np.arange(1, M.nElems + 1)
+            for p in range(nranks):
+                if p == r:
+                    continue
+                for rc in ranks[p][l].recv:
+                    if rc["proc"] != r:
+                        continue
+                    epos = g2l[rc["globalPos"]]
+                    assert np.all((epos >= 1) & (epos <= M.nFluid)), "a halo is not fluid on its owner"
+                    pos = ((epos[:, None] - 1) * QQ + np.arange(1, QQ + 1)[None, :]).ravel().astype(np.int32)
+                    M.send.append(dict(proc=int(p), pos=pos, elemPos=epos.astype(np.int32)))
+            M.send.sort(key=lambda c: c["proc"])
+    return ranks

@@ -805,3 +805,73 @@ class MultiLevelScheme:
         for l, s in self.s.items():
             tot += s.total_mass() / 8.0 ** (l - self.minLevel)
         return tot
+
+
+# --------------------------------------------------------------------------
+# multi-level on several ranks held in one process (lockstep recursion)
+# --------------------------------------------------------------------------
+class MultiRankMultiLevel:
+    """one MultiLevelScheme per rank on the descriptors of a partitioned multi-level mesh; after
+    every level step the ranks exchange the halo elements of that level: all QQ links of
+    state(:, next) (comm_isend_irecv_real through sendBuffer / recvBuffer) and their auxField
+    entries (auxField%sendBuffer, mus_auxField_module.f90:377-396), then interpolate their own
+    ghosts.  Test infrastructure: the truth is the single-domain MultiLevelScheme."""
+
+    def __init__(self, rank_levels, rank_tables, **kw):
+        self.r = [MultiLevelScheme(lv, tb, **kw) for lv, tb in zip(rank_levels, rank_tables)]
+        self.minLevel, self.maxLevel = self.r[0].minLevel, self.r[0].maxLevel
+
+    def _exchange(self, l):
+        L = lib()
+        mail_s, mail_a = {}, {}
+        for r, m in enumerate(self.r):
+            s = m.s[l]
+            st = s.state[s.nNext]
+            for snd in s.ld.send:
+                buf = np.empty(snd["pos"].size)
+                L.ora_comm_gather(_d(buf), _d(st), _i(snd["pos"]), int(buf.size))
+                mail_s[(r, snd["proc"])] = buf
+                e = snd["elemPos"].astype(np.int64)
+                mail_a[(r, snd["proc"])] = s.aux.reshape(-1, 4)[e - 1].copy()
+        for r, m in enumerate(self.r):
+            s = m.s[l]
+            st = s.state[s.nNext]
+            for rcv in s.ld.recv:
+                buf = mail_s[(rcv["proc"], r)]
+                assert buf.size == rcv["pos"].size
+                L.ora_comm_scatter(_d(st), _d(buf), _i(rcv["pos"]), int(buf.size))
+                e = rcv["elemPos"].astype(np.int64)
+                s.aux.reshape(-1, 4)[e - 1] = mail_a[(rcv["proc"], r)]
+
+    def _level_step(self, m, l):
+        L = lib()
+        s = m.s[l]
+        s.set_boundary()
+        s.nNow, s.nNext = s.nNext, s.nNow
+        s.calc_aux(s.state[s.nNow])
+        s.add_src_to_aux()
+        if l < m.maxLevel:
+            m._aux_from_finer(l)
+        L.ora_update_omega(_d(s.omega), _d(s.visc), s.ld.nSolve)
+        rc = L.ora_compute(s.relax, s.QQ, s.incomp, _d(s.state[s.nNow]), _d(s.state[s.nNext]), _d(s.aux),
+                           _i(s.ld.neigh), _d(s.omega), s.ld.nSize, s.ld.nSolve, ctypes.byref(s.rp))
+        if rc != 0:
+            raise RuntimeError("no oracle kernel for this (relaxation, layout, kind)")
+        s.apply_source_terms()
+
+    def do_computation(self, l=None):
+        l = self.minLevel if l is None else l
+        if l < self.maxLevel:
+            for _ in range(2):
+                self.do_computation(l + 1)
+        for m in self.r:
+            self._level_step(m, l)
+        self._exchange(l)
+        if l < self.maxLevel:
+            for m in self.r:
+                m._from_finer(l)
+                m._from_coarser(l)
+
+    def run(self, ncycles):
+        for _ in range(ncycles):
+            self.do_computation()

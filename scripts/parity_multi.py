@@ -6,6 +6,10 @@
                  halo link must carry the value of the element that owns it.
   --mode gpu   : one GPU per rank through libmusb200 + NCCL; after K steps each rank's fluid
                  PDFs must be bit-identical to the single-domain oracle run.
+  --mode gpu-ml: a multi-level mesh (nested refined boxes) cut along the global space-filling
+                 curve, one GPU per rank, halo exchange of state and auxField per level through
+                 NCCL, ghosts interpolated locally; fluid PDFs of every level bit-identical to the
+                 single-domain oracle after K coarse cycles.
 """
 import argparse
 import os
@@ -16,6 +20,57 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def run_multilevel(a, mb, dist, torch, rank, world, QQ):
+    from oracle import musoracle as mo
+    from musubi_b200 import treelm_multilevel as tm
+    from musubi_b200._lib import check, lib
+    from test_multilevel import OMEGA_MIN, build
+    boxes = [(5, 11)] if a.levels == 2 else [(4, 12), (12, 20)]
+    cyl = None
+    minL = 4
+    # every rank builds the global mesh and its partition (deterministic), and the single-domain
+    # oracle run that is the truth for all of them
+    lv, intp, tables, ms = build(mo, minL, boxes, QQ, a.method, a.relaxation, cyl, OMEGA_MIN[len(boxes)])
+    mine = tm.partition_multilevel(lv, world)[rank]
+    t = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        t = torch.frombuffer(bytearray(mb.get_unique_id()), dtype=torch.uint8).clone()
+    dist.broadcast(t, 0)
+    mb.mus_init(rank, world, int(os.environ.get("LOCAL_RANK", rank)), bytes(t.numpy().tobytes()))
+    ident = {"kind": "fluid", "relaxation": a.relaxation, "layout": a.layout}
+    omega = {l: float(1.0 / (3.0 * s.visc[0] + 0.5)) for l, s in ms.s.items()}
+    visc = {l: float(s.visc[0]) for l, s in ms.s.items()}
+    sch = mb.Scheme(ident, mine, omega, lambda_=0.25, omega_bulk=1.2,
+                    intp=(mb.multilevel_tables(mine, intp), intp["order"]), viscosity=visc)
+    for l, s in ms.s.items():
+        M = mine[l]
+        g = M.globalPos - 1
+        st = np.zeros(M.nSize * QQ)
+        st[:M.nElems * QQ] = s.state[s.nNext].reshape(-1, QQ)[g].ravel()
+        sch.upload_state(l, st, st)
+        aux = np.zeros(M.nSize * 4)
+        aux[:M.nElems * 4] = s.aux.reshape(-1, 4)[g].ravel()
+        check(lib.musb200_aux_upload(l, aux.ctypes.data))
+    sch.do_computation(a.steps)
+    ms.run(a.steps)
+    nd_total = 0
+    for l, s in ms.s.items():
+        M = mine[l]
+        g = M.globalPos[:M.nFluid] - 1
+        got = sch.download_state(l)[:M.nFluid * QQ].reshape(-1, QQ)
+        exp = s.state[s.nNext].reshape(-1, QQ)[g]
+        nd = int((got != exp).sum())
+        nd_total += nd
+        print("rank %d/%d level %d: %d fluid + %d/%d ghosts + %d halos, ndiff=%d" % (
+            rank, world, l, M.nFluid, M.nGhostFromCoarser, M.nGhostFromFiner, M.nHalo, nd))
+    print("rank %d/%d multilevel %s %s: ndiff=%d" % (rank, world, a.relaxation, a.layout, nd_total))
+    assert nd_total == 0
+    sch.synchronize()
+    dist.barrier()
+    sch.destroy()
+    mb.mus_finalize()
 
 
 def main():
@@ -30,6 +85,8 @@ def main():
     ap.add_argument("--octants", type=int, default=8)
     ap.add_argument("--overlap", action="store_true")
     ap.add_argument("--p2p", action="store_true")
+    ap.add_argument("--levels", type=int, default=2, help="gpu-ml: 2 or 3 levels")
+    ap.add_argument("--method", default="linear", help="gpu-ml: interpolation method")
     ap.add_argument("--fused-push", action="store_true",
                     help="peer-memory exchange with the push fused into the sweep kernel")
     a = ap.parse_args()
@@ -39,6 +96,11 @@ def main():
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import musubi_b200 as mb
     QQ = 19 if a.layout == "d3q19" else 27
+    if a.mode == "gpu-ml":
+        run_multilevel(a, mb, dist, torch, rank, world, QQ)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     ld = mb.LevelDesc(a.level, QQ, a.kind, rank, world, octants=a.octants)
 
     if a.mode == "lists":

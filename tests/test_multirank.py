@@ -60,3 +60,20 @@ def test_multi_gpu_matches_single_domain_oracle(layout, relax, kind, extra):
                         "--level", "5", "--steps", "40"] + extra, 29651)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert r.stdout.count("ndiff=0") == nproc
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layout,relax,levels,method", [
+    ("d3q19", "bgk", 2, "linear"), ("d3q27", "mrt", 2, "quadratic"), ("d3q19", "bgk", 3, "linear")],
+    ids=["2lvl-linear-bgk19", "2lvl-quad-mrt27", "3lvl-linear-bgk19"])
+def test_multi_gpu_multilevel_matches_single_domain_oracle(layout, relax, levels, method):
+    """multi-level mesh partitioned along the global space-filling curve, one GPU per rank:
+    state + auxField halo exchange per level through NCCL, ghosts interpolated locally"""
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    nproc = 2 if n < 4 else 4
+    r = _launch(nproc, ["--mode", "gpu-ml", "--layout", layout, "--relaxation", relax, "--levels", str(levels),
+                        "--method", method, "--steps", "6"], 29653)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count("ndiff=0") >= nproc * (levels + 1)
