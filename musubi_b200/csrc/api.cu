@@ -446,6 +446,41 @@ static int exchange(Level &L, int kind, double *state, int nComp, cudaStream_t s
   return 0;
 }
 
+// multi-level: state(:, next) and auxField of the halo elements in ONE message pair per peer
+// (the reference sends them separately, tags iLevel and iLevel + 100): two pack launches, one NCCL
+// group, two unpack launches instead of two complete exchanges
+static int exchangeStateAndAux(Level &L) {
+  if (g.nranks == 1) return 0;
+  CommBuf &s = L.send[MUSB200_BUF_HALO], &r = L.recv[MUSB200_BUF_HALO];
+  if (s.total == 0 && r.total == 0) return 0;
+  cudaStream_t st = g.stream;
+  Timed t(T_COMM, st);
+  double *state = L.state[L.nNext].p;
+  if (s.total) {
+    MUSB_TRY(launchPack(L.QQ, state, L.S, s.pos.p, s.total, s.buf.p, st));
+    MUSB_TRY(launchPack(4, L.aux.p, L.S, s.auxPos.p, s.auxTotal, s.buf.p + s.total, st));
+    g.launches += 2;
+  }
+  MUSB_NCCL(g.nccl->GroupStart());
+  for (size_t i = 0; i < s.proc.size(); ++i) {
+    MUSB_NCCL(g.nccl->Send(s.buf.p + s.offset[i], (size_t)s.nVals[i], ncclDouble, s.proc[i], g.comm, st));
+    MUSB_NCCL(g.nccl->Send(s.buf.p + s.total + s.auxOffset[i], (size_t)s.auxNVals[i], ncclDouble, s.proc[i],
+                           g.comm, st));
+  }
+  for (size_t i = 0; i < r.proc.size(); ++i) {
+    MUSB_NCCL(g.nccl->Recv(r.buf.p + r.offset[i], (size_t)r.nVals[i], ncclDouble, r.proc[i], g.comm, st));
+    MUSB_NCCL(g.nccl->Recv(r.buf.p + r.total + r.auxOffset[i], (size_t)r.auxNVals[i], ncclDouble, r.proc[i],
+                           g.comm, st));
+  }
+  MUSB_NCCL(g.nccl->GroupEnd());
+  if (r.total) {
+    MUSB_TRY(launchUnpack(L.QQ, state, L.S, r.pos.p, r.total, r.buf.p, st));
+    MUSB_TRY(launchUnpack(4, L.aux.p, L.S, r.auxPos.p, r.auxTotal, r.buf.p + r.total, st));
+    g.launches += 2;
+  }
+  return 0;
+}
+
 enum { SWEEP_ALL = 0, SWEEP_SENDHALO = 1, SWEEP_INTERIOR = 2 };
 static int sweep(Level &L, bool writeAux, int part = SWEEP_ALL, bool push = false) {
   if (!L.relaxSet) return setError(MUSB200_ERR_STATE, "musb200_set_relaxation missing");
@@ -570,8 +605,8 @@ static int levelStep(int iLevel, int minLevel, int maxLevel, bool lastCycle) {
   // (mus_intpAuxFieldCoarserAndExchange, mus_auxField_module.f90:404-444) is taken inside the
   // from-finer interpolation kernel below: same sources, and on one rank nothing reads those
   // entries before the from-coarser interpolation, which runs after it
-  if (multi && writeAux) MUSB_TRY(exchange(L, MUSB200_BUF_HALO, L.aux.p, 4)); // aux halo (tag level+100)
-  MUSB_TRY(exchange(L, MUSB200_BUF_HALO, L.state[L.nNext].p, L.QQ, nullptr, pushed));
+  if (multi && writeAux) MUSB_TRY(exchangeStateAndAux(L));   // state (tag level) + aux (tag level+100)
+  else MUSB_TRY(exchange(L, MUSB200_BUF_HALO, L.state[L.nNext].p, L.QQ, nullptr, pushed));
   if (iLevel > minLevel) MUSB_TRY(exchange(L, MUSB200_BUF_FROMCOARSER, L.state[L.nNext].p, L.QQ));
   if (iLevel < maxLevel) {
     Level *F = findLevel(iLevel + 1);
@@ -1240,7 +1275,7 @@ int musb200_comm_register(int level, int buf_kind, int dir, int nProcs, const in
     }
     c.auxTotal = (int)apos.size();
     MUSB_TRY(c.auxPos.upload(apos.data(), apos.size(), g.stream));
-    if (c.auxTotal > c.total) MUSB_TRY(c.buf.alloc((size_t)c.auxTotal));
+    MUSB_TRY(c.buf.alloc((size_t)std::max(1, c.total + c.auxTotal)));   // state links | auxField entries
     MUSB_CUDA(cudaStreamSynchronize(g.stream));
   }
   if (buf_kind == MUSB200_BUF_HALO && dir == MUSB200_DIR_SEND) {
