@@ -126,16 +126,20 @@ class FileLevelDesc:
     rank: total list [fluid | halo], property, nghElems (neighbour position, or -boundary id where
     the mesh file names a boundary), neigh (mus_construct_connectivity), halo send / recv lists.
     Neighbours across the universe cube wrap periodically (tem_IdOfCoord); boundaries of kind
-    'wall' need no link lists (the bounce-back lives in neigh).  Other boundary kinds need the
-    link lists of mus_init_boundary, which only the box generator builds: they are rejected."""
+    'wall' need no link lists (the bounce-back lives in neigh); for the other kinds of the hot path
+    (velocity_bounceback, pressure_expol / pressure_antibounceback, bound through bc_kind =
+    {label: kind}) the link and neighbour lists of mus_init_boundary are built: assignBCList
+    (mus_construction_module.fpp:2203-2440), mus_set_bcLinks / mus_set_inletUbb / outletExpol
+    (mus_bc_header_module.fpp:1702-1967, 2256-2319), setFieldBCNeigh (:1733-1900)."""
 
     def __init__(self, mesh, QQ, rank=0, nranks=1, bc_kind=None):
         if mesh["minLevel"] != mesh["maxLevel"]:
             raise ValueError("FileLevelDesc handles single-level meshes; use the multi-level generator")
         bc_kind = bc_kind or {}
         for lab in mesh["bc_labels"]:
-            if bc_kind.get(lab, "wall") != "wall":
-                raise ValueError("boundary %r: kind %r needs link lists (box generator only)" % (lab, bc_kind[lab]))
+            if bc_kind.get(lab, "wall") not in ("wall", "velocity_bounceback", "pressure", "pressure_expol",
+                                               "pressure_antibounceback"):
+                raise ValueError("boundary %r: kind %r is outside the hot path" % (lab, bc_kind[lab]))
         self.level, self.QQ, self.rank, self.nranks = mesh["minLevel"], QQ, rank, nranks
         L, QQN = self.level, QQ - 1
         n1 = 1 << L
@@ -204,9 +208,9 @@ class FileLevelDesc:
             self.nghElems[self.nFluid:] = positions(neighbours(halo_g))
         self.neigh = construct_connectivity(QQ, self.nghElems, self.property, self.nFluid,
                                             self.nFluid, self.nSize)
-        self.bc_elemBuffer = np.zeros(0, dtype=np.int32)
-        self.bc = []
         self.bc_labels = list(mesh["bc_labels"])
+        self._tid, self._lo, self._hi, self._positions = tid, lo, hi, positions
+        self._build_bc(bc_kind, cx, inv)
         # halo exchange lists (init_recvBuffers / init_sendBuffers, comm_reduced): per remote rank
         # the links a local element pulls from a halo, element-major, direction ascending
         owner = np.searchsorted(off, halo_g, side="right") - 1
@@ -223,6 +227,76 @@ class FileLevelDesc:
             self.recv.append(dict(proc=int(r), pos=((self.nFluid + hs[e]) * QQ + d + 1).astype(np.int32),
                                   elemPos=(self.nFluid + hs + 1).astype(np.int32)))
         self._mesh, self._bc_kind = mesh, bc_kind
+
+    def _build_bc(self, bc_kind, cx, inv):
+        """boundary element buffer and per-boundary lists, all 1-based as the Fortran arrays"""
+        QQ, QQN, nF = self.QQ, self.QQ - 1, self.nFluid
+        ngh = self.nghElems[:nF]
+        hasb = ((self.property[:nF] >> PRP_HASBND) & 1).astype(bool)
+        self.bc_elemBuffer = (np.nonzero(hasb)[0] + 1).astype(np.int32)
+        posInBuf = np.zeros(nF + 1, dtype=np.int64)
+        posInBuf[self.bc_elemBuffer] = np.arange(1, self.bc_elemBuffer.size + 1)
+        self.bc = []
+        if not self.bc_labels:
+            return
+        length = (cx[:QQN] ** 2).sum(axis=1)
+        wgt = np.where(length == 1, 4, np.where(length == 2, 2, 1))
+        prevail = cx[:QQN] / np.sqrt(length)[:, None]
+        x, y, z = coords(self.total[:nF] - first_id(self.level))
+        n1 = 1 << self.level
+        for bid, lab in enumerate(self.bc_labels, start=1):
+            kind = bc_kind.get(lab, "wall")
+            hit = ngh == -bid                                   # [nF][QQN]: stencil dir k sees boundary bid
+            sel = np.nonzero(hit.any(axis=1))[0]
+            bc = dict(id=bid, kind=kind, label=lab, elems=(sel + 1).astype(np.int32))
+            links, iDir, pib, outPos, iEl, sPos, nInd, pbe, nPos = [], [], [], [], [], [], [], [], []
+            for iElem, e in enumerate(sel, start=1):
+                ks = np.nonzero(hit[e])[0]
+                ds = np.sort(inv[ks])                              # bitmask(cxDirInv(k)) = true, 1-based dirs
+                nrm = -(wgt[ks, None] * cx[ks]).sum(axis=0).astype(np.float64)
+                for d in ds:
+                    links.append(self.neigh[(d - 1) * self.nSize + e])
+                    iDir.append(d)
+                    pib.append(posInBuf[e + 1])
+                    outPos.append(inv[d - 1] + (posInBuf[e + 1] - 1) * QQ)
+                    iEl.append(iElem)
+                    sPos.append(d + (iElem - 1) * QQ)
+                # tem_determine_discreteVector: first strict maximum of the projection, exit at 1
+                nl = np.sqrt((nrm * nrm).sum())
+                best, mx = 0, -2.0
+                for k in range(QQN):
+                    dp = min(max(float((nrm / nl) @ prevail[k]), -1.0), 1.0)
+                    if dp > mx:
+                        mx, best = dp, k
+                        if abs(mx - 1.0) <= np.finfo(float).eps:
+                            break
+                nInd.append(best + 1)
+                pbe.append(posInBuf[e + 1])
+                # setFieldBCNeigh: the elements at x + k * normal, k = 1, 2 (last valid one repeated)
+                np2 = [e + 1, e + 1]
+                for k in (1, 2):
+                    xn, yn, zn = x[e] + k * cx[best, 0], y[e] + k * cx[best, 1], z[e] + k * cx[best, 2]
+                    p = 0
+                    if 0 <= xn < n1 and 0 <= yn < n1 and 0 <= zn < n1:
+                        nid = first_id(self.level) + morton(np.array([xn]), np.array([yn]), np.array([zn]))[0]
+                        j = int(np.searchsorted(self._tid, nid))
+                        if j < self._tid.size and self._tid[j] == nid:
+                            p = int(self._positions(np.array([j]))[0])
+                    if p <= 0:
+                        if k == 1:
+                            np2 = [e + 1, e + 1]
+                        else:
+                            np2[1] = np2[0]
+                        break
+                    np2[k - 1] = p
+                    if k == 1:
+                        np2[1] = p
+                nPos.append(np2)
+            i32 = lambda v: np.array(v, dtype=np.int32)  # noqa: E731
+            bc.update(links=i32(links), iDir=i32(iDir), posInBuffer=i32(pib), outPos=i32(outPos),
+                      iElemOfLink=i32(iEl), statePos=i32(sPos), normalInd=i32(nInd), posInBcElemBuf=i32(pbe),
+                      neighPos=np.array(nPos, dtype=np.int32).reshape(-1, 2))
+            self.bc.append(bc)
 
     def build_send(self, peers):
         """send lists = the receivers' recv lists seen from here.  peers: {rank: FileLevelDesc};

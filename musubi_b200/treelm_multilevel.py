@@ -132,12 +132,10 @@ def build_multilevel(min_level, boxes, QQ=19, cylinder=None, intp_method="linear
               see a wall, boundary id 1).  Keep it >= 8 finest cells away from the box faces.
     returns {level: MLLevel}, intp dict (matrices per order).
     """
-    cx, inv = stencil_tables(QQ)
-    QQN = QQ - 1
     levels = list(range(min_level, min_level + len(boxes) + 1))
     max_level = levels[-1]
     # kind per cell: 0 none, 1 fluid, 2 ghostFromCoarser, 3 ghostFromFiner, 9 solid
-    kind, pos = {}, {}
+    kind = {}
     region = {}  # region[l] = (lo, hi) box of level-l cells that belong to level >= l
     region[min_level] = (0, 1 << min_level)
     for i, (lo, hi) in enumerate(boxes):
@@ -163,6 +161,45 @@ def build_multilevel(min_level, boxes, QQ=19, cylinder=None, intp_method="linear
             sol = (((xs + 0.5 - ccx) ** 2 + (ys + 0.5 - ccy) ** 2) < r * r) & (zs >= zlo) & (zs < zhi)
             k[m[sol]] = 9
         kind[l] = k
+
+    return build_from_kinds(kind, QQ, intp_method)
+
+
+def kinds_from_leaves(treeID):
+    """dense cell kinds per level from the leaf list of ANY multi-level mesh (e.g. a treelm mesh
+    file): 1 = leaf (fluid), 9 = solid: a cell that is no leaf, lies under no leaf and contains
+    none -- the holes Seeder leaves for obstacles; their faces act as walls."""
+    treeID = np.asarray(treeID, dtype=np.int64)
+    lvl = np.zeros(treeID.size, dtype=np.int64)
+    for l in range(1, 21):
+        lvl[treeID >= first_id(l)] = l
+    levels = list(range(int(lvl.min()), int(lvl.max()) + 1))
+    kind, leaf = {}, {}
+    for l in levels:
+        k = np.zeros(8 ** l, dtype=np.int8)
+        k[treeID[lvl == l] - first_id(l)] = 1
+        kind[l], leaf[l] = k, k == 1
+    under = {levels[0]: np.zeros(8 ** levels[0], dtype=bool)}      # some ancestor is a leaf
+    for l in levels[1:]:
+        under[l] = np.repeat(under[l - 1] | leaf[l - 1], 8)
+    holds = {levels[-1]: np.zeros(8 ** levels[-1], dtype=bool)}    # some descendant is a leaf
+    for l in reversed(levels[:-1]):
+        holds[l] = (holds[l + 1] | leaf[l + 1]).reshape(-1, 8).any(axis=1)
+    for l in levels:
+        kind[l][~leaf[l] & ~under[l] & ~holds[l]] = 9
+    return kind
+
+
+def build_from_kinds(kind, QQ=19, intp_method="linear"):
+    """level descriptors, ghost layers and vertical dependencies of a multi-level mesh given as
+    dense cell kinds per level ({level: int8 array over the Morton codes}: 1 fluid leaf, 9 solid,
+    0 elsewhere).  Solids are honoured on every level."""
+    cx, inv = stencil_tables(QQ)
+    QQN = QQ - 1
+    levels = sorted(kind)
+    min_level, max_level = levels[0], levels[-1]
+    kind = {l: np.array(k, dtype=np.int8, copy=True) for l, k in kind.items()}
+    pos = {}
 
     # ---- ghost layers: reqNesting = 3 rounds of stencil neighbours -----------------
     for l in levels:

@@ -157,3 +157,117 @@ def test_flow_past_sphere_from_mesh_file_matches_oracle(tmp_path, oracle, QQ, re
         sch.destroy()
     finally:
         mb.mus_finalize()
+
+
+@pytest.mark.parametrize("kind,QQ,nranks", [("cavity", 19, 1), ("cavity", 27, 1), ("channel", 19, 1),
+                                            ("channel", 27, 1), ("cavity", 19, 2), ("channel", 19, 4)])
+def test_boundary_lists_from_file_equal_box_generator(tmp_path, kind, QQ, nranks):
+    """velocity and pressure boundaries of a mesh file: bc_elemBuffer, links, outPos, posInBuffer,
+    iDir, normal index, neighbour positions ... bit-identical to the C++ box generator's"""
+    import musubi_b200 as mb
+    from musubi_b200 import treelm_io as tio
+    whole = mb.LevelDesc(4, QQ, kind)
+    m = tio.mesh_from_level_desc(whole)
+    tio.dump_treelmesh(str(tmp_path), m["treeID"], m["property"], bc_labels=m["bc_labels"],
+                       boundary_ID=m["boundary_ID"])
+    mesh = tio.load_treelmesh(str(tmp_path))
+    binding = {"lid": "velocity_bounceback", "inlet": "velocity_bounceback", "outlet": "pressure"}
+    for r in range(nranks):
+        fd = tio.FileLevelDesc(mesh, QQ, r, nranks, bc_kind=binding)
+        ld = mb.LevelDesc(4, QQ, kind, r, nranks)
+        assert np.array_equal(fd.bc_elemBuffer, ld.bc_elemBuffer)
+        assert [b["id"] for b in fd.bc] == [b["id"] for b in ld.bc]
+        for a, b in zip(fd.bc, ld.bc):
+            assert a["kind"] == b["kind"] and a["label"] == b["label"]
+            for key in ("elems", "links", "outPos", "posInBuffer", "iDir", "normalInd", "posInBcElemBuf",
+                        "neighPos", "iElemOfLink", "statePos"):
+                assert np.array_equal(a[key], b[key]), (r, a["label"], key)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,outlet", [("cavity", None), ("channel", "pressure_expol"),
+                                         ("channel", "pressure_antibounceback")])
+def test_boundaries_from_mesh_file_run_on_device(tmp_path, oracle, kind, outlet):
+    """lid-driven cavity / channel with velocity inlet and pressure outlet, the mesh and its
+    boundaries read from treelm files: device against the oracle on the oracle's own descriptor"""
+    import musubi_b200 as mb
+    from musubi_b200 import cases
+    from musubi_b200 import treelm_io as tio
+    from musubi_b200._lib import check, lib
+    mb.mus_init(0, 1, 0)
+    try:
+        QQ, level = 19, 4
+        whole = mb.LevelDesc(level, QQ, kind)
+        m = tio.mesh_from_level_desc(whole)
+        tio.dump_treelmesh(str(tmp_path), m["treeID"], m["property"], bc_labels=m["bc_labels"],
+                           boundary_ID=m["boundary_ID"])
+        binding = {"lid": "velocity_bounceback", "inlet": "velocity_bounceback", "outlet": outlet}
+        fd = tio.FileLevelDesc(tio.load_treelmesh(str(tmp_path)), QQ, bc_kind=binding)
+        old = oracle.build_level_desc(level, QQ, kind)
+        ref = oracle.Scheme(old, "trt", "fluid", omega=1.7, lambda_=3.0 / 16.0)
+        ref.init_equilibrium(1.0, np.zeros(3))
+        v = cases.lid_values(whole, (0.04, 0.01, 0.0))
+        ref.bc_vel[2] = v
+        sch = mb.Scheme({"kind": "fluid", "relaxation": "trt", "layout": "d3q19"}, fd,
+                        float(1.0 / (3.0 * ref.visc[0] + 0.5)), lambda_=3.0 / 16.0)
+        sch.upload_state(level, ref.state[ref.nNow], ref.state[ref.nNext])
+        sch.set_bc_values(level, 2, v)
+        if kind == "channel":
+            nOut = len(fd.bc[2]["elems"])
+            ref.bc_kind[3] = outlet
+            ref.bc_rho[3] = np.full(nOut, 1.0)
+            sch.set_bc_values(level, 3, ref.bc_rho[3])
+            check(lib.musb200_aux_upload(level, ref.aux.ctypes.data))
+        ref.run(40)
+        sch.do_computation(40)
+        k = fd.nFluid * QQ
+        assert np.array_equal(sch.download_state(level)[:k], ref.state[ref.nNext][:k])
+        sch.destroy()
+    finally:
+        mb.mus_finalize()
+
+
+@pytest.mark.parametrize("boxes,QQ,method", [([(5, 11)], 19, "linear"), ([(4, 12), (12, 20)], 19, "linear"),
+                                             ([(5, 11)], 27, "quadratic")])
+def test_multilevel_mesh_file_round_trip(tmp_path, oracle, boxes, QQ, method):
+    """a multi-level mesh written as treelm files (leaves of all levels in space-filling-curve
+    order) and read back: the descriptors, ghost lists and dependencies rebuilt from the leaf list
+    alone equal those of the parametric generator"""
+    from musubi_b200 import treelm_io as tio
+    from musubi_b200 import treelm_multilevel as tm
+    lv, intp = tm.build_multilevel(4, boxes, QQ=QQ, intp_method=method)
+    tid, lp = oracle.global_tree(lv)
+    prop = np.full(tid.size, 2, dtype=np.int64)
+    tio.dump_treelmesh(str(tmp_path), tid, prop, length=1.0)
+    m = tio.load_treelmesh(str(tmp_path))
+    assert (m["minLevel"], m["maxLevel"]) == (4, 4 + len(boxes)) and np.array_equal(m["treeID"], tid)
+    lv2, intp2 = tm.build_from_kinds(tm.kinds_from_leaves(m["treeID"]), QQ=QQ, intp_method=method)
+    assert sorted(lv2) == sorted(lv)
+    for l in lv:
+        A, B = lv[l], lv2[l]
+        for key in ("nFluid", "nGhostFromCoarser", "nGhostFromFiner", "nSize"):
+            assert getattr(A, key) == getattr(B, key), (l, key)
+        for key in ("total", "property", "nghElems", "neigh"):
+            assert np.array_equal(getattr(A, key), getattr(B, key)), (l, key)
+        assert len(A.depFromFiner) == len(B.depFromFiner)
+        assert all(np.array_equal(a, b) for a, b in zip(A.depFromFiner, B.depFromFiner))
+        for a, b in zip(A.depFromCoarser, B.depFromCoarser):
+            assert a["order"] == b["order"] and a["posInMat"] == b["posInMat"]
+            assert np.array_equal(a["sources"], b["sources"])
+
+
+def test_holes_in_a_multilevel_leaf_list_become_walls():
+    """cells that are neither leaves, nor under a leaf, nor above one are solid obstacles"""
+    from musubi_b200 import treelm_multilevel as tm
+    lv, _ = tm.build_multilevel(5, [(10, 22)], QQ=19, cylinder=(32.0, 32.0, 3.0, 29, 35))
+    tid = np.concatenate([L.total[:L.nFluid] for L in lv.values()])
+    kinds = tm.kinds_from_leaves(tid)
+    fine = kinds[6]
+    x, y, z = tm.coords(np.nonzero(fine == 9)[0])
+    assert x.size > 0
+    assert np.all(((x + 0.5 - 32.0) ** 2 + (y + 0.5 - 32.0) ** 2 < 9.0) & (z >= 29) & (z < 35))
+    lv2, _ = tm.build_from_kinds(kinds, QQ=19)
+    for l in lv:
+        assert lv2[l].nFluid == lv[l].nFluid
+        nf = lv[l].nFluid
+        assert np.array_equal(lv2[l].neigh.reshape(19, -1)[:, :nf], lv[l].neigh.reshape(19, -1)[:, :nf])
