@@ -4,6 +4,9 @@
                  mesh generator, fills a state array with a value that encodes (treeID, dir),
                  packs its send lists, exchanges them over gloo and unpacks; every received
                  halo link must carry the value of the element that owns it.
+  --mode lists-ml: the same for a partitioned multi-level mesh: per level, every halo element
+                 must receive all QQ links and its four auxField entries from the rank that owns
+                 it, and every element a local solved element pulls from must be present.
   --mode gpu   : one GPU per rank through libmusb200 + NCCL; after K steps each rank's fluid
                  PDFs must be bit-identical to the single-domain oracle run.
   --mode gpu-ml: a multi-level mesh (nested refined boxes) cut along the global space-filling
@@ -20,6 +23,57 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def lists_multilevel(a, dist, torch, rank, world, QQ):
+    """CPU only: the halo lists of partition_multilevel moved over gloo"""
+    from musubi_b200 import treelm_multilevel as tm
+    boxes = [(5, 11)] if a.levels == 2 else [(4, 12), (12, 20)]
+    lv, _ = tm.build_multilevel(4, boxes, QQ=QQ, intp_method=a.method)
+    mine = tm.partition_multilevel(lv, world)[rank]
+    nchk = 0
+    for l, M in sorted(mine.items()):
+        code = lambda tid, d: tid.astype(np.float64) * 100.0 + d  # noqa: E731
+        state = np.full(M.nSize * QQ, -1.0)
+        aux = np.full(M.nSize * 4, -1.0)
+        own = np.arange(M.nFluid)
+        for d in range(QQ):
+            state[own * QQ + d] = code(M.total[:M.nFluid], d + 1)
+        for k in range(4):
+            aux[own * 4 + k] = code(M.total[:M.nFluid], 50 + k)
+        reqs, bufs = [], {}
+        for s in M.send:
+            e = s["elemPos"].astype(np.int64) - 1
+            payload = np.concatenate([state[s["pos"] - 1], aux.reshape(-1, 4)[e].ravel()])
+            reqs.append(dist.isend(torch.from_numpy(payload), s["proc"], tag=l))
+        for r in M.recv:
+            bufs[r["proc"]] = torch.zeros(len(r["pos"]) + 4 * len(r["elemPos"]), dtype=torch.float64)
+            reqs.append(dist.irecv(bufs[r["proc"]], r["proc"], tag=l))
+        for q in reqs:
+            q.wait()
+        for r in M.recv:
+            buf = bufs[r["proc"]].numpy()
+            n = len(r["pos"])
+            state[r["pos"] - 1] = buf[:n]
+            e = r["elemPos"].astype(np.int64) - 1
+            aux.reshape(-1, 4)[e] = buf[n:].reshape(-1, 4)
+            el, d = (r["pos"] - 1) // QQ, (r["pos"] - 1) % QQ + 1
+            assert np.array_equal(state[r["pos"] - 1], code(M.total[el], d)), "halo carries foreign PDFs"
+            assert np.array_equal(aux.reshape(-1, 4)[e], np.stack([code(M.total[e], 50 + k) for k in range(4)], 1))
+            nchk += n
+        # every halo element complete; everything a solved element pulls from is present locally
+        h0 = M.nFluid + M.nGhostFromCoarser + M.nGhostFromFiner
+        assert np.all(state[h0 * QQ:M.nElems * QQ] >= 0.0) and np.all(aux[h0 * 4:M.nElems * 4] >= 0.0)
+        pulled = M.neigh.reshape(QQ, M.nSize)[:, :M.nFluid]
+        src = (pulled - 1) // QQ
+        assert np.all((src >= 0) & (src < M.nElems))
+        # a fluid element never bounces back where the single-domain mesh has a neighbour
+        g = M.globalPos[:M.nFluid] - 1
+        ref = lv[l].neigh.reshape(QQ, lv[l].nSize)[:, g]
+        ref_bounce = (ref - 1) // QQ == g[None, :]
+        my_bounce = src == np.arange(M.nFluid)[None, :]
+        assert np.array_equal(my_bounce, ref_bounce)
+    print("rank %d: %d multi-level halo links verified" % (rank, nchk))
 
 
 def run_multilevel(a, mb, dist, torch, rank, world, QQ):
@@ -96,6 +150,11 @@ def main():
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import musubi_b200 as mb
     QQ = 19 if a.layout == "d3q19" else 27
+    if a.mode == "lists-ml":
+        lists_multilevel(a, dist, torch, rank, world, QQ)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     if a.mode == "gpu-ml":
         run_multilevel(a, mb, dist, torch, rank, world, QQ)
         dist.barrier()

@@ -26,6 +26,13 @@ def test_halo_lists_over_gloo(nproc, layout, kind):
     assert r.stdout.count("halo links verified") == nproc
 
 
+@pytest.mark.parametrize("nproc,layout,levels", [(2, "d3q19", 2), (3, "d3q27", 2), (4, "d3q19", 3)])
+def test_multilevel_halo_lists_over_gloo(nproc, layout, levels):
+    r = _launch(nproc, ["--mode", "lists-ml", "--layout", layout, "--levels", str(levels)], 29631 + nproc)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count("multi-level halo links verified") == nproc
+
+
 def _ngpu():
     try:
         import ctypes
