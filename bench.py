@@ -73,8 +73,9 @@ def measured_traffic(kernel, cells):
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(kernel)
         if t and int(t["cells"]) == int(cells):
-            return {"value": float(t["traffic_gb"]), "unit": "GB per launch (ncu dram read+write)",
-                    "algorithmic_gb": None, "source": t["source"]}
+            return {"bytes": float(t["traffic_gb"]) * 1e9, "algorithmic_bytes": None,
+                    "what": "dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full)",
+                    "source": t["source"]}
     except Exception:
         pass
     return None
@@ -522,7 +523,7 @@ def main():
     kernel_name = "sweepKernel<%d,%s>" % (QQ, ident["relaxation"])
     traffic = measured_traffic(kernel_name, ld.nFluid)
     if traffic is not None:
-        traffic["algorithmic_gb"] = BYTES_PER_LUP[QQ] * float(ld.nFluid) / 1e9
+        traffic["algorithmic_bytes"] = BYTES_PER_LUP[QQ] * float(ld.nFluid)
 
     # ---------------- end to end through the C ABI with host buffers --------
     e2e = None
@@ -580,7 +581,8 @@ def main():
                        "l2": "state of %.2f GB per buffer per GPU >> 126 MB L2, no flush needed" % (nbytes / 1e9),
                        "aux_every_step": False, "setup_s": round(setup_s, 2)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": (traffic["bytes"] if traffic else None),
+                         "traffic_detail": traffic, "peak_source": peak_src,
                          "kernel": kernel_name,
                          "bytes_per_lup": BYTES_PER_LUP[QQ], "kernel_ms": sweep_ms,
                          "share_of_step": sweep_ms / (t2_ms / K),
