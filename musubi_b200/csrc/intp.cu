@@ -264,26 +264,6 @@ __global__ void __launch_bounds__(THREADS) fromFinerFusedKernel(int incomp, cons
   }
 }
 
-// fillArbiMyGhostsFromFiner_avg for the 4 auxField scalars
-__global__ void auxFromFinerKernel(const double *__restrict__ sAux, long long sS,
-                                   const int32_t *__restrict__ uniqueSrc, int nTargets,
-                                   const int32_t *__restrict__ targets,
-                                   const int32_t *__restrict__ srcOffset,
-                                   const int32_t *__restrict__ srcSlot, double *__restrict__ tAux,
-                                   long long tS) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= nTargets * 4) return;
-  const int i = idx % nTargets, k = idx / nTargets;
-  const int s0 = srcOffset[i], n = srcOffset[i + 1] - s0;
-  const double inv_n = 1.0 / (double)n;
-  double t = 0.0;
-  for (int s = 0; s < n; ++s) {
-    const int e = uniqueSrc[srcSlot[s0 + s]] - 1;
-    t = sAux[(long long)k * sS + e] + t;
-  }
-  tAux[(long long)k * tS + targets[i] - 1] = t * inv_n;
-}
-
 // host copies of omegaFromVisc / neqFac: IEEE double on both sides, identical bits
 static double hostOmega(double v) { return 1.0 / (3.0 * v + 0.5); }
 static double hostNeqFac(double omegaS, double omegaT) { return omegaS * (1.0 - omegaT) / ((1.0 - omegaS) * omegaT); }
@@ -331,14 +311,6 @@ int launchIntp(const IntpArgs &a, const IntpSet &set, bool fromFiner, cudaStream
 #undef MUSB_INTP
   MUSB_CUDA(cudaGetLastError());
   if (nLaunch) *nLaunch = 2;
-  return 0;
-}
-
-int launchAuxFromFiner(const IntpArgs &a, const IntpSet &set, cudaStream_t st) {
-  if (set.nTargets == 0) return 0;
-  auxFromFinerKernel<<<divUp((long long)set.nTargets * 4, 128), 128, 0, st>>>(
-      a.sAux, a.sS, set.uniqueSrc, set.nTargets, set.targets, set.srcOffset, set.srcSlot, a.tAux, a.tS);
-  MUSB_CUDA(cudaGetLastError());
   return 0;
 }
 

@@ -3,7 +3,8 @@
 // Replaces the pointees of intp%fillMineFromFiner%do_intp / do_intpArbiVal and
 // intp%fillFinerFromMe(order)%do_intp (mus_interpolate_header_module.f90:103-237):
 //   fillMyGhostsFromFiner_avg_feq_fneq       mus_interpolate_average_module.fpp:186-347
-//   fillArbiMyGhostsFromFiner_avg            mus_interpolate_average_module.fpp:95-185
+//   fillArbiMyGhostsFromFiner_avg            mus_interpolate_average_module.fpp:95-185 (auxField,
+//                                            taken inside the from-finer kernel)
 //   fillFinerGhostsFromMe_weighAvg_feq_fneq  mus_interpolate_average_module.fpp:854-1038
 //   fillFinerGhostsFromMe_linear_feq_fneq    mus_interpolate_linear_module.fpp:315-505
 //   fillFinerGhostsFromMe_quad_feq_fneq      mus_interpolate_quadratic_module.fpp:292-...
@@ -66,6 +67,5 @@ int registerIntp(IntpSet &set, int order, int nTargets, const int32_t *targetLis
                  const double *matrices, const double *childCoord, cudaStream_t st);
 // returns the number of kernels launched through *nLaunch
 int launchIntp(const IntpArgs &a, const IntpSet &set, bool fromFiner, cudaStream_t st, int *nLaunch);
-int launchAuxFromFiner(const IntpArgs &a, const IntpSet &set, cudaStream_t st);
 
 }  // namespace musb200
