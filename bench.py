@@ -28,6 +28,7 @@ import ctypes
 import json
 import math
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -128,18 +129,17 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------
-def cpu_baseline(wl, level, steps):
+def cpu_baseline(wl, level, steps, warmup=2, target_s=None):
     """the reference's CPU algorithm (oracle port: AOS, two-pass, per-element omega),
-    OpenMP over the host cores, on a bounded sample of the same workload."""
+    OpenMP over the host cores, on a bounded sample of the same workload: `steps` level steps
+    after `warmup` untimed ones; with target_s the step count is chosen from a short probe so
+    that the timed part is about target_s seconds of CPU work."""
     from oracle import musoracle as mo
     from musubi_b200 import cases
     QQ = 19 if wl["ident"]["layout"] == "d3q19" else 27
     ld = mo.build_level_desc(level, QQ, wl["kind"])
     sch = mo.Scheme(ld, wl["ident"]["relaxation"], wl["ident"]["kind"], omega=wl["omega"],
                     lambda_=3.0 / 16.0, omega_bulk=wl["omega"])
-
-    class _B:  # barycentres through the oracle's own topology code
-        pass
     if wl["kind"] == "cavity":
         rho, vel = np.ones(ld.nElems), np.zeros((ld.nElems, 3))
         for bc in ld.bc:
@@ -153,7 +153,11 @@ def cpu_baseline(wl, level, steps):
                         np.zeros(ld.nElems)], axis=1)
         rho = np.ones(ld.nElems)
     sch.init_equilibrium(rho, vel)
-    sch.run(2)
+    sch.run(max(1, warmup))
+    if target_s is not None:
+        t0 = time.perf_counter()
+        sch.run(3)
+        steps = int(min(1000, max(steps, target_s / ((time.perf_counter() - t0) / 3.0))))
     t0 = time.perf_counter()
     sch.run(steps)
     dt = time.perf_counter() - t0
@@ -161,7 +165,7 @@ def cpu_baseline(wl, level, steps):
     return dict(value=ld.nFluid * steps / dt / 1e6, unit="MLUPS", cores=cores, kind="port",
                 sample="%s at level %d (%d^3 = %d cells), %d steps, oracle C port of the reference "
                        "algorithm with OpenMP (Fortran toolchain unavailable)" % (
-                           wl["name"].split(" 2")[0].split(" 5")[0], level, 1 << level, ld.nFluid, steps),
+                           re.sub(r",? \d+\^3.*", "", wl["name"]), level, 1 << level, ld.nFluid, steps),
                 ms_per_step=dt / steps * 1e3)
 
 
@@ -171,11 +175,12 @@ def run_reference(args, wl_name, wl):
         return
     level = min(wl["level"], 7)
     t0 = time.perf_counter()
-    cb = cpu_baseline(wl, level, max(1, args.steps))
+    cb = cpu_baseline(wl, level, max(1, args.steps), warmup=args.warmup)
     line = {
         "impl": "reference", "metric": "MLUPS", "value": cb["value"], "unit": "MLUPS",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
+        "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak" if wl_name == "cfg2" else "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl_name + ": " + wl["name"], "sample": cb["sample"]},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -560,9 +565,9 @@ def main():
         check(lib.musb200_set_aux_every_step(0))
 
     cb = None
-    if rank == 0 and not args.no_cpu_baseline:
-        try:
-            cb = cpu_baseline(wl, min(level, 7), 10)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:    # about 10 s of CPU work on the host cores (N = 1 only)
+            cb = cpu_baseline(wl, min(level, 7), 10, target_s=10.0)
         except Exception as ex:  # the oracle is optional test infrastructure
             cb = {"value": None, "unit": "MLUPS", "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
     if rank == 0:

@@ -18,6 +18,14 @@ the device path can be checked on machines without /root/reference.
         the same case at refinement levels 5 and 6, np=3, line sample of the INITIAL state (the
         three files are the three ranks' shares of the line)
 
+  mus/examples/fluid_incompressible/benchmark/gaussianPulse/reference/  (stored with the prefix
+  "incomp_": the file names are those of the fluid case)
+     gaussianPulse_pressAlongLength_p00000_t10.001E+00.res              level 4, 9506 steps
+     gaussianPulse-L5_..._t0.000E+00.res / _t10.000E+00.res             level 5, 19011 steps
+     gaussianPulse-L6_..._t0.000E+00.res / _t10.000E+00.res             level 6, 38022 steps
+        fluid_incompressible / bgk / d3q19, IC pressure = predefined 'gausspulse'
+        (tem_ic_predefs_module.f90:230-255), line sample of the initial and the final state
+
 Run in the build container only:  python tests/golden/make_golden.py
 """
 import os
@@ -35,3 +43,7 @@ for d, f in ((EX + "/fluid/benchmark/gaussianPulse/reference",
              (TGV + "/TGV_Simple_Re1600/reference", "TGV_Simple_Re1600_kE_all_p00000.res")):
     shutil.copy(os.path.join(d, f), os.path.join(HERE, f))
     print("copied", f)
+INC = EX + "/fluid_incompressible/benchmark/gaussianPulse/reference"
+for f in sorted(os.listdir(INC)):
+    shutil.copy(os.path.join(INC, f), os.path.join(HERE, "incomp_" + f))
+    print("copied", f, "-> incomp_" + f)

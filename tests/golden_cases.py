@@ -2,6 +2,7 @@
 the oracle tests (CPU) and the device tests (GPU):
 
   gaussianPulse       mus/examples/fluid/benchmark/gaussianPulse/musubi.lua
+  gaussianPulse (incompressible)  mus/examples/fluid_incompressible/benchmark/gaussianPulse/musubi.lua
   TGV_Simple_Re800    mus/examples/fluid_incompressible/benchmark/TaylorGreenVortex/TGV_Simple/
   TGV_Simple_Re1600   .../TGV_Simple_Re1600/musubi.lua
 
@@ -17,11 +18,22 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLD_PULSE_IC = {lv: [os.path.join(GOLDEN_DIR, "gaussianPulse-L%d_pressAlongLength_p0000%d_t0.000E+00.res" % (lv, r))
                       for r in range(3)] for lv in (5, 6)}
 GOLD_PULSE = os.path.join(GOLDEN_DIR, "gaussianPulse_pressAlongLength_p00000_t10.001E+00.res")
+GOLD_PULSE_INCOMP = {     # level -> (initial state or None, final state, steps)
+    4: (None, os.path.join(GOLDEN_DIR, "incomp_gaussianPulse_pressAlongLength_p00000_t10.001E+00.res"), 9506),
+    5: (os.path.join(GOLDEN_DIR, "incomp_gaussianPulse-L5_pressAlongLength_p00000_t0.000E+00.res"),
+        os.path.join(GOLDEN_DIR, "incomp_gaussianPulse-L5_pressAlongLength_p00000_t10.000E+00.res"), 19011),
+    6: (os.path.join(GOLDEN_DIR, "incomp_gaussianPulse-L6_pressAlongLength_p00000_t0.000E+00.res"),
+        os.path.join(GOLDEN_DIR, "incomp_gaussianPulse-L6_pressAlongLength_p00000_t10.000E+00.res"), 38022),
+}
 GOLD_TGV800 = os.path.join(GOLDEN_DIR, "TGV_Simple_Re800_probeAtCenter_p00000.res")
 GOLD_TGV1600 = os.path.join(GOLDEN_DIR, "TGV_Simple_Re1600_kE_all_p00000.res")
 
 
-def gaussian_pulse_setup(mo, nranks=1, rank=0, level=4):
+def gaussian_pulse_setup(mo, nranks=1, rank=0, level=4, kind="fluid"):
+    """kind = "fluid": mus/examples/fluid/benchmark/gaussianPulse/musubi.lua (IC from the Lua function
+    ic_3Dgauss_pulse); "fluid_incompressible": mus/examples/fluid_incompressible/benchmark/
+    gaussianPulse/musubi.lua (IC predefined 'gausspulse', tem_ic_predefs_module.f90:230-255 -- the
+    same expression), otherwise the same values."""
     length = 10.0
     dx = length / 2.0 ** level
     nu_phy, cs_phy, rho0 = 0.01, 343.0, 1.0
@@ -32,7 +44,7 @@ def gaussian_pulse_setup(mo, nranks=1, rank=0, level=4):
     omega = 1.0 / (3.0 * nu_lat + 0.5)
     nsteps = int(math.ceil(10.0 / dt))
     ld = mo.build_level_desc(level, 19, "periodic", rank, nranks)
-    sch = mo.Scheme(ld, "bgk", "fluid", omega=omega)
+    sch = mo.Scheme(ld, "bgk", kind, omega=omega)
     sch.visc[:] = nu_lat
     bary = mo.barycenters(ld, (0.0, 0.0, 0.0), length)
     r = (bary[:, 0] - 5.0) ** 2 + (bary[:, 1] - 5.0) ** 2 + (bary[:, 2] - 5.0) ** 2

@@ -84,3 +84,25 @@ def test_tgv_re1600_device_kinetic_energy_matches_reference_golden(mb, oracle):
     assert np.allclose(got, gold[:, 1], rtol=1e-10, atol=1e-5)
     assert np.max(np.abs(got / gold[:, 1] - 1.0)) < 1e-11
     sch.destroy()
+
+
+@pytest.mark.parametrize("level", [4, 5, 6])
+def test_incompressible_gaussian_pulse_device_matches_reference_golden(mb, oracle, level):
+    """mus/examples/fluid_incompressible/benchmark/gaussianPulse at the reference's three
+    resolutions (16^3 / 32^3 / 64^3, 9506 / 19011 / 38022 steps in one musb200_step call)."""
+    from golden_cases import GOLD_PULSE_INCOMP
+    _, fin, steps = GOLD_PULSE_INCOMP[level]
+    gold = np.loadtxt(fin, comments="#")
+    ref, phys, bary, nsteps = gaussian_pulse_setup(oracle, level=level, kind="fluid_incompressible")
+    assert nsteps == steps
+    ident = {"kind": "fluid_incompressible", "relaxation": "bgk", "layout": "d3q19"}
+    ld, sch = device_scheme(mb, ref, ident, level)
+    sch.do_computation(nsteps)
+    aux = sch.download_aux(level).reshape(-1, 4)
+    got = pulse_track(aux, pulse_line_elements(ref, bary, level), phys, bary)
+    assert got.shape == gold.shape
+    assert np.allclose(got, gold, rtol=1e-10, atol=1e-5)
+    assert np.max(np.abs(got[:, 3] / gold[:, 3] - 1.0)) < 1e-13     # density_phy
+    assert np.max(np.abs(got[:, 4] / gold[:, 4] - 1.0)) < 1e-13     # pressure_phy
+    assert np.max(np.abs(got[:, 5:] - gold[:, 5:])) < 2e-11         # velocity_phy
+    sch.destroy()

@@ -4,7 +4,10 @@ exactly as the reference's pysys tests do: numpy.allclose(rtol=1e-10, atol=1e-5)
   gaussianPulse      fluid / bgk / d3q19, level 4, periodic, np=2, 9506 steps, line sample
   TGV_Simple_Re800   fluid_incompressible / mrt / d3q19, 64^3, np=12, centre probe EVERY step
                      (1962 samples) -- also pins mus_init_pdf with the acoustic f_neq
-  TGV_Simple_Re1600  fluid_incompressible / bgk / d3q19, 128^3, np=8, sum of kinetic energy"""
+  TGV_Simple_Re1600  fluid_incompressible / bgk / d3q19, 128^3, np=8, sum of kinetic energy
+  gaussianPulse (fluid_incompressible/benchmark)  fluid_incompressible / bgk / d3q19 at levels 4
+                     (9506 steps) and 5 (19011 steps), initial states at levels 5 and 6; level 6
+                     (38022 steps of 64^3) runs on the device only (tests/test_gpu_golden.py)"""
 import numpy as np
 import pytest
 
@@ -102,3 +105,40 @@ def test_gaussian_pulse_initial_state_matches_reference_goldens_at_levels_5_and_
     assert np.max(np.abs(got[:, 3] / gold[:, 3] - 1.0)) < 1e-15    # density_phy
     assert np.max(np.abs(got[:, 4] / gold[:, 4] - 1.0)) < 1e-15    # pressure_phy
     assert np.all(got[:, 5:] == 0.0) and np.all(gold[:, 5:] == 0.0)
+
+
+@pytest.mark.parametrize("level", [4, 5])
+def test_incompressible_gaussian_pulse_matches_reference_golden(oracle, level):
+    """mus/examples/fluid_incompressible/benchmark/gaussianPulse: the final line sample after
+    ceil(10 / dt) steps (and the initial one where the reference ships it)"""
+    from golden_cases import GOLD_PULSE_INCOMP
+    ic, fin, steps = GOLD_PULSE_INCOMP[level]
+    sch, phys, bary, nsteps = gaussian_pulse_setup(oracle, level=level, kind="fluid_incompressible")
+    assert nsteps == steps
+    sel = pulse_line_elements(sch, bary, level)
+    if ic is not None:
+        gold0 = np.loadtxt(ic, comments="#")
+        got0 = pulse_track(sch.aux.reshape(-1, 4), sel, phys, bary)
+        assert got0.shape == gold0.shape == (1 << level, 8)
+        assert np.max(np.abs(got0[:, 3] / gold0[:, 3] - 1.0)) < 1e-15
+        assert np.max(np.abs(got0[:, 4] / gold0[:, 4] - 1.0)) < 1e-15
+    gold = np.loadtxt(fin, comments="#")
+    sch.run(nsteps)
+    got = pulse_track(sch.aux.reshape(-1, 4), sel, phys, bary)
+    assert got.shape == gold.shape
+    assert np.allclose(got, gold, rtol=1e-10, atol=1e-5)
+    assert np.max(np.abs(got[:, 3] / gold[:, 3] - 1.0)) < 1e-13     # density_phy
+    assert np.max(np.abs(got[:, 4] / gold[:, 4] - 1.0)) < 1e-13     # pressure_phy
+    assert np.max(np.abs(got[:, 5:] - gold[:, 5:])) < 2e-11         # velocity_phy
+
+
+def test_incompressible_gaussian_pulse_initial_state_at_level_6(oracle):
+    from golden_cases import GOLD_PULSE_INCOMP
+    gold0 = np.loadtxt(GOLD_PULSE_INCOMP[6][0], comments="#")
+    sch, phys, bary, nsteps = gaussian_pulse_setup(oracle, level=6, kind="fluid_incompressible")
+    assert nsteps == GOLD_PULSE_INCOMP[6][2]
+    got0 = pulse_track(sch.aux.reshape(-1, 4), pulse_line_elements(sch, bary, 6), phys, bary)
+    assert got0.shape == gold0.shape == (64, 8)
+    assert np.max(np.abs(got0[:, :3] - gold0[:, :3])) < 1e-14
+    assert np.max(np.abs(got0[:, 3] / gold0[:, 3] - 1.0)) < 1e-15
+    assert np.max(np.abs(got0[:, 4] / gold0[:, 4] - 1.0)) < 1e-15
