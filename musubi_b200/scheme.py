@@ -91,6 +91,7 @@ class Scheme:
         self.slot = int(slot)
         self._bind()
         self.relax, self.kind, self.QQ = select_kernel(identify)
+        self.scheme_kind = identify.get("kind", "fluid")       # varSys%SystemName of the restart header
         self.passive_scalar = identify.get("kind", "fluid") == "passive_scalar"
         self.nAux = 1 if self.passive_scalar else 4
         if self.passive_scalar:
@@ -270,6 +271,33 @@ class Scheme:
         if b.size != t.size * self.QQ:
             raise ValueError("restart buffer: QQ values per element expected")
         check(lib.musb200_pdf_unserialize(t.size, ptr(t, P_I64), ptr(lp, P_I32), ptr(b, P_DBL)))
+
+    def write_restart(self, prefix, sim_name, time, mesh="./mesh/", elem_offset=0, nElems_global=None,
+                      write_header=True, **header_kw):
+        """mus_writeRestart (mus_restart_module.f90:57-166): the fluid PDFs of every level in
+        tree order -> <prefix><sim_name>_<stamp>.lsb + header scripts (restart_io.write_restart).
+        time = dict(sim=..., iter=...).  Returns (binary path, header path)."""
+        from . import restart_io
+        tid, lp = restart_io.tree_order(self.levelDesc)
+        vs = restart_io.fluid_varsys(self.scheme_kind, self.QQ)
+        if self.passive_scalar:
+            vs.update(nAuxScalars=1, nAuxVars=1)
+        return restart_io.write_restart(prefix, sim_name, self.pdf_serialize(tid, lp), time, vs, mesh=mesh,
+                                        elem_offset=elem_offset, nElems_global=nElems_global,
+                                        write_header=write_header, **header_kw)
+
+    def read_restart(self, header_path, rank=0, nranks=1, base_dir=None):
+        """mus_readRestart (mus_restart_module.f90:172-246): this rank's share of the binary file
+        -> state(:, nNext) of the fluid elements; returns the header's time_point.  Ghosts and
+        halos are not in the file (the reference re-fills them by interpolation / exchange)."""
+        from . import restart_io
+        rf, off, data = restart_io.read_restart(header_path, rank, nranks, base_dir)
+        tid, lp = restart_io.tree_order(self.levelDesc)
+        if rf.nScalars * rf.nDofs != self.QQ or data.shape[0] != tid.size:
+            raise ValueError("restart file %s: %d elements x %d scalars, this scheme holds %d x %d"
+                             % (header_path, data.shape[0], rf.nScalars * rf.nDofs, tid.size, self.QQ))
+        self.pdf_unserialize(tid, lp, data.ravel())
+        return rf.time
 
     # -- peer-memory halo exchange ------------------------------------------------
     def p2p_connect(self, dist, level=None):
