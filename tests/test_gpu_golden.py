@@ -106,3 +106,27 @@ def test_incompressible_gaussian_pulse_device_matches_reference_golden(mb, oracl
     assert np.max(np.abs(got[:, 4] / gold[:, 4] - 1.0)) < 1e-13     # pressure_phy
     assert np.max(np.abs(got[:, 5:] - gold[:, 5:])) < 2e-11         # velocity_phy
     sch.destroy()
+
+
+def test_device_tracking_file_passes_the_references_own_check(mb, oracle, tmp_path):
+    """the reference's regression test end to end on the device: run gaussianPulse, write the
+    'pressAlongLength' tracking object in the reference's asciiSpatial format
+    (musubi_b200/tracking.py), compare the FILE with the golden file as apeshelper.assertIsClose
+    does (numpy.loadtxt + allclose(rtol=1e-10, atol=1e-5)); name, header, coordinates identical."""
+    import os
+    from musubi_b200 import tracking as tr
+    ref, phys, bary, nsteps = gaussian_pulse_setup(oracle)
+    ld, sch = device_scheme(mb, ref, {"kind": "fluid", "relaxation": "bgk", "layout": "d3q19"}, 4)
+    sch.do_computation(nsteps)
+    aux = sch.download_aux(4).reshape(-1, 4)
+    tid = np.asarray(ld.total[:ld.nFluid])
+    sel = tr.select_line(tid, (0.0, 5.0, 5.0), (10.0, 0.0, 0.0), (0.0, 0.0, 0.0), 10.0)
+    variables = ["density_phy", "pressure_phy", "velocity_phy"]
+    name = tr.write_ascii_spatial(str(tmp_path) + os.sep, "gaussianPulse", "pressAlongLength", nsteps * phys.dt,
+                                  tr.barycenters_of(tid[sel], (0.0, 0.0, 0.0), 10.0),
+                                  tr.track(variables, aux[sel], tr.Physics(phys.dx, phys.dt, phys.rho0)), variables)
+    assert os.path.basename(name) == os.path.basename(GOLD_PULSE)
+    mine, gold = open(name).read().splitlines(), open(GOLD_PULSE).read().splitlines()
+    assert mine[:2] == gold[:2] and [l[:76] for l in mine[2:]] == [l[:76] for l in gold[2:]]
+    assert np.allclose(np.loadtxt(name, comments="#"), np.loadtxt(GOLD_PULSE, comments="#"), rtol=1e-10, atol=1e-5)
+    sch.destroy()

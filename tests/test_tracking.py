@@ -1,0 +1,125 @@
+"""Tracking files of the reference (libharvesting/hvs_ascii_module.f90) written by
+musubi_b200/tracking.py: number format, headers, canoND element selection and the derived
+variables, pinned by the reference's own golden .res files -- header lines and coordinate columns
+byte for byte, values by the reference's criterion numpy.allclose(rtol=1e-10, atol=1e-5)
+(pysys-extensions/apes/apeshelper.py:90-123) between the file WRITTEN HERE and the golden file."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from golden_cases import (GOLD_PULSE, GOLD_PULSE_IC, GOLD_PULSE_INCOMP, GOLD_TGV800, GOLD_TGV1600,
+                          gaussian_pulse_setup, tgv800_setup)
+from musubi_b200 import tracking as tr
+
+
+def _tokens(path, limit=4000):
+    out = []
+    for line in open(path):
+        if not line.startswith("#"):
+            out += line.split()
+            if len(out) > limit:
+                break
+    return out
+
+
+@pytest.mark.parametrize("path", [GOLD_PULSE, GOLD_TGV800, GOLD_TGV1600, GOLD_PULSE_INCOMP[6][1]])
+def test_e24_16e3_reproduces_every_number_the_reference_printed(path):
+    toks = _tokens(path)
+    assert len(toks) > 100
+    for t in toks:
+        assert tr.fortran_e(float(t)).strip() == t
+    assert tr.fortran_e(0.0) == " 0.0000000000000000E+000" and len(tr.fortran_e(-1.5e-300)) == 24
+    assert tr.fortran_e(0.99999999999999999) == " 0.1000000000000000E+001"
+
+
+def test_line_selection_and_barycentres_equal_the_golden_coordinates(oracle):
+    """canoND line origin (0, 5, 5) vec (10, 0, 0) lies ON cell faces at every level: the half-open
+    cube test keeps the upper row only; coordinates printed identically at levels 4, 5, 6"""
+    for level, files in ((4, [GOLD_PULSE]), (5, GOLD_PULSE_IC[5]), (6, GOLD_PULSE_IC[6])):
+        ld = oracle.build_level_desc(level, 19, "periodic")
+        tid = np.asarray(ld.total[:ld.nFluid])
+        sel = tr.select_line(tid, (0.0, 5.0, 5.0), (10.0, 0.0, 0.0), (0.0, 0.0, 0.0), 10.0)
+        assert sel.size == 1 << level
+        bary = tr.barycenters_of(tid[sel], (0.0, 0.0, 0.0), 10.0)
+        got = sorted(" ".join(tr.fortran_e(x) for x in b) for b in bary)
+        gold = sorted(line[1:75] for f in files for line in open(f) if not line.startswith("#"))
+        assert got == gold
+    # a line that starts and ends on cell faces inside the mesh: the cell whose FAR face touches
+    # the start is kept (t_far = 0 is not < 0, proj = 0), the one beginning at the end is not (proj < 1)
+    ld = oracle.build_level_desc(3, 19, "periodic")
+    tid = np.asarray(ld.total[:ld.nFluid])
+    sel = tr.select_line(tid, (2.5, 0.0, 0.0), (5.0, 0.0, 0.0), (0.0, 0.0, 0.0), 10.0)
+    assert sorted(tr.barycenters_of(tid[sel], (0, 0, 0), 10.0)[:, 0]) == [1.875, 3.125, 4.375, 5.625, 6.875]
+
+
+def test_point_selection_is_the_cell_whose_lower_corner_is_the_point(oracle):
+    sch, phys, probe, nsteps, _ = tgv800_setup(oracle)
+    L = 2.0 * math.pi
+    tid = np.asarray(sch.ld.total[:sch.ld.nFluid])
+    assert tr.select_point(tid, (0.5 * L, 0.5 * L, 0.5 * L), (0.0, 0.0, 0.0), L) == probe
+    assert tr.select_point(tid, (-1.0, 0.0, 0.0), (0.0, 0.0, 0.0), L) == 0            # clamped
+    # leaves of two levels: a point in the coarse part finds the coarse leaf through its ancestors
+    from musubi_b200 import treelm_multilevel as tm
+    from musubi_b200.restart_io import tree_order
+    lv, _ = tm.build_multilevel(4, [(5, 11)], QQ=19)
+    leaves, _ = tree_order(lv)
+    k = tr.select_point(leaves, (0.01, 0.01, 0.01), (0.0, 0.0, 0.0), 1.0)
+    assert leaves[k] == tm.first_id(4)
+    k = tr.select_point(leaves, (0.5, 0.5, 0.5), (0.0, 0.0, 0.0), 1.0)
+    assert tr._level_of(int(leaves[k])) == 5
+
+
+def test_pulse_line_file_written_here_passes_the_references_check(oracle, tmp_path):
+    """fluid/benchmark/gaussianPulse end to end: 9506 steps, tracking object 'pressAlongLength'
+    written as the reference writes it; file name, header and coordinates identical, values close"""
+    sch, phys, _, nsteps = gaussian_pulse_setup(oracle)
+    sch.run(nsteps)
+    tid = np.asarray(sch.ld.total[:sch.ld.nFluid])
+    sel = tr.select_line(tid, (0.0, 5.0, 5.0), (10.0, 0.0, 0.0), (0.0, 0.0, 0.0), 10.0)
+    p = tr.Physics(phys.dx, phys.dt, phys.rho0)
+    variables = ["density_phy", "pressure_phy", "velocity_phy"]
+    vals = tr.track(variables, sch.aux.reshape(-1, 4)[sel], p)
+    name = tr.write_ascii_spatial(str(tmp_path) + os.sep, "gaussianPulse", "pressAlongLength", nsteps * phys.dt,
+                                  tr.barycenters_of(tid[sel], (0.0, 0.0, 0.0), 10.0), vals, variables)
+    assert os.path.basename(name) == os.path.basename(GOLD_PULSE)
+    mine, gold = open(name).read().splitlines(), open(GOLD_PULSE).read().splitlines()
+    assert mine[:2] == gold[:2] and len(mine) == len(gold)
+    assert [l[:76] for l in mine[2:]] == [l[:76] for l in gold[2:]]
+    a, b = np.loadtxt(name, comments="#"), np.loadtxt(GOLD_PULSE, comments="#")
+    assert np.allclose(a, b, rtol=1e-10, atol=1e-5)
+
+
+def test_probe_series_file_has_the_references_header_and_rows(oracle, tmp_path):
+    """TGV_Simple_Re800 'probeAtCenter' (ascii format): header identical, first rows close"""
+    sch, phys, probe, nsteps, _ = tgv800_setup(oracle)
+    p = tr.Physics(phys.dx, phys.dt, phys.rho0)
+    variables = ["velocity_phy", "pressure_phy"]
+    t = tr.AsciiTracker(str(tmp_path) + os.sep, "TGV_Simple_Re800", "probeAtCenter", variables)
+    for k in range(6):
+        t.dump(k * phys.dt, tr.track(variables, sch.aux.reshape(-1, 4)[probe], p, incompressible=True))
+        sch.run(1)
+    t.close()
+    assert os.path.basename(t.name) == os.path.basename(GOLD_TGV800)
+    mine, gold = open(t.name).read().splitlines(), open(GOLD_TGV800).read().splitlines()
+    assert mine[:2] == gold[:2]
+    a, b = np.loadtxt(t.name, comments="#"), np.loadtxt(GOLD_TGV800, comments="#")[:6]
+    assert np.allclose(a, b, rtol=1e-10, atol=1e-5)
+    # appended to after a restart: no second header
+    t2 = tr.AsciiTracker(str(tmp_path) + os.sep, "TGV_Simple_Re800", "probeAtCenter", variables)
+    t2.dump(6 * phys.dt, np.zeros(4))
+    t2.close()
+    assert sum(l.startswith("#") for l in open(t.name)) == 2 and len(open(t.name).readlines()) == 9
+    # reduced variables carry the '_red' suffix (TGV_Simple_Re1600 'kE_all')
+    r = tr.AsciiTracker(str(tmp_path) + os.sep, "TGV_Simple_Re1600", "kE_all", ["kinetic_energy_phy"], reduced=True)
+    r.close()
+    assert open(r.name).read().splitlines() == open(GOLD_TGV1600).read().splitlines()[:2]
+
+
+def test_derive_rejects_unknown_variables_and_shapes(tmp_path):
+    with pytest.raises(ValueError):
+        tr.derive("wss_phy", np.zeros((1, 4)), tr.Physics(1.0, 1.0))
+    with pytest.raises(ValueError):
+        tr.write_ascii_spatial(str(tmp_path) + os.sep, "a", "b", 0.0, np.zeros((2, 3)), np.zeros((2, 2)),
+                               ["velocity_phy"])
