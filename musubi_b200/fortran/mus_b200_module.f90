@@ -35,6 +35,9 @@ module mus_b200_module
   public :: mus_b200_check
   public :: mus_b200_upload_intp, mus_b200_set_force, mus_b200_p2p_connect
   public :: mus_b200_pdf_serialize, mus_b200_pdf_unserialize
+  public :: mus_b200_probe, mus_b200_track_every_step, mus_b200_cleanup, mus_b200_timers
+  public :: mus_b200_bind_scheme, mus_b200_couple_transport_velocity
+  public :: mus_b200_set_bc_values, mus_b200_set_species, mus_b200_set_transport_velocity
 
   integer(c_int), parameter :: buf_halo = 0, buf_fromCoarser = 1, buf_fromFiner = 2
   integer(c_int), parameter :: dir_send = 0, dir_recv = 1
@@ -200,6 +203,46 @@ module mus_b200_module
       import :: c_int, c_double
       integer(c_int), value :: level, nElems, uniform
       real(c_double) :: vel(*)
+      integer(c_int) :: rc
+    end function
+    function musb200_level_destroy(level) bind(C, name='musb200_level_destroy') result(rc)
+      import :: c_int
+      integer(c_int), value :: level
+      integer(c_int) :: rc
+    end function
+    function musb200_aux_probe(level, elemPos, rho_u) bind(C, name='musb200_aux_probe') result(rc)
+      import :: c_int, c_double
+      integer(c_int), value :: level, elemPos
+      real(c_double) :: rho_u(4)
+      integer(c_int) :: rc
+    end function
+    function musb200_set_aux_every_step(flag) bind(C, name='musb200_set_aux_every_step') result(rc)
+      import :: c_int
+      integer(c_int), value :: flag
+      integer(c_int) :: rc
+    end function
+    function musb200_scheme_bind(slot) bind(C, name='musb200_scheme_bind') result(rc)
+      import :: c_int
+      integer(c_int), value :: slot
+      integer(c_int) :: rc
+    end function
+    function musb200_couple_transport_velocity(level, flow_slot, flow_level) &
+      & bind(C, name='musb200_couple_transport_velocity') result(rc)
+      import :: c_int
+      integer(c_int), value :: level, flow_slot, flow_level
+      integer(c_int) :: rc
+    end function
+    function musb200_synchronize() bind(C, name='musb200_synchronize') result(rc)
+      import :: c_int
+      integer(c_int) :: rc
+    end function
+    function musb200_timers(compute_ms, bc_ms, comm_ms, intp_ms) bind(C, name='musb200_timers') result(rc)
+      import :: c_int, c_double
+      real(c_double) :: compute_ms, bc_ms, comm_ms, intp_ms
+      integer(c_int) :: rc
+    end function
+    function musb200_timers_reset() bind(C, name='musb200_timers_reset') result(rc)
+      import :: c_int
       integer(c_int) :: rc
     end function
     function musb200_pdf_serialize(nElems, treeID, levelPointer, buffer) &
@@ -396,6 +439,57 @@ contains
     end associate
   end subroutine upload_bc
 
+  !> boundary values of the non-wall boundaries of one level, evaluated exactly as the
+  !! reference's boundary routines do at the top of every call -- the boundary's space-time
+  !! function through get_valOfIndex on its pntIndex list -- converted to lattice units and
+  !! handed to the device (double-buffered on a copy stream; current at the next mus_b200_step):
+  !!   velocity_bounceback      vel_b(3 per link) * 1/fac%vel    mus_bc_fluid_module.fpp:1536-1575
+  !!   pressure_expol / _antiBB rho_b(per BC element) * cs2inv / fac%press        :1249-1261
+  !! Call once after mus_b200_upload for constant boundaries, before every mus_b200_step
+  !! (nCycles = 1) for time-dependent ones.
+  subroutine mus_b200_set_bc_values(scheme, iLevel, params, time)
+    use tem_time_module, only: tem_time_type
+    use tem_param_module, only: cs2inv
+    type(mus_scheme_type), intent(in) :: scheme
+    integer, intent(in) :: iLevel
+    type(mus_param_type), intent(in) :: params
+    type(tem_time_type), intent(in) :: time
+    real(kind=rk), allocatable :: vals(:)
+    integer :: iBnd, nVals, varPos
+    do iBnd = 1, size(scheme%field(1)%bc)
+      associate(bc => scheme%field(1)%bc(iBnd))
+        select case (trim(bc%BC_kind))
+        case ('velocity_bounceback')
+          nVals = bc%links(iLevel)%nVals
+          if (nVals == 0) cycle
+          allocate(vals(3*nVals))
+          varPos = bc%BC_states%velocity%varPos
+          call scheme%varSys%method%val(varPos)%get_valOfIndex(                  &
+            & varSys = scheme%varSys, time = time, iLevel = iLevel,               &
+            & idx    = bc%BC_states%velocity%pntIndex%indexLvl(iLevel)%val(1:nVals), &
+            & nVals  = nVals, res = vals )
+          vals = vals * (1.0_rk / params%physics%fac(iLevel)%vel)
+          call chk(musb200_bc_set_values(int(iLevel, c_int), int(iBnd, c_int),    &
+            &      int(3*nVals, c_int), vals), 'bc_set_values')
+          deallocate(vals)
+        case ('pressure_expol', 'pressure_antibounceback')
+          nVals = scheme%globBC(iBnd)%nElems(iLevel)
+          if (nVals == 0) cycle
+          allocate(vals(nVals))
+          varPos = bc%BC_states%pressure%varPos
+          call scheme%varSys%method%val(varPos)%get_valOfIndex(                  &
+            & varSys = scheme%varSys, time = time, iLevel = iLevel,               &
+            & idx    = bc%BC_states%pressure%pntIndex%indexLvl(iLevel)%val(1:nVals), &
+            & nVals  = nVals, res = vals )
+          vals = vals * (1.0_rk / params%physics%fac(iLevel)%press * cs2inv)
+          call chk(musb200_bc_set_values(int(iLevel, c_int), int(iBnd, c_int),    &
+            &      int(nVals, c_int), vals), 'bc_set_values')
+          deallocate(vals)
+        end select
+      end associate
+    end do
+  end subroutine mus_b200_set_bc_values
+
   !> ghost interpolation: flatten depFromFiner / depFromCoarser of the target level into the CSR
   !! lists the library takes (tem_construction_module.f90:160-276; least-square matrices
   !! tem_matrix_module.fpp:75-96).  direction 0: fillMineFromFiner, 1: fillFinerFromMe(order)
@@ -580,6 +674,98 @@ contains
     call chk(musb200_reduce(int(iLevel, c_int), m, v, flag), 'reduce')
     totalDens = m; maxVel = v; hasNaN = (flag /= 0)
   end subroutine mus_b200_check
+
+  !> point tracking (tem_tracking with a canoND point, interval = {iter = 1}): density and
+  !! velocity of one element of levelDesc(iLevel)%total without downloading auxField --
+  !! what mus_derVarPos ... get_element reads from scheme%auxField(iLevel)%val((elemPos-1)*4+1:4)
+  subroutine mus_b200_probe(iLevel, elemPos, dens, vel)
+    integer, intent(in) :: iLevel, elemPos
+    real(kind=rk), intent(out) :: dens, vel(3)
+    real(c_double) :: r(4)
+    call chk(musb200_aux_probe(int(iLevel, c_int), int(elemPos, c_int), r), 'aux_probe')
+    dens = r(1); vel = r(2:4)
+  end subroutine mus_b200_probe
+
+  !> tracking objects that are active every iteration: 1 = auxField written by every level step,
+  !! 2 = lazy (mus_b200_probe computes the element's moments on demand), 0 = default
+  subroutine mus_b200_track_every_step(mode)
+    integer, intent(in) :: mode
+    call chk(musb200_set_aux_every_step(int(mode, c_int)), 'set_aux_every_step')
+  end subroutine mus_b200_track_every_step
+
+  !> mus_scheme_cleanup (mus_scheme_module.f90:441-480) before dynamic load balancing rebuilds the
+  !! level descriptors (mus_dynLoadBal_module.f90:116): download first (mus_b200_download), then
+  !! drop the device levels; mus_b200_upload of the re-partitioned scheme follows.  Every rank
+  !! synchronises before a peer's halo rows disappear (the caller adds the MPI barrier).
+  subroutine mus_b200_cleanup(minLevel, maxLevel)
+    integer, intent(in) :: minLevel, maxLevel
+    integer :: iLevel
+    call chk(musb200_synchronize(), 'synchronize')
+    do iLevel = minLevel, maxLevel
+      call chk(musb200_level_destroy(int(iLevel, c_int)), 'level_destroy')
+    end do
+  end subroutine mus_b200_cleanup
+
+  !> device time per stage since the last call, in seconds, for mus_timerHandles
+  !! (mus_timer_module.f90: compute, setBnd, comm, intp) and the MLUPS report of mus_perf_measure
+  subroutine mus_b200_timers(tCompute, tBC, tComm, tIntp)
+    real(kind=rk), intent(out) :: tCompute, tBC, tComm, tIntp
+    real(c_double) :: c, b, m, i
+    call chk(musb200_timers(c, b, m, i), 'timers')
+    call chk(musb200_timers_reset(), 'timers_reset')
+    tCompute = c * 1.e-3_rk; tBC = b * 1.e-3_rk; tComm = m * 1.e-3_rk; tIntp = i * 1.e-3_rk
+  end subroutine mus_b200_timers
+
+  !> passive scalar (scheme kind 'passive_scalar'): the species' relaxation after the level has
+  !! been created by mus_b200_upload (mus_init_advRel_lbm_ps, init/mus_initLBMPS_module.f90:59-160:
+  !! relax_id bgk with variant 1 = 'first' | 2 = 'second', trt = vStdNoOpt)
+  subroutine mus_b200_set_species(scheme, iLevel, relaxId, variant)
+    type(mus_scheme_type), intent(in) :: scheme
+    integer, intent(in) :: iLevel, relaxId, variant
+    call chk(musb200_set_species(int(iLevel, c_int), int(relaxId, c_int), int(variant, c_int),    &
+      &      real(scheme%field(1)%fieldProp%species%diff_coeff(1), c_double),                      &
+      &      real(scheme%field(1)%fieldProp%species%lambda, c_double)), 'set_species')
+  end subroutine mus_b200_set_species
+
+  !> transport velocity of a passive scalar from its space-time function, as the kernels fetch it
+  !! at the top of every call (mus_compute_passiveScalar_module.fpp:113-126): get_valOfIndex on
+  !! scheme%transVar%method(1) for the elements 1..nElems_solve, times 1/fac%vel.  Once for a
+  !! constant field, before every step for a time-dependent one; a velocity that IS another
+  !! scheme's flow field is coupled on the device instead (mus_b200_couple_transport_velocity).
+  subroutine mus_b200_set_transport_velocity(scheme, iLevel, params, time)
+    use tem_time_module, only: tem_time_type
+    type(mus_scheme_type), intent(in) :: scheme
+    integer, intent(in) :: iLevel
+    type(mus_param_type), intent(in) :: params
+    type(tem_time_type), intent(in) :: time
+    real(kind=rk), allocatable :: transVel(:)
+    integer :: nSolve, varPos
+    nSolve = scheme%pdf(iLevel)%nElems_solve
+    allocate(transVel(3*nSolve))
+    varPos = scheme%transVar%method(1)%data_varPos
+    call scheme%varSys%method%val(varPos)%get_valOfIndex(                            &
+      & varSys = scheme%varSys, time = time, iLevel = iLevel,                         &
+      & idx    = scheme%transVar%method(1)%pntIndex%indexLvl(iLevel)%val(1:nSolve),   &
+      & nVals  = nSolve, res = transVel )
+    transVel = transVel * (1.0_rk / params%physics%fac(iLevel)%vel)
+    call chk(musb200_set_transport_velocity(int(iLevel, c_int), int(nSolve, c_int), transVel, &
+      &      0_c_int), 'set_transport_velocity')
+    deallocate(transVel)
+  end subroutine mus_b200_set_transport_velocity
+
+  !> several schemes on one mesh (scheme slots): every following call addresses `slot`
+  subroutine mus_b200_bind_scheme(slot)
+    integer, intent(in) :: slot
+    call chk(musb200_scheme_bind(int(slot, c_int)), 'scheme_bind')
+  end subroutine mus_b200_bind_scheme
+
+  !> passive scalar whose transport_velocity is the flow scheme's velocity: read on the device
+  !! from the flow's auxField instead of get_valOfIndex + upload per step
+  subroutine mus_b200_couple_transport_velocity(iLevel, flowSlot)
+    integer, intent(in) :: iLevel, flowSlot
+    call chk(musb200_couple_transport_velocity(int(iLevel, c_int), int(flowSlot, c_int), &
+      &                                        int(iLevel, c_int)), 'couple_transport_velocity')
+  end subroutine mus_b200_couple_transport_velocity
 
   !> strict drop-in of the `kernel` interface (host arrays in, host arrays out); registered by
   !! mus_init_advRel_fluid for relaxation variant 'b200'.  One H2D + kernel + D2H per call:
