@@ -91,3 +91,38 @@ def test_every_bound_function_is_used_by_a_wrapper():
     body = src[src.lower().index("contains"):]
     for cname in fortran_interfaces():
         assert re.search(r"\b%s\s*\(" % cname, body), "%s is bound but never called" % cname
+
+
+def test_every_derived_type_component_the_shim_touches_exists_in_the_reference():
+    """No compiler can check the shim here, so at least every `%component` it dereferences must
+    be a component (or type-bound procedure) declared somewhere in the reference's sources."""
+    import pytest
+    ref = "/root/reference"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree absent")
+    src = re.sub(r"!.*", "", open(SHIM).read())
+    used = set(m.lower() for m in re.findall(r"%\s*([A-Za-z_]\w*)", src))
+    assert len(used) > 40
+    declared = set()
+    for base in (os.path.join(ref, "mus", "source"), os.path.join(ref, "tem", "source")):
+        for d, _, files in os.walk(base):
+            for f in files:
+                if not f.endswith((".f90", ".fpp", ".inc")):
+                    continue
+                text = open(os.path.join(d, f), errors="replace").read()
+                text = re.sub(r"&\s*\n\s*&?", " ", text)
+                for line in text.splitlines():
+                    line = line.split("!")[0]
+                    if "::" in line:
+                        for n in re.split(r",(?![^()]*\))", line.split("::", 1)[1]):
+                            n = re.sub(r"\(.*|=.*", "", n).strip().lower()
+                            if n:
+                                declared.add(n)
+                    m = re.match(r"\s*procedure\b.*?(\w+)\s*(=>.*)?$", line, flags=re.I)
+                    if m:
+                        declared.add(m.group(1).lower())
+    # tem_communication_type%buf_real is generated by a CoCo text macro (buf_?tname?,
+    # tem_comm_module.fpp:148-154) and used as me%buf_real throughout that file
+    declared.add("buf_real")
+    missing = sorted(used - declared)
+    assert not missing, "components not found in the reference: %s" % missing
