@@ -312,18 +312,7 @@ class Scheme:
         mine = torch.frombuffer(bytearray(blob.raw), dtype=torch.uint8).clone()
         allb = [torch.zeros(256, dtype=torch.uint8) for _ in range(dist.get_world_size())]
         dist.all_gather(allb, mine)
-        reqs, got = [], {}
-        for r in ld.recv:                                   # my recv list goes to its sender
-            reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(r["pos"], dtype=np.int32)), r["proc"]))
-        for s_ in ld.send:                                  # the receiver's list for my message
-            got[s_["proc"]] = torch.zeros(len(s_["pos"]), dtype=torch.int32)
-            reqs.append(dist.irecv(got[s_["proc"]], s_["proc"]))
-        for q in reqs:
-            q.wait()
-        proc = np.array([s_["proc"] for s_ in ld.send], dtype=np.int32)
-        nVals = np.array([len(s_["pos"]) for s_ in ld.send], dtype=np.int32)
-        rpos = (np.concatenate([got[int(p)].numpy() for p in proc]).astype(np.int32)
-                if len(proc) else np.zeros(0, dtype=np.int32))
+        proc, nVals, rpos = exchange_recv_lists(dist, ld)
         blobs = b"".join(bytes(allb[int(p)].numpy().tobytes()) for p in proc)
         check(lib.musb200_p2p_connect(level, len(proc), ptr(proc, P_I32), ctypes.c_char_p(blobs),
                                       ptr(nVals, P_I32), ptr(rpos, P_I32)))
@@ -348,6 +337,27 @@ class Scheme:
         self._bind()
         for lvl in list(self.levelDesc):
             lib.musb200_level_destroy(lvl)
+
+
+def exchange_recv_lists(dist, ld):
+    """host part of the peer-memory set-up over a torch.distributed group: every receiver ships
+    its recv position list to the rank it receives from (MPI_Sendrecv in the Fortran shim).
+    Returns (proc, nVals, remotePos) in the order of ld.send: remotePos = for every link I send,
+    the state position it has on the receiving rank."""
+    import torch
+    reqs, got = [], {}
+    for r in ld.recv:                                   # my recv list goes to its sender
+        reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(r["pos"], dtype=np.int32)), r["proc"]))
+    for s_ in ld.send:                                  # the receiver's list for my message
+        got[s_["proc"]] = torch.zeros(len(s_["pos"]), dtype=torch.int32)
+        reqs.append(dist.irecv(got[s_["proc"]], s_["proc"]))
+    for q in reqs:
+        q.wait()
+    proc = np.array([s_["proc"] for s_ in ld.send], dtype=np.int32)
+    nVals = np.array([len(s_["pos"]) for s_ in ld.send], dtype=np.int32)
+    rpos = (np.concatenate([got[int(p)].numpy() for p in proc]).astype(np.int32)
+            if len(proc) else np.zeros(0, dtype=np.int32))
+    return proc, nVals, rpos
 
 
 def compute_host(identify, inState, neigh, nElems, nSolve, omega, lambda_=0.25, omega_bulk=1.0):

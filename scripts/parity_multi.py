@@ -187,7 +187,34 @@ def main():
         pulled = ld.neigh[:].reshape(QQ, ld.nSize)[:, :ld.nFluid].ravel()
         from_halo = pulled[(pulled - 1) // QQ >= ld.nFluid]
         assert np.all(state[from_halo - 1] >= 0.0), "a pulled halo link was never received"
-        print("rank %d: %d halo links verified, %d pulled-from-halo links covered" % (rank, nchk, from_halo.size))
+        # the peer-memory path: every receiver ships its recv position list to its sender
+        # (Scheme.p2p_connect's host part), then the sender "pushes" (value, remote position) and the
+        # receiver stores each value where the sender says -- what pushHaloKernel does over NVLink
+        from musubi_b200.scheme import exchange_recv_lists
+        proc, nVals, rpos = exchange_recv_lists(dist, ld)
+        assert list(proc) == [s_["proc"] for s_ in ld.send] and rpos.size == int(nVals.sum())
+        state2 = np.full(ld.nSize * QQ, -1.0)
+        state2[:ld.nFluid * QQ] = state[:ld.nFluid * QQ]
+        reqs, bufs, off = [], {}, 0
+        for s_ in ld.send:
+            n = len(s_["pos"])
+            pay = np.concatenate([state[s_["pos"] - 1], rpos[off:off + n].astype(np.float64)])
+            reqs.append(dist.isend(torch.from_numpy(pay), s_["proc"], tag=7))
+            off += n
+        for r in ld.recv:
+            bufs[r["proc"]] = torch.zeros(2 * len(r["pos"]), dtype=torch.float64)
+            reqs.append(dist.irecv(bufs[r["proc"]], r["proc"], tag=7))
+        for q in reqs:
+            q.wait()
+        for r in ld.recv:
+            b = bufs[r["proc"]].numpy()
+            n = len(r["pos"])
+            where = b[n:].astype(np.int64)
+            assert np.array_equal(np.sort(where), np.sort(r["pos"])), "pushed positions are not my recv list"
+            state2[where - 1] = b[:n]
+        assert np.array_equal(state2, state), "peer push lands elsewhere than the recv unpack"
+        print("rank %d: %d halo links verified, %d pulled-from-halo links covered, %d peers" % (
+            rank, nchk, from_halo.size, len(ld.send)))
     else:
         from oracle import musoracle as mo
         from musubi_b200 import cases

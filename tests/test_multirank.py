@@ -19,9 +19,13 @@ def _launch(nproc, extra, port):
 
 
 @pytest.mark.parametrize("nproc,layout,kind", [(2, "d3q19", "periodic"), (4, "d3q27", "periodic"),
-                                               (3, "d3q19", "cavity"), (4, "d3q19", "channel")])
+                                               (3, "d3q19", "cavity"), (4, "d3q19", "channel"),
+                                               (8, "d3q19", "cavity"), (8, "d3q27", "periodic")])
 def test_halo_lists_over_gloo(nproc, layout, kind):
-    r = _launch(nproc, ["--mode", "lists", "--layout", layout, "--kind", kind, "--level", "4"], 29611 + nproc)
+    """incl. the 8-rank octant partition of bench.py --gpus 8 (cavity: face and edge peers;
+    periodic D3Q27: face, edge and corner peers) and the host part of the peer-memory set-up"""
+    r = _launch(nproc, ["--mode", "lists", "--layout", layout, "--kind", kind, "--level", "4"],
+                29611 + nproc + (40 if layout == "d3q27" else 0))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert r.stdout.count("halo links verified") == nproc
 
