@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _launch(nproc, extra, port):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
            "--master-addr", "127.0.0.1", "--master-port", str(port),
-           os.path.join(ROOT, "scripts", "parity_multi.py")] + extra
+           os.path.join(ROOT, "tests", "parity_multi.py")] + extra
     env = dict(os.environ, OMP_NUM_THREADS="2")
     return subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
 
