@@ -232,7 +232,8 @@ def run_multilevel(args, wl_name, wl):
     boxes = [(int(lo * scale), int(hi * scale)) for lo, hi in wl["boxes"]]
     cyl = tuple(c * scale for c in wl["cylinder"][:3]) + tuple(int(c * scale) for c in wl["cylinder"][3:])
     glob, intp = tm.build_multilevel(minL, boxes, QQ=19, cylinder=cyl, intp_method="linear")
-    lv = glob if world == 1 else tm.partition_multilevel(glob, world)[rank]
+    weights = tm.level_weights(glob) if args.balance else None      # SPartA cut by level steps per cycle
+    lv = glob if world == 1 else tm.partition_multilevel(glob, world, weights=weights)[rank]
     tables = mb.multilevel_tables(lv, intp)
     levels = sorted(lv)
     nu0 = (1.0 / wl["omega"] - 0.5) / 3.0
@@ -323,8 +324,9 @@ def run_multilevel(args, wl_name, wl):
                        "rank0": {str(l): {"fluid": int(lv[l].nFluid), "ghostFromCoarser": int(lv[l].nGhostFromCoarser),
                                           "ghostFromFiner": int(lv[l].nGhostFromFiner), "halo": int(lv[l].nHalo)}
                                  for l in levels},
-                       "partition": "global space-filling curve over all levels, %d equal ranges; ghosts "
-                                    "interpolated locally, fluid-only halos over NCCL" % world,
+                       "partition": "global space-filling curve over all levels, %d %s ranges; ghosts "
+                                    "interpolated locally, fluid-only halos over NCCL" % (
+                                        world, "SPartA-weighted" if args.balance else "equal"),
                        "step": "one coarse cycle = %s level steps" % "+".join(str(upd[l]) for l in levels),
                        "mlups_definition": "sum_l nFluid(l) * 2^(l-minLevel) per coarse cycle / time (SURVEY 8d)",
                        "mlups_by_reference_formula": value_ref_formula,
@@ -363,6 +365,9 @@ def main():
                     help="sweep the send-halo elements first and overlap their exchange with the rest")
     ap.add_argument("--fused-push", action="store_true",
                     help="peer-memory halo exchange with the link stores fused into the sweep kernel")
+    ap.add_argument("--balance", action="store_true",
+                    help="cfg4 on N > 1 ranks: cut the space-filling curve by tem_balance_sparta with level "
+                         "weights 2^(l - minLevel) instead of equal element counts")
     ap.add_argument("--no-p2p", action="store_true",
                     help="halo exchange through pack/ncclSend/ncclRecv/unpack instead of peer memory")
     args = ap.parse_args()

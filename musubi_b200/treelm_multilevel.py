@@ -441,10 +441,64 @@ def _grow(mask, ngh, hops):
     return out
 
 
-def partition_multilevel(lv, nranks):
+def sparta_split(weights, nParts):
+    """tem_balance_sparta (tem_sparta_module.f90:112-226) as ONE rank holding the whole weight
+    list sees it: the splitter of part k sits after the element whose weight prefix sum is
+    closest to (k+1) * W / nParts -- binary search on the prefix sums, then the comparison with
+    the neighbouring elements (:182-196).  weights: per element along the space-filling curve.
+    Returns the element count of every part (send_count)."""
+    w = np.asarray(weights, dtype=np.float64)
+    n = w.size
+    presum = np.cumsum(w)                       # sequential sum, as the reference's loop
+    w_opt = presum[-1] / float(nParts)
+    upper = presum[-1]
+    count = np.zeros(nParts, dtype=np.int64)
+    left_off = 1                                # 1-based, as in the reference
+    for iProc in range(nParts):
+        lb, ub = left_off, n
+        opt_split = (iProc + 1) * w_opt
+        if not iProc * w_opt < upper:
+            continue
+        while True:
+            mid = (lb + ub) // 2
+            wsplit = presum[mid - 1]
+            if abs(wsplit - opt_split) <= np.finfo(np.float64).eps * max(abs(wsplit), abs(opt_split)):
+                break                           # .feq.
+            if wsplit < opt_split:
+                lb = mid
+            else:
+                ub = mid
+            if lb >= ub - 1:
+                break
+        if abs(wsplit - opt_split) > abs(wsplit - opt_split - w[mid - 1]):
+            mid -= 1
+        elif mid + 1 <= n:
+            if abs(wsplit - opt_split) > abs(wsplit - opt_split + w[mid]):
+                mid += 1
+        elif opt_split > upper:
+            mid = n
+        if iProc == nParts - 1:
+            mid = n                             # the last part ends with the last element
+        count[iProc] = mid - left_off + 1
+        left_off = mid + 1
+    return count
+
+
+def level_weights(lv):
+    """per-leaf cost along the global space-filling curve: level steps per coarse cycle,
+    2^(level - minLevel) -- what mus_getWeights (mus_weights_module.f90:62-143: measured level
+    time / nFluid of the level) converges to for a bandwidth-bound sweep of uniform cost per
+    element update"""
+    glvl, _ = _sfc_keys(lv)
+    return 2.0 ** (glvl - min(lv)).astype(np.float64)
+
+
+def partition_multilevel(lv, nranks, weights=None):
     """cut a single-rank multi-level mesh (build_multilevel) into `nranks` parts the way treelm
     does -- equal contiguous ranges of the global space-filling curve over ALL levels
-    (treelmesh_module.f90:1276-1296) -- and build every rank's level descriptors.
+    (treelmesh_module.f90:1276-1296), or, with weights (one per leaf in curve order, e.g.
+    level_weights(lv)), the ranges tem_balance_sparta cuts (mus_dynLoadBal_module.f90:513-577)
+    -- and build every rank's level descriptors.
 
     Per rank and level the total list is [own fluid | ghostFromCoarser | ghostFromFiner | halo]:
       * ghosts are LOCAL and recomputed by interpolation on every rank that needs them: the
@@ -461,8 +515,15 @@ def partition_multilevel(lv, nranks):
     QQ = lv[levels[0]].QQ
     glvl, gidx = _sfc_keys(lv)
     N = glvl.size
-    base, rem = divmod(N, nranks)
-    cnt = np.array([base + (1 if r < rem else 0) for r in range(nranks)], dtype=np.int64)
+    if weights is None:
+        base, rem = divmod(N, nranks)
+        cnt = np.array([base + (1 if r < rem else 0) for r in range(nranks)], dtype=np.int64)
+    else:
+        if len(weights) != N:
+            raise ValueError("partition_multilevel: one weight per leaf (%d), got %d" % (N, len(weights)))
+        cnt = sparta_split(weights, nranks)
+        if cnt.sum() != N or np.any(cnt <= 0):
+            raise ValueError("weighted partition leaves a rank without elements: %r" % (cnt,))
     off = np.concatenate([[0], np.cumsum(cnt)])
     owner = {l: np.full(lv[l].nFluid, -1, dtype=np.int64) for l in levels}
     for r in range(nranks):

@@ -152,11 +152,12 @@ def test_multilevel_gpu_matches_oracle(mbgpu, oracle, min_level, boxes, QQ, meth
 
 
 # ---- several ranks -----------------------------------------------------------------------------
-def _partitioned(mo, min_level, boxes, QQ, method, nranks, relax="bgk", cyl=None, omega_min=1.6):
+def _partitioned(mo, min_level, boxes, QQ, method, nranks, relax="bgk", cyl=None, omega_min=1.6,
+                 balanced=False):
     import musubi_b200 as mb
     from musubi_b200 import treelm_multilevel as tm
     lv, intp, tables, ms = build(mo, min_level, boxes, QQ, method, relax, cyl, omega_min)
-    ranks = tm.partition_multilevel(lv, nranks)
+    ranks = tm.partition_multilevel(lv, nranks, weights=tm.level_weights(lv) if balanced else None)
     rtables = [mb.multilevel_tables(rl, intp) for rl in ranks]
     mr = mo.MultiRankMultiLevel(ranks, rtables, relaxation=relax, kind="fluid", omega_min=omega_min,
                                 omega_bulk=1.2, order=intp["order"])
@@ -187,6 +188,59 @@ def test_partitioned_multilevel_equals_single_domain(oracle, min_level, boxes, Q
     tot = [sum(rl[l].nFluid for l in lv) for rl in ranks]
     assert max(tot) - min(tot) <= 1
     ncyc = 6
+    ms.run(ncyc)
+    mr.run(ncyc)
+    for r, m in enumerate(mr.r):
+        for l, s in m.s.items():
+            M = ranks[r][l]
+            g = M.globalPos[:M.nFluid] - 1
+            got = s.state[s.nNext][:M.nFluid * QQ].reshape(-1, QQ)
+            exp = ms.s[l].state[ms.s[l].nNext].reshape(-1, QQ)[g]
+            assert np.array_equal(got, exp), "rank %d level %d fluid PDFs differ" % (r, l)
+
+
+def test_sparta_split_rule():
+    """tem_balance_sparta restated for one rank: every splitter sits after the element whose
+    weight prefix sum is closest to k * W / nParts"""
+    from musubi_b200 import treelm_multilevel as tm
+    assert list(tm.sparta_split(np.ones(12), 4)) == [3, 3, 3, 3]
+    assert list(tm.sparta_split(np.ones(10), 1)) == [10]
+    rng = np.random.default_rng(3)
+    for n, parts in ((1000, 7), (513, 8), (64, 3)):
+        w = rng.choice([1.0, 2.0, 4.0], size=n)
+        cnt = tm.sparta_split(w, parts)
+        assert cnt.sum() == n and np.all(cnt > 0)
+        pre = np.cumsum(w)
+        ends = np.cumsum(cnt)[:-1]
+        for k, e in enumerate(ends):
+            target = (k + 1) * pre[-1] / parts
+            assert abs(pre[e - 1] - target) <= np.min(np.abs(pre - target)) + 1e-9
+        load = np.add.reduceat(w, np.concatenate([[0], ends]))
+        assert load.max() - pre[-1] / parts <= 4.0          # never more than one element off per cut
+
+
+@pytest.mark.parametrize("min_level,boxes,nranks", [(4, [(5, 11)], 2), (4, [(5, 11)], 3),
+                                                    (4, [(4, 12), (12, 20)], 4)],
+                         ids=["2lvl-2ranks", "2lvl-3ranks", "3lvl-4ranks"])
+def test_weighted_partition_balances_the_work_and_stays_bit_identical(oracle, min_level, boxes, nranks):
+    """the SPartA cut with level weights 2^(l - minLevel): level steps per coarse cycle are spread
+    evenly (the equal-count cut of treelm's first distribution is not), results unchanged"""
+    from musubi_b200 import treelm_multilevel as tm
+    QQ = 19
+    lv, intp, ms, ranks, rtables, mr = _partitioned(oracle, min_level, boxes, QQ, "linear", nranks,
+                                                    omega_min=OMEGA_MIN[len(boxes)], balanced=True)
+    minL = min(lv)
+    work = [sum(rl[l].nFluid * 2 ** (l - minL) for l in lv) for rl in ranks]
+    plain = [sum(rl[l].nFluid * 2 ** (l - minL) for l in lv) for rl in tm.partition_multilevel(lv, nranks)]
+    finest = 2 ** (max(lv) - minL)
+    assert max(work) - min(work) <= 2 * finest          # within one finest element per cut
+    # never worse than the equal-count cut; equal where the octant symmetry of the centred boxes
+    # already balances it (2 and 4 ranks), better otherwise
+    assert max(work) <= max(plain) and (nranks in (2, 4) or max(work) < max(plain))
+    for l in lv:
+        owned = np.concatenate([rl[l].globalPos[:rl[l].nFluid] for rl in ranks])
+        assert np.array_equal(np.sort(owned), np.arange(1, lv[l].nFluid + 1))
+    ncyc = 4
     ms.run(ncyc)
     mr.run(ncyc)
     for r, m in enumerate(mr.r):
