@@ -121,6 +121,30 @@ def load_treelmesh(dirname):
     return out
 
 
+def dump_weights(filename, weights, elem_offset=0, nElems_global=None):
+    """tem_dump_weights (treelmesh_module.f90:2169-2233): one native double per element of the
+    mesh in tree order (the file the restart header's `weights` key and mesh.weights name, read
+    back by tem_load_weights and fed to tem_balance_sparta); this rank's share lands at byte
+    elem_offset * 8 of a file sized for the whole mesh."""
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    n = w.size + elem_offset if nElems_global is None else int(nElems_global)
+    if elem_offset < 0 or elem_offset + w.size > n:
+        raise ValueError("weights: elements %d..%d outside the mesh of %d" % (elem_offset, elem_offset + w.size, n))
+    with open(filename, "r+b" if os.path.exists(filename) else "w+b") as fh:
+        fh.truncate(n * 8)
+        fh.seek(elem_offset * 8)
+        w.tofile(fh)
+
+
+def load_weights(filename, elem_offset=0, nElems=None):
+    """this rank's weights from a file written by tem_dump_weights"""
+    size = os.path.getsize(filename) // 8
+    n = size - elem_offset if nElems is None else int(nElems)
+    if elem_offset < 0 or n < 0 or elem_offset + n > size:
+        raise ValueError("weights file %s holds %d elements, asked for %d..%d" % (filename, size, elem_offset, elem_offset + n))
+    return np.fromfile(filename, dtype=np.float64, count=n, offset=elem_offset * 8)
+
+
 class FileLevelDesc:
     """tem_levelDesc_type + pdf_data_type of a single-level treelm mesh read from disk, on one
     rank: total list [fluid | halo], property, nghElems (neighbour position, or -boundary id where

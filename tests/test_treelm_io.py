@@ -271,3 +271,27 @@ def test_holes_in_a_multilevel_leaf_list_become_walls():
         assert lv2[l].nFluid == lv[l].nFluid
         nf = lv[l].nFluid
         assert np.array_equal(lv2[l].neigh.reshape(19, -1)[:, :nf], lv[l].neigh.reshape(19, -1)[:, :nf])
+
+
+def test_weights_file_round_trip_and_sparta_cut(tmp_path):
+    """tem_dump_weights layout (one double per element, ranks write at their element offset) and
+    the cut tem_balance_sparta makes from the file"""
+    from musubi_b200 import treelm_io as tio
+    from musubi_b200 import treelm_multilevel as tm
+    lv, _ = tm.build_multilevel(4, [(5, 11)], QQ=19)
+    w = tm.level_weights(lv)
+    f = str(tmp_path / "sim_weight_t0.000E+00.lsb")
+    h = w.size // 3
+    tio.dump_weights(f, w[h:], elem_offset=h, nElems_global=w.size)      # rank 1 first
+    tio.dump_weights(f, w[:h], elem_offset=0, nElems_global=w.size)
+    assert np.fromfile(f).tobytes() == w.tobytes()
+    assert np.array_equal(tio.load_weights(f), w)
+    assert np.array_equal(tio.load_weights(f, h, 10), w[h:h + 10])
+    cnt = tm.sparta_split(tio.load_weights(f), 3)
+    ranks = tm.partition_multilevel(lv, 3, weights=tio.load_weights(f))
+    assert [sum(rl[l].nFluid for l in lv) for rl in ranks] == list(cnt)
+    import pytest
+    with pytest.raises(ValueError):
+        tio.load_weights(f, w.size - 2, 5)
+    with pytest.raises(ValueError):
+        tm.partition_multilevel(lv, 3, weights=w[:-1])
