@@ -200,6 +200,32 @@ class AsciiTracker:
         self.fh.close()
 
 
+def reduce_spatial(values, op, volumes=None):
+    """tem_reduction_spatial (tem_reduction_spatial_module.f90:419-667) over the tracked
+    elements of one rank: values [n][ncomp] -> [ncomp].  volumes: dx^3 per element (the
+    reference weights the squares of l2norm / l2normalized with the element volume).  Across
+    ranks the partial results combine as the reference's mpi_reduce does (sum / max / min)."""
+    v = np.asarray(values, dtype=np.float64)
+    if v.ndim == 1:
+        v = v[:, None]
+    vol = np.ones(v.shape[0]) if volumes is None else np.asarray(volumes, dtype=np.float64)
+    if op == "sum":
+        return v.sum(axis=0)
+    if op == "average":
+        return v.sum(axis=0) / float(v.shape[0])
+    if op in ("l2norm", "l2_norm"):
+        return np.sqrt((v * v * vol[:, None]).sum(axis=0))
+    if op == "l2normalized":
+        return np.sqrt((v * v * vol[:, None]).sum(axis=0) / vol.sum())
+    if op in ("linfnorm", "linf_norm", "l_inf_norm"):
+        return np.abs(v).max(axis=0)
+    if op in ("max", "maximum"):
+        return v.max(axis=0)
+    if op in ("min", "minimum"):
+        return v.min(axis=0)
+    raise ValueError("spatial reduction %r is not one of the reference's" % op)
+
+
 def track(variables, aux, phys, incompressible=False):
     """the variables' components side by side: [n][sum ncomp]"""
     return np.concatenate([derive(v, aux, phys, incompressible) for v in variables], axis=1)

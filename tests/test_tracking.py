@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from golden_cases import (GOLD_PULSE, GOLD_PULSE_IC, GOLD_PULSE_INCOMP, GOLD_TGV800, GOLD_TGV1600,
-                          gaussian_pulse_setup, tgv800_setup)
+                          gaussian_pulse_setup, tgv800_setup, tgv1600_sample_steps, tgv1600_setup)
 from musubi_b200 import tracking as tr
 
 
@@ -123,3 +123,38 @@ def test_derive_rejects_unknown_variables_and_shapes(tmp_path):
     with pytest.raises(ValueError):
         tr.write_ascii_spatial(str(tmp_path) + os.sep, "a", "b", 0.0, np.zeros((2, 3)), np.zeros((2, 2)),
                                ["velocity_phy"])
+
+
+def test_reduced_series_file_equals_the_references_kinetic_energy_golden(oracle, tmp_path):
+    """TGV_Simple_Re1600 'kE_all': shape = all, reduction = sum of kinetic_energy_phy, ascii
+    format -- the first samples (steps 0, 2, 4) written here against the golden rows"""
+    sch, phys, nsteps = tgv1600_setup(oracle)
+    gold = np.loadtxt(GOLD_TGV1600, comments="#")
+    steps = tgv1600_sample_steps(gold, phys)[:3]
+    p = tr.Physics(phys.dx, phys.dt, phys.rho0)
+    t = tr.AsciiTracker(str(tmp_path) + os.sep, "TGV_Simple_Re1600", "kE_all", ["kinetic_energy_phy"], reduced=True)
+    k = 0
+    for target in steps:
+        sch.run(int(target) - k)
+        k = int(target)
+        ke = tr.derive("kinetic_energy_phy", sch.aux.reshape(-1, 4)[:sch.ld.nFluid], p, incompressible=True)
+        t.dump(k * phys.dt, tr.reduce_spatial(ke, "sum"))
+    t.close()
+    assert os.path.basename(t.name) == os.path.basename(GOLD_TGV1600)
+    assert open(t.name).read().splitlines()[:2] == open(GOLD_TGV1600).read().splitlines()[:2]
+    assert np.allclose(np.loadtxt(t.name, comments="#"), gold[:3], rtol=1e-10, atol=1e-5)
+
+
+def test_spatial_reductions():
+    v = np.array([[1.0, -2.0], [3.0, 4.0], [-5.0, 0.5]])
+    vol = np.array([1.0, 0.125, 0.125])
+    assert list(tr.reduce_spatial(v, "sum")) == [-1.0, 2.5]
+    assert np.allclose(tr.reduce_spatial(v, "average"), [-1.0 / 3, 2.5 / 3], rtol=1e-15)
+    assert np.allclose(tr.reduce_spatial(v, "l2norm", vol), np.sqrt([1 + 9 / 8 + 25 / 8, 4 + 2 + 0.25 / 8]))
+    assert np.allclose(tr.reduce_spatial(v, "l2normalized", vol),
+                       np.sqrt(np.array([1 + 9 / 8 + 25 / 8, 4 + 2 + 0.25 / 8]) / 1.25))
+    assert list(tr.reduce_spatial(v, "linfnorm")) == [5.0, 4.0]
+    assert list(tr.reduce_spatial(v, "max")) == [3.0, 4.0] and list(tr.reduce_spatial(v, "min")) == [-5.0, -2.0]
+    assert list(tr.reduce_spatial(np.array([1.0, 2.0]), "sum")) == [3.0]
+    with pytest.raises(ValueError):
+        tr.reduce_spatial(v, "median")
