@@ -158,3 +158,26 @@ def test_spatial_reductions():
     assert list(tr.reduce_spatial(np.array([1.0, 2.0]), "sum")) == [3.0]
     with pytest.raises(ValueError):
         tr.reduce_spatial(v, "median")
+
+
+def test_number_formats_round_trip_random_doubles():
+    """e24.16e3 carries 16 significant digits: reading a printed value back gives the double to
+    within one unit of the 16th digit, and printing that again is a fixed point; EN24.15 (the
+    restart header's reals) likewise with 16 to 18 digits"""
+    from musubi_b200.restart_io import fortran_en
+    rng = np.random.default_rng(11)
+    x = np.concatenate([rng.standard_normal(300) * 10.0 ** rng.integers(-300, 300, 300),
+                        rng.random(100), [1.0, -1.0, 0.1, 999.9999999999999, 1e-320, 1.7e308]])
+    for v in x:
+        s = tr.fortran_e(v)
+        assert len(s) == 24 and s[-5] == "E" and s.strip()[:3] in ("0.0", "0.1", "0.2", "0.3", "0.4", "0.5", "0.6",
+                                                               "0.7", "0.8", "0.9", "-0.")
+        back = float(s)
+        assert back == v or abs(back / v - 1.0) < 1.0e-15
+        assert tr.fortran_e(back) == s
+        e = fortran_en(v, 15, 24)
+        mant = abs(float(e.split("E")[0]))
+        assert int(e.split("E")[1]) % 3 == 0 and (1.0 <= mant < 1000.0)
+        backe = float(e)
+        assert backe == v or abs(backe / v - 1.0) < 1.0e-15
+        assert fortran_en(backe, 15, 24) == e
