@@ -449,9 +449,9 @@ static int exchange(Level &L, int kind, double *state, int nComp, cudaStream_t s
 // multi-level: state(:, next) and auxField of the halo elements in ONE message pair per peer
 // (the reference sends them separately, tags iLevel and iLevel + 100): two pack launches, one NCCL
 // group, two unpack launches instead of two complete exchanges
-static int exchangeStateAndAux(Level &L) {
+static int exchangeStateAndAux(Level &L, int kind = MUSB200_BUF_HALO) {
   if (g.nranks == 1) return 0;
-  CommBuf &s = L.send[MUSB200_BUF_HALO], &r = L.recv[MUSB200_BUF_HALO];
+  CommBuf &s = L.send[kind], &r = L.recv[kind];
   if (s.total == 0 && r.total == 0) return 0;
   cudaStream_t st = g.stream;
   Timed t(T_COMM, st);
@@ -612,7 +612,9 @@ static int levelStep(int iLevel, int minLevel, int maxLevel, bool lastCycle) {
     Level *F = findLevel(iLevel + 1);
     // do_intpFinerAndExchange: my ghostFromFiner <- average over the children on level+1
     MUSB_TRY(applyIntp(*F, L, L.fromFiner, true));
-    MUSB_TRY(exchange(L, MUSB200_BUF_FROMFINER, L.state[L.nNext].p, L.QQ));
+    // ghostFromFiner elements another rank interpolated for me arrive with their auxField entries
+    // (the from-coarser interpolation below reads them when such a ghost is one of its sources)
+    MUSB_TRY(exchangeStateAndAux(L, MUSB200_BUF_FROMFINER));
     // do_intpCoarserAndExchange: ghostFromCoarser of level+1 <- me, orders 0..order
     for (auto &set : F->fromCoarser) MUSB_TRY(applyIntp(L, *F, set, false));
     MUSB_TRY(exchange(*F, MUSB200_BUF_FROMCOARSER, F->state[F->nNext].p, F->QQ));
@@ -1257,7 +1259,9 @@ int musb200_comm_register(int level, int buf_kind, int dir, int nProcs, const in
   MUSB_TRY(c.pos.upload(pos, (size_t)c.total, g.stream));
   MUSB_TRY(c.buf.alloc((size_t)std::max(1, c.total)));
   c.auxNVals.clear(); c.auxOffset.clear(); c.auxTotal = 0;
-  if (buf_kind == MUSB200_BUF_HALO) {
+  // halo elements and ghostFromFiner elements travel with their auxField entries
+  // (auxField%sendBuffer / sendBufferFromFiner, mus_auxField_module.f90:377-444)
+  if (buf_kind == MUSB200_BUF_HALO || buf_kind == MUSB200_BUF_FROMFINER) {
     std::vector<int32_t> apos;
     std::vector<char> seen;
     for (int i = 0; i < nProcs; ++i) {

@@ -81,13 +81,16 @@ class Scheme:
     """mus_scheme_type for one level range on one rank, device resident."""
 
     def __init__(self, identify, levelDescs, omega=None, lambda_=0.25, omega_bulk=None, intp=None,
-                 viscosity=None, bc_kind=None, slot=0, species=None):
+                 viscosity=None, bc_kind=None, slot=0, species=None, ghost_comm=None):
         """intp: None or (tables, order) with tables as built by multilevel_tables();
         viscosity: {level: lattice viscosity} (fluid%viscKine%dataOnLvl) for the interpolation;
         bc_kind: {boundary id: kind} binds the mesh's 'pressure' boundaries to pressure_expol or
         pressure_antibounceback (the boundary_condition table of the Lua configuration);
         slot: scheme slot of the library (several schemes on one mesh);
-        species: {"diff_coeff": D, "lambda": 0.25} of a passive_scalar scheme."""
+        species: {"diff_coeff": D, "lambda": 0.25} of a passive_scalar scheme;
+        ghost_comm: {level: {"fromCoarser" | "fromFiner": {"send" | "recv": [dict(proc, pos)]}}},
+        the level's sendBufferFromCoarser / FromFiner lists of a host that ships interpolated ghosts
+        between ranks as treelm's construction does (treelm_multilevel.delegate_shared_ghosts)."""
         self.slot = int(slot)
         self._bind()
         self.relax, self.kind, self.QQ = select_kernel(identify)
@@ -142,13 +145,17 @@ class Scheme:
                 else:
                     v = np.ascontiguousarray(v, dtype=np.float64)
                     check(lib.musb200_set_viscosity(lvl, ptr(v, P_DBL), 0.0))
-            for d, lists in ((0, ld.send), (1, ld.recv)):
+            bufs = [(0, 0, ld.send), (0, 1, ld.recv)]
+            for kind_id, name in ((1, "fromCoarser"), (2, "fromFiner")):
+                gc = (ghost_comm or {}).get(lvl, {}).get(name, {})
+                bufs += [(kind_id, 0, gc.get("send", [])), (kind_id, 1, gc.get("recv", []))]
+            for kind_id, d, lists in bufs:
                 if not lists:
                     continue
                 proc = np.array([c["proc"] for c in lists], dtype=np.int32)
                 nVals = np.array([len(c["pos"]) for c in lists], dtype=np.int32)
                 pos = np.concatenate([c["pos"] for c in lists]).astype(np.int32)
-                check(lib.musb200_comm_register(lvl, 0, d, len(lists), ptr(proc, P_I32),
+                check(lib.musb200_comm_register(lvl, kind_id, d, len(lists), ptr(proc, P_I32),
                                                 ptr(nVals, P_I32), ptr(pos, P_I32)))
 
         if intp is not None:

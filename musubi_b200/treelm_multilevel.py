@@ -665,3 +665,104 @@ def partition_multilevel(lv, nranks, weights=None):
                     M.send.append(dict(proc=int(p), pos=pos, elemPos=epos.astype(np.int32)))
             M.send.sort(key=lambda c: c["proc"])
     return ranks
+
+
+# ------------------------------------------------------------------------------------------------
+# reference-style ghost buffers (sendBufferFromCoarser / FromFiner) from the partition above
+# ------------------------------------------------------------------------------------------------
+def _filter_table(t, keep):
+    """an interpolation table (intp_tables) restricted to the targets with keep[i]"""
+    keep = np.asarray(keep, dtype=bool)
+    off = np.asarray(t["srcOffset"], dtype=np.int64)
+    n = np.diff(off)
+    src_keep = np.repeat(keep, n)
+    new_off = np.concatenate([[0], np.cumsum(n[keep])]).astype(np.int32)
+    out = dict(t)
+    out["targets"] = np.asarray(t["targets"])[keep]
+    out["srcOffset"] = new_off
+    out["srcPos"] = np.asarray(t["srcPos"])[src_keep]
+    if len(t["weights"]):
+        out["weights"] = np.asarray(t["weights"])[src_keep]
+    if len(t["posInMat"]):
+        out["posInMat"] = np.asarray(t["posInMat"])[keep]
+    if len(t["coord"]):
+        out["coord"] = np.asarray(t["coord"]).reshape(-1, 3)[keep]
+    return out
+
+
+def delegate_shared_ghosts(ranks, rtables, lv):
+    """Turns the locally-recomputed ghosts of partition_multilevel into the reference's form of
+    the same run: a ghost element that several ranks hold is interpolated by ONE of them and
+    travels to the others through the level's sendBufferFromCoarser / sendBufferFromFiner
+    (tem_construction_module.f90: the six buffer kinds of a level; exchanged by
+    do_intpCoarserAndExchange / do_intpFinerAndExchange, mus_control_module.f90:861-1051, and for
+    the auxField of ghostFromFiner elements by mus_intpAuxFieldCoarserAndExchange,
+    mus_auxField_module.f90:404-444).  The provider of a ghost is chosen by treeID (so that
+    messages flow both ways) among the holders that can stand in for the others: a
+    ghostFromCoarser element is swept like a fluid element and shipped after every level step
+    (recvBufferFromCoarser, mus_control_module.f90:434-465), so its provider must hold the
+    element's complete neighbourhood -- as many neighbours as the single-domain mesh `lv` gives
+    it; a ghost no holder can provide stays locally interpolated on every rank.
+
+    returns (tables, comm): tables = rtables with the delegated targets removed on the receiving
+    ranks; comm[rank][level][kind]['send' | 'recv'] = [dict(proc, pos, elemPos)], kind in
+    ('fromCoarser', 'fromFiner'), pos = all QQ state positions of every element, element-major."""
+    nranks = len(ranks)
+    levels = sorted(ranks[0])
+    QQ = ranks[0][levels[0]].QQ
+    tables = [{k: dict(v) for k, v in rt.items()} for rt in rtables]
+    comm = [{l: {k: {"send": {}, "recv": {}} for k in ("fromCoarser", "fromFiner")} for l in levels}
+            for _ in range(nranks)]
+    for l in levels:
+        for kind in ("fromCoarser", "fromFiner"):
+            holders = {}                                   # treeID -> [(rank, 1-based position)]
+            for r in range(nranks):
+                M = ranks[r][l]
+                lo = M.nFluid if kind == "fromCoarser" else M.nFluid + M.nGhostFromCoarser
+                hi = lo + (M.nGhostFromCoarser if kind == "fromCoarser" else M.nGhostFromFiner)
+                for p in range(lo, hi):
+                    holders.setdefault(int(M.total[p]), []).append((r, p + 1))
+            drop = [set() for _ in range(nranks)]          # positions a rank no longer interpolates
+            for tid in sorted(holders):
+                h = holders[tid]
+                if len(h) < 2:
+                    continue
+                able = h
+                if kind == "fromCoarser":
+                    able = []
+                    for r, pos in h:
+                        M = ranks[r][l]
+                        full = int((lv[l].nghElems[M.globalPos[pos - 1] - 1] > 0).sum())
+                        if int((M.nghElems[pos - 1] > 0).sum()) == full:
+                            able.append((r, pos))
+                    if not able:
+                        continue
+                prov, ppos = able[tid % len(able)]
+                for r, pos in h:
+                    if r == prov:
+                        continue
+                    drop[r].add(pos)
+                    comm[prov][l][kind]["send"].setdefault(r, []).append(ppos)
+                    comm[r][l][kind]["recv"].setdefault(prov, []).append(pos)
+            for r in range(nranks):
+                if not drop[r]:
+                    continue
+                gone = np.array(sorted(drop[r]), dtype=np.int64)
+                keys = [(l, "fromFiner")] if kind == "fromFiner" else \
+                    [k for k in tables[r] if k[0] == l and isinstance(k[1], tuple) and k[1][0] == "fromCoarser"]
+                for k in keys:
+                    if k in tables[r]:
+                        t = tables[r][k]
+                        tables[r][k] = _filter_table(t, ~np.isin(np.asarray(t["targets"], dtype=np.int64), gone))
+    d = np.arange(1, QQ + 1, dtype=np.int64)
+    out = [{l: {k: {"send": [], "recv": []} for k in ("fromCoarser", "fromFiner")} for l in levels}
+           for _ in range(nranks)]
+    for r in range(nranks):
+        for l in levels:
+            for kind in ("fromCoarser", "fromFiner"):
+                for way in ("send", "recv"):
+                    for p in sorted(comm[r][l][kind][way]):
+                        e = np.array(comm[r][l][kind][way][p], dtype=np.int64)
+                        pos = ((e[:, None] - 1) * QQ + d[None, :]).ravel().astype(np.int32)
+                        out[r][l][kind][way].append(dict(proc=int(p), pos=pos, elemPos=e.astype(np.int32)))
+    return tables, out

@@ -817,9 +817,39 @@ class MultiRankMultiLevel:
     entries (auxField%sendBuffer, mus_auxField_module.f90:377-396), then interpolate their own
     ghosts.  Test infrastructure: the truth is the single-domain MultiLevelScheme."""
 
-    def __init__(self, rank_levels, rank_tables, **kw):
+    def __init__(self, rank_levels, rank_tables, ghost_comm=None, **kw):
+        """ghost_comm: None, or comm[rank][level][kind]['send' | 'recv'] lists (kind 'fromCoarser' /
+        'fromFiner') of ghosts that one rank interpolates for others -- the reference's
+        sendBufferFromCoarser / FromFiner (exchanged after the interpolation that fills them)"""
         self.r = [MultiLevelScheme(lv, tb, **kw) for lv, tb in zip(rank_levels, rank_tables)]
         self.minLevel, self.maxLevel = self.r[0].minLevel, self.r[0].maxLevel
+        self.ghost_comm = ghost_comm
+
+    def _exchange_ghosts(self, l, kind, with_aux):
+        """comm_isend_irecv_real on the level's FromCoarser / FromFiner buffers (state(:, next),
+        all QQ links per element) and, for ghostFromFiner elements, their auxField entries
+        (mus_intpAuxFieldCoarserAndExchange, mus_auxField_module.f90:404-444)"""
+        if self.ghost_comm is None:
+            return
+        L = lib()
+        mail_s, mail_a = {}, {}
+        for r, m in enumerate(self.r):
+            s = m.s[l]
+            st = s.state[s.nNext]
+            for snd in self.ghost_comm[r][l][kind]["send"]:
+                buf = np.empty(snd["pos"].size)
+                L.ora_comm_gather(_d(buf), _d(st), _i(snd["pos"]), int(buf.size))
+                mail_s[(r, snd["proc"])] = buf
+                mail_a[(r, snd["proc"])] = s.aux.reshape(-1, 4)[snd["elemPos"].astype(np.int64) - 1].copy()
+        for r, m in enumerate(self.r):
+            s = m.s[l]
+            st = s.state[s.nNext]
+            for rcv in self.ghost_comm[r][l][kind]["recv"]:
+                buf = mail_s[(rcv["proc"], r)]
+                assert buf.size == rcv["pos"].size
+                L.ora_comm_scatter(_d(st), _d(buf), _i(rcv["pos"]), int(buf.size))
+                if with_aux:
+                    s.aux.reshape(-1, 4)[rcv["elemPos"].astype(np.int64) - 1] = mail_a[(rcv["proc"], r)]
 
     def _exchange(self, l):
         L = lib()
@@ -867,10 +897,15 @@ class MultiRankMultiLevel:
         for m in self.r:
             self._level_step(m, l)
         self._exchange(l)
+        if l > self.minLevel:                  # recvBufferFromCoarser after the level's own step
+            self._exchange_ghosts(l, "fromCoarser", with_aux=False)    # (mus_control_module.f90:434-465)
         if l < self.maxLevel:
             for m in self.r:
                 m._from_finer(l)
+            self._exchange_ghosts(l, "fromFiner", with_aux=True)       # do_intpFinerAndExchange
+            for m in self.r:
                 m._from_coarser(l)
+            self._exchange_ghosts(l + 1, "fromCoarser", with_aux=False)  # do_intpCoarserAndExchange
 
     def run(self, ncycles):
         for _ in range(ncycles):

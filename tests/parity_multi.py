@@ -87,7 +87,16 @@ def run_multilevel(a, mb, dist, torch, rank, world, QQ):
     # every rank builds the global mesh and its partition (deterministic), and the single-domain
     # oracle run that is the truth for all of them
     lv, intp, tables, ms = build(mo, minL, boxes, QQ, a.method, a.relaxation, cyl, OMEGA_MIN[len(boxes)])
-    mine = tm.partition_multilevel(lv, world)[rank]
+    ranks = tm.partition_multilevel(lv, world)
+    mine = ranks[rank]
+    my_tables, ghost_comm = mb.multilevel_tables(mine, intp), None
+    if a.ghost_exchange:
+        # the reference's form: shared ghosts interpolated by one rank, shipped through the
+        # FromCoarser / FromFiner buffers of the level (state links + auxField of ghostFromFiner)
+        dt, comm = tm.delegate_shared_ghosts(ranks, [mb.multilevel_tables(rl, intp) for rl in ranks], lv)
+        my_tables, ghost_comm = dt[rank], comm[rank]
+        print("rank %d: %d ghosts received through ghost buffers" % (
+            rank, sum(len(c["elemPos"]) for l in ghost_comm for k in ghost_comm[l] for c in ghost_comm[l][k]["recv"])))
     t = torch.zeros(128, dtype=torch.uint8)
     if rank == 0:
         t = torch.frombuffer(bytearray(mb.get_unique_id()), dtype=torch.uint8).clone()
@@ -97,7 +106,7 @@ def run_multilevel(a, mb, dist, torch, rank, world, QQ):
     omega = {l: float(1.0 / (3.0 * s.visc[0] + 0.5)) for l, s in ms.s.items()}
     visc = {l: float(s.visc[0]) for l, s in ms.s.items()}
     sch = mb.Scheme(ident, mine, omega, lambda_=0.25, omega_bulk=1.2,
-                    intp=(mb.multilevel_tables(mine, intp), intp["order"]), viscosity=visc)
+                    intp=(my_tables, intp["order"]), viscosity=visc, ghost_comm=ghost_comm)
     for l, s in ms.s.items():
         M = mine[l]
         g = M.globalPos - 1
@@ -141,6 +150,9 @@ def main():
     ap.add_argument("--p2p", action="store_true")
     ap.add_argument("--levels", type=int, default=2, help="gpu-ml: 2 or 3 levels")
     ap.add_argument("--method", default="linear", help="gpu-ml: interpolation method")
+    ap.add_argument("--ghost-exchange", action="store_true",
+                    help="gpu-ml: shared ghosts delegated to one rank and exchanged through the "
+                         "FromCoarser / FromFiner buffers (the reference's form of the run)")
     ap.add_argument("--fused-push", action="store_true",
                     help="peer-memory exchange with the push fused into the sweep kernel")
     a = ap.parse_args()

@@ -250,3 +250,63 @@ def test_weighted_partition_balances_the_work_and_stays_bit_identical(oracle, mi
             got = s.state[s.nNext][:M.nFluid * QQ].reshape(-1, QQ)
             exp = ms.s[l].state[ms.s[l].nNext].reshape(-1, QQ)[g]
             assert np.array_equal(got, exp), "rank %d level %d fluid PDFs differ" % (r, l)
+
+
+@pytest.mark.parametrize("min_level,boxes,QQ,method,relax,nranks", [
+    (4, [(5, 11)], 19, "linear", "bgk", 2), (4, [(5, 11)], 19, "linear", "bgk", 3),
+    (4, [(5, 11)], 27, "quadratic", "mrt", 2), (4, [(4, 12), (12, 20)], 19, "linear", "bgk", 4)],
+    ids=["2lvl-2ranks", "2lvl-3ranks", "2lvl-quad-mrt27-2ranks", "3lvl-4ranks"])
+def test_ghosts_delegated_through_the_from_coarser_and_from_finer_buffers(oracle, min_level, boxes, QQ, method,
+                                                                         relax, nranks):
+    """the reference's form of the same run: shared ghosts are interpolated by one rank and reach
+    the others through sendBufferFromCoarser / sendBufferFromFiner (+ the auxField of
+    ghostFromFiner elements) right after the interpolation that fills them; the fluid PDFs of
+    every rank stay bit-identical to the single-domain run"""
+    import musubi_b200 as mb
+    from musubi_b200 import treelm_multilevel as tm
+    lv, intp, tables, ms = build(oracle, min_level, boxes, QQ, method, relax, None, OMEGA_MIN[len(boxes)])
+    ranks = tm.partition_multilevel(lv, nranks)
+    rtables = [mb.multilevel_tables(rl, intp) for rl in ranks]
+    dtables, comm = tm.delegate_shared_ghosts(ranks, rtables, lv)
+    n_del = {k: sum(len(c["elemPos"]) for r in range(nranks) for l in lv for c in comm[r][l][k]["recv"])
+             for k in ("fromCoarser", "fromFiner")}
+    assert n_del["fromCoarser"] > 0 and n_del["fromFiner"] > 0
+    # every message has its counterpart, element for element (same treeIDs in the same order)
+    for r in range(nranks):
+        for l in lv:
+            for k in ("fromCoarser", "fromFiner"):
+                for snd in comm[r][l][k]["send"]:
+                    rcv = [c for c in comm[snd["proc"]][l][k]["recv"] if c["proc"] == r]
+                    assert len(rcv) == 1 and rcv[0]["pos"].size == snd["pos"].size
+                    assert np.array_equal(ranks[r][l].total[snd["elemPos"] - 1],
+                                          ranks[snd["proc"]][l].total[rcv[0]["elemPos"] - 1])
+    # the removed targets are exactly the received elements
+    for r in range(nranks):
+        for l in lv:
+            got = set()
+            for k in ("fromCoarser", "fromFiner"):
+                for c in comm[r][l][k]["recv"]:
+                    got |= set(int(e) for e in c["elemPos"])
+            before = set()
+            after = set()
+            for key in rtables[r]:
+                if key[0] == l:
+                    before |= set(int(t) for t in rtables[r][key]["targets"])
+                    after |= set(int(t) for t in dtables[r][key]["targets"])
+            assert before - after == got and after <= before
+    mr = oracle.MultiRankMultiLevel(ranks, dtables, ghost_comm=comm, relaxation=relax, kind="fluid",
+                                    omega_min=OMEGA_MIN[len(boxes)], omega_bulk=1.2, order=intp["order"])
+    for m in mr.r:
+        for l, s in m.s.items():
+            rho, vel = tgv_like(s.ld.bary_unit)
+            s.init_equilibrium(rho, vel)
+    ncyc = 5
+    ms.run(ncyc)
+    mr.run(ncyc)
+    for r, m in enumerate(mr.r):
+        for l, s in m.s.items():
+            M = ranks[r][l]
+            g = M.globalPos[:M.nFluid] - 1
+            got = s.state[s.nNext][:M.nFluid * QQ].reshape(-1, QQ)
+            exp = ms.s[l].state[ms.s[l].nNext].reshape(-1, QQ)[g]
+            assert np.array_equal(got, exp), "rank %d level %d fluid PDFs differ" % (r, l)
