@@ -135,7 +135,6 @@ def cpu_baseline(wl, level, steps, warmup=2, target_s=None):
     after `warmup` untimed ones; with target_s the step count is chosen from a short probe so
     that the timed part is about target_s seconds of CPU work."""
     from oracle import musoracle as mo
-    from musubi_b200 import cases
     QQ = 19 if wl["ident"]["layout"] == "d3q19" else 27
     ld = mo.build_level_desc(level, QQ, wl["kind"])
     sch = mo.Scheme(ld, wl["ident"]["relaxation"], wl["ident"]["kind"], omega=wl["omega"],
@@ -170,9 +169,14 @@ def cpu_baseline(wl, level, steps, warmup=2, target_s=None):
 
 
 def run_reference(args, wl_name, wl):
+    """the reference arm: nothing of the product is imported or loaded on this path"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("OMP_NUM_THREADS") == "1":
+        # torchrun pins every rank to one OpenMP thread; the CPU arm runs on rank 0 alone and
+        # takes all host cores (read by libgomp when the oracle library is loaded below)
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     level = min(wl["level"], 7)
     t0 = time.perf_counter()
     cb = cpu_baseline(wl, level, max(1, args.steps), warmup=args.warmup)
