@@ -15,7 +15,7 @@ import ctypes
 
 import numpy as np
 
-from . import _lib
+from . import _lib  # noqa: F401  (musubi_b200._lib is part of the package surface: bench.py, tests)
 from ._lib import P_DBL, P_I32, P_I64, check, lib, ptr
 
 BC_KIND = {"wall": 0, "velocity_bounceback": 1, "pressure_antibounceback": 2, "pressure_expol": 3}

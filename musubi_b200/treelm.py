@@ -4,7 +4,7 @@ reference's tem_levelDesc_type / pdf_data_type / boundary_type members so that
 what is handed to libmusb200 reads like what the Fortran shim hands over."""
 import numpy as np
 
-from . import _lib
+from . import _lib  # noqa: F401  (musubi_b200._lib is part of the package surface: bench.py, tests)
 from ._lib import P_I32, P_I64, P_DBL, mesh, ptr
 
 KIND = {"periodic": 0, "cavity": 1, "channel": 2}
