@@ -408,6 +408,8 @@ contains
     type(mus_scheme_type), intent(inout) :: scheme
     integer, intent(in) :: iLevel, iBnd
     integer(c_int) :: kind
+    integer(c_int32_t), allocatable :: iDir(:)
+    integer :: iLink, nLinks
     associate(bc => scheme%field(1)%bc(iBnd))
       select case (trim(bc%BC_kind))
       case ('wall');                kind = 0
@@ -421,18 +423,30 @@ contains
         call chk(musb200_bc_register(int(iLevel, c_int), int(iBnd, c_int), kind, 0_c_int, &
           &      bc%links(iLevel)%val, bc%links(iLevel)%val, bc%links(iLevel)%val,        &
           &      bc%links(iLevel)%val), 'bc_register')
-      else
+      else if (kind == 1) then
+        ! velocity_bounceback: the lists of mus_set_inletUbb (mus_bc_header_module.fpp:1876-1967)
         call chk(musb200_bc_register(int(iLevel, c_int), int(iBnd, c_int), kind,            &
           &      int(bc%links(iLevel)%nVals, c_int), bc%links(iLevel)%val,                   &
           &      bc%inletUbbQVal(iLevel)%outPos, bc%inletUbbQVal(iLevel)%posInBuffer,        &
           &      bc%inletUbbQVal(iLevel)%iDir), 'bc_register')
-      end if
-      if (kind >= 2) then
+      else
+        ! pressure boundaries carry mus_set_outletExpol's lists instead (:2256-2319):
+        ! statePos(l) = iDir(l) + (iElem(l)-1)*QQ; outPos / posInBuffer are not read for these kinds
+        nLinks = bc%links(iLevel)%nVals
+        allocate(iDir(max(nLinks, 1)))
+        do iLink = 1, nLinks
+          iDir(iLink) = bc%outletExpol(iLevel)%statePos(iLink) &
+            &         - (bc%outletExpol(iLevel)%iElem(iLink) - 1) * scheme%layout%fStencil%QQ
+        end do
+        call chk(musb200_bc_register(int(iLevel, c_int), int(iBnd, c_int), kind, int(nLinks, c_int), &
+          &      bc%links(iLevel)%val, bc%links(iLevel)%val, bc%links(iLevel)%val, iDir), 'bc_register')
+        deallocate(iDir)
         ! boundaries reading neighbours along the inward normal (mus_bc_header_module.fpp:1036-1060)
-        associate(gbc => scheme%globBC(iBnd)%elemLvl(iLevel))
-          call chk(musb200_bc_register_elems(int(iLevel, c_int), int(iBnd, c_int),           &
-            &      int(gbc%nElems, c_int), gbc%elem%val, gbc%posInBcElemBuf%val,             &
-            &      gbc%normalInd, int(bc%nNeighs, c_int), bc%neigh(iLevel)%posInState,       &
+        associate(gbc => scheme%globBC(iBnd))
+          call chk(musb200_bc_register_elems(int(iLevel, c_int), int(iBnd, c_int),              &
+            &      int(gbc%nElems(iLevel), c_int), gbc%elemLvl(iLevel)%elem%val,                 &
+            &      gbc%elemLvl(iLevel)%posInBcElemBuf%val, gbc%elemLvl(iLevel)%normalInd%val,    &
+            &      int(bc%nNeighs, c_int), bc%neigh(iLevel)%posInState,                          &
             &      bc%outletExpol(iLevel)%iElem), 'bc_register_elems')
         end associate
       end if

@@ -126,3 +126,151 @@ def test_every_derived_type_component_the_shim_touches_exists_in_the_reference()
     declared.add("buf_real")
     missing = sorted(used - declared)
     assert not missing, "components not found in the reference: %s" % missing
+
+
+# ---------------------------------------------------------------------------------------------
+# a type-aware pass: every component chain root%a(...)%b%c of the shim is resolved through the
+# derived-type definitions of the reference (a compiler's job; none is available here)
+def _reference_types(ref):
+    """{type name: {component: type name or None (intrinsic / procedure)}} incl. inherited ones"""
+    types, parents = {}, {}
+    for base in (os.path.join(ref, "mus", "source"), os.path.join(ref, "tem", "source")):
+        for d, _, files in os.walk(base):
+            for f in files:
+                if not f.endswith((".f90", ".fpp", ".inc")):
+                    continue
+                text = open(os.path.join(d, f), errors="replace").read()
+                text = re.sub(r"&\s*\n\s*&?", " ", text)
+                cur = None
+                for raw in text.splitlines():
+                    line = raw.split("!")[0].strip()
+                    low = line.lower()
+                    m = re.match(r"type\s*(?:,\s*([^:]*?))?\s*(?:::)?\s*(\w+)\s*$", line, flags=re.I)
+                    if cur is None and m and not low.startswith("type("):
+                        cur = m.group(2).lower()
+                        types.setdefault(cur, {})
+                        ext = re.search(r"extends\s*\(\s*(\w+)\s*\)", m.group(1) or "", flags=re.I)
+                        if ext:
+                            parents[cur] = ext.group(1).lower()
+                        continue
+                    if cur is not None:
+                        if re.match(r"end\s*type", low):
+                            cur = None
+                            continue
+                        if low.startswith("contains"):
+                            continue
+                        if "::" in line:
+                            spec, names = line.split("::", 1)
+                            t = re.match(r"\s*(?:type|class)\s*\(\s*(\w+)\s*\)", spec, flags=re.I)
+                            tname = t.group(1).lower() if t else None
+                            for n in re.split(r",(?![^()]*\))", names):
+                                n = re.sub(r"\(.*|=.*", "", n).strip().lower()
+                                if n:
+                                    types[cur][n] = tname
+                        else:
+                            m2 = re.match(r"procedure\b.*?(\w+)\s*(=>.*)?$", line, flags=re.I)
+                            if m2:
+                                types[cur][m2.group(1).lower()] = None
+    for t in list(types):
+        p = parents.get(t)
+        while p:
+            for k, v in types.get(p, {}).items():
+                types[t].setdefault(k, v)
+            p = parents.get(p)
+    # containers generated by CoCo text macros (tem_grow_array.fpp / tem_dyn_array.fpp, ?tname?):
+    for name in ("grw_intarray_type", "grw_longarray_type", "grw_realarray_type", "grw_int2darray_type",
+                 "grw_logical2darray_type", "dyn_intarray_type", "dyn_longarray_type"):
+        types.setdefault(name, {}).update({"nvals": None, "val": None, "containersize": None, "sorted": None})
+    # tem_communication_type%buf_real / tem_realbuffer_type come from the same kind of macro
+    types.setdefault("tem_communication_type", {})["buf_real"] = "tem_realbuffer_type"
+    types.setdefault("tem_realbuffer_type", {}).update({"pos": None, "nvals": None, "val": None})
+    return types
+
+
+def _chains(expr_text):
+    """component chains 'a%b(..)%c' of a source text -> lists of names"""
+    out, i, n = [], 0, len(expr_text)
+    while i < n:
+        m = re.compile(r"[A-Za-z_]\w*").match(expr_text, i)
+        if not m or (i > 0 and (expr_text[i - 1].isalnum() or expr_text[i - 1] in "_%")):
+            i += 1
+            continue
+        names, j = [m.group(0).lower()], m.end()
+        while True:
+            k = j
+            while k < n and expr_text[k] == " ":
+                k += 1
+            if k < n and expr_text[k] == "(":                    # skip a balanced argument list
+                depth = 0
+                while k < n:
+                    depth += expr_text[k] == "("
+                    depth -= expr_text[k] == ")"
+                    k += 1
+                    if depth == 0:
+                        break
+                while k < n and expr_text[k] == " ":
+                    k += 1
+            if k < n and expr_text[k] == "%":
+                m2 = re.compile(r"\s*([A-Za-z_]\w*)").match(expr_text, k + 1)
+                if not m2:
+                    break
+                names.append(m2.group(1).lower())
+                j = m2.end()
+                continue
+            break
+        if len(names) > 1:
+            out.append(names)
+        i = m.end()
+    return out
+
+
+def test_component_chains_resolve_through_the_references_type_definitions():
+    import pytest
+    ref = "/root/reference"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree absent")
+    types = _reference_types(ref)
+    assert "mus_scheme_type" in types and "layout" in types["mus_scheme_type"] and len(types) > 200
+    src = re.sub(r"&\s*\n\s*&?", " ", re.sub(r"!.*", "", open(SHIM).read()))
+    body = src[src.lower().index("\ncontains"):]
+    checked, problems = 0, []
+    for sub in re.split(r"\n\s*(?=subroutine\s+\w+)", body, flags=re.I):
+        env = {}
+        for m in re.finditer(r"(?:type|class)\s*\(\s*(\w+)\s*\)[^:\n]*::\s*([^\n]+)", sub, flags=re.I):
+            for n in re.split(r",(?![^()]*\))", m.group(2)):
+                env[re.sub(r"\(.*|=.*", "", n).strip().lower()] = m.group(1).lower()
+
+        def resolve(names):
+            t = env.get(names[0])
+            if t is None:
+                return "?"                          # not a derived-type variable of this scope
+            for c in names[1:]:
+                if t is None:
+                    return "component %s of an intrinsic / procedure component" % c
+                if t not in types:
+                    return "?"                      # a type defined outside the parsed sources
+                if c not in types[t]:
+                    return "type %s has no component %s" % (t, c)
+                t = types[t][c]
+            return t
+
+        # associate aliases, in order of appearance (an alias may build on an earlier one)
+        for m in re.finditer(r"associate\s*\((.*?)\)\s*\n", sub, flags=re.I | re.S):
+            for part in re.split(r",(?![^()]*\))", m.group(1)):
+                if "=>" not in part:
+                    continue
+                alias, expr = part.split("=>", 1)
+                ch = _chains(expr)
+                tgt = ch[0] if ch else [expr.strip().lower()]
+                r = resolve(tgt) if len(tgt) > 1 else env.get(tgt[0])
+                env[alias.strip().lower()] = r if (r in types) else env.get(alias.strip().lower())
+                if isinstance(r, str) and r.startswith(("type ", "component ")):
+                    problems.append("%s => %s: %s" % (alias.strip(), expr.strip(), r))
+        for names in _chains(sub):
+            r = resolve(names)
+            if r != "?":
+                checked += 1
+            if isinstance(r, str) and r.startswith(("type ", "component ")):
+                problems.append("%s: %s" % ("%".join(names), r))
+    assert checked > 60, checked
+    assert not problems, "\n".join(sorted(set(problems)))
