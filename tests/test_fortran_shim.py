@@ -266,6 +266,21 @@ def test_component_chains_resolve_through_the_references_type_definitions():
                 env[alias.strip().lower()] = r if (r in types) else env.get(alias.strip().lower())
                 if isinstance(r, str) and r.startswith(("type ", "component ")):
                     problems.append("%s => %s: %s" % (alias.strip(), expr.strip(), r))
+        # actual arguments of the bound C functions must be intrinsic data, never a derived type
+        # (e.g. a growing array must be passed as its %val)
+        for m in re.finditer(r"\b(musb200_\w+)\s*\(", sub):
+            k, depth = m.end(), 1
+            while k < len(sub) and depth:
+                depth += sub[k] == "("
+                depth -= sub[k] == ")"
+                k += 1
+            for arg in re.split(r",(?![^()]*\))", sub[m.end():k - 1]):
+                ch = _chains(arg)
+                pure = len(ch) == 1 and re.fullmatch(r"\s*[A-Za-z_]\w*(\s*\([^()]*\))?(\s*%\s*\w+(\s*\([^()]*\))?)+\s*", arg)
+                if pure:
+                    r = resolve(ch[0])
+                    if r in types:
+                        problems.append("%s(... %s ...): a %s is passed, not data" % (m.group(1), arg.strip(), r))
         for names in _chains(sub):
             r = resolve(names)
             if r != "?":
