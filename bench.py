@@ -293,11 +293,12 @@ def run_multilevel(args, wl_name, wl):
     check(lib.musb200_timers(ctypes.byref(cm), ctypes.byref(bm), ctypes.byref(com), ctypes.byref(im)))
     check(lib.musb200_set_profiling(0))
     value = lups_cycle * K / (t_ms * 1e-3) / 1e6
-    # the reference's own figure for the same run (calc_MLUPS, mus_tools_module.f90:505-507, 658-691):
-    # cellUpdates = sum_l nElems(l) / sf^(maxLevel - l) (integer division), iter = coarse cycles --
-    # it counts a fine cell once per coarse cycle, i.e. sf^(maxLevel - minLevel) times fewer updates
-    ref_updates = sum(int(glob[l].nFluid) // (2 ** (levels[-1] - l)) for l in levels)
-    value_ref_formula = ref_updates * K / (t_ms * 1e-3) / 1e6
+    # the reference's own figure for the same run (mus_perf_measure / calc_MLUPS,
+    # mus_tools_module.f90:498-531, 658-691): coarse levels scaled by 1 / sf^(maxLevel - l), the
+    # main loop's iteration count (coarse cycles) divided by sf^(maxLevel - minLevel) once more
+    from musubi_b200 import timing
+    value_ref_formula = timing.perf_measure({l: int(glob[l].nFluid) for l in levels}, K, t_ms * 1e-3,
+                                            max(cm.value, 1e-9) * 1e-3)[0]
     sweep_ms = cm.value / K
     peak, peak_src = measured_peak()
     achieved = BYTES_PER_LUP[19] * float(solve_cycle) / (sweep_ms * 1e-3) / 1e9
