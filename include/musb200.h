@@ -196,7 +196,13 @@ int musb200_bc_set_values(int level, int bc_id, int nVals, const double *vals);
 
 /* ---- halo exchange: tem_communication_type --------------------------------
  * tem/source/tem_comm_module.fpp:93-177; pos(iProc) = buf_real(iProc)%pos.
- * proc: 0-based ranks; nVals[iProc]; pos: concatenated position lists.        */
+ * proc: 0-based ranks; nVals[iProc]; pos: concatenated position lists.
+ * In multi-level runs the elements of the HALO buffer travel with their four auxField entries
+ * (auxField%sendBuffer, mus_auxField_module.f90:377-396), and so do the ghostFromFiner
+ * elements of the FROMFINER buffer (mus_intpAuxFieldCoarserAndExchange, :404-444): the entries
+ * are derived from the elements the positions belong to, no separate list is needed.
+ * FROMCOARSER is exchanged after the level's own step and after do_intpCoarserAndExchange,
+ * FROMFINER after do_intpFinerAndExchange (mus_control_module.f90:434-465, 861-1051).        */
 int musb200_comm_register(int level, int buf_kind, int dir, int nProcs, const int32_t *proc,
                           const int32_t *nVals, const int32_t *pos);
 
