@@ -114,3 +114,67 @@ def test_fneq_acoustic_moments(oracle, QQ):
     nu = (1.0 / omega - 0.5) / 3.0
     expect = -(2.0 * nu * S) * 2.0 / (2.0 - omega)      # -tau * cs4inv/(2-omega) * sum_i w_i Q_iab Q_icd
     assert np.max(np.abs(Pi - expect)) < 1e-14
+
+
+@pytest.mark.parametrize("QQ,relax,kind", [
+    (19, "bgk", "fluid"), (19, "trt", "fluid"), (19, "mrt", "fluid"), (19, "trt", "fluid_incompressible"),
+    (27, "bgk", "fluid"), (27, "trt", "fluid"), (27, "mrt", "fluid"), (27, "mrt", "fluid_incompressible")])
+def test_shear_wave_decays_with_the_configured_viscosity(oracle, QQ, relax, kind):
+    """physics pin for the kernels no reference fixture reaches (TRT D3Q19, the D3Q27 family):
+    u_x = U sin(k y) in a periodic box decays as exp(-nu k^2 t) with nu = (1/omega - 1/2)/3; the
+    shear relaxation rate every kernel applies must be omega (measured: within 1.3 %, the rest is
+    the O(k^2) lattice error and the start from f_eq)"""
+    import math
+    mo, N = oracle, 32
+    ld = mo.build_level_desc(5, QQ, "periodic")
+    omega = 1.6
+    nu = (1.0 / omega - 0.5) / 3.0
+    sch = mo.Scheme(ld, relax, kind, omega=omega, lambda_=0.25, omega_bulk=omega)
+    b = mo.barycenters(ld, (0.0, 0.0, 0.0), float(N))
+    k, U, n = 2.0 * math.pi / N, 1.0e-3, 200
+    vel = np.zeros((ld.nElems, 3))
+    vel[:, 0] = U * np.sin(k * b[:, 1])
+    sch.init_equilibrium(np.ones(ld.nElems), vel)
+    sch.run(n)
+    aux = sch.aux.reshape(-1, 4)[:ld.nFluid]
+    s = np.sin(k * b[:ld.nFluid, 1])
+    amp = float((aux[:, 1] * s).sum() / (s * s).sum())
+    rate = -math.log(amp / U) / n
+    assert abs(rate / (nu * k * k) - 1.0) < 0.02
+    # nothing leaks into the other components or the density beyond O(U^2)
+    assert np.max(np.abs(aux[:, 2])) < 1e-9 and np.max(np.abs(aux[:, 3])) < 1e-9
+    assert np.max(np.abs(aux[:, 0] - 1.0)) < 1e-6
+
+
+@pytest.mark.parametrize("outlet,tol_rho", [("pressure_expol", 3e-3), ("pressure_antibounceback", 1.5e-3)])
+def test_channel_reaches_a_steady_state_that_honours_its_boundaries(oracle, outlet, tol_rho):
+    """physics pin for velocity_bounceback + the pressure outlets in 3-D (no reference fixture
+    reaches them): a 16^3 duct with a uniform inflow u = 0.02 and an outlet held at rho = 1 becomes
+    steady; the mass flux is the same through every cross-section, equals rho u A up to the wall
+    corners of the inlet, the outlet density sits at the imposed value up to half a cell of
+    pressure gradient, and the total mass no longer changes"""
+    mo, N, u_in = oracle, 16, 0.02
+    ld = mo.build_level_desc(4, 19, "channel")
+    sch = mo.Scheme(ld, "bgk", "fluid", omega=1.0)
+    inlet = [b for b in ld.bc if b["id"] == 2][0]
+    assert inlet["kind"] == "velocity_bounceback"
+    sch.bc_vel[2] = np.tile(np.array([u_in, 0.0, 0.0]), (len(inlet["links"]), 1))
+    sch.bc_kind[3] = outlet
+    sch.bc_rho[3] = 1.0
+    sch.init_equilibrium(np.ones(ld.nElems), np.zeros((ld.nElems, 3)))
+    b = mo.barycenters(ld, (0.0, 0.0, 0.0), float(N))[:ld.nFluid]
+    sch.run(2000)
+    m0 = sch.total_mass()
+    sch.run(500)
+    assert abs(sch.total_mass() / m0 - 1.0) < 1e-9
+    aux = sch.aux.reshape(-1, 4)[:ld.nFluid]
+    flux = []
+    for x in (0.5, 4.5, 7.5, 11.5, 15.5):
+        sel = np.abs(b[:, 0] - x) < 1e-9
+        assert sel.sum() == N * N
+        flux.append(float((aux[sel, 0] * aux[sel, 1]).sum()))
+    assert max(flux) / min(flux) - 1.0 < 1e-5                   # the same through every plane
+    assert abs(flux[0] / (u_in * N * N) - 1.0) < 0.03          # what the inlet imposes
+    rho_out = float(aux[np.abs(b[:, 0] - (N - 0.5)) < 1e-9, 0].mean())
+    assert abs(rho_out - 1.0) < tol_rho                         # what the outlet imposes
+    assert float(aux[np.abs(b[:, 0] - 0.5) < 1e-9, 0].mean()) > rho_out   # pressure drops along the duct
