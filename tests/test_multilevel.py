@@ -310,3 +310,37 @@ def test_ghosts_delegated_through_the_from_coarser_and_from_finer_buffers(oracle
             got = s.state[s.nNext][:M.nFluid * QQ].reshape(-1, QQ)
             exp = ms.s[l].state[ms.s[l].nNext].reshape(-1, QQ)[g]
             assert np.array_equal(got, exp), "rank %d level %d fluid PDFs differ" % (r, l)
+
+
+def test_shear_wave_crosses_the_refinement_interface(oracle):
+    """physics pin for the ghost interpolation (no reference fixture reaches it): u_x = U sin(2 pi y)
+    on a 32^3 periodic cube with a 12^3-cell box refined once.  Acoustic scaling keeps the physical
+    viscosity across levels (f_neq rescaled at the interface), so the wave must decay at the coarse
+    level's nu k^2 and stay a sine on both levels; the quadratic interpolation leaves the smallest
+    distortion."""
+    import math
+    N, k, U, n = 32, 2.0 * math.pi, 1.0e-3, 100
+    resid = {}
+    for method in ("weighted_average", "linear", "quadratic"):
+        lv, intp, tables, ms = build(oracle, 5, [(10, 22)], 19, method, "bgk", None, 1.6)
+        for s in ms.s.values():
+            vel = np.zeros((s.ld.nElems, 3))
+            vel[:, 0] = U * np.sin(k * s.ld.bary_unit[:, 1])
+            s.init_equilibrium(np.ones(s.ld.nElems), vel)
+        nu0 = float(ms.s[5].visc[0])
+        assert abs(float(ms.s[6].visc[0]) / nu0 - 2.0) < 1e-14          # lattice viscosity doubles per level
+        ms.run(n)
+        worst = 0.0
+        for l, s in ms.s.items():
+            nf = s.ld.nFluid
+            aux, sn = s.aux.reshape(-1, 4)[:nf], np.sin(k * s.ld.bary_unit[:nf, 1])
+            amp = float((aux[:, 1] * sn).sum() / (sn * sn).sum())
+            if l == 5:      # the coarse level covers (almost) whole periods: its projection is the decay
+                rate = -math.log(amp / U) / n
+                assert abs(rate / (nu0 * (k / N) ** 2) - 1.0) < 0.05, (method, rate)
+            worst = max(worst, float(np.max(np.abs(aux[:, 1] - amp * sn))) / abs(amp),
+                        float(np.max(np.abs(aux[:, 2]))) / U, float(np.max(np.abs(aux[:, 3]))) / U)
+            assert np.max(np.abs(aux[:, 0] - 1.0)) < 1e-5
+        resid[method] = worst
+    assert resid["weighted_average"] < 0.03 and resid["linear"] < 0.03 and resid["quadratic"] < 0.008
+    assert resid["quadratic"] < 0.5 * resid["linear"]
