@@ -128,7 +128,7 @@ int musb200_set_viscosity(int level, const double *visc, double visc_uniform);
 
 /* ---- restart bridge: mus_pdf_serialize / mus_pdf_unserialize ---------------
  * mus/source/mus_buffer_module.fpp:80-190, called chunk-wise by tem_restart_writeData /
- * tem_restart_readData (mus_restart_module.f90:89-260).  treeID / levelPointer: the chunk of
+ * tem_restart_readData (mus_restart_module.f90:89-248).  treeID / levelPointer: the chunk of
  * tree%treeID and tree%levelPointer (position of each element in its level's total list);
  * buffer(nElems*QQ): QQ PDFs of state(:, nNext) per element in treeID (space-filling-curve)
  * order -- byte for byte the payload of the reference's restart *.lsb file.                    */
@@ -151,7 +151,7 @@ int musb200_source_force(int level, int order, int nElems, const int32_t *posInT
                          const double *force, int uniform);
 
 /* ---- passive scalar (scheme kind 'passive_scalar', nAuxScalars = 1) --------
- * mus_init_advRel_lbm_ps (init/mus_initLBMPS_module.f90:59-160): relaxation bgk with variant
+ * mus_init_advRel_lbm_ps (init/mus_initLBMPS_module.f90:59-159): relaxation bgk with variant
  * 1 = 'first' | 2 = 'second' (mus_compute_passiveScalar_module.fpp:77-279), trt = vStdNoOpt
  * (:293-398); diff_coeff = species%diff_coeff(1), lambda = species%lambda.                   */
 int musb200_set_species(int level, int relax_id, int variant, double diff_coeff, double lambda);

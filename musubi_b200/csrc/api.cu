@@ -743,7 +743,7 @@ int musb200_scheme_select(const char *kind, const char *relaxation, const char *
   else if (r == "mrt") rr = MUSB200_RELAX_MRT;
   else return setError(MUSB200_ERR_UNSUPPORTED, "relaxation '" + r + "' is outside the B200 hot path");
   if (kk == MUSB200_KIND_PASSIVE_SCALAR) {
-    // mus_init_advRel_lbm_ps (init/mus_initLBMPS_module.f90:59-160): bgk first|second for any
+    // mus_init_advRel_lbm_ps (init/mus_initLBMPS_module.f90:59-159): bgk first|second for any
     // layout, trt without a named variant = vStdNoOpt; the E/L-model variants and mrt are d3q19
     // special kernels outside the hot path
     const bool ok = (rr == MUSB200_RELAX_BGK && (v == "first" || v == "second")) ||

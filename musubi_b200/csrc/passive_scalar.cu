@@ -4,7 +4,7 @@
 //   mus_advRel_kPS_rBGK_v1st_l        mus/source/compute/mus_compute_passiveScalar_module.fpp:77-169
 //   mus_advRel_kPS_rBGK_v2nd_l        ...:183-279
 //   mus_advRel_kPS_rTRT_vStdNoOpt_l   ...:293-398
-// selected as mus_init_advRel_lbm_ps does (init/mus_initLBMPS_module.f90:59-160).
+// selected as mus_init_advRel_lbm_ps does (init/mus_initLBMPS_module.f90:59-159).
 //
 // The transport velocity (scheme%transVar%method(1), lattice units) is either uniform, a
 // per-element SoA array [3][S] uploaded by the host, or -- device-side coupling -- rows 1..3 of

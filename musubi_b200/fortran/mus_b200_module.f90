@@ -731,7 +731,7 @@ contains
   end subroutine mus_b200_timers
 
   !> passive scalar (scheme kind 'passive_scalar'): the species' relaxation after the level has
-  !! been created by mus_b200_upload (mus_init_advRel_lbm_ps, init/mus_initLBMPS_module.f90:59-160:
+  !! been created by mus_b200_upload (mus_init_advRel_lbm_ps, init/mus_initLBMPS_module.f90:59-159:
   !! relax_id bgk with variant 1 = 'first' | 2 = 'second', trt = vStdNoOpt)
   subroutine mus_b200_set_species(scheme, iLevel, relaxId, variant)
     type(mus_scheme_type), intent(in) :: scheme

@@ -1,10 +1,10 @@
 /* intp.c -- ORACLE (test infrastructure): coarse <-> fine ghost interpolation,
  * restated from
  *   fillMyGhostsFromFiner_avg_feq_fneq       mus/source/intp/mus_interpolate_average_module.fpp:274-347
- *   fillArbiMyGhostsFromFiner_avg            ...average_module.fpp:95-185
- *   fillFinerGhostsFromMe_weighAvg_feq_fneq  ...average_module.fpp:905-1038
+ *   fillArbiMyGhostsFromFiner_avg            mus_interpolate_average_module.fpp:95-185
+ *   fillFinerGhostsFromMe_weighAvg_feq_fneq  mus_interpolate_average_module.fpp:905-1038
  *   fillFinerGhostsFromMe_linear_feq_fneq    mus/source/intp/mus_interpolate_linear_module.fpp:399-505
- *   mus_interpolate_linear3D_leastSq         ...linear_module.fpp:1010-1049
+ *   mus_interpolate_linear3D_leastSq         mus_interpolate_linear_module.fpp:1010-1049
  *   fillFinerGhostsFromMe_quad_feq_fneq + mus_interpolate_quad3D_leastSq
  *                                            mus/source/intp/mus_interpolate_quadratic_module.fpp:292-..., 989-1034
  *   getNonEqFac_intp_*                       mus/source/mus_derivedQuantities_module.fpp:601-643
