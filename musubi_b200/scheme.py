@@ -293,13 +293,19 @@ class Scheme:
                                         elem_offset=elem_offset, nElems_global=nElems_global,
                                         write_header=write_header, **header_kw)
 
-    def read_restart(self, header_path, rank=0, nranks=1, base_dir=None):
+    def read_restart(self, header_path, rank=0, nranks=1, base_dir=None, elem_offset=None):
         """mus_readRestart (mus_restart_module.f90:172-246): this rank's share of the binary file
         -> state(:, nNext) of the fluid elements; returns the header's time_point.  Ghosts and
-        halos are not in the file (the reference re-fills them by interpolation / exchange)."""
+        halos are not in the file (the reference re-fills them by interpolation / exchange).
+        elem_offset: tree%elemOffset of this rank when the mesh is not distributed in treelm's
+        equal shares (a weighted partition); the element count is the scheme's own."""
         from . import restart_io
-        rf, off, data = restart_io.read_restart(header_path, rank, nranks, base_dir)
         tid, lp = restart_io.tree_order(self.levelDesc)
+        if elem_offset is None:
+            rf, off, data = restart_io.read_restart(header_path, rank, nranks, base_dir)
+        else:
+            rf = restart_io.RestartFile(header_path, base_dir)
+            data = rf.read(int(elem_offset), tid.size)
         if rf.nScalars * rf.nDofs != self.QQ or data.shape[0] != tid.size:
             raise ValueError("restart file %s: %d elements x %d scalars, this scheme holds %d x %d"
                              % (header_path, data.shape[0], rf.nScalars * rf.nDofs, tid.size, self.QQ))
