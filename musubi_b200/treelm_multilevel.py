@@ -122,6 +122,96 @@ def construct_connectivity(QQ, nghElems, property_, nFluid, haloOffset, nSize):
     return neigh
 
 
+def _poly(order, c):
+    """polyLinear_3D / polyQuadratic_3D (tem_matrix_module.fpp:464-523)"""
+    if order == LINEAR:
+        return np.array([1.0, c[0], c[1], c[2]])
+    return np.array([1.0, c[0], c[1], c[2], c[0] ** 2, c[1] ** 2, c[2] ** 2,
+                     c[0] * c[1], c[1] * c[2], c[2] * c[0]])
+
+
+def invert_matrix(A):
+    """invert_matrix (tem_matrix_module.fpp:610-660) = DGETRF + DGETRI as the reference's vendored
+    LAPACK executes them for these 4 x 4 / 10 x 10 matrices (tem/external/lapack: n is below every
+    block size, so DGETF2, DTRTI2 and the unblocked DGETRI loop run): partial pivoting on the
+    first largest entry, column scaling by the reciprocal pivot, and an EXACT zero pivot as the
+    only singularity criterion -- a merely ill-conditioned A^T A is inverted, as the reference
+    does.  Returns (inverse, errCode)."""
+    a = np.array(A, dtype=np.float64)
+    n = a.shape[0]
+    piv = np.zeros(n, dtype=np.int64)
+    info = 0
+    for j in range(n):                                  # DGETF2
+        jp = j + int(np.argmax(np.abs(a[j:, j])))       # IDAMAX: first maximum
+        piv[j] = jp
+        if a[jp, j] != 0.0:
+            if jp != j:
+                a[[j, jp], :] = a[[jp, j], :]
+            if j < n - 1:
+                if abs(a[j, j]) >= np.finfo(np.float64).tiny:
+                    a[j + 1:, j] = a[j + 1:, j] * (1.0 / a[j, j])
+                else:
+                    a[j + 1:, j] = a[j + 1:, j] / a[j, j]
+        elif info == 0:
+            info = j + 1
+        if j < n - 1:                                   # DGER, alpha = -1
+            for k in range(j + 1, n):
+                if a[j, k] != 0.0:
+                    a[j + 1:, k] = a[j + 1:, k] + a[j + 1:, j] * (-1.0 * a[j, k])
+    if info != 0:
+        return None, info
+    for j in range(n):                                  # DTRTRI: singularity check, then DTRTI2
+        if a[j, j] == 0.0:
+            return None, j + 1
+    for j in range(n):
+        a[j, j] = 1.0 / a[j, j]
+        ajj = -a[j, j]
+        for k in range(j):                              # DTRMV upper, no transpose, non-unit
+            if a[k, j] != 0.0:
+                t = a[k, j]
+                a[:k, j] = a[:k, j] + t * a[:k, k]
+                a[k, j] = a[k, j] * a[k, k]
+        a[:j, j] = ajj * a[:j, j]
+    for j in range(n - 1, -1, -1):                      # DGETRI: inv(A) * L = inv(U)
+        work = a[:, j].copy()
+        a[j + 1:, j] = 0.0
+        for k in range(j + 1, n):                       # DGEMV, alpha = -1, beta = 1
+            if work[k] != 0.0:
+                a[:, j] = a[:, j] + (-1.0 * work[k]) * a[:, k]
+    for j in range(n - 2, -1, -1):
+        if piv[j] != j:
+            a[:, [j, piv[j]]] = a[:, [piv[j], j]]
+    return a, 0
+
+
+def new_intp(order_max):
+    """the interpolation tables shared by all levels: intp%fillFinerFromMe(order)%intpMat_forLSF"""
+    return {"order": order_max, "matrices": {LINEAR: [], QUADRATIC: []},
+            "mat_ids": {LINEAR: {}, QUADRATIC: {}}, "mat_ok": {LINEAR: [], QUADRATIC: []}}
+
+
+def append_intp_matrix_lsf(intp, order, dirs, cxr):
+    """append_intpMatrixLSF (tem_matrix_module.fpp:161-244): one matrix ((A^T A)^-1 A^T, rows of A
+    = the polynomial basis at the source offsets cxDir) per distinct set of source directions,
+    identified by the bit set of the directions; returns its 0-based position, or -1 when A^T A
+    is singular (the caller falls back to the next lower order)."""
+    key = 0
+    for d in dirs:
+        key |= 1 << int(d)
+    ids = intp["mat_ids"][order]
+    if key in ids:
+        i = ids[key]
+        return (i if intp["mat_ok"][order][i] else -1)
+    A = np.array([_poly(order, cxr[d - 1]) for d in dirs])
+    inv, err = invert_matrix(A.T @ A)
+    ok = err == 0
+    M = inv @ A.T if ok else np.zeros((1, 1))
+    ids[key] = len(intp["matrices"][order])
+    intp["matrices"][order].append(M)
+    intp["mat_ok"][order].append(bool(ok))
+    return ids[key] if ok else -1
+
+
 def build_multilevel(min_level, boxes, QQ=19, cylinder=None, intp_method="linear"):
     """nested refined boxes in a periodic cube.
 
@@ -245,6 +335,7 @@ def build_from_kinds(kind, QQ=19, intp_method="linear"):
         L.nSolve = L.nFluid + L.nGhostFromCoarser
         L.total = (first_id(l) + codes).astype(np.int64)
         L.codes = codes
+        L.solid_ids = (first_id(l) + np.nonzero(k == 9)[0]).astype(np.int64)   # obstacle cells (walls)
         p = np.zeros(k.size, dtype=np.int32)
         p[codes] = np.arange(1, codes.size + 1, dtype=np.int32)
         pos[l] = p
@@ -275,33 +366,11 @@ def build_from_kinds(kind, QQ=19, intp_method="linear"):
     wavg = weighted_avg_dirs(QQ)
     nmax_wavg = 7 if QQ == 19 else 8
     nmin = {LINEAR: 4, QUADRATIC: 10}
-    intp = {"order": order_max, "matrices": {LINEAR: [], QUADRATIC: []},
-            "mat_ids": {LINEAR: {}, QUADRATIC: {}}, "mat_ok": {LINEAR: [], QUADRATIC: []}}
+    intp = new_intp(order_max)
     cxr = cx.astype(np.float64)
 
-    def poly(order, c):
-        if order == LINEAR:
-            return np.array([1.0, c[0], c[1], c[2]])
-        return np.array([1.0, c[0], c[1], c[2], c[0] ** 2, c[1] ** 2, c[2] ** 2,
-                         c[0] * c[1], c[1] * c[2], c[2] * c[0]])
-
     def lsf_matrix(order, dirs):
-        """append_intpMatrixLSF: one matrix per distinct source-direction set."""
-        key = 0
-        for d in dirs:
-            key |= 1 << int(d)
-        ids = intp["mat_ids"][order]
-        if key in ids:
-            i = ids[key]
-            return (i if intp["mat_ok"][order][i] else -1)
-        A = np.array([poly(order, cxr[d - 1]) for d in dirs])
-        AtA = A.T @ A
-        ok = np.linalg.matrix_rank(AtA) == AtA.shape[0] and np.linalg.cond(AtA) < 1e12
-        M = np.linalg.inv(AtA) @ A.T if ok else np.zeros((1, 1))
-        ids[key] = len(intp["matrices"][order])
-        intp["matrices"][order].append(M)
-        intp["mat_ok"][order].append(bool(ok))
-        return ids[key] if ok else -1
+        return append_intp_matrix_lsf(intp, order, dirs, cxr)
 
     for l in levels:
         L = out[l]

@@ -515,6 +515,67 @@ static void mrt_noopt(int QQ, int incomp, const double *in, double *out, const d
 }
 
 /* ======================================================================== */
+/* Generic formulations: second implementations of BGK and TRT written from the textbook
+ * definitions, NOT from the reference's optimised kernels -- table-driven equilibria and an
+ * explicit symmetric / antisymmetric split.  They are the comparison partners of the optimised
+ * restatements above where the reference's own utests offer none (TRT D3Q19 / D3Q27, BGK D3Q27),
+ * at the utests' tolerance of 2500 eps (tests/test_oracle_properties.py).
+ *   feq_kind 0: f_i = w_i rho (1 + 3 c.u + 9/2 (c.u)^2 - 3/2 u^2)     (get_pdfEq_d3q19 / _d3q27)
+ *   feq_kind 1: f_i = rho Phi_cx(ux) Phi_cy(uy) Phi_cz(uz), Phi_0(a) = 2/3 - a^2,
+ *               Phi_+-1(a) = (1/3 + a^2 +- a) / 2                      (the product form of
+ *               mus_advRel_kFluid_rTRT_vStd_lD3Q27, mus_compute_d3q27_module.fpp:601-655)
+ *   feq_kind 2: f_i = w_i (rho + rho0 (3 c.u + 9/2 (c.u)^2 - 3/2 u^2)), rho0 = 1 (incompressible) */
+static void feq_generic(int QQ, int feq_kind, double rho, const double u[3], double *fEq) {
+  const int *cx = ora_cxDir(QQ);
+  const double *w = ora_weights(QQ);
+  if (feq_kind == 1) {
+    for (int d = 0; d < QQ; ++d) {
+      double prod = rho;
+      for (int k = 0; k < 3; ++k) {
+        const int c = cx[3 * d + k];
+        const double a = u[k];
+        prod *= c == 0 ? (2.0 / 3.0 - a * a) : 0.5 * (1.0 / 3.0 + a * a + (double)c * a);
+      }
+      fEq[d] = prod;
+    }
+    return;
+  }
+  const double usq = u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
+  for (int d = 0; d < QQ; ++d) {
+    const double cu = (double)cx[3 * d] * u[0] + (double)cx[3 * d + 1] * u[1] + (double)cx[3 * d + 2] * u[2];
+    const double poly = 3.0 * cu + 4.5 * cu * cu - 1.5 * usq;
+    fEq[d] = feq_kind == 2 ? w[d] * (rho + poly) : w[d] * rho * (1.0 + poly);
+  }
+}
+
+int ora_compute_generic(int relax, int QQ, int feq_kind, const double *in, double *out,
+                        const double *aux, const int32_t *neigh, const double *omg,
+                        int nSize, int nSolve, const ora_relax_t *rp) {
+  if ((QQ != 19 && QQ != 27) || (relax != ORA_BGK && relax != ORA_TRT)) return -1;
+  const int *inv = ora_cxDirInv(QQ);
+  for (int e = 1; e <= nSolve; ++e) {
+    double f[27], fEq[27];
+    for (int d = 1; d <= QQ; ++d) f[d - 1] = PULL(d);
+    const double u[3] = {AUX(1), AUX(2), AUX(3)};
+    feq_generic(QQ, feq_kind, AUX(0), u, fEq);
+    const double wP = omg[e - 1];
+    if (relax == ORA_BGK) {
+      for (int d = 0; d < QQ; ++d) SAVE(d + 1) = f[d] + wP * (fEq[d] - f[d]);
+      continue;
+    }
+    /* TRT: omega^- from the magic parameter, Lambda = (1/omega^+ - 1/2)(1/omega^- - 1/2) */
+    const double wN = 1.0 / (rp->lambda / (1.0 / wP - 0.5) + 0.5);
+    for (int d = 0; d < QQ; ++d) {
+      const int b = inv[d] - 1;
+      const double fs = 0.5 * (f[d] + f[b]), fa = 0.5 * (f[d] - f[b]);
+      const double es = 0.5 * (fEq[d] + fEq[b]), ea = 0.5 * (fEq[d] - fEq[b]);
+      SAVE(d + 1) = f[d] - wP * (fs - es) - wN * (fa - ea);
+    }
+  }
+  return 0;
+}
+
+/* ======================================================================== */
 int ora_compute(int relax, int QQ, int incomp, const double *in, double *out,
                 const double *aux, const int32_t *neigh, const double *omega,
                 int nSize, int nSolve, const ora_relax_t *rp) {

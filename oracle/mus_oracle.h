@@ -74,6 +74,12 @@ int ora_compute_noopt(int relax, int QQ, const double *in, double *out,
 int ora_compute_noopt_kind(int relax, int QQ, int incompressible, const double *in, double *out,
                            const double *aux, const int32_t *neigh, const double *omega,
                            int nSize, int nSolve, const ora_relax_t *rp);
+/* generic formulations written from the textbook definitions (table-driven equilibrium, explicit
+ * symmetric / antisymmetric split), independent of the optimised restatements: relax = ORA_BGK |
+ * ORA_TRT; feq_kind 0 second-order polynomial, 1 product form (TRT D3Q27), 2 incompressible */
+int ora_compute_generic(int relax, int QQ, int feq_kind, const double *in, double *out,
+                        const double *aux, const int32_t *neigh, const double *omega,
+                        int nSize, int nSolve, const ora_relax_t *rp);
 const double *ora_mrt_matrix(int QQ, int inverse); /* [QQ][QQ] row-major */
 void ora_mrt_diag(int QQ, double omegaKine, double omegaBulk, double *s_mrt);
 
@@ -133,6 +139,29 @@ void ora_fill_finer_ghosts_from_me(int order, int QQ, int incomp, const double *
                                    const int32_t *posInMat, const int32_t *matOffset,
                                    const double *matrices, const double *coord,
                                    const double *tVisc);
+
+/* ---- ghost dependency build (dependencies.c): an implementation independent of the
+ * product's host-side generator, compared with it list by list ------------------------------- */
+/* tem_build_verticalDependencies (tem_construction_module.f90:2894-2985); blockStart[0..4]:
+ * 0-based start of the fluid / ghostFromCoarser / ghostFromFiner / halo blocks of `total`, end */
+void ora_vertical_dep_from_coarser(int nGhost, const int64_t *ghostID, const int64_t *cTotal,
+                                   const int32_t *cBlockStart, int32_t *parentPos, int32_t *childNum,
+                                   double *coord);
+void ora_vertical_dep_from_finer(int nGhost, const int64_t *ghostID, const int64_t *fTotal,
+                                 const int32_t *fBlockStart, int32_t *srcOffset, int32_t *srcPos);
+/* tem_intpMatrixLSF_type store of one interpolation order (tem_matrix_module.fpp:161-425) */
+void *ora_lsf_new(int order);
+void ora_lsf_delete(void *store);
+int ora_lsf_count(const void *store);
+int ora_lsf_get(const void *store, int pos, int32_t *hashID, int32_t *invertible, int32_t *rows,
+                int32_t *cols, double *A);
+int ora_lsf_append(void *store, int QQ, int nSources, const int32_t *neighDir, int32_t *pos);
+/* mus_intp_update_depFromCoarser (mus_interpolate_module.fpp:544-833) for one target level */
+int ora_update_dep_from_coarser(int QQ, int orderMax, int nGhost, const int32_t *parentPos,
+                                const int32_t *childNum, const double *coord,
+                                const int32_t *cNghElems, int32_t *order, int32_t *nSrc,
+                                int32_t *src, int32_t *dir, int32_t *posInMat, double *weights,
+                                void *lin, void *quad);
 
 /* ---- source terms and passive scalar (source.c) ------------------------ */
 /* force in lattice units, [nElems][3]; posInTotal = fun%elemLvl(iLevel)%posInTotal (1-based) */

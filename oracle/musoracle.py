@@ -650,6 +650,137 @@ def global_tree(levels):
     return ids[o], ptrs[o]
 
 
+# --------------------------------------------------------------------------
+# ghost dependency build (oracle/dependencies.c): independent of the product's generator
+# --------------------------------------------------------------------------
+def _block_start(ld):
+    b = np.zeros(5, dtype=np.int32)
+    b[1] = ld.nFluid
+    b[2] = b[1] + ld.nGhostFromCoarser
+    b[3] = b[2] + ld.nGhostFromFiner
+    b[4] = b[3] + ld.nHalo
+    return b
+
+
+def ngh_elems_from_total(ld, QQ, solid_ids=None):
+    """levelDesc%neigh(1)%nghElems of a (multi-level) descriptor from its total list alone: the
+    stencil neighbour's treeID (periodic wrap at the universe cube, tem_topology_module.f90:
+    590-638) looked up block by block (tem_treeIDinTotal); a neighbour that is a solid cell
+    (obstacle, boundary id 1) gives -1, a missing one 0.  Returns [nElems][QQ-1], 1-based."""
+    level = ld.level
+    n = 1 << level
+    cx = cx_dir(QQ)
+    first = first_id_at_level(level)
+    total = np.asarray(ld.total, dtype=np.int64)
+    nEl = total.size
+    x, y, z = coord_of_morton(total - first)
+    blocks = _block_start(ld)
+    solid = np.sort(np.asarray(solid_ids if solid_ids is not None else [], dtype=np.int64))
+    out = np.zeros((nEl, QQ - 1), dtype=np.int32)
+    for d in range(QQ - 1):
+        nid = first + morton_of_coord(np.mod(x + cx[d, 0], n), np.mod(y + cx[d, 1], n), np.mod(z + cx[d, 2], n))
+        pos = np.zeros(nEl, dtype=np.int64)
+        for b in range(4):
+            lo, hi = int(blocks[b]), int(blocks[b + 1])
+            if hi == lo:
+                continue
+            blk = total[lo:hi]
+            k = np.minimum(np.searchsorted(blk, nid), hi - lo - 1)
+            hit = (blk[k] == nid) & (pos == 0)
+            pos = np.where(hit, lo + k + 1, pos)
+        if solid.size:
+            k = np.minimum(np.searchsorted(solid, nid), solid.size - 1)
+            pos = np.where((pos == 0) & (solid[k] == nid), -1, pos)
+        out[:, d] = pos
+    return out
+
+
+class LsfStore:
+    """tem_intpMatrixLSF_type of one interpolation order (shared by all levels)"""
+
+    def __init__(self, order):
+        L = lib()
+        L.ora_lsf_new.restype = ctypes.c_void_p
+        L.ora_lsf_delete.argtypes = [ctypes.c_void_p]
+        L.ora_lsf_count.argtypes = [ctypes.c_void_p]
+        L.ora_lsf_get.argtypes = [ctypes.c_void_p, ctypes.c_int, _ip, _ip, _ip, _ip, _dp]
+        L.ora_lsf_append.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _ip, _ip]
+        self.order = order
+        self.h = ctypes.c_void_p(L.ora_lsf_new(order))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ora_lsf_delete(self.h)
+            self.h = None
+
+    def append(self, QQ, neighDir):
+        """append_intpMatrixLSF: returns (success, 1-based position)"""
+        d = np.ascontiguousarray(neighDir, dtype=np.int32)
+        pos = np.zeros(1, dtype=np.int32)
+        ok = lib().ora_lsf_append(self.h, QQ, d.size, _i(d), _i(pos))
+        return bool(ok), int(pos[0])
+
+    def __len__(self):
+        return lib().ora_lsf_count(self.h)
+
+    def get(self, pos):
+        """(hashID, invertible, matrix [nCoeffs][nSources]) of the 1-based position"""
+        hid, inv, r, c = (np.zeros(1, dtype=np.int32) for _ in range(4))
+        lib().ora_lsf_get(self.h, pos, _i(hid), _i(inv), _i(r), _i(c), None)
+        A = np.zeros(int(r[0]) * int(c[0]))
+        lib().ora_lsf_get(self.h, pos, _i(hid), _i(inv), _i(r), _i(c), _d(A))
+        return int(hid[0]), bool(inv[0]), A.reshape(int(r[0]), int(c[0]))
+
+
+def build_dependencies(levels, QQ, order_max, ngh=None):
+    """tem_build_verticalDependencies + mus_intp_update_depFromCoarser over all levels of a
+    multi-level mesh given as {level: descriptor with total, nFluid, nGhostFromCoarser,
+    nGhostFromFiner, nHalo}; ngh: {level: nghElems} (default: the descriptors' own).
+    Returns ({level: dict(fromFiner=(srcOffset, srcPos), fromCoarser=dict(parentPos, childNum,
+    coord, order, nSrc, src, dir, posInMat, weights))}, {order: LsfStore})."""
+    L = lib()
+    L.ora_update_dep_from_coarser.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, _ip, _ip, _dp, _ip,
+                                              _ip, _ip, _ip, _ip, _ip, _dp, ctypes.c_void_p, ctypes.c_void_p]
+    stores = {1: LsfStore(1), 2: LsfStore(2)}
+    out = {}
+    lv = sorted(levels)
+    for l in lv:                                   # source level ascending, as the reference loops
+        ld = levels[l]
+        dep = {}
+        total = np.ascontiguousarray(ld.total, dtype=np.int64)
+        nGFC, nGFF = int(ld.nGhostFromCoarser), int(ld.nGhostFromFiner)
+        if nGFC:
+            C = levels[l - 1]
+            ctot = np.ascontiguousarray(C.total, dtype=np.int64)
+            cb = _block_start(C)
+            gid = np.ascontiguousarray(total[ld.nFluid:ld.nFluid + nGFC])
+            parent, child = np.zeros(nGFC, dtype=np.int32), np.zeros(nGFC, dtype=np.int32)
+            coord = np.zeros((nGFC, 3))
+            L.ora_vertical_dep_from_coarser(nGFC, _l(gid), _l(ctot), _i(cb), _i(parent), _i(child), _d(coord))
+            cngh = np.ascontiguousarray(ngh[l - 1] if ngh is not None else C.nghElems, dtype=np.int32)
+            order, nSrc, pim = (np.zeros(nGFC, dtype=np.int32) for _ in range(3))
+            src, dirs = np.zeros((nGFC, 27), dtype=np.int32), np.zeros((nGFC, 27), dtype=np.int32)
+            w = np.zeros((nGFC, 27))
+            rc = L.ora_update_dep_from_coarser(QQ, order_max, nGFC, _i(parent), _i(child), _d(coord), _i(cngh),
+                                               _i(order), _i(nSrc), _i(src), _i(dirs), _i(pim), _d(w),
+                                               stores[1].h, stores[2].h)
+            if rc != 0:
+                raise RuntimeError("a ghostFromCoarser has no source (the reference aborts)")
+            dep["fromCoarser"] = dict(parentPos=parent, childNum=child, coord=coord, order=order, nSrc=nSrc,
+                                      src=src, dir=dirs, posInMat=pim, weights=w)
+        if nGFF:
+            F = levels[l + 1]
+            ftot = np.ascontiguousarray(F.total, dtype=np.int64)
+            fb = _block_start(F)
+            o0 = ld.nFluid + nGFC
+            gid = np.ascontiguousarray(total[o0:o0 + nGFF])
+            so, sp = np.zeros(nGFF + 1, dtype=np.int32), np.zeros(8 * nGFF, dtype=np.int32)
+            L.ora_vertical_dep_from_finer(nGFF, _l(gid), _l(ftot), _i(fb), _i(so), _i(sp))
+            dep["fromFiner"] = (so, sp[:so[-1]].copy())
+        out[l] = dep
+    return out, stores
+
+
 class PassiveScalarScheme:
     """scheme kind 'passive_scalar' on one level: mus_calcAuxField_zerothMoment +
     mus_advRel_kPS_* (mus_compute_passiveScalar_module.fpp), transport velocity in lattice units."""

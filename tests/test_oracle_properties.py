@@ -55,6 +55,69 @@ def test_optimised_kernel_equals_noopt_kernel(oracle, relax, QQ, incomp):
     assert np.max(np.abs(a - b)) < 2500 * EPS
 
 
+def run_generic(mo, relax, QQ, feq_kind, f, omega, lam=0.25, incomp=0):
+    n = f.size // QQ
+    ng = ident_neigh(QQ, n)
+    aux = np.zeros(n * 4)
+    (mo.lib().ora_calc_aux_incomp if incomp else mo.lib().ora_calc_aux)(QQ, mo._d(aux), mo._d(f), mo._i(ng), n, n)
+    out = np.zeros_like(f)
+    om = np.full(n, float(omega))
+    rp = mo._Relax(lam, 1.0)
+    rc = mo.lib().ora_compute_generic(mo.RELAX[relax], QQ, feq_kind, mo._d(f), mo._d(out), mo._d(aux),
+                                      mo._i(ng), mo._d(om), n, n, ctypes.byref(rp))
+    assert rc == 0
+    return out.reshape(n, QQ)
+
+
+# (relaxation, QQ, fluid_incompressible, equilibrium of the generic partner): the kernels whose
+# reference utests offer no comparison partner -- TRT D3Q19 (the bench's kernel), TRT D3Q27
+# (product-form equilibrium), BGK D3Q27 (the oracle's "NoOpt" BGK is the same function there)
+GENERIC = [("trt", 19, 0, 0), ("trt", 19, 1, 2), ("trt", 27, 0, 1), ("bgk", 27, 0, 0), ("bgk", 27, 1, 2),
+           ("bgk", 19, 0, 0), ("bgk", 19, 1, 2)]
+
+
+@pytest.mark.parametrize("relax,QQ,incomp,feq_kind", GENERIC)
+@pytest.mark.parametrize("omega,lam", [(1.7, 3.0 / 16.0), (0.8, 0.25), (1.95, 1.0 / 12.0)])
+def test_optimised_kernel_equals_generic_formulation(oracle, relax, QQ, incomp, feq_kind, omega, lam):
+    """two independent implementations agree at the reference utests' tolerance (2500 eps): the
+    restated optimised kernel and a textbook formulation (table-driven equilibrium, explicit
+    symmetric / antisymmetric split for TRT)"""
+    f = random_pdfs(oracle, QQ, 256, 31 + QQ + incomp)
+    a, _ = run_kernel(oracle, relax, QQ, incomp, f, omega, lam=lam)
+    b = run_generic(oracle, relax, QQ, feq_kind, f, omega, lam=lam, incomp=incomp)
+    assert np.max(np.abs(a - b)) < 2500 * EPS
+
+
+def test_product_form_equilibrium_of_trt_d3q27(oracle):
+    """the factorised equilibrium of the D3Q27 TRT kernel: its moments up to second order are
+    those of the polynomial equilibrium (rho, rho u, rho (u u + cs2 I)); it differs from it at
+    third order in u, which is why the TRT D3Q27 kernel needs its own comparison partner"""
+    rng = np.random.default_rng(9)
+    cx = oracle.cx_dir(27).astype(np.float64)
+    w = oracle.weights(27)
+    n = 64
+    rho = 1.0 + 0.05 * rng.standard_normal(n)
+    u = 0.05 * rng.standard_normal((n, 3))
+    f = np.zeros((n, 27))
+    for d in range(27):
+        phi = np.ones(n)
+        for k in range(3):
+            a = u[:, k]
+            phi = phi * ((2.0 / 3.0 - a * a) if cx[d, k] == 0 else 0.5 * (1.0 / 3.0 + a * a + cx[d, k] * a))
+        f[:, d] = rho * phi
+    # at f = feq the TRT collision is the identity
+    out, _ = run_kernel(oracle, "trt", 27, 0, f.ravel().copy(), 1.6)
+    assert np.max(np.abs(out - f)) < 50 * EPS
+    assert np.max(np.abs(f.sum(axis=1) - rho)) < 20 * EPS
+    assert np.max(np.abs(f @ cx - rho[:, None] * u)) < 20 * EPS
+    P = np.einsum("nd,da,db->nab", f, cx, cx)
+    exp = rho[:, None, None] * (u[:, :, None] * u[:, None, :] + np.eye(3)[None] / 3.0)
+    assert np.max(np.abs(P - exp)) < 50 * EPS
+    cu = u @ cx.T
+    poly = w[None, :] * rho[:, None] * (1.0 + 3.0 * cu + 4.5 * cu * cu - 1.5 * (u * u).sum(1)[:, None])
+    assert 1e-7 < np.max(np.abs(f - poly)) < 1e-3
+
+
 @pytest.mark.parametrize("relax,QQ,incomp", ALL)
 def test_rest_state_is_a_fixed_point(oracle, relax, QQ, incomp):
     w = oracle.weights(QQ)
