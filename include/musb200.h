@@ -95,6 +95,18 @@ int musb200_scheme_select(const char *kind, const char *relaxation, const char *
 int musb200_level_create(int level, int QQ, int nScalars, int nAuxScalars, int nSize,
                          int nFluid, int nGhostFromCoarser, int nGhostFromFiner, int nHalo,
                          const int32_t *neigh, const int64_t *property, const int64_t *treeID);
+/* treelm's predefined cube (`mesh = { predefined = 'cube', refinementLevel = treeLevel }`,
+ * generate_treelm_cube, tem/source/treelmesh_module.f90:1224-1318) on ONE rank with the
+ * connectivity of mus_construct_connectivity (mus_connectivity_module.fpp:113-177) generated on the
+ * device: all 8^treeLevel elements in Morton order, fully periodic (walls = 0) or closed by walls
+ * on the six faces (walls = 1).  The host form of the list ends at nSize*QQ < 2^31 (79 M elements
+ * for d3q27); this entry point has no such limit, so one B200 holds BASELINE config 3 (512^3,
+ * d3q27: 76 GB).  Equivalent to musb200_level_create with the list the host would build
+ * (musb200_neigh_download returns exactly that list where it is representable).            */
+int musb200_level_create_cube(int level, int treeLevel, int QQ, int walls);
+/* mus_init_pdf with zero strain rate (mus/source/mus_flow_module.fpp:484-589): both state
+ * buffers of every element <- f_eq(rho, u) of the auxField handed over by musb200_aux_upload   */
+int musb200_state_init_equilibrium(int level);
 int musb200_level_destroy(int level);
 /* reads back the device neighbour list re-encoded as the Fortran positions
  * (bit-exact parity check of the index lists) */
@@ -258,6 +270,16 @@ int musb200_step(int minLevel, int maxLevel, int nCoarseCycles);
  *    last step pulled from (tracking of a few elements every step then costs a one-thread
  *    kernel instead of 32 B of HBM writes per element and step) */
 int musb200_set_aux_every_step(int flag);
+/* mus_init_flow once the fluid PDFs are in state(:, nNext) -- after an initial condition or
+ * mus_readRestart (mus/source/mus_flow_module.fpp:206-240): mus_initAuxField (auxField of the
+ * fluid elements from their own PDFs, auxField halos, auxField of the ghostFromFiner elements),
+ * fillHelperElementsFineToCoarse (:1517-1588: ghostFromFiner <- finer level, FromFiner and halo
+ * exchange, finest level first) and fillHelperElementsCoarseToFine (:1601-1673: FromCoarser
+ * exchange, ghostFromCoarser <- coarser level for every order).  Restart files and initial
+ * conditions hold fluid elements only; without this call halo, ghost and auxField rows of a
+ * freshly created level are zero.  Collective over the ranks.                               */
+int musb200_fill_helper_elements(int minLevel, int maxLevel);
+
 /* 1: on several ranks the elements that own a send-buffer link (prp_sendHalo) are swept first
  * and their halo exchange (on a second, high-priority stream) overlaps the sweep of the
  * remaining elements; 0 (default): exchange strictly after compute as comm_isend_irecv_real is

@@ -31,6 +31,8 @@ SIGNATURES = {
     "musb200_device_count": [P_INT],
     "musb200_scheme_select": [c_char_p, c_char_p, c_char_p, c_char_p, P_INT, P_INT, P_INT],
     "musb200_level_create": [c_int] * 9 + [P_I32, P_I64, P_I64],
+    "musb200_level_create_cube": [c_int, c_int, c_int, c_int],
+    "musb200_state_init_equilibrium": [c_int],
     "musb200_level_destroy": [c_int],
     "musb200_neigh_download": [c_int, P_I32],
     "musb200_state_upload": [c_int, c_int, c_void_p],
@@ -59,6 +61,7 @@ SIGNATURES = {
                               P_I32, P_DBL, P_DBL],
     "musb200_step": [c_int, c_int, c_int],
     "musb200_set_aux_every_step": [c_int],
+    "musb200_fill_helper_elements": [c_int, c_int],
     "musb200_synchronize": [],
     "musb200_reduce": [c_int, P_DBL, P_DBL, P_INT],
     "musb200_compute_host": [c_int, c_int, c_int, P_DBL, P_DBL, P_DBL, P_I32, c_int, c_int, P_DBL,

@@ -263,11 +263,15 @@ static Level *findLevel(int level) {
   auto it = g.levels().find(level);
   return it == g.levels().end() ? nullptr : it->second.get();
 }
-#define GET_LEVEL(L, level)                                                          \
+// read-only queries (downloads, probes, reductions) leave a captured step graph valid
+#define GET_LEVEL_RO(L, level)                                                       \
   MUSB_TRY(needReady());                                                             \
-  ++g.epoch; /* any per-level call may change what a captured step graph would replay */ \
   Level *L = findLevel(level);                                                       \
   if (!L) return setError(MUSB200_ERR_ARG, "unknown level " + std::to_string(level))
+// calls that may change what a captured step graph would replay bump the epoch
+#define GET_LEVEL(L, level)                                                          \
+  GET_LEVEL_RO(L, level);                                                            \
+  ++g.epoch
 
 static int stageBuf(size_t n) {
   if (g.stage.n < n) MUSB_TRY(g.stage.alloc(n));
@@ -622,6 +626,36 @@ static int levelStep(int iLevel, int minLevel, int maxLevel, bool lastCycle) {
   return 0;
 }
 
+// mus_init_flow after the state has been filled (mus/source/mus_flow_module.fpp:206-240):
+// mus_initAuxField (:1677-1737), fillHelperElementsFineToCoarse (:1517-1588),
+// fillHelperElementsCoarseToFine (:1601-1673)
+static int fillFineToCoarse(int iLevel, int minLevel, int maxLevel) {
+  Level *L = findLevel(iLevel);
+  if (!L) return setError(MUSB200_ERR_ARG, "level " + std::to_string(iLevel) + " was not created");
+  const bool multi = maxLevel > minLevel;
+  if (iLevel < maxLevel) {
+    MUSB_TRY(fillFineToCoarse(iLevel + 1, minLevel, maxLevel));
+    Level *F = findLevel(iLevel + 1);
+    // state and auxField of my ghostFromFiner elements <- average over the children
+    // (do_intp of fillMineFromFiner + mus_intpAuxFieldCoarserAndExchange)
+    MUSB_TRY(applyIntp(*F, *L, L->fromFiner, true));
+    MUSB_TRY(exchangeStateAndAux(*L, MUSB200_BUF_FROMFINER));
+  }
+  if (multi || L->nAux == 4) MUSB_TRY(exchangeStateAndAux(*L));
+  else MUSB_TRY(exchange(*L, MUSB200_BUF_HALO, L->state[L->nNext].p, L->QQ));
+  return 0;
+}
+static int fillCoarseToFine(int iLevel, int minLevel, int maxLevel) {
+  Level *L = findLevel(iLevel);
+  if (iLevel > minLevel) MUSB_TRY(exchange(*L, MUSB200_BUF_FROMCOARSER, L->state[L->nNext].p, L->QQ));
+  if (iLevel < maxLevel) {
+    Level *F = findLevel(iLevel + 1);
+    for (auto &set : F->fromCoarser) MUSB_TRY(applyIntp(*L, *F, set, false));
+    MUSB_TRY(fillCoarseToFine(iLevel + 1, minLevel, maxLevel));
+  }
+  return 0;
+}
+
 }  // namespace musb200
 
 using namespace musb200;
@@ -811,6 +845,44 @@ int musb200_level_create(int level, int QQ, int nScalars, int nAuxScalars, int n
   return 0;
 }
 
+// treelm's predefined cube on one rank, connectivity generated on the device (cube.cu)
+int musb200_level_create_cube(int level, int treeLevel, int QQ, int walls) {
+  MUSB_TRY(needReady());
+  if (QQ != 19 && QQ != 27) return setError(MUSB200_ERR_UNSUPPORTED, "only d3q19 / d3q27");
+  if (treeLevel < 1 || treeLevel > 10) return setError(MUSB200_ERR_ARG, "cube: tree level must be 1..10");
+  const long long n = 1LL << (3 * treeLevel);
+  auto L = std::make_unique<Level>();
+  L->level = level; L->QQ = QQ; L->nSize = (int)n; L->nFluid = (int)n;
+  L->nElems = (int)n; L->nAux = 4; L->nSolve = (int)n;
+  L->S = (n + 31) / 32 * 32;
+  for (int b = 0; b < 2; ++b) {
+    MUSB_TRY(L->state[b].alloc((size_t)L->S * QQ));
+    MUSB_CUDA(cudaMemsetAsync(L->state[b].p, 0, (size_t)L->S * QQ * sizeof(double), g.stream));
+  }
+  MUSB_TRY(L->aux.alloc((size_t)L->S * 4));
+  MUSB_CUDA(cudaMemsetAsync(L->aux.p, 0, (size_t)L->S * 4 * sizeof(double), g.stream));
+  MUSB_TRY(L->nbr.alloc((size_t)L->S * (QQ - 1)));
+  MUSB_CUDA(cudaMemsetAsync(L->nbr.p, 0, (size_t)L->S * (QQ - 1) * sizeof(uint32_t), g.stream));
+  MUSB_TRY(launchCubeNeigh(QQ, L->nbr.p, treeLevel, walls ? 1 : 0, L->S, L->nElems, g.stream));
+  ++g.launches;
+  MUSB_CUDA(cudaStreamSynchronize(g.stream));
+  g.levels()[level] = std::move(L);
+  ++g.epoch;
+  return 0;
+}
+
+// mus_init_pdf with zero strain rate: both state buffers <- f_eq(auxField)
+int musb200_state_init_equilibrium(int level) {
+  GET_LEVEL(L, level);
+  if (!L->relaxSet || L->kind == MUSB200_KIND_PASSIVE_SCALAR)
+    return setError(MUSB200_ERR_STATE, "equilibrium initial state: musb200_set_relaxation of a fluid scheme first");
+  MUSB_TRY(launchInitEquilibrium(L->QQ, L->kind == MUSB200_KIND_FLUID_INCOMPRESSIBLE, L->aux.p, L->state[0].p,
+                                 L->state[1].p, L->S, L->nElems, g.stream));
+  ++g.launches;
+  L->auxValid = true;
+  return 0;
+}
+
 int musb200_level_destroy(int level) {
   MUSB_TRY(needReady());
   ++g.epoch;
@@ -820,8 +892,10 @@ int musb200_level_destroy(int level) {
 }
 
 int musb200_neigh_download(int level, int32_t *neigh) {
-  GET_LEVEL(L, level);
+  GET_LEVEL_RO(L, level);
   if (!neigh) return setError(MUSB200_ERR_ARG, "null argument");
+  if ((long long)L->nSize * L->QQ > 2147483647LL)
+    return setError(MUSB200_ERR_ARG, "nSize*QQ exceeds the 32-bit state positions of the host list");
   DevBuf<int32_t> tmp;
   MUSB_TRY(tmp.alloc((size_t)L->nSize * L->QQ));
   MUSB_CUDA(cudaMemsetAsync(tmp.p, 0, tmp.n * sizeof(int32_t), g.stream));
@@ -855,7 +929,7 @@ int musb200_state_upload(int level, int which, const double *aos_state) {
   return uploadAos(L, aos_state, L->state[which - 1].p, L->QQ);
 }
 int musb200_state_download(int level, int which, double *aos_state) {
-  GET_LEVEL(L, level);
+  GET_LEVEL_RO(L, level);
   if (which < 1 || which > 2 || !aos_state) return setError(MUSB200_ERR_ARG, "which must be 1|2");
   return downloadAos(L, L->state[which - 1].p, aos_state, L->QQ);
 }
@@ -879,14 +953,14 @@ static int auxOnDemand(Level *L, int first, int count) {
 }
 
 int musb200_aux_download(int level, double *aos_aux) {
-  GET_LEVEL(L, level);
+  GET_LEVEL_RO(L, level);
   if (!aos_aux) return setError(MUSB200_ERR_ARG, "null argument");
   MUSB_TRY(auxOnDemand(L, 0, L->nSolve));
   if (L->relaxSet && L->kind != MUSB200_KIND_PASSIVE_SCALAR) L->auxValid = true;
   return downloadAos(L, L->aux.p, aos_aux, L->nAux);
 }
 int musb200_aux_probe(int level, int elemPos, double *out) {
-  GET_LEVEL(L, level);
+  GET_LEVEL_RO(L, level);
   if (!out || elemPos < 1 || elemPos > L->nElems) return setError(MUSB200_ERR_ARG, "bad probe element");
   if (elemPos <= L->nSolve) MUSB_TRY(auxOnDemand(L, elemPos - 1, 1));
   MUSB_CUDA(cudaMemcpy2DAsync(out, sizeof(double), L->aux.p + (elemPos - 1), (size_t)L->S * sizeof(double),
@@ -908,7 +982,7 @@ int musb200_set_now_next(int level, int nNow, int nNext) {
   return 0;
 }
 int musb200_get_now_next(int level, int *nNow, int *nNext) {
-  GET_LEVEL(L, level);
+  GET_LEVEL_RO(L, level);
   if (nNow) *nNow = L->nNow + 1;
   if (nNext) *nNext = L->nNext + 1;
   return 0;
@@ -1536,6 +1610,28 @@ int musb200_step(int minLevel, int maxLevel, int nCoarseCycles) {
   return 0;
 }
 
+int musb200_fill_helper_elements(int minLevel, int maxLevel) {
+  MUSB_TRY(needReady());
+  if (maxLevel < minLevel) return setError(MUSB200_ERR_ARG, "bad level range");
+  ++g.epoch;
+  for (int l = minLevel; l <= maxLevel; ++l) {
+    Level *L = findLevel(l);
+    if (!L) return setError(MUSB200_ERR_ARG, "level " + std::to_string(l) + " was not created");
+    if (!L->relaxSet) return setError(MUSB200_ERR_STATE, "musb200_set_relaxation missing");
+    if (L->kind == MUSB200_KIND_PASSIVE_SCALAR) continue;   // its auxField is rebuilt by the first step
+    // mus_initAuxFieldFluidAndExchange: auxField of the fluid elements from their own PDFs
+    SweepArgs a{};
+    a.in = L->state[L->nNext].p; a.nbr = nullptr; a.aux = L->aux.p; a.S = L->S;
+    a.first = 0; a.count = L->nFluid;
+    MUSB_TRY(launchAuxOnly(L->QQ, L->kind, a, g.stream));
+    ++g.launches;
+    L->auxValid = true;
+  }
+  MUSB_TRY(fillFineToCoarse(minLevel, minLevel, maxLevel));
+  MUSB_TRY(fillCoarseToFine(minLevel, minLevel, maxLevel));
+  return 0;
+}
+
 int musb200_set_graphs(int flag) {
   g.useGraphs = flag ? 1 : 0;
   if (!flag) dropGraph();
@@ -1566,7 +1662,7 @@ int musb200_synchronize(void) {
 }
 
 int musb200_reduce(int level, double *total_mass, double *max_vel, int *any_nan) {
-  GET_LEVEL(L, level);
+  GET_LEVEL_RO(L, level);
   double *out = g.red.p + 3 * 592;
   MUSB_TRY(launchReduce(L->QQ, L->state[L->nNext].p, L->S, L->nFluid, g.red.p, out, g.stream));
   g.launches += 2;

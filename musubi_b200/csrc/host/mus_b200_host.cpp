@@ -180,6 +180,9 @@ int main(int argc, char **argv) {
   CHK(musb200_state_upload(L, 2, state.data()));
   CHK(musb200_set_now_next(L, 1, 2));
   CHK(musb200_state_copy_next_to_now(L));
+  // mus_init_flow: auxField of the fluid elements from the state, halos / ghosts filled
+  // (pressure_expol reads the auxField of the previous step in its very first call)
+  CHK(musb200_fill_helper_elements(L, L));
 
   // ---- the time loop -------------------------------------------------------------------------
   double mass0 = 0.0, vmax = 0.0;

@@ -79,6 +79,11 @@ int launchEncodeNeigh(int QQ, const int32_t *neigh, uint32_t *nbr, int nSize, in
 int launchDecodeNeigh(int QQ, const uint32_t *nbr, int32_t *neigh, int nSize, int nElems,
                       long long S, cudaStream_t st);
 
+// treelm's predefined cube generated on the device + equilibrium initial state (cube.cu)
+int launchCubeNeigh(int QQ, uint32_t *nbr, int level, int walls, long long S, int nElems, cudaStream_t st);
+int launchInitEquilibrium(int QQ, int incomp, const double *aux, double *s0, double *s1, long long S, int nElems,
+                          cudaStream_t st);
+
 // boundary kernels
 int launchFillBcBuffer(int QQ, const double *state, long long S, const int32_t *bcElems,
                        const int32_t *needed, int nNeeded, double *bcBuffer, cudaStream_t st);

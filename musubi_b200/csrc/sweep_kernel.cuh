@@ -214,11 +214,17 @@ __global__ void __launch_bounds__(128) auxOnlyKernel(const SweepArgs a) {
   const int e = a.first + i;
   const long long S = a.S;
   double f[QQ];
+  if (a.nbr == nullptr) {
+    // the element's own PDFs (SAVE access): auxFieldFromState of mus_initAuxField
 #pragma unroll
-  for (int q = 0; q < QQ - 1; ++q) {
-    const uint32_t n = a.nbr[q * S + e];
-    const long long row = (n & kBounceBit) ? (long long)invDir<QQ>(q) * S : (long long)q * S;
-    f[q] = a.in[row + (n & kElemMask)];
+    for (int q = 0; q < QQ - 1; ++q) f[q] = a.in[(long long)q * S + e];
+  } else {
+#pragma unroll
+    for (int q = 0; q < QQ - 1; ++q) {
+      const uint32_t n = a.nbr[q * S + e];
+      const long long row = (n & kBounceBit) ? (long long)invDir<QQ>(q) * S : (long long)q * S;
+      f[q] = a.in[row + (n & kElemMask)];
+    }
   }
   f[QQ - 1] = a.in[(long long)(QQ - 1) * S + e];
   double rho, ux, uy, uz;

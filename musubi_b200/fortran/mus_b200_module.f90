@@ -34,7 +34,7 @@ module mus_b200_module
   public :: mus_b200_step, mus_b200_compute
   public :: mus_b200_check
   public :: mus_b200_upload_intp, mus_b200_set_force, mus_b200_p2p_connect
-  public :: mus_b200_pdf_serialize, mus_b200_pdf_unserialize
+  public :: mus_b200_pdf_serialize, mus_b200_pdf_unserialize, mus_b200_fill_helper_elements
   public :: mus_b200_probe, mus_b200_track_every_step, mus_b200_cleanup, mus_b200_timers
   public :: mus_b200_bind_scheme, mus_b200_couple_transport_velocity
   public :: mus_b200_set_bc_values, mus_b200_set_species, mus_b200_set_transport_velocity
@@ -261,6 +261,12 @@ module mus_b200_module
       integer(c_int64_t) :: treeID(*)
       integer(c_int32_t) :: levelPointer(*)
       real(c_double) :: buffer(*)
+      integer(c_int) :: rc
+    end function
+    function musb200_fill_helper_elements(minLevel, maxLevel) &
+      & bind(C, name='musb200_fill_helper_elements') result(rc)
+      import :: c_int
+      integer(c_int), value :: minLevel, maxLevel
       integer(c_int) :: rc
     end function
     function musb200_p2p_export(level, blob) bind(C, name='musb200_p2p_export') result(rc)
@@ -655,6 +661,15 @@ contains
     real(kind=rk), intent(in) :: buffer(:)
     call chk(musb200_pdf_unserialize(int(nElems, c_int), treeID, levelPointer, buffer), 'pdf_unserialize')
   end subroutine mus_b200_pdf_unserialize
+
+  !> after mus_b200_pdf_unserialize filled state(:, nNext) of the fluid elements on the device
+  !! (a restart read straight into the device state): what mus_init_flow does next on the host,
+  !! mus_initAuxField + fillHelperElementsFineToCoarse + fillHelperElementsCoarseToFine
+  !! (mus_flow_module.fpp:206-240), on the device
+  subroutine mus_b200_fill_helper_elements(minLevel, maxLevel)
+    integer, intent(in) :: minLevel, maxLevel
+    call chk(musb200_fill_helper_elements(int(minLevel, c_int), int(maxLevel, c_int)), 'fill_helper_elements')
+  end subroutine mus_b200_fill_helper_elements
 
   !> control routine: one C call per coarse cycle instead of steps 1-9 of do_fast_singleLevel
   !! (registered in mus_init_control for control_routine = 'b200')

@@ -262,10 +262,17 @@ def write_restart(prefix, sim_name, data, time, varsys, mesh="./mesh/", elem_off
     if os.path.dirname(base):
         os.makedirs(os.path.dirname(base), exist_ok=True)
     bin_name = base + "_" + stamp + ENDIAN_SUFFIX
-    mode = "r+b" if os.path.exists(bin_name) else "w+b"
-    with open(bin_name, mode) as fh:
-        fh.seek(int(elem_offset) * nScalars * 8)
-        d.tofile(fh)
+    # every rank of a dump arrives here at once: open WITHOUT truncating (O_CREAT is atomic, two
+    # ranks that both find the file missing still share one file) and write this rank's share
+    # at its offset -- the MPI_File_write_all of tem_restart_writeData in POSIX terms
+    fd = os.open(bin_name, os.O_RDWR | os.O_CREAT, 0o644)
+    try:
+        buf, off = memoryview(d).cast("B"), int(elem_offset) * nScalars * 8
+        while len(buf):
+            k = os.pwrite(fd, buf[:1 << 30], off)
+            buf, off = buf[k:], off + k
+    finally:
+        os.close(fd)
     hdr_name = base + "_header_" + stamp + ".lua"
     if write_header:
         text = header_text(bin_name, time, nGlob, varsys, mesh=mesh, **header_kw)

@@ -62,6 +62,25 @@ def _relaxation_of(identify):
     return rel, variant
 
 
+def default_omega_bulk(identify, level, minLevel):
+    """fluid%omegaBulkLvl(level) when the fluid table has no bulk_viscosity
+    (mus_fluid_module.f90:205-262, 468-485): kind 'fluid' aborts unless the layout is d3q27
+    (omegaBulk 1.54 on the coarsest level); 'fluid_incompressible' takes 1.54 (d3q27) / 1.19 (d3q19).
+    That value defines viscBulk_phy on minLevel; acoustic scaling doubles the lattice bulk
+    viscosity per finer level, omegaBulk = 1 / (9 nu_bulk / (5 - 9 cs2) + 1/2)."""
+    kind, layout = identify.get("kind", "fluid"), identify.get("layout", "d3q19")
+    if layout == "d3q27":
+        ob = 1.54
+    elif kind == "fluid":
+        raise ValueError('"bulk_viscosity" is not provided in fluid table (kind fluid, layout %s): '
+                         "pass omega_bulk" % layout)
+    else:
+        ob = 1.19
+    cs2 = 1.0 / 3.0
+    visc_bulk = ((5.0 - 9.0 * cs2) / 9.0) * (1.0 / ob - 0.5) * 2.0 ** (level - minLevel)
+    return 1.0 / (9.0 * visc_bulk / (5.0 - 9.0 * cs2) + 0.5)
+
+
 def select_kernel(identify):
     """mus_init_advRel_fluid / _fluid_incompressible / _lbm_ps: the (kind, relaxation, variant,
     layout) dispatch."""
@@ -111,17 +130,24 @@ class Scheme:
         for lvl, ld in levelDescs.items():
             if ld.QQ != self.QQ:
                 raise ValueError("levelDesc built for another stencil")
-            check(lib.musb200_level_create(lvl, self.QQ, self.QQ, self.nAux, ld.nSize, ld.nFluid,
-                                           ld.nGhostFromCoarser, ld.nGhostFromFiner, ld.nHalo,
-                                           ptr(ld.neigh, P_I32), ptr(ld.property, P_I64),
-                                           ptr(ld.total, P_I64)))
+            if getattr(ld, "device_generated", False):
+                check(lib.musb200_level_create_cube(lvl, ld.level, self.QQ, 1 if ld.kind == "walls" else 0))
+            else:
+                check(lib.musb200_level_create(lvl, self.QQ, self.QQ, self.nAux, ld.nSize, ld.nFluid,
+                                               ld.nGhostFromCoarser, ld.nGhostFromFiner, ld.nHalo,
+                                               ptr(ld.neigh, P_I32), ptr(ld.property, P_I64),
+                                               ptr(ld.total, P_I64)))
             if self.passive_scalar:
                 check(lib.musb200_set_species(lvl, self.relax, self.ps_variant,
                                               float(species["diff_coeff"]),
                                               float(species.get("lambda", 0.25))))
             else:
                 om = omega[lvl] if isinstance(omega, dict) else omega
-                ob = omega_bulk if omega_bulk is not None else (om if np.isscalar(om) else 1.0)
+                ob = omega_bulk[lvl] if isinstance(omega_bulk, dict) else omega_bulk
+                if ob is None:
+                    # bgk and trt never read it; mrt gets the reference's default (or its abort)
+                    ob = (default_omega_bulk(identify, lvl, self.minLevel)
+                          if _relaxation_of(identify)[0] == "mrt" else 1.0)
                 self.set_relaxation(lvl, om, ob)
             if len(ld.bc_elemBuffer):
                 check(lib.musb200_bc_elembuffer(lvl, len(ld.bc_elemBuffer), ptr(ld.bc_elemBuffer, P_I32)))
@@ -220,6 +246,17 @@ class Scheme:
         check(lib.musb200_state_upload(level, nNext, b.ctypes.data))
         check(lib.musb200_set_now_next(level, nNow, nNext))
 
+    def init_equilibrium(self, level, rho, vel):
+        """mus_init_pdf with zero strain rate, evaluated on the device: auxField <- (rho, vel),
+        both state buffers <- f_eq(rho, vel)"""
+        self._bind()
+        ld = self.levelDesc[level]
+        aux = np.zeros((ld.nSize, 4))
+        aux[:ld.nElems, 0] = rho
+        aux[:ld.nElems, 1:] = vel
+        check(lib.musb200_aux_upload(level, aux.ctypes.data))
+        check(lib.musb200_state_init_equilibrium(level))
+
     def now_next(self, level):
         self._bind()
         a, b = ctypes.c_int(), ctypes.c_int()
@@ -310,7 +347,17 @@ class Scheme:
             raise ValueError("restart file %s: %d elements x %d scalars, this scheme holds %d x %d"
                              % (header_path, data.shape[0], rf.nScalars * rf.nDofs, tid.size, self.QQ))
         self.pdf_unserialize(tid, lp, data.ravel())
+        # the file holds fluid elements only: halos, ghosts and auxField are rebuilt as
+        # mus_init_flow does after mus_readRestart (mus_flow_module.fpp:206-240)
+        self.fill_helper_elements()
         return rf.time
+
+    def fill_helper_elements(self):
+        """mus_initAuxField + fillHelperElementsFineToCoarse / CoarseToFine on the device: auxField
+        of the fluid elements from state(:, nNext), halo exchange, ghost interpolation
+        (collective over the ranks)"""
+        self._bind()
+        check(lib.musb200_fill_helper_elements(self.minLevel, self.maxLevel))
 
     # -- peer-memory halo exchange ------------------------------------------------
     def p2p_connect(self, dist, level=None):

@@ -94,3 +94,32 @@ class LevelDesc:
         if h:
             mesh.musb200_mesh_destroy(h)
             self._handle = None
+
+
+class DeviceCube:
+    """treelm's predefined cube (all 8^level elements in Morton order) on ONE rank whose
+    connectivity libmusb200 generates on the device (musb200_level_create_cube): periodic, or
+    closed by walls.  No host index lists exist, so the 32-bit limit nSize*QQ < 2^31 of pdf%neigh
+    does not apply (BASELINE config 3, 512^3 d3q27, on one GPU)."""
+    device_generated = True
+
+    def __init__(self, level, QQ, kind="periodic"):
+        if kind not in ("periodic", "walls"):
+            raise ValueError("DeviceCube: kind must be 'periodic' or 'walls'")
+        n = 8 ** level
+        self.level, self.QQ, self.kind, self.rank, self.nranks = level, QQ, kind, 0, 1
+        self.nFluid = self.nElems = self.nSize = self.nSolve = n
+        self.nGhostFromCoarser = self.nGhostFromFiner = self.nHalo = 0
+        self.bc, self.send, self.recv = [], [], []
+        self.bc_elemBuffer = np.zeros(0, dtype=np.int32)
+
+    def barycenters(self, origin=(0.0, 0.0, 0.0), length=1.0, chunk=1 << 24):
+        """tem_BaryOfId: origin + (coord + 0.5) * dx, dx = length / 2^level"""
+        from .treelm_multilevel import coords
+        out = np.empty((self.nElems, 3))
+        dx = float(length) / (1 << self.level)
+        for s in range(0, self.nElems, chunk):
+            x, y, z = coords(np.arange(s, min(self.nElems, s + chunk), dtype=np.int64))
+            for k, c in enumerate((x, y, z)):
+                out[s:s + chunk, k] = origin[k] + (c + 0.5) * dx
+        return out

@@ -130,10 +130,17 @@ def dump_weights(filename, weights, elem_offset=0, nElems_global=None):
     n = w.size + elem_offset if nElems_global is None else int(nElems_global)
     if elem_offset < 0 or elem_offset + w.size > n:
         raise ValueError("weights: elements %d..%d outside the mesh of %d" % (elem_offset, elem_offset + w.size, n))
-    with open(filename, "r+b" if os.path.exists(filename) else "w+b") as fh:
-        fh.truncate(n * 8)
-        fh.seek(elem_offset * 8)
-        w.tofile(fh)
+    # all ranks write into one file at once: never truncate what another rank has written
+    fd = os.open(filename, os.O_RDWR | os.O_CREAT, 0o644)
+    try:
+        if os.fstat(fd).st_size != n * 8:
+            os.ftruncate(fd, n * 8)           # sizes the file; existing bytes below n * 8 are kept
+        buf, off = memoryview(w).cast("B"), int(elem_offset) * 8
+        while len(buf):
+            k = os.pwrite(fd, buf[:1 << 30], off)
+            buf, off = buf[k:], off + k
+    finally:
+        os.close(fd)
 
 
 def load_weights(filename, elem_offset=0, nElems=None):

@@ -938,6 +938,28 @@ class MultiLevelScheme:
             self._from_finer(l)
             self._from_coarser(l)
 
+    def fill_helper_elements(self):
+        """mus_init_flow once state(:, nNext) of the fluid elements is filled (initial condition or
+        mus_readRestart; mus_flow_module.fpp:206-240): mus_initAuxField (:1677-1737) -- auxField of
+        the FLUID elements from their own PDFs, auxField of the ghostFromFiner elements by
+        averaging, finest level first --, fillHelperElementsFineToCoarse (:1517-1588) and
+        fillHelperElementsCoarseToFine (:1601-1673).  (The auxField interpolated for the
+        ghostFromCoarser elements, mus_intpAuxFieldFinerAndExchange, is recomputed by the first
+        level step before anything reads it and is not restated.)"""
+        L = lib()
+        for s in self.s.values():
+            ident = np.zeros(s.QQ * s.ld.nSize, dtype=np.int32)
+            e = np.arange(s.ld.nSize, dtype=np.int64)
+            for d in range(s.QQ):
+                ident[d * s.ld.nSize:(d + 1) * s.ld.nSize] = e * s.QQ + d + 1
+            (L.ora_calc_aux_incomp if s.incomp else L.ora_calc_aux)(
+                s.QQ, _d(s.aux), _d(s.state[s.nNext]), _i(ident), s.ld.nSize, s.ld.nFluid)
+        for l in range(self.maxLevel - 1, self.minLevel - 1, -1):
+            self._aux_from_finer(l)
+            self._from_finer(l)
+        for l in range(self.minLevel, self.maxLevel):
+            self._from_coarser(l)
+
     def run(self, ncycles):
         for _ in range(ncycles):
             self.do_computation()

@@ -113,3 +113,17 @@ def test_send_and_recv_lists_pair_up(oracle):
     # reduced link set of a z-slab partition: 9 of 27 links per face halo
     two = mb.LevelDesc(4, 27, "periodic", 0, 2)
     assert len(two.recv[0]["pos"]) == 2 * 16 * 16 * 9
+
+
+def test_default_omega_bulk_follows_the_reference():
+    """fluid table without bulk_viscosity (mus_fluid_module.f90:205-262): d3q27 -> 1.54,
+    incompressible d3q19 -> 1.19, compressible d3q19 aborts; finer levels scale acoustically"""
+    from musubi_b200.scheme import default_omega_bulk
+    f27 = {"kind": "fluid", "relaxation": "mrt", "layout": "d3q27"}
+    i19 = {"kind": "fluid_incompressible", "relaxation": "mrt", "layout": "d3q19"}
+    assert abs(default_omega_bulk(f27, 5, 5) - 1.54) < 1e-15
+    assert abs(default_omega_bulk(i19, 7, 7) - 1.19) < 1e-15
+    nu = (2.0 / 9.0) * (1.0 / 1.54 - 0.5)
+    assert abs(default_omega_bulk(f27, 6, 5) - 1.0 / (9.0 * (2.0 * nu) / 2.0 + 0.5)) < 1e-15
+    with pytest.raises(ValueError, match="bulk_viscosity"):
+        default_omega_bulk({"kind": "fluid", "relaxation": "mrt", "layout": "d3q19"}, 4, 4)

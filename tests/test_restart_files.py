@@ -229,3 +229,33 @@ def test_device_restart_file_round_trip_continues_bit_identically(mbgpu, oracle,
     ms.run(3)
     assert sch.pdf_serialize(tid, lp).tobytes() == mo.pdf_serialize(ms.s, tid, lp).tobytes()
     sch.destroy()
+
+
+def _write_share(args):
+    prefix, rank, nranks, nGlob, nScal = args
+    from musubi_b200 import restart_io as rio
+    lo, hi = rank * nGlob // nranks, (rank + 1) * nGlob // nranks
+    data = (np.arange(lo, hi, dtype=np.float64)[:, None] * 100.0 + np.arange(nScal)[None, :]).ravel()
+    vs = rio.fluid_varsys("fluid", nScal)
+    rio.write_restart(prefix, "race", data, dict(sim=1.5, iter=3), vs, elem_offset=lo, nElems_global=nGlob,
+                      write_header=(rank == 0))
+    from musubi_b200 import treelm_io as tio
+    tio.dump_weights(prefix + "weights.lsb", np.arange(lo, hi, dtype=np.float64), elem_offset=lo, nElems_global=nGlob)
+    return hi - lo
+
+
+def test_all_ranks_write_one_dump_concurrently(tmp_path):
+    """every rank of a multi-rank dump opens the file at the same time: no rank may truncate
+    what another has already written (the file is opened without O_TRUNC and written with
+    pwrite at the rank's offset); repeated many times to give the race a chance"""
+    import multiprocessing as mp
+    nranks, nGlob, nScal = 8, 40000, 19
+    ctx = mp.get_context("fork")
+    for trial in range(6):
+        prefix = str(tmp_path / ("t%d_" % trial))
+        with ctx.Pool(nranks) as pool:
+            pool.map(_write_share, [(prefix, r, nranks, nGlob, nScal) for r in range(nranks)])
+        got = np.fromfile(prefix + "race_" + rio.time_stamp(1.5) + rio.ENDIAN_SUFFIX).reshape(nGlob, nScal)
+        exp = np.arange(nGlob, dtype=np.float64)[:, None] * 100.0 + np.arange(nScal)[None, :]
+        assert np.array_equal(got, exp)
+        assert np.array_equal(np.fromfile(prefix + "weights.lsb"), np.arange(nGlob, dtype=np.float64))
