@@ -234,7 +234,7 @@ int musb200_comm_register(int level, int buf_kind, int dir, int nProcs, const in
  * Ranks must keep pdf%nNow/nNext in lockstep (they do: one swap per level step) and must
  * synchronise + barrier before musb200_level_destroy.  The NCCL path stays available
  * (musb200_p2p_enable(level, 0)) and is the one used across nodes.                       */
-#define MUSB200_P2P_BLOB 256
+#define MUSB200_P2P_BLOB 512
 int musb200_p2p_export(int level, void *blob);
 int musb200_p2p_connect(int level, int nProcs, const int32_t *proc, const void *blobs,
                         const int32_t *nVals, const int32_t *remotePos);
@@ -287,6 +287,18 @@ int musb200_fill_helper_elements(int minLevel, int maxLevel);
  * results; the split sweep costs more than the exchange it hides at 256^3 elements per GPU
  * (profiles/r01_multi_gpu.md), so it is opt-in. */
 int musb200_set_overlap(int flag);
+/* Peer-memory halo exchange, single level: 1 (default) the wait for the links of step n moves
+ * into the sweep of step n+1, where only the CTAs that pull from a halo row wait (a bitmap built
+ * from the neighbour list) -- transfer and rank skew hide behind the sweep without splitting it;
+ * 0: MPI_Waitall right after the push (exchange strictly after compute, as
+ * comm_isend_irecv_real is called in do_fast_singleLevel).  Identical results. */
+int musb200_set_sweep_wait(int flag);
+/* Every wait of the peer-memory exchange gives up after `seconds` (default 30; 0 = never): the
+ * stream drains, and the next synchronising call (musb200_synchronize, musb200_reduce, ...) returns
+ * MUSB200_ERR_NCCL naming the rank that did not deliver -- the shim then calls tem_abort as the
+ * reference does when a rank fails (tem/source/tem_aux_module.f90:457-478).  The same calls poll
+ * ncclCommGetAsyncError on the NCCL path. */
+int musb200_set_exchange_timeout(double seconds);
 /* 1 (default): a single-rank musb200_step call of 8 or more coarse cycles without per-stage
  * timers replays a CUDA graph of two coarse cycles (captured on first use, re-captured after
  * any call that changes a level); 0: every kernel is launched directly.  Same kernels, same

@@ -70,6 +70,8 @@ SIGNATURES = {
     "musb200_timers_reset": [],
     "musb200_launch_count": [P_LL],
     "musb200_set_overlap": [c_int],
+    "musb200_set_sweep_wait": [c_int],
+    "musb200_set_exchange_timeout": [c_double],
     "musb200_set_graphs": [c_int],
     "musb200_set_fused_bc": [c_int],
     "musb200_p2p_export": [c_int, c_void_p],

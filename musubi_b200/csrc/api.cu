@@ -52,6 +52,8 @@ NcclApi *ncclApi() {
   SYM(GetUniqueId, "ncclGetUniqueId")
   SYM(CommInitRank, "ncclCommInitRank")
   SYM(CommDestroy, "ncclCommDestroy")
+  SYM(CommGetAsyncError, "ncclCommGetAsyncError")
+  SYM(CommAbort, "ncclCommAbort")
   SYM(Send, "ncclSend")
   SYM(Recv, "ncclRecv")
   SYM(AllReduce, "ncclAllReduce")
@@ -137,20 +139,28 @@ struct CommBuf {
   std::vector<int> auxNVals, auxOffset;
   int auxTotal = 0;
   DevBuf<int32_t> auxPos;
+  std::vector<int32_t> auxPosHost;   // the same list on the host (peer-memory set-up)
 };
 
 // peer-memory halo exchange of one level (p2p.cu)
 struct PeerLink {
   bool on = false;
-  unsigned long long count = 0;          // exchanges done so far (same on every rank)
+  bool pendingWait = false;              // a push has been issued whose arrival nobody has waited for yet
+  bool sweepWait = false;                // the next sweep may do that wait (symmetric peers, CTA bitmap built)
   std::vector<int> sendRank, recvRank;
   std::vector<void *> opened;            // IPC-opened pointers, closed at destroy
   double *remoteState[kMaxPeers][2] = {};
+  double *remoteAux[kMaxPeers] = {};
   long long remoteS[kMaxPeers] = {};
   unsigned long long *remoteArrived[kMaxPeers] = {};
   DevBuf<int32_t> srcPos, dstPos;        // send entries re-ordered for coalesced remote stores
   DevBuf<uint8_t> peerOf;
+  DevBuf<int32_t> auxSrcPos, auxDstPos;  // the auxField entries of the same elements
+  DevBuf<uint8_t> auxPeerOf;
+  int nAux = 0;
   DevBuf<unsigned long long> arrived;    // [nranks], written by the senders
+  DevBuf<unsigned long long> exch;       // this rank's exchange number, bumped by the push kernel
+  DevBuf<uint32_t> ctaMask;              // sweep CTAs that pull from a halo row
   DevBuf<unsigned int> ticket;
   // fused push (sweep_push.cu): the send entries grouped by the element that owns them
   DevBuf<uint32_t> pushMask, pushPrefix;
@@ -227,6 +237,9 @@ struct Context {
   int fusedPush = 0;
   int noFusedBc = 0; // musb200_set_fused_bc(0): always take the two-phase bcBuffer path
   int overlap = 0;   // measured slower than exchange-after-compute at 256^3 per GPU (profiles/)
+  int sweepWait = 1; // peer-memory exchange: the wait for the halo links moves into the next sweep
+  unsigned long long timeoutNs = 30000000000ull;   // every wait of the exchange gives up after this
+  DevBuf<int> errFlag;                             // {code, peer, exchange lo, exchange hi}, set by a wait
   NcclApi *nccl = nullptr;
   ncclComm_t comm = nullptr;
   // one element list per (scheme slot, level); slot 0 is the default scheme, further slots hold
@@ -317,9 +330,13 @@ static int applyPendingBc(Level &L) {
   return 0;
 }
 
+static int ensureArrived(Level &L, cudaStream_t st = nullptr);
+
 static int setBoundary(Level &L) {
   if (L.bcElems.n == 0) return 0;
   MUSB_TRY(applyPendingBc(L));
+  for (auto &b : L.bcs)   // boundaries that read neighbour elements may read halo rows
+    if (isPressureBc(b->kind) && b->nLinks > 0) { MUSB_TRY(ensureArrived(L, nullptr)); break; }
   Timed t(T_BC);
   double *st = L.state[L.nNext].p;
   bool any = false;
@@ -400,33 +417,74 @@ static int setBoundary(Level &L) {
   return 0;
 }
 
+// the receiving half of the peer-memory exchange (p2p.cu)
+static HaloWait haloWait(Level &L, bool forSweep) {
+  PeerLink &P = L.p2p;
+  HaloWait w{};
+  w.ctaMask = forSweep ? P.ctaMask.p : nullptr;
+  w.arrived = P.arrived.p;
+  w.exch = P.exch.p;
+  w.nRecvPeers = (int)P.recvRank.size();
+  for (int k = 0; k < w.nRecvPeers; ++k) w.recvRank[k] = P.recvRank[k];
+  w.timeoutNs = g.timeoutNs;
+  w.errFlag = g.errFlag.p;
+  return w;
+}
+// MPI_Waitall of the last push of this level, unless a sweep has done (or will do) it
+static int ensureArrived(Level &L, cudaStream_t st) {
+  if (!L.p2p.pendingWait) return 0;
+  Timed t(T_COMM, st ? st : g.stream);
+  MUSB_TRY(launchWaitHalo(haloWait(L, false), st ? st : g.stream));
+  ++g.launches;
+  L.p2p.pendingWait = false;
+  return 0;
+}
+// the sending half: one kernel stores every link (and, withAux, every auxField entry of the
+// communicated elements) into the receivers' halo rows and publishes the exchange number
+static int pushHalo(Level &L, bool withAux, cudaStream_t st, bool pushed) {
+  PeerLink &P = L.p2p;
+  CommBuf &s = L.send[MUSB200_BUF_HALO];
+  P2PArgs a{};
+  a.state = L.state[L.nNext].p; a.aux = L.aux.p; a.S = L.S; a.QQ = L.QQ;
+  a.n = s.total; a.nAux = withAux ? P.nAux : 0;
+  a.srcPos = P.srcPos.p; a.dstPos = P.dstPos.p; a.peerOf = P.peerOf.p;
+  a.auxSrcPos = P.auxSrcPos.p; a.auxDstPos = P.auxDstPos.p; a.auxPeerOf = P.auxPeerOf.p;
+  a.nSendPeers = (int)P.sendRank.size(); a.myRank = g.rank;
+  for (int k = 0; k < a.nSendPeers; ++k) {
+    a.remoteState[k] = P.remoteState[k][L.nNext];   // ranks swap now/next in lockstep
+    a.remoteAux[k] = P.remoteAux[k];
+    a.remoteS[k] = P.remoteS[k];
+    a.remoteArrived[k] = P.remoteArrived[k];
+  }
+  a.exch = P.exch.p; a.ticket = P.ticket.p;
+  a.handshake = a.nAux > 0 ? 1 : 0;
+  a.nranks = g.nranks; a.ready = P.arrived.p + g.nranks;
+  for (int k = 0; k < a.nSendPeers; ++k) a.sendRank[k] = P.sendRank[k];
+  a.timeoutNs = g.timeoutNs; a.errFlag = g.errFlag.p;
+  // pushed: the sweep stored the links itself (sweep_push.cu), only the publishing is left
+  if (pushed) MUSB_TRY(launchSignalHalo(a, st));
+  else MUSB_TRY(launchPushHalo(a, st));
+  ++g.launches;
+  P.pendingWait = true;
+  return 0;
+}
+
 static int exchange(Level &L, int kind, double *state, int nComp, cudaStream_t st = nullptr,
-                    bool pushed = false) {
+                    bool pushed = false, bool deferWait = false) {
   if (g.nranks == 1) return 0;
   if (!st) st = g.stream;
   CommBuf &s = L.send[kind], &r = L.recv[kind];
   if (s.total == 0 && r.total == 0) return 0;
-  Timed t(T_COMM, st);
   if (kind == MUSB200_BUF_HALO && L.p2p.on && state == L.state[L.nNext].p) {
-    // peer-memory path: one kernel stores every link into the receivers' halo rows
-    PeerLink &P = L.p2p;
-    P2PArgs a{};
-    a.state = state; a.S = L.S; a.QQ = L.QQ; a.n = s.total;
-    a.srcPos = P.srcPos.p; a.dstPos = P.dstPos.p; a.peerOf = P.peerOf.p;
-    a.nSendPeers = (int)P.sendRank.size(); a.nRecvPeers = (int)P.recvRank.size(); a.myRank = g.rank;
-    for (int k = 0; k < a.nSendPeers; ++k) {
-      a.remoteState[k] = P.remoteState[k][L.nNext];   // ranks swap now/next in lockstep
-      a.remoteS[k] = P.remoteS[k];
-      a.remoteArrived[k] = P.remoteArrived[k];
+    {
+      Timed t(T_COMM, st);
+      MUSB_TRY(pushHalo(L, false, st, pushed));
     }
-    for (int k = 0; k < a.nRecvPeers; ++k) a.recvRank[k] = P.recvRank[k];
-    a.arrived = P.arrived.p; a.count = ++P.count; a.ticket = P.ticket.p;
-    // pushed: the sweep stored the links itself (sweep_push.cu), only the handshake is left
-    if (pushed) MUSB_TRY(launchSignalHalo(a, st));
-    else MUSB_TRY(launchPushHalo(a, st));
-    ++g.launches;
+    // deferWait: the next sweep's halo CTAs wait (or ensureArrived at the end of the call)
+    if (!deferWait) MUSB_TRY(ensureArrived(L, st));
     return 0;
   }
+  Timed t(T_COMM, st);
   // the auxField travels through its own position lists (four entries per element)
   const bool isAux = (state == L.aux.p);
   const int32_t *sPos = isAux ? s.auxPos.p : s.pos.p, *rPos = isAux ? r.auxPos.p : r.pos.p;
@@ -458,6 +516,15 @@ static int exchangeStateAndAux(Level &L, int kind = MUSB200_BUF_HALO) {
   CommBuf &s = L.send[kind], &r = L.recv[kind];
   if (s.total == 0 && r.total == 0) return 0;
   cudaStream_t st = g.stream;
+  if (kind == MUSB200_BUF_HALO && L.p2p.on) {
+    // peer memory: state links and auxField entries in ONE kernel; the interpolation that
+    // follows reads halo rows, so the wait comes right behind it
+    {
+      Timed t(T_COMM, st);
+      MUSB_TRY(pushHalo(L, true, st, false));
+    }
+    return ensureArrived(L, st);
+  }
   Timed t(T_COMM, st);
   double *state = L.state[L.nNext].p;
   if (s.total) {
@@ -491,6 +558,7 @@ static int sweep(Level &L, bool writeAux, int part = SWEEP_ALL, bool push = fals
   Timed t(T_COMPUTE);
   if (L.kind == MUSB200_KIND_PASSIVE_SCALAR) {
     if (part != SWEEP_ALL) return setError(MUSB200_ERR_UNSUPPORTED, "passive scalar: no split sweep");
+    MUSB_TRY(ensureArrived(L));
     PsArgs p{};
     p.in = L.state[L.nNow].p; p.out = L.state[L.nNext].p; p.nbr = L.nbr.p; p.aux = L.aux.p;
     p.S = L.S; p.count = L.nSolve; p.write_aux = writeAux ? 1 : 0;
@@ -532,6 +600,13 @@ static int sweep(Level &L, bool writeAux, int part = SWEEP_ALL, bool push = fals
       a.push.remoteState[k] = P.remoteState[k][L.nNext];   // ranks swap now/next in lockstep
       a.push.remoteS[k] = P.remoteS[k];
     }
+  }
+  // the previous step's halo links may still be in flight: the CTAs that need them wait
+  if (part == SWEEP_ALL && L.p2p.pendingWait && L.p2p.sweepWait && g.sweepWait) {
+    a.wait = haloWait(L, true);
+    L.p2p.pendingWait = false;
+  } else {
+    MUSB_TRY(ensureArrived(L));
   }
   if (part == SWEEP_SENDHALO) { a.list = L.sendElems.p; a.count = L.nSendElems; }
   if (part == SWEEP_INTERIOR) a.skip = L.sendMask.p;
@@ -594,7 +669,7 @@ static int levelStep(int iLevel, int minLevel, int maxLevel, bool lastCycle) {
     MUSB_TRY(sweep(L, writeAux, SWEEP_SENDHALO));
     MUSB_CUDA(cudaEventRecord(g.evBoundary, g.stream));
     MUSB_CUDA(cudaStreamWaitEvent(g.commStream, g.evBoundary, 0));
-    MUSB_TRY(exchange(L, MUSB200_BUF_HALO, L.state[L.nNext].p, L.QQ, g.commStream));
+    MUSB_TRY(exchange(L, MUSB200_BUF_HALO, L.state[L.nNext].p, L.QQ, g.commStream));   // push + wait
     MUSB_CUDA(cudaEventRecord(g.evComm, g.commStream));
     MUSB_TRY(sweep(L, writeAux, SWEEP_INTERIOR));
     MUSB_CUDA(cudaStreamWaitEvent(g.stream, g.evComm, 0));
@@ -610,7 +685,7 @@ static int levelStep(int iLevel, int minLevel, int maxLevel, bool lastCycle) {
   // from-finer interpolation kernel below: same sources, and on one rank nothing reads those
   // entries before the from-coarser interpolation, which runs after it
   if (multi && writeAux) MUSB_TRY(exchangeStateAndAux(L));   // state (tag level) + aux (tag level+100)
-  else MUSB_TRY(exchange(L, MUSB200_BUF_HALO, L.state[L.nNext].p, L.QQ, nullptr, pushed));
+  else MUSB_TRY(exchange(L, MUSB200_BUF_HALO, L.state[L.nNext].p, L.QQ, nullptr, pushed, /*deferWait=*/!multi));
   if (iLevel > minLevel) MUSB_TRY(exchange(L, MUSB200_BUF_FROMCOARSER, L.state[L.nNext].p, L.QQ));
   if (iLevel < maxLevel) {
     Level *F = findLevel(iLevel + 1);
@@ -622,6 +697,29 @@ static int levelStep(int iLevel, int minLevel, int maxLevel, bool lastCycle) {
     // do_intpCoarserAndExchange: ghostFromCoarser of level+1 <- me, orders 0..order
     for (auto &set : F->fromCoarser) MUSB_TRY(applyIntp(L, *F, set, false));
     MUSB_TRY(exchange(*F, MUSB200_BUF_FROMCOARSER, F->state[F->nNext].p, F->QQ));
+  }
+  return 0;
+}
+
+// Failure detection at the points where the host synchronises anyway (the reference aborts all
+// ranks through tem_abort, tem/source/tem_aux_module.f90:457-478): a wait of the peer-memory
+// exchange that gave up (p2p.cu) and NCCL's asynchronous communicator errors.  The stream has
+// been synchronised by the caller.
+static int checkAsyncErrors() {
+  if (g.nranks == 1) return 0;
+  int h[4] = {0, 0, 0, 0};
+  MUSB_CUDA(cudaMemcpy(h, g.errFlag.p, sizeof(h), cudaMemcpyDeviceToHost));
+  if (h[0] != 0) {
+    const unsigned long long n = ((unsigned long long)(unsigned int)h[3] << 32) | (unsigned int)h[2];
+    return setError(MUSB200_ERR_NCCL, std::string("halo exchange timed out after ") +
+                                          std::to_string(g.timeoutNs / 1000000ull) + " ms: rank " +
+                                          std::to_string(h[1]) + (h[0] == 1 ? " did not deliver" : " was not ready for") +
+                                          " exchange " + std::to_string(n) + " (rank " + std::to_string(g.rank) + ")");
+  }
+  if (g.comm) {
+    ncclResult_t ar = ncclSuccess;
+    if (g.nccl->CommGetAsyncError(g.comm, &ar) == ncclSuccess && ar != ncclSuccess && ar != ncclInProgress)
+      return setError(MUSB200_ERR_NCCL, std::string("NCCL communicator error: ") + g.nccl->GetErrorString(ar));
   }
   return 0;
 }
@@ -720,6 +818,8 @@ int musb200_init(int rank, int nranks, int local_device, const void *nccl_unique
   MUSB_CUDA(cudaEventCreate(&g.mark[1]));
   MUSB_TRY(g.red.alloc(3 * 592 + 8));
   MUSB_TRY(g.flag.alloc(1));
+  MUSB_TRY(g.errFlag.alloc(4));
+  MUSB_CUDA(cudaMemsetAsync(g.errFlag.p, 0, 4 * sizeof(int), g.stream));
   if (nranks > 1) {
     if (!nccl_unique_id) return setError(MUSB200_ERR_ARG, "nranks > 1 needs the NCCL unique id");
     g.nccl = ncclApi();
@@ -738,7 +838,7 @@ int musb200_finalize(void) {
   dropGraph();
   for (auto &m : g.levelsOf) m.clear();
   g.slot = 0;
-  g.stage.release(); g.red.release(); g.flag.release();
+  g.stage.release(); g.red.release(); g.flag.release(); g.errFlag.release();
   for (auto &s : g.spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
   g.spans.clear();
   for (auto e : g.pool) cudaEventDestroy(e);
@@ -1332,7 +1432,7 @@ int musb200_comm_register(int level, int buf_kind, int dir, int nProcs, const in
   }
   MUSB_TRY(c.pos.upload(pos, (size_t)c.total, g.stream));
   MUSB_TRY(c.buf.alloc((size_t)std::max(1, c.total)));
-  c.auxNVals.clear(); c.auxOffset.clear(); c.auxTotal = 0;
+  c.auxNVals.clear(); c.auxOffset.clear(); c.auxTotal = 0; c.auxPosHost.clear();
   // halo elements and ghostFromFiner elements travel with their auxField entries
   // (auxField%sendBuffer / sendBufferFromFiner, mus_auxField_module.f90:377-444)
   if (buf_kind == MUSB200_BUF_HALO || buf_kind == MUSB200_BUF_FROMFINER) {
@@ -1352,6 +1452,7 @@ int musb200_comm_register(int level, int buf_kind, int dir, int nProcs, const in
       c.auxNVals.push_back((int)apos.size() - before);
     }
     c.auxTotal = (int)apos.size();
+    c.auxPosHost = apos;
     MUSB_TRY(c.auxPos.upload(apos.data(), apos.size(), g.stream));
     MUSB_TRY(c.buf.alloc((size_t)std::max(1, c.total + c.auxTotal)));   // state links | auxField entries
     MUSB_CUDA(cudaStreamSynchronize(g.stream));
@@ -1378,10 +1479,11 @@ int musb200_comm_register(int level, int buf_kind, int dir, int nProcs, const in
 namespace {
 struct P2PBlob {                 // MUSB200_P2P_BLOB bytes, plain data
   cudaIpcMemHandle_t state[2];
-  cudaIpcMemHandle_t arrived;
+  cudaIpcMemHandle_t arrived;    // arrived[nranks] | ready[nranks]
+  cudaIpcMemHandle_t aux;
   long long S;
   int rank, QQ, nSize, device;
-  char pad[MUSB200_P2P_BLOB - 3 * (int)sizeof(cudaIpcMemHandle_t) - (int)sizeof(long long) - 4 * (int)sizeof(int)];
+  char pad[MUSB200_P2P_BLOB - 4 * (int)sizeof(cudaIpcMemHandle_t) - (int)sizeof(long long) - 4 * (int)sizeof(int)];
 };
 static_assert(sizeof(P2PBlob) == MUSB200_P2P_BLOB, "blob layout");
 }  // namespace
@@ -1391,10 +1493,12 @@ int musb200_p2p_export(int level, void *blob) {
   if (!blob) return setError(MUSB200_ERR_ARG, "null argument");
   PeerLink &P = L->p2p;
   if (P.arrived.n == 0) {
-    MUSB_TRY(P.arrived.alloc((size_t)std::max(g.nranks, 1)));
+    MUSB_TRY(P.arrived.alloc((size_t)2 * std::max(g.nranks, 1)));
     MUSB_TRY(P.ticket.alloc(1));
+    MUSB_TRY(P.exch.alloc(1));
     MUSB_CUDA(cudaMemsetAsync(P.arrived.p, 0, P.arrived.n * sizeof(unsigned long long), g.stream));
     MUSB_CUDA(cudaMemsetAsync(P.ticket.p, 0, sizeof(unsigned int), g.stream));
+    MUSB_CUDA(cudaMemsetAsync(P.exch.p, 0, sizeof(unsigned long long), g.stream));
     MUSB_CUDA(cudaStreamSynchronize(g.stream));
   }
   P2PBlob b;
@@ -1402,6 +1506,7 @@ int musb200_p2p_export(int level, void *blob) {
   MUSB_CUDA(cudaIpcGetMemHandle(&b.state[0], L->state[0].p));
   MUSB_CUDA(cudaIpcGetMemHandle(&b.state[1], L->state[1].p));
   MUSB_CUDA(cudaIpcGetMemHandle(&b.arrived, P.arrived.p));
+  MUSB_CUDA(cudaIpcGetMemHandle(&b.aux, L->aux.p));
   b.S = L->S; b.rank = g.rank; b.QQ = L->QQ; b.nSize = L->nSize; b.device = g.device;
   std::memcpy(blob, &b, sizeof(b));
   return 0;
@@ -1417,6 +1522,13 @@ int musb200_p2p_connect(int level, int nProcs, const int32_t *proc, const void *
     return setError(MUSB200_ERR_ARG, "peer list does not match the halo send buffer");
   if (nProcs > 0 && (!proc || !blobs || !nVals || !remotePos)) return setError(MUSB200_ERR_ARG, "null argument");
   std::vector<uint8_t> peerOf((size_t)s.total);
+  const int QQ = L->QQ;
+  // auxField entries of the communicated elements on the receiving side: the elements of the
+  // receiver's list in order of first appearance, exactly how both sides build auxField%recvBuffer /
+  // sendBuffer from their own lists (musb200_comm_register), so entry j here pairs with entry j of
+  // this rank's s.auxPosHost
+  std::vector<int32_t> auxRemote;
+  std::vector<uint8_t> auxPeer;
   for (int k = 0; k < nProcs; ++k) {
     if (proc[k] != s.proc[k] || nVals[k] != s.nVals[k])
       return setError(MUSB200_ERR_ARG, "peer order / message length differs from musb200_comm_register");
@@ -1427,23 +1539,34 @@ int musb200_p2p_connect(int level, int nProcs, const int32_t *proc, const void *
     MUSB_CUDA(cudaDeviceCanAccessPeer(&can, g.device, b.device));
     if (!can) return setError(MUSB200_ERR_CUDA, "no peer access between devices " + std::to_string(g.device) +
                                                     " and " + std::to_string(b.device));
-    void *p0 = nullptr, *p1 = nullptr, *pf = nullptr;
+    void *p0 = nullptr, *p1 = nullptr, *pf = nullptr, *pa = nullptr;
     MUSB_CUDA(cudaIpcOpenMemHandle(&p0, b.state[0], cudaIpcMemLazyEnablePeerAccess));
     P.opened.push_back(p0);
     MUSB_CUDA(cudaIpcOpenMemHandle(&p1, b.state[1], cudaIpcMemLazyEnablePeerAccess));
     P.opened.push_back(p1);
     MUSB_CUDA(cudaIpcOpenMemHandle(&pf, b.arrived, cudaIpcMemLazyEnablePeerAccess));
     P.opened.push_back(pf);
+    MUSB_CUDA(cudaIpcOpenMemHandle(&pa, b.aux, cudaIpcMemLazyEnablePeerAccess));
+    P.opened.push_back(pa);
     P.remoteState[k][0] = static_cast<double *>(p0);
     P.remoteState[k][1] = static_cast<double *>(p1);
     P.remoteArrived[k] = static_cast<unsigned long long *>(pf);
+    P.remoteAux[k] = static_cast<double *>(pa);
     P.remoteS[k] = b.S;
+    std::vector<char> seen((size_t)b.nSize, 0);
     for (int i = 0; i < nVals[k]; ++i) {
       const int rp = remotePos[s.offset[k] + i];
       if (rp < 1 || rp > b.nSize * b.QQ) return setError(MUSB200_ERR_ARG, "remote position out of range");
       peerOf[(size_t)s.offset[k] + i] = (uint8_t)k;
+      const int e = (rp - 1) / QQ;
+      if (!seen[e]) {
+        seen[e] = 1;
+        for (int c = 0; c < 4; ++c) { auxRemote.push_back(e * 4 + c + 1); auxPeer.push_back((uint8_t)k); }
+      }
     }
   }
+  if (auxRemote.size() != s.auxPosHost.size())
+    return setError(MUSB200_ERR_ARG, "the receivers' element lists do not pair with this rank's send elements");
   P.sendRank.assign(s.proc.begin(), s.proc.end());
   P.recvRank.assign(r.proc.begin(), r.proc.end());
   // The lists come elem-major / direction-minor (the reference's AOS order).  The receiver's
@@ -1456,7 +1579,6 @@ int musb200_p2p_connect(int level, int nProcs, const int32_t *proc, const void *
   MUSB_CUDA(cudaStreamSynchronize(g.stream));
   std::vector<int32_t> order((size_t)s.total);
   for (int i = 0; i < s.total; ++i) order[i] = i;
-  const int QQ = L->QQ;
   std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
     if (peerOf[x] != peerOf[y]) return peerOf[x] < peerOf[y];
     const int dx = (remotePos[x] - 1) % QQ, dy = (remotePos[y] - 1) % QQ;
@@ -1473,6 +1595,25 @@ int musb200_p2p_connect(int level, int nProcs, const int32_t *proc, const void *
   MUSB_TRY(P.srcPos.upload(srcSorted.data(), srcSorted.size(), g.stream));
   MUSB_TRY(P.dstPos.upload(dstSorted.data(), dstSorted.size(), g.stream));
   MUSB_TRY(P.peerOf.upload(peerSorted.data(), peerSorted.size(), g.stream));
+  {
+    // auxField entries, ordered the same way: (peer, component, remote element)
+    const int nA = (int)auxRemote.size();
+    std::vector<int32_t> ao((size_t)nA);
+    for (int i = 0; i < nA; ++i) ao[i] = i;
+    std::stable_sort(ao.begin(), ao.end(), [&](int32_t x, int32_t y) {
+      if (auxPeer[x] != auxPeer[y]) return auxPeer[x] < auxPeer[y];
+      const int cx_ = (auxRemote[x] - 1) & 3, cy_ = (auxRemote[y] - 1) & 3;
+      if (cx_ != cy_) return cx_ < cy_;
+      return auxRemote[x] < auxRemote[y];
+    });
+    std::vector<int32_t> as((size_t)nA), ad((size_t)nA);
+    std::vector<uint8_t> ap((size_t)nA);
+    for (int i = 0; i < nA; ++i) { as[i] = s.auxPosHost[ao[i]]; ad[i] = auxRemote[ao[i]]; ap[i] = auxPeer[ao[i]]; }
+    MUSB_TRY(P.auxSrcPos.upload(as.data(), as.size(), g.stream));
+    MUSB_TRY(P.auxDstPos.upload(ad.data(), ad.size(), g.stream));
+    MUSB_TRY(P.auxPeerOf.upload(ap.data(), ap.size(), g.stream));
+    P.nAux = nA;
+  }
   {
     // the same entries grouped by owning element, for the push fused into the sweep
     std::vector<int32_t> byElem((size_t)s.total);
@@ -1503,6 +1644,24 @@ int musb200_p2p_connect(int level, int nProcs, const int32_t *proc, const void *
     MUSB_TRY(P.pushDst.upload(dst.data(), dst.size(), g.stream));
     MUSB_TRY(P.pushQ.upload(eq.data(), eq.size(), g.stream));
     MUSB_TRY(P.pushPeer.upload(ep.data(), ep.size(), g.stream));
+  }
+  {
+    // which CTAs of the sweep pull from a halo row: they do the exchange's wait (p2p.cu).  The
+    // protocol without a "ready to receive" handshake needs every rank this rank sends to to
+    // send to it as well.
+    const int block = sweepBlockSize(QQ);
+    const size_t nCtaWords = ((size_t)divUp(std::max(L->nSolve, 1), block) + 31) / 32;
+    MUSB_TRY(P.ctaMask.alloc(nCtaWords));
+    MUSB_CUDA(cudaMemsetAsync(P.ctaMask.p, 0, nCtaWords * sizeof(uint32_t), g.stream));
+    MUSB_TRY(launchHaloCtaMask(QQ, L->nbr.p, L->S, L->nSolve, L->nFluid + L->nGFC + L->nGFF, block,
+                               P.ctaMask.p, g.stream));
+    std::vector<int> a1(P.sendRank), a2(P.recvRank);
+    std::sort(a1.begin(), a1.end());
+    std::sort(a2.begin(), a2.end());
+    if (a1 != a2)
+      return setError(MUSB200_ERR_UNSUPPORTED, "peer-memory halo exchange needs symmetric peers (every rank this "
+                                               "rank sends to must send to it): stay on the NCCL path");
+    P.sweepWait = true;
   }
   MUSB_CUDA(cudaStreamSynchronize(g.stream));
   P.on = true;
@@ -1562,6 +1721,14 @@ static int stepGraphed(int minLevel, int maxLevel, int nPairs) {
     MUSB_CUDA(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
     int rc = 0;
     g.capturing = true;
+    // single level on several ranks: a replay follows a replay whose last push nobody has waited
+    // for, so the FIRST sweep of the pair must carry the wait as well (it passes at once when
+    // nothing is in flight)
+    if (g.nranks > 1 && maxLevel == minLevel) {
+      Level *L0 = findLevel(minLevel);
+      if (L0->p2p.on && (L0->send[MUSB200_BUF_HALO].total > 0 || L0->recv[MUSB200_BUF_HALO].total > 0))
+        L0->p2p.pendingWait = true;
+    }
     for (int it = 0; it < 2 && rc == 0; ++it) rc = levelStep(minLevel, minLevel, maxLevel, false);
     g.capturing = false;
     cudaError_t ce = cudaStreamEndCapture(g.stream, &graph);
@@ -1582,6 +1749,12 @@ static int stepGraphed(int minLevel, int maxLevel, int nPairs) {
     MUSB_CUDA(cudaGraphLaunch(g.graphExec, g.stream));
     g.launches += g.graphLaunches;
   }
+  if (nPairs > 0 && g.nranks > 1)
+    for (int l = minLevel; l <= maxLevel; ++l) {
+      Level *Lp = findLevel(l);
+      if (Lp->p2p.on && (Lp->send[MUSB200_BUF_HALO].total > 0 || Lp->recv[MUSB200_BUF_HALO].total > 0))
+        Lp->p2p.pendingWait = (maxLevel == minLevel);   // multi-level pushes are followed by their wait
+    }
   return 0;   // two cycles leave every level's now/next parity unchanged
 }
 
@@ -1589,7 +1762,21 @@ int musb200_step(int minLevel, int maxLevel, int nCoarseCycles) {
   MUSB_TRY(needReady());
   if (maxLevel < minLevel || nCoarseCycles < 0) return setError(MUSB200_ERR_ARG, "bad level range / cycles");
   int it = 0;
-  if (g.useGraphs && g.nranks == 1 && !g.profiling && nCoarseCycles >= 8) {
+  // several ranks: capturable when every exchange of the range goes through peer memory (its
+  // kernels keep the exchange number on the device; NCCL calls stay outside graphs)
+  bool capturable = true;
+  if (g.nranks > 1) {
+    if (g.overlap) capturable = false;
+    for (int l = minLevel; l <= maxLevel && capturable; ++l) {
+      Level *Lc = findLevel(l);
+      if (!Lc) break;
+      for (int k = 0; k < 3; ++k) {
+        const bool any = Lc->send[k].total > 0 || Lc->recv[k].total > 0;
+        if (any && !(k == MUSB200_BUF_HALO && Lc->p2p.on)) capturable = false;
+      }
+    }
+  }
+  if (g.useGraphs && capturable && !g.profiling && nCoarseCycles >= 8) {
     // all but the last cycles (the last one materialises auxField) in pairs through the graph
     const int nPairs = (nCoarseCycles - 1) / 2;
     for (int l = minLevel; l <= maxLevel; ++l) {
@@ -1607,6 +1794,11 @@ int musb200_step(int minLevel, int maxLevel, int nCoarseCycles) {
   }
   for (; it < nCoarseCycles; ++it)
     MUSB_TRY(levelStep(minLevel, minLevel, maxLevel, it == nCoarseCycles - 1));
+  // MPI_Waitall of the last exchange: whatever follows this call sees complete halo rows
+  for (int l = minLevel; l <= maxLevel; ++l) {
+    Level *Lw = findLevel(l);
+    if (Lw) MUSB_TRY(ensureArrived(*Lw));
+  }
   return 0;
 }
 
@@ -1629,6 +1821,7 @@ int musb200_fill_helper_elements(int minLevel, int maxLevel) {
   }
   MUSB_TRY(fillFineToCoarse(minLevel, minLevel, maxLevel));
   MUSB_TRY(fillCoarseToFine(minLevel, minLevel, maxLevel));
+  for (int l = minLevel; l <= maxLevel; ++l) MUSB_TRY(ensureArrived(*findLevel(l)));
   return 0;
 }
 
@@ -1649,6 +1842,19 @@ int musb200_set_fused_bc(int flag) {
   return 0;
 }
 
+int musb200_set_exchange_timeout(double seconds) {
+  if (!(seconds >= 0.0)) return setError(MUSB200_ERR_ARG, "timeout must be >= 0 (0 = wait for ever)");
+  ++g.epoch;
+  g.timeoutNs = (unsigned long long)(seconds * 1.0e9);
+  return 0;
+}
+
+int musb200_set_sweep_wait(int flag) {
+  ++g.epoch;
+  g.sweepWait = flag ? 1 : 0;
+  return 0;
+}
+
 int musb200_set_overlap(int flag) {
   g.overlap = flag ? 1 : 0;
   return 0;
@@ -1658,7 +1864,7 @@ int musb200_synchronize(void) {
   MUSB_TRY(needReady());
   MUSB_CUDA(cudaStreamSynchronize(g.stream));
   MUSB_CUDA(cudaStreamSynchronize(g.commStream));
-  return 0;
+  return checkAsyncErrors();
 }
 
 int musb200_reduce(int level, double *total_mass, double *max_vel, int *any_nan) {
@@ -1676,6 +1882,7 @@ int musb200_reduce(int level, double *total_mass, double *max_vel, int *any_nan)
   double h[3];
   MUSB_CUDA(cudaMemcpyAsync(h, out, 3 * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
   MUSB_CUDA(cudaStreamSynchronize(g.stream));
+  MUSB_TRY(checkAsyncErrors());
   if (total_mass) *total_mass = h[0];
   if (max_vel) *max_vel = sqrt(h[1]);
   if (any_nan) *any_nan = (h[2] > 0.0 || h[0] != h[0]) ? 1 : 0;

@@ -20,6 +20,51 @@ struct PushArgs {
   long long remoteS[kMaxPeers];
 };
 
+// the receiving half of the peer-memory halo exchange (p2p.cu): wait until every rank this rank
+// receives from has published an exchange number >= this rank's own
+struct HaloWait {
+  const uint32_t *ctaMask;              // sweep: 1 bit per CTA that pulls from a halo row; nullptr = no wait
+  const unsigned long long *arrived;    // my arrived[nranks], written by the senders
+  const unsigned long long *exch;       // my exchange number (device memory)
+  int nRecvPeers;
+  int recvRank[kMaxPeers];
+  unsigned long long timeoutNs;         // 0 = wait for ever
+  int *errFlag;                         // device memory: {code, peer rank, exchange lo, exchange hi}
+};
+
+__device__ __forceinline__ unsigned long long globalTimerNs() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// called by ONE thread; the caller separates it from the readers of the halo rows by a barrier
+__device__ __forceinline__ void waitHaloArrival(const HaloWait &w) {
+  const unsigned long long want = *reinterpret_cast<const volatile unsigned long long *>(w.exch);
+  unsigned long long t0 = 0ull;
+  for (int k = 0; k < w.nRecvPeers; ++k) {
+    const volatile unsigned long long *flag = w.arrived + w.recvRank[k];
+    unsigned int spins = 0u;
+    while (*flag < want) {
+      __nanosleep(64);
+      if (w.timeoutNs != 0ull && (++spins & 1023u) == 0u) {
+        const unsigned long long now = globalTimerNs();
+        if (t0 == 0ull) t0 = now;
+        if (now - t0 > w.timeoutNs) {
+          if (atomicCAS(w.errFlag, 0, 1) == 0) {           // first reporter keeps its details
+            w.errFlag[1] = w.recvRank[k];
+            w.errFlag[2] = (int)(want & 0xffffffffull);
+            w.errFlag[3] = (int)(want >> 32);
+            __threadfence_system();
+          }
+          return;
+        }
+      }
+    }
+  }
+  __threadfence_system();
+}
+
 // Arguments of one fused "auxField + stream + collide" sweep over a level.
 // State and aux are SoA with row stride S (elements): f[q][e] = ptr[q*S + e].
 struct SweepArgs {
@@ -40,6 +85,7 @@ struct SweepArgs {
   const double *force;
   double force_uniform[3];
   PushArgs push;
+  HaloWait wait;         // single level, several ranks: CTAs that pull from halo rows wait for the exchange
 };
 
 int launchSweep(int QQ, int relax, int kind, const SweepArgs &a, cudaStream_t st);
@@ -127,23 +173,41 @@ int launchUnserialize(int QQ, double *state, long long S, const int32_t *slot, c
 // peer-memory halo exchange (p2p.cu)
 struct P2PArgs {
   const double *state;        // my state(:, next)
+  const double *aux;          // my auxField (multi-level: travels with the halo elements), or nullptr
   long long S;
-  int QQ, n;                  // n = all send entries, peers concatenated
+  int QQ, n, nAux;            // n = all state send entries, nAux = all auxField entries, peers concatenated
   const int32_t *srcPos;      // my state positions (the send buffer's pos list)
   const int32_t *dstPos;      // the receiver's state positions (its recv buffer's pos list)
   const uint8_t *peerOf;      // entry -> index into the peer tables below
-  int nSendPeers, nRecvPeers, myRank;
+  const int32_t *auxSrcPos;   // auxField positions (elem-1)*4 + k, mine / the receiver's
+  const int32_t *auxDstPos;
+  const uint8_t *auxPeerOf;
+  int nSendPeers, myRank;
   double *remoteState[kMaxPeers];              // receiver's state(:, next), peer-mapped
+  double *remoteAux[kMaxPeers];                // receiver's auxField, peer-mapped
   long long remoteS[kMaxPeers];
   unsigned long long *remoteArrived[kMaxPeers];  // receiver's arrived[nranks], peer-mapped
-  int recvRank[kMaxPeers];
-  unsigned long long *arrived;  // my arrived[nranks]
-  unsigned long long count;     // number of this exchange
+  unsigned long long *exch;     // my exchange number, bumped by the kernel
   unsigned int *ticket;
+  // auxField rows are single-buffered: before storing, wait until every receiver has announced
+  // that it no longer reads the previous exchange (ready[] sits behind arrived[], same mapping)
+  int handshake;
+  int nranks;
+  const unsigned long long *ready;   // my ready[nranks], written by the peers
+  int sendRank[kMaxPeers];
+  unsigned long long timeoutNs;
+  int *errFlag;
 };
 int launchPushHalo(const P2PArgs &a, cudaStream_t st);
-// arrival handshake only (the links were stored by the sweep with the fused push)
+// publish only (the links were stored by the sweep with the fused push)
 int launchSignalHalo(const P2PArgs &a, cudaStream_t st);
+// MPI_Waitall of the exchange as a one-thread kernel
+int launchWaitHalo(const HaloWait &w, cudaStream_t st);
+// bitmap of the sweep CTAs (block elements each) that pull from rows >= haloStart
+int launchHaloCtaMask(int QQ, const uint32_t *nbr, long long S, int nSolve, int haloStart, int block,
+                      uint32_t *mask, cudaStream_t st);
+// threads per CTA of the sweep for this stencil (sweep.cu)
+int sweepBlockSize(int QQ);
 
 // reductions: out[0] = total mass, out[1] = max |u|^2, out[2] = nan count
 int launchReduce(int QQ, const double *state, long long S, int nFluid, double *scratch,

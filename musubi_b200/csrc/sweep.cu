@@ -26,6 +26,8 @@ int launchSweep(int QQ, int relax, int kind, const SweepArgs &a, cudaStream_t st
   return dispatchSweep<0>(QQ, relax, kind, a, st);
 }
 
+int sweepBlockSize(int QQ) { return QQ == 27 ? sweepThreads<27>() : sweepThreads<19>(); }
+
 int launchAuxOnly(int QQ, int kind, const SweepArgs &a, cudaStream_t st) {
   if (a.count <= 0) return 0;
   const int grid = divUp(a.count, 128);

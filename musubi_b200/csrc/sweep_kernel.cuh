@@ -114,6 +114,16 @@ struct ForceSrc {
 template <int QQ, int RELAX, bool INCOMP, int VAR>
 __global__ void __launch_bounds__(sweepThreads<QQ>(), sweepMinBlocks<QQ>()) sweepKernel(const SweepArgs a) {
   constexpr bool FORCE = VAR == 1, PUSH = VAR == 2;
+  // several ranks, peer-memory halo exchange: a CTA that pulls from a halo row waits until the
+  // peers' links of the previous step have arrived (p2p.cu); all other CTAs start right away
+  bool halo = false;
+  if (a.wait.ctaMask != nullptr) {
+    halo = (a.wait.ctaMask[blockIdx.x >> 5] >> (blockIdx.x & 31)) & 1u;   // uniform over the CTA
+    if (halo) {
+      if (threadIdx.x == 0) waitHaloArrival(a.wait);
+      __syncthreads();
+    }
+  }
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.count) return;
   int e;
@@ -130,10 +140,20 @@ __global__ void __launch_bounds__(sweepThreads<QQ>(), sweepMinBlocks<QQ>()) swee
     uint32_t n[QQ - 1];
 #pragma unroll
     for (int q = 0; q < QQ - 1; ++q) n[q] = __ldcs(a.nbr + q * S + e);
+    if (!halo) {
 #pragma unroll
-    for (int q = 0; q < QQ - 1; ++q) {
-      const long long row = (n[q] & kBounceBit) ? (long long)invDir<QQ>(q) * S : (long long)q * S;
-      f[q] = __ldg(a.in + row + (n[q] & kElemMask));
+      for (int q = 0; q < QQ - 1; ++q) {
+        const long long row = (n[q] & kBounceBit) ? (long long)invDir<QQ>(q) * S : (long long)q * S;
+        f[q] = __ldg(a.in + row + (n[q] & kElemMask));
+      }
+    } else {
+      // halo rows were written by a peer DURING this kernel: not read-only data, so no
+      // ld.global.nc and no L1 (a line shared with own elements may sit there stale) -- L2 only
+#pragma unroll
+      for (int q = 0; q < QQ - 1; ++q) {
+        const long long row = (n[q] & kBounceBit) ? (long long)invDir<QQ>(q) * S : (long long)q * S;
+        f[q] = __ldcg(a.in + row + (n[q] & kElemMask));
+      }
     }
     f[QQ - 1] = __ldg(a.in + (long long)(QQ - 1) * S + e);
   }

@@ -295,6 +295,8 @@ module mus_b200_module
   end interface
 
   integer(c_int), save :: relax_id = 0, kind_id = 0, QQ_id = 19
+  !> MUSB200_P2P_BLOB of include/musb200.h
+  integer, parameter :: p2p_blob = 512
 
 contains
 
@@ -617,15 +619,16 @@ contains
     integer, allocatable :: req(:)
     integer :: iProc, nRanks, iError, n, off
     call mpi_comm_size(comm, nRanks, iError)
-    allocate(blob(256), allBlobs(256*nRanks), peerBlobs(256*max(1, send%nProcs)))
+    allocate(blob(p2p_blob), allBlobs(p2p_blob*nRanks), peerBlobs(p2p_blob*max(1, send%nProcs)))
     call chk(musb200_p2p_export(int(iLevel, c_int), blob), 'p2p_export')
-    call mpi_allgather(blob, 256, mpi_character, allBlobs, 256, mpi_character, comm, iError)
+    call mpi_allgather(blob, p2p_blob, mpi_character, allBlobs, p2p_blob, mpi_character, comm, iError)
     allocate(proc(send%nProcs), nVals(send%nProcs), req(send%nProcs + recv%nProcs))
     n = 0
     do iProc = 1, send%nProcs
       proc(iProc) = send%proc(iProc); nVals(iProc) = send%buf_real(iProc)%nVals
       n = n + nVals(iProc)
-      peerBlobs(256*(iProc-1)+1:256*iProc) = allBlobs(256*send%proc(iProc)+1:256*(send%proc(iProc)+1))
+      peerBlobs(p2p_blob*(iProc-1)+1:p2p_blob*iProc) = &
+        & allBlobs(p2p_blob*send%proc(iProc)+1:p2p_blob*(send%proc(iProc)+1))
     end do
     allocate(remotePos(max(1, n)))
     off = 0

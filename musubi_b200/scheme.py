@@ -18,6 +18,7 @@ import numpy as np
 from . import _lib  # noqa: F401  (musubi_b200._lib is part of the package surface: bench.py, tests)
 from ._lib import P_DBL, P_I32, P_I64, check, lib, ptr
 
+P2P_BLOB = 512          # MUSB200_P2P_BLOB of include/musb200.h
 BC_KIND = {"wall": 0, "velocity_bounceback": 1, "pressure_antibounceback": 2, "pressure_expol": 3}
 _initialized = False
 
@@ -367,10 +368,10 @@ class Scheme:
         import torch
         level = self.minLevel if level is None else level
         ld = self.levelDesc[level]
-        blob = ctypes.create_string_buffer(256)
+        blob = ctypes.create_string_buffer(P2P_BLOB)
         check(lib.musb200_p2p_export(level, blob))
         mine = torch.frombuffer(bytearray(blob.raw), dtype=torch.uint8).clone()
-        allb = [torch.zeros(256, dtype=torch.uint8) for _ in range(dist.get_world_size())]
+        allb = [torch.zeros(P2P_BLOB, dtype=torch.uint8) for _ in range(dist.get_world_size())]
         dist.all_gather(allb, mine)
         proc, nVals, rpos = exchange_recv_lists(dist, ld)
         blobs = b"".join(bytes(allb[int(p)].numpy().tobytes()) for p in proc)

@@ -105,9 +105,40 @@ def run_multilevel(a, mb, dist, torch, rank, world, QQ):
     ident = {"kind": "fluid", "relaxation": a.relaxation, "layout": a.layout}
     omega = {l: float(1.0 / (3.0 * s.visc[0] + 0.5)) for l, s in ms.s.items()}
     visc = {l: float(s.visc[0]) for l, s in ms.s.items()}
-    sch = mb.Scheme(ident, mine, omega, lambda_=0.25, omega_bulk=1.2,
-                    intp=(my_tables, intp["order"]), viscosity=visc, ghost_comm=ghost_comm)
+    kw = dict(lambda_=0.25, omega_bulk=1.2, intp=(my_tables, intp["order"]), viscosity=visc, ghost_comm=ghost_comm)
+    check(lib.musb200_set_graphs(0 if a.no_graphs else 1))
+
+    def connect(sc):
+        if a.p2p:      # peer-memory exchange of state + auxField halos on every level (collective)
+            for l in sorted(mine):
+                sc.p2p_connect(dist, l)
+
+    if a.restart:
+        # mus_readRestart into a FRESH scheme on every rank: only the fluid PDFs are known; halos,
+        # ghosts and auxField come from musb200_fill_helper_elements (collective).  Truth: the
+        # single-domain oracle restarted the same way.
+        from musubi_b200 import restart_io
+        ms.run(3)
+        gtid, glp = mo.global_tree(lv)
+        dump = mo.pdf_serialize(ms.s, gtid, glp)
+        ms2 = mo.MultiLevelScheme(lv, tables, a.relaxation, "fluid", omega_min=OMEGA_MIN[len(boxes)],
+                                  omega_bulk=1.2, order=intp["order"])
+        mo.pdf_unserialize(ms2.s, gtid, glp, dump)
+        ms2.fill_helper_elements()
+        sch = mb.Scheme(ident, mine, omega, **kw)
+        connect(sch)
+        tid, lp = restart_io.tree_order(mine)
+        where = {int(t): i for i, t in enumerate(gtid)}
+        sel = np.array([where[int(t)] for t in tid], dtype=np.int64)
+        sch.pdf_unserialize(tid, lp, dump.reshape(-1, QQ)[sel].ravel())
+        sch.fill_helper_elements()
+        ms = ms2
+    else:
+        sch = mb.Scheme(ident, mine, omega, **kw)
+        connect(sch)
     for l, s in ms.s.items():
+        if a.restart:
+            break
         M = mine[l]
         g = M.globalPos - 1
         st = np.zeros(M.nSize * QQ)
@@ -155,6 +186,11 @@ def main():
                          "FromCoarser / FromFiner buffers (the reference's form of the run)")
     ap.add_argument("--fused-push", action="store_true",
                     help="peer-memory exchange with the push fused into the sweep kernel")
+    ap.add_argument("--no-sweep-wait", action="store_true",
+                    help="peer-memory exchange: wait right after the push instead of inside the next sweep")
+    ap.add_argument("--no-graphs", action="store_true", help="direct launches instead of CUDA-graph replay")
+    ap.add_argument("--restart", action="store_true",
+                    help="gpu-ml: restart into a fresh scheme (fluid PDFs only + musb200_fill_helper_elements)")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -239,6 +275,8 @@ def main():
         # single-domain oracle = the truth for every rank
         mb._lib.check(mb._lib.lib.musb200_set_overlap(1 if a.overlap else 0))
         mb._lib.check(mb._lib.lib.musb200_set_fused_push(1 if a.fused_push else 0))
+        mb._lib.check(mb._lib.lib.musb200_set_sweep_wait(0 if a.no_sweep_wait else 1))
+        mb._lib.check(mb._lib.lib.musb200_set_graphs(0 if a.no_graphs else 1))
         gl = mo.build_level_desc(a.level, QQ, a.kind, octants=a.octants)
         ref = mo.Scheme(gl, a.relaxation, "fluid", omega=1.7, lambda_=0.25, omega_bulk=1.3)
         gld = mb.LevelDesc(a.level, QQ, a.kind, 0, 1, octants=a.octants)

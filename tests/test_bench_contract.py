@@ -32,10 +32,23 @@ def test_reference_arm_other_ranks_stay_silent():
     assert r.returncode == 0 and not [l for l in r.stdout.splitlines() if l.startswith("{")]
 
 
-def test_committed_traffic_capture_is_readable():
+def test_traffic_capture_is_keyed_by_the_kernel_source(tmp_path):
+    """roofline.traffic comes from a committed ncu capture; an entry only counts for the kernel
+    source it was taken of (hash of sweep_kernel.cuh + collide.cuh + ...), so it cannot go stale
+    silently when the kernel changes"""
     sys.path.insert(0, ROOT)
     import bench
-    t = bench.measured_traffic("sweepKernel<19,trt>", 256 ** 3)
-    assert t and 6.0e9 < t["bytes"] < 6.6e9
-    assert bench.measured_traffic("sweepKernel<19,trt>", 64 ** 3) is None
+    sha = bench.kernel_source_hash()
+    p = tmp_path / "traffic.json"
+    p.write_text(json.dumps([
+        {"kernel": "sweepKernel<19,trt>", "cells": 256 ** 3, "traffic_gb": 6.36, "source": "x", "source_sha": sha},
+        {"kernel": "sweepKernel<27,mrt>", "cells": 256 ** 3, "traffic_gb": 9.2, "source": "y", "source_sha": "0" * 16}]))
+    t = bench.measured_traffic("sweepKernel<19,trt>", 256 ** 3, str(p))
+    assert t and 6.0e9 < t["bytes"] < 6.6e9 and t["source_sha"] == sha
+    assert bench.measured_traffic("sweepKernel<19,trt>", 64 ** 3, str(p)) is None
+    assert bench.measured_traffic("sweepKernel<27,mrt>", 256 ** 3, str(p)) is None     # stale capture
     assert bench.BYTES_PER_LUP == {19: 380, 27: 540}
+    committed = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(committed):
+        for e in json.load(open(committed)):
+            assert {"kernel", "cells", "traffic_gb", "source", "source_sha"} <= set(e)

@@ -56,10 +56,14 @@ def _ngpu():
     ("d3q19", "trt", "cavity", ["--octants", "2", "--p2p"]),
     ("d3q19", "bgk", "channel", ["--p2p", "--overlap"]),
     ("d3q27", "mrt", "periodic", ["--p2p", "--fused-push"]),      # links stored by the sweep itself
-    ("d3q19", "trt", "cavity", ["--octants", "2", "--p2p", "--fused-push"])],
+    ("d3q19", "trt", "cavity", ["--octants", "2", "--p2p", "--fused-push"]),
+    ("d3q27", "mrt", "periodic", ["--p2p", "--no-sweep-wait"]),   # MPI_Waitall right after the push
+    ("d3q19", "trt", "cavity", ["--octants", "2", "--p2p", "--no-graphs"]),   # direct launches
+    ("d3q19", "bgk", "channel", ["--p2p"])],                      # pressure boundary reads halo neighbours
     ids=["mrt27-periodic", "trt19-cavity", "bgk19-channel", "mrt27-periodic-overlap", "trt19-cavity-2oct",
          "mrt27-periodic-p2p", "trt19-cavity-2oct-p2p", "bgk19-channel-p2p-overlap",
-         "mrt27-periodic-p2p-fusedpush", "trt19-cavity-2oct-p2p-fusedpush"])
+         "mrt27-periodic-p2p-fusedpush", "trt19-cavity-2oct-p2p-fusedpush", "mrt27-periodic-p2p-nosweepwait",
+         "trt19-cavity-2oct-p2p-nographs", "bgk19-channel-p2p"])
 def test_multi_gpu_matches_single_domain_oracle(layout, relax, kind, extra):
     n = _ngpu()
     if n < 2:
@@ -74,17 +78,25 @@ def test_multi_gpu_matches_single_domain_oracle(layout, relax, kind, extra):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("layout,relax,levels,method", [
-    ("d3q19", "bgk", 2, "linear"), ("d3q27", "mrt", 2, "quadratic"), ("d3q19", "bgk", 3, "linear")],
-    ids=["2lvl-linear-bgk19", "2lvl-quad-mrt27", "3lvl-linear-bgk19"])
-def test_multi_gpu_multilevel_matches_single_domain_oracle(layout, relax, levels, method):
+@pytest.mark.parametrize("layout,relax,levels,method,extra", [
+    ("d3q19", "bgk", 2, "linear", []), ("d3q27", "mrt", 2, "quadratic", []), ("d3q19", "bgk", 3, "linear", []),
+    ("d3q19", "bgk", 2, "linear", ["--p2p"]), ("d3q27", "mrt", 2, "quadratic", ["--p2p", "--no-graphs"]),
+    ("d3q19", "bgk", 3, "linear", ["--p2p"]), ("d3q19", "bgk", 2, "linear", ["--restart"]),
+    ("d3q19", "bgk", 3, "linear", ["--restart", "--p2p"]), ("d3q19", "bgk", 2, "linear", ["--ghost-exchange"])],
+    ids=["2lvl-linear-bgk19", "2lvl-quad-mrt27", "3lvl-linear-bgk19", "2lvl-linear-bgk19-p2p",
+         "2lvl-quad-mrt27-p2p-nographs", "3lvl-linear-bgk19-p2p", "2lvl-restart", "3lvl-restart-p2p",
+         "2lvl-ghost-exchange"])
+def test_multi_gpu_multilevel_matches_single_domain_oracle(layout, relax, levels, method, extra):
     """multi-level mesh partitioned along the global space-filling curve, one GPU per rank:
-    state + auxField halo exchange per level through NCCL, ghosts interpolated locally"""
+    state + auxField halo exchange per level through NCCL or peer memory (--p2p: one push kernel
+    per level step, CUDA-graph replay of the cycle), ghosts interpolated locally; --restart: fluid
+    PDFs into a fresh scheme + musb200_fill_helper_elements; --ghost-exchange: the reference's
+    FromCoarser / FromFiner buffers"""
     n = _ngpu()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     nproc = 2 if n < 4 else 4
     r = _launch(nproc, ["--mode", "gpu-ml", "--layout", layout, "--relaxation", relax, "--levels", str(levels),
-                        "--method", method, "--steps", "6"], 29653)
+                        "--method", method, "--steps", "10"] + extra, 29653)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert r.stdout.count("ndiff=0") >= nproc * (levels + 1)

@@ -199,8 +199,10 @@ def mbgpu():
 @pytest.mark.gpu
 def test_device_restart_file_round_trip_continues_bit_identically(mbgpu, oracle, tmp_path):
     """Scheme.write_restart after 4 cycles of a two-level run: the file's bytes equal the oracle's
-    serialisation; a perturbed device state restored with Scheme.read_restart continues exactly
-    like the uninterrupted oracle run."""
+    serialisation; a perturbed device state restored with Scheme.read_restart -- which, as
+    mus_init_flow does after mus_readRestart, rebuilds auxField and ghosts from the stored fluid
+    PDFs (musb200_fill_helper_elements) -- continues exactly like the oracle that does the same
+    fill, and to rounding like the uninterrupted run."""
     from test_multilevel import build
     from musubi_b200._lib import check, lib
     mb, mo, QQ = mbgpu, oracle, 19
@@ -225,9 +227,16 @@ def test_device_restart_file_round_trip_continues_bit_identically(mbgpu, oracle,
     t = sch.read_restart(hname, base_dir="/")
     assert t["iter"] == 4 and t["sim"] == 4.0
     assert sch.pdf_serialize(tid, lp).tobytes() == exp.tobytes()
+    import copy
+    cont = copy.deepcopy(ms)                                  # the uninterrupted run
+    cont.run(3)
+    ms.fill_helper_elements()                                 # the oracle's restart: same fill
     sch.do_computation(3)
     ms.run(3)
-    assert sch.pdf_serialize(tid, lp).tobytes() == mo.pdf_serialize(ms.s, tid, lp).tobytes()
+    got = sch.pdf_serialize(tid, lp)
+    assert got.tobytes() == mo.pdf_serialize(ms.s, tid, lp).tobytes()
+    ref = mo.pdf_serialize(cont.s, tid, lp)
+    assert np.max(np.abs(got - ref) / np.abs(ref)) < 1e-11
     sch.destroy()
 
 
