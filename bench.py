@@ -3,7 +3,7 @@
 GPU) with the HBM roofline and the reference's CPU algorithm timed beside it.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl musb200|reference]
-                  [--workload cfg1|cfg2|cfg3|cfg3-256|cfg4] [--level L]
+                  [--workload cfg1|cfg2|cfg3|cfg3-256|cfg4|cfg5] [--level L]
 
 Workloads (BASELINE.json configs):
   N = 1 : cfg2  D3Q19 TRT lid-driven cavity 256^3 (level 8), bounce-back walls +
@@ -20,6 +20,9 @@ Workloads (BASELINE.json configs):
   --workload cfg4 : BASELINE config 4, two-level octree with linear ghost interpolation; a step is
                 one coarse cycle (1 coarse + 2 fine level steps); with --gpus N the mesh is cut along
                 the global space-filling curve (strong scaling)
+  --workload cfg5 : BASELINE config 5, three-level octree, D3Q19 BGK flow + passive scalar coupled
+                on the device (two schemes stepped together); no reference behaviour exists, reported
+                separately
   --workload cfg3 : the cfg3 block alone as the main line (also cfg3-256 on one GPU)
 A "step" is one level time step (set_boundary, swap, fused aux+stream+collide,
 halo exchange) over the whole mesh.  `value` is device-timed with inputs resident
@@ -57,6 +60,10 @@ WORKLOADS = {
                  kind="multilevel", omega=1.7, boxes=[(32, 96)], cylinder=(128.0, 128.0, 16.0, 72, 184),
                  name="two-level octree: level-7 periodic cube, 64^3 coarse cells refined to level 8 "
                       "around a solid cylinder, D3Q19 BGK, linear ghost interpolation"),
+    "cfg5": dict(ident={"kind": "fluid", "relaxation": "bgk", "layout": "d3q19"}, level=7,
+                 kind="multilevel", omega=1.8, boxes=[(32, 96), (96, 160)], cylinder=None, scalar=True,
+                 name="three-level octree (levels 7/8/9, nested 128^3-cell boxes), D3Q19 BGK flow + passive scalar "
+                      "(bgk, first order) transported by it, linear ghost interpolation"),
     "cfg3-256": dict(ident={"kind": "fluid", "relaxation": "mrt", "layout": "d3q27"}, level=8,
                      kind="periodic", omega=1.9, name="D3Q27 MRT periodic channel 256^3"),
 }
@@ -590,7 +597,9 @@ def run_multilevel(args, comm, mb, wl_name, wl):
     minL = args.level or WORKLOADS[wl_name]["level"]
     scale = 2.0 ** (minL - WORKLOADS[wl_name]["level"])      # boxes / cylinder are given at the base level
     boxes = [(int(lo * scale), int(hi * scale)) for lo, hi in wl["boxes"]]
-    cyl = tuple(c * scale for c in wl["cylinder"][:3]) + tuple(int(c * scale) for c in wl["cylinder"][3:])
+    cyl = None
+    if wl.get("cylinder"):
+        cyl = tuple(c * scale for c in wl["cylinder"][:3]) + tuple(int(c * scale) for c in wl["cylinder"][3:])
     glob, intp = tm.build_multilevel(minL, boxes, QQ=19, cylinder=cyl, intp_method="linear")
     weights = tm.level_weights(glob) if args.balance else None      # SPartA cut by level steps per cycle
     lv = glob if world == 1 else tm.partition_multilevel(glob, world, weights=weights)[rank]
@@ -600,6 +609,14 @@ def run_multilevel(args, comm, mb, wl_name, wl):
     visc = {l: nu0 * 2.0 ** (l - levels[0]) for l in levels}       # acoustic scaling
     omega = {l: 1.0 / (3.0 * visc[l] + 0.5) for l in levels}
     sch = mb.Scheme(wl["ident"], lv, omega, intp=(tables, intp["order"]), viscosity=visc)
+    scalar = None
+    if wl.get("scalar"):
+        # BASELINE config 5: a passive scalar in scheme slot 1, transported by the flow of slot 0
+        # (velocity read from the flow's auxField on the device), diffusivity scaled acoustically
+        diff = {l: 0.02 * 2.0 ** (l - levels[0]) for l in levels}
+        scalar = mb.Scheme({"kind": "passive_scalar", "relaxation": {"name": "bgk", "variant": "first"},
+                            "layout": "d3q19"}, lv, species={"diff_coeff": diff, "lambda": 0.25},
+                           intp=(tables, intp["order"]), slot=1)
     host, nbytes = {}, 0
     for l in levels:
         L = lv[l]
@@ -613,28 +630,45 @@ def run_multilevel(args, comm, mb, wl_name, wl):
         sch.upload_state(l, host[l])
         aux = np.zeros(L.nSize * 4)
         aux[:L.nElems * 4] = np.concatenate([np.ones((L.nElems, 1)), vel], axis=1).ravel()
+        sch._bind()
         check(lib.musb200_aux_upload(l, aux.ctypes.data))
+        if scalar is not None:
+            r2 = ((L.bary_unit - 0.5) ** 2).sum(axis=1)
+            conc = 1.0 + 0.5 * np.exp(-r2 / 0.02)
+            scalar.upload_state(l, cases.equilibrium_state(19, conc, np.zeros((L.nElems, 3)), L.nSize))
+            scalar.couple_transport_velocity(l, sch)
     p2p_on = False
     if world > 1 and not args.no_p2p:
-        p2p_on = all([connect_p2p(comm, sch, l, True) for l in levels])
+        p2p_on = all([connect_p2p(comm, sc, l, True) for sc in ([sch] + ([scalar] if scalar else [])) for l in levels])
+    nsch = 2 if scalar is not None else 1
+
+    def do_cycles(n):
+        if scalar is None:
+            sch.do_computation(n)
+        else:
+            mb.step_schemes([sch, scalar], n)
+
+    class _Stepper:               # what timed_steps drives
+        do_computation = staticmethod(do_cycles)
+        synchronize = staticmethod(sch.synchronize)
     sch.synchronize()
     setup_s = time.perf_counter() - t_setup
     upd = {l: 2 ** (l - levels[0]) for l in levels}                # level steps per coarse cycle
-    lups_cycle = comm.allred(float(sum(lv[l].nFluid * upd[l] for l in levels)), "SUM")
-    solve_cycle = sum((lv[l].nFluid + lv[l].nGhostFromCoarser) * upd[l] for l in levels)   # this rank
+    lups_cycle = nsch * comm.allred(float(sum(lv[l].nFluid * upd[l] for l in levels)), "SUM")
+    solve_cycle = nsch * sum((lv[l].nFluid + lv[l].nGhostFromCoarser) * upd[l] for l in levels)   # this rank
 
-    sch.do_computation(W)
+    do_cycles(W)
     sch.synchronize()
     sampler = ClockSampler(comm.local_rank)
     if rank == 0:
         sampler.start()
     check(lib.musb200_timers_reset())
-    t_ms = timed_steps(comm, sch, K, sampler)      # region 1: nothing but the cycle's own launches
+    t_ms = timed_steps(comm, _Stepper, K, sampler)      # region 1: nothing but the cycle's own launches
     nl = ctypes.c_longlong()
     check(lib.musb200_launch_count(ctypes.byref(nl)))
     check(lib.musb200_set_profiling(1))         # region 2: CUDA events around every stage
     check(lib.musb200_timers_reset())
-    t2_ms = timed_steps(comm, sch, K, sampler)
+    t2_ms = timed_steps(comm, _Stepper, K, sampler)
     clocks = sampler.finish() if rank == 0 else None
     cm, bm, com, im = (ctypes.c_double() for _ in range(4))
     check(lib.musb200_timers(ctypes.byref(cm), ctypes.byref(bm), ctypes.byref(com), ctypes.byref(im)))
@@ -650,9 +684,11 @@ def run_multilevel(args, comm, mb, wl_name, wl):
     peak, peak_src = measured_peak()
     achieved = BYTES_PER_LUP[19] * float(solve_cycle) / (sweep_ms * 1e-3) / 1e9
     mass = sum(sch.reduce(l)[0] / 8.0 ** (l - levels[0]) for l in levels) if world == 1 else None
+    smass = (sum(scalar.reduce(l)[0] / 8.0 ** (l - levels[0]) for l in levels)
+             if (world == 1 and scalar is not None) else None)
 
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and scalar is None:
         comm.barrier()
         t0 = time.perf_counter()
         for l in levels:
@@ -681,23 +717,34 @@ def run_multilevel(args, comm, mb, wl_name, wl):
                                         world, "SPartA-weighted" if args.balance else "equal",
                                         "peer memory, one push kernel per level step" if p2p_on else "NCCL"),
                        "step": "one coarse cycle = %s level steps" % "+".join(str(upd[l]) for l in levels),
-                       "mlups_definition": "sum_l nFluid(l) * 2^(l-minLevel) per coarse cycle / time (SURVEY 8d)",
+                       "mlups_definition": "sum_l nFluid(l) * 2^(l-minLevel) per coarse cycle / time (SURVEY 8d)" + (
+                           ", flow and scalar updates both counted (two schemes)" if scalar is not None else ""),
+                       "schemes": (["fluid bgk d3q19 (slot 0)", "passive_scalar bgk/first d3q19 (slot 1), transport "
+                                    "velocity = the flow's auxField of the same level step, ghosts by the reference's "
+                                    "arbitrary-value interpolation of its PDFs"] if scalar is not None else
+                                   ["fluid bgk d3q19"]),
+                       "reference_behaviour": ("none: the reference aborts for a passive scalar on a multi-level mesh "
+                                               "(mus_scheme_module.f90:166-190); parity is against the oracle's "
+                                               "coupled scheme only" if scalar is not None else "do_recursive_multiLevel"),
                        "mlups_by_reference_formula": value_ref_formula,
                        "interpolation": "linear", "omega": {str(l): omega[l] for l in levels},
                        "l2": "state %.2f GB per rank > 126 MB L2" % (2 * nbytes / 1e9), "setup_s": round(setup_s, 2)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
-                         "kernel": "sweepKernel<19,bgk> (all level steps of a cycle, rank 0)",
+                         "kernel": "sweepKernel<19,bgk>%s (all level steps of a cycle, rank 0)" % (
+                             " + passiveScalarKernel<19>" if scalar is not None else ""),
                          "bytes_per_lup": BYTES_PER_LUP[19], "kernel_ms": sweep_ms,
                          "share_of_step": sweep_ms / (t2_ms / K)},
             "timers_ms_per_step": {"compute": cm.value / K, "bc": bm.value / K, "comm": com.value / K,
                                    "intp": im.value / K},
             "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(nl.value), "clocks": clocks,
-            "check": {"total_mass": mass},
+            "check": {"total_mass": mass, "scalar_mass": smass},
         }
         print(json.dumps(line), flush=True)
     sch.synchronize()
     comm.barrier()
+    if scalar is not None:
+        scalar.destroy()
     sch.destroy()
 
 

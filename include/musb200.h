@@ -263,6 +263,17 @@ int musb200_intp_register(int tgtLevel, int direction, int order, int nTargets,
  * (mus/source/mus_control_module.f90:242-701) on the device: set_boundary, swap,
  * fused auxField + stream-collide, halo exchange, ghost interpolation.         */
 int musb200_step(int minLevel, int maxLevel, int nCoarseCycles);
+/* Several schemes on one mesh stepped TOGETHER (BASELINE config 5: a passive scalar transported by
+ * the flow of another slot, musb200_couple_transport_velocity): within every level step of the
+ * recursive schedule the schemes advance in the order given -- slots[0] first -- so that a scalar's
+ * sweep reads the auxField the flow's sweep of the same level step has just written, also on the
+ * finer levels' sub-steps; then each scheme fills its ghosts.  A passive scalar's ghosts are filled
+ * by the reference's interpolation of arbitrary values applied to its PDFs
+ * (fillArbiMyGhostsFromFiner_avg, fillArbiFinerGhostsFromMe_weighAvg / _linear / _quad,
+ * mus_interpolate_average_module.fpp:95-185, 762-850, mus_interpolate_linear_module.fpp:124-205,
+ * mus_interpolate_quadratic_module.fpp:102-190): the reference itself aborts for a passive scalar on
+ * a multi-level mesh (mus_scheme_module.f90:166-190), this is the documented extension.         */
+int musb200_step_schemes(int nSlots, const int *slots, int minLevel, int maxLevel, int nCoarseCycles);
 /* 1: auxField is written by every level step;
  * 0 (default): only where the schedule reads it and on the last step of a call;
  * 2 (lazy): only where the schedule reads it -- musb200_aux_probe and musb200_aux_download
@@ -310,6 +321,11 @@ int musb200_set_graphs(int flag);
  * bcBuffer snapshot; 0: always the reference's two phases (fill_bcBuffer, then the link loops).
  * Identical results; the fused form saves two launches and the snapshot traffic per step. */
 int musb200_set_fused_bc(int flag);
+/* 1 (default): the coarse -> fine interpolation (fillFinerGhostsFromMe_*, all orders) runs tile by
+ * tile: consecutive targets whose sources -- the children of a parent share one neighbourhood --
+ * fit a shared-memory tile are evaluated from one staged copy of those sources; 0: one thread per
+ * (target, direction) gathering its sources from global memory.  Identical results. */
+int musb200_set_intp_tiled(int flag);
 int musb200_synchronize(void);
 
 /* check_density / check_flow_status (mus_tools_module.f90:224-313):

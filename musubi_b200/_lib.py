@@ -60,6 +60,7 @@ SIGNATURES = {
     "musb200_intp_register": [c_int, c_int, c_int, c_int, P_I32, P_I32, P_I32, P_DBL, P_I32, c_int,
                               P_I32, P_DBL, P_DBL],
     "musb200_step": [c_int, c_int, c_int],
+    "musb200_step_schemes": [c_int, P_INT, c_int, c_int, c_int],
     "musb200_set_aux_every_step": [c_int],
     "musb200_fill_helper_elements": [c_int, c_int],
     "musb200_synchronize": [],
@@ -74,6 +75,7 @@ SIGNATURES = {
     "musb200_set_exchange_timeout": [c_double],
     "musb200_set_graphs": [c_int],
     "musb200_set_fused_bc": [c_int],
+    "musb200_set_intp_tiled": [c_int],
     "musb200_p2p_export": [c_int, c_void_p],
     "musb200_p2p_connect": [c_int, c_int, P_I32, c_void_p, P_I32, P_I32],
     "musb200_p2p_enable": [c_int, c_int],

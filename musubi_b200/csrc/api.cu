@@ -422,6 +422,7 @@ static HaloWait haloWait(Level &L, bool forSweep) {
   PeerLink &P = L.p2p;
   HaloWait w{};
   w.ctaMask = forSweep ? P.ctaMask.p : nullptr;
+  w.haloStart = L.nFluid + L.nGFC + L.nGFF;
   w.arrived = P.arrived.p;
   w.exch = P.exch.p;
   w.nRecvPeers = (int)P.recvRank.size();
@@ -631,28 +632,31 @@ static IntpArgs intpArgs(Level &src, Level &tgt) {
   return a;
 }
 
-static int applyIntp(Level &src, Level &tgt, IntpSet &set, bool fromFiner) {
+static int applyIntp(Level &src, Level &tgt, IntpSet &set, bool fromFiner, bool withAux = false) {
   if (set.nTargets == 0) return 0;
-  if (!tgt.viscSet && tgt.elemOmega)
+  if (!tgt.viscSet && tgt.elemOmega && tgt.kind != MUSB200_KIND_PASSIVE_SCALAR)
     return setError(MUSB200_ERR_STATE, "per-element omega needs musb200_set_viscosity for interpolation");
   Timed t(T_INTP);
   int n = 0;
   IntpArgs ia = intpArgs(src, tgt);
-  ia.withAux = fromFiner;
+  ia.withAux = withAux;
+  // a passive scalar's ghosts: the reference's interpolation of arbitrary values applied to the
+  // PDFs themselves (fillArbiMyGhostsFromFiner_avg / fillArbiFinerGhostsFromMe_*), no f_eq / f_neq split
+  ia.passive = tgt.kind == MUSB200_KIND_PASSIVE_SCALAR;
   MUSB_TRY(launchIntp(ia, set, fromFiner, g.stream, &n));
   g.launches += n;
   return 0;
 }
 
-static int levelStep(int iLevel, int minLevel, int maxLevel, bool lastCycle) {
+// one level step of ONE scheme without the ghost interpolation: set_boundary -> swap -> fused
+// auxField + stream + collide -> halo exchange (steps 3-9 of do_fast_singleLevel / the body of
+// do_recursive_multiLevel, mus/source/mus_control_module.f90:242-497, 507-701)
+static int levelAdvance(int iLevel, int minLevel, int maxLevel, bool lastCycle) {
   Level *Lp = findLevel(iLevel);
   if (!Lp) return setError(MUSB200_ERR_ARG, "level " + std::to_string(iLevel) + " was not created");
   Level &L = *Lp;
   const bool multi = (maxLevel > minLevel);
-  if (iLevel < maxLevel) {
-    // nNesting = 2 (acoustic scaling, mus_param_module.f90:191-195)
-    for (int n = 0; n < 2; ++n) MUSB_TRY(levelStep(iLevel + 1, minLevel, maxLevel, lastCycle && n == 1));
-  }
+  const bool passive = L.kind == MUSB200_KIND_PASSIVE_SCALAR;
   MUSB_TRY(setBoundary(L));
   if (!g.capturing && L.bcElems.n) MUSB_CUDA(cudaEventRecord(g.evBcDone, g.stream));
   std::swap(L.nNow, L.nNext);
@@ -661,7 +665,7 @@ static int levelStep(int iLevel, int minLevel, int maxLevel, bool lastCycle) {
   // schedule reads it; musb200_aux_probe / _download compute it on demand)
   const bool writeAux = g.auxEveryStep == 1 || multi || (lastCycle && g.auxEveryStep != 2) || L.auxForBc;
   L.auxValid = writeAux;
-  if (!multi && g.nranks > 1 && g.overlap && L.nSendElems > 0) {
+  if (!multi && g.nranks > 1 && g.overlap && L.nSendElems > 0 && !passive) {
     // single level, several ranks: sweep the send-halo elements first, then exchange them on the
     // communication stream while the remaining elements are swept (the reference exchanges
     // strictly after compute, mus_control_module.f90:605-649; results are identical because the
@@ -678,27 +682,72 @@ static int levelStep(int iLevel, int minLevel, int maxLevel, bool lastCycle) {
   // single level on several ranks with the peer-memory exchange: the sweep pushes the halo links
   // itself (the force-source variant of the sweep keeps the separate push kernel)
   const bool pushed = !multi && g.nranks > 1 && g.fusedPush && L.p2p.on && L.forceOrder == 0 &&
-                      L.kind != MUSB200_KIND_PASSIVE_SCALAR && L.p2p.pushMask.n > 0;
+                      !passive && L.p2p.pushMask.n > 0;
   MUSB_TRY(sweep(L, writeAux, SWEEP_ALL, pushed));
   // auxField of my ghostFromFiner elements <- average of level+1
   // (mus_intpAuxFieldCoarserAndExchange, mus_auxField_module.f90:404-444) is taken inside the
   // from-finer interpolation kernel below: same sources, and on one rank nothing reads those
   // entries before the from-coarser interpolation, which runs after it
-  if (multi && writeAux) MUSB_TRY(exchangeStateAndAux(L));   // state (tag level) + aux (tag level+100)
+  if (multi && writeAux && !passive) MUSB_TRY(exchangeStateAndAux(L));   // state (tag level) + aux (tag level+100)
   else MUSB_TRY(exchange(L, MUSB200_BUF_HALO, L.state[L.nNext].p, L.QQ, nullptr, pushed, /*deferWait=*/!multi));
   if (iLevel > minLevel) MUSB_TRY(exchange(L, MUSB200_BUF_FROMCOARSER, L.state[L.nNext].p, L.QQ));
-  if (iLevel < maxLevel) {
-    Level *F = findLevel(iLevel + 1);
-    // do_intpFinerAndExchange: my ghostFromFiner <- average over the children on level+1
-    MUSB_TRY(applyIntp(*F, L, L.fromFiner, true));
-    // ghostFromFiner elements another rank interpolated for me arrive with their auxField entries
-    // (the from-coarser interpolation below reads them when such a ghost is one of its sources)
-    MUSB_TRY(exchangeStateAndAux(L, MUSB200_BUF_FROMFINER));
-    // do_intpCoarserAndExchange: ghostFromCoarser of level+1 <- me, orders 0..order
-    for (auto &set : F->fromCoarser) MUSB_TRY(applyIntp(L, *F, set, false));
-    MUSB_TRY(exchange(*F, MUSB200_BUF_FROMCOARSER, F->state[F->nNext].p, F->QQ));
-  }
   return 0;
+}
+
+// the ghost interpolation that closes a level step (do_intpFinerAndExchange,
+// do_intpCoarserAndExchange, mus_control_module.f90:861-1051)
+static int levelInterpolate(int iLevel, int maxLevel) {
+  if (iLevel >= maxLevel) return 0;
+  Level &L = *findLevel(iLevel);
+  Level *F = findLevel(iLevel + 1);
+  const bool passive = L.kind == MUSB200_KIND_PASSIVE_SCALAR;
+  // do_intpFinerAndExchange: my ghostFromFiner <- average over the children on level+1
+  MUSB_TRY(applyIntp(*F, L, L.fromFiner, true, !passive));
+  // ghostFromFiner elements another rank interpolated for me arrive with their auxField entries
+  // (the from-coarser interpolation below reads them when such a ghost is one of its sources)
+  if (passive) MUSB_TRY(exchange(L, MUSB200_BUF_FROMFINER, L.state[L.nNext].p, L.QQ));
+  else MUSB_TRY(exchangeStateAndAux(L, MUSB200_BUF_FROMFINER));
+  // do_intpCoarserAndExchange: ghostFromCoarser of level+1 <- me, orders 0..order
+  for (auto &set : F->fromCoarser) MUSB_TRY(applyIntp(L, *F, set, false));
+  MUSB_TRY(exchange(*F, MUSB200_BUF_FROMCOARSER, F->state[F->nNext].p, F->QQ));
+  return 0;
+}
+
+// the schemes stepped together (default: the bound slot alone).  Several schemes on one mesh
+// -- a passive scalar transported by a flow, BASELINE config 5 -- advance level step by level
+// step in the order given, so that the scalar's sweep reads the auxField the flow's sweep of the
+// SAME level step has just written; then each scheme interpolates its ghosts.
+static int gStepSlots[Context::kSlots] = {0, 0, 0, 0};
+static int gNStepSlots = 0;   // 0: the bound slot only
+
+// every scheme stepped by this call, one after the other, with `slot` bound
+template <class F>
+static int forEachStepSlot(F f) {
+  if (gNStepSlots == 0) return f();
+  const int keep = g.slot;
+  int rc = 0;
+  for (int k = 0; k < gNStepSlots && rc == 0; ++k) { g.slot = gStepSlots[k]; rc = f(); }
+  g.slot = keep;
+  return rc;
+}
+
+
+static int levelStep(int iLevel, int minLevel, int maxLevel, bool lastCycle) {
+  if (!findLevel(iLevel)) return setError(MUSB200_ERR_ARG, "level " + std::to_string(iLevel) + " was not created");
+  if (iLevel < maxLevel) {
+    // nNesting = 2 (acoustic scaling, mus_param_module.f90:191-195)
+    for (int n = 0; n < 2; ++n) MUSB_TRY(levelStep(iLevel + 1, minLevel, maxLevel, lastCycle && n == 1));
+  }
+  if (gNStepSlots == 0) {
+    MUSB_TRY(levelAdvance(iLevel, minLevel, maxLevel, lastCycle));
+    return levelInterpolate(iLevel, maxLevel);
+  }
+  const int keep = g.slot;
+  int rc = 0;
+  for (int k = 0; k < gNStepSlots && rc == 0; ++k) { g.slot = gStepSlots[k]; rc = levelAdvance(iLevel, minLevel, maxLevel, lastCycle); }
+  for (int k = 0; k < gNStepSlots && rc == 0; ++k) { g.slot = gStepSlots[k]; rc = levelInterpolate(iLevel, maxLevel); }
+  g.slot = keep;
+  return rc;
 }
 
 // Failure detection at the points where the host synchronises anyway (the reference aborts all
@@ -736,7 +785,7 @@ static int fillFineToCoarse(int iLevel, int minLevel, int maxLevel) {
     Level *F = findLevel(iLevel + 1);
     // state and auxField of my ghostFromFiner elements <- average over the children
     // (do_intp of fillMineFromFiner + mus_intpAuxFieldCoarserAndExchange)
-    MUSB_TRY(applyIntp(*F, *L, L->fromFiner, true));
+    MUSB_TRY(applyIntp(*F, *L, L->fromFiner, true, L->kind != MUSB200_KIND_PASSIVE_SCALAR));
     MUSB_TRY(exchangeStateAndAux(*L, MUSB200_BUF_FROMFINER));
   }
   if (multi || L->nAux == 4) MUSB_TRY(exchangeStateAndAux(*L));
@@ -1707,13 +1756,22 @@ int musb200_set_aux_every_step(int flag) {
 // stepping loop of a small or multi-level mesh is launch-bound (64^3: 19 us of kernel per 22 us
 // step; a two-level cycle is 7 launches).  Several ranks stay on direct launches: the peer-memory
 // exchange carries a running exchange number as a kernel argument.
+// identifies what a captured graph steps: the bound slot, or the list of coupled slots
+static int stepSlotKey() {
+  if (gNStepSlots == 0) return g.slot;
+  int key = 1000;
+  for (int k = 0; k < gNStepSlots; ++k) key = key * 8 + gStepSlots[k] + 1;
+  return key;
+}
+
 static int stepGraphed(int minLevel, int maxLevel, int nPairs) {
   // the captured kernel arguments hold the now/next buffers of the capture: a replay must start
   // from the same parity of the coarsest level (finer levels toggle twice per cycle; an explicit
   // musb200_set_now_next bumps the epoch)
-  const int parity = findLevel(minLevel)->nNow;
+  int parity = 0, nth = 0;
+  forEachStepSlot([&] { parity |= findLevel(minLevel)->nNow << nth++; return 0; });
   if (!g.graphExec || g.graphEpoch != g.epoch || g.graphMin != minLevel || g.graphMax != maxLevel ||
-      g.graphSlot != g.slot || g.graphParity != parity) {
+      g.graphSlot != stepSlotKey() || g.graphParity != parity) {
     dropGraph();
     const long long before = g.launches;
     const int auxSave = g.auxEveryStep;
@@ -1724,11 +1782,13 @@ static int stepGraphed(int minLevel, int maxLevel, int nPairs) {
     // single level on several ranks: a replay follows a replay whose last push nobody has waited
     // for, so the FIRST sweep of the pair must carry the wait as well (it passes at once when
     // nothing is in flight)
-    if (g.nranks > 1 && maxLevel == minLevel) {
-      Level *L0 = findLevel(minLevel);
-      if (L0->p2p.on && (L0->send[MUSB200_BUF_HALO].total > 0 || L0->recv[MUSB200_BUF_HALO].total > 0))
-        L0->p2p.pendingWait = true;
-    }
+    if (g.nranks > 1 && maxLevel == minLevel)
+      forEachStepSlot([&] {
+        Level *L0 = findLevel(minLevel);
+        if (L0->p2p.on && (L0->send[MUSB200_BUF_HALO].total > 0 || L0->recv[MUSB200_BUF_HALO].total > 0))
+          L0->p2p.pendingWait = true;
+        return 0;
+      });
     for (int it = 0; it < 2 && rc == 0; ++it) rc = levelStep(minLevel, minLevel, maxLevel, false);
     g.capturing = false;
     cudaError_t ce = cudaStreamEndCapture(g.stream, &graph);
@@ -1742,7 +1802,7 @@ static int stepGraphed(int minLevel, int maxLevel, int nPairs) {
     MUSB_CUDA(ce);
     // capturing ran the host side of two cycles: every level toggled now/next an even number of
     // times, so the indices are where they were and nothing was executed yet
-    g.graphEpoch = g.epoch; g.graphMin = minLevel; g.graphMax = maxLevel; g.graphSlot = g.slot;
+    g.graphEpoch = g.epoch; g.graphMin = minLevel; g.graphMax = maxLevel; g.graphSlot = stepSlotKey();
     g.graphParity = parity;
   }
   for (int p = 0; p < nPairs; ++p) {
@@ -1750,56 +1810,94 @@ static int stepGraphed(int minLevel, int maxLevel, int nPairs) {
     g.launches += g.graphLaunches;
   }
   if (nPairs > 0 && g.nranks > 1)
-    for (int l = minLevel; l <= maxLevel; ++l) {
-      Level *Lp = findLevel(l);
-      if (Lp->p2p.on && (Lp->send[MUSB200_BUF_HALO].total > 0 || Lp->recv[MUSB200_BUF_HALO].total > 0))
-        Lp->p2p.pendingWait = (maxLevel == minLevel);   // multi-level pushes are followed by their wait
-    }
+    forEachStepSlot([&] {
+      for (int l = minLevel; l <= maxLevel; ++l) {
+        Level *Lp = findLevel(l);
+        if (Lp->p2p.on && (Lp->send[MUSB200_BUF_HALO].total > 0 || Lp->recv[MUSB200_BUF_HALO].total > 0))
+          Lp->p2p.pendingWait = (maxLevel == minLevel);   // multi-level pushes are followed by their wait
+      }
+      return 0;
+    });
   return 0;   // two cycles leave every level's now/next parity unchanged
 }
 
+static int stepImpl(int minLevel, int maxLevel, int nCoarseCycles);
+
 int musb200_step(int minLevel, int maxLevel, int nCoarseCycles) {
   MUSB_TRY(needReady());
+  gNStepSlots = 0;
+  return stepImpl(minLevel, maxLevel, nCoarseCycles);
+}
+
+int musb200_step_schemes(int nSlots, const int *slots, int minLevel, int maxLevel, int nCoarseCycles) {
+  MUSB_TRY(needReady());
+  if (nSlots < 1 || nSlots > Context::kSlots || !slots) return setError(MUSB200_ERR_ARG, "bad scheme slot list");
+  for (int k = 0; k < nSlots; ++k) {
+    if (slots[k] < 0 || slots[k] >= Context::kSlots) return setError(MUSB200_ERR_ARG, "scheme slot out of range");
+    for (int j = 0; j < k; ++j)
+      if (slots[j] == slots[k]) return setError(MUSB200_ERR_ARG, "scheme slot listed twice");
+    gStepSlots[k] = slots[k];
+  }
+  gNStepSlots = nSlots;
+  const int keep = g.slot;
+  g.slot = slots[0];
+  const int rc = stepImpl(minLevel, maxLevel, nCoarseCycles);
+  g.slot = keep;
+  gNStepSlots = 0;
+  return rc;
+}
+
+static int stepImpl(int minLevel, int maxLevel, int nCoarseCycles) {
   if (maxLevel < minLevel || nCoarseCycles < 0) return setError(MUSB200_ERR_ARG, "bad level range / cycles");
   int it = 0;
   // several ranks: capturable when every exchange of the range goes through peer memory (its
   // kernels keep the exchange number on the device; NCCL calls stay outside graphs)
   bool capturable = true;
+  MUSB_TRY(forEachStepSlot([&] {
+    for (int l = minLevel; l <= maxLevel; ++l)
+      if (!findLevel(l))
+        return setError(MUSB200_ERR_ARG, "level " + std::to_string(l) + " was not created (scheme slot " +
+                                             std::to_string(g.slot) + ")");
+    return 0;
+  }));
   if (g.nranks > 1) {
     if (g.overlap) capturable = false;
-    for (int l = minLevel; l <= maxLevel && capturable; ++l) {
-      Level *Lc = findLevel(l);
-      if (!Lc) break;
-      for (int k = 0; k < 3; ++k) {
-        const bool any = Lc->send[k].total > 0 || Lc->recv[k].total > 0;
-        if (any && !(k == MUSB200_BUF_HALO && Lc->p2p.on)) capturable = false;
+    forEachStepSlot([&] {
+      for (int l = minLevel; l <= maxLevel; ++l) {
+        Level *Lc = findLevel(l);
+        for (int k = 0; k < 3; ++k) {
+          const bool any = Lc->send[k].total > 0 || Lc->recv[k].total > 0;
+          if (any && !(k == MUSB200_BUF_HALO && Lc->p2p.on)) capturable = false;
+        }
       }
-    }
+      return 0;
+    });
   }
   if (g.useGraphs && capturable && !g.profiling && nCoarseCycles >= 8) {
     // all but the last cycles (the last one materialises auxField) in pairs through the graph
     const int nPairs = (nCoarseCycles - 1) / 2;
-    for (int l = minLevel; l <= maxLevel; ++l) {
-      Level *Lg = findLevel(l);
-      if (!Lg) return setError(MUSB200_ERR_ARG, "level " + std::to_string(l) + " was not created");
-      MUSB_TRY(applyPendingBc(*Lg));   // cross-stream waits stay outside the capture
-    }
+    MUSB_TRY(forEachStepSlot([&] {
+      for (int l = minLevel; l <= maxLevel; ++l) MUSB_TRY(applyPendingBc(*findLevel(l)));   // cross-stream waits stay outside the capture
+      return 0;
+    }));
     MUSB_TRY(stepGraphed(minLevel, maxLevel, nPairs));
-    for (int l = minLevel; l <= maxLevel; ++l) {
-      Level *Lg = findLevel(l);
-      if (Lg->bcElems.n) MUSB_CUDA(cudaEventRecord(g.evBcDone, g.stream));
-      Lg->auxValid = (maxLevel > minLevel) || g.auxEveryStep == 1 || Lg->auxForBc;
-    }
+    MUSB_TRY(forEachStepSlot([&] {
+      for (int l = minLevel; l <= maxLevel; ++l) {
+        Level *Lg = findLevel(l);
+        if (Lg->bcElems.n) MUSB_CUDA(cudaEventRecord(g.evBcDone, g.stream));
+        Lg->auxValid = (maxLevel > minLevel) || g.auxEveryStep == 1 || Lg->auxForBc;
+      }
+      return 0;
+    }));
     it = 2 * nPairs;
   }
   for (; it < nCoarseCycles; ++it)
     MUSB_TRY(levelStep(minLevel, minLevel, maxLevel, it == nCoarseCycles - 1));
   // MPI_Waitall of the last exchange: whatever follows this call sees complete halo rows
-  for (int l = minLevel; l <= maxLevel; ++l) {
-    Level *Lw = findLevel(l);
-    if (Lw) MUSB_TRY(ensureArrived(*Lw));
-  }
-  return 0;
+  return forEachStepSlot([&] {
+    for (int l = minLevel; l <= maxLevel; ++l) MUSB_TRY(ensureArrived(*findLevel(l)));
+    return 0;
+  });
 }
 
 int musb200_fill_helper_elements(int minLevel, int maxLevel) {
@@ -1846,6 +1944,12 @@ int musb200_set_exchange_timeout(double seconds) {
   if (!(seconds >= 0.0)) return setError(MUSB200_ERR_ARG, "timeout must be >= 0 (0 = wait for ever)");
   ++g.epoch;
   g.timeoutNs = (unsigned long long)(seconds * 1.0e9);
+  return 0;
+}
+
+int musb200_set_intp_tiled(int flag) {
+  ++g.epoch;
+  g_intpTargetMajor = flag ? 0 : 1;
   return 0;
 }
 

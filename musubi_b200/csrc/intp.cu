@@ -9,8 +9,8 @@ namespace musb200 {
 void IntpSet::release() {
   auto fr = [](auto *&p) { if (p) cudaFree(p); p = nullptr; };
   fr(targets); fr(srcOffset); fr(srcSlot); fr(uniqueSrc); fr(weights); fr(posInMat); fr(matOffset);
-  fr(matrices); fr(coord); fr(scratch);
-  nTargets = 0; nMatrices = 0; nUnique = 0; maxSrc = 0;
+  fr(matrices); fr(matricesT); fr(matOffsetT); fr(coord); fr(scratch); fr(tileTarget); fr(tileSrcStart); fr(tileSrc); fr(localSrc);
+  nTargets = 0; nMatrices = 0; nUnique = 0; maxSrc = 0; nTiles = 0;
 }
 
 IntpSet &IntpSet::operator=(IntpSet &&o) noexcept {
@@ -19,8 +19,12 @@ IntpSet &IntpSet::operator=(IntpSet &&o) noexcept {
     order = o.order; nTargets = o.nTargets; nMatrices = o.nMatrices; nUnique = o.nUnique;
     targets = o.targets; srcOffset = o.srcOffset; srcSlot = o.srcSlot; uniqueSrc = o.uniqueSrc;
     weights = o.weights; posInMat = o.posInMat; matOffset = o.matOffset; matrices = o.matrices;
-    coord = o.coord; scratch = o.scratch;
+    coord = o.coord; scratch = o.scratch; matricesT = o.matricesT; o.matricesT = nullptr;
+    matOffsetT = o.matOffsetT; o.matOffsetT = nullptr;
     maxSrc = o.maxSrc; o.maxSrc = 0;
+    nTiles = o.nTiles; o.nTiles = 0;
+    tileTarget = o.tileTarget; tileSrcStart = o.tileSrcStart; tileSrc = o.tileSrc; localSrc = o.localSrc;
+    o.tileTarget = nullptr; o.tileSrcStart = nullptr; o.tileSrc = nullptr; o.localSrc = nullptr;
     o.targets = nullptr; o.srcOffset = nullptr; o.srcSlot = nullptr; o.uniqueSrc = nullptr;
     o.weights = nullptr; o.posInMat = nullptr; o.matOffset = nullptr; o.matrices = nullptr;
     o.coord = nullptr; o.scratch = nullptr;
@@ -69,6 +73,30 @@ int registerIntp(IntpSet &set, int order, int nTargets, const int32_t *targetLis
     rc |= up(set.posInMat, posInMat, nTargets, st);
     rc |= up(set.matOffset, matOffset, (size_t)nMatrices + 1, st);
     rc |= up(set.matrices, matrices, (size_t)matOffset[nMatrices], st);
+    {
+      // the same matrices transposed, [s][k]: the nCoeff coefficients of a source side by side,
+      // every matrix at an even offset (16-byte aligned pairs)
+      const int nc = order == 1 ? 4 : 10;
+      std::vector<double> mt;
+      std::vector<int32_t> offT((size_t)nMatrices + 1, 0);
+      for (int mI = 0; mI < nMatrices; ++mI) {
+        const int off = matOffset[mI], len = matOffset[mI + 1] - off;
+        offT[mI] = (int32_t)mt.size();
+        if (len % nc == 0) {                   // else: the 1 x 1 placeholder of a singular set, never referenced
+          const int nS = len / nc;
+          mt.resize(mt.size() + (size_t)len);
+          for (int k = 0; k < nc; ++k)
+            for (int sI = 0; sI < nS; ++sI)
+              mt[(size_t)offT[mI] + (size_t)sI * nc + k] = matrices[(size_t)off + (size_t)k * nS + sI];
+        }
+        if (mt.size() & 1u) mt.push_back(0.0);
+      }
+      offT[nMatrices] = (int32_t)mt.size();
+      if (mt.empty()) mt.push_back(0.0);
+      rc |= up(set.matricesT, mt.data(), mt.size(), st);
+      rc |= up(set.matOffsetT, offT.data(), offT.size(), st);
+      MUSB_CUDA(cudaStreamSynchronize(st));
+    }
     rc |= up(set.coord, childCoord, (size_t)3 * nTargets, st);
   }
   if (rc) return rc;
@@ -77,6 +105,40 @@ int registerIntp(IntpSet &set, int order, int nTargets, const int32_t *targetLis
   for (int i = 0; i < nTargets; ++i) set.maxSrc = std::max(set.maxSrc, srcOffset[i + 1] - srcOffset[i]);
   set.nMatrices = nMatrices;
   set.nUnique = (int)uniq.size();
+  {
+    // tiles: greedily pack consecutive targets while the union of their sources stays within
+    // kTileSrc and the tile within kTileTgt targets
+    std::vector<int32_t> tileTarget{0}, tileSrcStart{0}, tileSrc;
+    std::vector<uint8_t> local((size_t)nSrc);
+    std::vector<int32_t> where((size_t)set.nUnique, -1);   // slot -> index in the current tile
+    std::vector<int32_t> cur;
+    auto flush = [&](int nextTarget) {
+      for (int32_t sl : cur) where[sl] = -1;
+      tileSrc.insert(tileSrc.end(), cur.begin(), cur.end());
+      cur.clear();
+      tileTarget.push_back(nextTarget);
+      tileSrcStart.push_back((int32_t)tileSrc.size());
+    };
+    for (int i = 0; i < nTargets; ++i) {
+      int add = 0;
+      for (int j = srcOffset[i]; j < srcOffset[i + 1]; ++j)
+        if (where[slot[j]] < 0) ++add;
+      if ((int)cur.size() + add > kTileSrc || i - tileTarget.back() >= kTileTgt) flush(i);
+      for (int j = srcOffset[i]; j < srcOffset[i + 1]; ++j) {
+        if (where[slot[j]] < 0) { where[slot[j]] = (int32_t)cur.size(); cur.push_back(slot[j]); }
+        local[j] = (uint8_t)where[slot[j]];
+      }
+    }
+    flush(nTargets);
+    set.nTiles = (int)tileTarget.size() - 1;
+    int rc2 = 0;
+    rc2 |= up(set.tileTarget, tileTarget.data(), tileTarget.size(), st);
+    rc2 |= up(set.tileSrcStart, tileSrcStart.data(), tileSrcStart.size(), st);
+    rc2 |= up(set.tileSrc, tileSrc.data(), tileSrc.size(), st);
+    rc2 |= up(set.localSrc, local.data(), local.size(), st);
+    if (rc2) return rc2;
+    MUSB_CUDA(cudaStreamSynchronize(st));  // the tile vectors go out of scope
+  }
   MUSB_CUDA(cudaMalloc(&set.scratch, (size_t)2 * 27 * set.nUnique * sizeof(double)));
   MUSB_CUDA(cudaStreamSynchronize(st));  // host vectors go out of scope
   return 0;
@@ -88,7 +150,7 @@ int registerIntp(IntpSet &set, int order, int nTargets, const int32_t *targetLis
 // shared-memory tile so that the global
 // stores of a CTA are one contiguous, fully coalesced run
 template <int QQ, int THREADS>
-__global__ void __launch_bounds__(THREADS) eqNeqKernel(int incomp, const double *__restrict__ sState,
+__global__ void __launch_bounds__(THREADS) eqNeqKernel(int incomp, int passive, const double *__restrict__ sState,
                             const double *__restrict__ sAux, long long sS,
                             const int32_t *__restrict__ uniqueSrc, int nUnique,
                             double *__restrict__ scratch) {
@@ -97,9 +159,14 @@ __global__ void __launch_bounds__(THREADS) eqNeqKernel(int incomp, const double 
   const int u = blockIdx.x * THREADS + threadIdx.x;
   if (u < nUnique) {
     const int e = uniqueSrc[u] - 1;
-    const double rho = sAux[e], vx = sAux[sS + e], vy = sAux[2 * sS + e], vz = sAux[3 * sS + e];
+    double rho = 0.0, vx = 0.0, vy = 0.0, vz = 0.0;
+    if (!passive) { rho = sAux[e]; vx = sAux[sS + e]; vy = sAux[2 * sS + e]; vz = sAux[3 * sS + e]; }
     double feq[QQ];
-    if (QQ == 19) {
+    if (passive) {
+      // arbitrary-value interpolation of the PDFs: the pair is {f, 0}
+#pragma unroll
+      for (int q = 0; q < QQ; ++q) feq[q] = sState[(long long)q * sS + e];
+    } else if (QQ == 19) {
       double(&g)[19] = reinterpret_cast<double(&)[19]>(feq);
       if (incomp) pdfEqIncompD3Q19(rho, vx, vy, vz, g);
       else pdfEqD3Q19(rho, vx, vy, vz, g);
@@ -112,7 +179,7 @@ __global__ void __launch_bounds__(THREADS) eqNeqKernel(int incomp, const double 
     for (int q = 0; q < QQ; ++q) {
       const double f = sState[(long long)q * sS + e];
       tile[threadIdx.x * P + 2 * q] = feq[q];
-      tile[threadIdx.x * P + 2 * q + 1] = f - feq[q];
+      tile[threadIdx.x * P + 2 * q + 1] = passive ? 0.0 : f - feq[q];
     }
   }
   __syncthreads();
@@ -193,13 +260,121 @@ __global__ void __launch_bounds__(128) intpKernel(int QQ, const double *__restri
   tState[(long long)d * tS + tgt] = t_neq + t_eq;
 }
 
+// The same interpolation organised around the SOURCES instead of the targets: the 8 children of a
+// coarse parent draw their sources from one <= 19 / 27 element neighbourhood, and neighbouring
+// parents share most of theirs.  A CTA takes a tile of consecutive targets (host-packed so that
+// the tile has at most kTileSrc distinct sources), copies the {f_eq, f_neq} rows of those sources
+// from the scratch into shared memory ONCE -- contiguous rows, fully coalesced -- and evaluates
+// every (target, direction) of the tile from there: the per-thread chain of dependent
+// slot -> value gathers through L1 (62 % of the L1 data pipe in the target-major kernel above,
+// profiles/r01_intp_cfg4.md) becomes shared-memory reads, and the L2 -> SM traffic drops from
+// nSrc rows per target to about one row per target.  Per (target, direction) the sources are
+// accumulated in the host's order exactly as above, so the bits are unchanged.  Results go
+// through shared memory once more so that the stores run along the targets (siblings are
+// consecutive in the total list): 64-byte segments instead of 8-byte scattered stores.
+template <int MODE, int D>
+__global__ void __launch_bounds__(128) intpTileKernel(int QQ, const double *__restrict__ scratch,
+                               const int32_t *__restrict__ tileTarget, const int32_t *__restrict__ tileSrcStart,
+                               const int32_t *__restrict__ tileSrc, const uint8_t *__restrict__ localSrc,
+                               const int32_t *__restrict__ targets, const int32_t *__restrict__ srcOffset,
+                               const double *__restrict__ weights, const int32_t *__restrict__ posInMat,
+                               const int32_t *__restrict__ matOffset, const double *__restrict__ matricesT,
+                               const double *__restrict__ coord, double *__restrict__ tState, long long tS,
+                               const double *__restrict__ tVisc, double tViscUniform) {
+  // One thread evaluates D consecutive directions of a target: the coefficients of a source
+  // (one 16-byte aligned group per source in the TRANSPOSED matrix, matricesT[s][k]) are loaded
+  // once and used for D directions -- the target-major kernel issues 6 loads per (source,
+  // direction), this one (3 + D) / D.
+  constexpr int nCoeff = MODE == 1 ? 1 : (MODE == 2 ? 4 : 10);
+  extern __shared__ double2 sm2[];                 // [kTileSrc][QQ] pairs | [QQ][kTileTgt] results
+  double *res = reinterpret_cast<double *>(sm2 + kTileSrc * QQ);
+  const int t0 = tileTarget[blockIdx.x], nT = tileTarget[blockIdx.x + 1] - t0;
+  const int u0 = tileSrcStart[blockIdx.x], nU = tileSrcStart[blockIdx.x + 1] - u0;
+  const double2 *sc2 = reinterpret_cast<const double2 *>(scratch);
+  for (int idx = threadIdx.x; idx < nU * QQ; idx += blockDim.x) {
+    const int r = idx / QQ, d = idx - r * QQ;
+    sm2[idx] = sc2[(long long)tileSrc[u0 + r] * QQ + d];
+  }
+  __syncthreads();
+  const int nG = (QQ + D - 1) / D;
+  for (int p = threadIdx.x; p < nT * nG; p += blockDim.x) {
+    const int il = p / nG, d0 = (p - il * nG) * D;
+    const int nd = min(D, QQ - d0);
+    const int i = t0 + il;
+    const int s0 = srcOffset[i], n = srcOffset[i + 1] - s0;
+    const double *A = MODE == 1 ? weights + s0 : matricesT + matOffset[posInMat[i]];
+    double ce[D][nCoeff], cn[D][nCoeff];
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+#pragma unroll
+      for (int k = 0; k < nCoeff; ++k) { ce[j][k] = 0.0; cn[j][k] = 0.0; }
+    for (int s = 0; s < n; ++s) {
+      double m[nCoeff];
+      if (MODE == 1) {
+        m[0] = A[s];
+      } else {
+        const double2 *As = reinterpret_cast<const double2 *>(A + s * nCoeff);   // 16-byte aligned
+#pragma unroll
+        for (int k = 0; k < nCoeff; k += 2) { const double2 t = As[k >> 1]; m[k] = t.x; m[k + 1] = t.y; }
+      }
+      const double2 *row = sm2 + (int)localSrc[s0 + s] * QQ + d0;
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        if (j < nd) {
+          const double2 v = row[j];
+#pragma unroll
+          for (int k = 0; k < nCoeff; ++k) {   // per coefficient the sum over the sources, in the host's order
+            ce[j][k] = ce[j][k] + m[k] * v.x;
+            cn[j][k] = cn[j][k] + m[k] * v.y;
+          }
+        }
+      }
+    }
+    double fac;   // 0.5 * getNonEqFac_intp_coarse_to_fine
+    if (tVisc) {
+      const double visc = tVisc[targets[i] - 1];
+      fac = 0.5 * neqFac(omegaFromVisc(0.5 * visc), omegaFromVisc(visc));
+    } else {
+      fac = tViscUniform;   // the factor itself, evaluated by the launcher with the same expression
+    }
+    double x = 0.0, y = 0.0, z = 0.0;
+    if (MODE != 1) { x = coord[3 * i + 0]; y = coord[3 * i + 1]; z = coord[3 * i + 2]; }
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      if (j < nd) {
+        double t_eq, t_neq;
+        if (MODE == 1) {
+          t_eq = ce[j][0];
+          t_neq = cn[j][0];
+        } else {
+          t_eq = ce[j][0] + ce[j][1] * x + ce[j][2] * y + ce[j][3] * z;
+          t_neq = cn[j][0] + cn[j][1] * x + cn[j][2] * y + cn[j][3] * z;
+          if (MODE == 3) {
+            t_eq = t_eq + ce[j][4 % nCoeff] * x * x + ce[j][5 % nCoeff] * y * y + ce[j][6 % nCoeff] * z * z +
+                   ce[j][7 % nCoeff] * x * y + ce[j][8 % nCoeff] * y * z + ce[j][9 % nCoeff] * z * x;
+            t_neq = t_neq + cn[j][4 % nCoeff] * x * x + cn[j][5 % nCoeff] * y * y + cn[j][6 % nCoeff] * z * z +
+                    cn[j][7 % nCoeff] * x * y + cn[j][8 % nCoeff] * y * z + cn[j][9 % nCoeff] * z * x;
+          }
+        }
+        t_neq = t_neq * fac;
+        res[(d0 + j) * kTileTgt + il] = t_neq + t_eq;
+      }
+    }
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < nT * QQ; p += blockDim.x) {
+    const int d = p / nT, il = p - d * nT;
+    tState[(long long)d * tS + (targets[t0 + il] - 1)] = res[d * kTileTgt + il];
+  }
+}
+
 // fillMyGhostsFromFiner_avg_feq_fneq without a scratch pass: 8 lanes per coarse ghost, one lane per
 // child (the children are Morton-contiguous fine elements: coalesced loads).  Each lane forms
 // f_eq(rho, u from auxField) and f - f_eq of its child and parks them in shared memory; the lanes
 // of the group then share the QQ directions, each summing its directions over the children in
 // the children's order, a = (..((c1 + c2) + c3)..), as the reference's loop does.
 template <int QQ, int THREADS>
-__global__ void __launch_bounds__(THREADS) fromFinerFusedKernel(int incomp, const double *__restrict__ sState,
+__global__ void __launch_bounds__(THREADS) fromFinerFusedKernel(int incomp, int passive, const double *__restrict__ sState,
                                      const double *__restrict__ sAux, long long sS,
                                      const int32_t *__restrict__ uniqueSrc, int nTargets,
                                      const int32_t *__restrict__ targets,
@@ -219,11 +394,16 @@ __global__ void __launch_bounds__(THREADS) fromFinerFusedKernel(int incomp, cons
   if (valid) { s0 = srcOffset[i]; n = srcOffset[i + 1] - s0; tgt = targets[i] - 1; }
   if (c < n) {
     const int e = uniqueSrc[srcSlot[s0 + c]] - 1;
-    const double rho = sAux[e], vx = sAux[sS + e], vy = sAux[2 * sS + e], vz = sAux[3 * sS + e];
+    double rho = 0.0, vx = 0.0, vy = 0.0, vz = 0.0;
+    if (!passive) { rho = sAux[e]; vx = sAux[sS + e]; vy = sAux[2 * sS + e]; vz = sAux[3 * sS + e]; }
     double f[QQ], eq[QQ];
 #pragma unroll
     for (int q = 0; q < QQ; ++q) f[q] = sState[(long long)q * sS + e];
-    if (QQ == 19) {
+    if (passive) {
+      // fillArbiMyGhostsFromFiner_avg applied to the PDFs: plain average, {f, 0}
+#pragma unroll
+      for (int q = 0; q < QQ; ++q) eq[q] = f[q];
+    } else if (QQ == 19) {
       double(&g)[19] = reinterpret_cast<double(&)[19]>(eq);
       if (incomp) pdfEqIncompD3Q19(rho, vx, vy, vz, g);
       else pdfEqD3Q19(rho, vx, vy, vz, g);
@@ -236,7 +416,7 @@ __global__ void __launch_bounds__(THREADS) fromFinerFusedKernel(int incomp, cons
 #pragma unroll
     for (int q = 0; q < QQ; ++q) {
       row[q] = eq[q];
-      row[QQ + q] = f[q] - eq[q];
+      row[QQ + q] = passive ? 0.0 : f[q] - eq[q];
     }
     row[W] = rho; row[W + 1] = vx; row[W + 2] = vy; row[W + 3] = vz;
   }
@@ -245,7 +425,7 @@ __global__ void __launch_bounds__(THREADS) fromFinerFusedKernel(int incomp, cons
   const double visc = tVisc ? tVisc[tgt] : tViscUniform;
   const double inv_n = 1.0 / (double)n;
   const double fOmega = omegaFromVisc(2.0 * visc), cOmega = omegaFromVisc(visc);
-  const double fac = 2.0 * neqFac(fOmega, cOmega);  // getNonEqFac_intp_fine_to_coarse
+  const double fac = passive ? 0.0 : 2.0 * neqFac(fOmega, cOmega);  // getNonEqFac_intp_fine_to_coarse
   const double *grp = tile + (threadIdx.x & ~7) * P;   // rows of my group's children
   for (int q = c; q < QQ; q += 8) {
     double a = 0.0, b = 0.0;
@@ -264,6 +444,9 @@ __global__ void __launch_bounds__(THREADS) fromFinerFusedKernel(int incomp, cons
   }
 }
 
+// 1: the target-major kernel (kept for comparison and as the reference of the tiled one)
+int g_intpTargetMajor = 0;
+
 // host copies of omegaFromVisc / neqFac: IEEE double on both sides, identical bits
 static double hostOmega(double v) { return 1.0 / (3.0 * v + 0.5); }
 static double hostNeqFac(double omegaS, double omegaT) { return omegaS * (1.0 - omegaT) / ((1.0 - omegaS) * omegaT); }
@@ -276,34 +459,51 @@ int launchIntp(const IntpArgs &a, const IntpSet &set, bool fromFiner, cudaStream
     if (set.maxSrc > 8) return setError(1, "a ghostFromFiner element has more than 8 children");
     if (a.QQ == 19)   // 128 threads x 43 doubles = 44 KB of shared memory
       fromFinerFusedKernel<19, 128><<<divUp((long long)set.nTargets * 8, 128), 128, 0, st>>>(
-          a.incomp, a.sState, a.sAux, a.sS, set.uniqueSrc, set.nTargets, set.targets, set.srcOffset,
+          a.incomp, a.passive ? 1 : 0, a.sState, a.sAux, a.sS, set.uniqueSrc, set.nTargets, set.targets, set.srcOffset,
           set.srcSlot, a.tState, a.withAux ? a.tAux : nullptr, a.tS, a.tVisc, a.tViscUniform);
     else              // 64 threads x 59 doubles = 30 KB
       fromFinerFusedKernel<27, 64><<<divUp((long long)set.nTargets * 8, 64), 64, 0, st>>>(
-          a.incomp, a.sState, a.sAux, a.sS, set.uniqueSrc, set.nTargets, set.targets, set.srcOffset,
+          a.incomp, a.passive ? 1 : 0, a.sState, a.sAux, a.sS, set.uniqueSrc, set.nTargets, set.targets, set.srcOffset,
           set.srcSlot, a.tState, a.withAux ? a.tAux : nullptr, a.tS, a.tVisc, a.tViscUniform);
     MUSB_CUDA(cudaGetLastError());
     if (nLaunch) *nLaunch = 1;
     return 0;
   }
   if (a.QQ == 19)
-    eqNeqKernel<19, 128><<<divUp(set.nUnique, 128), 128, 0, st>>>(a.incomp, a.sState, a.sAux, a.sS,
+    eqNeqKernel<19, 128><<<divUp(set.nUnique, 128), 128, 0, st>>>(a.incomp, a.passive ? 1 : 0, a.sState, a.sAux, a.sS,
                                                                   set.uniqueSrc, set.nUnique, set.scratch);
   else
-    eqNeqKernel<27, 64><<<divUp(set.nUnique, 64), 64, 0, st>>>(a.incomp, a.sState, a.sAux, a.sS,
+    eqNeqKernel<27, 64><<<divUp(set.nUnique, 64), 64, 0, st>>>(a.incomp, a.passive ? 1 : 0, a.sState, a.sAux, a.sS,
                                                                 set.uniqueSrc, set.nUnique, set.scratch);
   MUSB_CUDA(cudaGetLastError());
   const int mode = 1 + set.order;
   if (mode == 1 && !set.weights) return setError(1, "weighted-average set without weights");
   const int grid = divUp((long long)set.nTargets * a.QQ, B);
   // uniform viscosity: hand over 0.5 * getNonEqFac_intp_coarse_to_fine instead of the viscosity
-  const double facOrVisc =
-      a.tVisc ? 0.0 : 0.5 * hostNeqFac(hostOmega(0.5 * a.tViscUniform), hostOmega(a.tViscUniform));
+  const double facOrVisc = (a.tVisc || a.passive)
+      ? 0.0 : 0.5 * hostNeqFac(hostOmega(0.5 * a.tViscUniform), hostOmega(a.tViscUniform));
+  const double *tViscArr = a.passive ? nullptr : a.tVisc;   // passive scalar: factor 0 on the zero f_neq
+  if (set.nTiles > 0 && !g_intpTargetMajor) {
+    const size_t smem = (size_t)kTileSrc * a.QQ * sizeof(double2) + (size_t)kTileTgt * a.QQ * sizeof(double);
+#define MUSB_TILE(M, D)                                                                               \
+  intpTileKernel<M, D><<<set.nTiles, 128, smem, st>>>(a.QQ, set.scratch, set.tileTarget, set.tileSrcStart, \
+                                                  set.tileSrc, set.localSrc, set.targets, set.srcOffset, \
+                                                  set.weights, set.posInMat, set.matOffsetT, set.matricesT, \
+                                                  set.coord, a.tState, a.tS, tViscArr, facOrVisc)
+    if (mode == 1) MUSB_TILE(1, 4);
+    else if (mode == 2) MUSB_TILE(2, 4);
+    else if (mode == 3) MUSB_TILE(3, 2);
+    else return setError(1, "interpolation order must be 0, 1 or 2");
+#undef MUSB_TILE
+    MUSB_CUDA(cudaGetLastError());
+    if (nLaunch) *nLaunch = 2;
+    return 0;
+  }
 #define MUSB_INTP(M)                                                                              \
   intpKernel<M><<<grid, B, 0, st>>>(a.QQ, set.scratch, set.nUnique, set.nTargets, set.targets,    \
                                     set.srcOffset, set.srcSlot, set.weights, set.posInMat,        \
                                     set.matOffset, set.matrices, set.coord, a.tState, a.tS,       \
-                                    a.tVisc, facOrVisc)
+                                    tViscArr, facOrVisc)
   if (mode == 1) MUSB_INTP(1);
   else if (mode == 2) MUSB_INTP(2);
   else if (mode == 3) MUSB_INTP(3);

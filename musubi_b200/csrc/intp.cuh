@@ -22,6 +22,9 @@
 
 namespace musb200 {
 
+constexpr int kTileSrc = 64;   // distinct sources per tile
+constexpr int kTileTgt = 64;   // targets per tile
+
 struct IntpSet {
   int order = 0;
   int nTargets = 0;
@@ -35,9 +38,19 @@ struct IntpSet {
   int32_t *posInMat = nullptr;   // [nTargets]
   int32_t *matOffset = nullptr;  // [nMatrices+1]
   double *matrices = nullptr;    // concatenated row-major (nCoeff x nSrc)
+  double *matricesT = nullptr;   // the same, each matrix transposed (nSrc x nCoeff): tile kernel
+  int32_t *matOffsetT = nullptr; // [nMatrices+1] into matricesT (even offsets)
   double *coord = nullptr;       // [nTargets][3]
   double *scratch = nullptr;     // [nUnique][2*QQ]  f_eq | f_neq per distinct source
   int maxSrc = 0;                // largest number of sources of a target
+  // from-coarser sets: consecutive targets (treeID order: siblings, then neighbouring parents)
+  // packed into CTA tiles whose sources -- at most kTileSrc distinct ones -- are staged in shared
+  // memory once and shared by all targets of the tile
+  int nTiles = 0;
+  int32_t *tileTarget = nullptr; // [nTiles+1] first target of each tile
+  int32_t *tileSrcStart = nullptr; // [nTiles+1] into tileSrc
+  int32_t *tileSrc = nullptr;    // distinct source slots of each tile, concatenated
+  uint8_t *localSrc = nullptr;   // CSR like srcSlot: index into the tile's source list
   void release();
   ~IntpSet() { release(); }
   IntpSet() = default;
@@ -59,6 +72,7 @@ struct IntpArgs {
   const double *tVisc;   // per-element lattice viscosity of the target level or nullptr
   double tViscUniform;
   bool withAux;          // from-finer: average the auxField in the same kernel
+  bool passive;          // passive scalar: interpolate the PDFs themselves (f_eq := f, f_neq := 0)
 };
 
 int registerIntp(IntpSet &set, int order, int nTargets, const int32_t *targetList,
@@ -66,6 +80,7 @@ int registerIntp(IntpSet &set, int order, int nTargets, const int32_t *targetLis
                  const int32_t *posInMat, int nMatrices, const int32_t *matOffset,
                  const double *matrices, const double *childCoord, cudaStream_t st);
 // returns the number of kernels launched through *nLaunch
+extern int g_intpTargetMajor;
 int launchIntp(const IntpArgs &a, const IntpSet &set, bool fromFiner, cudaStream_t st, int *nLaunch);
 
 }  // namespace musb200

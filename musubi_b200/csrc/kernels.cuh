@@ -24,6 +24,7 @@ struct PushArgs {
 // receives from has published an exchange number >= this rank's own
 struct HaloWait {
   const uint32_t *ctaMask;              // sweep: 1 bit per CTA that pulls from a halo row; nullptr = no wait
+  int haloStart;                        // first halo element of the level's rows
   const unsigned long long *arrived;    // my arrived[nranks], written by the senders
   const unsigned long long *exch;       // my exchange number (device memory)
   int nRecvPeers;

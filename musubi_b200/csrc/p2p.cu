@@ -37,6 +37,27 @@
 
 namespace musb200 {
 
+// one (entry -> remote store); QQ is a template parameter so that position -> (direction, element)
+// is a multiply-shift, not a division
+template <int QQ>
+__device__ __forceinline__ void pushOne(const P2PArgs &a, int i) {
+  if (i < a.n) {
+    const int p = a.srcPos[i] - 1;
+    const double v = a.state[(long long)(p % QQ) * a.S + p / QQ];
+    const int k = a.peerOf[i];
+    const int r = a.dstPos[i] - 1;
+    a.remoteState[k][(long long)(r % QQ) * a.remoteS[k] + r / QQ] = v;
+  } else {
+    const int j = i - a.n;
+    const int p = a.auxSrcPos[j] - 1;
+    const double v = a.aux[(long long)(p & 3) * a.S + (p >> 2)];
+    const int k = a.auxPeerOf[j];
+    const int r = a.auxDstPos[j] - 1;
+    a.remoteAux[k][(long long)(r & 3) * a.remoteS[k] + (r >> 2)] = v;
+  }
+}
+
+template <int QQ>
 __global__ void __launch_bounds__(256) pushHaloKernel(P2PArgs a) {
   if (a.handshake) {
     // "ready to receive": this rank has finished every kernel that read exchange n-1 (stream
@@ -74,24 +95,18 @@ __global__ void __launch_bounds__(256) pushHaloKernel(P2PArgs a) {
     }
     __syncthreads();
   }
+  // the transfer is latency bound (index load -> gather -> remote store): many threads, and four
+  // independent entries in flight per thread
   const int stride = gridDim.x * blockDim.x;
   const int total = a.n + a.nAux;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    if (i < a.n) {
-      const int p = a.srcPos[i] - 1;
-      const double v = a.state[(long long)(p % a.QQ) * a.S + p / a.QQ];
-      const int k = a.peerOf[i];
-      const int r = a.dstPos[i] - 1;
-      a.remoteState[k][(long long)(r % a.QQ) * a.remoteS[k] + r / a.QQ] = v;
-    } else {
-      const int j = i - a.n;
-      const int p = a.auxSrcPos[j] - 1;
-      const double v = a.aux[(long long)(p & 3) * a.S + (p >> 2)];
-      const int k = a.auxPeerOf[j];
-      const int r = a.auxDstPos[j] - 1;
-      a.remoteAux[k][(long long)(r & 3) * a.remoteS[k] + (r >> 2)] = v;
-    }
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < total; i += 4 * stride) {
+    pushOne<QQ>(a, i);
+    pushOne<QQ>(a, i + stride);
+    pushOne<QQ>(a, i + 2 * stride);
+    pushOne<QQ>(a, i + 3 * stride);
   }
+  for (; i < total; i += stride) pushOne<QQ>(a, i);
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x != 0) return;
@@ -172,8 +187,9 @@ int launchPushHalo(const P2PArgs &a, cudaStream_t st) {
   // enough CTAs to saturate NVLink stores, few enough to keep the ticket cheap
   const int total = a.n + a.nAux;
   int blocks = divUp(total > 0 ? total : 1, 256);
-  if (blocks > 296) blocks = 296;      // 2 x 148 SMs
-  pushHaloKernel<<<blocks, 256, 0, st>>>(a);
+  if (blocks > 148 * 8) blocks = 148 * 8;      // a full wave of 256-thread CTAs
+  if (a.QQ == 19) pushHaloKernel<19><<<blocks, 256, 0, st>>>(a);
+  else pushHaloKernel<27><<<blocks, 256, 0, st>>>(a);
   MUSB_CUDA(cudaGetLastError());
   return 0;
 }

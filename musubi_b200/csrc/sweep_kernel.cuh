@@ -148,11 +148,15 @@ __global__ void __launch_bounds__(sweepThreads<QQ>(), sweepMinBlocks<QQ>()) swee
       }
     } else {
       // halo rows were written by a peer DURING this kernel: not read-only data, so no
-      // ld.global.nc and no L1 (a line shared with own elements may sit there stale) -- L2 only
+      // ld.global.nc and no L1 (a line shared with own elements may sit there stale) -- they
+      // come from L2; the CTA's pulls from own elements keep the read-only path
+      const uint32_t h0 = (uint32_t)a.wait.haloStart;
 #pragma unroll
       for (int q = 0; q < QQ - 1; ++q) {
         const long long row = (n[q] & kBounceBit) ? (long long)invDir<QQ>(q) * S : (long long)q * S;
-        f[q] = __ldcg(a.in + row + (n[q] & kElemMask));
+        const uint32_t src = n[q] & kElemMask;
+        const double *ptr = a.in + row + src;
+        f[q] = src >= h0 ? __ldcg(ptr) : __ldg(ptr);
       }
     }
     f[QQ - 1] = __ldg(a.in + (long long)(QQ - 1) * S + e);

@@ -139,8 +139,9 @@ class Scheme:
                                                ptr(ld.neigh, P_I32), ptr(ld.property, P_I64),
                                                ptr(ld.total, P_I64)))
             if self.passive_scalar:
+                dc = species["diff_coeff"]          # lattice units of the level: {level: D} or one value
                 check(lib.musb200_set_species(lvl, self.relax, self.ps_variant,
-                                              float(species["diff_coeff"]),
+                                              float(dc[lvl] if isinstance(dc, dict) else dc),
                                               float(species.get("lambda", 0.25))))
             else:
                 om = omega[lvl] if isinstance(omega, dict) else omega
@@ -398,6 +399,17 @@ class Scheme:
         self._bind()
         for lvl in list(self.levelDesc):
             lib.musb200_level_destroy(lvl)
+
+
+def step_schemes(schemes, nCycles=1):
+    """several schemes on one mesh stepped together (musb200_step_schemes): within every level step
+    they advance in the order given -- the flow first, then the passive scalar that reads its
+    velocity -- and then fill their ghosts"""
+    slots = (ctypes.c_int * len(schemes))(*[sc.slot for sc in schemes])
+    lo, hi = schemes[0].minLevel, schemes[0].maxLevel
+    if any((sc.minLevel, sc.maxLevel) != (lo, hi) for sc in schemes):
+        raise ValueError("coupled schemes must live on the same levels")
+    check(lib.musb200_step_schemes(len(schemes), slots, lo, hi, int(nCycles)))
 
 
 def exchange_recv_lists(dist, ld):

@@ -65,7 +65,7 @@ void ora_fill_arbi_from_finer_avg(int nScalars, const double *sVal, double *tVal
     const int tgt = targetPos[i];
     const int n = srcOffset[i + 1] - srcOffset[i];
     const double inv_n = 1.0 / (double)n;
-    double t[8];
+    double t[27];
     for (int k = 0; k < nScalars; ++k) t[k] = 0.0;
     for (int s = 0; s < n; ++s) {
       const int src = srcPos[srcOffset[i] + s];
@@ -127,6 +127,49 @@ void ora_fill_finer_ghosts_from_me(int order, int QQ, int incomp, const double *
     for (int d = 0; d < QQ; ++d) {
       t_neq[d] = t_neq[d] * fac;
       tState[(size_t)(tgt - 1) * QQ + d] = t_neq[d] + t_eq[d];
+    }
+  }
+}
+
+/* fillArbiFinerGhostsFromMe_weighAvg / _linear / _quad
+ *   mus/source/intp/mus_interpolate_average_module.fpp:762-850 (sum(weight * sArbi) per variable),
+ *   mus_interpolate_linear_module.fpp:124-205 + mus_interpolate_linear3D_leastSq :1010-1049,
+ *   mus_interpolate_quadratic_module.fpp:102-... + mus_interpolate_quad3D_leastSq :989-1034
+ * the reference's interpolation of ARBITRARY per-element values (it applies them to the
+ * auxField); applied here to the nScalars = QQ PDFs of a passive scalar, whose ghosts have no
+ * f_eq / f_neq rescaling.  sVal / tVal: AOS, nScalars per element. */
+void ora_fill_arbi_finer_from_me(int order, int nScalars, const double *sVal, double *tVal,
+                                 int nTargets, const int32_t *targetPos, const int32_t *srcOffset,
+                                 const int32_t *srcPos, const double *weights,
+                                 const int32_t *posInMat, const int32_t *matOffset,
+                                 const double *matrices, const double *coord) {
+  const int nCoeff = order == 1 ? 4 : 10;
+  for (int i = 0; i < nTargets; ++i) {
+    const int tgt = targetPos[i];
+    const int n = srcOffset[i + 1] - srcOffset[i];
+    for (int v = 0; v < nScalars; ++v) {
+      double phi;
+      if (order == 0) {
+        const double *w = weights + srcOffset[i];
+        phi = 0.0;
+        for (int s = 0; s < n; ++s)
+          phi = phi + w[s] * sVal[(size_t)(srcPos[srcOffset[i] + s] - 1) * nScalars + v];
+      } else {
+        const double *A = matrices + matOffset[posInMat[i]];
+        const double x = coord[3 * i + 0], y = coord[3 * i + 1], z = coord[3 * i + 2];
+        double a[10];
+        for (int k = 0; k < nCoeff; ++k) {
+          double acc = 0.0;
+          for (int s = 0; s < n; ++s)
+            acc = acc + A[(size_t)k * n + s] * sVal[(size_t)(srcPos[srcOffset[i] + s] - 1) * nScalars + v];
+          a[k] = acc;
+        }
+        phi = a[0] + a[1] * x + a[2] * y + a[3] * z;
+        if (order == 2)
+          phi = phi + a[4] * x * x + a[5] * y * y + a[6] * z * z + a[7] * x * y + a[8] * y * z +
+                a[9] * z * x;
+      }
+      tVal[(size_t)(tgt - 1) * nScalars + v] = phi;
     }
   }
 }

@@ -140,6 +140,14 @@ void ora_fill_finer_ghosts_from_me(int order, int QQ, int incomp, const double *
                                    const double *matrices, const double *coord,
                                    const double *tVisc);
 
+/* the reference's interpolation of arbitrary per-element values (fillArbiFinerGhostsFromMe_*),
+ * applied to the PDFs of a passive scalar on a multi-level mesh */
+void ora_fill_arbi_finer_from_me(int order, int nScalars, const double *sVal, double *tVal,
+                                 int nTargets, const int32_t *targetPos, const int32_t *srcOffset,
+                                 const int32_t *srcPos, const double *weights,
+                                 const int32_t *posInMat, const int32_t *matOffset,
+                                 const double *matrices, const double *coord);
+
 /* ---- ghost dependency build (dependencies.c): an implementation independent of the
  * product's host-side generator, compared with it list by list ------------------------------- */
 /* tem_build_verticalDependencies (tem_construction_module.f90:2894-2985); blockStart[0..4]:

@@ -917,10 +917,20 @@ class MultiLevelScheme:
 
     def do_computation(self, l=None):
         l = self.minLevel if l is None else l
-        L = lib()
         if l < self.maxLevel:
             for _ in range(2):                                   # nNesting = 2 (acoustic)
                 self.do_computation(l + 1)
+        self.advance(l)
+        self.interpolate(l)
+
+    def interpolate(self, l):
+        if l < self.maxLevel:
+            self._from_finer(l)
+            self._from_coarser(l)
+
+    def advance(self, l):
+        """the level step without the ghost interpolation that closes it"""
+        L = lib()
         s = self.s[l]
         s.set_boundary()
         s.nNow, s.nNext = s.nNext, s.nNow
@@ -934,9 +944,6 @@ class MultiLevelScheme:
         if rc != 0:
             raise RuntimeError("no oracle kernel for this (relaxation, layout, kind)")
         s.apply_source_terms()
-        if l < self.maxLevel:
-            self._from_finer(l)
-            self._from_coarser(l)
 
     def fill_helper_elements(self):
         """mus_init_flow once state(:, nNext) of the fluid elements is filled (initial condition or
@@ -970,6 +977,67 @@ class MultiLevelScheme:
         for l, s in self.s.items():
             tot += s.total_mass() / 8.0 ** (l - self.minLevel)
         return tot
+
+
+class CoupledMultiLevel:
+    """BASELINE config 5: a flow and a passive scalar transported by it on the same multi-level
+    mesh.  The reference has no such run (it aborts for a passive scalar on a multi-level mesh,
+    mus_scheme_module.f90:166-190, and holds one scheme per process): this is the documented
+    extension, built from reference pieces only -- the recursive schedule of
+    do_recursive_multiLevel with both schemes advancing inside every level step (flow first: the
+    scalar's transport velocity is the auxField velocity of the same level step), the scalar's
+    kernels (mus_compute_passiveScalar_module.fpp) and, for the scalar's ghosts, the reference's
+    interpolation of ARBITRARY values applied to the PDFs (fillArbiMyGhostsFromFiner_avg,
+    fillArbiFinerGhostsFromMe_weighAvg / _linear / _quad).  Diffusivity scales acoustically like
+    the viscosity: the lattice value doubles per finer level."""
+
+    def __init__(self, flow, relaxation="bgk", variant="first", diff_coeff_min=0.01, lambda_=0.25):
+        self.flow = flow
+        self.minLevel, self.maxLevel = flow.minLevel, flow.maxLevel
+        self.diff = {l: diff_coeff_min * 2.0 ** (l - self.minLevel) for l in flow.levels}
+        self.ps = {l: PassiveScalarScheme(ld, relaxation, variant, diff_coeff=self.diff[l], lambda_=lambda_)
+                   for l, ld in flow.levels.items()}
+
+    def _ps_from_finer(self, l):
+        t = self.flow.tables.get((l, "fromFiner"))
+        if t is None or len(t["targets"]) == 0:
+            return
+        c, f = self.ps[l], self.ps[l + 1]
+        lib().ora_fill_arbi_from_finer_avg(c.QQ, _d(f.state[f.nNext]), _d(c.state[c.nNext]), len(t["targets"]),
+                                           _i(t["targets"]), _i(t["srcOffset"]), _i(t["srcPos"]))
+
+    def _ps_from_coarser(self, l):
+        c, f = self.ps[l], self.ps[l + 1]
+        for o in range(0, self.flow.order + 1):
+            t = self.flow.tables.get((l + 1, ("fromCoarser", o)))
+            if t is None or len(t["targets"]) == 0:
+                continue
+            coord = np.ascontiguousarray(t["coord"], dtype=np.float64)
+            lib().ora_fill_arbi_finer_from_me(
+                o, c.QQ, _d(c.state[c.nNext]), _d(f.state[f.nNext]), len(t["targets"]), _i(t["targets"]),
+                _i(t["srcOffset"]), _i(t["srcPos"]), _d(np.ascontiguousarray(t["weights"])), _i(t["posInMat"]),
+                _i(t["matOffset"]), _d(np.ascontiguousarray(t["matrices"])), _d(coord))
+
+    def do_computation(self, l=None):
+        l = self.minLevel if l is None else l
+        if l < self.maxLevel:
+            for _ in range(2):
+                self.do_computation(l + 1)
+        self.flow.advance(l)
+        p, ld = self.ps[l], self.flow.levels[l]
+        p.set_transport_velocity(self.flow.s[l].aux[:ld.nSolve * 4].reshape(-1, 4)[:, 1:])
+        p.step()
+        self.flow.interpolate(l)
+        if l < self.maxLevel:
+            self._ps_from_finer(l)
+            self._ps_from_coarser(l)
+
+    def run(self, ncycles):
+        for _ in range(ncycles):
+            self.do_computation()
+
+    def scalar_mass(self):
+        return sum(p.total_mass() / 8.0 ** (l - self.minLevel) for l, p in self.ps.items())
 
 
 # --------------------------------------------------------------------------

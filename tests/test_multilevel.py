@@ -116,11 +116,16 @@ OMEGA_MIN = {1: 1.6, 2: 1.75}
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("tiled", [1, 0], ids=["tiled", "target-major"])
 @pytest.mark.parametrize("min_level,boxes,QQ,method,relax,cyl", CASES,
                          ids=["2lvl-linear-bgk19", "2lvl-cylinder", "2lvl-quad-mrt27", "2lvl-wavg-trt19",
                               "3lvl-linear-bgk19"])
-def test_multilevel_gpu_matches_oracle(mbgpu, oracle, min_level, boxes, QQ, method, relax, cyl):
+def test_multilevel_gpu_matches_oracle(mbgpu, oracle, min_level, boxes, QQ, method, relax, cyl, tiled):
+    """both forms of the coarse -> fine interpolation kernel (shared-memory tiles of sources /
+    one thread per (target, direction)) against the oracle, bit for bit"""
     mb = mbgpu
+    from musubi_b200._lib import check, lib
+    check(lib.musb200_set_intp_tiled(tiled))
     lv, intp, tables, ms = build(oracle, min_level, boxes, QQ, method, relax, cyl,
                                  omega_min=OMEGA_MIN[len(boxes)])
     ident = {"kind": "fluid", "relaxation": relax, "layout": "d3q%d" % QQ}
@@ -149,6 +154,7 @@ def test_multilevel_gpu_matches_oracle(mbgpu, oracle, min_level, boxes, QQ, meth
         aux = sch.download_aux(l)[:L.nElems * 4]
         assert np.array_equal(aux[:nf * 4], s.aux[:nf * 4])
     sch.destroy()
+    check(lib.musb200_set_intp_tiled(1))
 
 
 # ---- several ranks -----------------------------------------------------------------------------
