@@ -9,7 +9,7 @@ namespace musb200 {
 void IntpSet::release() {
   auto fr = [](auto *&p) { if (p) cudaFree(p); p = nullptr; };
   fr(targets); fr(srcOffset); fr(srcSlot); fr(uniqueSrc); fr(weights); fr(posInMat); fr(matOffset);
-  fr(matrices); fr(matricesT); fr(matOffsetT); fr(coord); fr(scratch); fr(tileTarget); fr(tileSrcStart); fr(tileSrc); fr(localSrc);
+  fr(matrices); fr(matricesT); fr(matOffsetT); fr(coord); fr(scratch); fr(tileTarget); fr(tileSrcStart); fr(tileSrc); fr(localSrc); fr(tileMatStart); fr(tileMat); fr(tgtMeta);
   nTargets = 0; nMatrices = 0; nUnique = 0; maxSrc = 0; nTiles = 0;
 }
 
@@ -25,6 +25,8 @@ IntpSet &IntpSet::operator=(IntpSet &&o) noexcept {
     nTiles = o.nTiles; o.nTiles = 0;
     tileTarget = o.tileTarget; tileSrcStart = o.tileSrcStart; tileSrc = o.tileSrc; localSrc = o.localSrc;
     o.tileTarget = nullptr; o.tileSrcStart = nullptr; o.tileSrc = nullptr; o.localSrc = nullptr;
+    tileMatStart = o.tileMatStart; tileMat = o.tileMat; tgtMeta = o.tgtMeta;
+    o.tileMatStart = nullptr; o.tileMat = nullptr; o.tgtMeta = nullptr;
     o.targets = nullptr; o.srcOffset = nullptr; o.srcSlot = nullptr; o.uniqueSrc = nullptr;
     o.weights = nullptr; o.posInMat = nullptr; o.matOffset = nullptr; o.matrices = nullptr;
     o.coord = nullptr; o.scratch = nullptr;
@@ -62,6 +64,7 @@ int registerIntp(IntpSet &set, int order, int nTargets, const int32_t *targetLis
     if (srcOffset[i + 1] - srcOffset[i] < 1 || srcOffset[i + 1] - srcOffset[i] > 27)
       return setError(1, "an interpolation target needs between 1 and 27 sources");
   int rc = 0;
+  std::vector<int32_t> offT;   // offsets of the transposed matrices (least-square orders)
   rc |= up(set.targets, targetList, nTargets, st);
   rc |= up(set.srcOffset, srcOffset, (size_t)nTargets + 1, st);
   rc |= up(set.srcSlot, slot.data(), (size_t)nSrc, st);
@@ -78,7 +81,7 @@ int registerIntp(IntpSet &set, int order, int nTargets, const int32_t *targetLis
       // every matrix at an even offset (16-byte aligned pairs)
       const int nc = order == 1 ? 4 : 10;
       std::vector<double> mt;
-      std::vector<int32_t> offT((size_t)nMatrices + 1, 0);
+      offT.assign((size_t)nMatrices + 1, 0);
       for (int mI = 0; mI < nMatrices; ++mI) {
         const int off = matOffset[mI], len = matOffset[mI + 1] - off;
         offT[mI] = (int32_t)mt.size();
@@ -107,35 +110,74 @@ int registerIntp(IntpSet &set, int order, int nTargets, const int32_t *targetLis
   set.nUnique = (int)uniq.size();
   {
     // tiles: greedily pack consecutive targets while the union of their sources stays within
-    // kTileSrc and the tile within kTileTgt targets
-    std::vector<int32_t> tileTarget{0}, tileSrcStart{0}, tileSrc;
+    // kTileSrc, the tile within kTileTgt targets and kTileEnt (target, source) entries, and its
+    // distinct least-square matrices within kTileMat doubles
+    const int nc = order == 0 ? 1 : (order == 1 ? 4 : 10);
+    std::vector<int32_t> tileTarget{0}, tileSrcStart{0}, tileSrc, tileMatStart{0}, tileMat;
+    std::vector<int32_t> meta((size_t)nTargets * 4, 0);
     std::vector<uint8_t> local((size_t)nSrc);
     std::vector<int32_t> where((size_t)set.nUnique, -1);   // slot -> index in the current tile
     std::vector<int32_t> cur;
+    std::vector<std::pair<int32_t, int32_t>> curMat;        // (matrix id, offset in the staged area)
+    int matDoubles = 0;
     auto flush = [&](int nextTarget) {
       for (int32_t sl : cur) where[sl] = -1;
       tileSrc.insert(tileSrc.end(), cur.begin(), cur.end());
       cur.clear();
+      for (auto &m : curMat) {
+        tileMat.push_back(offT[m.first]);
+        tileMat.push_back(offT[m.first + 1] - offT[m.first]);
+      }
+      curMat.clear();
+      matDoubles = 0;
       tileTarget.push_back(nextTarget);
       tileSrcStart.push_back((int32_t)tileSrc.size());
+      tileMatStart.push_back((int32_t)tileMat.size() / 2);
     };
     for (int i = 0; i < nTargets; ++i) {
       int add = 0;
       for (int j = srcOffset[i]; j < srcOffset[i + 1]; ++j)
         if (where[slot[j]] < 0) ++add;
-      if ((int)cur.size() + add > kTileSrc || i - tileTarget.back() >= kTileTgt) flush(i);
+      int matAdd = 0, matId = -1;
+      if (order > 0) {
+        matId = posInMat[i];
+        bool have = false;
+        for (auto &m : curMat) have = have || m.first == matId;
+        if (!have) matAdd = offT[matId + 1] - offT[matId];
+      }
+      if ((int)cur.size() + add > kTileSrc || i - tileTarget.back() >= kTileTgt ||
+          srcOffset[i + 1] - srcOffset[tileTarget.back()] > kTileEnt || matDoubles + matAdd > kTileMat) {
+        flush(i);
+        if (order > 0) matAdd = offT[matId + 1] - offT[matId];
+      }
       for (int j = srcOffset[i]; j < srcOffset[i + 1]; ++j) {
         if (where[slot[j]] < 0) { where[slot[j]] = (int32_t)cur.size(); cur.push_back(slot[j]); }
         local[j] = (uint8_t)where[slot[j]];
       }
+      int matOff = 0;
+      if (order > 0) {
+        bool have = false;
+        for (auto &m : curMat)
+          if (m.first == matId) { have = true; matOff = m.second; }
+        if (!have) { matOff = matDoubles; curMat.push_back({matId, matDoubles}); matDoubles += matAdd; }
+      }
+      meta[(size_t)i * 4 + 0] = srcOffset[i] - srcOffset[tileTarget.back()];
+      meta[(size_t)i * 4 + 1] = srcOffset[i + 1] - srcOffset[i];
+      meta[(size_t)i * 4 + 2] = matOff;
+      meta[(size_t)i * 4 + 3] = targetList[i] - 1;
     }
     flush(nTargets);
+    (void)nc;
     set.nTiles = (int)tileTarget.size() - 1;
     int rc2 = 0;
     rc2 |= up(set.tileTarget, tileTarget.data(), tileTarget.size(), st);
     rc2 |= up(set.tileSrcStart, tileSrcStart.data(), tileSrcStart.size(), st);
     rc2 |= up(set.tileSrc, tileSrc.data(), tileSrc.size(), st);
     rc2 |= up(set.localSrc, local.data(), local.size(), st);
+    rc2 |= up(set.tileMatStart, tileMatStart.data(), tileMatStart.size(), st);
+    if (tileMat.empty()) tileMat.push_back(0);
+    rc2 |= up(set.tileMat, tileMat.data(), tileMat.size(), st);
+    rc2 |= up(set.tgtMeta, meta.data(), meta.size(), st);
     if (rc2) return rc2;
     MUSB_CUDA(cudaStreamSynchronize(st));  // the tile vectors go out of scope
   }
@@ -272,37 +314,55 @@ __global__ void __launch_bounds__(128) intpKernel(int QQ, const double *__restri
 // accumulated in the host's order exactly as above, so the bits are unchanged.  Results go
 // through shared memory once more so that the stores run along the targets (siblings are
 // consecutive in the total list): 64-byte segments instead of 8-byte scattered stores.
-template <int MODE, int D>
-__global__ void __launch_bounds__(128) intpTileKernel(int QQ, const double *__restrict__ scratch,
+template <int MODE, int QQ, int D>
+__global__ void __launch_bounds__(128) intpTileKernel(const double *__restrict__ scratch,
                                const int32_t *__restrict__ tileTarget, const int32_t *__restrict__ tileSrcStart,
                                const int32_t *__restrict__ tileSrc, const uint8_t *__restrict__ localSrc,
-                               const int32_t *__restrict__ targets, const int32_t *__restrict__ srcOffset,
-                               const double *__restrict__ weights, const int32_t *__restrict__ posInMat,
-                               const int32_t *__restrict__ matOffset, const double *__restrict__ matricesT,
+                               const int32_t *__restrict__ tileMatStart, const int32_t *__restrict__ tileMat,
+                               const int4 *__restrict__ tgtMeta, const int32_t *__restrict__ srcOffset,
+                               const double *__restrict__ weights, const double *__restrict__ matricesT,
                                const double *__restrict__ coord, double *__restrict__ tState, long long tS,
                                const double *__restrict__ tVisc, double tViscUniform) {
-  // One thread evaluates D consecutive directions of a target: the coefficients of a source
-  // (one 16-byte aligned group per source in the TRANSPOSED matrix, matricesT[s][k]) are loaded
-  // once and used for D directions -- the target-major kernel issues 6 loads per (source,
-  // direction), this one (3 + D) / D.
+  // Everything the evaluation reads is staged in shared memory first, each piece by independent,
+  // contiguous loads (no dependent index chains): the {f_eq, f_neq} rows of the tile's sources,
+  // the tile's DISTINCT least-square matrices (transposed, matricesT[s][k]: the coefficients of a
+  // source side by side; a refinement surface uses a handful: one per child position), the row
+  // index of every (target, source) entry and one int4 of metadata per target.  The inner loops
+  // issue no global load; one thread evaluates D consecutive directions of a target.
   constexpr int nCoeff = MODE == 1 ? 1 : (MODE == 2 ? 4 : 10);
-  extern __shared__ double2 sm2[];                 // [kTileSrc][QQ] pairs | [QQ][kTileTgt] results
-  double *res = reinterpret_cast<double *>(sm2 + kTileSrc * QQ);
+  constexpr int nG = (QQ + D - 1) / D;
+  extern __shared__ double2 sm2[];                                   // [kTileSrc][QQ] pairs
+  double *res = reinterpret_cast<double *>(sm2 + kTileSrc * QQ);      // [QQ][kTileTgt] results
+  double *mats = res + kTileTgt * QQ;                                // staged matrices / MODE 1: weights per entry
+  int4 *meta = reinterpret_cast<int4 *>(mats + (MODE == 1 ? kTileEnt : kTileMat));   // [kTileTgt]
+  uint8_t *rowOf = reinterpret_cast<uint8_t *>(meta + kTileTgt);     // [kTileEnt]
   const int t0 = tileTarget[blockIdx.x], nT = tileTarget[blockIdx.x + 1] - t0;
   const int u0 = tileSrcStart[blockIdx.x], nU = tileSrcStart[blockIdx.x + 1] - u0;
+  const int e0 = srcOffset[t0], nE = srcOffset[t0 + nT] - e0;
   const double2 *sc2 = reinterpret_cast<const double2 *>(scratch);
   for (int idx = threadIdx.x; idx < nU * QQ; idx += blockDim.x) {
     const int r = idx / QQ, d = idx - r * QQ;
     sm2[idx] = sc2[(long long)tileSrc[u0 + r] * QQ + d];
   }
+  for (int e = threadIdx.x; e < nE; e += blockDim.x) rowOf[e] = localSrc[e0 + e];
+  if (threadIdx.x < nT) meta[threadIdx.x] = tgtMeta[t0 + threadIdx.x];
+  if (MODE == 1) {
+    for (int e = threadIdx.x; e < nE; e += blockDim.x) mats[e] = weights[e0 + e];
+  } else {
+    int off = 0;
+    for (int m = tileMatStart[blockIdx.x]; m < tileMatStart[blockIdx.x + 1]; ++m) {
+      const int base = tileMat[2 * m], len = tileMat[2 * m + 1];
+      for (int k = threadIdx.x; k < len; k += blockDim.x) mats[off + k] = matricesT[base + k];
+      off += len;
+    }
+  }
   __syncthreads();
-  const int nG = (QQ + D - 1) / D;
   for (int p = threadIdx.x; p < nT * nG; p += blockDim.x) {
     const int il = p / nG, d0 = (p - il * nG) * D;
     const int nd = min(D, QQ - d0);
-    const int i = t0 + il;
-    const int s0 = srcOffset[i], n = srcOffset[i + 1] - s0;
-    const double *A = MODE == 1 ? weights + s0 : matricesT + matOffset[posInMat[i]];
+    const int4 mt = meta[il];                     // entry offset, nSrc, matrix offset, target
+    const int s0 = mt.x, n = mt.y;
+    const double *A = MODE == 1 ? mats + s0 : mats + mt.z;
     double ce[D][nCoeff], cn[D][nCoeff];
 #pragma unroll
     for (int j = 0; j < D; ++j)
@@ -310,14 +370,9 @@ __global__ void __launch_bounds__(128) intpTileKernel(int QQ, const double *__re
       for (int k = 0; k < nCoeff; ++k) { ce[j][k] = 0.0; cn[j][k] = 0.0; }
     for (int s = 0; s < n; ++s) {
       double m[nCoeff];
-      if (MODE == 1) {
-        m[0] = A[s];
-      } else {
-        const double2 *As = reinterpret_cast<const double2 *>(A + s * nCoeff);   // 16-byte aligned
 #pragma unroll
-        for (int k = 0; k < nCoeff; k += 2) { const double2 t = As[k >> 1]; m[k] = t.x; m[k + 1] = t.y; }
-      }
-      const double2 *row = sm2 + (int)localSrc[s0 + s] * QQ + d0;
+      for (int k = 0; k < nCoeff; ++k) m[k] = A[s * nCoeff + k];
+      const double2 *row = sm2 + (int)rowOf[s0 + s] * QQ + d0;
 #pragma unroll
       for (int j = 0; j < D; ++j) {
         if (j < nd) {
@@ -330,9 +385,10 @@ __global__ void __launch_bounds__(128) intpTileKernel(int QQ, const double *__re
         }
       }
     }
+    const int i = t0 + il;
     double fac;   // 0.5 * getNonEqFac_intp_coarse_to_fine
     if (tVisc) {
-      const double visc = tVisc[targets[i] - 1];
+      const double visc = tVisc[mt.w];
       fac = 0.5 * neqFac(omegaFromVisc(0.5 * visc), omegaFromVisc(visc));
     } else {
       fac = tViscUniform;   // the factor itself, evaluated by the launcher with the same expression
@@ -364,7 +420,7 @@ __global__ void __launch_bounds__(128) intpTileKernel(int QQ, const double *__re
   __syncthreads();
   for (int p = threadIdx.x; p < nT * QQ; p += blockDim.x) {
     const int d = p / nT, il = p - d * nT;
-    tState[(long long)d * tS + (targets[t0 + il] - 1)] = res[d * kTileTgt + il];
+    tState[(long long)d * tS + meta[il].w] = res[d * kTileTgt + il];
   }
 }
 
@@ -484,16 +540,31 @@ int launchIntp(const IntpArgs &a, const IntpSet &set, bool fromFiner, cudaStream
       ? 0.0 : 0.5 * hostNeqFac(hostOmega(0.5 * a.tViscUniform), hostOmega(a.tViscUniform));
   const double *tViscArr = a.passive ? nullptr : a.tVisc;   // passive scalar: factor 0 on the zero f_neq
   if (set.nTiles > 0 && !g_intpTargetMajor) {
-    const size_t smem = (size_t)kTileSrc * a.QQ * sizeof(double2) + (size_t)kTileTgt * a.QQ * sizeof(double);
-#define MUSB_TILE(M, D)                                                                               \
-  intpTileKernel<M, D><<<set.nTiles, 128, smem, st>>>(a.QQ, set.scratch, set.tileTarget, set.tileSrcStart, \
-                                                  set.tileSrc, set.localSrc, set.targets, set.srcOffset, \
-                                                  set.weights, set.posInMat, set.matOffsetT, set.matricesT, \
-                                                  set.coord, a.tState, a.tS, tViscArr, facOrVisc)
-    if (mode == 1) MUSB_TILE(1, 4);
-    else if (mode == 2) MUSB_TILE(2, 4);
-    else if (mode == 3) MUSB_TILE(3, 2);
-    else return setError(1, "interpolation order must be 0, 1 or 2");
+    const size_t smem = (size_t)kTileSrc * a.QQ * sizeof(double2) + (size_t)kTileTgt * a.QQ * sizeof(double) +
+                        (size_t)(mode == 1 ? kTileEnt : kTileMat) * sizeof(double) + (size_t)kTileTgt * sizeof(int4) +
+                        (size_t)kTileEnt;
+#define MUSB_TILE(M, Q, D)                                                                                   \
+  {                                                                                                          \
+    static bool optIn = false;   /* more than 48 KB of dynamic shared memory needs the attribute, once */     \
+    if (!optIn && smem > 48 * 1024) {                                                                        \
+      MUSB_CUDA(cudaFuncSetAttribute(intpTileKernel<M, Q, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                     (int)smem));                                                            \
+      optIn = true;                                                                                          \
+    }                                                                                                        \
+  }                                                                                                          \
+  intpTileKernel<M, Q, D><<<set.nTiles, 128, smem, st>>>(                                                    \
+      set.scratch, set.tileTarget, set.tileSrcStart, set.tileSrc, set.localSrc, set.tileMatStart, set.tileMat, \
+      reinterpret_cast<const int4 *>(set.tgtMeta), set.srcOffset, set.weights, set.matricesT, set.coord,       \
+      a.tState, a.tS, tViscArr, facOrVisc)
+    if (a.QQ == 19) {
+      if (mode == 1) MUSB_TILE(1, 19, 4);
+      else if (mode == 2) MUSB_TILE(2, 19, 2);
+      else MUSB_TILE(3, 19, 2);
+    } else {
+      if (mode == 1) MUSB_TILE(1, 27, 4);
+      else if (mode == 2) MUSB_TILE(2, 27, 2);
+      else MUSB_TILE(3, 27, 2);
+    }
 #undef MUSB_TILE
     MUSB_CUDA(cudaGetLastError());
     if (nLaunch) *nLaunch = 2;

@@ -24,6 +24,8 @@ namespace musb200 {
 
 constexpr int kTileSrc = 64;   // distinct sources per tile
 constexpr int kTileTgt = 64;   // targets per tile
+constexpr int kTileEnt = 512;  // (target, source) entries per tile
+constexpr int kTileMat = 1024; // doubles of distinct least-square matrices per tile
 
 struct IntpSet {
   int order = 0;
@@ -51,6 +53,10 @@ struct IntpSet {
   int32_t *tileSrcStart = nullptr; // [nTiles+1] into tileSrc
   int32_t *tileSrc = nullptr;    // distinct source slots of each tile, concatenated
   uint8_t *localSrc = nullptr;   // CSR like srcSlot: index into the tile's source list
+  int32_t *tileMatStart = nullptr; // [nTiles+1] into tileMat
+  int32_t *tileMat = nullptr;    // per tile: (offset in matricesT, length) of its distinct matrices
+  int32_t *tgtMeta = nullptr;    // [nTargets][4]: entry offset in the tile, nSrc, offset of its matrix in the
+                                 // tile's staged matrices (MODE 1: unused), target position - 1
   void release();
   ~IntpSet() { release(); }
   IntpSet() = default;

@@ -42,6 +42,7 @@ __device__ __forceinline__ unsigned long long globalTimerNs() {
 // called by ONE thread; the caller separates it from the readers of the halo rows by a barrier
 __device__ __forceinline__ void waitHaloArrival(const HaloWait &w) {
   const unsigned long long want = *reinterpret_cast<const volatile unsigned long long *>(w.exch);
+  if (*reinterpret_cast<volatile int *>(w.errFlag) != 0) return;   // an exchange has failed already: drain
   unsigned long long t0 = 0ull;
   for (int k = 0; k < w.nRecvPeers; ++k) {
     const volatile unsigned long long *flag = w.arrived + w.recvRank[k];
@@ -198,6 +199,7 @@ struct P2PArgs {
   int sendRank[kMaxPeers];
   unsigned long long timeoutNs;
   int *errFlag;
+  int exp;                      // timing experiments only (MUSB200_PUSH_EXP): 1 no remote store, 2 no gather
 };
 int launchPushHalo(const P2PArgs &a, cudaStream_t st);
 // publish only (the links were stored by the sweep with the fused push)

@@ -114,16 +114,6 @@ struct ForceSrc {
 template <int QQ, int RELAX, bool INCOMP, int VAR>
 __global__ void __launch_bounds__(sweepThreads<QQ>(), sweepMinBlocks<QQ>()) sweepKernel(const SweepArgs a) {
   constexpr bool FORCE = VAR == 1, PUSH = VAR == 2;
-  // several ranks, peer-memory halo exchange: a CTA that pulls from a halo row waits until the
-  // peers' links of the previous step have arrived (p2p.cu); all other CTAs start right away
-  bool halo = false;
-  if (a.wait.ctaMask != nullptr) {
-    halo = (a.wait.ctaMask[blockIdx.x >> 5] >> (blockIdx.x & 31)) & 1u;   // uniform over the CTA
-    if (halo) {
-      if (threadIdx.x == 0) waitHaloArrival(a.wait);
-      __syncthreads();
-    }
-  }
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.count) return;
   int e;
@@ -137,9 +127,20 @@ __global__ void __launch_bounds__(sweepThreads<QQ>(), sweepMinBlocks<QQ>()) swee
 
   double f[QQ];
   {
+    // several ranks, peer-memory halo exchange: a CTA that pulls from a halo row waits until the
+    // peers' links of the previous step have arrived (p2p.cu); all other CTAs run right away.
+    // The CTA's mask word is fetched together with the index loads, so the check costs no extra
+    // memory round trip at the head of every CTA.
+    uint32_t maskWord = 0u;
+    if (a.wait.ctaMask != nullptr) maskWord = __ldg(a.wait.ctaMask + (blockIdx.x >> 5));
     uint32_t n[QQ - 1];
 #pragma unroll
     for (int q = 0; q < QQ - 1; ++q) n[q] = __ldcs(a.nbr + q * S + e);
+    const bool halo = (maskWord >> (blockIdx.x & 31)) & 1u;   // uniform over the CTA
+    if (halo) {
+      if (threadIdx.x == 0) waitHaloArrival(a.wait);   // thread 0 of a CTA is always in range
+      __syncthreads();                                 // threads out of range have exited
+    }
     if (!halo) {
 #pragma unroll
       for (int q = 0; q < QQ - 1; ++q) {

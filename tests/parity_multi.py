@@ -210,6 +210,46 @@ def main():
         return
     ld = mb.LevelDesc(a.level, QQ, a.kind, rank, world, octants=a.octants)
 
+    if a.mode == "gpu-timeout":
+        # failure handling of the peer-memory exchange: the last rank "dies" (stops stepping) while
+        # the others go on; their waits give up after the timeout, the stream drains and the next
+        # synchronising call returns MUSB200_ERR_NCCL naming the silent rank -- no hang
+        from musubi_b200 import cases
+        from musubi_b200._lib import Musb200Error, check, lib
+        t = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            t = torch.frombuffer(bytearray(mb.get_unique_id()), dtype=torch.uint8).clone()
+        dist.broadcast(t, 0)
+        mb.mus_init(rank, world, int(os.environ.get("LOCAL_RANK", rank)), bytes(t.numpy().tobytes()))
+        check(lib.musb200_set_exchange_timeout(1.5))
+        check(lib.musb200_set_sweep_wait(0 if a.no_sweep_wait else 1))
+        ident = {"kind": "fluid", "relaxation": a.relaxation, "layout": a.layout}
+        sch = mb.Scheme(ident, ld, 1.7, lambda_=0.25, omega_bulk=1.3)
+        rho, vel = cases.taylor_green(ld)
+        st = cases.equilibrium_state(QQ, rho, vel, ld.nSize)
+        sch.upload_state(a.level, st, st)
+        sch.p2p_connect(dist, a.level)
+        sch.do_computation(3)
+        sch.synchronize()
+        dist.barrier()
+        import time
+        t0 = time.time()
+        if rank == world - 1:
+            print("rank %d: going silent" % rank)
+        else:
+            try:
+                sch.do_computation(4)
+                sch.synchronize()
+                print("rank %d: NO ERROR after %.1f s" % (rank, time.time() - t0))
+            except Musb200Error as ex:
+                ok = ex.code == 3 and "timed out" in str(ex)
+                print("rank %d: %s after %.1f s -> %s" % (rank, "timeout reported" if ok else "unexpected", time.time() - t0, ex))
+        dist.barrier()
+        mb.mus_finalize()
+        dist.barrier()
+        dist.destroy_process_group()
+        return
+
     if a.mode == "lists":
         code = lambda tid, d: tid.astype(np.float64) * 100.0 + d  # noqa: E731
         state = np.full(ld.nSize * QQ, -1.0)

@@ -100,3 +100,18 @@ def test_multi_gpu_multilevel_matches_single_domain_oracle(layout, relax, levels
                         "--method", method, "--steps", "10"] + extra, 29653)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert r.stdout.count("ndiff=0") >= nproc * (levels + 1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("extra", [[], ["--no-sweep-wait"]], ids=["wait-in-sweep", "wait-after-push"])
+def test_exchange_timeout_surfaces_as_an_error_instead_of_a_hang(extra):
+    """a rank that stops stepping: the others' waits give up after the configured timeout and the
+    next synchronising call returns MUSB200_ERR_NCCL (the reference aborts all ranks through
+    tem_abort, tem/source/tem_aux_module.f90:457-478)"""
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    r = _launch(2, ["--mode", "gpu-timeout", "--layout", "d3q19", "--relaxation", "bgk", "--kind", "periodic",
+                    "--level", "5"] + extra, 29655)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count("timeout reported") == 1 and "NO ERROR" not in r.stdout
