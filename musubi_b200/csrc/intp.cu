@@ -551,19 +551,19 @@ int launchIntp(const IntpArgs &a, const IntpSet &set, bool fromFiner, cudaStream
                                      (int)smem));                                                            \
       optIn = true;                                                                                          \
     }                                                                                                        \
-  }                                                                                                          \
-  intpTileKernel<M, Q, D><<<set.nTiles, 128, smem, st>>>(                                                    \
-      set.scratch, set.tileTarget, set.tileSrcStart, set.tileSrc, set.localSrc, set.tileMatStart, set.tileMat, \
-      reinterpret_cast<const int4 *>(set.tgtMeta), set.srcOffset, set.weights, set.matricesT, set.coord,       \
-      a.tState, a.tS, tViscArr, facOrVisc)
+    intpTileKernel<M, Q, D><<<set.nTiles, 128, smem, st>>>(                                                  \
+        set.scratch, set.tileTarget, set.tileSrcStart, set.tileSrc, set.localSrc, set.tileMatStart,          \
+        set.tileMat, reinterpret_cast<const int4 *>(set.tgtMeta), set.srcOffset, set.weights, set.matricesT, \
+        set.coord, a.tState, a.tS, tViscArr, facOrVisc);                                                     \
+  }
     if (a.QQ == 19) {
-      if (mode == 1) MUSB_TILE(1, 19, 4);
-      else if (mode == 2) MUSB_TILE(2, 19, 2);
-      else MUSB_TILE(3, 19, 2);
+      if (mode == 1) MUSB_TILE(1, 19, 4)
+      else if (mode == 2) MUSB_TILE(2, 19, 2)
+      else MUSB_TILE(3, 19, 2)
     } else {
-      if (mode == 1) MUSB_TILE(1, 27, 4);
-      else if (mode == 2) MUSB_TILE(2, 27, 2);
-      else MUSB_TILE(3, 27, 2);
+      if (mode == 1) MUSB_TILE(1, 27, 4)
+      else if (mode == 2) MUSB_TILE(2, 27, 2)
+      else MUSB_TILE(3, 27, 2)
     }
 #undef MUSB_TILE
     MUSB_CUDA(cudaGetLastError());
