@@ -233,6 +233,8 @@ def run_reference(args, wl_name, wl, gpu_level):
         "scaling": "weak" if wl_name == "cfg2" else "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl_name + ": " + wl["name"], "sample": cb["sample"], "level": level,
+                   "cells": int((1 << level) ** 3), "relaxation": wl["ident"]["relaxation"],
+                   "layout": wl["ident"]["layout"], "omega": wl["omega"],
                    "same_config_as_gpu_arm": same,
                    "note": ("the GPU arm's configuration, step for step" if same else
                             "N > 1: the GPU arm runs %d x 256^3 cells weak-scaled; the CPU arm (one host, rank 0) "

@@ -335,7 +335,8 @@ __global__ void __launch_bounds__(128) intpTileKernel(const double *__restrict__
   double *res = reinterpret_cast<double *>(sm2 + kTileSrc * QQ);      // [QQ][kTileTgt] results
   double *mats = res + kTileTgt * QQ;                                // staged matrices / MODE 1: weights per entry
   int4 *meta = reinterpret_cast<int4 *>(mats + (MODE == 1 ? kTileEnt : kTileMat));   // [kTileTgt]
-  uint8_t *rowOf = reinterpret_cast<uint8_t *>(meta + kTileTgt);     // [kTileEnt]
+  double *xyz = reinterpret_cast<double *>(meta + kTileTgt);         // [kTileTgt][4]: child coordinates, factor
+  uint8_t *rowOf = reinterpret_cast<uint8_t *>(xyz + 4 * kTileTgt);  // [kTileEnt]
   const int t0 = tileTarget[blockIdx.x], nT = tileTarget[blockIdx.x + 1] - t0;
   const int u0 = tileSrcStart[blockIdx.x], nU = tileSrcStart[blockIdx.x + 1] - u0;
   const int e0 = srcOffset[t0], nE = srcOffset[t0 + nT] - e0;
@@ -345,7 +346,20 @@ __global__ void __launch_bounds__(128) intpTileKernel(const double *__restrict__
     sm2[idx] = sc2[(long long)tileSrc[u0 + r] * QQ + d];
   }
   for (int e = threadIdx.x; e < nE; e += blockDim.x) rowOf[e] = localSrc[e0 + e];
-  if (threadIdx.x < nT) meta[threadIdx.x] = tgtMeta[t0 + threadIdx.x];
+  if (threadIdx.x < nT) {
+    const int4 mt = tgtMeta[t0 + threadIdx.x];
+    meta[threadIdx.x] = mt;
+    double fac;   // 0.5 * getNonEqFac_intp_coarse_to_fine
+    if (tVisc) {
+      const double visc = tVisc[mt.w];
+      fac = 0.5 * neqFac(omegaFromVisc(0.5 * visc), omegaFromVisc(visc));
+    } else {
+      fac = tViscUniform;   // the factor itself, evaluated by the launcher with the same expression
+    }
+    xyz[4 * threadIdx.x + 3] = fac;
+  }
+  if (MODE != 1)
+    for (int k = threadIdx.x; k < 3 * nT; k += blockDim.x) xyz[4 * (k / 3) + k % 3] = coord[3 * t0 + k];
   if (MODE == 1) {
     for (int e = threadIdx.x; e < nE; e += blockDim.x) mats[e] = weights[e0 + e];
   } else {
@@ -385,16 +399,7 @@ __global__ void __launch_bounds__(128) intpTileKernel(const double *__restrict__
         }
       }
     }
-    const int i = t0 + il;
-    double fac;   // 0.5 * getNonEqFac_intp_coarse_to_fine
-    if (tVisc) {
-      const double visc = tVisc[mt.w];
-      fac = 0.5 * neqFac(omegaFromVisc(0.5 * visc), omegaFromVisc(visc));
-    } else {
-      fac = tViscUniform;   // the factor itself, evaluated by the launcher with the same expression
-    }
-    double x = 0.0, y = 0.0, z = 0.0;
-    if (MODE != 1) { x = coord[3 * i + 0]; y = coord[3 * i + 1]; z = coord[3 * i + 2]; }
+    const double x = xyz[4 * il], y = xyz[4 * il + 1], z = xyz[4 * il + 2], fac = xyz[4 * il + 3];
 #pragma unroll
     for (int j = 0; j < D; ++j) {
       if (j < nd) {
@@ -542,7 +547,7 @@ int launchIntp(const IntpArgs &a, const IntpSet &set, bool fromFiner, cudaStream
   if (set.nTiles > 0 && !g_intpTargetMajor) {
     const size_t smem = (size_t)kTileSrc * a.QQ * sizeof(double2) + (size_t)kTileTgt * a.QQ * sizeof(double) +
                         (size_t)(mode == 1 ? kTileEnt : kTileMat) * sizeof(double) + (size_t)kTileTgt * sizeof(int4) +
-                        (size_t)kTileEnt;
+                        (size_t)4 * kTileTgt * sizeof(double) + (size_t)kTileEnt;
 #define MUSB_TILE(M, Q, D)                                                                                   \
   {                                                                                                          \
     static bool optIn = false;   /* more than 48 KB of dynamic shared memory needs the attribute, once */     \
