@@ -354,11 +354,14 @@ def multirank_check(comm, mb, want_p2p):
     from musubi_b200 import cases
     from musubi_b200._lib import check, lib
     steps, level, out, t0 = 24, 6, {}, time.perf_counter()
-    paths = [("p2p", dict(p2p=True, sweep_wait=1, graphs=1), "peer-memory push, wait inside the next sweep, CUDA graph"),
-             ("p2p-direct", dict(p2p=True, sweep_wait=0, graphs=0), "peer-memory push, wait after the push, direct launches"),
-             ("nccl", dict(p2p=False, sweep_wait=1, graphs=1), "pack / ncclSend / ncclRecv / unpack")]
+    paths = [("p2p", dict(p2p=True, sweep_wait=0, graphs=1, overlap=0), "peer-memory push + wait kernel, CUDA graph"),
+             ("p2p-overlap", dict(p2p=True, sweep_wait=0, graphs=0, overlap=1),
+              "push on a second stream overlapping the sweep of the CTAs that need no halo row, then wait + second launch"),
+             ("p2p-sweepwait", dict(p2p=True, sweep_wait=1, graphs=0, overlap=0),
+              "peer-memory push, wait inside the next sweep (halo CTAs), direct launches"),
+             ("nccl", dict(p2p=False, sweep_wait=0, graphs=1, overlap=0), "pack / ncclSend / ncclRecv / unpack")]
     if not want_p2p:
-        paths = paths[2:]
+        paths = paths[3:]
     for name, ident, kind, octants, omega in (
             ("cfg2", WORKLOADS["cfg2"]["ident"], "cavity", comm.world, 1.7),
             ("cfg3", WORKLOADS["cfg3"]["ident"], "periodic", 8, 1.9)):
@@ -383,6 +386,7 @@ def multirank_check(comm, mb, want_p2p):
         for pname, opt, _ in paths:
             check(lib.musb200_set_sweep_wait(opt["sweep_wait"]))
             check(lib.musb200_set_graphs(opt["graphs"]))
+            check(lib.musb200_set_overlap(opt["overlap"]))
             sch = mb.Scheme(ident, ld, omega, lambda_=3.0 / 16.0, omega_bulk=omega)
             sch.upload_state(level, init, init)
             on = connect_p2p(comm, sch, level, opt["p2p"])
@@ -398,8 +402,9 @@ def multirank_check(comm, mb, want_p2p):
                 allv = np.concatenate(parts).reshape(-1, QQ)
                 nd = int(np.count_nonzero(allv != ref)) if allv.shape == ref.shape else -1
                 out["%s/%s%s" % (name, pname, "" if (on or not opt["p2p"]) else " (fell back to nccl)")] = nd
-    check(lib.musb200_set_sweep_wait(1))
+    check(lib.musb200_set_sweep_wait(0))
     check(lib.musb200_set_graphs(1))
+    check(lib.musb200_set_overlap(0))
     if comm.rank != 0:
         return None
     return {"multirank_ndiff": int(sum(max(v, 0) for v in out.values()) + sum(1 for v in out.values() if v < 0)),
@@ -424,9 +429,10 @@ def run_single_level(args, comm, mb, wl_name, wl, octants, K, W, sampler, with_e
         ld = mb.DeviceCube(level, QQ, "periodic")
     else:
         ld = mb.LevelDesc(level, QQ, wl["kind"], rank, world, octants=octants)
-    check(lib.musb200_set_overlap(1 if args.overlap else 0))
+    overlap = (not args.no_overlap) and world > 1
+    check(lib.musb200_set_overlap(1 if overlap else 0))
     check(lib.musb200_set_fused_push(1 if args.fused_push else 0))
-    check(lib.musb200_set_sweep_wait(0 if args.no_sweep_wait else 1))
+    check(lib.musb200_set_sweep_wait(1 if args.sweep_wait else 0))
     nbytes = ld.nSize * QQ * 8
     sch = mb.Scheme(ident, ld, wl["omega"], lambda_=3.0 / 16.0, omega_bulk=wl["omega"])
     host_state, hp = None, None
@@ -452,8 +458,10 @@ def run_single_level(args, comm, mb, wl_name, wl, octants, K, W, sampler, with_e
             halo_path = "peer-memory stores over NVLink fused into the sweep kernel + arrival flags"
         elif p2p_on:
             halo_path = "peer-memory stores over NVLink (one push kernel per step), " + (
-                "arrival waited for right after the push" if args.no_sweep_wait or args.overlap else
-                "arrival waited for inside the next sweep by the CTAs that pull from halo rows")
+                "on a second stream overlapping the next sweep's CTAs that pull from no halo row; wait + second "
+                "launch for the CTAs that do" if overlap else
+                "arrival waited for inside the next sweep by the CTAs that pull from halo rows" if args.sweep_wait
+                else "arrival waited for right after the push")
         else:
             halo_path = "NCCL send/recv (pack, group, unpack) after compute"
     lid = cases.lid_values(ld) if wl["kind"] == "cavity" else None
@@ -762,12 +770,13 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cfg3", action="store_true", help="skip the cfg3 block of the default line")
     ap.add_argument("--no-check", action="store_true", help="skip the multi-rank bit-compare of the default line")
-    ap.add_argument("--overlap", action="store_true",
-                    help="sweep the send-halo elements first and overlap their exchange with the rest")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="peer-memory halo exchange strictly after compute (push + wait kernel in the stepping "
+                         "stream) instead of overlapped with the next sweep's halo-free CTAs")
     ap.add_argument("--fused-push", action="store_true",
                     help="peer-memory halo exchange with the link stores fused into the sweep kernel")
-    ap.add_argument("--no-sweep-wait", action="store_true",
-                    help="peer-memory halo exchange: wait right after the push, not inside the next sweep")
+    ap.add_argument("--sweep-wait", action="store_true",
+                    help="peer-memory halo exchange: wait inside the next sweep (halo CTAs) instead of a wait kernel")
     ap.add_argument("--balance", action="store_true",
                     help="cfg4 on N > 1 ranks: cut the space-filling curve by tem_balance_sparta with level "
                          "weights 2^(l - minLevel) instead of equal element counts")

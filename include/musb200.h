@@ -291,18 +291,18 @@ int musb200_set_aux_every_step(int flag);
  * freshly created level are zero.  Collective over the ranks.                               */
 int musb200_fill_helper_elements(int minLevel, int maxLevel);
 
-/* 1: on several ranks the elements that own a send-buffer link (prp_sendHalo) are swept first
- * and their halo exchange (on a second, high-priority stream) overlaps the sweep of the
- * remaining elements; 0 (default): exchange strictly after compute as comm_isend_irecv_real is
- * called in do_fast_singleLevel (mus_control_module.f90:644-649).  Both orders give identical
- * results; the split sweep costs more than the exchange it hides at 256^3 elements per GPU
- * (profiles/r01_multi_gpu.md), so it is opt-in. */
+/* Single level on several ranks with the peer-memory exchange: 1 = the push of step n runs on a
+ * second, high-priority stream WHILE the main launch of step n+1 sweeps every CTA that pulls from
+ * no halo row (a bitmap built from the neighbour list: 92-97 % of the CTAs at 256^3 per GPU); then
+ * the wait, then a second launch for the CTAs that do -- whole CTAs of consecutive elements, so
+ * nothing is lost in coalescing (round 1 split by an element list and lost more than it hid).
+ * 0 (default): exchange strictly after compute as comm_isend_irecv_real is called in
+ * do_fast_singleLevel (mus_control_module.f90:644-649).  Identical results either way. */
 int musb200_set_overlap(int flag);
-/* Peer-memory halo exchange, single level: 1 (default) the wait for the links of step n moves
- * into the sweep of step n+1, where only the CTAs that pull from a halo row wait (a bitmap built
- * from the neighbour list) -- transfer and rank skew hide behind the sweep without splitting it;
- * 0: MPI_Waitall right after the push (exchange strictly after compute, as
- * comm_isend_irecv_real is called in do_fast_singleLevel).  Identical results. */
+/* Peer-memory halo exchange, single level: 1 = the wait for the links of step n moves into the
+ * sweep of step n+1, where only the CTAs that pull from a halo row wait (the same bitmap); 0
+ * (default) = MPI_Waitall right after the push.  Identical results; measured on 2 and 8 B200 the
+ * in-sweep wait is 1-2 % slower than the wait kernel (the push itself is what costs). */
 int musb200_set_sweep_wait(int flag);
 /* Every wait of the peer-memory exchange gives up after `seconds` (default 30; 0 = never): the
  * stream drains, and the next synchronising call (musb200_synchronize, musb200_reduce, ...) returns

@@ -161,6 +161,12 @@ struct PeerLink {
   DevBuf<unsigned long long> arrived;    // [nranks], written by the senders
   DevBuf<unsigned long long> exch;       // this rank's exchange number, bumped by the push kernel
   DevBuf<uint32_t> ctaMask;              // sweep CTAs that pull from a halo row
+  DevBuf<int32_t> haloCtas;              // the same CTAs as a list (second launch of the overlapped exchange)
+  int nHaloCtas = 0, nCtas = 0;
+  // overlapped exchange: sweep done; push done, one event per buffer parity (the push of step n
+  // reads the buffer that the sweep of step n + 2 overwrites)
+  cudaEvent_t evSwept = nullptr, evPushed[2] = {nullptr, nullptr};
+  bool pushedOnce[2] = {false, false};
   DevBuf<unsigned int> ticket;
   // fused push (sweep_push.cu): the send entries grouped by the element that owns them
   DevBuf<uint32_t> pushMask, pushPrefix;
@@ -168,6 +174,9 @@ struct PeerLink {
   DevBuf<uint8_t> pushQ, pushPeer;
   ~PeerLink() {
     for (void *p : opened) cudaIpcCloseMemHandle(p);
+    if (evSwept) cudaEventDestroy(evSwept);
+    for (cudaEvent_t e : evPushed)
+      if (e) cudaEventDestroy(e);
   }
 };
 
@@ -195,9 +204,6 @@ struct Level {
   // elements that own a link of the halo send buffer (prp_sendHalo, set_sendHaloBits
   // mus_construction_module.fpp:2765): swept first so that their exchange overlaps the rest
   PeerLink p2p;
-  DevBuf<int32_t> sendElems;   // 0-based, ascending
-  DevBuf<uint32_t> sendMask;   // 1 bit per element
-  int nSendElems = 0;
   // source = { force }: order 0 (none) / 1 / 2, uniform or per-element SoA [3][S]
   int forceOrder = 0;
   bool forceElem = false;
@@ -237,7 +243,8 @@ struct Context {
   int fusedPush = 0;
   int noFusedBc = 0; // musb200_set_fused_bc(0): always take the two-phase bcBuffer path
   int overlap = 0;   // measured slower than exchange-after-compute at 256^3 per GPU (profiles/)
-  int sweepWait = 1; // peer-memory exchange: the wait for the halo links moves into the next sweep
+  int sweepWait = 0; // peer-memory exchange: 1 = the wait for the halo links moves into the next sweep
+  bool commBusy = false;   // a push is in flight on the communication stream
   unsigned long long timeoutNs = 30000000000ull;   // every wait of the exchange gives up after this
   DevBuf<int> errFlag;                             // {code, peer, exchange lo, exchange hi}, set by a wait
   NcclApi *nccl = nullptr;
@@ -553,7 +560,9 @@ static int exchangeStateAndAux(Level &L, int kind = MUSB200_BUF_HALO) {
   return 0;
 }
 
-enum { SWEEP_ALL = 0, SWEEP_SENDHALO = 1, SWEEP_INTERIOR = 2 };
+// SWEEP_ALL: every CTA; overlapped exchange: SWEEP_MAIN every CTA that pulls from no halo row,
+// then (after the wait) SWEEP_HALO the remaining ones, both as whole CTAs of consecutive elements
+enum { SWEEP_ALL = 0, SWEEP_MAIN = 1, SWEEP_HALO = 2 };
 static int sweep(Level &L, bool writeAux, int part = SWEEP_ALL, bool push = false) {
   if (!L.relaxSet) return setError(MUSB200_ERR_STATE, "musb200_set_relaxation missing");
   Timed t(T_COMPUTE);
@@ -583,8 +592,9 @@ static int sweep(Level &L, bool writeAux, int part = SWEEP_ALL, bool push = fals
   a.nbr = L.nbr.p;
   a.aux = L.aux.p;
   a.omega = L.elemOmega ? L.omega.p : nullptr;
-  a.list = nullptr;
-  a.skip = nullptr;
+  a.ctaList = nullptr;
+  a.ctaMode = 0;
+  a.nCtas = 0;
   a.S = L.S;
   a.first = 0;
   a.count = L.nSolve;
@@ -603,14 +613,18 @@ static int sweep(Level &L, bool writeAux, int part = SWEEP_ALL, bool push = fals
     }
   }
   // the previous step's halo links may still be in flight: the CTAs that need them wait
-  if (part == SWEEP_ALL && L.p2p.pendingWait && L.p2p.sweepWait && g.sweepWait) {
+  if (part == SWEEP_MAIN) {
+    a.wait = haloWait(L, true);      // the mask only: these CTAs need no halo row, nothing to wait for
+    a.ctaMode = 1;
+  } else if (part == SWEEP_HALO) {
+    MUSB_TRY(ensureArrived(L));      // MPI_Waitall of the push that has been overlapping SWEEP_MAIN
+    a.ctaList = L.p2p.haloCtas.p; a.ctaMode = 2; a.nCtas = L.p2p.nHaloCtas;
+  } else if (L.p2p.pendingWait && L.p2p.sweepWait && g.sweepWait) {
     a.wait = haloWait(L, true);
     L.p2p.pendingWait = false;
   } else {
     MUSB_TRY(ensureArrived(L));
   }
-  if (part == SWEEP_SENDHALO) { a.list = L.sendElems.p; a.count = L.nSendElems; }
-  if (part == SWEEP_INTERIOR) a.skip = L.sendMask.p;
   MUSB_TRY(launchSweep(L.QQ, L.relax, L.kind, a, g.stream));
   ++g.launches;
   return 0;
@@ -665,18 +679,30 @@ static int levelAdvance(int iLevel, int minLevel, int maxLevel, bool lastCycle) 
   // schedule reads it; musb200_aux_probe / _download compute it on demand)
   const bool writeAux = g.auxEveryStep == 1 || multi || (lastCycle && g.auxEveryStep != 2) || L.auxForBc;
   L.auxValid = writeAux;
-  if (!multi && g.nranks > 1 && g.overlap && L.nSendElems > 0 && !passive) {
-    // single level, several ranks: sweep the send-halo elements first, then exchange them on the
-    // communication stream while the remaining elements are swept (the reference exchanges
-    // strictly after compute, mus_control_module.f90:605-649; results are identical because the
-    // packed links are final once their elements are collided and the unpack touches halo rows only)
-    MUSB_TRY(sweep(L, writeAux, SWEEP_SENDHALO));
-    MUSB_CUDA(cudaEventRecord(g.evBoundary, g.stream));
-    MUSB_CUDA(cudaStreamWaitEvent(g.commStream, g.evBoundary, 0));
-    MUSB_TRY(exchange(L, MUSB200_BUF_HALO, L.state[L.nNext].p, L.QQ, g.commStream));   // push + wait
-    MUSB_CUDA(cudaEventRecord(g.evComm, g.commStream));
-    MUSB_TRY(sweep(L, writeAux, SWEEP_INTERIOR));
-    MUSB_CUDA(cudaStreamWaitEvent(g.stream, g.evComm, 0));
+  if (!multi && g.nranks > 1 && g.overlap && L.p2p.on && L.p2p.nHaloCtas > 0 && !passive &&
+      (L.send[MUSB200_BUF_HALO].total > 0 || L.recv[MUSB200_BUF_HALO].total > 0)) {
+    // single level, several ranks, exchange overlapped with compute WITHOUT giving up coalescing:
+    // the push of step n runs on the communication stream while the main launch of step n+1
+    // sweeps every CTA that pulls from no halo row (92-97 % of them); then the wait, then a
+    // second launch for the CTAs that do -- whole CTAs of consecutive elements from a list, not
+    // an element list.  The reference exchanges strictly after compute
+    // (mus_control_module.f90:605-649); the results are identical: the pushed links are final
+    // once sweep n has finished, the boundary kernels of step n+1 touch other slots (a link a
+    // boundary rewrites points at a wall, no rank pulls it), and peers store into halo rows only.
+    PeerLink &P = L.p2p;
+    // this step writes state(:, next): the push that last read that buffer (two steps ago) must be done
+    if (P.pushedOnce[L.nNext]) MUSB_CUDA(cudaStreamWaitEvent(g.stream, P.evPushed[L.nNext], 0));
+    MUSB_TRY(sweep(L, writeAux, SWEEP_MAIN));
+    MUSB_TRY(sweep(L, writeAux, SWEEP_HALO));                 // waits for the push of the previous step first
+    MUSB_CUDA(cudaEventRecord(P.evSwept, g.stream));
+    MUSB_CUDA(cudaStreamWaitEvent(g.commStream, P.evSwept, 0));
+    {
+      Timed t(T_COMM, g.commStream);
+      MUSB_TRY(pushHalo(L, false, g.commStream, false));       // pendingWait = true
+    }
+    MUSB_CUDA(cudaEventRecord(P.evPushed[L.nNext], g.commStream));
+    P.pushedOnce[L.nNext] = true;
+    g.commBusy = true;
     return 0;
   }
   // single level on several ranks with the peer-memory exchange: the sweep pushes the halo links
@@ -1506,20 +1532,6 @@ int musb200_comm_register(int level, int buf_kind, int dir, int nProcs, const in
     MUSB_TRY(c.buf.alloc((size_t)std::max(1, c.total + c.auxTotal)));   // state links | auxField entries
     MUSB_CUDA(cudaStreamSynchronize(g.stream));
   }
-  if (buf_kind == MUSB200_BUF_HALO && dir == MUSB200_DIR_SEND) {
-    std::vector<uint32_t> mask(((size_t)L->S + 31) / 32, 0u);
-    std::vector<int32_t> elems;
-    for (int i = 0; i < c.total; ++i) {
-      const int e = (pos[i] - 1) / L->QQ;
-      if (e < 0 || e >= L->nSolve) return setError(MUSB200_ERR_ARG, "send position outside the solved elements");
-      if (!((mask[e >> 5] >> (e & 31)) & 1u)) { mask[e >> 5] |= 1u << (e & 31); elems.push_back(e); }
-    }
-    std::sort(elems.begin(), elems.end());
-    L->nSendElems = (int)elems.size();
-    MUSB_TRY(L->sendElems.upload(elems.data(), elems.size(), g.stream));
-    MUSB_TRY(L->sendMask.upload(mask.data(), mask.size(), g.stream));
-    MUSB_CUDA(cudaStreamSynchronize(g.stream));
-  }
   return 0;
 }
 
@@ -1704,6 +1716,21 @@ int musb200_p2p_connect(int level, int nProcs, const int32_t *proc, const void *
     MUSB_CUDA(cudaMemsetAsync(P.ctaMask.p, 0, nCtaWords * sizeof(uint32_t), g.stream));
     MUSB_TRY(launchHaloCtaMask(QQ, L->nbr.p, L->S, L->nSolve, L->nFluid + L->nGFC + L->nGFF, block,
                                P.ctaMask.p, g.stream));
+    {
+      std::vector<uint32_t> hm(nCtaWords);
+      MUSB_CUDA(cudaMemcpyAsync(hm.data(), P.ctaMask.p, nCtaWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, g.stream));
+      MUSB_CUDA(cudaStreamSynchronize(g.stream));
+      std::vector<int32_t> list;
+      P.nCtas = divUp(std::max(L->nSolve, 1), block);
+      for (int c = 0; c < P.nCtas; ++c)
+        if ((hm[c >> 5] >> (c & 31)) & 1u) list.push_back(c);
+      P.nHaloCtas = (int)list.size();
+      if (list.empty()) list.push_back(0);
+      MUSB_TRY(P.haloCtas.upload(list.data(), list.size(), g.stream));
+      if (!P.evSwept) MUSB_CUDA(cudaEventCreateWithFlags(&P.evSwept, cudaEventDisableTiming));
+      for (int b = 0; b < 2; ++b)
+        if (!P.evPushed[b]) MUSB_CUDA(cudaEventCreateWithFlags(&P.evPushed[b], cudaEventDisableTiming));
+    }
     std::vector<int> a1(P.sendRank), a2(P.recvRank);
     std::sort(a1.begin(), a1.end());
     std::sort(a2.begin(), a2.end());
@@ -1895,7 +1922,13 @@ static int stepImpl(int minLevel, int maxLevel, int nCoarseCycles) {
     MUSB_TRY(levelStep(minLevel, minLevel, maxLevel, it == nCoarseCycles - 1));
   // MPI_Waitall of the last exchange: whatever follows this call sees complete halo rows
   return forEachStepSlot([&] {
-    for (int l = minLevel; l <= maxLevel; ++l) MUSB_TRY(ensureArrived(*findLevel(l)));
+    for (int l = minLevel; l <= maxLevel; ++l) {
+      Level *Lw = findLevel(l);
+      MUSB_TRY(ensureArrived(*Lw));
+      for (int b = 0; b < 2; ++b)
+        if (g.commBusy && Lw->p2p.pushedOnce[b]) MUSB_CUDA(cudaStreamWaitEvent(g.stream, Lw->p2p.evPushed[b], 0));
+    }
+    g.commBusy = false;
     return 0;
   });
 }

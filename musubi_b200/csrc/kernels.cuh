@@ -75,8 +75,13 @@ struct SweepArgs {
   const uint32_t *nbr;     // [QQ-1][S] encoded pull sources (rest direction is implicit)
   double *aux;             // [4][S] rho, ux, uy, uz (written when write_aux)
   const double *omega;     // per-element omega or nullptr (uniform)
-  const int32_t *list;     // optional element list (0-based) or nullptr
-  const uint32_t *skip;    // optional bitmask (1 bit / element): skip when set
+  // split of the sweep by whole CTAs for the overlapped halo exchange (several ranks, p2p.cu):
+  // ctaMode 0 every CTA (those of wait.ctaMask wait for the halo links first); 1 the CTAs of
+  // wait.ctaMask return at once (they are swept by the second launch); 2 only the CTAs listed in
+  // ctaList (gridDim.x of them)
+  const int32_t *ctaList;
+  int ctaMode;
+  int nCtas;               // ctaMode 2: length of ctaList
   long long S;
   int first;               // first element (0-based) of the contiguous range
   int count;               // number of elements (range) or list entries

@@ -114,15 +114,12 @@ struct ForceSrc {
 template <int QQ, int RELAX, bool INCOMP, int VAR>
 __global__ void __launch_bounds__(sweepThreads<QQ>(), sweepMinBlocks<QQ>()) sweepKernel(const SweepArgs a) {
   constexpr bool FORCE = VAR == 1, PUSH = VAR == 2;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // a CTA always sweeps blockDim.x CONSECUTIVE elements (full coalescing); which block of them is
+  // blockIdx.x, or -- second launch of the overlapped exchange -- an entry of the halo-CTA list
+  const int cta = a.ctaMode == 2 ? a.ctaList[blockIdx.x] : (int)blockIdx.x;
+  const int i = cta * blockDim.x + threadIdx.x;
   if (i >= a.count) return;
-  int e;
-  if (a.list != nullptr) {
-    e = a.list[i];
-  } else {
-    e = a.first + i;
-    if (a.skip != nullptr && ((a.skip[e >> 5] >> (e & 31)) & 1u)) return;
-  }
+  const int e = a.first + i;
   const long long S = a.S;
 
   double f[QQ];
@@ -132,11 +129,12 @@ __global__ void __launch_bounds__(sweepThreads<QQ>(), sweepMinBlocks<QQ>()) swee
     // The CTA's mask word is fetched together with the index loads, so the check costs no extra
     // memory round trip at the head of every CTA.
     uint32_t maskWord = 0u;
-    if (a.wait.ctaMask != nullptr) maskWord = __ldg(a.wait.ctaMask + (blockIdx.x >> 5));
+    if (a.wait.ctaMask != nullptr && a.ctaMode != 2) maskWord = __ldg(a.wait.ctaMask + (cta >> 5));
     uint32_t n[QQ - 1];
 #pragma unroll
     for (int q = 0; q < QQ - 1; ++q) n[q] = __ldcs(a.nbr + q * S + e);
-    const bool halo = (maskWord >> (blockIdx.x & 31)) & 1u;   // uniform over the CTA
+    const bool halo = (maskWord >> (cta & 31)) & 1u;   // uniform over the CTA
+    if (halo && a.ctaMode == 1) return;               // swept by the second launch, after the wait
     if (halo) {
       if (threadIdx.x == 0) waitHaloArrival(a.wait);   // thread 0 of a CTA is always in range
       __syncthreads();                                 // threads out of range have exited
@@ -278,7 +276,9 @@ template <int QQ, int RELAX, bool INCOMP, int VAR>
 static int launchT(const SweepArgs &a, cudaStream_t st) {
   if (a.count <= 0) return 0;
   const int block = sweepThreads<QQ>();
-  sweepKernel<QQ, RELAX, INCOMP, VAR><<<divUp(a.count, block), block, 0, st>>>(a);
+  const int grid = a.ctaMode == 2 ? a.nCtas : divUp(a.count, block);
+  if (grid <= 0) return 0;
+  sweepKernel<QQ, RELAX, INCOMP, VAR><<<grid, block, 0, st>>>(a);
   MUSB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -186,8 +186,8 @@ def main():
                          "FromCoarser / FromFiner buffers (the reference's form of the run)")
     ap.add_argument("--fused-push", action="store_true",
                     help="peer-memory exchange with the push fused into the sweep kernel")
-    ap.add_argument("--no-sweep-wait", action="store_true",
-                    help="peer-memory exchange: wait right after the push instead of inside the next sweep")
+    ap.add_argument("--sweep-wait", action="store_true",
+                    help="peer-memory exchange: wait inside the next sweep (halo CTAs) instead of a wait kernel")
     ap.add_argument("--no-graphs", action="store_true", help="direct launches instead of CUDA-graph replay")
     ap.add_argument("--restart", action="store_true",
                     help="gpu-ml: restart into a fresh scheme (fluid PDFs only + musb200_fill_helper_elements)")
@@ -222,7 +222,8 @@ def main():
         dist.broadcast(t, 0)
         mb.mus_init(rank, world, int(os.environ.get("LOCAL_RANK", rank)), bytes(t.numpy().tobytes()))
         check(lib.musb200_set_exchange_timeout(1.5))
-        check(lib.musb200_set_sweep_wait(0 if a.no_sweep_wait else 1))
+        check(lib.musb200_set_sweep_wait(1 if a.sweep_wait else 0))
+        check(lib.musb200_set_overlap(1 if a.overlap else 0))
         ident = {"kind": "fluid", "relaxation": a.relaxation, "layout": a.layout}
         sch = mb.Scheme(ident, ld, 1.7, lambda_=0.25, omega_bulk=1.3)
         rho, vel = cases.taylor_green(ld)
@@ -315,7 +316,7 @@ def main():
         # single-domain oracle = the truth for every rank
         mb._lib.check(mb._lib.lib.musb200_set_overlap(1 if a.overlap else 0))
         mb._lib.check(mb._lib.lib.musb200_set_fused_push(1 if a.fused_push else 0))
-        mb._lib.check(mb._lib.lib.musb200_set_sweep_wait(0 if a.no_sweep_wait else 1))
+        mb._lib.check(mb._lib.lib.musb200_set_sweep_wait(1 if a.sweep_wait else 0))
         mb._lib.check(mb._lib.lib.musb200_set_graphs(0 if a.no_graphs else 1))
         gl = mo.build_level_desc(a.level, QQ, a.kind, octants=a.octants)
         ref = mo.Scheme(gl, a.relaxation, "fluid", omega=1.7, lambda_=0.25, omega_bulk=1.3)

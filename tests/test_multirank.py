@@ -50,19 +50,22 @@ def _ngpu():
 @pytest.mark.gpu
 @pytest.mark.parametrize("layout,relax,kind,extra", [
     ("d3q27", "mrt", "periodic", []), ("d3q19", "trt", "cavity", []), ("d3q19", "bgk", "channel", []),
-    ("d3q27", "mrt", "periodic", ["--overlap"]),             # send-halo elements first, 2 streams
+    ("d3q27", "mrt", "periodic", ["--overlap"]),             # without peer memory: plain exchange
     ("d3q19", "trt", "cavity", ["--octants", "2"]),          # the weak-scaling mesh of bench.py
     ("d3q27", "mrt", "periodic", ["--p2p"]),                 # peer-memory halo exchange
     ("d3q19", "trt", "cavity", ["--octants", "2", "--p2p"]),
-    ("d3q19", "bgk", "channel", ["--p2p", "--overlap"]),
+    ("d3q19", "bgk", "channel", ["--p2p", "--overlap"]),     # push overlapped with the halo-free CTAs
+    ("d3q19", "trt", "cavity", ["--octants", "2", "--p2p", "--overlap"]),
+    ("d3q27", "mrt", "periodic", ["--p2p", "--overlap"]),
     ("d3q27", "mrt", "periodic", ["--p2p", "--fused-push"]),      # links stored by the sweep itself
     ("d3q19", "trt", "cavity", ["--octants", "2", "--p2p", "--fused-push"]),
-    ("d3q27", "mrt", "periodic", ["--p2p", "--no-sweep-wait"]),   # MPI_Waitall right after the push
+    ("d3q27", "mrt", "periodic", ["--p2p", "--sweep-wait"]),      # wait inside the next sweep (halo CTAs)
     ("d3q19", "trt", "cavity", ["--octants", "2", "--p2p", "--no-graphs"]),   # direct launches
     ("d3q19", "bgk", "channel", ["--p2p"])],                      # pressure boundary reads halo neighbours
     ids=["mrt27-periodic", "trt19-cavity", "bgk19-channel", "mrt27-periodic-overlap", "trt19-cavity-2oct",
-         "mrt27-periodic-p2p", "trt19-cavity-2oct-p2p", "bgk19-channel-p2p-overlap",
-         "mrt27-periodic-p2p-fusedpush", "trt19-cavity-2oct-p2p-fusedpush", "mrt27-periodic-p2p-nosweepwait",
+         "mrt27-periodic-p2p", "trt19-cavity-2oct-p2p", "bgk19-channel-p2p-overlap", "trt19-cavity-2oct-p2p-overlap",
+         "mrt27-periodic-p2p-overlap",
+         "mrt27-periodic-p2p-fusedpush", "trt19-cavity-2oct-p2p-fusedpush", "mrt27-periodic-p2p-sweepwait",
          "trt19-cavity-2oct-p2p-nographs", "bgk19-channel-p2p"])
 def test_multi_gpu_matches_single_domain_oracle(layout, relax, kind, extra):
     n = _ngpu()
@@ -103,7 +106,8 @@ def test_multi_gpu_multilevel_matches_single_domain_oracle(layout, relax, levels
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("extra", [[], ["--no-sweep-wait"]], ids=["wait-in-sweep", "wait-after-push"])
+@pytest.mark.parametrize("extra", [[], ["--sweep-wait"], ["--overlap"]],
+                         ids=["wait-after-push", "wait-in-sweep", "overlapped"])
 def test_exchange_timeout_surfaces_as_an_error_instead_of_a_hang(extra):
     """a rank that stops stepping: the others' waits give up after the configured timeout and the
     next synchronising call returns MUSB200_ERR_NCCL (the reference aborts all ranks through
