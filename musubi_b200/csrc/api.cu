@@ -159,7 +159,8 @@ struct PeerLink {
   DevBuf<uint8_t> auxPeerOf;
   int nAux = 0;
   DevBuf<unsigned long long> arrived;    // [nranks], written by the senders
-  DevBuf<unsigned long long> exch;       // this rank's exchange number, bumped by the push kernel
+  DevBuf<unsigned long long> exch;       // [3]: this rank's exchange number, bumped by the push kernel (or, overlapped
+                                         // exchange, in the stepping stream) | the number parked for the push in flight, per parity
   DevBuf<uint32_t> ctaMask;              // sweep CTAs that pull from a halo row
   DevBuf<int32_t> haloCtas;              // the same CTAs as a list (second launch of the overlapped exchange)
   int nHaloCtas = 0, nCtas = 0;
@@ -449,7 +450,7 @@ static int ensureArrived(Level &L, cudaStream_t st) {
 }
 // the sending half: one kernel stores every link (and, withAux, every auxField entry of the
 // communicated elements) into the receivers' halo rows and publishes the exchange number
-static int pushHalo(Level &L, bool withAux, cudaStream_t st, bool pushed) {
+static int pushHalo(Level &L, bool withAux, cudaStream_t st, bool pushed, const unsigned long long *publish = nullptr) {
   PeerLink &P = L.p2p;
   CommBuf &s = L.send[MUSB200_BUF_HALO];
   P2PArgs a{};
@@ -464,7 +465,7 @@ static int pushHalo(Level &L, bool withAux, cudaStream_t st, bool pushed) {
     a.remoteS[k] = P.remoteS[k];
     a.remoteArrived[k] = P.remoteArrived[k];
   }
-  a.exch = P.exch.p; a.ticket = P.ticket.p;
+  a.exch = P.exch.p; a.ticket = P.ticket.p; a.publish = publish;
   a.handshake = a.nAux > 0 ? 1 : 0;
   a.nranks = g.nranks; a.ready = P.arrived.p + g.nranks;
   for (int k = 0; k < a.nSendPeers; ++k) a.sendRank[k] = P.sendRank[k];
@@ -560,9 +561,9 @@ static int exchangeStateAndAux(Level &L, int kind = MUSB200_BUF_HALO) {
   return 0;
 }
 
-// SWEEP_ALL: every CTA; overlapped exchange: SWEEP_MAIN every CTA that pulls from no halo row,
-// then (after the wait) SWEEP_HALO the remaining ones, both as whole CTAs of consecutive elements
-enum { SWEEP_ALL = 0, SWEEP_MAIN = 1, SWEEP_HALO = 2 };
+// SWEEP_ALL: every CTA in natural order; SWEEP_HALO_LAST (overlapped exchange): the CTAs that pull
+// from a halo row are moved to the end of the launch and wait there for the halo links
+enum { SWEEP_ALL = 0, SWEEP_HALO_LAST = 1 };
 static int sweep(Level &L, bool writeAux, int part = SWEEP_ALL, bool push = false) {
   if (!L.relaxSet) return setError(MUSB200_ERR_STATE, "musb200_set_relaxation missing");
   Timed t(T_COMPUTE);
@@ -594,6 +595,7 @@ static int sweep(Level &L, bool writeAux, int part = SWEEP_ALL, bool push = fals
   a.omega = L.elemOmega ? L.omega.p : nullptr;
   a.ctaList = nullptr;
   a.ctaMode = 0;
+  a.nMain = 0;
   a.nCtas = 0;
   a.S = L.S;
   a.first = 0;
@@ -613,12 +615,10 @@ static int sweep(Level &L, bool writeAux, int part = SWEEP_ALL, bool push = fals
     }
   }
   // the previous step's halo links may still be in flight: the CTAs that need them wait
-  if (part == SWEEP_MAIN) {
-    a.wait = haloWait(L, true);      // the mask only: these CTAs need no halo row, nothing to wait for
-    a.ctaMode = 1;
-  } else if (part == SWEEP_HALO) {
-    MUSB_TRY(ensureArrived(L));      // MPI_Waitall of the push that has been overlapping SWEEP_MAIN
-    a.ctaList = L.p2p.haloCtas.p; a.ctaMode = 2; a.nCtas = L.p2p.nHaloCtas;
+  if (part == SWEEP_HALO_LAST) {
+    a.wait = haloWait(L, true);
+    a.ctaList = L.p2p.haloCtas.p; a.ctaMode = 1; a.nMain = L.p2p.nCtas; a.nCtas = L.p2p.nHaloCtas;
+    L.p2p.pendingWait = false;       // the appended CTAs do the wait
   } else if (L.p2p.pendingWait && L.p2p.sweepWait && g.sweepWait) {
     a.wait = haloWait(L, true);
     L.p2p.pendingWait = false;
@@ -682,23 +682,30 @@ static int levelAdvance(int iLevel, int minLevel, int maxLevel, bool lastCycle) 
   if (!multi && g.nranks > 1 && g.overlap && L.p2p.on && L.p2p.nHaloCtas > 0 && !passive &&
       (L.send[MUSB200_BUF_HALO].total > 0 || L.recv[MUSB200_BUF_HALO].total > 0)) {
     // single level, several ranks, exchange overlapped with compute WITHOUT giving up coalescing:
-    // the push of step n runs on the communication stream while the main launch of step n+1
-    // sweeps every CTA that pulls from no halo row (92-97 % of them); then the wait, then a
-    // second launch for the CTAs that do -- whole CTAs of consecutive elements from a list, not
-    // an element list.  The reference exchanges strictly after compute
-    // (mus_control_module.f90:605-649); the results are identical: the pushed links are final
-    // once sweep n has finished, the boundary kernels of step n+1 touch other slots (a link a
-    // boundary rewrites points at a wall, no rank pulls it), and peers store into halo rows only.
+    // the push of step n runs on the communication stream while step n+1 is being swept.  The
+    // CTAs that pull from a halo row (3-12 % of them) are moved to the END of that launch --
+    // whole CTAs of consecutive elements, appended from a list -- and wait there for the peers'
+    // links, which by then have long arrived; every other CTA runs in natural order at once.
+    // (Round 1 split by an element list and lost coalescing; a second launch for the halo CTAs
+    // costs five latency-bound waves: profiles/r02_multi_gpu.md.)  The reference exchanges strictly
+    // after compute (mus_control_module.f90:605-649); the results are identical: the pushed links
+    // are final once sweep n has finished, the boundary kernels of step n+1 touch other slots (a
+    // link a boundary rewrites points at a wall, no rank pulls it), peers store into halo rows only.
+    // No waiting CTA can starve a push: a rank's push n is enqueued (high-priority stream) when
+    // its sweep n ends, the first waiting CTA of sweep n+1 is dispatched after all its other CTAs.
     PeerLink &P = L.p2p;
     // this step writes state(:, next): the push that last read that buffer (two steps ago) must be done
     if (P.pushedOnce[L.nNext]) MUSB_CUDA(cudaStreamWaitEvent(g.stream, P.evPushed[L.nNext], 0));
-    MUSB_TRY(sweep(L, writeAux, SWEEP_MAIN));
-    MUSB_TRY(sweep(L, writeAux, SWEEP_HALO));                 // waits for the push of the previous step first
+    MUSB_TRY(sweep(L, writeAux, SWEEP_HALO_LAST));
+    // the exchange number advances here, in the stepping stream: the next wait reads it in
+    // stream order, whenever the push on the other stream gets to run
+    MUSB_TRY(launchBumpExch(P.exch.p, P.exch.p + 1 + L.nNext, g.stream));
+    ++g.launches;
     MUSB_CUDA(cudaEventRecord(P.evSwept, g.stream));
     MUSB_CUDA(cudaStreamWaitEvent(g.commStream, P.evSwept, 0));
     {
       Timed t(T_COMM, g.commStream);
-      MUSB_TRY(pushHalo(L, false, g.commStream, false));       // pendingWait = true
+      MUSB_TRY(pushHalo(L, false, g.commStream, false, P.exch.p + 1 + L.nNext));       // pendingWait = true
     }
     MUSB_CUDA(cudaEventRecord(P.evPushed[L.nNext], g.commStream));
     P.pushedOnce[L.nNext] = true;
@@ -1556,10 +1563,10 @@ int musb200_p2p_export(int level, void *blob) {
   if (P.arrived.n == 0) {
     MUSB_TRY(P.arrived.alloc((size_t)2 * std::max(g.nranks, 1)));
     MUSB_TRY(P.ticket.alloc(1));
-    MUSB_TRY(P.exch.alloc(1));
+    MUSB_TRY(P.exch.alloc(3));
     MUSB_CUDA(cudaMemsetAsync(P.arrived.p, 0, P.arrived.n * sizeof(unsigned long long), g.stream));
     MUSB_CUDA(cudaMemsetAsync(P.ticket.p, 0, sizeof(unsigned int), g.stream));
-    MUSB_CUDA(cudaMemsetAsync(P.exch.p, 0, sizeof(unsigned long long), g.stream));
+    MUSB_CUDA(cudaMemsetAsync(P.exch.p, 0, 3 * sizeof(unsigned long long), g.stream));
     MUSB_CUDA(cudaStreamSynchronize(g.stream));
   }
   P2PBlob b;

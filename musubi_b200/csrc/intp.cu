@@ -341,11 +341,43 @@ __global__ void __launch_bounds__(128) intpTileKernel(const double *__restrict__
   const int u0 = tileSrcStart[blockIdx.x], nU = tileSrcStart[blockIdx.x + 1] - u0;
   const int e0 = srcOffset[t0], nE = srcOffset[t0 + nT] - e0;
   const double2 *sc2 = reinterpret_cast<const double2 *>(scratch);
-  for (int idx = threadIdx.x; idx < nU * QQ; idx += blockDim.x) {
-    const int r = idx / QQ, d = idx - r * QQ;
-    sm2[idx] = sc2[(long long)tileSrc[u0 + r] * QQ + d];
+  {
+    // all of a thread's loads in flight at once (index, then row piece): the loop form ran its
+    // <= 10 iterations back to back, two dependent memory latencies each -- 44 % of the kernel's
+    // stall samples sat on the stores of this staging phase (profiles/r02_intp_cfg4.md)
+    constexpr int ITER = (kTileSrc * QQ + 127) / 128;
+    int srcRow[ITER];
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+      const int idx = threadIdx.x + it * 128;
+      srcRow[it] = idx < nU * QQ ? tileSrc[u0 + idx / QQ] : -1;
+    }
+    double2 v[ITER];
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+      const int idx = threadIdx.x + it * 128;
+      if (srcRow[it] >= 0) v[it] = sc2[(long long)srcRow[it] * QQ + (idx % QQ)];
+    }
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+      const int idx = threadIdx.x + it * 128;
+      if (srcRow[it] >= 0) sm2[idx] = v[it];
+    }
   }
-  for (int e = threadIdx.x; e < nE; e += blockDim.x) rowOf[e] = localSrc[e0 + e];
+  {
+    constexpr int ITER = kTileEnt / 128;
+    uint8_t b[ITER];
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+      const int e = threadIdx.x + it * 128;
+      b[it] = e < nE ? localSrc[e0 + e] : 0;
+    }
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+      const int e = threadIdx.x + it * 128;
+      if (e < nE) rowOf[e] = b[it];
+    }
+  }
   if (threadIdx.x < nT) {
     const int4 mt = tgtMeta[t0 + threadIdx.x];
     meta[threadIdx.x] = mt;
@@ -361,13 +393,40 @@ __global__ void __launch_bounds__(128) intpTileKernel(const double *__restrict__
   if (MODE != 1)
     for (int k = threadIdx.x; k < 3 * nT; k += blockDim.x) xyz[4 * (k / 3) + k % 3] = coord[3 * t0 + k];
   if (MODE == 1) {
-    for (int e = threadIdx.x; e < nE; e += blockDim.x) mats[e] = weights[e0 + e];
+    constexpr int ITER = kTileEnt / 128;
+    double w[ITER];
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+      const int e = threadIdx.x + it * 128;
+      w[it] = e < nE ? weights[e0 + e] : 0.0;
+    }
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+      const int e = threadIdx.x + it * 128;
+      if (e < nE) mats[e] = w[it];
+    }
   } else {
-    int off = 0;
-    for (int m = tileMatStart[blockIdx.x]; m < tileMatStart[blockIdx.x + 1]; ++m) {
-      const int base = tileMat[2 * m], len = tileMat[2 * m + 1];
-      for (int k = threadIdx.x; k < len; k += blockDim.x) mats[off + k] = matricesT[base + k];
-      off += len;
+    // the tile's distinct matrices lie back to back in tileMat's order: thread k of the staged
+    // area finds its matrix by walking the (few) lengths, no dependent loads between matrices
+    const int m0 = tileMatStart[blockIdx.x], m1 = tileMatStart[blockIdx.x + 1];
+    constexpr int ITER = kTileMat / 128;
+    double c[ITER];
+    int total = 0;
+    for (int m = m0; m < m1; ++m) total += tileMat[2 * m + 1];
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+      const int k = threadIdx.x + it * 128;
+      c[it] = 0.0;
+      if (k < total) {
+        int off = 0, m = m0;
+        while (k >= off + tileMat[2 * m + 1]) { off += tileMat[2 * m + 1]; ++m; }
+        c[it] = matricesT[tileMat[2 * m] + (k - off)];
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+      const int k = threadIdx.x + it * 128;
+      if (k < total) mats[k] = c[it];
     }
   }
   __syncthreads();

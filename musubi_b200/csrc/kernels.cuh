@@ -75,13 +75,14 @@ struct SweepArgs {
   const uint32_t *nbr;     // [QQ-1][S] encoded pull sources (rest direction is implicit)
   double *aux;             // [4][S] rho, ux, uy, uz (written when write_aux)
   const double *omega;     // per-element omega or nullptr (uniform)
-  // split of the sweep by whole CTAs for the overlapped halo exchange (several ranks, p2p.cu):
-  // ctaMode 0 every CTA (those of wait.ctaMask wait for the halo links first); 1 the CTAs of
-  // wait.ctaMask return at once (they are swept by the second launch); 2 only the CTAs listed in
-  // ctaList (gridDim.x of them)
+  // re-ordering of the sweep by whole CTAs for the overlapped halo exchange (several ranks, p2p.cu):
+  // ctaMode 0: natural order, the CTAs of wait.ctaMask wait for the halo links before they gather;
+  // ctaMode 1: the grid is nMain + nCtas CTAs -- the first nMain in natural order, of which the
+  // CTAs of wait.ctaMask return at once; they are appended as ctaList[0 .. nCtas) and wait there,
+  // i.e. at the END of the launch, when the push that overlapped its beginning has long arrived
   const int32_t *ctaList;
   int ctaMode;
-  int nCtas;               // ctaMode 2: length of ctaList
+  int nMain, nCtas;
   long long S;
   int first;               // first element (0-based) of the contiguous range
   int count;               // number of elements (range) or list entries
@@ -194,7 +195,8 @@ struct P2PArgs {
   double *remoteAux[kMaxPeers];                // receiver's auxField, peer-mapped
   long long remoteS[kMaxPeers];
   unsigned long long *remoteArrived[kMaxPeers];  // receiver's arrived[nranks], peer-mapped
-  unsigned long long *exch;     // my exchange number, bumped by the kernel
+  unsigned long long *exch;     // my exchange number, bumped by the kernel ...
+  const unsigned long long *publish;   // ... unless set: the number to publish, bumped in the stepping stream
   unsigned int *ticket;
   // auxField rows are single-buffered: before storing, wait until every receiver has announced
   // that it no longer reads the previous exchange (ready[] sits behind arrived[], same mapping)
@@ -211,6 +213,9 @@ int launchPushHalo(const P2PArgs &a, cudaStream_t st);
 int launchSignalHalo(const P2PArgs &a, cudaStream_t st);
 // MPI_Waitall of the exchange as a one-thread kernel
 int launchWaitHalo(const HaloWait &w, cudaStream_t st);
+// overlapped exchange: the exchange number advances in the STEPPING stream (the waits read it
+// there); the push on the communication stream publishes the value parked in *slot
+int launchBumpExch(unsigned long long *exch, unsigned long long *slot, cudaStream_t st);
 // bitmap of the sweep CTAs (block elements each) that pull from rows >= haloStart
 int launchHaloCtaMask(int QQ, const uint32_t *nbr, long long S, int nSolve, int haloStart, int block,
                       uint32_t *mask, cudaStream_t st);

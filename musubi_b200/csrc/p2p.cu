@@ -116,14 +116,31 @@ __global__ void __launch_bounds__(256) pushHaloKernel(P2PArgs a) {
   const unsigned int ticket = atomicAdd(a.ticket, 1u);
   if (ticket != gridDim.x - 1) return;
   *a.ticket = 0u;                      // ready for the next launch (stream order)
-  const unsigned long long count = *a.exch + 1ull;
-  *a.exch = count;
+  unsigned long long count;
+  if (a.publish != nullptr) {
+    count = *reinterpret_cast<const volatile unsigned long long *>(a.publish);
+  } else {
+    count = *a.exch + 1ull;
+    *a.exch = count;
+  }
   __threadfence_system();
   for (int k = 0; k < a.nSendPeers; ++k) {
     volatile unsigned long long *flag = a.remoteArrived[k] + a.myRank;
     *flag = count;
   }
   __threadfence_system();
+}
+
+__global__ void bumpExchKernel(unsigned long long *exch, unsigned long long *slot) {
+  const unsigned long long n = *exch + 1ull;
+  *exch = n;
+  *slot = n;
+}
+
+int launchBumpExch(unsigned long long *exch, unsigned long long *slot, cudaStream_t st) {
+  bumpExchKernel<<<1, 1, 0, st>>>(exch, slot);
+  MUSB_CUDA(cudaGetLastError());
+  return 0;
 }
 
 // the publishing half alone, for steps whose links were stored by the sweep itself

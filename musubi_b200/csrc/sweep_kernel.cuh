@@ -116,7 +116,8 @@ __global__ void __launch_bounds__(sweepThreads<QQ>(), sweepMinBlocks<QQ>()) swee
   constexpr bool FORCE = VAR == 1, PUSH = VAR == 2;
   // a CTA always sweeps blockDim.x CONSECUTIVE elements (full coalescing); which block of them is
   // blockIdx.x, or -- second launch of the overlapped exchange -- an entry of the halo-CTA list
-  const int cta = a.ctaMode == 2 ? a.ctaList[blockIdx.x] : (int)blockIdx.x;
+  const bool appended = a.ctaMode == 1 && (int)blockIdx.x >= a.nMain;
+  const int cta = appended ? a.ctaList[(int)blockIdx.x - a.nMain] : (int)blockIdx.x;
   const int i = cta * blockDim.x + threadIdx.x;
   if (i >= a.count) return;
   const int e = a.first + i;
@@ -129,12 +130,13 @@ __global__ void __launch_bounds__(sweepThreads<QQ>(), sweepMinBlocks<QQ>()) swee
     // The CTA's mask word is fetched together with the index loads, so the check costs no extra
     // memory round trip at the head of every CTA.
     uint32_t maskWord = 0u;
-    if (a.wait.ctaMask != nullptr && a.ctaMode != 2) maskWord = __ldg(a.wait.ctaMask + (cta >> 5));
+    if (a.wait.ctaMask != nullptr && !appended) maskWord = __ldg(a.wait.ctaMask + (cta >> 5));
     uint32_t n[QQ - 1];
 #pragma unroll
     for (int q = 0; q < QQ - 1; ++q) n[q] = __ldcs(a.nbr + q * S + e);
-    const bool halo = (maskWord >> (cta & 31)) & 1u;   // uniform over the CTA
-    if (halo && a.ctaMode == 1) return;               // swept by the second launch, after the wait
+    const bool masked = (maskWord >> (cta & 31)) & 1u;   // uniform over the CTA
+    if (masked && a.ctaMode == 1) return;                // swept by its appended twin at the end of the launch
+    const bool halo = masked || appended;
     if (halo) {
       if (threadIdx.x == 0) waitHaloArrival(a.wait);   // thread 0 of a CTA is always in range
       __syncthreads();                                 // threads out of range have exited
@@ -276,7 +278,7 @@ template <int QQ, int RELAX, bool INCOMP, int VAR>
 static int launchT(const SweepArgs &a, cudaStream_t st) {
   if (a.count <= 0) return 0;
   const int block = sweepThreads<QQ>();
-  const int grid = a.ctaMode == 2 ? a.nCtas : divUp(a.count, block);
+  const int grid = a.ctaMode == 1 ? a.nMain + a.nCtas : divUp(a.count, block);
   if (grid <= 0) return 0;
   sweepKernel<QQ, RELAX, INCOMP, VAR><<<grid, block, 0, st>>>(a);
   MUSB_CUDA(cudaGetLastError());
