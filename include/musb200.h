@@ -292,12 +292,13 @@ int musb200_set_aux_every_step(int flag);
 int musb200_fill_helper_elements(int minLevel, int maxLevel);
 
 /* Single level on several ranks with the peer-memory exchange: 1 = the push of step n runs on a
- * second, high-priority stream WHILE the main launch of step n+1 sweeps every CTA that pulls from
- * no halo row (a bitmap built from the neighbour list: 92-97 % of the CTAs at 256^3 per GPU); then
- * the wait, then a second launch for the CTAs that do -- whole CTAs of consecutive elements, so
- * nothing is lost in coalescing (round 1 split by an element list and lost more than it hid).
- * 0 (default): exchange strictly after compute as comm_isend_irecv_real is called in
- * do_fast_singleLevel (mus_control_module.f90:644-649).  Identical results either way. */
+ * second, high-priority stream WHILE step n+1 is swept; the CTAs of that sweep that pull from a halo
+ * row (a bitmap built from the neighbour list: 3-12 % of the CTAs at 256^3 per GPU) are moved to the
+ * END of the launch -- whole CTAs of consecutive elements, so nothing is lost in coalescing -- and
+ * wait there for the peers' links.  0 (default): exchange strictly after compute as
+ * comm_isend_irecv_real is called in do_fast_singleLevel (mus_control_module.f90:644-649).
+ * Identical results either way; measured on 2 x B200 the overlapped form is 2 % slower (the
+ * re-ordered CTAs lose the L2 locality of their neighbours), so it is opt-in. */
 int musb200_set_overlap(int flag);
 /* Peer-memory halo exchange, single level: 1 = the wait for the links of step n moves into the
  * sweep of step n+1, where only the CTAs that pull from a halo row wait (the same bitmap); 0

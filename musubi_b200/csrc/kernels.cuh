@@ -206,7 +206,6 @@ struct P2PArgs {
   int sendRank[kMaxPeers];
   unsigned long long timeoutNs;
   int *errFlag;
-  int exp;                      // timing experiments only (MUSB200_PUSH_EXP): 1 no remote store, 2 no gather
 };
 int launchPushHalo(const P2PArgs &a, cudaStream_t st);
 // publish only (the links were stored by the sweep with the fused push)

@@ -34,7 +34,6 @@
 //   drains and the next API call returns MUSB200_ERR_NCCL instead of hanging (the reference
 //   aborts all ranks, tem/source/tem_aux_module.f90:457-478).
 #include "kernels.cuh"
-#include <cstdlib>
 
 namespace musb200 {
 
@@ -44,10 +43,10 @@ template <int QQ>
 __device__ __forceinline__ void pushOne(const P2PArgs &a, int i) {
   if (i < a.n) {
     const int p = a.srcPos[i] - 1;
-    const double v = a.exp == 2 ? 1.0 : a.state[(long long)(p % QQ) * a.S + p / QQ];
+    const double v = a.state[(long long)(p % QQ) * a.S + p / QQ];
     const int k = a.peerOf[i];
     const int r = a.dstPos[i] - 1;
-    if (a.exp != 1 || v == 1.0e300) a.remoteState[k][(long long)(r % QQ) * a.remoteS[k] + r / QQ] = v;
+    a.remoteState[k][(long long)(r % QQ) * a.remoteS[k] + r / QQ] = v;
   } else {
     const int j = i - a.n;
     const int p = a.auxSrcPos[j] - 1;
@@ -208,11 +207,8 @@ int launchPushHalo(const P2PArgs &a, cudaStream_t st) {
   const int total = a.n + a.nAux;
   int blocks = divUp(total > 0 ? total : 1, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;      // a full wave of 256-thread CTAs
-  static const int exp = getenv("MUSB200_PUSH_EXP") ? atoi(getenv("MUSB200_PUSH_EXP")) : 0;
-  P2PArgs b = a;
-  b.exp = exp;
-  if (a.QQ == 19) pushHaloKernel<19><<<blocks, 256, 0, st>>>(b);
-  else pushHaloKernel<27><<<blocks, 256, 0, st>>>(b);
+  if (a.QQ == 19) pushHaloKernel<19><<<blocks, 256, 0, st>>>(a);
+  else pushHaloKernel<27><<<blocks, 256, 0, st>>>(a);
   MUSB_CUDA(cudaGetLastError());
   return 0;
 }
