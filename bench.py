@@ -356,7 +356,7 @@ def multirank_check(comm, mb, want_p2p):
     steps, level, out, t0 = 24, 6, {}, time.perf_counter()
     paths = [("p2p", dict(p2p=True, sweep_wait=0, graphs=1, overlap=0), "peer-memory push + wait kernel, CUDA graph"),
              ("p2p-overlap", dict(p2p=True, sweep_wait=0, graphs=0, overlap=1),
-              "push on a second stream overlapping the sweep of the CTAs that need no halo row, then wait + second launch"),
+              "push on a second stream overlapping the next sweep, whose CTAs that pull from halo rows run last and wait"),
              ("p2p-sweepwait", dict(p2p=True, sweep_wait=1, graphs=0, overlap=0),
               "peer-memory push, wait inside the next sweep (halo CTAs), direct launches"),
              ("nccl", dict(p2p=False, sweep_wait=0, graphs=1, overlap=0), "pack / ncclSend / ncclRecv / unpack")]

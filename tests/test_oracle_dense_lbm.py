@@ -1,0 +1,131 @@
+"""A third, list-free implementation: the textbook lattice-Boltzmann step on DENSE arrays (numpy
+rolls for streaming, half-way bounce-back at the walls, the velocity bounce-back formula at the lid,
+collision from the definitions) against the oracle's list-driven restatement of the reference
+(Morton element order, `neigh` positions, bc link lists, optimised kernels).  Nothing is shared
+between the two but the stencil tables: this checks connectivity, the wall and `velocity_bounceback`
+boundary lists and the TRT / BGK collisions of BASELINE configs 1-3 end to end on 16^3, where no
+reference-held fixture exists (cfg2 is the bench's workload)."""
+import numpy as np
+import pytest
+
+
+def _stencil(mo, QQ):
+    cx = mo.cx_dir(QQ).astype(np.int64)
+    inv = mo.cx_dir_inv(QQ) - 1
+    return cx, mo.weights(QQ), inv
+
+
+def _feq(kind, rho, u, cx, w):
+    """kind 0: w rho (1 + 3cu + 4.5cu^2 - 1.5u^2); kind 1: product form of the D3Q27 TRT kernel"""
+    QQ = len(w)
+    out = np.empty((QQ,) + rho.shape)
+    if kind == 1:
+        for q in range(QQ):
+            phi = rho.copy()
+            for k in range(3):
+                a = u[k]
+                phi = phi * ((2.0 / 3.0 - a * a) if cx[q, k] == 0 else 0.5 * (1.0 / 3.0 + a * a + cx[q, k] * a))
+            out[q] = phi
+        return out
+    usq = u[0] ** 2 + u[1] ** 2 + u[2] ** 2
+    for q in range(QQ):
+        cu = cx[q, 0] * u[0] + cx[q, 1] * u[1] + cx[q, 2] * u[2]
+        out[q] = w[q] * rho * (1.0 + 3.0 * cu + 4.5 * cu * cu - 1.5 * usq)
+    return out
+
+
+class DenseLBM:
+    def __init__(self, mo, QQ, n, relax, omega, lam, walls, u_lid=None, feq_kind=0, mrt=None):
+        self.cx, self.w, self.inv = _stencil(mo, QQ)
+        self.QQ, self.n, self.relax, self.omega, self.lam = QQ, n, relax, omega, lam
+        self.walls, self.u_lid, self.feq_kind, self.mrt = walls, u_lid, feq_kind, mrt
+        ax = np.arange(n)
+        self.X, self.Y, self.Z = np.meshgrid(ax, ax, ax, indexing="ij")
+
+    def step(self, f):
+        """f: post-collision PDFs [q, x, y, z] -> post-collision PDFs of the next step"""
+        QQ, n, cx, w, inv = self.QQ, self.n, self.cx, self.w, self.inv
+        rho_post = f.sum(axis=0)
+        g = np.empty_like(f)
+        for q in range(QQ):
+            g[q] = np.roll(f[q], shift=(cx[q, 0], cx[q, 1], cx[q, 2]), axis=(0, 1, 2))   # g(x) = f(x - c)
+            if self.walls:
+                xs, ys, zs = self.X - cx[q, 0], self.Y - cx[q, 1], self.Z - cx[q, 2]
+                out = (xs < 0) | (xs >= n) | (ys < 0) | (ys >= n) | (zs < 0) | (zs >= n)
+                bb = f[inv[q]]                                    # half-way bounce-back: own opposite PDF
+                if self.u_lid is not None:
+                    lid = (zs >= n) & (xs >= 0) & (xs < n) & (ys >= 0) & (ys < n)
+                    cu = float(cx[q] @ np.asarray(self.u_lid))
+                    bb = np.where(lid, bb + w[q] * 6.0 * rho_post * cu, bb)
+                g[q] = np.where(out, bb, g[q])
+        rho = g.sum(axis=0)
+        u = np.stack([(cx[:, k, None, None, None] * g).sum(axis=0) / rho for k in range(3)])
+        fe = _feq(self.feq_kind, rho, u, cx, w)
+        if self.relax == "bgk":
+            return g + self.omega * (fe - g)
+        if self.relax == "trt":
+            wN = 1.0 / (self.lam / (1.0 / self.omega - 0.5) + 0.5)
+            fs, fa = 0.5 * (g + g[inv]), 0.5 * (g - g[inv])
+            es, ea = 0.5 * (fe + fe[inv]), 0.5 * (fe - fe[inv])
+            return g - self.omega * (fs - es) - wN * (fa - ea)
+        M, Mi, s = self.mrt                                      # mrt: f - M^-1 S M (f - feq)
+        neq = (g - fe).reshape(QQ, -1)
+        return g - (Mi @ (s[:, None] * (M @ neq))).reshape(g.shape)
+
+
+def _to_dense(mo, aos, QQ, n):
+    x, y, z = mo.coord_of_morton(np.arange(n ** 3, dtype=np.int64))
+    f = np.empty((QQ, n, n, n))
+    f[:, x, y, z] = aos[:n ** 3 * QQ].reshape(-1, QQ).T
+    return f
+
+
+CASES = [("cfg2 cavity trt d3q19", 19, "trt", "cavity", 0), ("cfg1 periodic bgk d3q19", 19, "bgk", "periodic", 0),
+         ("periodic trt d3q19", 19, "trt", "periodic", 0), ("periodic bgk d3q27", 27, "bgk", "periodic", 0),
+         ("periodic trt d3q27 (product-form f_eq)", 27, "trt", "periodic", 1),
+         ("cfg3 periodic mrt d3q27", 27, "mrt", "periodic", 0), ("cavity mrt d3q19", 19, "mrt", "cavity", 0)]
+
+
+@pytest.mark.parametrize("name,QQ,relax,kind,feq_kind", CASES, ids=[c[0] for c in CASES])
+def test_list_driven_oracle_equals_dense_textbook_lbm(oracle, name, QQ, relax, kind, feq_kind):
+    mo, level, nsteps = oracle, 4, 30
+    n = 1 << level
+    omega, lam, ob = 1.7, 3.0 / 16.0, 1.3
+    ld = mo.build_level_desc(level, QQ, kind)
+    ref = mo.Scheme(ld, relax, "fluid", omega=omega, lambda_=lam, omega_bulk=ob)
+    x = mo.barycenters(ld, (0.0, 0.0, 0.0), 2.0 * np.pi)
+    u0 = 0.04
+    vel = np.stack([u0 * np.sin(x[:, 0]) * np.cos(x[:, 1]) * np.cos(x[:, 2]) + 0.01,
+                    -u0 * np.cos(x[:, 0]) * np.sin(x[:, 1]) * np.cos(x[:, 2]) - 0.02,
+                    0.015 + 0.0 * x[:, 0]], axis=1)
+    rho = 1.0 + 0.01 * np.cos(x[:, 0]) * np.cos(x[:, 2])
+    ref.init_equilibrium(rho, vel)
+    u_lid = None
+    if kind == "cavity":
+        u_lid = (0.05, 0.02, 0.0)
+        for bc in ld.bc:
+            if bc["id"] == 2:
+                ref.bc_vel[2] = np.tile(np.array(u_lid), (len(bc["links"]), 1))
+    mrt = None
+    if relax == "mrt":
+        L = mo.lib()
+        M = np.ctypeslib.as_array(L.ora_mrt_matrix(QQ, 0), shape=(QQ, QQ)).copy()
+        Mi = np.ctypeslib.as_array(L.ora_mrt_matrix(QQ, 1), shape=(QQ, QQ)).copy()
+        s = np.zeros(QQ)
+        L.ora_mrt_diag(QQ, ctypes_double(float(1.0 / (3.0 * ref.visc[0] + 0.5))), ctypes_double(ob), mo._d(s))
+        mrt = (M, Mi, s)
+    dense = DenseLBM(mo, QQ, n, relax, float(1.0 / (3.0 * ref.visc[0] + 0.5)), lam, kind == "cavity", u_lid,
+                     feq_kind, mrt)
+    f = _to_dense(mo, ref.state[ref.nNext], QQ, n)
+    ref.run(nsteps)
+    for _ in range(nsteps):
+        f = dense.step(f)
+    got = _to_dense(mo, ref.state[ref.nNext], QQ, n)
+    err = np.max(np.abs(got - f) / np.maximum(np.abs(f), 1e-3))
+    assert err < 2e-12, (name, err)
+    assert abs(got.sum() / f.sum() - 1.0) < 1e-13
+
+
+def ctypes_double(v):
+    import ctypes
+    return ctypes.c_double(v)
