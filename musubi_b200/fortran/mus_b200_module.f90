@@ -31,7 +31,7 @@ module mus_b200_module
 
   public :: mus_b200_init, mus_b200_finalize
   public :: mus_b200_upload, mus_b200_download
-  public :: mus_b200_step, mus_b200_compute
+  public :: mus_b200_step, mus_b200_step_schemes, mus_b200_compute
   public :: mus_b200_check
   public :: mus_b200_upload_intp, mus_b200_set_force, mus_b200_p2p_connect
   public :: mus_b200_pdf_serialize, mus_b200_pdf_unserialize, mus_b200_fill_helper_elements
@@ -151,6 +151,18 @@ module mus_b200_module
     function musb200_step(minLevel, maxLevel, nCycles) bind(C, name='musb200_step') result(rc)
       import :: c_int
       integer(c_int), value :: minLevel, maxLevel, nCycles
+      integer(c_int) :: rc
+    end function
+    function musb200_step_schemes(nSlots, slots, minLevel, maxLevel, nCycles) &
+      & bind(C, name='musb200_step_schemes') result(rc)
+      import :: c_int
+      integer(c_int), value :: nSlots, minLevel, maxLevel, nCycles
+      integer(c_int) :: slots(*)
+      integer(c_int) :: rc
+    end function
+    function musb200_set_exchange_timeout(seconds) bind(C, name='musb200_set_exchange_timeout') result(rc)
+      import :: c_int, c_double
+      real(c_double), value :: seconds
       integer(c_int) :: rc
     end function
     function musb200_reduce(level, mass, maxvel, anynan) bind(C, name='musb200_reduce') result(rc)
@@ -331,6 +343,9 @@ contains
     call chk(musb200_init(int(params%general%proc%rank, c_int),      &
       &                   int(params%general%proc%comm_size, c_int), &
       &                   int(localRank, c_int), c_loc(id)), 'init')
+    ! a rank that dies must not hang the others: the waits of the halo exchange give up after this
+    ! many seconds and the next synchronising call reports the silent rank (chk -> tem_abort)
+    call chk(musb200_set_exchange_timeout(60.0_c_double), 'set_exchange_timeout')
   end subroutine mus_b200_init
 
   subroutine mus_b200_finalize()
@@ -664,6 +679,17 @@ contains
     real(kind=rk), intent(in) :: buffer(:)
     call chk(musb200_pdf_unserialize(int(nElems, c_int), treeID, levelPointer, buffer), 'pdf_unserialize')
   end subroutine mus_b200_pdf_unserialize
+
+  !> several schemes on one mesh stepped together (a passive scalar in slot 1 transported by the
+  !! flow in slot 0): one C call per coarse cycle for all of them, the flow advancing first inside
+  !! every level step
+  subroutine mus_b200_step_schemes(slots, minLevel, maxLevel, nCycles)
+    integer, intent(in) :: slots(:), minLevel, maxLevel, nCycles
+    integer(c_int) :: cslots(size(slots))
+    cslots = int(slots, c_int)
+    call chk(musb200_step_schemes(int(size(slots), c_int), cslots, int(minLevel, c_int), &
+      &                           int(maxLevel, c_int), int(nCycles, c_int)), 'step_schemes')
+  end subroutine mus_b200_step_schemes
 
   !> after mus_b200_pdf_unserialize filled state(:, nNext) of the fluid elements on the device
   !! (a restart read straight into the device state): what mus_init_flow does next on the host,

@@ -129,3 +129,95 @@ def test_list_driven_oracle_equals_dense_textbook_lbm(oracle, name, QQ, relax, k
 def ctypes_double(v):
     import ctypes
     return ctypes.c_double(v)
+
+
+class DenseChannel(DenseLBM):
+    """channel: walls across y and z, velocity_bounceback inlet at x < 0, a pressure outlet at
+    x >= n (pressure_expol or pressure_antibounceback), written on dense arrays from the boundary
+    conditions' definitions (mus_bc_fluid_module.fpp:1165-1362, 2161-2353) -- no element, link or
+    neighbour lists: the outlet elements' inward normal is -x, their neighbours are the planes
+    x = n-2 and n-3"""
+
+    def __init__(self, mo, QQ, n, omega, u_in, rho_out, outlet):
+        super().__init__(mo, QQ, n, "bgk", omega, 0.25, True)
+        self.u_in, self.rho_out, self.outlet = np.asarray(u_in, dtype=np.float64), rho_out, outlet
+
+    def step(self, f, aux_prev):
+        QQ, n, cx, w, inv = self.QQ, self.n, self.cx, self.w, self.inv
+        rho_post = f.sum(axis=0)
+        g = np.empty_like(f)
+        inside_yz = {}
+        for q in range(QQ):
+            g[q] = np.roll(f[q], shift=(cx[q, 0], cx[q, 1], cx[q, 2]), axis=(0, 1, 2))
+            xs, ys, zs = self.X - cx[q, 0], self.Y - cx[q, 1], self.Z - cx[q, 2]
+            out_yz = (ys < 0) | (ys >= n) | (zs < 0) | (zs >= n)
+            inside_yz[q] = ~out_yz
+            g[q] = np.where(out_yz | (xs < 0) | (xs >= n), f[inv[q]], g[q])            # bounce-back everywhere first
+            inlet = (~out_yz) & (xs < 0)
+            g[q] = np.where(inlet, f[inv[q]] + w[q] * 6.0 * rho_post * float(cx[q] @ self.u_in), g[q])
+        # the outlet: incoming links of the plane x = n-1 (c_x = -1, source inside in y and z)
+        q0 = int(np.nonzero((cx == np.array([-1, 0, 0])).all(axis=1))[0][0])
+        if self.outlet == "pressure_expol":
+            for q in range(QQ):
+                if cx[q, 0] != -1:
+                    continue
+                m = inside_yz[q][n - 1]
+                g[q, n - 1] = np.where(m, 1.5 * g[q, n - 2] - 0.5 * g[q, n - 3], g[q, n - 1])
+            # the normal direction: equilibrium at the prescribed density + the bounced non-equilibrium,
+            # moments = the auxField of the previous step
+            rho_a, u_a = aux_prev[0][n - 1], aux_prev[1:, n - 1]
+            fe = _feq(0, rho_a, u_a, cx, w)
+            fe0 = _feq(0, np.full_like(rho_a, self.rho_out), u_a, cx, w)
+            g[q0, n - 1] = fe0[q0] + (f[inv[q0], n - 1] - fe[inv[q0]])
+        else:
+            fF, fN = f[:, n - 1], f[:, n - 2]                      # post-collision PDFs: element, its neighbour
+            rhoF, rhoN = fF.sum(axis=0), fN.sum(axis=0)
+            uF = np.stack([(cx[:, k, None, None] * fF).sum(axis=0) / rhoF for k in range(3)])
+            uN = np.stack([(cx[:, k, None, None] * fN).sum(axis=0) / rhoN for k in range(3)])
+            uB = 1.5 * uF - 0.5 * uN
+            usqB, usqF = (uB ** 2).sum(axis=0), (uF ** 2).sum(axis=0)
+            for q in range(QQ):
+                if cx[q, 0] != -1:
+                    continue
+                b = inv[q]
+                cuF = sum(cx[b, k] * uF[k] for k in range(3))
+                cuB = sum(cx[b, k] * uB[k] for k in range(3))
+                eqF = w[q] * rhoF + 4.5 * w[q] * (cuF * cuF - usqF / 3.0)
+                eqB = w[q] * self.rho_out + 4.5 * w[q] * (cuB * cuB - usqB / 3.0)
+                val = -fF[b] + 2.0 * eqB + (2.0 - self.omega) * (0.5 * (fF[q] + fF[b]) - eqF)
+                g[q, n - 1] = np.where(inside_yz[q][n - 1], val, g[q, n - 1])
+        rho = g.sum(axis=0)
+        u = np.stack([(cx[:, k, None, None, None] * g).sum(axis=0) / rho for k in range(3)])
+        fe = _feq(0, rho, u, cx, w)
+        return g + self.omega * (fe - g), np.concatenate([rho[None], u])
+
+
+@pytest.mark.parametrize("outlet", ["pressure_expol", "pressure_antibounceback"])
+def test_channel_with_pressure_outlet_equals_dense_textbook_lbm(oracle, outlet):
+    """a12: fill_neighBuffer + pressure_expol / pressure_antiBounceBack + the inlet's
+    velocity_bounceback through the oracle's element, link, normal and neighbour lists against the
+    dense formulation, 25 steps of a developing channel flow on 16^3"""
+    mo, QQ, level, nsteps = oracle, 19, 4, 25
+    n = 1 << level
+    ld = mo.build_level_desc(level, QQ, "channel")
+    ref = mo.Scheme(ld, "bgk", "fluid", omega=1.6)
+    ref.init_equilibrium(np.ones(ld.nElems), np.zeros((ld.nElems, 3)))
+    u_in, rho_out = (0.03, 0.0, 0.0), 1.0
+    for bc in ld.bc:
+        if bc["id"] == 2:
+            ref.bc_vel[2] = np.tile(np.array(u_in), (len(bc["links"]), 1))
+        if bc["id"] == 3:
+            ref.bc_kind[3] = outlet
+            ref.bc_rho[3] = np.full(len(bc["elems"]), rho_out)
+    dense = DenseChannel(mo, QQ, n, float(1.0 / (3.0 * ref.visc[0] + 0.5)), u_in, rho_out, outlet)
+    f = _to_dense(mo, ref.state[ref.nNext], QQ, n)
+    x, y, z = mo.coord_of_morton(np.arange(n ** 3, dtype=np.int64))
+    aux = np.zeros((4, n, n, n))
+    aux[:, x, y, z] = ref.aux[:n ** 3 * 4].reshape(-1, 4).T
+    ref.run(nsteps)
+    for _ in range(nsteps):
+        f, aux = dense.step(f, aux)
+    got = _to_dense(mo, ref.state[ref.nNext], QQ, n)
+    err = np.max(np.abs(got - f) / np.maximum(np.abs(f), 1e-3))
+    assert err < 2e-12, (outlet, err)
+    assert np.abs(aux[1]).max() > 0.02          # the flow has developed: the boundaries acted
