@@ -60,14 +60,28 @@ class DenseLBM:
                 g[q] = np.where(out, bb, g[q])
         rho = g.sum(axis=0)
         u = np.stack([(cx[:, k, None, None, None] * g).sum(axis=0) / rho for k in range(3)])
+        src = 0.0
+        F = getattr(self, "force", None)
+        if F is not None:
+            F = np.asarray(F, dtype=np.float64)
+            if self.force_order == 2:
+                # Guo et al. 2002: velocity shifted by F / (2 rho), source (1 - omega/2) w (3 (c - u) + 9 (c.u) c) . F
+                u = u + 0.5 * F[:, None, None, None] / rho
+                cu = np.einsum("qk,kxyz->qxyz", cx.astype(np.float64), u)
+                cF = cx.astype(np.float64) @ F
+                uF = np.einsum("k,kxyz->xyz", F, u)
+                src = (1.0 - 0.5 * self.omega) * w[:, None, None, None] * (
+                    3.0 * (cF[:, None, None, None] - uF[None]) + 9.0 * cu * cF[:, None, None, None])
+            else:
+                src = (w * 3.0 * (cx.astype(np.float64) @ F))[:, None, None, None] * np.ones_like(rho)[None]
         fe = _feq(self.feq_kind, rho, u, cx, w)
         if self.relax == "bgk":
-            return g + self.omega * (fe - g)
+            return g + self.omega * (fe - g) + src
         if self.relax == "trt":
             wN = 1.0 / (self.lam / (1.0 / self.omega - 0.5) + 0.5)
             fs, fa = 0.5 * (g + g[inv]), 0.5 * (g - g[inv])
             es, ea = 0.5 * (fe + fe[inv]), 0.5 * (fe - fe[inv])
-            return g - self.omega * (fs - es) - wN * (fa - ea)
+            return g - self.omega * (fs - es) - wN * (fa - ea) + src
         M, Mi, s = self.mrt                                      # mrt: f - M^-1 S M (f - feq)
         neq = (g - fe).reshape(QQ, -1)
         return g - (Mi @ (s[:, None] * (M @ neq))).reshape(g.shape)
@@ -221,3 +235,38 @@ def test_channel_with_pressure_outlet_equals_dense_textbook_lbm(oracle, outlet):
     err = np.max(np.abs(got - f) / np.maximum(np.abs(f), 1e-3))
     assert err < 2e-12, (outlet, err)
     assert np.abs(aux[1]).max() > 0.02          # the flow has developed: the boundaries acted
+
+
+@pytest.mark.parametrize("QQ,relax,order", [(19, "bgk", 2), (19, "trt", 2), (27, "bgk", 2), (19, "bgk", 1)])
+def test_body_force_equals_the_textbook_guo_scheme(oracle, QQ, relax, order):
+    """n3: mus_addForceToAuxField_fluid + applySrc_force (order 2) / applySrc_force1stOrd (order 1)
+    as restated by the oracle against Guo's forcing written on dense arrays: half-force velocity
+    shift, source (1 - omega/2) w_i (3 (c_i - u) + 9 (c_i.u) c_i) . F; first order: 3 w_i c_i . F"""
+    mo, level, nsteps = oracle, 4, 25
+    n = 1 << level
+    ld = mo.build_level_desc(level, QQ, "periodic")
+    ref = mo.Scheme(ld, relax, "fluid", omega=1.6, lambda_=0.2)
+    x = mo.barycenters(ld, (0.0, 0.0, 0.0), 2.0 * np.pi)
+    vel = np.stack([0.03 * np.sin(x[:, 1]), 0.02 * np.cos(x[:, 2]), 0.01 * np.sin(x[:, 0])], axis=1)
+    ref.init_equilibrium(np.ones(ld.nElems), vel)
+    F = [2.0e-5, -1.0e-5, 3.0e-5]
+    ref.set_force(F, order=order)
+    dense = DenseLBM(mo, QQ, n, relax, float(1.0 / (3.0 * ref.visc[0] + 0.5)), 0.2, False)
+    dense.force, dense.force_order = F, order
+    f = _to_dense(mo, ref.state[ref.nNext], QQ, n)
+    p0 = np.einsum("qk,qxyz->k", dense.cx.astype(np.float64), f)
+    ref.run(nsteps)
+    for _ in range(nsteps):
+        f = dense.step(f)
+    got = _to_dense(mo, ref.state[ref.nNext], QQ, n)
+    err = np.max(np.abs(got - f) / np.maximum(np.abs(f), 1e-3))
+    assert err < 2e-12, err
+    # and the physics: with BGK the momentum of the periodic box grows by F per cell and step (the
+    # reference applies the same source, weighted with omega, under TRT, where the odd part of the
+    # collision relaxes with omega^-: the gain is then F (1 - omega/2 + omega^-/2), its behaviour)
+    p1 = np.einsum("qk,qxyz->k", dense.cx.astype(np.float64), got)
+    if relax == "bgk":
+        assert np.allclose((p1 - p0) / (nsteps * n ** 3), F, rtol=1e-9)
+    else:
+        wN = 1.0 / (0.2 / (1.0 / dense.omega - 0.5) + 0.5)
+        assert np.allclose((p1 - p0) / (nsteps * n ** 3), np.array(F) * (1.0 - 0.5 * dense.omega + 0.5 * wN), rtol=1e-9)
