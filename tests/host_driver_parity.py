@@ -1,7 +1,7 @@
 """GPU pass of the compiled host (mus_b200_host): initial state from a file, N steps, restart dump
-bit-compared with the oracle.  Run by scripts/gpu_verify_1gpu.sh; NOT YET RUN ON A GPU (written
-after the round's GPU budget was spent) -- move into tests/test_host_driver.py as a gpu test once
-it has passed."""
+bit-compared with the oracle.  Run by tests/test_host_driver.py (gpu test) and
+scripts/gpu_verify_1gpu.sh; green on a B200 in round 2 (it found the missing auxField
+initialisation of the host, since closed by musb200_fill_helper_elements)."""
 import os
 import subprocess
 import sys

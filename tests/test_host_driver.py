@@ -1,9 +1,12 @@
 """The compiled host above the C ABI (musubi_b200/csrc/host/mus_b200_host.cpp): builds against
 include/musb200.h and the exported symbols only, and fails loudly where the library does.  Its
-run on a GPU (state file in, 40 steps, dump bit-compared with the oracle) is part of
-scripts/gpu_verify_1gpu.sh."""
+run on a GPU (state file in, 40 steps, dump bit-compared with the oracle: tests/host_driver_parity.py,
+periodic BGK / MRT, the lid cavity and the channel with a pressure outlet) is the gpu test below."""
 import os
 import subprocess
+import sys
+
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "musubi_b200", "mus_b200_host")
@@ -47,3 +50,13 @@ def test_host_driver_error_behaviour_mirrors_the_library():
         assert r.returncode == 0 and "MLUPS" in r.stdout, r.stderr
     else:
         assert r.returncode == 2 and "musb200_init" in r.stderr and "failed (code 2)" in r.stderr
+
+
+@pytest.mark.gpu
+def test_host_driver_runs_match_the_oracle_bit_for_bit():
+    """the C++ host program drives libmusb200.so through the header alone: initial state from a
+    file, 40 steps, restart dump -- four cases, every PDF equal to the oracle's"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "host_driver_parity.py")], cwd=ROOT,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ndiff=0") == 4 and "host driver parity: OK" in r.stdout
