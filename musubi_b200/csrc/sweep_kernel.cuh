@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(sweepThreads<QQ>(), sweepMinBlocks<QQ>()) swee
     if (a.wait.ctaMask != nullptr && !appended) maskWord = __ldg(a.wait.ctaMask + (cta >> 5));
     uint32_t n[QQ - 1];
 #pragma unroll
-    for (int q = 0; q < QQ - 1; ++q) n[q] = __ldcs(a.nbr + q * S + e);
+    for (int q = 0; q < QQ - 1; ++q) n[q] = __ldg(a.nbr + q * S + e);
     const bool masked = (maskWord >> (cta & 31)) & 1u;   // uniform over the CTA
     if (masked && a.ctaMode == 1) return;                // swept by its appended twin at the end of the launch
     const bool halo = masked || appended;
@@ -173,9 +173,9 @@ __global__ void __launch_bounds__(sweepThreads<QQ>(), sweepMinBlocks<QQ>()) swee
   ForceSrc<QQ, RELAX> fs;
   if (FORCE) {
     if (a.force != nullptr) {
-      fs.Fx = __ldcs(a.force + e);
-      fs.Fy = __ldcs(a.force + S + e);
-      fs.Fz = __ldcs(a.force + 2 * S + e);
+      fs.Fx = __ldg(a.force + e);
+      fs.Fy = __ldg(a.force + S + e);
+      fs.Fz = __ldg(a.force + 2 * S + e);
     } else {
       fs.Fx = a.force_uniform[0]; fs.Fy = a.force_uniform[1]; fs.Fz = a.force_uniform[2];
     }
@@ -189,18 +189,18 @@ __global__ void __launch_bounds__(sweepThreads<QQ>(), sweepMinBlocks<QQ>()) swee
     fs.ux = ux; fs.uy = uy; fs.uz = uz;
   }
   if (a.write_aux) {
-    __stcs(a.aux + e, rho);
-    __stcs(a.aux + S + e, ux);
-    __stcs(a.aux + 2 * S + e, uy);
-    __stcs(a.aux + 3 * S + e, uz);
+    a.aux[e] = rho;
+    a.aux[S + e] = ux;
+    a.aux[2 * S + e] = uy;
+    a.aux[3 * S + e] = uz;
   }
-  const double omega = (a.omega != nullptr) ? __ldcs(a.omega + e) : a.rp.omega_uniform;
+  const double omega = (a.omega != nullptr) ? __ldg(a.omega + e) : a.rp.omega_uniform;
 
   double *out = a.out + e;
   if (FORCE) fs.prepare(omega, a.rp.omega_bulk);
   auto st = [&](int q, double v) {
     if (FORCE) v = v + fs.term(q);
-    __stcs(out + (long long)q * S, v);
+    out[(long long)q * S] = v;
   };
   if (QQ == 19) {
     const double(&g)[19] = reinterpret_cast<const double(&)[19]>(f);
