@@ -270,3 +270,60 @@ def test_body_force_equals_the_textbook_guo_scheme(oracle, QQ, relax, order):
     else:
         wN = 1.0 / (0.2 / (1.0 / dense.omega - 0.5) + 0.5)
         assert np.allclose((p1 - p0) / (nsteps * n ** 3), np.array(F) * (1.0 - 0.5 * dense.omega + 0.5 * wN), rtol=1e-9)
+
+
+@pytest.mark.parametrize("relax,variant,QQ,kind", [("bgk", "first", 19, "periodic"), ("bgk", "second", 19, "cavity"),
+                                                   ("trt", "standard", 19, "periodic"), ("bgk", "second", 27, "periodic"),
+                                                   ("trt", "standard", 27, "cavity")])
+def test_passive_scalar_equals_dense_advection_diffusion_lbm(oracle, relax, variant, QQ, kind):
+    """n3: mus_calcAuxField_zerothMoment + mus_advRel_kPS_rBGK_v1st_l / _v2nd_l / rTRT_vStdNoOpt_l through
+    the oracle's element and neighbour lists against the advection-diffusion lattice-Boltzmann step on
+    dense arrays: roll-streaming, bounce-back at the box walls (no flux through them), equilibrium
+    w rho (1 + 3 c.u [+ 4.5 (c.u)^2 - 1.5 u^2]) with a space-dependent transport velocity, omega_D =
+    1 / (3 D + 1/2), for trt the even part relaxed with the magic-parameter partner"""
+    mo, level, nsteps = oracle, 4, 30
+    n = 1 << level
+    D, lam = 0.02, 0.2
+    ld = mo.build_level_desc(level, QQ, kind)
+    ref = mo.PassiveScalarScheme(ld, relax, variant, diff_coeff=D, lambda_=lam)
+    x = mo.barycenters(ld, (0.0, 0.0, 0.0), 2.0 * np.pi)
+    rho0 = 1.0 + 0.3 * np.sin(x[:, 0]) * np.cos(x[:, 1]) + 0.1 * np.cos(2.0 * x[:, 2])
+    ref.init_equilibrium(rho0)
+    xs = x[:ld.nSolve]
+    vel = np.stack([0.05 * np.sin(xs[:, 1]), -0.04 * np.cos(xs[:, 2]), 0.03 * np.sin(xs[:, 0]) + 0.01], axis=1)
+    ref.set_transport_velocity(vel)
+    cx, w, inv = _stencil(mo, QQ)
+    X, Y, Z = mo.coord_of_morton(np.arange(n ** 3, dtype=np.int64))
+    u = np.zeros((3, n, n, n))
+    u[:, X, Y, Z] = vel[:n ** 3].T
+    omega = 1.0 / (3.0 * D + 0.5)
+    omega_even = 1.0 / (lam / (1.0 / omega - 0.5) + 0.5)
+    ax = np.arange(n)
+    GX, GY, GZ = np.meshgrid(ax, ax, ax, indexing="ij")
+    f = _to_dense(mo, ref.state[ref.nNext], QQ, n)
+    m0 = f.sum()
+    ref.run(nsteps)
+    usq = (u ** 2).sum(axis=0)
+    for _ in range(nsteps):
+        g = np.empty_like(f)
+        for q in range(QQ):
+            g[q] = np.roll(f[q], shift=(cx[q, 0], cx[q, 1], cx[q, 2]), axis=(0, 1, 2))
+            if kind == "cavity":
+                sx, sy, sz = GX - cx[q, 0], GY - cx[q, 1], GZ - cx[q, 2]
+                out = (sx < 0) | (sx >= n) | (sy < 0) | (sy >= n) | (sz < 0) | (sz >= n)
+                g[q] = np.where(out, f[inv[q]], g[q])
+        rho = g.sum(axis=0)
+        cu = np.einsum("qk,kxyz->qxyz", cx.astype(np.float64), u)
+        even = 4.5 * cu * cu - 1.5 * usq[None]
+        wr = w[:, None, None, None] * rho[None]
+        if relax == "bgk":
+            fe = wr * (1.0 + 3.0 * cu + (even if variant == "second" else 0.0))
+            f = g + omega * (fe - g)
+        else:
+            fe_even, fe_odd = wr * (1.0 + even), wr * 3.0 * cu
+            f = g + omega * (fe_odd - 0.5 * (g - g[inv])) + omega_even * (fe_even - 0.5 * (g + g[inv]))
+    got = _to_dense(mo, ref.state[ref.nNext], QQ, n)
+    err = np.max(np.abs(got - f) / np.maximum(np.abs(f), 1e-3))
+    assert err < 2e-12, err
+    assert abs(got.sum() / m0 - 1.0) < 1e-13            # the scalar is conserved, walls or not
+    assert np.abs(got.sum(axis=0) - _to_dense(mo, np.repeat(rho0, QQ) * np.tile(w, rho0.size), QQ, n).sum(axis=0)).max() > 0.01
