@@ -211,6 +211,12 @@ def test_sparta_split_rule():
     from musubi_b200 import treelm_multilevel as tm
     assert list(tm.sparta_split(np.ones(12), 4)) == [3, 3, 3, 3]
     assert list(tm.sparta_split(np.ones(10), 1)) == [10]
+    # the reference's own known-answer test (tem/utests/tem_sparta_test.f90:46-86): five ranks with five
+    # elements each and these weights end up with 4 / 3 / 5 / 5 / 8 elements at offsets 0 / 4 / 7 / 12 / 17
+    w = np.array([5, 3, 1, 2, 1, 4, 6, 1, 3, 2, 1, 3, 1, 1, 1, 1, 9, 1, 1, 1, 1, 1, 1, 1, 1], dtype=np.float64)
+    cnt = tm.sparta_split(w, 5)
+    assert list(cnt) == [4, 3, 5, 5, 8]
+    assert list(np.concatenate([[0], np.cumsum(cnt)[:-1]])) == [0, 4, 7, 12, 17]
     rng = np.random.default_rng(3)
     for n, parts in ((1000, 7), (513, 8), (64, 3)):
         w = rng.choice([1.0, 2.0, 4.0], size=n)
