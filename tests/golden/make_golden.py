@@ -26,6 +26,12 @@ the device path can be checked on machines without /root/reference.
         fluid_incompressible / bgk / d3q19, IC pressure = predefined 'gausspulse'
         (tem_ic_predefs_module.f90:230-255), line sample of the initial and the final state
 
+  mus/examples/tutorials/tutorial_cases/tutorial_gaussian_pulse/ref/
+     Gausspulse_track_pressure_p00000.res   (stored as tutorial_Gausspulse_track_pressure_p00000.res)
+        fluid / bgk / d3q19, level 6 (64^3 -- the mesh and the kernel of BASELINE config 1), no physics
+        table (lattice units), plane pressure pulse; point probe of density, pressure, velocity after
+        every one of its 50 steps
+
 Run in the build container only:  python tests/golden/make_golden.py
 """
 import os
@@ -47,3 +53,7 @@ INC = EX + "/fluid_incompressible/benchmark/gaussianPulse/reference"
 for f in sorted(os.listdir(INC)):
     shutil.copy(os.path.join(INC, f), os.path.join(HERE, "incomp_" + f))
     print("copied", f, "-> incomp_" + f)
+TUT = EX + "/tutorials/tutorial_cases/tutorial_gaussian_pulse/ref"
+shutil.copy(os.path.join(TUT, "Gausspulse_track_pressure_p00000.res"),
+            os.path.join(HERE, "tutorial_Gausspulse_track_pressure_p00000.res"))
+print("copied Gausspulse_track_pressure_p00000.res -> tutorial_Gausspulse_track_pressure_p00000.res")

@@ -5,6 +5,7 @@ the oracle tests (CPU) and the device tests (GPU):
   gaussianPulse (incompressible)  mus/examples/fluid_incompressible/benchmark/gaussianPulse/musubi.lua
   TGV_Simple_Re800    mus/examples/fluid_incompressible/benchmark/TaylorGreenVortex/TGV_Simple/
   TGV_Simple_Re1600   .../TGV_Simple_Re1600/musubi.lua
+  tutorial Gausspulse mus/examples/tutorials/tutorial_cases/tutorial_gaussian_pulse/musubi.lua
 
 Each setup returns an oracle Scheme holding the initial condition exactly as
 mus_init_pdf (mus_flow_module.fpp:422-601) builds it, plus the unit conversion.
@@ -27,6 +28,7 @@ GOLD_PULSE_INCOMP = {     # level -> (initial state or None, final state, steps)
 }
 GOLD_TGV800 = os.path.join(GOLDEN_DIR, "TGV_Simple_Re800_probeAtCenter_p00000.res")
 GOLD_TGV1600 = os.path.join(GOLDEN_DIR, "TGV_Simple_Re1600_kE_all_p00000.res")
+GOLD_TUTORIAL_PULSE = os.path.join(GOLDEN_DIR, "tutorial_Gausspulse_track_pressure_p00000.res")
 
 
 def gaussian_pulse_setup(mo, nranks=1, rank=0, level=4, kind="fluid"):
@@ -52,6 +54,33 @@ def gaussian_pulse_setup(mo, nranks=1, rank=0, level=4, kind="fluid"):
     rho = p * 3.0 * (1.0 / phys.fac_press)        # rho*cs2inv*inv_p, mus_flow_module.fpp:527
     sch.init_equilibrium(rho, np.zeros(3))
     return sch, phys, bary, nsteps
+
+
+def tutorial_pulse_setup(mo):
+    """tutorial_gaussian_pulse/musubi.lua: fluid / bgk / d3q19 on the predefined cube of edge 10 at
+    refinement level 6 -- 64^3 periodic, the mesh and the kernel of BASELINE config 1 --, NO physics
+    table, so every conversion factor is 1 (mus_load_physics, mus_physics_module.f90:231-236) and
+    kinematic_viscosity = 0.03 is the lattice viscosity; IC: a plane pressure pulse
+    p0 + 0.01 exp(-(x - 5)^2 / 2), fluid at rest; 50 steps; tracking: the element that holds the
+    point (1, 1, 1), density / pressure / velocity after every step.  Returns (scheme, 0-based probe
+    element, number of steps)."""
+    level, length, nu = 6, 10.0, 0.03
+    dx = length / 2.0 ** level
+    ld = mo.build_level_desc(level, 19, "periodic")
+    sch = mo.Scheme(ld, "bgk", "fluid", omega=1.0 / (3.0 * nu + 0.5))
+    sch.visc[:] = nu
+    bary = mo.barycenters(ld, (0.0, 0.0, 0.0), length)
+    p = 1.0 * (1.0 / 3.0) + 0.01 * np.exp(-0.5 / 1.0 ** 2 * (bary[:, 0] - 5.0) ** 2)
+    sch.init_equilibrium(p * 3.0, np.zeros(3))               # rho = p * cs2inv * inv_p, mus_flow_module.fpp:527
+    c = (math.floor(1.0 / dx) + 0.5) * dx                    # barycentre of the element holding (1, 1, 1)
+    probe = int(np.nonzero((np.abs(bary[:, 0] - c) < 1e-9) & (np.abs(bary[:, 1] - c) < 1e-9)
+                           & (np.abs(bary[:, 2] - c) < 1e-9))[0][0])
+    return sch, probe, 50
+
+
+def tutorial_pulse_row(k, aux):
+    """time (dt = 1), density, pressure = rho cs^2, velocity of the probe after k steps"""
+    return [float(k), aux[0], aux[0] * (1.0 / 3.0), aux[1], aux[2], aux[3]]
 
 
 def pulse_line_elements(sch, bary, level=4):

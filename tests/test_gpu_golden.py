@@ -5,9 +5,10 @@ committed .res files by the reference's criterion numpy.allclose(rtol=1e-10, ato
 import numpy as np
 import pytest
 
-from golden_cases import (GOLD_PULSE, GOLD_TGV800, GOLD_TGV1600, gaussian_pulse_setup,
+from golden_cases import (GOLD_PULSE, GOLD_TGV800, GOLD_TGV1600, GOLD_TUTORIAL_PULSE, gaussian_pulse_setup,
                           kinetic_energy_phy, pulse_line_elements, pulse_track, tgv800_row,
-                          tgv800_setup, tgv1600_sample_steps, tgv1600_setup)
+                          tgv800_setup, tgv1600_sample_steps, tgv1600_setup, tutorial_pulse_row,
+                          tutorial_pulse_setup)
 
 pytestmark = pytest.mark.gpu
 
@@ -64,6 +65,28 @@ def test_tgv_re800_device_probe_series_matches_reference_golden(mb, oracle):
     sch2.do_computation(60)
     n = ld2.nFluid * 19
     assert np.array_equal(sch2.download_state(6)[:n], ref.state[ref.nNext][:n])
+    sch.destroy()
+
+
+def test_tutorial_gaussian_pulse_device_probe_series_matches_reference_golden(mb, oracle):
+    """fluid / bgk / d3q19 at 64^3 in lattice units -- BASELINE config 1's mesh and kernel: the
+    reference's point probe after every one of its 50 steps"""
+    gold = np.loadtxt(GOLD_TUTORIAL_PULSE, comments="#")
+    ref, probe, nsteps = tutorial_pulse_setup(oracle)
+    ld, sch = device_scheme(mb, ref, {"kind": "fluid", "relaxation": "bgk", "layout": "d3q19"}, 6)
+    rows = []
+    for k in range(1, nsteps + 1):
+        sch.do_computation(1)
+        rows.append(tutorial_pulse_row(k, sch.aux_probe(6, probe + 1)))
+    got = np.array(rows)
+    assert got.shape == gold.shape
+    assert np.allclose(got, gold, rtol=1e-10, atol=1e-5)
+    assert np.max(np.abs(got[:, 1:3] / gold[:, 1:3] - 1.0)) < 1e-13      # density, pressure
+    assert np.max(np.abs(got[:, 3:] - gold[:, 3:])) < 1e-13              # velocity, absolute
+    # and the device equals the oracle bit for bit after the 50 steps
+    ref.run(nsteps)
+    n = ld.nFluid * 19
+    assert np.array_equal(sch.download_state(6)[:n], ref.state[ref.nNext][:n])
     sch.destroy()
 
 

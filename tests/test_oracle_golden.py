@@ -142,3 +142,24 @@ def test_incompressible_gaussian_pulse_initial_state_at_level_6(oracle):
     assert np.max(np.abs(got0[:, :3] - gold0[:, :3])) < 1e-14
     assert np.max(np.abs(got0[:, 3] / gold0[:, 3] - 1.0)) < 1e-15
     assert np.max(np.abs(got0[:, 4] / gold0[:, 4] - 1.0)) < 1e-15
+
+
+def test_tutorial_gaussian_pulse_probe_series_matches_reference_golden(oracle):
+    """the tutorial's reference run (mus/examples/tutorials/tutorial_cases/tutorial_gaussian_pulse):
+    fluid / bgk / d3q19 on 64^3 -- BASELINE config 1's mesh and kernel -- in lattice units; density,
+    pressure and velocity of one element after EVERY one of its 50 steps"""
+    from golden_cases import GOLD_TUTORIAL_PULSE, tutorial_pulse_row, tutorial_pulse_setup
+    gold = np.loadtxt(GOLD_TUTORIAL_PULSE, comments="#")
+    sch, probe, nsteps = tutorial_pulse_setup(oracle)
+    assert gold.shape == (nsteps, 6) and sch.ld.nFluid == 64 ** 3
+    rows = []
+    for k in range(1, nsteps + 1):
+        sch.step()
+        rows.append(tutorial_pulse_row(k, sch.aux.reshape(-1, 4)[probe]))
+    got = np.array(rows)
+    assert np.allclose(got, gold, rtol=1e-10, atol=1e-5)             # the reference's criterion
+    assert np.array_equal(got[:, 0], gold[:, 0])                     # time axis: iterations, dt = 1
+    assert np.max(np.abs(got[:, 1] / gold[:, 1] - 1.0)) < 1e-14      # density   (measured 2.4e-15)
+    assert np.max(np.abs(got[:, 2] / gold[:, 2] - 1.0)) < 1e-14      # pressure  (2.1e-15)
+    assert np.max(np.abs(got[:, 3:] - gold[:, 3:])) < 5e-15          # velocity, absolute (8e-16)
+    assert np.max(np.abs(got[:, 3] / gold[:, 3] - 1.0)) < 1e-10      # u_x grows from 2e-6 to 2e-3: relative too

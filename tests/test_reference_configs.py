@@ -12,12 +12,13 @@ import os
 import numpy as np
 import pytest
 
-from golden_cases import gaussian_pulse_setup, tgv800_setup, tgv1600_setup
+from golden_cases import gaussian_pulse_setup, tgv800_setup, tgv1600_setup, tutorial_pulse_setup
 
 EX = "/root/reference/mus/examples"
 PULSE = EX + "/fluid/benchmark/gaussianPulse/musubi.lua"
 PULSE_INC = EX + "/fluid_incompressible/benchmark/gaussianPulse/musubi.lua"
 TGV = EX + "/fluid_incompressible/benchmark/TaylorGreenVortex/TGV_Simple/TGV_Simple_Re%d/musubi.lua"
+TUTORIAL = EX + "/tutorials/tutorial_cases/tutorial_gaussian_pulse/musubi.lua"
 
 lua_ref = pytest.importorskip("oracle.lua_ref")
 pytestmark = pytest.mark.skipif(not (os.path.exists(PULSE) and lua_ref.available()),
@@ -118,6 +119,32 @@ def test_taylor_green_cases_are_the_references_scripts(oracle, script, Re):
         # PDFs are O(50) and their first moment carries 1e-14 of rounding
         assert abs(aux[e, 1] - vx / phys.fac_vel) < 1e-13 and abs(aux[e, 2] - vy / phys.fac_vel) < 1e-13
         assert vz == 0 and abs(aux[e, 3]) < 1e-13
+
+
+def test_tutorial_gaussian_pulse_case_is_the_references_script(oracle, script):
+    cfg = script(TUTORIAL)
+    sch, probe, nsteps = tutorial_pulse_setup(oracle)
+    assert cfg.get("mesh.predefined") == "cube" and cfg.get("mesh.refinementLevel") == 6 == sch.ld.level
+    assert cfg.get("mesh.origin") == [0.0, 0.0, 0.0] and cfg.get("mesh.length") == 10.0
+    assert cfg.get("identify.kind") == "fluid" and cfg.get("identify.layout") == "d3q19"
+    assert cfg.get("identify.relaxation") == "bgk"
+    assert cfg.get("physics") is None                   # lattice units: every conversion factor is 1
+    assert cfg.get("fluid.kinematic_viscosity") == sch.visc[0] == 0.03
+    assert cfg.get("sim_control.time_control.max.iter") == nsteps == 50
+    bary = oracle.barycenters(sch.ld, (0.0, 0.0, 0.0), 10.0)[:sch.ld.nFluid]
+    aux = sch.aux.reshape(-1, 4)[:sch.ld.nFluid]
+    for e in list(range(0, sch.ld.nFluid, 997)) + [probe]:
+        p = cfg.call("initial_condition.pressure", bary[e, 0], bary[e, 1], bary[e, 2])
+        assert abs(aux[e, 0] / (p * 3.0) - 1.0) < 2e-15 and np.all(aux[e, 1:] == 0.0)
+    for k in ("velocityX", "velocityY", "velocityZ"):
+        assert cfg.get("initial_condition." + k) == 0.0
+    t = cfg.get("tracking")
+    assert t["label"] == "track_pressure" and t["variable"] == ["density", "pressure", "velocity"]
+    assert t["output"] == {"format": "ascii"} and t["shape"]["object"] == {"origin": [1.0, 1.0, 1.0]}
+    assert t["time_control"]["interval"] == {"iter": 1} and t["time_control"]["min"] == {"iter": 1}
+    dx = 10.0 / 64
+    assert np.all(np.abs(bary[probe] - 1.0) <= 0.5 * dx)       # the probe element holds the point (1, 1, 1)
+    assert cfg.get("simulation_name") == "Gausspulse"
 
 
 def test_lua_bridge_basics():
