@@ -127,3 +127,21 @@ def test_default_omega_bulk_follows_the_reference():
     assert abs(default_omega_bulk(f27, 6, 5) - 1.0 / (9.0 * (2.0 * nu) / 2.0 + 0.5)) < 1e-15
     with pytest.raises(ValueError, match="bulk_viscosity"):
         default_omega_bulk({"kind": "fluid", "relaxation": "mrt", "layout": "d3q19"}, 4, 4)
+
+
+def test_periodic_level1_cube_neighbours_are_the_references_known_answers(oracle):
+    """treelm's own unit tests hold the neighbour relations of the predefined periodic cube at
+    refinement level 1 (tem/utests/tem_serial_singlelevel_test.f90:95-260, cube from
+    tem_utestEnv_module.f90:43-49): the right neighbour of element 2 in x is 1, of 6 is 5; of 3 in
+    y is 1; of 1 in z is 5, of 4 is 8 (treeIDs).  Here: both connectivity generators, through the
+    neigh list -- direction d with c_d = -e_axis pulls from the right neighbour"""
+    import musubi_b200 as mb
+    for QQ in (19, 27):
+        for ld in (mb.LevelDesc(1, QQ, "periodic"), oracle.build_level_desc(1, QQ, "periodic")):
+            assert ld.nFluid == 8 and list(ld.total[:8]) == list(range(1, 9))     # level-1 treeIDs 1..8
+            cx = oracle.cx_dir(QQ)
+            for left, right, axis in ((2, 1, 0), (6, 5, 0), (3, 1, 1), (1, 5, 2), (4, 8, 2)):
+                want = -np.eye(3, dtype=cx.dtype)[axis]
+                d = int(np.nonzero((cx == want).all(axis=1))[0][0])
+                pos = int(ld.neigh[d * ld.nSize + (left - 1)])           # 1-based state position
+                assert (pos - 1) // QQ == right - 1 and (pos - 1) % QQ == d, (QQ, left, right, axis)
