@@ -241,3 +241,47 @@ def test_channel_reaches_a_steady_state_that_honours_its_boundaries(oracle, outl
     rho_out = float(aux[np.abs(b[:, 0] - (N - 0.5)) < 1e-9, 0].mean())
     assert abs(rho_out - 1.0) < tol_rho                         # what the outlet imposes
     assert float(aux[np.abs(b[:, 0] - 0.5) < 1e-9, 0].mean()) > rho_out   # pressure drops along the duct
+
+
+@pytest.mark.parametrize("QQ", [19, 27])
+def test_mrt_moment_basis_structure_derived_independently(oracle, QQ):
+    """a7 / a10: the tables generated from the reference's parameter arrays (MMtrD3Q19 / MMIvD3Q19,
+    WMMtrD3Q27 / WMMIvD3Q27, mus_mrtInit_module.f90) against what a weighted-orthogonal moment basis
+    must satisfy -- none of it taken from the tables' inverse:
+      * the rows are orthogonal under the lattice-weight inner product, so the inverse is
+        W M^T diag(1 / <m_i, m_i>_w): the reference's inverse table equals that to rounding;
+      * the moments with relaxation rate 0 are exactly 1, c_x, c_y, c_z (mass, momentum);
+      * the moments relaxed with omega are exactly the five traceless second-order polynomials
+        c_x c_y, c_y c_z, c_x c_z, 3 c_x^2 - c^2, c_y^2 - c_z^2 (so nu = (1/omega - 1/2) / 3, what the
+        shear-wave test measures), the one relaxed with omega_bulk is affine in c^2 (the trace)"""
+    mo = oracle
+    L = mo.lib()
+    M = np.ctypeslib.as_array(L.ora_mrt_matrix(QQ, 0), shape=(QQ, QQ)).copy()
+    Mi = np.ctypeslib.as_array(L.ora_mrt_matrix(QQ, 1), shape=(QQ, QQ)).copy()
+    w = mo.weights(QQ)
+    G = M @ np.diag(w) @ M.T
+    assert np.max(np.abs(G - np.diag(np.diag(G)))) < 1e-15
+    assert np.max(np.abs(Mi - (w[:, None] * M.T) / np.diag(G)[None, :])) < 1e-15
+    omega, omega_bulk = 1.7, 1.3
+    s = np.zeros(QQ)
+    L.ora_mrt_diag(QQ, ctypes.c_double(omega), ctypes.c_double(omega_bulk), mo._d(s))
+    c = mo.cx_dir(QQ).astype(np.float64)
+    x, y, z = c[:, 0], c[:, 1], c[:, 2]
+    c2 = x * x + y * y + z * z
+
+    def parallel(a, b):
+        return abs(abs(a @ b) - np.linalg.norm(a) * np.linalg.norm(b)) < 1e-12 * np.linalg.norm(a) * np.linalg.norm(b)
+
+    conserved = [M[i] for i in range(QQ) if s[i] == 0.0]
+    assert len(conserved) == 4
+    for want in (np.ones(QQ), x, y, z):
+        assert sum(np.array_equal(r, want) for r in conserved) == 1
+    shear = [M[i] for i in range(QQ) if s[i] == omega]
+    assert len(shear) == 5
+    for want in (x * y, y * z, x * z, 3.0 * x * x - c2, y * y - z * z):
+        assert sum(parallel(r, want) for r in shear) == 1
+    bulk = [M[i] for i in range(QQ) if s[i] == omega_bulk]
+    assert len(bulk) == 1
+    A = np.stack([np.ones(QQ), c2], axis=1)
+    coef, res, *_ = np.linalg.lstsq(A, bulk[0], rcond=None)
+    assert np.max(np.abs(A @ coef - bulk[0])) < 1e-13 and abs(coef[1]) > 0.5
