@@ -12,7 +12,14 @@ Lambda = (1/omega - 1/2)^2 for BGK.  So
     relaxation would show up at 1e-3 or more;
   * at other omega the measured slip must follow the formula.
 (TRT and MRT are left out on purpose: the reference weights the whole source with omega^+ only, so
-its TRT profile is not the textbook one -- characterised in tests/test_oracle_dense_lbm.py.)"""
+its TRT profile is not the textbook one -- characterised in tests/test_oracle_dense_lbm.py.)
+
+And plane COUETTE flow for velocity_bounceback (a11): a wall at rest below, a wall moving with
+(U_x, 0, U_z) above (the reference's velocity_bounceback with its element, link and buffer lists built
+from the mesh files' boundary IDs).  The steady profile is linear, its second derivative vanishes,
+so half-way bounce-back has no slip error at any relaxation rate: u(y_j) = U (j + 1/2) / H to ROUNDING
+for BGK and TRT, D3Q19 and D3Q27, fluid and fluid_incompressible; MRT keeps an O(u^2) density
+stratification from its energy moment (6e-7 here), nothing else."""
 import math
 
 import numpy as np
@@ -34,6 +41,24 @@ def _plane_channel(dirname, L):
     hasb = bid.any(axis=1)
     tio.dump_treelmesh(dirname, first_id(L) + code[order], np.where(hasb, 2 | 8, 2).astype(np.int64), length=1.0,
                        bc_labels=("wall",), boundary_ID=bid[hasb])
+    return tio.load_treelmesh(dirname), ys
+
+
+def _couette_channel(dirname, L):
+    from musubi_b200 import treelm_io as tio
+    from musubi_b200.treelm_multilevel import first_id, morton
+    n = 1 << L
+    g = np.arange(n)
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    code = morton(X.ravel(), Y.ravel(), Z.ravel())
+    order = np.argsort(code)
+    ys = Y.ravel()[order]
+    bid = np.zeros((n ** 3, 26), dtype=np.int64)
+    for s, d in enumerate(tio.Q_OFFSET):
+        bid[:, s] = np.where(ys + d[1] < 0, 1, np.where(ys + d[1] >= n, 2, 0))   # 1 = 'wall', 2 = 'lid'
+    hasb = bid.any(axis=1)
+    tio.dump_treelmesh(dirname, first_id(L) + code[order], np.where(hasb, 2 | 8, 2).astype(np.int64), length=1.0,
+                       bc_labels=("wall", "lid"), boundary_ID=bid[hasb])
     return tio.load_treelmesh(dirname), ys
 
 
@@ -71,3 +96,31 @@ def test_poiseuille_slip_follows_the_half_way_bounce_back_formula(oracle, tmp_pa
     theory = (16.0 * (1.0 / omega - 0.5) ** 2 - 3.0) / (3.0 * H * H)
     assert np.max(np.abs(slip - slip.mean())) < 1e-10              # a UNIFORM shift of the exact parabola
     assert abs(slip.mean() / theory - 1.0) < 0.02                  # 5.29e-3 vs 5.21e-3; -1.455e-2 vs -1.432e-2
+
+
+@pytest.mark.parametrize("relax,QQ,kind,omega,tol", [
+    ("bgk", 19, "fluid", 1.0, 1e-12), ("bgk", 19, "fluid", 1.7, 1e-12), ("trt", 19, "fluid", 1.7, 1e-12),
+    ("bgk", 27, "fluid", 1.3, 1e-12), ("trt", 27, "fluid", 1.3, 1e-12),
+    ("bgk", 19, "fluid_incompressible", 1.2, 1e-12), ("mrt", 19, "fluid_incompressible", 1.2, 1e-12),
+    ("mrt", 19, "fluid", 1.7, 1e-5), ("mrt", 27, "fluid", 1.3, 1e-5)])
+def test_couette_profile_between_a_wall_and_a_velocity_bounceback_lid_is_linear(oracle, tmp_path, relax, QQ, kind,
+                                                                                omega, tol):
+    from musubi_b200 import treelm_io as tio
+    mo, L = oracle, 3
+    H = 1 << L
+    mesh, ys = _couette_channel(str(tmp_path), L)
+    fd = tio.FileLevelDesc(mesh, QQ, bc_kind={"lid": "velocity_bounceback"})
+    sch = mo.Scheme(fd, relax, kind, omega=omega, lambda_=0.2, omega_bulk=1.1)
+    sch.init_equilibrium(1.0, np.zeros(3))
+    U = np.array([0.01, 0.0, 0.004])
+    lids = [bc for bc in fd.bc if bc["kind"] == "velocity_bounceback"]
+    assert len(lids) == 1 and len(lids[0]["elems"]) == H * H
+    sch.bc_vel[lids[0]["id"]] = np.tile(U, (len(lids[0]["links"]), 1))
+    nu = (1.0 / omega - 0.5) / 3.0
+    sch.run(int(36 * H * H / (math.pi ** 2 * nu)))
+    aux = sch.aux.reshape(-1, 4)[:fd.nFluid]
+    y = (np.arange(H) + 0.5) / H
+    for k in (1, 3):
+        prof = np.array([aux[ys == j, k].mean() for j in range(H)])
+        assert np.max(np.abs(prof - U[k - 1] * y)) / U[k - 1] < tol, (k, prof)
+    assert np.max(np.abs(aux[:, 2])) < 1e-14
