@@ -67,7 +67,7 @@ static void bgk_d3q19(int incomp, const double *in, double *out, const double *a
   const int QQ = 19;
   const double div1_3 = 1.0 / 3.0, div1_8 = 1.0 / 8.0, div1_36 = 1.0 / 36.0;
   const double div3_4h = 3.0 / 4.5;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (nSolve >= 20000)
   for (int e = 1; e <= nSolve; ++e) {
     const double fN00 = PULL(qN00), f0N0 = PULL(q0N0), f00N = PULL(q00N);
     const double f100 = PULL(q100), f010 = PULL(q010), f001 = PULL(q001);
@@ -129,7 +129,7 @@ static void trt_d3q19(const double *in, double *out, const double *aux,
   const int QQ = 19;
   const double div1_3 = 1.0 / 3.0, t2cs4inv = 4.5;
   const double t1x2_0 = 1.0 / 18.0 * 2.0, t2x2_0 = 1.0 / 36.0 * 2.0;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (nSolve >= 20000)
   for (int e = 1; e <= nSolve; ++e) {
     const double fN00 = PULL(qN00), f0N0 = PULL(q0N0), f00N = PULL(q00N);
     const double f100 = PULL(q100), f010 = PULL(q010), f001 = PULL(q001);
@@ -180,7 +180,7 @@ static void trt_d3q19_incomp(const double *in, double *out, const double *aux,
   const double div1_3 = 1.0 / 3.0, div1_6 = 1.0 / 6.0, t2cs4inv = 4.5;
   const double t1x2 = 1.0 / 9.0, t2x2 = 1.0 / 18.0;
   const double fac1 = t1x2 * t2cs4inv, fac2 = t2x2 * t2cs4inv;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (nSolve >= 20000)
   for (int e = 1; e <= nSolve; ++e) {
     const double fN00 = PULL(qN00), f0N0 = PULL(q0N0), f00N = PULL(q00N);
     const double f100 = PULL(q100), f010 = PULL(q010), f001 = PULL(q001);
@@ -233,7 +233,7 @@ static void mrt_d3q19(int incomp, const double *in, double *out, const double *a
   double *sc = s0 - 1; /* 1-based */
   sc[2] *= div1_24; sc[3] *= div1_72; sc[5] *= div1_24; sc[7] *= div1_24; sc[9] *= div1_24;
   sc[17] *= div1_8; sc[18] *= div1_8; sc[19] *= div1_8;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (nSolve >= 20000)
   for (int e = 1; e <= nSolve; ++e) {
     double sl[19];
     for (int i = 0; i < 19; ++i) sl[i] = s0[i];
@@ -352,7 +352,7 @@ static void bgk_generic(int QQ, int incomp, const double *in, double *out, const
    * out = f - omega*(f - fEq) with fEq = pdfEq_ptr(rho, vel); for
    * fluid_incompressible the pointer is get_pdfEq_incomp_d3q27
    * (mus_scheme_derived_quantities_type_module.f90:751-811).                  */
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (nSolve >= 20000)
   for (int e = 1; e <= nSolve; ++e) {
     double f[27], fEq[27];
     for (int d = 1; d <= QQ; ++d) f[d - 1] = PULL(d);
@@ -376,7 +376,7 @@ static void trt_d3q27(const double *in, double *out, const double *aux,
     {q101, qN0N}, {q10N, qN01}, {q110, qNN0}, {q1N0, qN10}, {q1NN, qN11},
     {q11N, qNN1}, {q1N1, qN1N}, {q111, qNNN}};
   const int *cx = ora_cxDir(27);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (nSolve >= 20000)
   for (int e = 1; e <= nSolve; ++e) {
     double f[28];
     for (int d = 1; d <= QQ; ++d) f[d] = PULL(d);
@@ -411,7 +411,7 @@ static void mrt_d3q27(int incomp, const double *in, double *out, const double *a
   const int QQ = 27;
   double s0[27];
   ora_mrt_diag(27, 1.0, omegaBulk, s0);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (nSolve >= 20000)
   for (int e = 1; e <= nSolve; ++e) {
     double f[28], mom[28], meq[28], mneq[28], s[28];
     for (int d = 1; d <= QQ; ++d) { f[d] = PULL(d); s[d] = s0[d - 1]; meq[d] = 0.0; }
@@ -490,7 +490,7 @@ static void mrt_noopt(int QQ, int incomp, const double *in, double *out, const d
                       double omegaBulk) {
   /* M^-1 S M (f - fEq); the D3Q27 NoOpt variant (mrt_d3q27:88-185) has the
    * same structure with the weighted matrices.                               */
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (nSolve >= 20000)
   for (int e = 1; e <= nSolve; ++e) {
     double f[27], fEq[27], fneq[27], mneq[27], s[27];
     for (int d = 1; d <= QQ; ++d) f[d - 1] = PULL(d);

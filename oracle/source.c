@@ -178,7 +178,7 @@ int ora_compute_passive_scalar(int variant, int QQ, const double *in, double *ou
   const double *w = ora_weights(QQ);
   const double d_omega = 2.0 / (1.0 + 6.0 * diff_coeff);
   const double aux_omega = 1.0 / (lambda / (1.0 / d_omega - 0.5) + 0.5);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (nSolve >= 20000)
   for (int e = 1; e <= nSolve; ++e) {
     const double *u = transVel + 3 * (size_t)(e - 1);
     double pdf[27], rho = 0.0;

@@ -293,7 +293,7 @@ void ora_first_moment(int QQ, const double *p, double m[3]) {
 
 static void calc_aux(int QQ, int incomp, double *aux, const double *state,
                      const int32_t *neigh, int nSize, int nSolve) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (nSolve >= 20000)
   for (int e = 1; e <= nSolve; ++e) {
     double pdf[28];
     for (int d = 1; d <= QQ; ++d) pdf[d] = state[neigh[(size_t)(d - 1) * nSize + (e - 1)] - 1];
